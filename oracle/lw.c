@@ -1,0 +1,1187 @@
+/*
+ * lw.c -- oracle restatement of RRTMG_LW as linked by MiMA (clear sky, icld=0, idrv=0).
+ * TEST INFRASTRUCTURE ONLY (see rrtmg_oracle.h).
+ *
+ * Follows  LW/src/rrtmg_lw_rad.nomcica.f90:80-569  (rrtmg_lw), :572-901 (inatm)
+ *          LW/src/rrtmg_lw_cldprop.f90:154-162     (clear sky: ncbands=1, taucloud=0)
+ *          LW/src/rrtmg_lw_setcoef.f90:31-415      (setcoef)
+ *          LW/src/rrtmg_lw_taumol.f90:31-3149      (taumol, taugb1..16)
+ *          LW/src/rrtmg_lw_rtrnmr.f90:259-280, 481-777 (rtrnmr, "Clear layer" branch)
+ * One column at a time, loop order and arithmetic order as in the Fortran.  All arrays 1-based
+ * like the Fortran (index 0 unused unless the Fortran array starts at 0).
+ */
+#include "rrtmg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NL (ORC_MAXLAY + 2)
+
+/* Fortran-style accessors (1-based, column-major) */
+#define F2(p, n1, i, j) ((p)[((long)(j) - 1) * (n1) + ((i) - 1)])
+#define F3(p, n1, n2, i, j, k) ((p)[(((long)(k) - 1) * (n2) + ((j) - 1)) * (n1) + ((i) - 1)])
+#define CHI(m, j) (S->chi_mls[((j) - 1) * 7 + ((m) - 1)])
+
+static const int nspa[16] = {1, 1, 9, 9, 9, 1, 9, 1, 9, 1, 1, 9, 9, 1, 9, 9};
+static const int nspb[16] = {1, 1, 5, 5, 5, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0, 0};
+static const int ngs[16] = {10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138, 140};
+static const int ngc[16] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+static const double delwave[16] = {340., 150., 130., 70., 120., 160., 100., 100.,
+                                   210., 90., 320., 280., 170., 130., 220., 650.};
+
+typedef struct {
+    int nlayers, laytrop;
+    double pavel[NL], tavel[NL], pz[NL], tz[NL], tbound, coldry[NL], wbrodl[NL];
+    double wkl[8][NL], wx[5][NL], pwvcm, semiss[17], taua[NL][17];
+    int jp[NL], jt[NL], jt1[NL], indself[NL], indfor[NL], indminor[NL];
+    double planklay[NL][17], planklev[NL][17], plankbnd[17];
+    double colh2o[NL], colco2[NL], colo3[NL], coln2o[NL], colco[NL], colch4[NL], colo2[NL], colbrd[NL];
+    double fac00[NL], fac01[NL], fac10[NL], fac11[NL];
+    double rat_h2oco2[NL], rat_h2oco2_1[NL], rat_h2oo3[NL], rat_h2oo3_1[NL];
+    double rat_h2on2o[NL], rat_h2on2o_1[NL], rat_h2och4[NL], rat_h2och4_1[NL];
+    double rat_n2oco2[NL], rat_n2oco2_1[NL], rat_o3co2[NL], rat_o3co2_1[NL];
+    double selffac[NL], selffrac[NL], forfac[NL], forfrac[NL];
+    double minorfrac[NL], scaleminor[NL], scaleminorn2[NL];
+    double taug[ORC_NGPTLW + 1][NL], fracs[ORC_NGPTLW + 1][NL], taut[ORC_NGPTLW + 1][NL];
+    double totuflux[NL], totdflux[NL], fnet[NL], htr[NL];
+    double totuclfl[NL], totdclfl[NL], fnetc[NL], htrc[NL];
+    double oneminus, fluxfac;
+} lwcol_t;
+
+/* ---------------------------------------------------------------- inatm (rad.nomcica:572-901) */
+static void inatm(lwcol_t *c, int iplon, int ncol, int nlay, int iaer,
+                  const double *play, const double *plev, const double *tlay, const double *tlev,
+                  const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                  const double *ccl4vmr, const double *emis, const double *tauaer)
+{
+    const double amd = 28.9660, amw = 18.0160, amdw = 1.607793, amdo = 0.603428;
+    const double grav = 9.8066, avogad = 6.02214199e+23;
+    const int nmol = 7, maxxsec = 4;
+    static const int ixindx[4] = {1, 2, 3, 4};
+    double amm, amttl, wvttl, wvsh, summol;
+#define IN2(a, l) ((a)[((long)(l) - 1) * ncol + (iplon - 1)])
+
+    c->nlayers = nlay;
+    for (int m = 0; m < 8; ++m)
+        for (int l = 0; l < NL; ++l) c->wkl[m][l] = 0.0;
+    for (int m = 0; m < 5; ++m)
+        for (int l = 0; l < NL; ++l) c->wx[m][l] = 0.0;
+    for (int l = 0; l < NL; ++l)
+        for (int ib = 0; ib < 17; ++ib) c->taua[l][ib] = 0.0;
+    amttl = 0.0;
+    wvttl = 0.0;
+
+    c->tbound = tsfc[iplon - 1];
+    c->pz[0] = IN2(plev, 1);
+    c->tz[0] = IN2(tlev, 1);
+    for (int l = 1; l <= nlay; ++l) {
+        c->pavel[l] = IN2(play, l);
+        c->tavel[l] = IN2(tlay, l);
+        c->pz[l] = IN2(plev, l + 1);
+        c->tz[l] = IN2(tlev, l + 1);
+        /* MiMA: h2o input is specific humidity, o3 is mass mixing ratio (:775-778) */
+        c->wkl[1][l] = (IN2(h2ovmr, l) / (1.0 - IN2(h2ovmr, l))) * amdw;
+        c->wkl[2][l] = IN2(co2vmr, l);
+        c->wkl[3][l] = IN2(o3vmr, l) * amdo;
+        c->wkl[4][l] = IN2(n2ovmr, l);
+        c->wkl[6][l] = IN2(ch4vmr, l);
+        c->wkl[7][l] = IN2(o2vmr, l);
+        amm = (1.0 - c->wkl[1][l]) * amd + c->wkl[1][l] * amw;
+        c->coldry[l] = (c->pz[l - 1] - c->pz[l]) * 1.e3 * avogad /
+                       (1.e2 * grav * amm * (1.0 + c->wkl[1][l]));
+    }
+    for (int l = 1; l <= nlay; ++l) {
+        c->wx[1][l] = IN2(ccl4vmr, l);
+        c->wx[2][l] = IN2(cfc11vmr, l);
+        c->wx[3][l] = IN2(cfc12vmr, l);
+        c->wx[4][l] = IN2(cfc22vmr, l);
+    }
+    for (int l = 1; l <= nlay; ++l) {
+        summol = 0.0;
+        for (int imol = 2; imol <= nmol; ++imol) summol = summol + c->wkl[imol][l];
+        c->wbrodl[l] = c->coldry[l] * (1.0 - summol);
+        for (int imol = 1; imol <= nmol; ++imol) c->wkl[imol][l] = c->coldry[l] * c->wkl[imol][l];
+        amttl = amttl + c->coldry[l] + c->wkl[1][l];
+        wvttl = wvttl + c->wkl[1][l];
+        for (int ix = 1; ix <= maxxsec; ++ix) {
+            if (ixindx[ix - 1] != 0)
+                c->wx[ixindx[ix - 1]][l] = c->coldry[l] * c->wx[ix][l] * 1.e-20;
+        }
+    }
+    wvsh = (amw * wvttl) / (amd * amttl);
+    c->pwvcm = wvsh * (1.e3 * c->pz[0]) / (1.e2 * grav);
+
+    for (int n = 1; n <= 16; ++n) c->semiss[n] = emis[((long)n - 1) * ncol + (iplon - 1)];
+    if (iaer >= 1) {
+        for (int l = 1; l <= nlay; ++l)
+            for (int ib = 1; ib <= 16; ++ib)
+                c->taua[l][ib] = tauaer[(((long)ib - 1) * nlay + (l - 1)) * ncol + (iplon - 1)];
+    }
+#undef IN2
+}
+
+/* ---------------------------------------------------------------- setcoef (setcoef.f90:31-415) */
+static void setcoef(lwcol_t *c, int istart)
+{
+    const orc_state_t *S = &g_orc;
+    const int nlayers = c->nlayers;
+    int indbound, indlev0, indlay, indlev, jp1;
+    double stpfac, tbndfrac, t0frac, tlayfrac, tlevfrac, dbdtlev, dbdtlay;
+    double plog, fp, ft, ft1, water, scalefac, factor, compfp;
+#define TOTPLNK(i, b) F2(S->totplnk, 181, i, b)
+    (void)istart;
+    stpfac = 296. / 1013.;
+
+    indbound = (int)(c->tbound - 159.);
+    if (indbound < 1) indbound = 1;
+    else if (indbound > 180) indbound = 180;
+    tbndfrac = c->tbound - 159. - (double)indbound;
+    indlev0 = (int)(c->tz[0] - 159.);
+    if (indlev0 < 1) indlev0 = 1;
+    else if (indlev0 > 180) indlev0 = 180;
+    t0frac = c->tz[0] - 159. - (double)indlev0;
+    c->laytrop = 0;
+
+    for (int lay = 1; lay <= nlayers; ++lay) {
+        indlay = (int)(c->tavel[lay] - 159.);
+        if (indlay < 1) indlay = 1;
+        else if (indlay > 180) indlay = 180;
+        tlayfrac = c->tavel[lay] - 159. - (double)indlay;
+        indlev = (int)(c->tz[lay] - 159.);
+        if (indlev < 1) indlev = 1;
+        else if (indlev > 180) indlev = 180;
+        tlevfrac = c->tz[lay] - 159. - (double)indlev;
+
+        /* bands 1-15, then band 16 through the istart/=16 branch: identical formulas (:170-249) */
+        for (int iband = 1; iband <= 16; ++iband) {
+            if (lay == 1) {
+                dbdtlev = TOTPLNK(indbound + 1, iband) - TOTPLNK(indbound, iband);
+                c->plankbnd[iband] = c->semiss[iband] * (TOTPLNK(indbound, iband) + tbndfrac * dbdtlev);
+                dbdtlev = TOTPLNK(indlev0 + 1, iband) - TOTPLNK(indlev0, iband);
+                c->planklev[0][iband] = TOTPLNK(indlev0, iband) + t0frac * dbdtlev;
+            }
+            dbdtlev = TOTPLNK(indlev + 1, iband) - TOTPLNK(indlev, iband);
+            dbdtlay = TOTPLNK(indlay + 1, iband) - TOTPLNK(indlay, iband);
+            c->planklay[lay][iband] = TOTPLNK(indlay, iband) + tlayfrac * dbdtlay;
+            c->planklev[lay][iband] = TOTPLNK(indlev, iband) + tlevfrac * dbdtlev;
+        }
+
+        plog = log(c->pavel[lay]);
+        c->jp[lay] = (int)(36. - 5 * (plog + 0.04));
+        if (c->jp[lay] < 1) c->jp[lay] = 1;
+        else if (c->jp[lay] > 58) c->jp[lay] = 58;
+        jp1 = c->jp[lay] + 1;
+        fp = 5. * (S->lw_preflog[c->jp[lay] - 1] - plog);
+
+        c->jt[lay] = (int)(3. + (c->tavel[lay] - S->lw_tref[c->jp[lay] - 1]) / 15.);
+        if (c->jt[lay] < 1) c->jt[lay] = 1;
+        else if (c->jt[lay] > 4) c->jt[lay] = 4;
+        ft = ((c->tavel[lay] - S->lw_tref[c->jp[lay] - 1]) / 15.) - (double)(c->jt[lay] - 3);
+        c->jt1[lay] = (int)(3. + (c->tavel[lay] - S->lw_tref[jp1 - 1]) / 15.);
+        if (c->jt1[lay] < 1) c->jt1[lay] = 1;
+        else if (c->jt1[lay] > 4) c->jt1[lay] = 4;
+        ft1 = ((c->tavel[lay] - S->lw_tref[jp1 - 1]) / 15.) - (double)(c->jt1[lay] - 3);
+        water = c->wkl[1][lay] / c->coldry[lay];
+        scalefac = c->pavel[lay] * stpfac / c->tavel[lay];
+
+        if (!(plog <= 4.56)) {
+            /* below the tropopause (:293-348) */
+            c->laytrop = c->laytrop + 1;
+            c->forfac[lay] = scalefac / (1. + water);
+            factor = (332.0 - c->tavel[lay]) / 36.0;
+            c->indfor[lay] = (int)fmin(2, fmax(1, (int)factor));
+            c->forfrac[lay] = factor - (double)c->indfor[lay];
+            c->selffac[lay] = water * c->forfac[lay];
+            factor = (c->tavel[lay] - 188.0) / 7.2;
+            {
+                int t = (int)factor - 7;
+                c->indself[lay] = t < 1 ? 1 : (t > 9 ? 9 : t);
+            }
+            c->selffrac[lay] = factor - (double)(c->indself[lay] + 7);
+            c->scaleminor[lay] = c->pavel[lay] / c->tavel[lay];
+            c->scaleminorn2[lay] = (c->pavel[lay] / c->tavel[lay]) *
+                                   (c->wbrodl[lay] / (c->coldry[lay] + c->wkl[1][lay]));
+            factor = (c->tavel[lay] - 180.8) / 7.2;
+            {
+                int t = (int)factor;
+                c->indminor[lay] = t < 1 ? 1 : (t > 18 ? 18 : t);
+            }
+            c->minorfrac[lay] = factor - (double)c->indminor[lay];
+            {
+                const int j = c->jp[lay];
+                c->rat_h2oco2[lay] = CHI(1, j) / CHI(2, j);
+                c->rat_h2oco2_1[lay] = CHI(1, j + 1) / CHI(2, j + 1);
+                c->rat_h2oo3[lay] = CHI(1, j) / CHI(3, j);
+                c->rat_h2oo3_1[lay] = CHI(1, j + 1) / CHI(3, j + 1);
+                c->rat_h2on2o[lay] = CHI(1, j) / CHI(4, j);
+                c->rat_h2on2o_1[lay] = CHI(1, j + 1) / CHI(4, j + 1);
+                c->rat_h2och4[lay] = CHI(1, j) / CHI(6, j);
+                c->rat_h2och4_1[lay] = CHI(1, j + 1) / CHI(6, j + 1);
+                c->rat_n2oco2[lay] = CHI(4, j) / CHI(2, j);
+                c->rat_n2oco2_1[lay] = CHI(4, j + 1) / CHI(2, j + 1);
+            }
+        } else {
+            /* above the tropopause (:350-398) */
+            c->forfac[lay] = scalefac / (1. + water);
+            factor = (c->tavel[lay] - 188.0) / 36.0;
+            c->indfor[lay] = 3;
+            c->forfrac[lay] = factor - 1.0;
+            c->selffac[lay] = water * c->forfac[lay];
+            c->scaleminor[lay] = c->pavel[lay] / c->tavel[lay];
+            c->scaleminorn2[lay] = (c->pavel[lay] / c->tavel[lay]) *
+                                   (c->wbrodl[lay] / (c->coldry[lay] + c->wkl[1][lay]));
+            factor = (c->tavel[lay] - 180.8) / 7.2;
+            {
+                int t = (int)factor;
+                c->indminor[lay] = t < 1 ? 1 : (t > 18 ? 18 : t);
+            }
+            c->minorfrac[lay] = factor - (double)c->indminor[lay];
+            {
+                const int j = c->jp[lay];
+                c->rat_h2oco2[lay] = CHI(1, j) / CHI(2, j);
+                c->rat_h2oco2_1[lay] = CHI(1, j + 1) / CHI(2, j + 1);
+                c->rat_o3co2[lay] = CHI(3, j) / CHI(2, j);
+                c->rat_o3co2_1[lay] = CHI(3, j + 1) / CHI(2, j + 1);
+            }
+            /* not assigned by the Fortran above laytrop; defined here so stage dumps are deterministic */
+            c->indself[lay] = 0;
+            c->selffrac[lay] = 0.0;
+        }
+        /* column amounts (:335-348 / :378-391) -- same in both branches */
+        c->colh2o[lay] = 1.e-20 * c->wkl[1][lay];
+        c->colco2[lay] = 1.e-20 * c->wkl[2][lay];
+        c->colo3[lay] = 1.e-20 * c->wkl[3][lay];
+        c->coln2o[lay] = 1.e-20 * c->wkl[4][lay];
+        c->colco[lay] = 1.e-20 * c->wkl[5][lay];
+        c->colch4[lay] = 1.e-20 * c->wkl[6][lay];
+        c->colo2[lay] = 1.e-20 * c->wkl[7][lay];
+        if (c->colco2[lay] == 0.) c->colco2[lay] = 1.e-32 * c->coldry[lay];
+        if (c->colo3[lay] == 0.) c->colo3[lay] = 1.e-32 * c->coldry[lay];
+        if (c->coln2o[lay] == 0.) c->coln2o[lay] = 1.e-32 * c->coldry[lay];
+        if (c->colco[lay] == 0.) c->colco[lay] = 1.e-32 * c->coldry[lay];
+        if (c->colch4[lay] == 0.) c->colch4[lay] = 1.e-32 * c->coldry[lay];
+        c->colbrd[lay] = 1.e-20 * c->wbrodl[lay];
+
+        compfp = 1. - fp;
+        c->fac10[lay] = compfp * ft;
+        c->fac00[lay] = compfp * (1. - ft);
+        c->fac11[lay] = fp * ft1;
+        c->fac01[lay] = fp * (1. - ft1);
+        c->selffac[lay] = c->colh2o[lay] * c->selffac[lay];
+        c->forfac[lay] = c->colh2o[lay] * c->forfac[lay];
+    }
+#undef TOTPLNK
+}
+
+/* ---------------------------------------------------------------- taumol helpers */
+/* The 3-point / 2-point binary-species stencil block that is textually identical in
+ * taugb3,4,5,7,9,12,13,15,16 (template: taumol.f90:548-606 and :622-680). */
+typedef struct { double f0, f1, f2, g0, g1, g2; int mode; } stencil_t;
+
+static stencil_t stencil(double specparm, double fs, double facA, double facB)
+{
+    stencil_t s;
+    double p, p4, fk0, fk1, fk2;
+    if (specparm < 0.125) {
+        p = fs - 1;
+        p4 = (p * p) * (p * p);
+        fk0 = p4;
+        fk1 = 1 - p - 2.0 * p4;
+        fk2 = p + p4;
+        s.f0 = fk0 * facA; s.f1 = fk1 * facA; s.f2 = fk2 * facA;
+        s.g0 = fk0 * facB; s.g1 = fk1 * facB; s.g2 = fk2 * facB;
+        s.mode = 0;
+    } else if (specparm > 0.875) {
+        p = -fs;
+        p4 = (p * p) * (p * p);
+        fk0 = p4;
+        fk1 = 1 - p - 2.0 * p4;
+        fk2 = p + p4;
+        s.f0 = fk0 * facA; s.f1 = fk1 * facA; s.f2 = fk2 * facA;
+        s.g0 = fk0 * facB; s.g1 = fk1 * facB; s.g2 = fk2 * facB;
+        s.mode = 1;
+    } else {
+        s.f0 = (1. - fs) * facA; s.g0 = (1. - fs) * facB;
+        s.f1 = fs * facA;        s.g1 = fs * facB;
+        s.f2 = 0.0; s.g2 = 0.0;
+        s.mode = 2;
+    }
+    return s;
+}
+
+/* tau_major = speccomb * (...), with fac000=f0, fac100=f1, fac200=f2, fac010=g0, fac110=g1, fac210=g2 */
+static double tau_major(const stencil_t *s, double speccomb, const double *absa, int na, int ind, int ig)
+{
+#define ABSA(i) F2(absa, na, i, ig)
+    if (s->mode == 0)
+        return speccomb * (s->f0 * ABSA(ind) + s->f1 * ABSA(ind + 1) + s->f2 * ABSA(ind + 2) +
+                           s->g0 * ABSA(ind + 9) + s->g1 * ABSA(ind + 10) + s->g2 * ABSA(ind + 11));
+    else if (s->mode == 1)
+        return speccomb * (s->f2 * ABSA(ind - 1) + s->f1 * ABSA(ind) + s->f0 * ABSA(ind + 1) +
+                           s->g2 * ABSA(ind + 8) + s->g1 * ABSA(ind + 9) + s->g0 * ABSA(ind + 10));
+    else
+        return speccomb * (s->f0 * ABSA(ind) + s->f1 * ABSA(ind + 1) +
+                           s->g0 * ABSA(ind + 9) + s->g1 * ABSA(ind + 10));
+#undef ABSA
+}
+
+/* eta = colA/(colA + rat*colB) clamped, js = 1+int(mult*eta), fs = mod(mult*eta,1) */
+static void binary(double colA, double rat, double colB, double mult, double oneminus,
+                   double *speccomb, double *specparm, int *js, double *fs)
+{
+    double specmult;
+    *speccomb = colA + rat * colB;
+    *specparm = colA / *speccomb;
+    if (*specparm >= oneminus) *specparm = oneminus;
+    specmult = mult * (*specparm);
+    *js = 1 + (int)specmult;
+    *fs = fmod(specmult, 1.0);
+}
+
+#define SELF(K, lay, inds, ig) (c->selffac[lay] * (F2((K)->selfref, 10, inds, ig) + c->selffrac[lay] * \
+                                (F2((K)->selfref, 10, (inds) + 1, ig) - F2((K)->selfref, 10, inds, ig))))
+#define FORN(K, lay, indf, ig) (c->forfac[lay] * (F2((K)->forref, 4, indf, ig) + c->forfrac[lay] * \
+                                (F2((K)->forref, 4, (indf) + 1, ig) - F2((K)->forref, 4, indf, ig))))
+#define MINOR1(tab, indm, ig) (F2(tab, 19, indm, ig) + c->minorfrac[lay] * \
+                               (F2(tab, 19, (indm) + 1, ig) - F2(tab, 19, indm, ig)))
+/* minor gas with eta dimension: (neta,19,ng) */
+static double minor_eta(const double *tab, int neta, int jm, double fm, int indm, double minorfrac, int ig)
+{
+    double m1 = F3(tab, neta, 19, jm, indm, ig) + fm * (F3(tab, neta, 19, jm + 1, indm, ig) - F3(tab, neta, 19, jm, indm, ig));
+    double m2 = F3(tab, neta, 19, jm, indm + 1, ig) + fm * (F3(tab, neta, 19, jm + 1, indm + 1, ig) - F3(tab, neta, 19, jm, indm + 1, ig));
+    return m1 + minorfrac * (m2 - m1);
+}
+/* 4-point single-species key interpolation */
+#define KEY4(abs_, n_, ind0, ind1, ig) (c->fac00[lay] * F2(abs_, n_, ind0, ig) + c->fac10[lay] * F2(abs_, n_, (ind0) + 1, ig) + \
+                                        c->fac01[lay] * F2(abs_, n_, ind1, ig) + c->fac11[lay] * F2(abs_, n_, (ind1) + 1, ig))
+
+#define IND0A(b) (((c->jp[lay] - 1) * 5 + (c->jt[lay] - 1)) * nspa[(b) - 1])
+#define IND1A(b) ((c->jp[lay] * 5 + (c->jt1[lay] - 1)) * nspa[(b) - 1])
+#define IND0B(b) (((c->jp[lay] - 13) * 5 + (c->jt[lay] - 1)) * nspb[(b) - 1])
+#define IND1B(b) (((c->jp[lay] - 12) * 5 + (c->jt1[lay] - 1)) * nspb[(b) - 1])
+
+/* upper-atmosphere binary band (2-point eta stencil): taumol.f90:681-757 template */
+static double upper_binary(const lwcol_t *c, int lay, const double *absb, int nb, int ind0, int ind1,
+                           double speccomb, double fs, double speccomb1, double fs1, int ig)
+{
+    double fac000 = (1. - fs) * c->fac00[lay], fac010 = (1. - fs) * c->fac10[lay];
+    double fac100 = fs * c->fac00[lay], fac110 = fs * c->fac10[lay];
+    double fac001 = (1. - fs1) * c->fac01[lay], fac011 = (1. - fs1) * c->fac11[lay];
+    double fac101 = fs1 * c->fac01[lay], fac111 = fs1 * c->fac11[lay];
+    return speccomb * (fac000 * F2(absb, nb, ind0, ig) + fac100 * F2(absb, nb, ind0 + 1, ig) +
+                       fac010 * F2(absb, nb, ind0 + 5, ig) + fac110 * F2(absb, nb, ind0 + 6, ig)) +
+           speccomb1 * (fac001 * F2(absb, nb, ind1, ig) + fac101 * F2(absb, nb, ind1 + 1, ig) +
+                        fac011 * F2(absb, nb, ind1 + 5, ig) + fac111 * F2(absb, nb, ind1 + 6, ig));
+}
+
+/* ---------------------------------------------------------------- taumol (taumol.f90:260-3147) */
+static void taumol(lwcol_t *c)
+{
+    const orc_state_t *S = &g_orc;
+    const int nlayers = c->nlayers, laytrop = c->laytrop;
+    const double oneminus = c->oneminus;
+    int lay, ig, ind0, ind1, inds, indf, indm, js, js1, jpl, jm, jm2;
+    double speccomb, specparm, fs, speccomb1, specparm1, fs1, sc, sp, fpl, fm, fm2;
+    double tauself, taufor, corradj, pp, scalen2, adjfac, adjcol, chi, rat, ratx;
+    const orc_lw_kg_t *K;
+
+    /* ---- band 1: 10-350 cm-1 (low key h2o; high key h2o), N2 minor (:280-373) */
+    K = &S->lw[0];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        ind0 = IND0A(1) + 1; ind1 = IND1A(1) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+        pp = c->pavel[lay];
+        corradj = 1.;
+        if (pp < 250.) corradj = 1. - 0.15 * (250. - pp) / 154.4;
+        scalen2 = c->colbrd[lay] * c->scaleminorn2[lay];
+        for (ig = 1; ig <= ngc[0]; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            double taun2 = scalen2 * MINOR1(K->ka_mn2, indm, ig);
+            c->taug[ig][lay] = corradj * (c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor + taun2);
+            c->fracs[ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        ind0 = IND0B(1) + 1; ind1 = IND1B(1) + 1;
+        indf = c->indfor[lay]; indm = c->indminor[lay];
+        pp = c->pavel[lay];
+        corradj = 1. - 0.15 * (pp / 95.6);
+        scalen2 = c->colbrd[lay] * c->scaleminorn2[lay];
+        for (ig = 1; ig <= ngc[0]; ++ig) {
+            taufor = FORN(K, lay, indf, ig);
+            double taun2 = scalen2 * MINOR1(K->kb_mn2, indm, ig);
+            c->taug[ig][lay] = corradj * (c->colh2o[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + taufor + taun2);
+            c->fracs[ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 2: 350-500 (h2o; h2o) (:376-445) */
+    K = &S->lw[1];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        ind0 = IND0A(2) + 1; ind1 = IND1A(2) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay];
+        pp = c->pavel[lay];
+        corradj = 1. - .05 * (pp - 100.) / 900.;
+        for (ig = 1; ig <= ngc[1]; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            c->taug[ngs[0] + ig][lay] = corradj * (c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor);
+            c->fracs[ngs[0] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        ind0 = IND0B(2) + 1; ind1 = IND1B(2) + 1;
+        indf = c->indfor[lay];
+        for (ig = 1; ig <= ngc[1]; ++ig) {
+            taufor = FORN(K, lay, indf, ig);
+            c->taug[ngs[0] + ig][lay] = c->colh2o[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + taufor;
+            c->fracs[ngs[0] + ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 3: 500-630 (h2o,co2; h2o,co2), N2O minor (:448-760) */
+    K = &S->lw[2];
+    {
+        const double refrat_planck_a = CHI(1, 9) / CHI(2, 9);
+        const double refrat_planck_b = CHI(1, 13) / CHI(2, 13);
+        const double refrat_m_a = CHI(1, 3) / CHI(2, 3);
+        const double refrat_m_b = CHI(1, 13) / CHI(2, 13);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oco2[lay], c->colco2[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oco2_1[lay], c->colco2[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            chi = c->coln2o[lay] / c->coldry[lay];
+            rat = 1.e20 * chi / CHI(4, c->jp[lay] + 1);
+            if (rat > 1.5) {
+                adjfac = 0.5 + pow(rat - 0.5, 0.65);
+                adjcol = adjfac * CHI(4, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->coln2o[lay];
+            }
+            binary(c->colh2o[lay], refrat_planck_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(3) + js; ind1 = IND1A(3) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= ngc[2]; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double absn2o = minor_eta(K->ka_mn2o, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[1] + ig][lay] = tm + tm1 + tauself + taufor + adjcol * absn2o;
+                c->fracs[ngs[1] + ig][lay] = F2(K->fracrefa, 16, ig, jpl) + fpl * (F2(K->fracrefa, 16, ig, jpl + 1) - F2(K->fracrefa, 16, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oco2[lay], c->colco2[lay], 4., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oco2_1[lay], c->colco2[lay], 4., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_b, c->colco2[lay], 4., oneminus, &sc, &sp, &jm, &fm);
+            chi = c->coln2o[lay] / c->coldry[lay];
+            rat = 1.e20 * chi / CHI(4, c->jp[lay] + 1);
+            if (rat > 1.5) {
+                adjfac = 0.5 + pow(rat - 0.5, 0.65);
+                adjcol = adjfac * CHI(4, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->coln2o[lay];
+            }
+            binary(c->colh2o[lay], refrat_planck_b, c->colco2[lay], 4., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0B(3) + js; ind1 = IND1B(3) + js1;
+            indf = c->indfor[lay]; indm = c->indminor[lay];
+            for (ig = 1; ig <= ngc[2]; ++ig) {
+                taufor = FORN(K, lay, indf, ig);
+                double absn2o = minor_eta(K->kb_mn2o, 5, jm, fm, indm, c->minorfrac[lay], ig);
+                c->taug[ngs[1] + ig][lay] = upper_binary(c, lay, K->absb, 1175, ind0, ind1, speccomb, fs, speccomb1, fs1, ig)
+                                            + taufor + adjcol * absn2o;
+                c->fracs[ngs[1] + ig][lay] = F2(K->fracrefb, 16, ig, jpl) + fpl * (F2(K->fracrefb, 16, ig, jpl + 1) - F2(K->fracrefb, 16, ig, jpl));
+            }
+        }
+    }
+
+    /* ---- band 4: 630-700 (h2o,co2; o3,co2) (:763-1019) */
+    K = &S->lw[3];
+    {
+        const double refrat_planck_a = CHI(1, 11) / CHI(2, 11);
+        const double refrat_planck_b = CHI(3, 13) / CHI(2, 13);
+        const int n4 = 14;
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oco2[lay], c->colco2[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oco2_1[lay], c->colco2[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_planck_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(4) + js; ind1 = IND1A(4) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= n4; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[2] + ig][lay] = tm + tm1 + tauself + taufor;
+                c->fracs[ngs[2] + ig][lay] = F2(K->fracrefa, n4, ig, jpl) + fpl * (F2(K->fracrefa, n4, ig, jpl + 1) - F2(K->fracrefa, n4, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            binary(c->colo3[lay], c->rat_o3co2[lay], c->colco2[lay], 4., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colo3[lay], c->rat_o3co2_1[lay], c->colco2[lay], 4., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colo3[lay], refrat_planck_b, c->colco2[lay], 4., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0B(4) + js; ind1 = IND1B(4) + js1;
+            for (ig = 1; ig <= n4; ++ig) {
+                c->taug[ngs[2] + ig][lay] = upper_binary(c, lay, K->absb, 1175, ind0, ind1, speccomb, fs, speccomb1, fs1, ig);
+                c->fracs[ngs[2] + ig][lay] = F2(K->fracrefb, n4, ig, jpl) + fpl * (F2(K->fracrefb, n4, ig, jpl + 1) - F2(K->fracrefb, n4, ig, jpl));
+            }
+            /* empirical stratospheric CO2 correction (:1009-1015) */
+            c->taug[ngs[2] + 8][lay] = c->taug[ngs[2] + 8][lay] * 0.92;
+            c->taug[ngs[2] + 9][lay] = c->taug[ngs[2] + 9][lay] * 0.88;
+            c->taug[ngs[2] + 10][lay] = c->taug[ngs[2] + 10][lay] * 1.07;
+            c->taug[ngs[2] + 11][lay] = c->taug[ngs[2] + 11][lay] * 1.1;
+            c->taug[ngs[2] + 12][lay] = c->taug[ngs[2] + 12][lay] * 0.99;
+            c->taug[ngs[2] + 13][lay] = c->taug[ngs[2] + 13][lay] * 0.88;
+            c->taug[ngs[2] + 14][lay] = c->taug[ngs[2] + 14][lay] * 0.943;
+        }
+    }
+
+    /* ---- band 5: 700-820 (h2o,co2; o3,co2), O3 minor, CCl4 (:1022-1294) */
+    K = &S->lw[4];
+    {
+        const double refrat_planck_a = CHI(1, 5) / CHI(2, 5);
+        const double refrat_planck_b = CHI(3, 43) / CHI(2, 43);
+        const double refrat_m_a = CHI(1, 7) / CHI(2, 7);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oco2[lay], c->colco2[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oco2_1[lay], c->colco2[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            binary(c->colh2o[lay], refrat_planck_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(5) + js; ind1 = IND1A(5) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 16; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double abso3 = minor_eta(K->ka_mo3, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[3] + ig][lay] = tm + tm1 + tauself + taufor + abso3 * c->colo3[lay] + c->wx[1][lay] * K->ccl4[ig - 1];
+                c->fracs[ngs[3] + ig][lay] = F2(K->fracrefa, 16, ig, jpl) + fpl * (F2(K->fracrefa, 16, ig, jpl + 1) - F2(K->fracrefa, 16, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            binary(c->colo3[lay], c->rat_o3co2[lay], c->colco2[lay], 4., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colo3[lay], c->rat_o3co2_1[lay], c->colco2[lay], 4., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colo3[lay], refrat_planck_b, c->colco2[lay], 4., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0B(5) + js; ind1 = IND1B(5) + js1;
+            for (ig = 1; ig <= 16; ++ig) {
+                c->taug[ngs[3] + ig][lay] = upper_binary(c, lay, K->absb, 1175, ind0, ind1, speccomb, fs, speccomb1, fs1, ig)
+                                            + c->wx[1][lay] * K->ccl4[ig - 1];
+                c->fracs[ngs[3] + ig][lay] = F2(K->fracrefb, 16, ig, jpl) + fpl * (F2(K->fracrefb, 16, ig, jpl + 1) - F2(K->fracrefb, 16, ig, jpl));
+            }
+        }
+    }
+
+    /* ---- band 6: 820-980 (h2o; nothing), CO2 minor, CFC11, CFC12 (:1297-1380) */
+    K = &S->lw[5];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        chi = c->colco2[lay] / (c->coldry[lay]);
+        rat = 1.e20 * chi / CHI(2, c->jp[lay] + 1);
+        if (rat > 3.0) {
+            adjfac = 2.0 + pow(rat - 2.0, 0.77);
+            adjcol = adjfac * CHI(2, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+        } else {
+            adjcol = c->colco2[lay];
+        }
+        ind0 = IND0A(6) + 1; ind1 = IND1A(6) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+        for (ig = 1; ig <= 8; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            double absco2 = MINOR1(K->ka_mco2, indm, ig);
+            c->taug[ngs[4] + ig][lay] = c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor
+                                        + adjcol * absco2 + c->wx[2][lay] * K->cfc11adj[ig - 1] + c->wx[3][lay] * K->cfc12[ig - 1];
+            c->fracs[ngs[4] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        for (ig = 1; ig <= 8; ++ig) {
+            c->taug[ngs[4] + ig][lay] = 0.0 + c->wx[2][lay] * K->cfc11adj[ig - 1] + c->wx[3][lay] * K->cfc12[ig - 1];
+            c->fracs[ngs[4] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+
+    /* ---- band 7: 980-1080 (h2o,o3; o3), CO2 minor (:1383-1654) */
+    K = &S->lw[6];
+    {
+        const double refrat_planck_a = CHI(1, 3) / CHI(3, 3);
+        const double refrat_m_a = CHI(1, 3) / CHI(3, 3);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oo3[lay], c->colo3[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oo3_1[lay], c->colo3[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_a, c->colo3[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            chi = c->colco2[lay] / (c->coldry[lay]);
+            rat = 1.e20 * chi / CHI(2, c->jp[lay] + 1);
+            if (rat > 3.0) {
+                adjfac = 3.0 + pow(rat - 3.0, 0.79);
+                adjcol = adjfac * CHI(2, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->colco2[lay];
+            }
+            binary(c->colh2o[lay], refrat_planck_a, c->colo3[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(7) + js; ind1 = IND1A(7) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 12; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double absco2 = minor_eta(K->ka_mco2, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[5] + ig][lay] = tm + tm1 + tauself + taufor + adjcol * absco2;
+                c->fracs[ngs[5] + ig][lay] = F2(K->fracrefa, 12, ig, jpl) + fpl * (F2(K->fracrefa, 12, ig, jpl + 1) - F2(K->fracrefa, 12, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            chi = c->colco2[lay] / (c->coldry[lay]);
+            rat = 1.e20 * chi / CHI(2, c->jp[lay] + 1);
+            if (rat > 3.0) {
+                adjfac = 2.0 + pow(rat - 2.0, 0.79);
+                adjcol = adjfac * CHI(2, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->colco2[lay];
+            }
+            ind0 = IND0B(7) + 1; ind1 = IND1B(7) + 1;
+            indm = c->indminor[lay];
+            for (ig = 1; ig <= 12; ++ig) {
+                double absco2 = MINOR1(K->kb_mco2, indm, ig);
+                c->taug[ngs[5] + ig][lay] = c->colo3[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + adjcol * absco2;
+                c->fracs[ngs[5] + ig][lay] = K->fracrefb[ig - 1];
+            }
+            /* empirical stratospheric CO2 correction (:1645-1650) */
+            c->taug[ngs[5] + 6][lay] = c->taug[ngs[5] + 6][lay] * 0.92;
+            c->taug[ngs[5] + 7][lay] = c->taug[ngs[5] + 7][lay] * 0.88;
+            c->taug[ngs[5] + 8][lay] = c->taug[ngs[5] + 8][lay] * 1.07;
+            c->taug[ngs[5] + 9][lay] = c->taug[ngs[5] + 9][lay] * 1.1;
+            c->taug[ngs[5] + 10][lay] = c->taug[ngs[5] + 10][lay] * 0.99;
+            c->taug[ngs[5] + 11][lay] = c->taug[ngs[5] + 11][lay] * 0.855;
+        }
+    }
+
+    /* ---- band 8: 1080-1180 (h2o; o3), CO2/O3/N2O minor, CFC12, CFC22 (:1657-1777) */
+    K = &S->lw[7];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        chi = c->colco2[lay] / (c->coldry[lay]);
+        rat = 1.e20 * chi / CHI(2, c->jp[lay] + 1);
+        if (rat > 3.0) {
+            adjfac = 2.0 + pow(rat - 2.0, 0.65);
+            adjcol = adjfac * CHI(2, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+        } else {
+            adjcol = c->colco2[lay];
+        }
+        ind0 = IND0A(8) + 1; ind1 = IND1A(8) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+        for (ig = 1; ig <= 8; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            double absco2 = MINOR1(K->ka_mco2, indm, ig);
+            double abso3 = MINOR1(K->ka_mo3, indm, ig);
+            double absn2o = MINOR1(K->ka_mn2o, indm, ig);
+            c->taug[ngs[6] + ig][lay] = c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor
+                                        + adjcol * absco2 + c->colo3[lay] * abso3 + c->coln2o[lay] * absn2o
+                                        + c->wx[3][lay] * K->cfc12[ig - 1] + c->wx[4][lay] * K->cfc22adj[ig - 1];
+            c->fracs[ngs[6] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        chi = c->colco2[lay] / c->coldry[lay];
+        rat = 1.e20 * chi / CHI(2, c->jp[lay] + 1);
+        if (rat > 3.0) {
+            adjfac = 2.0 + pow(rat - 2.0, 0.65);
+            adjcol = adjfac * CHI(2, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+        } else {
+            adjcol = c->colco2[lay];
+        }
+        ind0 = IND0B(8) + 1; ind1 = IND1B(8) + 1;
+        indm = c->indminor[lay];
+        for (ig = 1; ig <= 8; ++ig) {
+            double absco2 = MINOR1(K->kb_mco2, indm, ig);
+            double absn2o = MINOR1(K->kb_mn2o, indm, ig);
+            c->taug[ngs[6] + ig][lay] = c->colo3[lay] * KEY4(K->absb, 235, ind0, ind1, ig)
+                                        + adjcol * absco2 + c->coln2o[lay] * absn2o
+                                        + c->wx[3][lay] * K->cfc12[ig - 1] + c->wx[4][lay] * K->cfc22adj[ig - 1];
+            c->fracs[ngs[6] + ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 9: 1180-1390 (h2o,ch4; ch4), N2O minor (:1780-2040) */
+    K = &S->lw[8];
+    {
+        const double refrat_planck_a = CHI(1, 9) / CHI(6, 9);
+        const double refrat_m_a = CHI(1, 3) / CHI(6, 3);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2och4[lay], c->colch4[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2och4_1[lay], c->colch4[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_a, c->colch4[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            chi = c->coln2o[lay] / (c->coldry[lay]);
+            rat = 1.e20 * chi / CHI(4, c->jp[lay] + 1);
+            if (rat > 1.5) {
+                adjfac = 0.5 + pow(rat - 0.5, 0.65);
+                adjcol = adjfac * CHI(4, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->coln2o[lay];
+            }
+            binary(c->colh2o[lay], refrat_planck_a, c->colch4[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(9) + js; ind1 = IND1A(9) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 12; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double absn2o = minor_eta(K->ka_mn2o, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[7] + ig][lay] = tm + tm1 + tauself + taufor + adjcol * absn2o;
+                c->fracs[ngs[7] + ig][lay] = F2(K->fracrefa, 12, ig, jpl) + fpl * (F2(K->fracrefa, 12, ig, jpl + 1) - F2(K->fracrefa, 12, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            chi = c->coln2o[lay] / (c->coldry[lay]);
+            rat = 1.e20 * chi / CHI(4, c->jp[lay] + 1);
+            if (rat > 1.5) {
+                adjfac = 0.5 + pow(rat - 0.5, 0.65);
+                adjcol = adjfac * CHI(4, c->jp[lay] + 1) * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->coln2o[lay];
+            }
+            ind0 = IND0B(9) + 1; ind1 = IND1B(9) + 1;
+            indm = c->indminor[lay];
+            for (ig = 1; ig <= 12; ++ig) {
+                double absn2o = MINOR1(K->kb_mn2o, indm, ig);
+                c->taug[ngs[7] + ig][lay] = c->colch4[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + adjcol * absn2o;
+                c->fracs[ngs[7] + ig][lay] = K->fracrefb[ig - 1];
+            }
+        }
+    }
+
+    /* ---- band 10: 1390-1480 (h2o; h2o) (:2043-2107) */
+    K = &S->lw[9];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        ind0 = IND0A(10) + 1; ind1 = IND1A(10) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay];
+        for (ig = 1; ig <= 6; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            c->taug[ngs[8] + ig][lay] = c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor;
+            c->fracs[ngs[8] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        ind0 = IND0B(10) + 1; ind1 = IND1B(10) + 1;
+        indf = c->indfor[lay];
+        for (ig = 1; ig <= 6; ++ig) {
+            taufor = FORN(K, lay, indf, ig);
+            c->taug[ngs[8] + ig][lay] = c->colh2o[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + taufor;
+            c->fracs[ngs[8] + ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 11: 1480-1800 (h2o; h2o), O2 minor (:2110-2187) */
+    K = &S->lw[10];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        ind0 = IND0A(11) + 1; ind1 = IND1A(11) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+        double scaleo2 = c->colo2[lay] * c->scaleminor[lay];
+        for (ig = 1; ig <= 8; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            double tauo2 = scaleo2 * MINOR1(K->ka_mo2, indm, ig);
+            c->taug[ngs[9] + ig][lay] = c->colh2o[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor + tauo2;
+            c->fracs[ngs[9] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        ind0 = IND0B(11) + 1; ind1 = IND1B(11) + 1;
+        indf = c->indfor[lay]; indm = c->indminor[lay];
+        double scaleo2 = c->colo2[lay] * c->scaleminor[lay];
+        for (ig = 1; ig <= 8; ++ig) {
+            taufor = FORN(K, lay, indf, ig);
+            double tauo2 = scaleo2 * MINOR1(K->kb_mo2, indm, ig);
+            c->taug[ngs[9] + ig][lay] = c->colh2o[lay] * KEY4(K->absb, 235, ind0, ind1, ig) + taufor + tauo2;
+            c->fracs[ngs[9] + ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 12: 1800-2080 (h2o,co2; nothing) (:2190-2392) */
+    K = &S->lw[11];
+    {
+        const double refrat_planck_a = CHI(1, 10) / CHI(2, 10);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2oco2[lay], c->colco2[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2oco2_1[lay], c->colco2[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_planck_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(12) + js; ind1 = IND1A(12) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 8; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[10] + ig][lay] = tm + tm1 + tauself + taufor;
+                c->fracs[ngs[10] + ig][lay] = F2(K->fracrefa, 8, ig, jpl) + fpl * (F2(K->fracrefa, 8, ig, jpl + 1) - F2(K->fracrefa, 8, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay)
+            for (ig = 1; ig <= 8; ++ig) {
+                c->taug[ngs[10] + ig][lay] = 0.0;
+                c->fracs[ngs[10] + ig][lay] = 0.0;
+            }
+    }
+
+    /* ---- band 13: 2080-2250 (h2o,n2o; nothing), CO2+CO minor low, O3 minor high (:2395-2652) */
+    K = &S->lw[12];
+    {
+        const double refrat_planck_a = CHI(1, 5) / CHI(4, 5);
+        const double refrat_m_a = CHI(1, 1) / CHI(4, 1);
+        const double refrat_m_a3 = CHI(1, 3) / CHI(4, 3);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2on2o[lay], c->coln2o[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2on2o_1[lay], c->coln2o[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_m_a, c->coln2o[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            chi = c->colco2[lay] / (c->coldry[lay]);
+            ratx = 1.e20 * chi / 3.55e-4;
+            if (ratx > 3.0) {
+                adjfac = 2.0 + pow(ratx - 2.0, 0.68);
+                adjcol = adjfac * 3.55e-4 * c->coldry[lay] * 1.e-20;
+            } else {
+                adjcol = c->colco2[lay];
+            }
+            binary(c->colh2o[lay], refrat_m_a3, c->coln2o[lay], 8., oneminus, &sc, &sp, &jm2, &fm2);
+            binary(c->colh2o[lay], refrat_planck_a, c->coln2o[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(13) + js; ind1 = IND1A(13) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 4; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double absco2 = minor_eta(K->ka_mco2, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double absco = minor_eta(K->ka_mco, 9, jm2, fm2, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[11] + ig][lay] = tm + tm1 + tauself + taufor + adjcol * absco2 + c->colco[lay] * absco;
+                c->fracs[ngs[11] + ig][lay] = F2(K->fracrefa, 4, ig, jpl) + fpl * (F2(K->fracrefa, 4, ig, jpl + 1) - F2(K->fracrefa, 4, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            indm = c->indminor[lay];
+            for (ig = 1; ig <= 4; ++ig) {
+                double abso3 = MINOR1(K->kb_mo3, indm, ig);
+                c->taug[ngs[11] + ig][lay] = c->colo3[lay] * abso3;
+                c->fracs[ngs[11] + ig][lay] = K->fracrefb[ig - 1];
+            }
+        }
+    }
+
+    /* ---- band 14: 2250-2380 (co2; co2) (:2655-2713) */
+    K = &S->lw[13];
+    for (lay = 1; lay <= laytrop; ++lay) {
+        ind0 = IND0A(14) + 1; ind1 = IND1A(14) + 1;
+        inds = c->indself[lay]; indf = c->indfor[lay];
+        for (ig = 1; ig <= 2; ++ig) {
+            tauself = SELF(K, lay, inds, ig);
+            taufor = FORN(K, lay, indf, ig);
+            c->taug[ngs[12] + ig][lay] = c->colco2[lay] * KEY4(K->absa, 65, ind0, ind1, ig) + tauself + taufor;
+            c->fracs[ngs[12] + ig][lay] = K->fracrefa[ig - 1];
+        }
+    }
+    for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+        ind0 = IND0B(14) + 1; ind1 = IND1B(14) + 1;
+        for (ig = 1; ig <= 2; ++ig) {
+            c->taug[ngs[12] + ig][lay] = c->colco2[lay] * KEY4(K->absb, 235, ind0, ind1, ig);
+            c->fracs[ngs[12] + ig][lay] = K->fracrefb[ig - 1];
+        }
+    }
+
+    /* ---- band 15: 2380-2600 (n2o,co2; nothing), N2 minor (:2716-2938) */
+    K = &S->lw[14];
+    {
+        const double refrat_planck_a = CHI(4, 1) / CHI(2, 1);
+        const double refrat_m_a = CHI(4, 1) / CHI(2, 1);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->coln2o[lay], c->rat_n2oco2[lay], c->colco2[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->coln2o[lay], c->rat_n2oco2_1[lay], c->colco2[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->coln2o[lay], refrat_m_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jm, &fm);
+            binary(c->coln2o[lay], refrat_planck_a, c->colco2[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(15) + js; ind1 = IND1A(15) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay]; indm = c->indminor[lay];
+            scalen2 = c->colbrd[lay] * c->scaleminor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 2; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double taun2 = scalen2 * minor_eta(K->ka_mn2, 9, jm, fm, indm, c->minorfrac[lay], ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[13] + ig][lay] = tm + tm1 + tauself + taufor + taun2;
+                c->fracs[ngs[13] + ig][lay] = F2(K->fracrefa, 2, ig, jpl) + fpl * (F2(K->fracrefa, 2, ig, jpl + 1) - F2(K->fracrefa, 2, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay)
+            for (ig = 1; ig <= 2; ++ig) {
+                c->taug[ngs[13] + ig][lay] = 0.0;
+                c->fracs[ngs[13] + ig][lay] = 0.0;
+            }
+    }
+
+    /* ---- band 16: 2600-3250 (h2o,ch4; ch4) (:2941-3147) */
+    K = &S->lw[15];
+    {
+        const double refrat_planck_a = CHI(1, 6) / CHI(6, 6);
+        for (lay = 1; lay <= laytrop; ++lay) {
+            binary(c->colh2o[lay], c->rat_h2och4[lay], c->colch4[lay], 8., oneminus, &speccomb, &specparm, &js, &fs);
+            binary(c->colh2o[lay], c->rat_h2och4_1[lay], c->colch4[lay], 8., oneminus, &speccomb1, &specparm1, &js1, &fs1);
+            binary(c->colh2o[lay], refrat_planck_a, c->colch4[lay], 8., oneminus, &sc, &sp, &jpl, &fpl);
+            ind0 = IND0A(16) + js; ind1 = IND1A(16) + js1;
+            inds = c->indself[lay]; indf = c->indfor[lay];
+            stencil_t s0 = stencil(specparm, fs, c->fac00[lay], c->fac10[lay]);
+            stencil_t s1 = stencil(specparm1, fs1, c->fac01[lay], c->fac11[lay]);
+            for (ig = 1; ig <= 2; ++ig) {
+                tauself = SELF(K, lay, inds, ig);
+                taufor = FORN(K, lay, indf, ig);
+                double tm = tau_major(&s0, speccomb, K->absa, 585, ind0, ig);
+                double tm1 = tau_major(&s1, speccomb1, K->absa, 585, ind1, ig);
+                c->taug[ngs[14] + ig][lay] = tm + tm1 + tauself + taufor;
+                c->fracs[ngs[14] + ig][lay] = F2(K->fracrefa, 2, ig, jpl) + fpl * (F2(K->fracrefa, 2, ig, jpl + 1) - F2(K->fracrefa, 2, ig, jpl));
+            }
+        }
+        for (lay = laytrop + 1; lay <= nlayers; ++lay) {
+            ind0 = IND0B(16) + 1; ind1 = IND1B(16) + 1;
+            for (ig = 1; ig <= 2; ++ig) {
+                c->taug[ngs[14] + ig][lay] = c->colch4[lay] * KEY4(K->absb, 235, ind0, ind1, ig);
+                c->fracs[ngs[14] + ig][lay] = K->fracrefb[ig - 1];
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- rtrnmr, clear branch (rtrnmr.f90) */
+static void rtrnmr_clear(lwcol_t *c)
+{
+    const orc_state_t *S = &g_orc;
+    const int nlayers = c->nlayers;
+    const double tblint = 10000.0, bpade = S->lw_bpade;
+    const double wtdiff = 0.5, rec_6 = 0.166667;
+    static const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
+    static const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    static const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    double secdiff[17], atrans[NL], bbugas[NL], urad[NL], drad[NL], clrurad[NL], clrdrad[NL];
+    double uflux, dflux, uclfl, dclfl;
+    int igc, itr, lev, iband, ibnd, l;
+
+    /* :259-280 */
+    for (ibnd = 1; ibnd <= 16; ++ibnd) {
+        if (ibnd == 1 || ibnd == 4 || ibnd >= 10) {
+            secdiff[ibnd] = 1.66;
+        } else {
+            secdiff[ibnd] = a0[ibnd - 1] + a1[ibnd - 1] * exp(a2[ibnd - 1] * c->pwvcm);
+            if (secdiff[ibnd] > 1.80) secdiff[ibnd] = 1.80;
+            if (secdiff[ibnd] < 1.50) secdiff[ibnd] = 1.50;
+        }
+    }
+    for (lev = 0; lev <= nlayers; ++lev) {
+        urad[lev] = 0.0; drad[lev] = 0.0; clrurad[lev] = 0.0; clrdrad[lev] = 0.0;
+        c->totuflux[lev] = 0.0; c->totdflux[lev] = 0.0; c->totuclfl[lev] = 0.0; c->totdclfl[lev] = 0.0;
+    }
+    igc = 1;
+    for (iband = 1; iband <= 16; ++iband) {
+        do { /* g-point loop: "1000 continue ... if (igc .le. ngs(iband)) go to 1000" */
+            double radld = 0., radclrd = 0., radlu, radclru, rad0, reflect;
+            /* downward loop (:505-618), clear-layer branch :589-607 and iclddn=0 branch :614-616 */
+            for (lev = nlayers; lev >= 1; --lev) {
+                double plfrac = c->fracs[igc][lev];
+                double blay = c->planklay[lev][iband];
+                double dplankup = c->planklev[lev][iband] - blay;
+                double dplankdn = c->planklev[lev - 1][iband] - blay;
+                double odepth = secdiff[iband] * c->taut[igc][lev];
+                double bbd;
+                if (odepth < 0.0) odepth = 0.0;
+                if (odepth <= 0.06) {
+                    atrans[lev] = odepth - 0.5 * odepth * odepth;
+                    odepth = rec_6 * odepth;
+                    bbd = plfrac * (blay + dplankdn * odepth);
+                    bbugas[lev] = plfrac * (blay + dplankup * odepth);
+                } else {
+                    double tblind = odepth / (bpade + odepth);
+                    itr = (int)(tblint * tblind + 0.5);
+                    double transc = S->exp_tbl[itr];
+                    atrans[lev] = 1. - transc;
+                    double tausfac = S->tfn_tbl[itr];
+                    bbd = plfrac * (blay + tausfac * dplankdn);
+                    bbugas[lev] = plfrac * (blay + tausfac * dplankup);
+                }
+                radld = radld + (bbd - radld) * atrans[lev];
+                drad[lev - 1] = drad[lev - 1] + radld;
+                radclrd = radld;
+                clrdrad[lev - 1] = drad[lev - 1];
+            }
+            /* surface (:628-636) */
+            rad0 = c->fracs[igc][1] * c->plankbnd[iband];
+            reflect = 1. - c->semiss[iband];
+            radlu = rad0 + reflect * radld;
+            radclru = rad0 + reflect * radclrd;
+            urad[0] = urad[0] + radlu;
+            clrurad[0] = clrurad[0] + radclru;
+            /* upward loop (:649-711), clear-layer branch :682-701 */
+            for (lev = 1; lev <= nlayers; ++lev) {
+                radlu = radlu + (bbugas[lev] - radlu) * atrans[lev];
+                urad[lev] = urad[lev] + radlu;
+                radclru = radlu;
+                clrurad[lev] = urad[lev];
+            }
+            igc = igc + 1;
+        } while (igc <= ngs[iband - 1]);
+
+        /* band totals (:720-733) */
+        for (lev = nlayers; lev >= 0; --lev) {
+            uflux = urad[lev] * wtdiff;
+            dflux = drad[lev] * wtdiff;
+            urad[lev] = 0.0;
+            drad[lev] = 0.0;
+            c->totuflux[lev] = c->totuflux[lev] + uflux * delwave[iband - 1];
+            c->totdflux[lev] = c->totdflux[lev] + dflux * delwave[iband - 1];
+            uclfl = clrurad[lev] * wtdiff;
+            dclfl = clrdrad[lev] * wtdiff;
+            clrurad[lev] = 0.0;
+            clrdrad[lev] = 0.0;
+            c->totuclfl[lev] = c->totuclfl[lev] + uclfl * delwave[iband - 1];
+            c->totdclfl[lev] = c->totdclfl[lev] + dclfl * delwave[iband - 1];
+        }
+    }
+    /* fluxes and heating rates (:751-777) */
+    c->totuflux[0] = c->totuflux[0] * c->fluxfac;
+    c->totdflux[0] = c->totdflux[0] * c->fluxfac;
+    c->fnet[0] = c->totuflux[0] - c->totdflux[0];
+    c->totuclfl[0] = c->totuclfl[0] * c->fluxfac;
+    c->totdclfl[0] = c->totdclfl[0] * c->fluxfac;
+    c->fnetc[0] = c->totuclfl[0] - c->totdclfl[0];
+    for (lev = 1; lev <= nlayers; ++lev) {
+        c->totuflux[lev] = c->totuflux[lev] * c->fluxfac;
+        c->totdflux[lev] = c->totdflux[lev] * c->fluxfac;
+        c->fnet[lev] = c->totuflux[lev] - c->totdflux[lev];
+        c->totuclfl[lev] = c->totuclfl[lev] * c->fluxfac;
+        c->totdclfl[lev] = c->totdclfl[lev] * c->fluxfac;
+        c->fnetc[lev] = c->totuclfl[lev] - c->totdclfl[lev];
+        l = lev - 1;
+        c->htr[l] = S->lw_heatfac * (c->fnet[l] - c->fnet[lev]) / (c->pz[l] - c->pz[lev]);
+        c->htrc[l] = S->lw_heatfac * (c->fnetc[l] - c->fnetc[lev]) / (c->pz[l] - c->pz[lev]);
+    }
+    c->htr[nlayers] = 0.0;
+    c->htrc[nlayers] = 0.0;
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------- rrtmg_lw (rad.nomcica:80-569) */
+int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
+                 const double *play, const double *plev, const double *tlay, const double *tlev,
+                 const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                 const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                 const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                 const double *ccl4vmr, const double *emis, const double *tauaer,
+                 double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                 const orc_lw_stages_t *st, int nthreads)
+{
+    if (!g_orc.ready) return 1;
+    if (icld != 0 || idrv != 0) return 2; /* cloudy / derivative branches are not restated */
+    if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
+    if (nthreads < 1) nthreads = 1;
+    const int iaer = 10; /* forced (:442) */
+    const int istart = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        lwcol_t *c = (lwcol_t *)malloc(sizeof(lwcol_t));
+        /* :419-421 */
+        c->oneminus = 1. - 1.e-6;
+        {
+            double pi = 2. * asin(1.);
+            c->fluxfac = pi * 2.e4;
+        }
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int iplon = 1; iplon <= ncol; ++iplon) {
+            inatm(c, iplon, ncol, nlay, iaer, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr,
+                  n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer);
+            /* cldprop with cldfrac=0: ncbands=1, taucloud=0 -- nothing to compute */
+            setcoef(c, istart);
+            taumol(c);
+            /* :514-519, iaer=10 */
+            for (int k = 1; k <= nlay; ++k)
+                for (int ig = 1; ig <= ORC_NGPTLW; ++ig) {
+                    int b = 0;
+                    while (ig > ngs[b]) ++b; /* ngb(ig) */
+                    c->taut[ig][k] = c->taug[ig][k] + c->taua[k][b + 1];
+                }
+            rtrnmr_clear(c);
+            const long i0 = iplon - 1;
+            for (int k = 0; k <= nlay; ++k) {
+                uflx[(long)k * ncol + i0] = c->totuflux[k];
+                dflx[(long)k * ncol + i0] = c->totdflux[k];
+                uflxc[(long)k * ncol + i0] = c->totuclfl[k];
+                dflxc[(long)k * ncol + i0] = c->totdclfl[k];
+            }
+            for (int k = 0; k <= nlay - 1; ++k) {
+                hr[(long)k * ncol + i0] = c->htr[k];
+                hrc[(long)k * ncol + i0] = c->htrc[k];
+            }
+            if (st) {
+#define PUT(dst, src) if (st->dst) for (int l = 1; l <= nlay; ++l) st->dst[(long)(l - 1) * ncol + i0] = c->src[l]
+                if (st->laytrop) st->laytrop[i0] = c->laytrop;
+                if (st->pwvcm) st->pwvcm[i0] = c->pwvcm;
+                PUT(jp, jp); PUT(jt, jt); PUT(jt1, jt1); PUT(indself, indself); PUT(indfor, indfor); PUT(indminor, indminor);
+                PUT(fac00, fac00); PUT(fac01, fac01); PUT(fac10, fac10); PUT(fac11, fac11);
+                PUT(colh2o, colh2o); PUT(colco2, colco2); PUT(colo3, colo3); PUT(coln2o, coln2o);
+                PUT(colco, colco); PUT(colch4, colch4); PUT(colo2, colo2); PUT(colbrd, colbrd);
+                PUT(selffac, selffac); PUT(selffrac, selffrac); PUT(forfac, forfac); PUT(forfrac, forfrac);
+                PUT(minorfrac, minorfrac); PUT(scaleminor, scaleminor); PUT(scaleminorn2, scaleminorn2);
+                PUT(coldry, coldry);
+#undef PUT
+                for (int ib = 1; ib <= 16; ++ib) {
+                    if (st->plankbnd) st->plankbnd[(long)(ib - 1) * ncol + i0] = c->plankbnd[ib];
+                    if (st->planklay)
+                        for (int l = 1; l <= nlay; ++l)
+                            st->planklay[((long)(ib - 1) * nlay + (l - 1)) * ncol + i0] = c->planklay[l][ib];
+                    if (st->planklev)
+                        for (int l = 0; l <= nlay; ++l)
+                            st->planklev[((long)(ib - 1) * (nlay + 1) + l) * ncol + i0] = c->planklev[l][ib];
+                }
+                for (int ig = 1; ig <= ORC_NGPTLW; ++ig)
+                    for (int l = 1; l <= nlay; ++l) {
+                        if (st->taug) st->taug[((long)(ig - 1) * nlay + (l - 1)) * ncol + i0] = c->taug[ig][l];
+                        if (st->fracs) st->fracs[((long)(ig - 1) * nlay + (l - 1)) * ncol + i0] = c->fracs[ig][l];
+                    }
+            }
+        }
+        free(c);
+    }
+    return 0;
+}

@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""Build the coefficient blobs the oracle and the CUDA library load at init.
+
+Run in the authoring container (needs /root/reference); the outputs are committed because the
+GPU box has no copy of the reference:
+
+  mima_b200/data/rrtmg_sw_kg.bin        SW k-distribution data, 16 g-points per band, parsed from
+                                        SW/src/rrtmg_sw_k_g.f90 (subroutines sw_kgb16..29), plus the
+                                        reference atmosphere of SW/src/rrtmg_sw_setcoef.f90:289-343.
+  mima_b200/data/rrtmg_lw_ref.bin       LW data that IS present in the reference: pref/preflog/tref,
+                                        chi_mls (LW/src/rrtmg_lw_setcoef.f90:418-576) and the Planck
+                                        tables totplnk/totplk16 (+derivatives) (:586-1990).
+  mima_b200/data/rrtmg_lw_kg_synth.bin  LW k-distribution data with the exact shapes declared in
+                                        LW/modules/rrlw_kg01..16.f90 but SYNTHETIC values: the real
+                                        file LW/src/rrtmg_lw_k_g.f90 is stripped from the reference
+                                        checkout (.MISSING_LARGE_BLOBS).  Smooth, positive, seeded.
+
+Blob format (little endian): 8-byte magic "RRTMGTB1", uint32 n, then n records
+{char name[32]; uint32 ndim; uint32 dims[4]; uint64 offset_in_doubles}, then the doubles.
+Every array is stored in Fortran (column-major) element order with the dimensions the Fortran
+module declares, g-point dimension still 16 wide ("o" = original arrays).  The 16 -> ngc reduction
+(cmbgbNN) is done at init by the consumer, not here.
+"""
+import os
+import re
+import struct
+import sys
+
+import numpy as np
+
+REF = os.environ.get("MIMA_REFERENCE", "/root/reference")
+RR = os.path.join(REF, "src/atmos_param/rrtm_radiation")
+LW = os.path.join(RR, "rrtmg_lw/gcm_model")
+SW = os.path.join(RR, "rrtmg_sw/gcm_model")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mima_b200", "data")
+
+MAGIC = b"RRTMGTB1"
+
+
+def write_blob(path, arrays):
+    """arrays: dict name -> np.ndarray (any order); stored column-major."""
+    names = list(arrays)
+    recs = []
+    off = 0
+    payload = []
+    for n in names:
+        a = np.asarray(arrays[n], dtype=np.float64)
+        dims = list(a.shape) + [1] * (4 - a.ndim)
+        assert a.ndim <= 4 and len(n) < 32, n
+        recs.append(struct.pack("<32sI4IQ", n.encode(), a.ndim, *dims, off))
+        flat = np.asfortranarray(a).ravel(order="F")
+        payload.append(flat.tobytes())
+        off += flat.size
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<I", len(names)))
+        for r in recs:
+            f.write(r)
+        for p in payload:
+            f.write(p)
+    print(f"wrote {path}: {len(names)} arrays, {off} doubles, {os.path.getsize(path)} bytes")
+
+
+def read_blob(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    assert raw[:8] == MAGIC
+    (n,) = struct.unpack_from("<I", raw, 8)
+    pos = 12
+    recs = []
+    for _ in range(n):
+        name, ndim, d0, d1, d2, d3, off = struct.unpack_from("<32sI4IQ", raw, pos)
+        pos += struct.calcsize("<32sI4IQ")
+        recs.append((name.rstrip(b"\0").decode(), ndim, (d0, d1, d2, d3)[:ndim], off))
+    data = np.frombuffer(raw, dtype="<f8", offset=pos)
+    out = {}
+    for name, ndim, dims, off in recs:
+        cnt = int(np.prod(dims))
+        out[name] = data[off:off + cnt].reshape(dims, order="F")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Minimal Fortran reader: module array declarations and "name(slice) = (/ ... /)" assignments.
+# ----------------------------------------------------------------------------------------------
+
+def strip_comment(line):
+    i = line.find("!")
+    return line if i < 0 else line[:i]
+
+
+def parse_decls(path, params):
+    """Return {name: (shape tuple, lower-bounds tuple)} for real arrays declared in a module."""
+    txt = [strip_comment(l) for l in open(path)]
+    # join continuation lines
+    joined = []
+    cur = ""
+    for l in txt:
+        s = l.rstrip()
+        if not s.strip():
+            continue
+        if cur:
+            s2 = s.strip()
+            if s2.startswith("&"):
+                s2 = s2[1:]
+            cur += s2
+        else:
+            cur = s
+        if cur.rstrip().endswith("&"):
+            cur = cur.rstrip()[:-1]
+            continue
+        joined.append(cur)
+        cur = ""
+    for l in joined:
+        m = re.match(r"\s*integer\(kind=im\)\s*,\s*parameter\s*::\s*(\w+)\s*=\s*(\d+)", l)
+        if m:
+            params[m.group(1)] = int(m.group(2))
+    decls = {}
+
+    def dimlist(s):
+        shape, lows = [], []
+        for d in s.split(","):
+            d = d.strip()
+            if ":" in d:
+                lo, hi = d.split(":")
+                lo, hi = int(params.get(lo.strip(), lo)), int(params.get(hi.strip(), hi))
+            else:
+                lo, hi = 1, int(params.get(d, d))
+            shape.append(hi - lo + 1)
+            lows.append(lo)
+        return tuple(shape), tuple(lows)
+
+    for l in joined:
+        m = re.match(r"\s*real\(kind=rb\)\s*,\s*dimension\(([^)]*)\)\s*::\s*(.*)", l)
+        if m:
+            sh = dimlist(m.group(1))
+            for n in m.group(2).split(","):
+                decls[n.strip()] = sh
+            continue
+        m = re.match(r"\s*real\(kind=rb\)\s*::\s*(.*)", l)
+        if m:
+            for n, d in re.findall(r"(\w+)\s*\(([^)]*)\)", m.group(1)):
+                decls[n] = dimlist(d)
+            # scalars
+            rest = re.sub(r"\w+\s*\([^)]*\)", "", m.group(1))
+            for n in rest.split(","):
+                if n.strip():
+                    decls[n.strip()] = ((), ())
+    return decls
+
+
+NUM = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eEdD][-+]?\d+)?")
+
+
+def parse_numbers(s):
+    s = s.replace("_rb", "")
+    vals = []
+    for tok in NUM.findall(s):
+        vals.append(float(tok.replace("d", "e").replace("D", "e")))
+    return vals
+
+
+def parse_assignments(lines, decls):
+    """Execute 'name(slice) = (/ ... /)' and 'name = scalar' statements on numpy arrays."""
+    arrays = {}
+    for n, (shape, lows) in decls.items():
+        arrays[n] = np.full(shape, np.nan, order="F") if shape else np.nan
+    i = 0
+    nl = len(lines)
+    while i < nl:
+        l = strip_comment(lines[i]).rstrip()
+        m = re.match(r"\s*(\w+)\s*(\(([^)]*)\))?\s*=\s*(.*)$", l)
+        if not m or m.group(1) not in decls:
+            i += 1
+            continue
+        name, sl, rhs = m.group(1), m.group(3), m.group(4)
+        # gather continuation
+        stmt = rhs
+        while stmt.rstrip().endswith("&"):
+            i += 1
+            nxt = strip_comment(lines[i]).strip()
+            if not nxt:                      # comment line inside a continued statement
+                continue
+            if nxt.startswith("&"):
+                nxt = nxt[1:]
+            stmt = stmt.rstrip()[:-1] + " " + nxt
+        i += 1
+        shape, lows = decls[name]
+        if "(/" in stmt:
+            body = stmt[stmt.index("(/") + 2: stmt.rindex("/)")]
+            vals = parse_numbers(body)
+        else:
+            vals = parse_numbers(stmt)
+            if not vals:
+                continue
+        if not shape:
+            arrays[name] = vals[0]
+            continue
+        idx = []
+        for k, d in enumerate(sl.split(",")):
+            d = d.strip()
+            if d == ":":
+                idx.append(slice(None))
+            elif ":" in d:
+                lo, hi = d.split(":")
+                idx.append(slice(int(lo) - lows[k], int(hi) - lows[k] + 1))
+            else:
+                idx.append(int(d) - lows[k])
+        tgt = arrays[name][tuple(idx)]
+        v = np.array(vals, dtype=np.float64)
+        assert tgt.size == v.size, (name, sl, tgt.shape, v.size)
+        arrays[name][tuple(idx)] = v.reshape(tgt.shape, order="F")
+    return arrays
+
+
+def split_subroutines(path, pat):
+    out = {}
+    cur = None
+    for l in open(path):
+        m = re.match(r"\s*subroutine\s+" + pat, l)
+        if m:
+            cur = m.group(1)
+            out[cur] = []
+            continue
+        if re.match(r"\s*end subroutine", l):
+            cur = None
+            continue
+        if cur is not None:
+            out[cur].append(l)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+def build_sw():
+    params = {}
+    for l in open(os.path.join(SW, "modules/parrrsw.f90")):
+        m = re.match(r"\s*integer\(kind=im\)\s*,\s*parameter\s*::\s*(\w+)\s*=\s*(\d+)", strip_comment(l))
+        if m:
+            params[m.group(1)] = int(m.group(2))
+    subs = split_subroutines(os.path.join(SW, "src/rrtmg_sw_k_g.f90"), r"sw_kgb(\d+)")
+    out = {}
+    for b in range(16, 30):
+        decls = parse_decls(os.path.join(SW, f"modules/rrsw_kg{b}.f90"), dict(params))
+        # original (16-g) arrays end in 'o'; scalar rayl is shared
+        want = {n: d for n, d in decls.items()
+                if (n.endswith("o") and d[0] and d[0][-1] == 16) or (n.endswith("o") and d[0] and d[0][0] == 16)
+                or (n == "rayl" and not d[0])}
+        arrs = parse_assignments(subs[str(b)], want)
+        for n, a in arrs.items():
+            if isinstance(a, float):
+                assert not np.isnan(a), (b, n)
+                out[f"sw{b}.{n}"] = np.array([a])
+            else:
+                assert not np.isnan(a).any(), (b, n, int(np.isnan(a).sum()))
+                out[f"sw{b}.{n}"] = a
+    # reference atmosphere (SW copy)
+    subs = split_subroutines(os.path.join(SW, "src/rrtmg_sw_setcoef.f90"), r"(swatmref)")
+    decls = {"pref": ((59,), (1,)), "preflog": ((59,), (1,)), "tref": ((59,), (1,))}
+    arrs = parse_assignments(subs["swatmref"], decls)
+    for n, a in arrs.items():
+        assert not np.isnan(a).any()
+        out[f"swref.{n}"] = a
+    return out
+
+
+def build_lw_ref():
+    out = {}
+    subs = split_subroutines(os.path.join(LW, "src/rrtmg_lw_setcoef.f90"),
+                             r"(lwatmref|lwavplank|lwavplankderiv)\b")
+    decls = {"pref": ((59,), (1,)), "preflog": ((59,), (1,)), "tref": ((59,), (1,)),
+             "chi_mls": ((7, 59), (1, 1))}
+    arrs = parse_assignments(subs["lwatmref"], decls)
+    for n, a in arrs.items():
+        assert not np.isnan(a).any(), n
+        out[f"lwref.{n}"] = a
+    decls = {"totplnk": ((181, 16), (1, 1)), "totplk16": ((181,), (1,))}
+    arrs = parse_assignments(subs["lwavplank"], decls)
+    for n, a in arrs.items():
+        assert not np.isnan(a).any(), n
+        out[f"lwref.{n}"] = a
+    decls = {"totplnkderiv": ((181, 16), (1, 1)), "totplk16deriv": ((181,), (1,))}
+    arrs = parse_assignments(subs["lwavplankderiv"], decls)
+    for n, a in arrs.items():
+        assert not np.isnan(a).any(), n
+        out[f"lwref.{n}"] = a
+    return out
+
+
+def build_lw_synth(seed=20240917):
+    """Synthetic LW k-distribution with the declared shapes (rrlw_kgNN.f90).
+
+    Design: absorption rises ~5 decades across the 16 g-points (as real k-distributions do), varies
+    smoothly with the binary-species index, temperature index and reference pressure level, and is
+    perturbed by 5 % seeded log-normal noise so that no two table rows are proportional.  Planck
+    fractions are positive and sum to one over the 16 g-points for every eta column.
+    """
+    rng = np.random.default_rng(seed)
+    params = {}
+    for l in open(os.path.join(LW, "modules/parrrtm.f90")):
+        m = re.match(r"\s*integer\(kind=im\)\s*,\s*parameter\s*::\s*(\w+)\s*=\s*(\d+)", strip_comment(l))
+        if m:
+            params[m.group(1)] = int(m.group(2))
+    out = {}
+    g = np.arange(16)
+    gshape = 10.0 ** (-4.0 + 5.2 * (g / 15.0) ** 1.5)          # 1e-4 .. ~16
+    # per-band strength of the key species (arbitrary but fixed)
+    kscale = {1: 3.0, 2: 1.0, 3: 0.6, 4: 2.0, 5: 0.8, 6: 0.02, 7: 0.3, 8: 0.05, 9: 0.4, 10: 1.5,
+              11: 2.5, 12: 0.2, 13: 0.05, 14: 5.0, 15: 0.5, 16: 0.1}
+    for b in range(1, 17):
+        decls = parse_decls(os.path.join(LW, f"modules/rrlw_kg{b:02d}.f90"), dict(params))
+        for n, (shape, lows) in decls.items():
+            original = n.startswith(("kao", "kbo")) or n in (
+                "selfrefo", "forrefo", "fracrefao", "fracrefbo", "ccl4o", "cfc11adjo", "cfc12o", "cfc22adjo")
+            if not original or not shape:
+                continue
+            assert 16 in (shape[-1], shape[0]), (b, n, shape)
+            if n in ("fracrefao", "fracrefbo"):
+                # g first: (16) or (16, neta)
+                neta = shape[1] if len(shape) == 2 else 1
+                base = np.exp(-0.5 * ((g[:, None] - (5.0 + 0.6 * np.arange(neta)[None, :] + 0.3 * b)) / 4.5) ** 2)
+                base = base * (1.0 + 0.05 * rng.standard_normal(base.shape)).clip(0.5)
+                base /= base.sum(axis=0, keepdims=True)
+                a = base.reshape(shape, order="F")
+            elif n in ("kao", "kbo"):
+                # (neta?, 5, npress, 16)
+                a = np.empty(shape, order="F")
+                npress = shape[-2]
+                plev = np.arange(npress) + (0 if n == "kao" else 12)
+                pfac = np.exp(-0.045 * plev)                       # weaker lines aloft
+                tfac = 1.0 + 0.12 * (np.arange(5) - 2)              # temperature dependence
+                core = tfac[:, None, None] * pfac[None, :, None] * gshape[None, None, :]
+                if len(shape) == 4:
+                    neta = shape[0]
+                    eta = np.linspace(0.0, 1.0, neta)
+                    efac = 0.35 + 0.65 * eta ** 0.7 + 0.25 * (1 - eta) ** 2
+                    core = efac[:, None, None, None] * core[None]
+                a[...] = 8.0 * kscale[b] * core * np.exp(0.05 * rng.standard_normal(shape))
+            elif n == "selfrefo":
+                tf = np.exp(-0.06 * np.arange(10))
+                a = (2.0e-2 * kscale[b] * tf[:, None] * gshape[None, :] ** 0.8
+                     * np.exp(0.05 * rng.standard_normal(shape)))
+            elif n == "forrefo":
+                tf = 1.0 + 0.1 * np.arange(shape[0])
+                a = (2.0e-4 * kscale[b] * tf[:, None] * gshape[None, :] ** 0.6
+                     * np.exp(0.05 * rng.standard_normal(shape)))
+            elif n.startswith("kao_m") or n.startswith("kbo_m"):
+                # minor species: (19,16) or (neta,19,16)
+                tf = 1.0 + 0.03 * np.arange(19)
+                core = tf[:, None] * gshape[None, :] ** 0.9
+                if len(shape) == 3:
+                    eta = np.linspace(0.0, 1.0, shape[0])
+                    core = (0.5 + eta ** 1.3)[:, None, None] * core[None]
+                minor_scale = {"mn2": 2e-7, "mn2o": 3.0, "mo3": 0.5, "mco2": 5e-3, "mco": 2.0, "mo2": 2e-7}
+                key = n.split("_")[1]
+                a = minor_scale[key] * core * np.exp(0.05 * rng.standard_normal(shape))
+            else:
+                # halocarbon cross sections (ccl4o, cfc11adjo, cfc12o, cfc22adjo): (16,)
+                a = 40.0 * (1.0 + 0.4 * np.sin(0.7 * g + b)) * np.exp(0.05 * rng.standard_normal(shape))
+            assert a.shape == shape and (a > 0).all(), (b, n)
+            out[f"lw{b:02d}.{n}"] = np.asfortranarray(a)
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sw = build_sw()
+    write_blob(os.path.join(OUT, "rrtmg_sw_kg.bin"), sw)
+    lwref = build_lw_ref()
+    write_blob(os.path.join(OUT, "rrtmg_lw_ref.bin"), lwref)
+    lw = build_lw_synth()
+    write_blob(os.path.join(OUT, "rrtmg_lw_kg_synth.bin"), lw)
+    # round-trip check
+    for fn, src in (("rrtmg_sw_kg.bin", sw), ("rrtmg_lw_ref.bin", lwref), ("rrtmg_lw_kg_synth.bin", lw)):
+        back = read_blob(os.path.join(OUT, fn))
+        for n, a in src.items():
+            assert np.array_equal(np.asarray(a).reshape(back[n].shape, order="F"), back[n]), n
+    print("round-trip ok")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
