@@ -1,0 +1,172 @@
+/*
+ * rrtmg_b200.h -- C ABI of the B200-native RRTMG LW+SW radiation path (librrtmg_b200.so).
+ *
+ * Drop-in boundary: these entry points are what a Fortran ISO_C_BINDING shim for MiMA binds in place
+ * of the four module procedures `run_rrtmg`/`physics_driver_init` call today (the reference has no C
+ * ABI; see INTEGRATION.md for the shim):
+ *
+ *   rrtmg_b200_lw_init  <- subroutine rrtmg_lw_ini(cpdair)   LW/src/rrtmg_lw_init.f90:28
+ *   rrtmg_b200_sw_init  <- subroutine rrtmg_sw_ini(cpdair)   SW/src/rrtmg_sw_init.f90:28
+ *   rrtmg_b200_lw       <- subroutine rrtmg_lw(...)          LW/src/rrtmg_lw_rad.nomcica.f90:80-89
+ *                          called at src/atmos_param/rrtm_radiation/rrtm_radiation.f90:722-748
+ *   rrtmg_b200_sw       <- subroutine rrtmg_sw(...)          SW/src/rrtmg_sw_rad.nomcica.f90:78-88
+ *                          called at src/atmos_param/rrtm_radiation/rrtm_radiation.f90:686-712
+ *   (LW/ = src/atmos_param/rrtm_radiation/rrtmg_lw/gcm_model/, SW/ = .../rrtmg_sw/gcm_model/)
+ *
+ * Conventions (identical to the Fortran interface):
+ *   - every array is contiguous, column-major, FP64; leading dimension = ncol unless stated;
+ *     level index 1 = surface; pressures hPa, temperatures K;
+ *   - h2ovmr is SPECIFIC HUMIDITY, o3vmr is MASS MIXING RATIO, all other gases volume mixing ratio
+ *     (MiMA-specific, LW rad.nomcica:775-778 / SW rad.nomcica:1004-1007);
+ *   - argument order and meaning are those of the Fortran dummy lists; scalars are passed by value
+ *     except icld (intent(inout): clamped to 2 when outside 0..3, LW rad.nomcica:437).
+ *   - outputs are fully overwritten for every column (night columns in SW get zeros).
+ *
+ * Extensions relative to the Fortran interface (all optional):
+ *   - an input array pointer that is NULL means "all zeros" for: ch4vmr, n2ovmr, o2vmr, cfc11vmr,
+ *     cfc12vmr, cfc22vmr, ccl4vmr, tauaer; emis == NULL means emissivity 1 in all bands.
+ *     (MiMA passes compile-time zeros/ones for these, rrtm_radiation.f90:700-712,737-748; the shim
+ *     can skip the PCIe transfer.)
+ *   - cloud and SW aerosol arrays are never dereferenced when icld == 0 / iaer == 0 (as in the
+ *     reference) and may be NULL or of any extent.
+ *   - *_device variants take device pointers plus a cudaStream_t and run asynchronously.
+ *
+ * Error behaviour: every function returns 0 on success or one of RRTMG_B200_ERR_*; nothing is ever
+ * computed on the CPU and there is no fallback path.  The Fortran `stop 'PARTIAL CLOUD NOT ALLOWED'`
+ * (SW rad.nomcica:537) and the unrestated branches (icld > 0, idrv = 1, SW iaer != 0) map to error codes.
+ */
+#ifndef RRTMG_B200_H
+#define RRTMG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTMG_B200_OK 0
+#define RRTMG_B200_ERR_NOT_INITIALIZED 1 /* init not called (cf. FATAL at rrtm_radiation.f90:527-528) */
+#define RRTMG_B200_ERR_UNSUPPORTED 2     /* icld > 0, idrv = 1, SW iaer != 0: branch not built yet */
+#define RRTMG_B200_ERR_PARTIAL_CLOUD 3   /* SW rad.nomcica:537 */
+#define RRTMG_B200_ERR_BAD_ARGUMENT 4
+#define RRTMG_B200_ERR_CUDA 5            /* see rrtmg_b200_last_error() */
+#define RRTMG_B200_ERR_TABLES 6          /* a coefficient array is missing or has the wrong shape */
+
+#define RRTMG_B200_NBNDLW 16
+#define RRTMG_B200_NGPTLW 140
+#define RRTMG_B200_NBNDSW 14
+#define RRTMG_B200_NGPTSW 112
+
+/* Select the GPU for this process: cudaSetDevice(local_rank % device_count).  One MiMA MPI rank (one
+ * block of latitude rows, src/atmos_spectral/tools/spec_mpp.f90:42-44) drives one GPU. */
+int rrtmg_b200_set_device(int local_rank);
+
+/* Coefficient ingestion.  Arrays are registered by name with the dimensions the Fortran modules declare
+ * (16 g-points per band, before the cmbgbNN reduction), e.g. "lw03.kao" (9,5,13,16), "sw24.raylao"
+ * (16,9), "lwref.totplnk" (181,16), "lwref.chi_mls" (7,59).  load_tables registers every array of a
+ * blob written by tools/build_tables.py; set_table registers one array from host memory (what the
+ * Fortran shim does with the rrlw_kgNN / rrsw_kgNN module arrays after the stock *_ini has run). */
+int rrtmg_b200_load_tables(const char *blob_path);
+int rrtmg_b200_set_table(const char *name, const double *data, int ndim, const int *dims);
+
+/* rrtmg_lw_ini / rrtmg_sw_ini: constants, lookup tables, 16 -> ngc g-point reduction, upload. */
+int rrtmg_b200_lw_init(double cpdair);
+int rrtmg_b200_sw_init(double cpdair);
+int rrtmg_b200_finalize(void);
+
+/* Export a reduced table as the device sees it, in the Fortran (column-major) order of the reduced
+ * module array, e.g. "lw03.absa" (585,16).  Returns the element count, or -1. (test hook) */
+long rrtmg_b200_get_table(const char *name, double *out, long capacity);
+
+const char *rrtmg_b200_last_error(void);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+long rrtmg_b200_launch_count(void);
+
+/* ---- rrtmg_lw ------------------------------------------------------------------------------
+ * play,tlay,h2ovmr..ccl4vmr,cldfr,cicewp,cliqwp,reice,reliq (ncol,nlay); plev,tlev (ncol,nlay+1);
+ * tsfc (ncol); emis (ncol,16); taucld (16,ncol,nlay); tauaer (ncol,nlay,16);
+ * uflx,dflx,uflxc,dflxc (ncol,nlay+1) W/m2; hr,hrc (ncol,nlay) K/day;
+ * duflx_dt,duflxc_dt (ncol,nlay+1) only written when idrv == 1 (unsupported -> error). */
+int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
+                  const double *play, const double *plev, const double *tlay, const double *tlev,
+                  const double *tsfc,
+                  const double *h2ovmr, const double *o3vmr, const double *co2vmr, const double *ch4vmr,
+                  const double *n2ovmr, const double *o2vmr,
+                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                  const double *ccl4vmr, const double *emis,
+                  int inflglw, int iceflglw, int liqflglw, const double *cldfr,
+                  const double *taucld, const double *cicewp, const double *cliqwp,
+                  const double *reice, const double *reliq,
+                  const double *tauaer,
+                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                  double *duflx_dt, double *duflxc_dt);
+
+/* Same arguments, device pointers, asynchronous on `stream` (a cudaStream_t; NULL = default stream). */
+int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
+                         const double *play, const double *plev, const double *tlay, const double *tlev,
+                         const double *tsfc,
+                         const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                         const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                         const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                         const double *ccl4vmr, const double *emis,
+                         int inflglw, int iceflglw, int liqflglw, const double *cldfr,
+                         const double *taucld, const double *cicewp, const double *cliqwp,
+                         const double *reice, const double *reliq,
+                         const double *tauaer,
+                         double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                         double *duflx_dt, double *duflxc_dt, void *stream);
+
+/* ---- rrtmg_sw ------------------------------------------------------------------------------
+ * asdir,asdif,aldir,aldif,coszen (ncol); adjes, scon scalars; dyofyr day of year (0 = use adjes);
+ * taucld,ssacld,asmcld,fsfcld (14,ncol,nlay); tauaer,ssaaer,asmaer (ncol,nlay,14); ecaer (ncol,nlay,6);
+ * swuflx,swdflx,swuflxc,swdflxc (ncol,nlay+1) W/m2; swhr,swhrc (ncol,nlay) K/day. */
+int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
+                  const double *play, const double *plev, const double *tlay, const double *tlev,
+                  const double *tsfc,
+                  const double *h2ovmr, const double *o3vmr, const double *co2vmr, const double *ch4vmr,
+                  const double *n2ovmr, const double *o2vmr,
+                  const double *asdir, const double *asdif, const double *aldir, const double *aldif,
+                  const double *coszen, double adjes, int dyofyr, double scon,
+                  int inflgsw, int iceflgsw, int liqflgsw, const double *cldfr,
+                  const double *taucld, const double *ssacld, const double *asmcld, const double *fsfcld,
+                  const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
+                  const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
+                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
+                  double *swhrc);
+
+int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
+                         const double *play, const double *plev, const double *tlay, const double *tlev,
+                         const double *tsfc,
+                         const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                         const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                         const double *asdir, const double *asdif, const double *aldir, const double *aldif,
+                         const double *coszen, double adjes, int dyofyr, double scon,
+                         int inflgsw, int iceflgsw, int liqflgsw, const double *cldfr,
+                         const double *taucld, const double *ssacld, const double *asmcld,
+                         const double *fsfcld,
+                         const double *cicewp, const double *cliqwp, const double *reice,
+                         const double *reliq,
+                         const double *tauaer, const double *ssaaer, const double *asmaer,
+                         const double *ecaer,
+                         double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
+                         double *swhrc, void *stream);
+
+/* ---- stage dumps (test hooks; device-side intermediates of the most recent *_device / host call,
+ *      valid only when the call fitted one column chunk -- see rrtmg_b200_set_chunk) -------------
+ * which: "lw.taug","lw.fracs" (ncol,nlay,140); "sw.taug","sw.taur" (ncol,nlay,112); "sw.sfluxzen"
+ * (ncol,112); "lw.jp","lw.jt",... packed indices unpacked to double (ncol,nlay); "lw.fac00",... ;
+ * "lw.planklay" (ncol,nlay,16), "lw.planklev" (ncol,nlay+1,16), "lw.plankbnd" (ncol,16),
+ * "lw.laytrop","sw.laytrop" (ncol).  Output is column-major with ncol leading, FP64. */
+long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
+
+/* Columns per device pass (0 = automatic).  The working set of one pass is
+ * ~ chunk * nlay * 2.6 KB (LW) so that the taumol -> solver staging fields stay L2-resident. */
+int rrtmg_b200_set_chunk(int ncol_per_pass);
+
+/* Generic options: "chunk" (as above), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
+ * LW solver otherwise overwrites in place; test hook). */
+int rrtmg_b200_set_option(const char *key, long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

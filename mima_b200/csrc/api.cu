@@ -1,0 +1,918 @@
+// api.cu -- host side of librrtmg_b200.so: coefficient registry, rrtmg_*_ini (g-point reduction, lookup
+// tables, device table packing), workspace management, column chunking and the extern "C" ABI declared
+// in include/rrtmg_b200.h.  No compute happens on the host; if CUDA is unavailable every entry point
+// fails with RRTMG_B200_ERR_CUDA.
+//
+// Reference for the init path: LW/src/rrtmg_lw_init.f90:28-175 (+ :178-281 lwdatinit, :284-363 lwcmbdat,
+// :366-2659 cmbgb1..16), SW/src/rrtmg_sw_init.f90:28-154 (+ :157-241, :244-367, :473-1516).
+#include "../../include/rrtmg_b200.h"
+#include "rrtmg_dev.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace rrtmg;
+
+namespace {
+
+struct HostArr {
+    std::vector<int> dims;
+    std::vector<double> data;   // column-major
+    long size() const { long n = 1; for (int d : dims) n *= d; return n; }
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct State {
+    std::mutex mu;
+    std::map<std::string, HostArr> reg;          // registered original (16-g) arrays
+    std::map<std::string, HostArr> reduced;      // reduced arrays in Fortran order (test hook)
+    std::string err;
+    long launches = 0;
+    int chunk = 0;
+    bool capture = false;
+    // LW
+    bool lw_ready = false;
+    LwConst lwc;
+    LwTables lwt{};
+    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_stage_in, lw_stage_out, lw_cap;
+    LwWork lw_last{};
+    int lw_last_ncol = 0;
+    // SW
+    bool sw_ready = false;
+    SwConst swc;
+    SwTables swt{};
+    DevBuf sw_tab, sw_exptbl, sw_work, sw_stage_in, sw_stage_out;
+    SwWork sw_last{};
+    int sw_last_ncol = 0;
+};
+State G;
+
+int fail(int code, const std::string &msg)
+{
+    G.err = msg;
+    return code;
+}
+#define CUDA_OK(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(RRTMG_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// g-point reduction.  Each band's 16 original g-points are merged into ngc groups of consecutive
+// points (group sizes ngn); absorption-like quantities are averaged with the Gaussian weights wt
+// normalised inside the group, Planck fractions and the solar source are summed.
+// ------------------------------------------------------------------------------------------------
+const double kWt[16] = {0.1527534276, 0.1491729617, 0.1420961469, 0.1316886544, 0.1181945205, 0.1019300893,
+                        0.0832767040, 0.0626720116, 0.0424925000, 0.0046269894, 0.0038279891, 0.0030260086,
+                        0.0022199750, 0.0014140010, 0.0005330000, 0.0000750000};
+const int kLwNgc[16] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+const std::vector<std::vector<int>> kLwNgn = {
+    {1, 1, 2, 2, 2, 2, 2, 2, 1, 1}, {1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2},
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3},
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, {2, 2, 2, 2, 2, 2, 2, 2},
+    {2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2}, {2, 2, 2, 2, 2, 2, 2, 2},
+    {1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2}, {2, 2, 2, 2, 4, 4},
+    {1, 1, 2, 2, 2, 2, 3, 3}, {1, 1, 1, 1, 2, 2, 4, 4},
+    {3, 3, 4, 6}, {8, 8}, {8, 8}, {4, 12}};
+const int kSwNgc[14] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};
+const std::vector<std::vector<int>> kSwNgn = {
+    {2, 2, 2, 2, 4, 4}, {1, 1, 1, 1, 1, 2, 1, 2, 1, 2, 1, 2}, {1, 1, 1, 1, 2, 2, 4, 4}, {1, 1, 1, 1, 2, 2, 4, 4},
+    {1, 1, 1, 1, 1, 1, 1, 1, 2, 6}, {1, 1, 1, 1, 1, 1, 1, 1, 2, 6}, {8, 8}, {2, 2, 1, 1, 1, 1, 1, 1, 2, 4},
+    {2, 2, 2, 2, 2, 2, 2, 2}, {1, 1, 2, 2, 4, 6}, {1, 1, 2, 2, 4, 6}, {1, 1, 1, 1, 1, 1, 4, 6},
+    {1, 1, 2, 2, 4, 6}, {1, 1, 1, 1, 2, 2, 2, 2, 1, 1, 1, 1}};
+
+struct GMap {
+    int ngc;
+    int first[16], count[16];
+    double rw[16];
+};
+GMap make_gmap(int ngc, const std::vector<int> &ngn)
+{
+    GMap m;
+    m.ngc = ngc;
+    int pos = 0;
+    for (int k = 0; k < ngc; ++k) {
+        m.first[k] = pos;
+        m.count[k] = ngn[k];
+        double wsum = 0.0;
+        for (int i = 0; i < ngn[k]; ++i) wsum = wsum + kWt[pos + i];
+        for (int i = 0; i < ngn[k]; ++i) m.rw[pos + i] = (ngc < 16) ? kWt[pos + i] / wsum : 1.0;
+        pos += ngn[k];
+    }
+    return m;
+}
+
+enum class GAxis { First, Last };
+// Reduce the 16-wide g axis; result keeps the Fortran layout with 16 replaced by ngc.
+HostArr reduce_g(const HostArr &a, const GMap &m, GAxis axis, bool weighted)
+{
+    HostArr r;
+    r.dims = a.dims;
+    const long total = a.size();
+    const long other = total / 16;
+    if (axis == GAxis::Last) {
+        r.dims.back() = m.ngc;
+        r.data.assign((size_t)other * m.ngc, 0.0);
+        for (int k = 0; k < m.ngc; ++k)
+            for (long e = 0; e < other; ++e) {
+                double s = 0.0;
+                for (int i = m.first[k]; i < m.first[k] + m.count[k]; ++i) {
+                    const double v = a.data[(size_t)i * other + e];
+                    s = weighted ? s + v * m.rw[i] : s + v;
+                }
+                r.data[(size_t)k * other + e] = s;
+            }
+    } else {
+        r.dims.front() = m.ngc;
+        r.data.assign((size_t)other * m.ngc, 0.0);
+        for (long o = 0; o < other; ++o)
+            for (int k = 0; k < m.ngc; ++k) {
+                double s = 0.0;
+                for (int i = m.first[k]; i < m.first[k] + m.count[k]; ++i) {
+                    const double v = a.data[(size_t)o * 16 + i];
+                    s = weighted ? s + v * m.rw[i] : s + v;
+                }
+                r.data[(size_t)o * m.ngc + k] = s;
+            }
+    }
+    return r;
+}
+
+const HostArr *find(const std::string &name)
+{
+    auto it = G.reg.find(name);
+    return it == G.reg.end() ? nullptr : &it->second;
+}
+
+// Reduce registry array "<pfx>.<oname>" and remember it as "<pfx>.<rname>"; nullptr if absent.
+const HostArr *reduce_named(const std::string &pfx, const char *oname, const char *rname, const GMap &m)
+{
+    const HostArr *a = find(pfx + "." + oname);
+    if (!a) return nullptr;
+    const std::string on(oname);
+    const bool plain = on == "fracrefao" || on == "fracrefbo" || on == "sfluxrefo";
+    const bool gfirst = plain || on == "raylao" || a->dims.size() == 1;
+    if ((gfirst ? a->dims.front() : a->dims.back()) != 16) return nullptr;
+    HostArr r = reduce_g(*a, m, gfirst ? GAxis::First : GAxis::Last, !plain);
+    auto &slot = G.reduced[pfx + "." + rname];
+    slot = std::move(r);
+    return &slot;
+}
+
+// Append a reduced (rows, ng) Fortran array (g last) or (ng, rows) (g first) to the band table as
+// [row][ig]; returns the first row index.
+int append_rows(std::vector<double> &tab, int base, int ng, const HostArr *a, bool gfirst)
+{
+    const int row0 = (int)((tab.size() - base) / ng);
+    if (!a) return -1;
+    const long rows = a->size() / ng;
+    const size_t o = tab.size();
+    tab.resize(o + (size_t)rows * ng);
+    for (long r = 0; r < rows; ++r)
+        for (int ig = 0; ig < ng; ++ig)
+            tab[o + (size_t)r * ng + ig] = gfirst ? a->data[(size_t)r * ng + ig] : a->data[(size_t)ig * rows + r];
+    return row0;
+}
+int append_const_row(std::vector<double> &tab, int base, int ng, const double *vals)
+{
+    const int row0 = (int)((tab.size() - base) / ng);
+    for (int ig = 0; ig < ng; ++ig) tab.push_back(vals[ig]);
+    return row0;
+}
+
+int copy_exact(const char *name, double *dst, long n)
+{
+    const HostArr *a = find(name);
+    if (!a || a->size() != n) return -1;
+    std::memcpy(dst, a->data.data(), sizeof(double) * (size_t)n);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int lw_init_impl(double cpdair)
+{
+    LwConst &c = G.lwc;
+    std::memset(&c, 0, sizeof c);
+    double pref[59];
+    if (copy_exact("lwref.pref", pref, 59) || copy_exact("lwref.preflog", c.preflog, 59) ||
+        copy_exact("lwref.tref", c.tref, 59) || copy_exact("lwref.chi_mls", c.chi_mls, 7 * 59))
+        return fail(RRTMG_B200_ERR_TABLES, "lwref.{pref,preflog,tref,chi_mls} missing or wrong shape");
+    const HostArr *totplnk = find("lwref.totplnk");
+    if (!totplnk || totplnk->size() != 181 * 16) return fail(RRTMG_B200_ERR_TABLES, "lwref.totplnk missing");
+    auto chi = [&](int m, int j) { return c.chi_mls[(j - 1) * 7 + (m - 1)]; };
+    for (int j = 1; j <= 59; ++j) {
+        c.rat_h2oco2[j - 1] = chi(1, j) / chi(2, j);
+        c.rat_h2oo3[j - 1] = chi(1, j) / chi(3, j);
+        c.rat_h2on2o[j - 1] = chi(1, j) / chi(4, j);
+        c.rat_h2och4[j - 1] = chi(1, j) / chi(6, j);
+        c.rat_n2oco2[j - 1] = chi(4, j) / chi(2, j);
+        c.rat_o3co2[j - 1] = chi(3, j) / chi(2, j);
+    }
+    const double delwave[16] = {340., 150., 130., 70., 120., 160., 100., 100., 210., 90., 320., 280., 170., 130., 220., 650.};
+    const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
+    const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    for (int b = 0; b < 16; ++b) { c.delwave[b] = delwave[b]; c.a0[b] = a0[b]; c.a1[b] = a1[b]; c.a2[b] = a2[b]; }
+    const double grav = 9.8066, secdy = 8.6400e4;
+    c.heatfac = grav * secdy / (cpdair * 1.e2);
+    c.oneminus = 1. - 1.e-6;
+    c.fluxfac = (2. * std::asin(1.)) * 2.e4;
+    c.bpade = 1.0 / 0.278;
+
+    // band-specific reference ratios (taumol.f90, e.g. :485-494): {planck_a, planck_b, m_a, m_b, m_a3}
+    auto R = [&](int m1, int j1, int m2) { return chi(m1, j1) / chi(m2, j1); };
+    double rr[16][5] = {};
+    rr[2][0] = R(1, 9, 2);  rr[2][1] = R(1, 13, 2); rr[2][2] = R(1, 3, 2); rr[2][3] = R(1, 13, 2);
+    rr[3][0] = R(1, 11, 2); rr[3][1] = R(3, 13, 2);
+    rr[4][0] = R(1, 5, 2);  rr[4][1] = R(3, 43, 2); rr[4][2] = R(1, 7, 2);
+    rr[6][0] = R(1, 3, 3);  rr[6][2] = R(1, 3, 3);
+    rr[8][0] = R(1, 9, 6);  rr[8][2] = R(1, 3, 6);
+    rr[11][0] = R(1, 10, 2);
+    rr[12][0] = R(1, 5, 4); rr[12][2] = R(1, 1, 4); rr[12][4] = R(1, 3, 4);
+    rr[14][0] = R(4, 1, 2); rr[14][2] = R(4, 1, 2);
+    rr[15][0] = R(1, 6, 6);
+
+    std::vector<double> tab;
+    int g0 = 0;
+    for (int b = 0; b < 16; ++b) {
+        LwBand &B = c.band[b];
+        char pfx[8];
+        std::snprintf(pfx, sizeof pfx, "lw%02d", b + 1);
+        const GMap m = make_gmap(kLwNgc[b], kLwNgn[b]);
+        const int ng = m.ngc;
+        B.ng = ng;
+        B.g0 = g0;
+        g0 += ng;
+        B.base = (int)tab.size();
+        for (int k = 0; k < 5; ++k) B.refrat[k] = rr[b][k];
+        for (int k = 0; k < LS_COUNT; ++k) B.sec[k] = -1;
+        auto add = [&](int sec, const char *o, const char *r) {
+            const HostArr *a = reduce_named(pfx, o, r, m);
+            if (a) B.sec[sec] = append_rows(tab, B.base, ng, a, std::string(o).rfind("fracref", 0) == 0);
+            return a != nullptr;
+        };
+        if (!add(LS_ABSA, "kao", "absa") || !add(LS_SELF, "selfrefo", "selfref") || !add(LS_FOR, "forrefo", "forref") ||
+            !add(LS_FRACA, "fracrefao", "fracrefa"))
+            return fail(RRTMG_B200_ERR_TABLES, std::string(pfx) + ": kao/selfrefo/forrefo/fracrefao missing");
+        add(LS_ABSB, "kbo", "absb");
+        add(LS_FRACB, "fracrefbo", "fracrefb");
+        // minor species and cross sections, per band (rrlw_kgNN.f90)
+        struct Slot { int band, sec; const char *o, *r; };
+        static const Slot slots[] = {
+            {1, LS_MA1, "kao_mn2", "ka_mn2"},    {1, LS_MB1, "kbo_mn2", "kb_mn2"},
+            {3, LS_MA1, "kao_mn2o", "ka_mn2o"},  {3, LS_MB1, "kbo_mn2o", "kb_mn2o"},
+            {5, LS_MA1, "kao_mo3", "ka_mo3"},    {5, LS_X1, "ccl4o", "ccl4"},
+            {6, LS_MA1, "kao_mco2", "ka_mco2"},  {6, LS_X1, "cfc11adjo", "cfc11adj"}, {6, LS_X2, "cfc12o", "cfc12"},
+            {7, LS_MA1, "kao_mco2", "ka_mco2"},  {7, LS_MB1, "kbo_mco2", "kb_mco2"},
+            {8, LS_MA1, "kao_mco2", "ka_mco2"},  {8, LS_MA2, "kao_mo3", "ka_mo3"},    {8, LS_MA3, "kao_mn2o", "ka_mn2o"},
+            {8, LS_MB1, "kbo_mco2", "kb_mco2"},  {8, LS_MB2, "kbo_mn2o", "kb_mn2o"},
+            {8, LS_X1, "cfc12o", "cfc12"},       {8, LS_X2, "cfc22adjo", "cfc22adj"},
+            {9, LS_MA1, "kao_mn2o", "ka_mn2o"},  {9, LS_MB1, "kbo_mn2o", "kb_mn2o"},
+            {11, LS_MA1, "kao_mo2", "ka_mo2"},   {11, LS_MB1, "kbo_mo2", "kb_mo2"},
+            {13, LS_MA1, "kao_mco2", "ka_mco2"}, {13, LS_MA2, "kao_mco", "ka_mco"},   {13, LS_MB1, "kbo_mo3", "kb_mo3"},
+            {15, LS_MA1, "kao_mn2", "ka_mn2"}};
+        for (const Slot &s : slots)
+            if (s.band == b + 1 && !add(s.sec, s.o, s.r))
+                return fail(RRTMG_B200_ERR_TABLES, std::string(pfx) + "." + s.o + " missing");
+        // stratospheric g-point scaling of bands 4 and 7 (taumol.f90:1009-1015, :1645-1650)
+        if (b == 3) {
+            double gsc[14];
+            for (int i = 0; i < 14; ++i) gsc[i] = 1.0;
+            const double f[7] = {0.92, 0.88, 1.07, 1.1, 0.99, 0.88, 0.943};
+            for (int i = 0; i < 7; ++i) gsc[7 + i] = f[i];
+            B.sec[LS_GSCALE] = append_const_row(tab, B.base, ng, gsc);
+        } else if (b == 6) {
+            double gsc[12];
+            for (int i = 0; i < 12; ++i) gsc[i] = 1.0;
+            const double f[6] = {0.92, 0.88, 1.07, 1.1, 0.99, 0.855};
+            for (int i = 0; i < 6; ++i) gsc[5 + i] = f[i];
+            B.sec[LS_GSCALE] = append_const_row(tab, B.base, ng, gsc);
+        }
+    }
+    // lookup tables (rrtmg_lw_init.f90:106-123), interleaved {exp_tbl, tfn_tbl}
+    std::vector<double> et(2 * (NTBL + 1));
+    {
+        const double expeps = 1.e-20;
+        std::vector<double> tau(NTBL + 1), ex(NTBL + 1), tf(NTBL + 1);
+        tau[0] = 0.0; tau[NTBL] = 1.e10; ex[0] = 1.0; ex[NTBL] = expeps; tf[0] = 0.0; tf[NTBL] = 1.0;
+        for (int itr = 1; itr <= NTBL - 1; ++itr) {
+            const double tfn = (double)itr / (double)NTBL;
+            tau[itr] = c.bpade * tfn / (1. - tfn);
+            ex[itr] = std::exp(-tau[itr]);
+            if (ex[itr] <= expeps) ex[itr] = expeps;
+            if (tau[itr] < 0.06) tf[itr] = tau[itr] / 6.;
+            else tf[itr] = 1. - 2. * ((1. / tau[itr]) - (ex[itr] / (1. - ex[itr])));
+        }
+        for (int i = 0; i <= NTBL; ++i) { et[2 * i] = ex[i]; et[2 * i + 1] = tf[i]; }
+        HostArr &he = G.reduced["lw.exp_tbl"]; he.dims = {NTBL + 1}; he.data = ex;
+        HostArr &ht = G.reduced["lw.tfn_tbl"]; ht.dims = {NTBL + 1}; ht.data = tf;
+    }
+    if (G.lw_tab.ensure(tab.size() * 8) || G.lw_totplnk.ensure(181 * 16 * 8) || G.lw_exptfn.ensure(et.size() * 8))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for LW tables");
+    CUDA_OK(cudaMemcpy(G.lw_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.lw_totplnk.p, totplnk->data.data(), 181 * 16 * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.lw_exptfn.p, et.data(), et.size() * 8, cudaMemcpyHostToDevice));
+    G.lwt.tab = (const double *)G.lw_tab.p;
+    G.lwt.totplnk = (const double *)G.lw_totplnk.p;
+    G.lwt.exptfn = (const double *)G.lw_exptfn.p;
+    if (lw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_lw) failed");
+    G.lw_ready = true;
+    return RRTMG_B200_OK;
+}
+
+int sw_init_impl(double cpdair)
+{
+    SwConst &c = G.swc;
+    std::memset(&c, 0, sizeof c);
+    double pref[59];
+    if (copy_exact("swref.pref", pref, 59) || copy_exact("swref.preflog", c.preflog, 59) ||
+        copy_exact("swref.tref", c.tref, 59))
+        return fail(RRTMG_B200_ERR_TABLES, "swref.{pref,preflog,tref} missing or wrong shape");
+    const double grav = 9.8066, secdy = 8.6400e4;
+    c.heatfac = grav * secdy / (cpdair * 1.e2);
+    c.oneminus = 1.0 - 1.e-06;
+    c.bpade = 1.0 / 0.278;
+
+    std::vector<double> tab;
+    int g0 = 0;
+    for (int b = 0; b < 14; ++b) {
+        SwBand &B = c.band[b];
+        char pfx[8];
+        std::snprintf(pfx, sizeof pfx, "sw%d", b + 16);
+        const GMap m = make_gmap(kSwNgc[b], kSwNgn[b]);
+        const int ng = m.ngc;
+        B.ng = ng;
+        B.g0 = g0;
+        g0 += ng;
+        B.base = (int)tab.size();
+        for (int k = 0; k < SS_COUNT; ++k) B.sec[k] = -1;
+        auto add = [&](int sec, const char *o, const char *r, bool gfirst) {
+            const HostArr *a = reduce_named(pfx, o, r, m);
+            if (a) B.sec[sec] = append_rows(tab, B.base, ng, a, gfirst);
+            return a;
+        };
+        add(SS_ABSA, "kao", "absa", false);
+        add(SS_ABSB, "kbo", "absb", false);
+        add(SS_SELF, "selfrefo", "selfref", false);
+        add(SS_FOR, "forrefo", "forref", false);
+        const HostArr *sf = add(SS_SFLUX, "sfluxrefo", "sfluxref", true);
+        if (!sf) return fail(RRTMG_B200_ERR_TABLES, std::string(pfx) + ".sfluxrefo missing");
+        B.nsflux = (int)(sf->size() / ng);
+        // Rayleigh: scalar (one row filled with it), per-g row, or band 24's (ng,9) + raylb
+        const HostArr *rs = find(std::string(pfx) + ".rayl");
+        if (rs) {
+            double row[16];
+            for (int i = 0; i < ng; ++i) row[i] = rs->data[0];
+            B.sec[SS_RAYL] = append_const_row(tab, B.base, ng, row);
+            B.nrayl = 1;
+        } else if (add(SS_RAYL, "raylo", "rayl", true)) {
+            B.nrayl = 1;
+        } else if (add(SS_RAYL, "raylao", "rayla", true)) {
+            B.nrayl = 9;
+            if (!add(SS_RAYLB, "raylbo", "raylb", true)) return fail(RRTMG_B200_ERR_TABLES, std::string(pfx) + ".raylbo missing");
+        } else {
+            return fail(RRTMG_B200_ERR_TABLES, std::string(pfx) + ": no Rayleigh coefficients");
+        }
+        if (b + 16 == 20) add(SS_X1, "absch4o", "absch4", true);
+        if (b + 16 == 24 || b + 16 == 25) { add(SS_X1, "abso3ao", "abso3a", true); add(SS_X2, "abso3bo", "abso3b", true); }
+        if (b + 16 == 29) { add(SS_X1, "absh2oo", "absh2o", true); add(SS_X2, "absco2o", "absco2", true); }
+    }
+    // exp_tbl (rrtmg_sw_init.f90:96-105), interleaved with its reciprocal
+    std::vector<double> et(2 * (NTBL + 1));
+    {
+        const double expeps = 1.e-20;
+        std::vector<double> ex(NTBL + 1);
+        ex[0] = 1.0; ex[NTBL] = expeps;
+        for (int itr = 1; itr <= NTBL - 1; ++itr) {
+            const double tfn = (double)itr / (double)NTBL;
+            const double tau = c.bpade * tfn / (1. - tfn);
+            ex[itr] = std::exp(-tau);
+            if (ex[itr] <= expeps) ex[itr] = expeps;
+        }
+        for (int i = 0; i <= NTBL; ++i) { et[2 * i] = ex[i]; et[2 * i + 1] = 1. / ex[i]; }
+        HostArr &he = G.reduced["sw.exp_tbl"]; he.dims = {NTBL + 1}; he.data = ex;
+    }
+    if (G.sw_tab.ensure(tab.size() * 8) || G.sw_exptbl.ensure(et.size() * 8))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for SW tables");
+    CUDA_OK(cudaMemcpy(G.sw_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.sw_exptbl.p, et.data(), et.size() * 8, cudaMemcpyHostToDevice));
+    G.swt.tab = (const double *)G.sw_tab.p;
+    G.swt.exptbl = (const double *)G.sw_exptbl.p;
+    if (sw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_sw) failed");
+    G.sw_ready = true;
+    return RRTMG_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+struct Carver {
+    char *p;
+    size_t off = 0;
+    explicit Carver(void *base) : p((char *)base) {}
+    template <class T> T *take(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T *r = p ? (T *)(p + off) : nullptr;
+        off += n * sizeof(T);
+        return r;
+    }
+};
+size_t lw_carve(LwWork &w, void *base, int nc, int nlay)
+{
+    Carver c(base);
+    w.nc = nc; w.nlay = nlay;
+    const size_t np = (size_t)nc * nlay;
+    w.idx = c.take<uint32_t>(np);
+    w.laytrop = c.take<int>(nc);
+    w.f = c.take<double>(np * LF_COUNT);
+    w.secdiff = c.take<double>((size_t)nc * 16);
+    w.planklay = c.take<double>(np * 16);
+    w.planklev = c.take<double>((size_t)nc * (nlay + 1) * 16);
+    w.plankbnd = c.take<double>((size_t)nc * 16);
+    w.taug = c.take<double>(np * NGPTLW);
+    w.fracs = c.take<double>(np * NGPTLW);
+    return c.off + 256;
+}
+size_t sw_carve(SwWork &w, void *base, int nc, int nlay)
+{
+    Carver c(base);
+    w.nc = nc; w.nlay = nlay;
+    const size_t np = (size_t)nc * nlay;
+    w.idx = c.take<uint32_t>(np);
+    w.laytrop = c.take<int>(nc);
+    w.laysolfr = c.take<int>((size_t)nc * 14);
+    w.f = c.take<double>(np * SF_COUNT);
+    w.taug = c.take<double>(np * NGPTSW);
+    w.taur = c.take<double>(np * NGPTSW);
+    w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
+    return c.off + 256;
+}
+
+int pick_chunk(int ncol)
+{
+    int ch = G.chunk > 0 ? G.chunk : 4096;
+    return ch < ncol ? ch : ncol;
+}
+
+// ------------------------------------------------------------------------------------------------
+int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st)
+{
+    if (!G.lw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_lw_init has not been called");
+    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
+    if (icld && (*icld < 0 || *icld > 3)) *icld = 2;     // LW rad.nomcica:437
+    if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: icld > 0 (cloudy-sky branch) is not built");
+    if (idrv != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: idrv = 1 (flux derivatives) is not built");
+    if (ncol == 0) return RRTMG_B200_OK;
+    const int chunk = pick_chunk(ncol);
+    LwWork w;
+    const size_t need = lw_carve(w, nullptr, chunk, nlay);
+    if (G.lw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        lw_carve(w, G.lw_work.p, nc, nlay);
+        LwIn in = in0;
+        LwOut out = out0;
+#define OFF(p) if (in.p) in.p += c0
+        OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
+        OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
+#undef OFF
+        out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
+        double *cap = nullptr;
+        if (G.capture && ncol <= chunk) {
+            if (G.lw_cap.ensure(2 * (size_t)nc * nlay * NGPTLW * 8)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (capture)");
+            cap = (double *)G.lw_cap.p;
+        }
+        G.launches += lw_run_pass(G.lwt, in, out, w, st, cap);
+        CUDA_OK(cudaGetLastError());
+    }
+    G.lw_last = w;
+    G.lw_last_ncol = (ncol <= chunk) ? ncol : 0;
+    return RRTMG_B200_OK;
+}
+
+int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st)
+{
+    if (!G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_sw_init has not been called");
+    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
+    if (icld && (*icld < 0 || *icld > 3)) *icld = 2;                           // SW rad.nomcica:468
+    if (iaer && *iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;            // SW rad.nomcica:473
+    if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: icld > 0 (cloudy-sky branch) is not built");
+    if (iaer && *iaer != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: iaer = 6/10 (aerosols) is not built");
+    if (ncol == 0) return RRTMG_B200_OK;
+    const int chunk = pick_chunk(ncol);
+    SwWork w;
+    const size_t need = sw_carve(w, nullptr, chunk, nlay);
+    if (G.sw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        sw_carve(w, G.sw_work.p, nc, nlay);
+        SwIn in = in0;
+        SwOut out = out0;
+#define OFF(p) if (in.p) in.p += c0
+        OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
+        OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
+#undef OFF
+        out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
+        CUDA_OK(cudaMemsetAsync(w.sfluxzen, 0, (size_t)nc * NGPTSW * 8, st));
+        G.launches += sw_run_pass(G.swt, in, out, w, st);
+        CUDA_OK(cudaGetLastError());
+    }
+    G.sw_last = w;
+    G.sw_last_ncol = (ncol <= chunk) ? ncol : 0;
+    return RRTMG_B200_OK;
+}
+
+// adjflux (SW rad.nomcica:953-972, earth_sun :734-758)
+double sw_adjflux(double adjes, int dyofyr, double scon)
+{
+    double adjflx = adjes;
+    if (dyofyr > 0) {
+        const double pi = 2. * std::asin(1.);
+        const double gamma = 2. * pi * (dyofyr - 1) / 365.;
+        adjflx = 1.000110 + .034221 * std::cos(gamma) + .001289 * std::sin(gamma) + .000719 * std::cos(2. * gamma) +
+                 .000077 * std::sin(2. * gamma);
+    }
+    const double solvar = scon / 1.36822e+03;
+    return adjflx * solvar;
+}
+
+// host staging helper: copies a host array to the device staging area (or keeps nullptr)
+struct Stager {
+    char *base;
+    size_t off = 0;
+    cudaStream_t st;
+    bool ok = true;
+    const double *up(const double *h, size_t n)
+    {
+        if (!h) return nullptr;
+        double *d = (double *)(base + off);
+        off += ((n * 8 + 255) & ~(size_t)255);
+        if (cudaMemcpyAsync(d, h, n * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        return d;
+    }
+    double *out(size_t n)
+    {
+        double *d = (double *)(base + off);
+        off += ((n * 8 + 255) & ~(size_t)255);
+        return d;
+    }
+};
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *rrtmg_b200_last_error(void) { return G.err.c_str(); }
+long rrtmg_b200_launch_count(void) { return G.launches; }
+
+int rrtmg_b200_set_device(int local_rank)
+{
+    int n = 0;
+    CUDA_OK(cudaGetDeviceCount(&n));
+    if (n <= 0) return fail(RRTMG_B200_ERR_CUDA, "no CUDA device");
+    CUDA_OK(cudaSetDevice(((local_rank % n) + n) % n));
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_set_table(const char *name, const double *data, int ndim, const int *dims)
+{
+    if (!name || !data || ndim < 1 || ndim > 4 || !dims) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "set_table: bad argument");
+    std::lock_guard<std::mutex> lk(G.mu);
+    HostArr a;
+    a.dims.assign(dims, dims + ndim);
+    for (int d : a.dims) if (d < 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "set_table: non-positive dimension");
+    a.data.assign(data, data + a.size());
+    G.reg[name] = std::move(a);
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_load_tables(const char *path)
+{
+    FILE *f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) return fail(RRTMG_B200_ERR_TABLES, std::string("cannot open ") + (path ? path : "(null)"));
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<unsigned char> raw((size_t)sz);
+    const bool ok = std::fread(raw.data(), 1, (size_t)sz, f) == (size_t)sz;
+    std::fclose(f);
+    if (!ok || sz < 12 || std::memcmp(raw.data(), "RRTMGTB1", 8) != 0) return fail(RRTMG_B200_ERR_TABLES, "not an RRTMGTB1 blob");
+    uint32_t n;
+    std::memcpy(&n, raw.data() + 8, 4);
+    const size_t recsz = 60;
+    if ((size_t)sz < 12 + n * recsz) return fail(RRTMG_B200_ERR_TABLES, "truncated blob");
+    const unsigned char *data = raw.data() + 12 + n * recsz;
+    for (uint32_t i = 0; i < n; ++i) {
+        const unsigned char *p = raw.data() + 12 + i * recsz;
+        char name[33];
+        std::memcpy(name, p, 32);
+        name[32] = 0;
+        uint32_t nd, d[4];
+        uint64_t off;
+        std::memcpy(&nd, p + 32, 4);
+        std::memcpy(d, p + 36, 16);
+        std::memcpy(&off, p + 52, 8);
+        if (nd < 1 || nd > 4) return fail(RRTMG_B200_ERR_TABLES, "bad record in blob");
+        int dims[4];
+        size_t cnt = 1;
+        for (uint32_t k = 0; k < nd; ++k) { dims[k] = (int)d[k]; cnt *= d[k]; }
+        if (data + (off + cnt) * 8 > raw.data() + sz) return fail(RRTMG_B200_ERR_TABLES, "blob record out of range");
+        std::vector<double> tmp(cnt);
+        std::memcpy(tmp.data(), data + off * 8, cnt * 8);
+        const int rc = rrtmg_b200_set_table(name, tmp.data(), (int)nd, dims);
+        if (rc) return rc;
+    }
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_lw_init(double cpdair)
+{
+    std::lock_guard<std::mutex> lk(G.mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(RRTMG_B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    return lw_init_impl(cpdair);
+}
+int rrtmg_b200_sw_init(double cpdair)
+{
+    std::lock_guard<std::mutex> lk(G.mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(RRTMG_B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    return sw_init_impl(cpdair);
+}
+
+int rrtmg_b200_finalize(void)
+{
+    std::lock_guard<std::mutex> lk(G.mu);
+    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_stage_in, &G.lw_stage_out, &G.lw_cap,
+                      &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_stage_in, &G.sw_stage_out})
+        b->release();
+    G.lw_ready = G.sw_ready = false;
+    G.lw_last_ncol = G.sw_last_ncol = 0;
+    G.reduced.clear();
+    return RRTMG_B200_OK;
+}
+
+long rrtmg_b200_get_table(const char *name, double *out, long capacity)
+{
+    auto it = G.reduced.find(name ? name : "");
+    if (it == G.reduced.end()) return -1;
+    const long n = it->second.size();
+    if (out && capacity >= n) std::memcpy(out, it->second.data.data(), (size_t)n * 8);
+    return n;
+}
+
+int rrtmg_b200_set_chunk(int ncol_per_pass)
+{
+    if (ncol_per_pass < 0) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "chunk must be >= 0");
+    G.chunk = ncol_per_pass;
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
+                         const double *play, const double *plev, const double *tlay, const double *tlev,
+                         const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                         const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                         const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                         const double *ccl4vmr, const double *emis,
+                         int, int, int, const double *, const double *, const double *, const double *,
+                         const double *, const double *,
+                         const double *tauaer,
+                         double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                         double *, double *, void *stream)
+{
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
+        !uflxc || !dflxc || !hrc)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
+    LwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+            cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer};
+    LwOut out{ncol, uflx, dflx, hr, uflxc, dflxc, hrc};
+    return lw_device_impl(ncol, nlay, icld, idrv, in, out, (cudaStream_t)stream);
+}
+
+int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
+                  const double *play, const double *plev, const double *tlay, const double *tlev,
+                  const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
+                  const double *ccl4vmr, const double *emis,
+                  int inflglw, int iceflglw, int liqflglw, const double *cldfr,
+                  const double *taucld, const double *cicewp, const double *cliqwp,
+                  const double *reice, const double *reliq, const double *tauaer,
+                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                  double *duflx_dt, double *duflxc_dt)
+{
+    if (!G.lw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_lw_init has not been called");
+    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range");
+    if (ncol == 0) return RRTMG_B200_OK;
+    const size_t nl = (size_t)ncol * nlay, nv = (size_t)ncol * (nlay + 1);
+    const size_t in_bytes = (13 * nl + 2 * nv + ncol + 16 * (size_t)ncol + 16 * nl) * 8 + 64 * 256;
+    const size_t out_bytes = (4 * nv + 2 * nl) * 8 + 8 * 256;
+    if (G.lw_stage_in.ensure(in_bytes) || G.lw_stage_out.ensure(out_bytes))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for LW staging");
+    cudaStream_t st = 0;
+    Stager s{(char *)G.lw_stage_in.p, 0, st};
+    const double *d_play = s.up(play, nl), *d_plev = s.up(plev, nv), *d_tlay = s.up(tlay, nl), *d_tlev = s.up(tlev, nv);
+    const double *d_tsfc = s.up(tsfc, ncol), *d_h2o = s.up(h2ovmr, nl), *d_o3 = s.up(o3vmr, nl), *d_co2 = s.up(co2vmr, nl);
+    const double *d_ch4 = s.up(ch4vmr, nl), *d_n2o = s.up(n2ovmr, nl), *d_o2 = s.up(o2vmr, nl);
+    const double *d_c11 = s.up(cfc11vmr, nl), *d_c12 = s.up(cfc12vmr, nl), *d_c22 = s.up(cfc22vmr, nl), *d_ccl4 = s.up(ccl4vmr, nl);
+    const double *d_emis = s.up(emis, 16 * (size_t)ncol), *d_taer = s.up(tauaer, 16 * nl);
+    if (!s.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
+    Stager o{(char *)G.lw_stage_out.p, 0, st};
+    double *d_uflx = o.out(nv), *d_dflx = o.out(nv), *d_hr = o.out(nl), *d_uflxc = o.out(nv), *d_dflxc = o.out(nv), *d_hrc = o.out(nl);
+    const int rc = rrtmg_b200_lw_device(ncol, nlay, icld, idrv, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2,
+                                        d_ch4, d_n2o, d_o2, d_c11, d_c12, d_c22, d_ccl4, d_emis, inflglw, iceflglw, liqflglw,
+                                        cldfr, taucld, cicewp, cliqwp, reice, reliq, d_taer, d_uflx, d_dflx, d_hr, d_uflxc,
+                                        d_dflxc, d_hrc, duflx_dt, duflxc_dt, (void *)st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(uflx, d_uflx, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(dflx, d_dflx, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(hr, d_hr, nl * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(uflxc, d_uflxc, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(dflxc, d_dflxc, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(hrc, d_hrc, nl * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
+                         const double *play, const double *plev, const double *tlay, const double *tlev,
+                         const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                         const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                         const double *asdir, const double *asdif, const double *aldir, const double *aldif,
+                         const double *coszen, double adjes, int dyofyr, double scon,
+                         int, int, int, const double *, const double *, const double *, const double *,
+                         const double *, const double *, const double *, const double *, const double *,
+                         const double *, const double *, const double *, const double *,
+                         double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
+                         double *swhrc, void *stream)
+{
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
+        !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
+    SwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+            asdir, asdif, aldir, aldif, coszen, sw_adjflux(adjes, dyofyr, scon)};
+    SwOut out{ncol, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
+    return sw_device_impl(ncol, nlay, icld, iaer, in, out, (cudaStream_t)stream);
+}
+
+int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
+                  const double *play, const double *plev, const double *tlay, const double *tlev,
+                  const double *tsfc, const double *h2ovmr, const double *o3vmr, const double *co2vmr,
+                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
+                  const double *asdir, const double *asdif, const double *aldir, const double *aldif,
+                  const double *coszen, double adjes, int dyofyr, double scon,
+                  int inflgsw, int iceflgsw, int liqflgsw, const double *cldfr,
+                  const double *taucld, const double *ssacld, const double *asmcld, const double *fsfcld,
+                  const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
+                  const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
+                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc, double *swhrc)
+{
+    if (!G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_sw_init has not been called");
+    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range");
+    if (ncol == 0) return RRTMG_B200_OK;
+    const size_t nl = (size_t)ncol * nlay, nv = (size_t)ncol * (nlay + 1);
+    const size_t in_bytes = (9 * nl + 2 * nv + 6 * (size_t)ncol) * 8 + 64 * 256;
+    const size_t out_bytes = (4 * nv + 2 * nl) * 8 + 8 * 256;
+    if (G.sw_stage_in.ensure(in_bytes) || G.sw_stage_out.ensure(out_bytes))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for SW staging");
+    cudaStream_t st = 0;
+    Stager s{(char *)G.sw_stage_in.p, 0, st};
+    const double *d_play = s.up(play, nl), *d_plev = s.up(plev, nv), *d_tlay = s.up(tlay, nl), *d_tlev = s.up(tlev, nv);
+    const double *d_tsfc = s.up(tsfc, ncol), *d_h2o = s.up(h2ovmr, nl), *d_o3 = s.up(o3vmr, nl), *d_co2 = s.up(co2vmr, nl);
+    const double *d_ch4 = s.up(ch4vmr, nl), *d_n2o = s.up(n2ovmr, nl), *d_o2 = s.up(o2vmr, nl);
+    // MiMA passes the same albedo array four times (rrtm_radiation.f90:690): upload once per distinct pointer
+    const double *d_asdir = s.up(asdir, ncol);
+    const double *d_asdif = asdif == asdir ? d_asdir : s.up(asdif, ncol);
+    const double *d_aldir = aldir == asdir ? d_asdir : s.up(aldir, ncol);
+    const double *d_aldif = aldif == asdir ? d_asdir : (aldif == aldir ? d_aldir : s.up(aldif, ncol));
+    const double *d_cosz = s.up(coszen, ncol);
+    if (!s.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
+    Stager o{(char *)G.sw_stage_out.p, 0, st};
+    double *d_u = o.out(nv), *d_d = o.out(nv), *d_h = o.out(nl), *d_uc = o.out(nv), *d_dc = o.out(nv), *d_hc = o.out(nl);
+    const int rc = rrtmg_b200_sw_device(ncol, nlay, icld, iaer, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2,
+                                        d_ch4, d_n2o, d_o2, d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjes, dyofyr, scon,
+                                        inflgsw, iceflgsw, liqflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, cicewp, cliqwp,
+                                        reice, reliq, tauaer, ssaaer, asmaer, ecaer, d_u, d_d, d_h, d_uc, d_dc, d_hc, (void *)st);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(swuflx, d_u, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(swdflx, d_d, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(swhr, d_h, nl * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(swuflxc, d_uc, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(swdflxc, d_dc, nv * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(swhrc, d_hc, nl * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RRTMG_B200_OK;
+}
+
+// ---- stage dumps ---------------------------------------------------------------------------------
+static long dump_field(const void *dev, size_t count, bool is_int, std::vector<double> &host)
+{
+    host.resize(count);
+    if (is_int) {
+        std::vector<int> tmp(count);
+        if (cudaMemcpy(tmp.data(), dev, count * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        for (size_t i = 0; i < count; ++i) host[i] = tmp[i];
+    } else if (cudaMemcpy(host.data(), dev, count * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long)count;
+}
+
+long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
+{
+    if (!which) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    const std::string k(which);
+    const bool lw = k.rfind("lw.", 0) == 0, sw = k.rfind("sw.", 0) == 0;
+    if (!lw && !sw) return -1;
+    const std::string f = k.substr(3);
+    const int nc = lw ? G.lw_last_ncol : G.sw_last_ncol;
+    if (nc <= 0) return -1;
+    const int nlay = lw ? G.lw_last.nlay : G.sw_last.nlay;
+    std::vector<double> h;
+    long n = -1;
+    // [lay][col] fields are already (ncol,nlay) column-major
+    static const char *lwf[LF_COUNT] = {"fac00", "fac01", "fac10", "fac11", "colh2o", "colco2", "colo3", "coln2o", "colco",
+                                        "colch4", "colo2", "colbrd", "selffac", "selffrac", "forfac", "forfrac", "minorfrac",
+                                        "scaleminor", "scaleminorn2", "coldry", "pavel", "wx1", "wx2", "wx3", "wx4"};
+    static const char *swf[SF_COUNT] = {"fac00", "fac01", "fac10", "fac11", "colh2o", "colco2", "colo3", "colch4", "colo2",
+                                        "colmol", "coln2o", "selffac", "selffrac", "forfac", "forfrac"};
+    const size_t np = (size_t)nc * nlay;
+    auto transposed = [&](const double *dev, int inner, int mid) -> long {
+        // device [col][mid][inner] -> host (ncol, mid, inner) column-major
+        std::vector<double> t;
+        if (dump_field(dev, (size_t)nc * mid * inner, false, t) < 0) return -1;
+        h.resize(t.size());
+        for (int c = 0; c < nc; ++c)
+            for (int m = 0; m < mid; ++m)
+                for (int i = 0; i < inner; ++i)
+                    h[((size_t)i * mid + m) * nc + c] = t[((size_t)c * mid + m) * inner + i];
+        return (long)h.size();
+    };
+    if (f == "laytrop") n = dump_field(lw ? (void *)G.lw_last.laytrop : (void *)G.sw_last.laytrop, nc, true, h);
+    else if (f == "jp" || f == "jt" || f == "jt1" || f == "indself" || f == "indfor" || f == "indminor") {
+        std::vector<uint32_t> tmp(np);
+        if (cudaMemcpy(tmp.data(), lw ? G.lw_last.idx : G.sw_last.idx, np * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        h.resize(np);
+        for (size_t i = 0; i < np; ++i) {
+            const LwIdx ix = lw_unpack(tmp[i]);   // SW packing is a prefix of the LW packing
+            h[i] = f == "jp" ? ix.jp : f == "jt" ? ix.jt : f == "jt1" ? ix.jt1 : f == "indself" ? ix.inds : f == "indfor" ? ix.indf : ix.indm;
+        }
+        n = (long)np;
+    } else if (lw && f == "planklay") n = transposed(G.lw_last.planklay, 16, nlay);
+    else if (lw && f == "planklev") n = transposed(G.lw_last.planklev, 16, nlay + 1);
+    else if (lw && f == "plankbnd") n = transposed(G.lw_last.plankbnd, 16, 1);
+    else if (lw && f == "secdiff") n = transposed(G.lw_last.secdiff, 16, 1);
+    else if (lw && (f == "taug" || f == "fracs")) {
+        if (!G.lw_cap.p) return -1;
+        const double *base = (const double *)G.lw_cap.p + (f == "fracs" ? np * NGPTLW : 0);
+        n = transposed(base, NGPTLW, nlay);
+    } else if (sw && f == "taug") n = transposed(G.sw_last.taug, NGPTSW, nlay);
+    else if (sw && f == "taur") n = transposed(G.sw_last.taur, NGPTSW, nlay);
+    else if (sw && f == "sfluxzen") n = transposed(G.sw_last.sfluxzen, NGPTSW, 1);
+    else if (sw && f == "laysolfr") {
+        std::vector<double> t;
+        if (dump_field(G.sw_last.laysolfr, (size_t)nc * 14, true, t) < 0) return -1;
+        h.resize(t.size());
+        for (int c = 0; c < nc; ++c)
+            for (int b = 0; b < 14; ++b) h[(size_t)b * nc + c] = t[(size_t)c * 14 + b];
+        n = (long)h.size();
+    } else {
+        const int nf = lw ? (int)LF_COUNT : (int)SF_COUNT;
+        for (int i = 0; i < nf; ++i)
+            if (f == (lw ? lwf[i] : swf[i])) n = dump_field(lw ? G.lw_last.fld(i) : G.sw_last.fld(i), np, false, h);
+    }
+    if (n < 0) return -1;
+    if (out && capacity >= n) std::memcpy(out, h.data(), (size_t)n * 8);
+    return n;
+}
+
+int rrtmg_b200_set_option(const char *key, long value)
+{
+    const std::string k(key ? key : "");
+    if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
+    if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
+    return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "unknown option " + k);
+}
+
+} // extern "C"

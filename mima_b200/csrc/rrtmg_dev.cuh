@@ -1,0 +1,175 @@
+// rrtmg_dev.cuh -- device-side data layout shared by the LW and SW kernels (sm_100a).
+//
+// HBM layout (one "pass" = a chunk of nc columns, all nlay layers):
+//   * interface arrays arrive (ncol, nlay) column-major: the column index is contiguous, so a
+//     thread-per-column kernel reads fully coalesced.
+//   * per-(layer, column) interpolation state produced by the *_prep kernels is stored as
+//     structure-of-arrays fields F[field][lay][col] (column fastest) -- coalesced for the planner
+//     phase of taumol (thread <-> column at one layer).
+//   * the taumol -> solver staging fields (LW taug/fracs, SW taug/taur) are stored [col][lay][g]
+//     with the g-point index fastest: one warp of the solver (lanes = g-points) reads 256
+//     contiguous bytes per layer step, and the taumol executor (lanes = g-points of a few adjacent
+//     columns) reads each k-table row as one contiguous segment.
+//   * k-distribution tables are transposed at init from the Fortran (row, ig) to [row][ig] so the
+//     g-lanes of one stencil point are contiguous (<= 128 B).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rrtmg {
+
+constexpr int NBNDLW = 16, NGPTLW = 140, NBNDSW = 14, NGPTSW = 112, NTBL = 10000;
+constexpr int MAXLAY = 128;
+
+// ------------------------------------------------------------------------------------ LW
+// packed per-(lay,col) indices: jp:6 | jt:3 | jt1:3 | indself:4 | indfor:2 | indminor:5
+__host__ __device__ inline uint32_t lw_pack(int jp, int jt, int jt1, int inds, int indf, int indm)
+{
+    return (uint32_t)jp | ((uint32_t)jt << 6) | ((uint32_t)jt1 << 9) | ((uint32_t)inds << 12) |
+           ((uint32_t)indf << 16) | ((uint32_t)indm << 18);
+}
+struct LwIdx { int jp, jt, jt1, inds, indf, indm; };
+__host__ __device__ inline LwIdx lw_unpack(uint32_t v)
+{
+    LwIdx r;
+    r.jp = v & 63; r.jt = (v >> 6) & 7; r.jt1 = (v >> 9) & 7; r.inds = (v >> 12) & 15;
+    r.indf = (v >> 16) & 3; r.indm = (v >> 18) & 31;
+    return r;
+}
+
+enum LwField {
+    LF_FAC00, LF_FAC01, LF_FAC10, LF_FAC11,
+    LF_COLH2O, LF_COLCO2, LF_COLO3, LF_COLN2O, LF_COLCO, LF_COLCH4, LF_COLO2, LF_COLBRD,
+    LF_SELFFAC, LF_SELFFRAC, LF_FORFAC, LF_FORFRAC, LF_MINORFRAC, LF_SCALEMINOR, LF_SCALEMINORN2,
+    LF_COLDRY, LF_PAVEL, LF_WX1, LF_WX2, LF_WX3, LF_WX4,
+    LF_COUNT
+};
+
+// sections of one band's table; values are row offsets inside the band table (-1 = absent)
+enum LwSec {
+    LS_ABSA, LS_ABSB, LS_SELF, LS_FOR, LS_FRACA, LS_FRACB,
+    LS_MA1, LS_MA2, LS_MA3, LS_MB1, LS_MB2, LS_X1, LS_X2, LS_GSCALE,
+    LS_COUNT
+};
+
+struct LwBand {
+    int ng;            // reduced g-points in the band
+    int g0;            // first g-point (0-based) in the 140-vector
+    int base;          // element offset of the band table in LwTables::tab
+    int sec[LS_COUNT]; // row offsets
+    double refrat[5];  // planck_a, planck_b, m_a, m_b, m_a3 (band-specific chi_mls ratios)
+};
+
+struct LwConst {
+    LwBand band[NBNDLW];
+    double preflog[59], tref[59];
+    double chi_mls[7 * 59];                 // (7,59) column-major
+    double rat_h2oco2[59], rat_h2oo3[59], rat_h2on2o[59], rat_h2och4[59], rat_n2oco2[59], rat_o3co2[59];
+    double delwave[NBNDLW];
+    double a0[NBNDLW], a1[NBNDLW], a2[NBNDLW];
+    double heatfac, fluxfac, oneminus, bpade;
+};
+
+struct LwTables {             // device pointers
+    const double *tab;        // all band tables, [row][ig]
+    const double *totplnk;    // (181,16) column-major as in the Fortran
+    const double *exptfn;     // interleaved {exp_tbl[i], tfn_tbl[i]}, i = 0..NTBL
+};
+
+struct LwIn {                 // interface arrays of the current pass (device pointers, may be offset)
+    int ld;                   // leading dimension of the interface arrays (= ncol of the call)
+    const double *play, *plev, *tlay, *tlev, *tsfc;
+    const double *h2o, *o3, *co2, *ch4, *n2o, *o2, *cfc11, *cfc12, *cfc22, *ccl4;
+    const double *emis, *tauaer;  // emis (ld,16); tauaer (ld,nlay,16); either may be null
+};
+
+struct LwOut {
+    int ld;
+    double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+};
+
+struct LwWork {
+    int nc, nlay;
+    uint32_t *idx;            // [lay][col]
+    int *laytrop;             // [col]
+    double *f;                // LF_COUNT fields, each [lay][col]
+    double *secdiff;          // [col][16]
+    double *planklay;         // [col][lay][16]
+    double *planklev;         // [col][lay+1][16]  (level 0 = surface)
+    double *plankbnd;         // [col][16]
+    double *taug, *fracs;     // [col][lay][140]
+    __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
+    __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
+};
+
+// ------------------------------------------------------------------------------------ SW
+// packed: jp:6 | jt:3 | jt1:3 | indself:4 | indfor:2
+__host__ __device__ inline uint32_t sw_pack(int jp, int jt, int jt1, int inds, int indf)
+{
+    return (uint32_t)jp | ((uint32_t)jt << 6) | ((uint32_t)jt1 << 9) | ((uint32_t)inds << 12) | ((uint32_t)indf << 16);
+}
+
+enum SwField {
+    SF_FAC00, SF_FAC01, SF_FAC10, SF_FAC11,
+    SF_COLH2O, SF_COLCO2, SF_COLO3, SF_COLCH4, SF_COLO2, SF_COLMOL, SF_COLN2O,
+    SF_SELFFAC, SF_SELFFRAC, SF_FORFAC, SF_FORFRAC,
+    SF_COUNT
+};
+
+enum SwSec {
+    SS_ABSA, SS_ABSB, SS_SELF, SS_FOR, SS_SFLUX, SS_RAYL, SS_RAYLB, SS_X1, SS_X2,
+    SS_COUNT
+};
+
+struct SwBand {
+    int ng, g0, base;
+    int sec[SS_COUNT];
+    int nsflux;        // number of sfluxref rows (1, 5 or 9)
+    int nrayl;         // number of rayl rows (1 or 9)
+};
+
+struct SwConst {
+    SwBand band[NBNDSW];
+    double preflog[59], tref[59];
+    double heatfac, oneminus, bpade;
+};
+
+struct SwTables {
+    const double *tab;
+    const double *exptbl;     // interleaved {exp_tbl[i], 1/exp_tbl[i]}, i = 0..NTBL
+};
+
+struct SwIn {
+    int ld;
+    const double *play, *plev, *tlay, *tlev, *tsfc;
+    const double *h2o, *o3, *co2, *ch4, *n2o, *o2;
+    const double *asdir, *asdif, *aldir, *aldif, *coszen;
+    double adjflux;           // adjflx * scon / rrsw_scon (same for all bands, rad.nomcica:953-972)
+};
+
+struct SwOut {
+    int ld;
+    double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+};
+
+struct SwWork {
+    int nc, nlay;
+    uint32_t *idx;            // [lay][col]
+    int *laytrop;             // [col]
+    int *laysolfr;            // [col][14]: layer (1-based) whose eta selects the solar source; 0 = never written
+    double *f;                // SF_COUNT fields, each [lay][col]
+    double *taug, *taur;      // [col][lay][112]
+    double *sfluxzen;         // [col][112]
+    __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
+    __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
+};
+
+// kernel launchers (defined in lw_kernels.cu / sw_kernels.cu); each returns the number of launches
+int lw_upload_const(const LwConst &c);
+int sw_upload_const(const SwConst &c);
+// `cap` (optional): device buffer of 2*nc*nlay*140 doubles receiving a copy of taug|fracs before the solver
+// overwrites them in place (test hook).
+int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, double *cap);
+int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s);
+
+} // namespace rrtmg

@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's RRTMG interface over the C ABI of librrtmg_b200.so.
+
+Same procedure names, argument order and meaning as the Fortran module procedures MiMA calls:
+
+    rrtmg_lw_ini(cpdair)   LW/src/rrtmg_lw_init.f90:28            (physics_driver.f90:577)
+    rrtmg_sw_ini(cpdair)   SW/src/rrtmg_sw_init.f90:28            (physics_driver.f90:578)
+    rrtmg_lw(...)          LW/src/rrtmg_lw_rad.nomcica.f90:80-89  (rrtm_radiation.f90:722-748)
+    rrtmg_sw(...)          SW/src/rrtmg_sw_rad.nomcica.f90:78-88  (rrtm_radiation.f90:686-712)
+
+The Fortran intent(out) dummies are returned instead of passed.  Arrays are numpy float64; anything not
+already Fortran-ordered is converted.  There is no CPU path: if the shared library or a CUDA device is
+missing the calls raise.  Error codes of the C ABI become exceptions (RRTMGError); the reference's
+`stop 'PARTIAL CLOUD NOT ALLOWED'` and its unbuilt branches surface the same way.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+CP_AIR = 287.04 / (2.0 / 7.0)      # RDGAS/KAPPA (src/shared/constants/constants.f90:64-67)
+NBNDLW, NGPTLW, NBNDSW, NGPTSW = 16, 140, 14, 112
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+_dp = C.POINTER(C.c_double)
+_ERR = {1: "not initialised", 2: "unsupported option", 3: "PARTIAL CLOUD NOT ALLOWED", 4: "bad argument",
+        5: "CUDA error", 6: "coefficient tables"}
+
+
+class RRTMGError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rrtmg_b200 error {code} ({_ERR.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load librrtmg_b200.so (built in-tree by mima_b200.build).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            raise RRTMGError(5, f"{path} is missing: run `python -m mima_b200.build` (nvcc) first; there is no fallback")
+        L = C.CDLL(path)
+        L.rrtmg_b200_last_error.restype = C.c_char_p
+        L.rrtmg_b200_launch_count.restype = C.c_long
+        L.rrtmg_b200_get_table.restype = C.c_long
+        L.rrtmg_b200_get_table.argtypes = [C.c_char_p, _dp, C.c_long]
+        L.rrtmg_b200_get_stage.restype = C.c_long
+        L.rrtmg_b200_get_stage.argtypes = [C.c_char_p, _dp, C.c_long]
+        L.rrtmg_b200_set_table.argtypes = [C.c_char_p, _dp, C.c_int, C.POINTER(C.c_int)]
+        L.rrtmg_b200_load_tables.argtypes = [C.c_char_p]
+        L.rrtmg_b200_lw_init.argtypes = [C.c_double]
+        L.rrtmg_b200_sw_init.argtypes = [C.c_double]
+        L.rrtmg_b200_set_option.argtypes = [C.c_char_p, C.c_long]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc:
+        raise RRTMGError(rc, lib().rrtmg_b200_last_error().decode())
+
+
+def set_device(local_rank: int = 0):
+    _check(lib().rrtmg_b200_set_device(int(local_rank)))
+
+
+def load_tables(path: str):
+    _check(lib().rrtmg_b200_load_tables(path.encode()))
+
+
+def set_table(name: str, array):
+    a = np.asfortranarray(array, dtype=np.float64)
+    dims = (C.c_int * a.ndim)(*a.shape)
+    _check(lib().rrtmg_b200_set_table(name.encode(), a.ctypes.data_as(_dp), a.ndim, dims))
+
+
+def set_option(key: str, value: int):
+    _check(lib().rrtmg_b200_set_option(key.encode(), int(value)))
+
+
+def launch_count() -> int:
+    return int(lib().rrtmg_b200_launch_count())
+
+
+_loaded = set()
+
+
+def _default_tables(kind: str):
+    files = {"lw": ["rrtmg_lw_ref.bin", "rrtmg_lw_kg_synth.bin"], "sw": ["rrtmg_sw_kg.bin"]}[kind]
+    for f in files:
+        if f not in _loaded:
+            load_tables(os.path.join(DATA_DIR, f))
+            _loaded.add(f)
+
+
+def rrtmg_lw_ini(cpdair: float = CP_AIR, *, default_tables: bool = True):
+    """rrtmg_lw_ini(cpdair).  With default_tables the packaged blobs are registered first (the LW
+    k-distribution blob is SYNTHETIC -- the real rrtmg_lw_k_g.f90 is not in the reference checkout;
+    register real arrays with set_table()/load_tables() and pass default_tables=False to use them)."""
+    if default_tables:
+        _default_tables("lw")
+    _check(lib().rrtmg_b200_lw_init(float(cpdair)))
+
+
+def rrtmg_sw_ini(cpdair: float = CP_AIR, *, default_tables: bool = True):
+    if default_tables:
+        _default_tables("sw")
+    _check(lib().rrtmg_b200_sw_init(float(cpdair)))
+
+
+def finalize():
+    _check(lib().rrtmg_b200_finalize())
+    _loaded.clear()
+
+
+def get_table(name: str) -> np.ndarray:
+    n = lib().rrtmg_b200_get_table(name.encode(), None, 0)
+    if n < 0:
+        raise KeyError(name)
+    out = np.empty(n)
+    lib().rrtmg_b200_get_table(name.encode(), out.ctypes.data_as(_dp), n)
+    return out
+
+
+def get_stage(name: str, shape) -> np.ndarray:
+    n = lib().rrtmg_b200_get_stage(name.encode(), None, 0)
+    if n < 0:
+        raise KeyError(f"stage {name} unavailable (single-pass calls only; lw.taug/fracs need capture_stages)")
+    out = np.empty(n)
+    lib().rrtmg_b200_get_stage(name.encode(), out.ctypes.data_as(_dp), n)
+    return out.reshape(shape, order="F")
+
+
+def _in(a, shape, name, optional=False):
+    if a is None:
+        if optional:
+            return None, None
+        raise RRTMGError(4, f"{name} is required")
+    arr = np.asfortranarray(a, dtype=np.float64)
+    if arr.shape != tuple(shape):
+        raise RRTMGError(4, f"{name}: expected shape {tuple(shape)}, got {arr.shape}")
+    return arr, arr.ctypes.data_as(_dp)
+
+
+def rrtmg_lw(ncol, nlay, icld, idrv,
+             play, plev, tlay, tlev, tsfc,
+             h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+             cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis,
+             inflglw=0, iceflglw=0, liqflglw=0, cldfr=None,
+             taucld=None, cicewp=None, cliqwp=None, reice=None, reliq=None,
+             tauaer=None):
+    """Returns (uflx, dflx, hr, uflxc, dflxc, hrc); fluxes (ncol, nlay+1) W/m2, heating (ncol, nlay) K/day.
+    ch4vmr..ccl4vmr, emis, tauaer may be None (zeros / emissivity 1).  Cloud arrays are ignored (icld=0)."""
+    L = (ncol, nlay)
+    V = (ncol, nlay + 1)
+    keep = []
+    ptrs = []
+    for a, shp, nm, opt in ((play, L, "play", False), (plev, V, "plev", False), (tlay, L, "tlay", False),
+                            (tlev, V, "tlev", False), (tsfc, (ncol,), "tsfc", False),
+                            (h2ovmr, L, "h2ovmr", False), (o3vmr, L, "o3vmr", False), (co2vmr, L, "co2vmr", False),
+                            (ch4vmr, L, "ch4vmr", True), (n2ovmr, L, "n2ovmr", True), (o2vmr, L, "o2vmr", True),
+                            (cfc11vmr, L, "cfc11vmr", True), (cfc12vmr, L, "cfc12vmr", True),
+                            (cfc22vmr, L, "cfc22vmr", True), (ccl4vmr, L, "ccl4vmr", True),
+                            (emis, (ncol, NBNDLW), "emis", True)):
+        arr, p = _in(a, shp, nm, opt)
+        keep.append(arr)
+        ptrs.append(p)
+    taer, ptaer = _in(tauaer, (ncol, nlay, NBNDLW), "tauaer", True)
+    out = [np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F"),
+           np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
+    icld_c = C.c_int(int(icld))
+    rc = lib().rrtmg_b200_lw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.c_int(int(idrv)), *ptrs,
+                             C.c_int(inflglw), C.c_int(iceflglw), C.c_int(liqflglw), None, None, None, None, None, None,
+                             ptaer, *[o.ctypes.data_as(_dp) for o in out], None, None)
+    _check(rc)
+    return tuple(out)
+
+
+def rrtmg_sw(ncol, nlay, icld, iaer,
+             play, plev, tlay, tlev, tsfc,
+             h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+             asdir, asdif, aldir, aldif,
+             coszen, adjes, dyofyr, scon,
+             inflgsw=0, iceflgsw=0, liqflgsw=0, cldfr=None,
+             taucld=None, ssacld=None, asmcld=None, fsfcld=None,
+             cicewp=None, cliqwp=None, reice=None, reliq=None,
+             tauaer=None, ssaaer=None, asmaer=None, ecaer=None):
+    """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc)."""
+    L = (ncol, nlay)
+    V = (ncol, nlay + 1)
+    keep = []
+    ptrs = []
+    for a, shp, nm, opt in ((play, L, "play", False), (plev, V, "plev", False), (tlay, L, "tlay", False),
+                            (tlev, V, "tlev", False), (tsfc, (ncol,), "tsfc", False),
+                            (h2ovmr, L, "h2ovmr", False), (o3vmr, L, "o3vmr", False), (co2vmr, L, "co2vmr", False),
+                            (ch4vmr, L, "ch4vmr", True), (n2ovmr, L, "n2ovmr", True), (o2vmr, L, "o2vmr", True),
+                            (asdir, (ncol,), "asdir", False), (asdif, (ncol,), "asdif", False),
+                            (aldir, (ncol,), "aldir", False), (aldif, (ncol,), "aldif", False),
+                            (coszen, (ncol,), "coszen", False)):
+        arr, p = _in(a, shp, nm, opt)
+        keep.append(arr)
+        ptrs.append(p)
+    out = [np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F"),
+           np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
+    icld_c, iaer_c = C.c_int(int(icld)), C.c_int(int(iaer))
+    rc = lib().rrtmg_b200_sw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.byref(iaer_c), *ptrs,
+                             C.c_double(float(adjes)), C.c_int(int(dyofyr)), C.c_double(float(scon)),
+                             C.c_int(inflgsw), C.c_int(iceflgsw), C.c_int(liqflgsw),
+                             None, None, None, None, None, None, None, None, None, None, None, None, None,
+                             *[o.ctypes.data_as(_dp) for o in out])
+    _check(rc)
+    return tuple(out)
+
+
+# ---- convenience over a Columns batch (mima_b200.columns) ---------------------------------------------
+def _opt(a):
+    """MiMA passes literal zeros for the secondary gases by default; forward None so the ABI skips them."""
+    return None if (a is None or not np.any(a)) else a
+
+
+def lw_from_columns(c, tauaer=None):
+    return rrtmg_lw(c.ncol, c.nlay, 0, 0, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
+                    _opt(c.ch4), _opt(c.n2o), _opt(c.o2), _opt(c.cfc11), _opt(c.cfc12), _opt(c.cfc22), _opt(c.ccl4),
+                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer)
+
+
+def sw_from_columns(c):
+    return rrtmg_sw(c.ncol, c.nlay, 0, 0, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
+                    _opt(c.ch4), _opt(c.n2o), _opt(c.o2), c.albedo, c.albedo, c.albedo, c.albedo,
+                    c.coszen, c.adjes, c.dyofyr, c.scon)
