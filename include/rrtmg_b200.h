@@ -163,8 +163,13 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
 int rrtmg_b200_set_chunk(int ncol_per_pass);
 
 /* Generic options: "chunk" (as above), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
- * LW solver otherwise overwrites in place; test hook). */
+ * LW solver otherwise overwrites in place; test hook), "kernel_timing" (see rrtmg_b200_kernel_times). */
 int rrtmg_b200_set_option(const char *key, long value);
+
+/* With option "kernel_timing" = 1 every kernel launch is bracketed by CUDA events on its stream.  Returns the
+ * accumulated device time [ms] and launch count per kernel since the last reset, in the order
+ * lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver (arrays of 6). */
+int rrtmg_b200_kernel_times(double *ms, long *launches, int reset);
 
 #ifdef __cplusplus
 }

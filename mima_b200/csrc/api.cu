@@ -66,6 +66,35 @@ struct State {
 };
 State G;
 
+// ---- per-kernel event timing (off by default; bench.py turns it on for the roofline numbers)
+struct KTimer {
+    bool on = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[K_COUNT] = {};
+    long n[K_COUNT] = {};
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void collect()
+    {
+        for (Rec &r : recs) {
+            cudaEventSynchronize(r.b);
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.id] += t; n[r.id] += 1; }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+};
+KTimer KT;
+
 int fail(int code, const std::string &msg)
 {
     G.err = msg;
@@ -581,8 +610,36 @@ struct Stager {
 
 } // namespace
 
+namespace rrtmg {
+void ktimer_begin(int id, cudaStream_t s)
+{
+    if (!KT.on) return;
+    KTimer::Rec r{id, KT.get(), KT.get()};
+    cudaEventRecord(r.a, s);
+    KT.recs.push_back(r);
+}
+void ktimer_end(cudaStream_t s)
+{
+    if (!KT.on) return;
+    cudaEventRecord(KT.recs.back().b, s);
+}
+} // namespace rrtmg
+
 // =================================================================================================
 extern "C" {
+
+/* Accumulated device time [ms] and launch count per kernel since the last reset (needs option
+ * "kernel_timing" = 1).  Order: lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver. */
+int rrtmg_b200_kernel_times(double *ms, long *launches, int reset)
+{
+    KT.collect();
+    for (int i = 0; i < K_COUNT; ++i) {
+        if (ms) ms[i] = KT.ms[i];
+        if (launches) launches[i] = KT.n[i];
+        if (reset) { KT.ms[i] = 0.0; KT.n[i] = 0; }
+    }
+    return RRTMG_B200_OK;
+}
 
 const char *rrtmg_b200_last_error(void) { return G.err.c_str(); }
 long rrtmg_b200_launch_count(void) { return G.launches; }
@@ -912,6 +969,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     const std::string k(key ? key : "");
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
+    if (k == "kernel_timing") { KT.collect(); KT.on = value != 0; return RRTMG_B200_OK; }
     return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "unknown option " + k);
 }
 

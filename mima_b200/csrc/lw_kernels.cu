@@ -622,7 +622,10 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             frac_eta(pw, B, LS_FRACA, p.colh2o, B.refrat[0], p.colch4, 8.);
         } else {
-            key4(pw, B, LS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colch4, p);
+            // The reference sets nspb(16) = 0 (rrtmg_lw_init.f90:209), so taugb16's upper-atmosphere indices
+            // ind0 = (...)*nspb(16) + 1 and ind1 collapse to row 1 for every layer (taumol.f90:3135-3136).
+            // Reproduced as is: results must match the reference, not the intent.
+            key4(pw, B, LS_ABSB, IND0B(0) + 1, IND1B(0) + 1, p.colch4, p);
             frac_const(pw, B, LS_FRACB);
         }
     } break;
@@ -839,15 +842,21 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
 
 int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, double *cap)
 {
+    ktimer_begin(K_LW_PREP, s);
     lw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(t, in, w);
+    ktimer_end(s);
     dim3 grid((w.nc + TP - 1) / TP, w.nlay);
+    ktimer_begin(K_LW_TAUMOL, s);
     lw_taumol_kernel<<<grid, TP, 0, s>>>(t, w);
+    ktimer_end(s);
     if (cap) {
         const size_t n = (size_t)w.nc * w.nlay * NGPTLW;
         cudaMemcpyAsync(cap, w.taug, n * 8, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(cap + n, w.fracs, n * 8, cudaMemcpyDeviceToDevice, s);
     }
+    ktimer_begin(K_LW_RTRN, s);
     lw_rtrn_kernel<<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w);
+    ktimer_end(s);
     return 3;
 }
 

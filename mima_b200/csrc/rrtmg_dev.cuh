@@ -164,6 +164,11 @@ struct SwWork {
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
 
+// optional per-kernel CUDA-event timing (api.cu); ids: 0 lw_prep, 1 lw_taumol, 2 lw_rtrn, 3 sw_prep, 4 sw_taumol, 5 sw_solver
+enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_COUNT };
+void ktimer_begin(int id, cudaStream_t s);
+void ktimer_end(cudaStream_t s);
+
 // kernel launchers (defined in lw_kernels.cu / sw_kernels.cu); each returns the number of launches
 int lw_upload_const(const LwConst &c);
 int sw_upload_const(const SwConst &c);

@@ -696,11 +696,17 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
 
 int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
+    ktimer_begin(K_SW_PREP, s);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
+    ktimer_end(s);
     dim3 grid((w.nc + TP - 1) / TP, w.nlay);
+    ktimer_begin(K_SW_TAUMOL, s);
     sw_taumol_kernel<<<grid, TP, 0, s>>>(t, w);
+    ktimer_end(s);
+    ktimer_begin(K_SW_SOLVER, s);
     if (w.nlay <= 64) sw_solver_kernel<64><<<w.nc, SV_THREADS, 0, s>>>(t, in, out, w);
     else sw_solver_kernel<MAXLAY><<<w.nc, SV_THREADS, 0, s>>>(t, in, out, w);
+    ktimer_end(s);
     return 3;
 }
 

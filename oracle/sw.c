@@ -104,6 +104,11 @@ static void setcoef_sw(swcol_t *c)
     c->laytrop = 0;
     c->layswtch = 0;
     c->laylow = 0;
+    /* taumol reads jp(lay-1) at lay = laytrop+1 and jp(lay+1) at lay = laytrop (taumol.f90:321, :481): outside
+     * 1..nlayers only when laytrop is 0 or nlayers, where the Fortran reads undefined storage.  Defined as 0
+     * here (the product does the same) so that the oracle is deterministic. */
+    c->jp[0] = 0;
+    c->jp[nlayers + 1] = 0;
     for (int lay = 1; lay <= nlayers; ++lay) {
         plog = log(c->pavel[lay]);
         c->jp[lay] = (int)(36. - 5 * (plog + 0.04));

@@ -395,6 +395,18 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
         K->rayl = ra ? ra->data[0] : 0.0;
         if (!K->sfluxref) return 6;
     }
+    /* export the lookup tables through the same registry (copies, so finalize can free them) */
+    {
+        const struct { const char *name; const double *src; } lut[3] = {
+            {"lw.exp_tbl", S->exp_tbl}, {"lw.tfn_tbl", S->tfn_tbl}, {"sw.exp_tbl", S->sw_exp_tbl}};
+        for (int i = 0; i < 3; ++i) {
+            reg_t *r = &g_reg[g_nreg++];
+            snprintf(r->name, sizeof r->name, "%s", lut[i].name);
+            r->n = ORC_NTBL + 1;
+            r->data = (double *)malloc(sizeof(double) * (ORC_NTBL + 1));
+            memcpy(r->data, lut[i].src, sizeof(double) * (ORC_NTBL + 1));
+        }
+    }
     orc_blob_free(&bref);
     orc_blob_free(&blw);
     orc_blob_free(&bsw);

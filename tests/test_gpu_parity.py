@@ -1,0 +1,217 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(mima_b200.rrtmg -> librrtmg_b200.so); the oracle is only the checker.
+
+Tolerances (BASELINE.json north_star): fluxes 1e-6 relative, heating rates 1e-4 K/day.  Integer/index work
+(jp, jt, jt1, indself, indfor, indminor, laytrop, laysolfr) and the reduced coefficient tables must be
+bit-exact.  The CUDA kernels reproduce the oracle far more tightly than the tolerance; the tighter bounds
+asserted below (1e-10 on optical depths, 1e-9 on fluxes) guard against regressions hiding in the slack.
+"""
+import numpy as np
+import pytest
+
+from mima_b200.columns import make_columns
+
+pytestmark = pytest.mark.gpu
+
+FLUX_RTOL = 1e-6       # north_star
+HR_ATOL = 1e-4         # K/day, north_star
+TIGHT = 1e-9
+
+LW_OUT = ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")
+SW_OUT = ("swuflx", "swdflx", "swhr", "swuflxc", "swdflxc", "swhrc")
+LW_NGS = [0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138, 140]
+
+
+def _check_outputs(got, ref, names, tight=True):
+    for g, n in zip(got, names):
+        o = ref[n]
+        assert np.isfinite(g).all(), n
+        if "hr" in n:
+            assert np.max(np.abs(g - o)) < HR_ATOL, (n, float(np.max(np.abs(g - o))))
+            if tight:
+                assert np.max(np.abs(g - o)) < 1e-7, (n, float(np.max(np.abs(g - o))))
+        else:
+            scale = np.maximum(np.abs(o), 1e-6 * np.abs(o).max())
+            r = np.max(np.abs(g - o) / scale)
+            assert r < FLUX_RTOL, (n, float(r))
+            if tight:
+                assert r < TIGHT, (n, float(r))
+
+
+def _relerr(g, o):
+    d = np.abs(g - o)
+    return np.where(o != 0, d / np.maximum(np.abs(o), 1e-300), d)
+
+
+@pytest.fixture(scope="module")
+def t42(oracle):
+    cols = make_columns("T42L40", nlon=64, nlat=16)
+    return cols, oracle.rrtmg_lw(cols, stages=True), oracle.rrtmg_sw(cols, stages=True)
+
+
+def test_reduced_tables_bit_exact(gpu, oracle):
+    """rrtmg_lw_ini / rrtmg_sw_ini: the 16 -> ngc reduction (cmbgbNN) and lookup tables, bit for bit."""
+    names = []
+    for b in range(1, 17):
+        names += [f"lw{b:02d}.absa", f"lw{b:02d}.selfref", f"lw{b:02d}.forref", f"lw{b:02d}.fracrefa"]
+    names += ["lw01.ka_mn2", "lw01.kb_mn2", "lw03.absb", "lw03.ka_mn2o", "lw03.kb_mn2o", "lw03.fracrefb", "lw05.ka_mo3",
+              "lw05.ccl4", "lw06.ka_mco2", "lw06.cfc11adj", "lw06.cfc12", "lw07.kb_mco2", "lw08.ka_mo3", "lw08.cfc22adj",
+              "lw09.kb_mn2o", "lw11.ka_mo2", "lw13.ka_mco", "lw13.kb_mo3", "lw15.ka_mn2", "lw16.absb"]
+    for b in range(16, 30):
+        names += [f"sw{b}.sfluxref"]
+    names += ["sw16.absa", "sw16.absb", "sw17.absb", "sw17.forref", "sw20.absch4", "sw22.selfref", "sw23.rayl",
+              "sw24.rayla", "sw24.raylb", "sw24.abso3a", "sw25.abso3b", "sw27.absb", "sw28.absa", "sw29.absh2o", "sw29.absco2",
+              "lw.exp_tbl", "lw.tfn_tbl", "sw.exp_tbl"]
+    for n in names:
+        a, b = gpu.get_table(n), oracle.table(n)
+        assert a.shape == b.shape and np.array_equal(a, b), n
+
+
+def test_lw_stages(gpu, t42):
+    cols, olw, _ = t42
+    gpu.set_option("capture_stages", 1)
+    gpu.set_option("chunk", 1 << 20)
+    try:
+        got = gpu.lw_from_columns(cols)
+        nc, nl = cols.ncol, cols.nlay
+        st = olw["stages"]
+        assert np.array_equal(gpu.get_stage("lw.laytrop", (nc,)), st["laytrop"])
+        low = np.arange(1, nl + 1)[None, :] <= st["laytrop"][:, None]
+        for f in ("jp", "jt", "jt1", "indfor", "indminor"):
+            assert np.array_equal(gpu.get_stage("lw." + f, (nc, nl)), st[f]), f
+        assert np.array_equal(gpu.get_stage("lw.indself", (nc, nl))[low], st["indself"][low])
+        for f in ("colh2o", "colco2", "colo3", "coln2o", "colco", "colch4", "colo2", "colbrd", "selffac", "forfac",
+                  "forfrac", "minorfrac", "scaleminor", "scaleminorn2", "coldry"):
+            assert np.array_equal(gpu.get_stage("lw." + f, (nc, nl)), st[f]), f      # no transcendental involved
+        for f in ("fac00", "fac01", "fac10", "fac11"):                               # depend on log(p): ulp-level
+            assert np.allclose(gpu.get_stage("lw." + f, (nc, nl)), st[f], rtol=1e-11, atol=1e-14), f
+        for f, shp in (("planklay", (nc, nl, 16)), ("planklev", (nc, nl + 1, 16)), ("plankbnd", (nc, 16))):
+            assert np.array_equal(gpu.get_stage("lw." + f, shp), st[f]), f
+        for f in ("taug", "fracs"):
+            g = gpu.get_stage("lw." + f, (nc, nl, 140))
+            o = st[f]
+            scale = np.maximum(np.abs(o), 1e-12 * np.abs(o).max())
+            for b in range(16):
+                sl = slice(LW_NGS[b], LW_NGS[b + 1])
+                r = np.max(np.abs(g[:, :, sl] - o[:, :, sl]) / scale[:, :, sl])
+                assert r < 1e-10, (f, "band", b + 1, float(r))
+        _check_outputs(got, olw, LW_OUT)
+    finally:
+        gpu.set_option("capture_stages", 0)
+        gpu.set_option("chunk", 0)
+
+
+def test_sw_stages(gpu, t42):
+    cols, _, osw = t42
+    gpu.set_option("chunk", 1 << 20)
+    try:
+        got = gpu.sw_from_columns(cols)
+        nc, nl = cols.ncol, cols.nlay
+        st = osw["stages"]
+        assert np.array_equal(gpu.get_stage("sw.laytrop", (nc,)), st["laytrop"])
+        for f in ("jp", "jt", "jt1", "indfor", "indself"):
+            assert np.array_equal(gpu.get_stage("sw." + f, (nc, nl)), st[f]), f
+        for f in ("colh2o", "colco2", "colo3", "colch4", "colo2", "colmol", "selffac", "selffrac", "forfac", "forfrac"):
+            assert np.array_equal(gpu.get_stage("sw." + f, (nc, nl)), st[f]), f
+        for f in ("taug", "taur"):
+            g = gpu.get_stage("sw." + f, (nc, nl, 112))
+            o = st[f]
+            scale = np.maximum(np.abs(o), 1e-12 * np.abs(o).max())
+            assert np.max(np.abs(g - o) / scale) < 1e-10, f
+        assert np.allclose(gpu.get_stage("sw.sfluxzen", (nc, 112)), st["sfluxzen"], rtol=1e-14)
+        _check_outputs(got, osw, SW_OUT)
+    finally:
+        gpu.set_option("chunk", 0)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(resolution="T42L40", nlon=128, nlat=8, night=True),                                        # config 1 slice, with night
+    dict(resolution="T42L40", nlon=64, nlat=16, co2_ppmv=1560.0, ozone="file", secondary_gases=True),  # config 4
+    dict(resolution="T170L60", nlon=64, nlat=8),                                                    # L60
+    dict(resolution="T341L80", nlon=32, nlat=8, secondary_gases=True),                              # L80 (LMAX=128 path)
+])
+def test_end_to_end_parity(gpu, oracle, kw):
+    cols = make_columns(**kw)
+    _check_outputs(gpu.lw_from_columns(cols), oracle.rrtmg_lw(cols), LW_OUT)
+    _check_outputs(gpu.sw_from_columns(cols), oracle.rrtmg_sw(cols), SW_OUT)
+
+
+def test_emissivity_and_aerosol_inputs(gpu, oracle):
+    """Spectrally varying emissivity (reflection term, rtrnmr.f90:628-636) and a non-zero LW tauaer
+    (iaer = 10 is forced, rad.nomcica:442, :514-519)."""
+    cols = make_columns("T42L40", nlon=32, nlat=4)
+    rng = np.random.default_rng(7)
+    cols.emis = np.asfortranarray(rng.uniform(0.85, 1.0, (cols.ncol, 16)))
+    taer = np.asfortranarray(rng.uniform(0.0, 0.05, (cols.ncol, cols.nlay, 16)))
+    _check_outputs(gpu.lw_from_columns(cols, tauaer=taer), oracle.rrtmg_lw(cols, tauaer=taer), LW_OUT)
+
+
+def test_ragged_sizes_and_chunking(gpu, oracle):
+    """ncol not a multiple of any tile, single column, and a chunk smaller than the batch."""
+    base = make_columns("T42L40", nlon=64, nlat=4, night=True)
+    for n in (1, 3, 129, 200):
+        c = base.take(np.arange(n))
+        _check_outputs(gpu.lw_from_columns(c), oracle.rrtmg_lw(c), LW_OUT)
+        _check_outputs(gpu.sw_from_columns(c), oracle.rrtmg_sw(c), SW_OUT)
+    gpu.set_option("chunk", 50)
+    try:
+        c = base.take(np.arange(173))
+        _check_outputs(gpu.lw_from_columns(c), oracle.rrtmg_lw(c), LW_OUT)
+        _check_outputs(gpu.sw_from_columns(c), oracle.rrtmg_sw(c), SW_OUT)
+    finally:
+        gpu.set_option("chunk", 0)
+    # empty batch is a no-op
+    e = base.take(np.arange(0))
+    assert gpu.lw_from_columns(e)[0].shape == (0, 41)
+
+
+def test_night_columns_and_clear_equals_total(gpu):
+    c = make_columns("T42L40", nlon=64, nlat=4, night=True)
+    sw = gpu.sw_from_columns(c)
+    night = c.coszen < 1e-10
+    assert night.any()
+    for a in sw:
+        assert (a[night] == 0).all()
+    assert np.array_equal(sw[0], sw[3]) and np.array_equal(sw[1], sw[4]) and np.array_equal(sw[2], sw[5])
+    lw = gpu.lw_from_columns(c)
+    assert np.array_equal(lw[0], lw[3]) and np.array_equal(lw[2], lw[5])
+
+
+def test_unsupported_options_fail_loudly(gpu):
+    c = make_columns("T42L40", nlon=4, nlat=2)
+    args = (c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2, None, None, None)
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_lw(c.ncol, c.nlay, 1, 0, *args, None, None, None, None, None)
+    assert e.value.code == 2
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_lw(c.ncol, c.nlay, 0, 1, *args, None, None, None, None, None)
+    assert e.value.code == 2
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_sw(c.ncol, c.nlay, 0, 10, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
+    assert e.value.code == 2
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_lw(c.ncol, 200, 0, 0, *args, None, None, None, None, None)
+    assert e.value.code == 4
+
+
+def test_full_size_properties_t85(gpu):
+    """BASELINE config 2 at full size (32768 x 40), checked through size-independent properties: shard
+    invariance (any split of the batch gives bit-identical columns), heating = flux divergence, TOA
+    insolation = S0 cos(z), surface reflection, clear == total."""
+    c = make_columns("T85L40")
+    lw = gpu.lw_from_columns(c)
+    sw = gpu.sw_from_columns(c)
+    for a in lw + sw:
+        assert np.isfinite(a).all()
+    heatfac = 9.8066 * 86400.0 / (1004.64 * 100.0)
+    fnet = lw[0] - lw[1]
+    hr = heatfac * (fnet[:, :-1] - fnet[:, 1:]) / (c.plev[:, :-1] - c.plev[:, 1:])
+    assert np.allclose(lw[2], hr, rtol=1e-10, atol=1e-10)
+    assert np.allclose(sw[1][:, -1], c.scon * c.coszen, rtol=2e-5)
+    assert np.allclose(sw[0][:, 0], c.albedo * sw[1][:, 0], rtol=1e-9)
+    # shard invariance: rows 32..64 computed alone equal the same rows of the full call
+    blk = c.rows(32, 64)
+    lwb, swb = gpu.lw_from_columns(blk), gpu.sw_from_columns(blk)
+    s = slice(32 * c.nlon, 64 * c.nlon)
+    for a, b in zip(lw + sw, lwb + swb):
+        assert np.array_equal(a[s], b)

@@ -1,0 +1,129 @@
+"""Known-answer checks that pin the oracle's data path to the reference where the reference allows it.
+
+The reference ships no golden flux vectors for SW and its LW golden files need the stripped k_g file, so
+the oracle is pinned through constants the reference itself states:
+  * rrsw_scon = 1368.22 W/m2 (SW/modules/parrrsw.f90:115): the reduced Kurucz solar source, as selected by
+    taumol_sw for a standard column, must sum to it;
+  * the Planck table totplnk (LW/src/rrtmg_lw_setcoef.f90:586-1990) integrates to sigma*T^4 over 10-3250 cm-1;
+  * Gaussian weights wt sum to 1 (rrtmg_lw_init.f90:356-361);
+  * lookup-table end points (rrtmg_lw_init.f90:106-123).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from build_tables import read_blob  # noqa: E402
+
+DATA = os.path.join(ROOT, "mima_b200", "data")
+
+
+@pytest.fixture(scope="module")
+def sw_blob():
+    return read_blob(os.path.join(DATA, "rrtmg_sw_kg.bin"))
+
+
+@pytest.fixture(scope="module")
+def lw_ref():
+    return read_blob(os.path.join(DATA, "rrtmg_lw_ref.bin"))
+
+
+def test_sw_blob_shapes(sw_blob):
+    # SW/modules/rrsw_kgNN.f90 declarations
+    assert sw_blob["sw16.kao"].shape == (9, 5, 13, 16)
+    assert sw_blob["sw16.kbo"].shape == (5, 47, 16)
+    assert sw_blob["sw17.kbo"].shape == (5, 5, 47, 16)
+    assert sw_blob["sw20.kao"].shape == (5, 13, 16)
+    assert sw_blob["sw16.forrefo"].shape == (3, 16) and sw_blob["sw17.forrefo"].shape == (4, 16)
+    assert sw_blob["sw24.raylao"].shape == (16, 9) and sw_blob["sw28.sfluxrefo"].shape == (16, 5)
+    for k, v in sw_blob.items():
+        assert np.isfinite(v).all(), k
+    # spot values typed from SW/src/rrtmg_sw_k_g.f90:46-53 (band 16 solar source, Rayleigh)
+    assert sw_blob["sw16.sfluxrefo"][0] == 1.92269 and sw_blob["sw16.sfluxrefo"][15] == 9.70770e-04
+    assert sw_blob["sw16.rayl"][0] == 2.91e-10
+    assert sw_blob["sw16.kao"][0, 0, 0, 0] == 0.15349e-04 and sw_blob["sw16.kao"][8, 0, 0, 0] == 0.23334e-04
+
+
+def test_solar_source_sums_to_rrsw_scon(oracle):
+    """sum_g sfluxzen == rrsw_scon (1368.22 W/m2) for a sunlit standard column: pins table parsing, the
+    cmbgb reduction (plain sums for sfluxref) and the laysolfr selection logic together."""
+    from mima_b200.columns import make_columns
+    cols = make_columns("T42L40", nlon=8, nlat=8)
+    out = oracle.rrtmg_sw(cols, stages=True)
+    s = out["stages"]["sfluxzen"].sum(axis=1)
+    assert np.allclose(s, 1368.22, rtol=2e-5), (s.min(), s.max())
+    # and the TOA downward flux is scon/rrsw_scon * sum * cosz
+    toa = out["swdflx"][:, -1]
+    assert np.allclose(toa, cols.scon / 1368.22 * s * cols.coszen, rtol=1e-12)
+
+
+def test_planck_table_matches_stefan_boltzmann(lw_ref):
+    t = lw_ref["lwref.totplnk"]
+    dw = np.array([340, 150, 130, 70, 120, 160, 100, 100, 210, 90, 320, 280, 170, 130, 220, 650.0])
+    for T in (200, 250, 300):
+        flux = np.pi * 1e4 * (t[T - 160] * dw).sum()
+        sb = 5.6704e-8 * T ** 4
+        assert 0.985 * sb < flux <= 1.0001 * sb, (T, flux, sb)
+    assert lw_ref["lwref.chi_mls"].shape == (7, 59)
+    assert np.allclose(lw_ref["lwref.preflog"], 6.96 - 0.2 * np.arange(59), atol=1e-4)
+    assert (np.diff(lw_ref["lwref.pref"]) < 0).all()
+
+
+def test_lookup_tables(oracle):
+    """rrtmg_lw_init.f90:106-123 / rrtmg_sw_init.f90:96-105: end points and the Pade mapping."""
+    ex, tf, sx = oracle.table("lw.exp_tbl"), oracle.table("lw.tfn_tbl"), oracle.table("sw.exp_tbl")
+    assert ex.size == 10001 and ex[0] == 1.0 and ex[-1] == 1e-20 and tf[0] == 0.0 and tf[-1] == 1.0
+    assert np.array_equal(ex, sx)
+    i = np.arange(1, 10000)
+    tfn = i / 10000.0
+    tau = (1.0 / 0.278) * tfn / (1.0 - tfn)
+    assert np.allclose(ex[1:-1], np.maximum(np.exp(-tau), 1e-20), rtol=1e-14)
+    assert (np.diff(ex) <= 0).all() and (np.diff(tf) >= -1e-15).all()
+    # thin limit of the Pade source weight: tfn_tbl -> tau/6
+    assert np.allclose(tf[1:10], tau[:9] / 6.0, rtol=1e-12)
+
+
+def test_planck_fractions_keep_their_sum(oracle):
+    """cmbgbN sums fracrefa/fracrefb unweighted (e.g. rrtmg_lw_init.f90:462-473): the total over g stays 1."""
+    ngc = [10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2]
+    for b in range(1, 17):
+        fa = oracle.table(f"lw{b:02d}.fracrefa").reshape((ngc[b - 1], -1), order="F")
+        assert np.allclose(fa.sum(axis=0), 1.0, rtol=1e-13), b
+
+
+def test_reduction_preserves_constants(tmp_path):
+    """A k-table that is constant over the 16 g-points must reduce to the same constant (weights are
+    normalised inside each group), and Planck fractions / solar source must keep their sum."""
+    import subprocess
+    from build_tables import write_blob
+    from oracle.pyoracle import Oracle
+    sw = dict(read_blob(os.path.join(DATA, "rrtmg_sw_kg.bin")))
+    tot = {b: sw[f"sw{b}.sfluxrefo"].sum(axis=0) for b in range(16, 30)}
+    sw = {k: np.array(v) for k, v in sw.items()}
+    sw["sw16.kao"][...] = 3.25
+    p = tmp_path / "sw.bin"
+    write_blob(str(p), sw)
+    import ctypes as C
+    o = Oracle.__new__(Oracle)
+    o.lib = C.CDLL(pyoracle_path())
+    o.lib.orc_init.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_double]
+    o.lib.orc_get_table.restype = C.c_long
+    o.lib.orc_get_table.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_double))]
+    rc = o.lib.orc_init(os.path.join(DATA, "rrtmg_lw_ref.bin").encode(), os.path.join(DATA, "rrtmg_lw_kg_synth.bin").encode(),
+                        str(p).encode(), 1004.64)
+    assert rc == 0
+    assert np.allclose(o.table("sw16.absa"), 3.25, rtol=1e-15)
+    ngc = [6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12]
+    for i, b in enumerate(range(16, 30)):
+        r = o.table(f"sw{b}.sfluxref").reshape((ngc[i], -1), order="F")
+        assert np.allclose(r.sum(axis=0), tot[b], rtol=1e-13)
+    # restore the default tables for the other tests sharing the library's global state
+    Oracle()
+
+
+def pyoracle_path():
+    from oracle import pyoracle
+    return pyoracle.build()
