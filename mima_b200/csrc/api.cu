@@ -500,7 +500,7 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay)
 
 int pick_chunk(int ncol)
 {
-    int ch = G.chunk > 0 ? G.chunk : 4096;
+    int ch = G.chunk > 0 ? G.chunk : 32768;
     return ch < ncol ? ch : ncol;
 }
 
