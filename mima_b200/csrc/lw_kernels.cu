@@ -716,16 +716,16 @@ __global__ void __launch_bounds__(TP) lw_taumol_kernel(LwTables T, LwWork w)
 // The staging fields are overwritten in place: taug -> atrans, fracs -> bbugas (needed by the up sweep).
 // =====================================================================================================
 constexpr int RT_THREADS = 160;   // 140 g-points -> 5 warps
-constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_S = 141;         // tile row stride (odd)
 
 __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
 {
-    __shared__ double s_part[RT_WARPS][MAXLAY + 1];
+    __shared__ double s_tile[16 * RT_S];
+    __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
     __shared__ double s_dn[MAXLAY + 1], s_up[MAXLAY + 1];
     const int col = blockIdx.x;
     const int nlay = w.nlay;
     const int g = threadIdx.x;
-    const int lane = g & 31, wid = g >> 5;
     const bool active = g < NGPTLW;
     const int band = active ? c_lw_ngb[g] : 0;
     const double secd = w.secdiff[(size_t)col * 16 + band];
@@ -739,11 +739,12 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
     const double *pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
     const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
 
-    // ---- downward sweep (:505-618)
+    // ---- downward sweep (:505-618); batches of 16 levels go through tile_reduce16
     double radld = 0.0;
     double plfrac1 = 0.0;
-    for (int lev = nlay; lev >= 1; --lev) {
-        double x = 0.0;
+    for (int k = 0; k < nlay; ++k) {
+        const int lev = nlay - k;
+        const int slot = k & 15;
         if (active) {
             const size_t o = (size_t)(lev - 1) * NGPTLW;
             const double plfrac = fracs[o];
@@ -761,7 +762,7 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
                 bbd = plfrac * (blay + dplankdn * odepth);
                 bbugas = plfrac * (blay + dplankup * odepth);
             } else {
-                const double tblind = odepth / (bpade + odepth);
+                const double tblind = odepth * rcp_fast(bpade + odepth);
                 const int itr = (int)(10000.0 * tblind + 0.5);
                 const double2 e = __ldg(et + itr);
                 atrans = 1. - e.x;
@@ -771,56 +772,39 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
             radld = fma(bbd - radld, atrans, radld);
             taug[o] = atrans;
             fracs[o] = bbugas;
-            x = radld * wgt;
+            s_tile[slot * RT_S + g] = radld * wgt;
             if (lev == 1) plfrac1 = plfrac;
         }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-        if (lane == 0) s_part[wid][lev - 1] = x;
-    }
-    __syncthreads();
-    for (int lev = threadIdx.x; lev < nlay; lev += RT_THREADS) {
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < RT_WARPS; ++k) sum += s_part[k][lev];
-        s_dn[lev] = sum * c_lw.fluxfac;
+        if (slot == 15 || k == nlay - 1) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (k & ~15) + threadIdx.x;
+            if (threadIdx.x < 16 && kk <= k) s_dn[nlay - 1 - kk] = sum * c_lw.fluxfac;
+        }
     }
     if (threadIdx.x == 0) s_dn[nlay] = 0.0;   // no downward flux enters at the top (drad(nlayers) = 0)
-    __syncthreads();
 
-    // ---- surface (:628-636) and upward sweep (:649-711)
+    // ---- surface (:628-636) and upward sweep (:649-711); level k = 0 is the surface
     double radlu = 0.0;
-    {
-        double x = 0.0;
+    for (int k = 0; k <= nlay; ++k) {
+        const int slot = k & 15;
         if (active) {
-            const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
-            const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
-            const double reflect = 1. - semiss;
-            radlu = rad0 + reflect * radld;
-            x = radlu * wgt;
+            if (k == 0) {
+                const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
+                const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
+                const double reflect = 1. - semiss;
+                radlu = rad0 + reflect * radld;
+            } else {
+                const size_t o = (size_t)(k - 1) * NGPTLW;
+                const double atrans = taug[o], bbugas = fracs[o];
+                radlu = fma(bbugas - radlu, atrans, radlu);
+            }
+            s_tile[slot * RT_S + g] = radlu * wgt;
         }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-        if (lane == 0) s_part[wid][0] = x;
-    }
-    for (int lev = 1; lev <= nlay; ++lev) {
-        double x = 0.0;
-        if (active) {
-            const size_t o = (size_t)(lev - 1) * NGPTLW;
-            const double atrans = taug[o], bbugas = fracs[o];
-            radlu = fma(bbugas - radlu, atrans, radlu);
-            x = radlu * wgt;
+        if (slot == 15 || k == nlay) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (k & ~15) + threadIdx.x;
+            if (threadIdx.x < 16 && kk <= k) s_up[kk] = sum * c_lw.fluxfac;
         }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-        if (lane == 0) s_part[wid][lev] = x;
-    }
-    __syncthreads();
-    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < RT_WARPS; ++k) sum += s_part[k][lev];
-        s_up[lev] = sum * c_lw.fluxfac;
     }
     __syncthreads();
 

@@ -164,6 +164,59 @@ struct SwWork {
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
 
+
+// ------------------------------------------------------------------------------------ device math
+#ifdef __CUDACC__
+// FP64 reciprocal and square root from the 20-bit MUFU seeds plus Newton steps written as fma().  They
+// replace the IEEE-rounded `/` and sqrt() sequences (which carry a slow-path call) in the solvers, where
+// the divide count bounds the FP64 pipe.  Relative error <= ~2 ulp; arguments here are normal, positive
+// or bounded away from zero by the callers, so no special-case handling is needed.
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+__device__ __forceinline__ double sqrt_fast(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    return fma(g, r, g);
+}
+
+// Sum over the g-points of one column (threads of a block) of R = 16 rows of per-thread values that the
+// caller has stored in `tile` as tile[row * S + thread] (S odd, >= NACT).  Stage 1: thread t sums the
+// strided elements of row (t & 15); stage 2: threads 0..15 combine the NT/16 partials in a fixed order,
+// so the result is bitwise reproducible.  Two barriers; `tile` may be refilled right after the call.
+// Returns the row sum in threads 0..15.
+template <int NT, int NACT, int S>
+__device__ __forceinline__ double tile_reduce16(const double *tile, double *part)
+{
+    constexpr int P = NT / 16;
+    const int t = threadIdx.x, row = t & 15, p = t >> 4;
+    __syncthreads();
+    double acc = 0.0;
+    const double *src = tile + row * S;
+#pragma unroll
+    for (int j = p; j < NACT; j += P) acc += src[j];
+    part[row * (P + 1) + p] = acc;
+    __syncthreads();
+    double sum = 0.0;
+    if (t < 16) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) sum += part[t * (P + 1) + k];
+    }
+    return sum;     // valid in threads 0..15 (row = threadIdx.x)
+}
+#endif
+
 // optional per-kernel CUDA-event timing (api.cu); ids: 0 lw_prep, 1 lw_taumol, 2 lw_rtrn, 3 sw_prep, 4 sw_taumol, 5 sw_solver
 enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_COUNT };
 void ktimer_begin(int id, cudaStream_t s);

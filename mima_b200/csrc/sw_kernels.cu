@@ -487,14 +487,30 @@ __global__ void __launch_bounds__(TP) sw_taumol_kernel(SwTables T, SwWork w)
 // icld = 0 and iaer = 0: the aerosol/cloud terms of the layer assembly are exact identities
 // (tau_a = 0, omega_a = 1, g = 0 => delta scaling is the identity) and the total-sky stream equals the
 // clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
+//
+// Block <-> column, thread <-> g-point.  Two sweeps instead of the reference's four loops:
+//   up   (surface -> top): layer R/T (reftra) fused with the bottom-up adding recurrence (vrtqdr :103-121);
+//        keeps ref, refd, tra, trad, dbt per layer and rup, rupd per level in per-thread local arrays;
+//   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
+//        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
+//        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
+// The direct-beam transmittance of spcvrt :519-531 is the same table look-up as reftra's exp(-tau/mu0)
+// (for tau/mu0 > 500 both hit the 1e-20 floor of exp_tbl), so it is taken from there.
+// Divides go through rcp_fast/sqrt_fast; zbeta is folded into zdend's denominator.
+// The sum over g-points goes through shared memory in batches of 8 levels (tile_reduce16).
 // =====================================================================================================
 constexpr int SV_THREADS = 128;   // 112 g-points -> 3.5 warps
-constexpr int SV_WARPS = SV_THREADS / 32;
+constexpr int SV_S = 113;         // tile row stride (odd)
 
-__device__ __forceinline__ double exp_lookup(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
+// exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
+__device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
 {
-    // ze > od_lo: table; caller handles the series branch
-    const double tblind = ze / (bpade + ze);
+    if (ze <= 0.06) {
+        const double em = 1. - ze + 0.5 * ze * ze;
+        recip = rcp_fast(em);
+        return em;
+    }
+    const double tblind = ze * rcp_fast(bpade + ze);
     const int itind = (int)(10000.0 * tblind + 0.5);
     const double2 e = __ldg(tb + itind);
     recip = e.y;
@@ -504,16 +520,16 @@ __device__ __forceinline__ double exp_lookup(const double2 *__restrict__ tb, dou
 template <int LMAX>
 __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
 {
-    __shared__ double s_pu[SV_WARPS][LMAX + 1], s_pd[SV_WARPS][LMAX + 1];
-    __shared__ double s_net[LMAX + 1];
+    __shared__ double s_tile[16 * SV_S];
+    __shared__ double s_part[16 * (SV_THREADS / 16 + 1)];
+    __shared__ double s_up[LMAX + 1], s_dn[LMAX + 1];
     const int col = blockIdx.x;
     const int klev = w.nlay;
     const int g = threadIdx.x;
-    const int lane = g & 31, wid = g >> 5;
     const size_t old = (size_t)out.ld;
 
-    const double prmu0_in = in.coszen[col];
-    if (prmu0_in < ZEPZEN) {
+    const double prmu0 = in.coszen[col];
+    if (prmu0 < ZEPZEN) {
         // night column: zero everything (rad.nomcica:502-510)
         for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
             const size_t o = col + (size_t)lev * old;
@@ -522,19 +538,20 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
         }
         return;
     }
-    const double prmu0 = prmu0_in;     // cossza; >= zepzen here
     const bool active = g < NGPTSW;
     const int band = active ? c_sw_ngb[g] : 0;
     const double bpade = c_sw.bpade;
-    const double od_lo = 0.06, eps = 1.e-08, zwcrit = 0.9999995;
+    const double eps = 1.e-08, zwcrit = 0.9999995;
     const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
+    const double rmu0 = 1. / prmu0;
 
     // band albedos (rad.nomcica:565-578): bands 16-24 and 29 near-IR, 25-28 UV/visible
     const bool uvvis = band >= 9 && band <= 12;
     const double albd = uvvis ? in.asdif[col] : in.aldif[col];   // palbd: diffuse
     const double albp = uvvis ? in.asdir[col] : in.aldir[col];   // palbp: direct
 
-    double zref[LMAX + 1], zrefd[LMAX + 1], ztra[LMAX], ztrad[LMAX], zdbt[LMAX];
+    // per-thread state, index = layer / level counted from the surface
+    double zref[LMAX], zrefd[LMAX], ztra[LMAX], ztrad[LMAX], zdbt[LMAX];
     double zrup[LMAX + 1], zrupd[LMAX + 1];
     double zincflx = 0.0;
 
@@ -542,152 +559,128 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
         zincflx = in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0;
         const double *taug = w.taug + (size_t)col * klev * NGPTSW + g;
         const double *taur = w.taur + (size_t)col * klev * NGPTSW + g;
-        // ---- layer properties, top -> bottom (jk = 1..klev; Fortran layer ikl = klev+1-jk)
-        for (int jk = 1; jk <= klev; ++jk) {
-            const size_t o = (size_t)(klev - jk) * NGPTSW;
-            const double tr = taur[o];
-            const double zto1 = tr + taug[o];          // ztauc
-            const double zw = tr / zto1;               // zomcc
-            // reftra, zg = 0
+        double rup = albp, rupd = albd;      // zrup(klev+1) = palbp, zrupd(klev+1) = palbd
+        zrup[0] = rup;
+        zrupd[0] = rupd;
+#pragma unroll 2
+        for (int l = 0; l < klev; ++l) {
+            const double tr = taur[(size_t)l * NGPTSW];
+            const double zto1 = tr + taug[(size_t)l * NGPTSW];      // ztauc
+            const double zw = tr * rcp_fast(zto1);                   // zomcc
+            // ---- reftra, zg = 0: gamma3 = gamma4 = 1/2, zwo = zw
             const double zgamma1 = (8. - zw * 5.) * 0.25;
             const double zgamma2 = 3. * zw * 0.25;
-            const double zgamma3 = 0.5;
-            const double zgamma4 = 0.5;
-            const double zwo = zw;
+            const double zed = zto1 * rmu0;                          // direct-beam optical path
             double ref, refd, tra, trad, dbt;
-            const double zed = zto1 / prmu0;           // direct-beam optical path
-            if (zwo >= zwcrit) {
-                // conservative scattering
-                const double za = zgamma1 * prmu0;
-                const double za1 = za - zgamma3;
+            if (zw >= zwcrit) {
+                // conservative scattering (:162-214)
+                const double za1 = zgamma1 * prmu0 - 0.5;
                 const double zgt = zgamma1 * zto1;
-                const double ze1 = fmin(zed, 500.);
-                double ze2, rcp;
-                if (ze1 <= od_lo) ze2 = 1. - ze1 + 0.5 * ze1 * ze1;
-                else ze2 = exp_lookup(tb, ze1, bpade, rcp);
-                ref = (zgt - za1 * (1. - ze2)) / (1. + zgt);
+                double rcp;
+                const double ze2 = sw_exp(tb, fmin(zed, 500.), bpade, rcp);
+                const double rg = rcp_fast(1. + zgt);
+                ref = (zgt - za1 * (1. - ze2)) * rg;
                 tra = 1. - ref;
-                refd = zgt / (1. + zgt);
+                refd = zgt * rg;
                 trad = 1. - refd;
                 if (ze2 == 1.0) { ref = 0.0; tra = 1.0; refd = 0.0; trad = 1.0; }
+                dbt = ze2;
             } else {
-                const double za1 = zgamma1 * zgamma4 + zgamma2 * zgamma3;
-                const double za2 = zgamma1 * zgamma3 + zgamma2 * zgamma4;
-                const double zrk = sqrt(zgamma1 * zgamma1 - zgamma2 * zgamma2);
+                const double za1 = (zgamma1 + zgamma2) * 0.5;        // = za2
+                const double zrk = sqrt_fast(zgamma1 * zgamma1 - zgamma2 * zgamma2);
                 const double zrp = zrk * prmu0;
                 const double zrp1 = 1. + zrp;
                 const double zrm1 = 1. - zrp;
                 const double zrk2 = 2. * zrk;
                 const double zrpp = 1. - zrp * zrp;
                 const double zrkg = zrk + zgamma1;
-                const double zr1 = zrm1 * (za2 + zrk * zgamma3);
-                const double zr2 = zrp1 * (za2 - zrk * zgamma3);
-                const double zr3 = zrk2 * (zgamma3 - za2 * prmu0);
+                const double hA = fma(zrk, 0.5, za1), hB = fma(zrk, -0.5, za1);
+                const double zr1 = zrm1 * hA;
+                const double zr2 = zrp1 * hB;
+                const double zr3 = zrk2 * (0.5 - za1 * prmu0);
                 const double zr4 = zrpp * zrkg;
                 const double zr5 = zrpp * (zrk - zgamma1);
-                const double zt1 = zrp1 * (za1 + zrk * zgamma4);
-                const double zt2 = zrm1 * (za1 - zrk * zgamma4);
-                const double zt3 = zrk2 * (zgamma4 + za1 * prmu0);
-                const double zbeta = (zgamma1 - zrk) / zrkg;
-                const double ze1 = fmin(zrk * zto1, 500.);
-                const double ze2 = fmin(zed, 500.);
-                double zem1, zep1, zem2, zep2;
-                if (ze1 <= od_lo) { zem1 = 1. - ze1 + 0.5 * ze1 * ze1; zep1 = 1. / zem1; }
-                else zem1 = exp_lookup(tb, ze1, bpade, zep1);
-                if (ze2 <= od_lo) { zem2 = 1. - ze2 + 0.5 * ze2 * ze2; zep2 = 1. / zem2; }
-                else zem2 = exp_lookup(tb, ze2, bpade, zep2);
-                const double zdenr = zr4 * zep1 + zr5 * zem1;
-                const double zdent = zr4 * zep1 + zr5 * zem1;   // zt4 = zr4, zt5 = zr5
+                const double zt1 = zrp1 * hA;
+                const double zt2 = zrm1 * hB;
+                const double zt3 = zrk2 * (0.5 + za1 * prmu0);
+                double zep1, zep2;
+                const double zem1 = sw_exp(tb, fmin(zrk * zto1, 500.), bpade, zep1);
+                const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
+                const double zdenr = fma(zr4, zep1, zr5 * zem1);     // = zdent (zt4 = zr4, zt5 = zr5)
                 if (zdenr >= -eps && zdenr <= eps) {
                     ref = eps;
                     tra = zem2;
                 } else {
-                    ref = zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) / zdenr;
-                    tra = zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) / zdent;
+                    const double rd = zw * rcp_fast(zdenr);
+                    ref = (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * rd;
+                    tra = zem2 - zem2 * ((zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * rd);
                 }
                 const double zemm = zem1 * zem1;
-                const double zdend = 1. / ((1. - zbeta * zemm) * zrkg);
+                // zdend = 1/((1 - zbeta*zemm)*zrkg), zbeta = (gamma1 - zrk)/zrkg
+                const double zdend = rcp_fast(fma(-(zgamma1 - zrk), zemm, zrkg));
                 refd = zgamma2 * (1. - zemm) * zdend;
                 trad = zrk2 * zem1 * zdend;
+                dbt = zem2;
             }
-            // direct beam transmittance (spcvrt:519-531)
-            if (zed <= od_lo) dbt = 1. - zed + 0.5 * zed * zed;
-            else { double rcp; dbt = exp_lookup(tb, zed, bpade, rcp); }
-            zref[jk - 1] = ref; zrefd[jk - 1] = refd; ztra[jk - 1] = tra; ztrad[jk - 1] = trad; zdbt[jk - 1] = dbt;
-        }
-        zref[klev] = albp;     // zrefc(klev+1) = palbp
-        zrefd[klev] = albd;    // zrefdc(klev+1) = palbd
-
-        // ---- vrtqdr: link lowest layer with surface, then bottom -> top (:103-121)   [0-based: jk-1]
-        {
-            double zreflect = 1. / (1. - zrefd[klev] * zrefd[klev - 1]);
-            zrup[klev - 1] = zref[klev - 1] + (ztrad[klev - 1] * ((ztra[klev - 1] - zdbt[klev - 1]) * zrefd[klev] +
-                                                                  zdbt[klev - 1] * zref[klev])) * zreflect;
-            zrupd[klev - 1] = zrefd[klev - 1] + ztrad[klev - 1] * ztrad[klev - 1] * zrefd[klev] * zreflect;
-            zrup[klev] = albp;
-            zrupd[klev] = albd;
-            for (int ikx = klev - 2; ikx >= 0; --ikx) {
-                const int ikp = ikx + 1;
-                zreflect = 1. / (1. - zrupd[ikp] * zrefd[ikx]);
-                zrup[ikx] = zref[ikx] + (ztrad[ikx] * ((ztra[ikx] - zdbt[ikx]) * zrupd[ikp] + zdbt[ikx] * zrup[ikp])) * zreflect;
-                zrupd[ikx] = zrefd[ikx] + ztrad[ikx] * ztrad[ikx] * zrupd[ikp] * zreflect;
-            }
+            zref[l] = ref; zrefd[l] = refd; ztra[l] = tra; ztrad[l] = trad; zdbt[l] = dbt;
+            // ---- vrtqdr, bottom -> top (:103-121)
+            const double zreflect = rcp_fast(1. - rupd * refd);
+            const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
+            const double rupd_n = refd + trad * trad * rupd * zreflect;
+            rup = rup_n;
+            rupd = rupd_n;
+            zrup[l + 1] = rup;
+            zrupd[l + 1] = rupd;
         }
     }
 
     // ---- top -> bottom: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
     double ztdn = 1., zrdnd = 0., ztdbt = 1.;
-    for (int jk = 1; jk <= klev + 1; ++jk) {
-        double fu = 0.0, fd = 0.0;
+    for (int k = 0; k <= klev; ++k) {
+        const int s = klev - k;            // level counted from the surface
+        const int slot = k & 7;
         if (active) {
-            const int i = jk - 1;
-            const double zreflect = 1. / (1. - zrdnd * zrupd[i]);
-            const double pfu = (ztdbt * zrup[i] + (ztdn - ztdbt) * zrupd[i]) * zreflect;
-            const double pfd = ztdbt + (ztdn - ztdbt + ztdbt * zrup[i] * zrdnd) * zreflect;
-            fu = zincflx * pfu;
-            fd = zincflx * pfd;
-            if (jk <= klev) {
-                // advance to level jk+1
-                double ztdn_n, zrdnd_n;
-                if (jk == 1) {
-                    ztdn_n = ztra[0];
-                    zrdnd_n = zrefd[0];
-                } else {
-                    const double zr = 1. / (1. - zrefd[i] * zrdnd);
-                    ztdn_n = ztdbt * ztra[i] + (ztrad[i] * ((ztdn - ztdbt) + ztdbt * zref[i] * zrdnd)) * zr;
-                    zrdnd_n = zrefd[i] + ztrad[i] * ztrad[i] * zrdnd * zr;
-                }
-                ztdbt = zdbt[i] * ztdbt;
+            const double ru = zrup[s], rud = zrupd[s];
+            const double zreflect = rcp_fast(1. - zrdnd * rud);
+            const double dif = ztdn - ztdbt;
+            const double pfu = (ztdbt * ru + dif * rud) * zreflect;
+            const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
+            s_tile[(2 * slot) * SV_S + g] = zincflx * pfu;
+            s_tile[(2 * slot + 1) * SV_S + g] = zincflx * pfd;
+            if (s > 0) {
+                const int l = s - 1;
+                const double ref = zref[l], refd = zrefd[l], tra = ztra[l], trad = ztrad[l], dbt = zdbt[l];
+                const double zr = rcp_fast(1. - refd * zrdnd);
+                const double ztdn_n = ztdbt * tra + (trad * (dif + ztdbt * ref * zrdnd)) * zr;
+                const double zrdnd_n = refd + trad * trad * zrdnd * zr;
+                ztdbt = dbt * ztdbt;
                 ztdn = ztdn_n;
                 zrdnd = zrdnd_n;
             }
         }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            fu += __shfl_xor_sync(0xffffffffu, fu, m);
-            fd += __shfl_xor_sync(0xffffffffu, fd, m);
-        }
-        if (lane == 0) {
-            s_pu[wid][klev + 1 - jk] = fu;     // ikl = klev+2-jk (1-based) -> 0-based level from the surface
-            s_pd[wid][klev + 1 - jk] = fd;
+        if (slot == 7 || k == klev) {
+            const double sum = tile_reduce16<SV_THREADS, NGPTSW, SV_S>(s_tile, s_part);
+            if (threadIdx.x < 16) {
+                const int kk = (k & ~7) + (threadIdx.x >> 1);
+                if (kk <= k) {
+                    if (threadIdx.x & 1) s_dn[klev - kk] = sum;
+                    else s_up[klev - kk] = sum;
+                }
+            }
         }
     }
     __syncthreads();
     for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
-        double u = 0.0, d = 0.0;
-#pragma unroll
-        for (int k = 0; k < SV_WARPS; ++k) { u += s_pu[k][lev]; d += s_pd[k][lev]; }
+        const double u = s_up[lev], d = s_dn[lev];
         const size_t o = col + (size_t)lev * old;
         out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
-        s_net[lev] = d - u;
     }
-    __syncthreads();
     for (int lay = threadIdx.x; lay < klev; lay += SV_THREADS) {
         const size_t o = col + (size_t)lay * old;
         double h = 0.0;
         if (lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
             const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
-            h = (s_net[lay + 1] - s_net[lay]) * (c_sw.heatfac / pdp);
+            h = ((s_dn[lay + 1] - s_up[lay + 1]) - (s_dn[lay] - s_up[lay])) * (c_sw.heatfac / pdp);
         }
         out.hr[o] = h;
         out.hrc[o] = h;
