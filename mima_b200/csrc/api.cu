@@ -467,14 +467,15 @@ struct Carver {
         return r;
     }
 };
-size_t lw_carve(LwWork &w, void *base, int nc, int nlay)
+size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
 {
     Carver c(base);
     w.nc = nc; w.nlay = nlay;
     const size_t np = (size_t)nc * nlay;
-    w.idx = c.take<uint32_t>(np);
     w.laytrop = c.take<int>(nc);
-    w.f = c.take<double>(np * LF_COUNT);
+    // per-cell setcoef state is only materialised for the stage-capture test hook
+    w.idx = fields ? c.take<uint32_t>(np) : nullptr;
+    w.f = fields ? c.take<double>(np * LF_COUNT) : nullptr;
     w.secdiff = c.take<double>((size_t)nc * 16);
     w.planklay = c.take<double>(np * 16);
     w.planklev = c.take<double>((size_t)nc * (nlay + 1) * 16);
@@ -483,15 +484,15 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay)
     w.fracs = c.take<double>(np * NGPTLW);
     return c.off + 256;
 }
-size_t sw_carve(SwWork &w, void *base, int nc, int nlay)
+size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
 {
     Carver c(base);
     w.nc = nc; w.nlay = nlay;
     const size_t np = (size_t)nc * nlay;
-    w.idx = c.take<uint32_t>(np);
     w.laytrop = c.take<int>(nc);
     w.laysolfr = c.take<int>((size_t)nc * 14);
-    w.f = c.take<double>(np * SF_COUNT);
+    w.idx = fields ? c.take<uint32_t>(np) : nullptr;
+    w.f = fields ? c.take<double>(np * SF_COUNT) : nullptr;
     w.taug = c.take<double>(np * NGPTSW);
     w.taur = c.take<double>(np * NGPTSW);
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
@@ -515,11 +516,12 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     LwWork w;
-    const size_t need = lw_carve(w, nullptr, chunk, nlay);
+    const bool fields = G.capture && ncol <= chunk;
+    const size_t need = lw_carve(w, nullptr, chunk, nlay, fields);
     if (G.lw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        lw_carve(w, G.lw_work.p, nc, nlay);
+        lw_carve(w, G.lw_work.p, nc, nlay, fields);
         LwIn in = in0;
         LwOut out = out0;
 #define OFF(p) if (in.p) in.p += c0
@@ -551,11 +553,12 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     SwWork w;
-    const size_t need = sw_carve(w, nullptr, chunk, nlay);
+    const bool fields = G.capture && ncol <= chunk;
+    const size_t need = sw_carve(w, nullptr, chunk, nlay, fields);
     if (G.sw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        sw_carve(w, G.sw_work.p, nc, nlay);
+        sw_carve(w, G.sw_work.p, nc, nlay, fields);
         SwIn in = in0;
         SwOut out = out0;
 #define OFF(p) if (in.p) in.p += c0
@@ -611,6 +614,7 @@ struct Stager {
 } // namespace
 
 namespace rrtmg {
+Tuning g_tune = {0, 0};
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -915,6 +919,7 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
     static const char *swf[SF_COUNT] = {"fac00", "fac01", "fac10", "fac11", "colh2o", "colco2", "colo3", "colch4", "colo2",
                                         "colmol", "coln2o", "selffac", "selffrac", "forfac", "forfrac"};
     const size_t np = (size_t)nc * nlay;
+    const bool have_fields = lw ? G.lw_last.f != nullptr : G.sw_last.f != nullptr;
     auto transposed = [&](const double *dev, int inner, int mid) -> long {
         // device [col][mid][inner] -> host (ncol, mid, inner) column-major
         std::vector<double> t;
@@ -928,6 +933,7 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
     };
     if (f == "laytrop") n = dump_field(lw ? (void *)G.lw_last.laytrop : (void *)G.sw_last.laytrop, nc, true, h);
     else if (f == "jp" || f == "jt" || f == "jt1" || f == "indself" || f == "indfor" || f == "indminor") {
+        if (!have_fields) return -1;      // needs option capture_stages
         std::vector<uint32_t> tmp(np);
         if (cudaMemcpy(tmp.data(), lw ? G.lw_last.idx : G.sw_last.idx, np * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         h.resize(np);
@@ -956,6 +962,7 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
         n = (long)h.size();
     } else {
         const int nf = lw ? (int)LF_COUNT : (int)SF_COUNT;
+        if (!have_fields) return -1;
         for (int i = 0; i < nf; ++i)
             if (f == (lw ? lwf[i] : swf[i])) n = dump_field(lw ? G.lw_last.fld(i) : G.sw_last.fld(i), np, false, h);
     }
@@ -969,6 +976,8 @@ int rrtmg_b200_set_option(const char *key, long value)
     const std::string k(key ? key : "");
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
+    if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
+    if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "kernel_timing") { KT.collect(); KT.on = value != 0; return RRTMG_B200_OK; }
     return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "unknown option " + k);
 }

@@ -32,9 +32,126 @@ int lw_upload_const(const LwConst &c)
 
 #define CHI(m, j) c_lw.chi_mls[((j) - 1) * 7 + ((m) - 1)]
 
+// Interpolation state of one (column, layer) cell: everything setcoef hands to taumol.
+struct LwPair {
+    int jp, jt, jt1, inds, indf, indm;
+    double fac00, fac01, fac10, fac11;
+    double colh2o, colco2, colo3, coln2o, colco, colch4, colo2, colbrd;
+    double selffac, selffrac, forfac, forfrac, minorfrac, scaleminor, scaleminorn2, coldry, pavel;
+    double wx1, wx2, wx3, wx4;
+};
+
 // =====================================================================================================
-// prep: inatm (LW/src/rrtmg_lw_rad.nomcica.f90:572-901) + setcoef (LW/src/rrtmg_lw_setcoef.f90:31-415)
-//       + diffusivity secant (LW/src/rrtmg_lw_rtrnmr.f90:259-280)
+// inatm (LW/src/rrtmg_lw_rad.nomcica.f90:572-901) + setcoef (LW/src/rrtmg_lw_setcoef.f90:251-410) for one
+// (column, layer) cell.  Everything here is local to the cell (coldry needs only the two interface
+// pressures of the layer), so the taumol kernel evaluates it in place instead of reading it back from HBM;
+// the prep kernel calls the same function for the column-integrated quantities (laytrop, pwvcm), which
+// keeps the two bit-identical.  Returns true when the layer counts towards laytrop (plog > 4.56).
+// `wkl1` (H2O column amount, molecules/cm2) is returned for the precipitable-water integral.
+// =====================================================================================================
+__device__ __forceinline__ bool lw_cell(const LwIn &in, int col, int l, LwPair &p, double &wkl1_out)
+{
+    const double amd = 28.9660, amw = 18.0160, amdw = 1.607793, amdo = 0.603428;
+    const double grav = 9.8066, avogad = 6.02214199e+23;
+    const double stpfac = 296. / 1013.;
+    const size_t ld = (size_t)in.ld;
+    const size_t o = col + (size_t)l * ld;
+    const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pzm = in.plev[o], pz = in.plev[o + ld];
+    // ---- inatm
+    const double q = in.h2o[o];
+    double wkl1 = (q / (1.0 - q)) * amdw;
+    double wkl2 = in.co2[o];
+    double wkl3 = in.o3[o] * amdo;
+    double wkl4 = in.n2o ? in.n2o[o] : 0.0;
+    double wkl6 = in.ch4 ? in.ch4[o] : 0.0;
+    double wkl7 = in.o2 ? in.o2[o] : 0.0;
+    const double amm = (1.0 - wkl1) * amd + wkl1 * amw;
+    const double coldry = (pzm - pz) * 1.e3 * avogad / (1.e2 * grav * amm * (1.0 + wkl1));
+    double summol = 0.0;
+    summol = summol + wkl2; summol = summol + wkl3; summol = summol + wkl4;
+    summol = summol + 0.0;  summol = summol + wkl6; summol = summol + wkl7;
+    const double wbrodl = coldry * (1.0 - summol);
+    wkl1 = coldry * wkl1; wkl2 = coldry * wkl2; wkl3 = coldry * wkl3; wkl4 = coldry * wkl4;
+    wkl6 = coldry * wkl6; wkl7 = coldry * wkl7;
+    const double wkl5 = coldry * 0.0;
+    wkl1_out = wkl1;
+    p.wx1 = in.ccl4 ? coldry * in.ccl4[o] * 1.e-20 : 0.0;
+    p.wx2 = in.cfc11 ? coldry * in.cfc11[o] * 1.e-20 : 0.0;
+    p.wx3 = in.cfc12 ? coldry * in.cfc12[o] * 1.e-20 : 0.0;
+    p.wx4 = in.cfc22 ? coldry * in.cfc22[o] * 1.e-20 : 0.0;
+
+    // ---- setcoef: interpolation indices and factors
+    const double plog = log(pavel);
+    int jp = (int)(36. - 5 * (plog + 0.04));
+    jp = jp < 1 ? 1 : (jp > 58 ? 58 : jp);
+    const double fp = 5. * (c_lw.preflog[jp - 1] - plog);
+    const double tr0 = (tavel - c_lw.tref[jp - 1]) / 15.;
+    int jt = (int)(3. + tr0);
+    jt = jt < 1 ? 1 : (jt > 4 ? 4 : jt);
+    const double ft = tr0 - (double)(jt - 3);
+    const double tr1 = (tavel - c_lw.tref[jp]) / 15.;
+    int jt1 = (int)(3. + tr1);
+    jt1 = jt1 < 1 ? 1 : (jt1 > 4 ? 4 : jt1);
+    const double ft1 = tr1 - (double)(jt1 - 3);
+    const double water = wkl1 / coldry;
+    const double scalefac = pavel * stpfac / tavel;
+    double forfac, forfrac, selffac, selffrac = 0.0, factor;
+    int indfor, indself = 0;
+    forfac = scalefac / (1. + water);
+    selffac = water * forfac;
+    const bool lower = !(plog <= 4.56);
+    if (lower) {
+        factor = (332.0 - tavel) / 36.0;
+        indfor = (int)factor;
+        indfor = indfor < 1 ? 1 : (indfor > 2 ? 2 : indfor);
+        forfrac = factor - (double)indfor;
+        factor = (tavel - 188.0) / 7.2;
+        indself = (int)factor - 7;
+        indself = indself < 1 ? 1 : (indself > 9 ? 9 : indself);
+        selffrac = factor - (double)(indself + 7);
+    } else {
+        factor = (tavel - 188.0) / 36.0;
+        indfor = 3;
+        forfrac = factor - 1.0;
+    }
+    p.scaleminor = pavel / tavel;
+    p.scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + wkl1));
+    factor = (tavel - 180.8) / 7.2;
+    int indminor = (int)factor;
+    indminor = indminor < 1 ? 1 : (indminor > 18 ? 18 : indminor);
+    p.minorfrac = factor - (double)indminor;
+
+    p.colh2o = 1.e-20 * wkl1;
+    double colco2 = 1.e-20 * wkl2, colo3 = 1.e-20 * wkl3, coln2o = 1.e-20 * wkl4;
+    double colco = 1.e-20 * wkl5, colch4 = 1.e-20 * wkl6;
+    p.colo2 = 1.e-20 * wkl7;
+    if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+    if (colo3 == 0.) colo3 = 1.e-32 * coldry;
+    if (coln2o == 0.) coln2o = 1.e-32 * coldry;
+    if (colco == 0.) colco = 1.e-32 * coldry;
+    if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+    p.colco2 = colco2; p.colo3 = colo3; p.coln2o = coln2o; p.colco = colco; p.colch4 = colch4;
+    p.colbrd = 1.e-20 * wbrodl;
+    const double compfp = 1. - fp;
+    p.jp = jp; p.jt = jt; p.jt1 = jt1; p.inds = indself; p.indf = indfor; p.indm = indminor;
+    p.fac10 = compfp * ft;
+    p.fac00 = compfp * (1. - ft);
+    p.fac11 = fp * ft1;
+    p.fac01 = fp * (1. - ft1);
+    p.selffac = p.colh2o * selffac;
+    p.selffrac = selffrac;
+    p.forfac = p.colh2o * forfac;
+    p.forfrac = forfrac;
+    p.coldry = coldry;
+    p.pavel = pavel;
+    return lower;
+}
+
+// =====================================================================================================
+// prep: column-integrated quantities -- laytrop (setcoef.f90:293-294), precipitable water and the
+//       diffusivity secant per band (rtrnmr.f90:259-280) -- and the Planck sources (setcoef.f90:154-249).
+//       With w.f != nullptr (stage capture, test hook) the per-cell setcoef state is also written out.
 // =====================================================================================================
 __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWork w)
 {
@@ -42,15 +159,12 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
     if (col >= w.nc) return;
     const int nlay = w.nlay, nc = w.nc;
     const size_t ld = (size_t)in.ld;
-    const double amd = 28.9660, amw = 18.0160, amdw = 1.607793, amdo = 0.603428;
-    const double grav = 9.8066, avogad = 6.02214199e+23;
-    const double stpfac = 296. / 1013.;
+    const double amd = 28.9660, amw = 18.0160, grav = 9.8066;
 
     double amttl = 0.0, wvttl = 0.0;
     const double tbound = in.tsfc[col];
     const double pz0 = in.plev[col];
     const double tz0 = in.tlev[col];
-    double pzm = pz0;
     int laytrop = 0;
 
     // surface / level-0 Planck terms
@@ -76,136 +190,52 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
 
     for (int l = 0; l < nlay; ++l) {
         const size_t o = col + (size_t)l * ld;
-        const size_t wo = (size_t)l * nc + col;
-        const double pavel = in.play[o], tavel = in.tlay[o];
-        const double pz = in.plev[o + ld], tz = in.tlev[o + ld];
-        // ---- inatm
-        const double q = in.h2o[o];
-        double wkl1 = (q / (1.0 - q)) * amdw;
-        double wkl2 = in.co2[o];
-        double wkl3 = in.o3[o] * amdo;
-        double wkl4 = in.n2o ? in.n2o[o] : 0.0;
-        double wkl6 = in.ch4 ? in.ch4[o] : 0.0;
-        double wkl7 = in.o2 ? in.o2[o] : 0.0;
-        const double amm = (1.0 - wkl1) * amd + wkl1 * amw;
-        const double coldry = (pzm - pz) * 1.e3 * avogad / (1.e2 * grav * amm * (1.0 + wkl1));
-        pzm = pz;
-        double summol = 0.0;
-        summol = summol + wkl2; summol = summol + wkl3; summol = summol + wkl4;
-        summol = summol + 0.0;  summol = summol + wkl6; summol = summol + wkl7;
-        const double wbrodl = coldry * (1.0 - summol);
-        wkl1 = coldry * wkl1; wkl2 = coldry * wkl2; wkl3 = coldry * wkl3; wkl4 = coldry * wkl4;
-        wkl6 = coldry * wkl6; wkl7 = coldry * wkl7;
-        const double wkl5 = coldry * 0.0;
-        amttl = amttl + coldry + wkl1;
+        LwPair p;
+        double wkl1;
+        if (lw_cell(in, col, l, p, wkl1)) laytrop = laytrop + 1;
+        amttl = amttl + p.coldry + wkl1;
         wvttl = wvttl + wkl1;
-        w.fld(LF_WX1)[wo] = in.ccl4 ? coldry * in.ccl4[o] * 1.e-20 : 0.0;
-        w.fld(LF_WX2)[wo] = in.cfc11 ? coldry * in.cfc11[o] * 1.e-20 : 0.0;
-        w.fld(LF_WX3)[wo] = in.cfc12 ? coldry * in.cfc12[o] * 1.e-20 : 0.0;
-        w.fld(LF_WX4)[wo] = in.cfc22 ? coldry * in.cfc22[o] * 1.e-20 : 0.0;
-
+        if (w.f) {
+            const size_t wo = (size_t)l * nc + col;
+            w.idx[wo] = lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm);
+            w.fld(LF_FAC00)[wo] = p.fac00; w.fld(LF_FAC01)[wo] = p.fac01;
+            w.fld(LF_FAC10)[wo] = p.fac10; w.fld(LF_FAC11)[wo] = p.fac11;
+            w.fld(LF_COLH2O)[wo] = p.colh2o; w.fld(LF_COLCO2)[wo] = p.colco2; w.fld(LF_COLO3)[wo] = p.colo3;
+            w.fld(LF_COLN2O)[wo] = p.coln2o; w.fld(LF_COLCO)[wo] = p.colco; w.fld(LF_COLCH4)[wo] = p.colch4;
+            w.fld(LF_COLO2)[wo] = p.colo2; w.fld(LF_COLBRD)[wo] = p.colbrd;
+            w.fld(LF_SELFFAC)[wo] = p.selffac; w.fld(LF_SELFFRAC)[wo] = p.selffrac;
+            w.fld(LF_FORFAC)[wo] = p.forfac; w.fld(LF_FORFRAC)[wo] = p.forfrac;
+            w.fld(LF_MINORFRAC)[wo] = p.minorfrac; w.fld(LF_SCALEMINOR)[wo] = p.scaleminor;
+            w.fld(LF_SCALEMINORN2)[wo] = p.scaleminorn2; w.fld(LF_COLDRY)[wo] = p.coldry;
+            w.fld(LF_PAVEL)[wo] = p.pavel;
+            w.fld(LF_WX1)[wo] = p.wx1; w.fld(LF_WX2)[wo] = p.wx2; w.fld(LF_WX3)[wo] = p.wx3; w.fld(LF_WX4)[wo] = p.wx4;
+        }
         // ---- setcoef: Planck sources
+        const double tavel = in.tlay[o], tz = in.tlev[o + ld];
         int indlay = (int)(tavel - 159.);
         indlay = indlay < 1 ? 1 : (indlay > 180 ? 180 : indlay);
         const double tlayfrac = tavel - 159. - (double)indlay;
         int indlev = (int)(tz - 159.);
         indlev = indlev < 1 ? 1 : (indlev > 180 ? 180 : indlev);
         const double tlevfrac = tz - 159. - (double)indlev;
-        {
-            double2 *play2 = reinterpret_cast<double2 *>(w.planklay + ((size_t)col * nlay + l) * 16);
-            double2 *plev2 = reinterpret_cast<double2 *>(w.planklev + ((size_t)col * (nlay + 1) + l + 1) * 16);
+        double2 *play2 = reinterpret_cast<double2 *>(w.planklay + ((size_t)col * nlay + l) * 16);
+        double2 *plev2 = reinterpret_cast<double2 *>(w.planklev + ((size_t)col * (nlay + 1) + l + 1) * 16);
 #pragma unroll 2
-            for (int ib = 0; ib < 16; ib += 2) {
-                double2 a, b;
-                const double *tp = T.totplnk + ib * 181;
-                double d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
-                a.x = __ldg(tp + indlay - 1) + tlayfrac * d;
-                d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
-                b.x = __ldg(tp + indlev - 1) + tlevfrac * d;
-                tp += 181;
-                d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
-                a.y = __ldg(tp + indlay - 1) + tlayfrac * d;
-                d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
-                b.y = __ldg(tp + indlev - 1) + tlevfrac * d;
-                play2[ib >> 1] = a;
-                plev2[ib >> 1] = b;
-            }
+        for (int ib = 0; ib < 16; ib += 2) {
+            double2 a, b;
+            const double *tp = T.totplnk + ib * 181;
+            double d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
+            a.x = __ldg(tp + indlay - 1) + tlayfrac * d;
+            d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
+            b.x = __ldg(tp + indlev - 1) + tlevfrac * d;
+            tp += 181;
+            d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
+            a.y = __ldg(tp + indlay - 1) + tlayfrac * d;
+            d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
+            b.y = __ldg(tp + indlev - 1) + tlevfrac * d;
+            play2[ib >> 1] = a;
+            plev2[ib >> 1] = b;
         }
-        // ---- setcoef: interpolation indices and factors
-        const double plog = log(pavel);
-        int jp = (int)(36. - 5 * (plog + 0.04));
-        jp = jp < 1 ? 1 : (jp > 58 ? 58 : jp);
-        const double fp = 5. * (c_lw.preflog[jp - 1] - plog);
-        const double tr0 = (tavel - c_lw.tref[jp - 1]) / 15.;
-        int jt = (int)(3. + tr0);
-        jt = jt < 1 ? 1 : (jt > 4 ? 4 : jt);
-        const double ft = tr0 - (double)(jt - 3);
-        const double tr1 = (tavel - c_lw.tref[jp]) / 15.;
-        int jt1 = (int)(3. + tr1);
-        jt1 = jt1 < 1 ? 1 : (jt1 > 4 ? 4 : jt1);
-        const double ft1 = tr1 - (double)(jt1 - 3);
-        const double water = wkl1 / coldry;
-        const double scalefac = pavel * stpfac / tavel;
-        double forfac, forfrac, selffac, selffrac = 0.0, factor;
-        int indfor, indself = 0;
-        forfac = scalefac / (1. + water);
-        selffac = water * forfac;
-        if (!(plog <= 4.56)) {
-            laytrop = laytrop + 1;
-            factor = (332.0 - tavel) / 36.0;
-            indfor = (int)factor;
-            indfor = indfor < 1 ? 1 : (indfor > 2 ? 2 : indfor);
-            forfrac = factor - (double)indfor;
-            factor = (tavel - 188.0) / 7.2;
-            indself = (int)factor - 7;
-            indself = indself < 1 ? 1 : (indself > 9 ? 9 : indself);
-            selffrac = factor - (double)(indself + 7);
-        } else {
-            factor = (tavel - 188.0) / 36.0;
-            indfor = 3;
-            forfrac = factor - 1.0;
-        }
-        const double scaleminor = pavel / tavel;
-        const double scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + wkl1));
-        factor = (tavel - 180.8) / 7.2;
-        int indminor = (int)factor;
-        indminor = indminor < 1 ? 1 : (indminor > 18 ? 18 : indminor);
-        const double minorfrac = factor - (double)indminor;
-
-        const double colh2o = 1.e-20 * wkl1;
-        double colco2 = 1.e-20 * wkl2, colo3 = 1.e-20 * wkl3, coln2o = 1.e-20 * wkl4;
-        double colco = 1.e-20 * wkl5, colch4 = 1.e-20 * wkl6;
-        const double colo2 = 1.e-20 * wkl7;
-        if (colco2 == 0.) colco2 = 1.e-32 * coldry;
-        if (colo3 == 0.) colo3 = 1.e-32 * coldry;
-        if (coln2o == 0.) coln2o = 1.e-32 * coldry;
-        if (colco == 0.) colco = 1.e-32 * coldry;
-        if (colch4 == 0.) colch4 = 1.e-32 * coldry;
-        const double colbrd = 1.e-20 * wbrodl;
-        const double compfp = 1. - fp;
-
-        w.idx[wo] = lw_pack(jp, jt, jt1, indself, indfor, indminor);
-        w.fld(LF_FAC10)[wo] = compfp * ft;
-        w.fld(LF_FAC00)[wo] = compfp * (1. - ft);
-        w.fld(LF_FAC11)[wo] = fp * ft1;
-        w.fld(LF_FAC01)[wo] = fp * (1. - ft1);
-        w.fld(LF_COLH2O)[wo] = colh2o;
-        w.fld(LF_COLCO2)[wo] = colco2;
-        w.fld(LF_COLO3)[wo] = colo3;
-        w.fld(LF_COLN2O)[wo] = coln2o;
-        w.fld(LF_COLCO)[wo] = colco;
-        w.fld(LF_COLCH4)[wo] = colch4;
-        w.fld(LF_COLO2)[wo] = colo2;
-        w.fld(LF_COLBRD)[wo] = colbrd;
-        w.fld(LF_SELFFAC)[wo] = colh2o * selffac;
-        w.fld(LF_SELFFRAC)[wo] = selffrac;
-        w.fld(LF_FORFAC)[wo] = colh2o * forfac;
-        w.fld(LF_FORFRAC)[wo] = forfrac;
-        w.fld(LF_MINORFRAC)[wo] = minorfrac;
-        w.fld(LF_SCALEMINOR)[wo] = scaleminor;
-        w.fld(LF_SCALEMINORN2)[wo] = scaleminorn2;
-        w.fld(LF_COLDRY)[wo] = coldry;
-        w.fld(LF_PAVEL)[wo] = pavel;
     }
     w.laytrop[col] = laytrop;
     // precipitable water and diffusivity secant per band
@@ -227,31 +257,73 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
 
 // =====================================================================================================
 // taumol: LW/src/rrtmg_lw_taumol.f90:260-3147 (taugb1..16)
+//
+// Every gas optical depth of RRTMG is a weighted sum of k-table rows, tau(g) = sum_k w_k * T[row_k][g],
+// with (w_k, row_k) depending only on the (column, layer) cell and the band.  Thread <-> cell (lanes =
+// 32 adjacent columns of one layer): the thread walks the band formula of taugbN, and every term is
+// consumed at once into NG register accumulators (NG = g-points of the band, compile-time), the table
+// row being read as NG/2 16-byte loads through the read-only path (rows of neighbouring columns mostly
+// coincide -> L1 broadcast).  No plan is ever stored.  The finished NG values per cell are transposed
+// through a per-warp shared-memory slab so that the staging fields are written [col][lay][g] (g
+// fastest, what the solver's g-lanes read) in 16-byte pieces.
 // =====================================================================================================
-constexpr int TP = 128;    // columns per tile == threads per block
-constexpr int KMAX = 24;   // most terms any band needs (band 13 lower: 6+6+2+2+4+4)
+constexpr int TM_WARPS = 4;        // warps per block; warp <-> one layer of a 32-column tile
+constexpr int TM_STRIDE = 18;      // slab row stride in doubles (36 words: conflict-free 16-byte accesses)
 
-struct PlanSmem {
-    double w[KMAX][TP];
-    int off[KMAX][TP];
-    double wf[2][TP];
-    int offf[2][TP];
-    int n[TP], nf[TP], gs[TP];
-};
-
-struct PW {
-    PlanSmem *s;
-    int t, n, nf;
-    __device__ __forceinline__ void add(int off, double wgt) { s->w[n][t] = wgt; s->off[n][t] = off; ++n; }
-    __device__ __forceinline__ void addf(int off, double wgt) { s->wf[nf][t] = wgt; s->offf[nf][t] = off; ++nf; }
-};
-
-struct LwPair {
-    int jp, jt, jt1, inds, indf, indm;
-    double fac00, fac01, fac10, fac11;
-    double colh2o, colco2, colo3, coln2o, colco, colch4, colo2, colbrd;
-    double selffac, selffrac, forfac, forfrac, minorfrac, scaleminor, scaleminorn2, coldry, pavel;
-    double wx1, wx2, wx3, wx4;
+template <int NG>
+struct BandAcc {
+    double t[NG];                    // taug accumulators of this cell
+    const double *__restrict__ tab;  // band table, [row][NG]
+    double *sf;                      // this lane's fracs row in the slab
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) t[g] = 0.0;
+    }
+    __device__ __forceinline__ void add(int off, double wgt)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            t[2 * j] = fma(wgt, v.x, t[2 * j]);
+            t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
+        }
+    }
+    __device__ __forceinline__ void scale(int off)      // taug(g) *= T[off + g]
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            t[2 * j] = t[2 * j] * v.x;
+            t[2 * j + 1] = t[2 * j + 1] * v.y;
+        }
+    }
+    __device__ __forceinline__ void frac1(int off)      // fracs(g) = T[off + g]
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) reinterpret_cast<double2 *>(sf)[j] = __ldg(q + j);
+    }
+    __device__ __forceinline__ void frac2(int o0, double w0, int o1, double w1)   // w0*T[o0+g] + w1*T[o1+g]
+    {
+        const double2 *__restrict__ q0 = reinterpret_cast<const double2 *>(tab + o0);
+        const double2 *__restrict__ q1 = reinterpret_cast<const double2 *>(tab + o1);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 a = __ldg(q0 + j), b = __ldg(q1 + j);
+            double2 r;
+            r.x = fma(w1, b.x, w0 * a.x);
+            r.y = fma(w1, b.y, w0 * a.y);
+            reinterpret_cast<double2 *>(sf)[j] = r;
+        }
+    }
+    __device__ __forceinline__ void fzero()
+    {
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) reinterpret_cast<double2 *>(sf)[j] = make_double2(0.0, 0.0);
+    }
 };
 
 struct Eta { double speccomb, specparm, fs; int js; };
@@ -270,6 +342,7 @@ __device__ __forceinline__ Eta binary(double colA, double rat, double colB, doub
 }
 
 // rows are Fortran 1-based; `sec` is the section's first row
+template <class PW>
 __device__ __forceinline__ void key4(PW &pw, const LwBand &B, int sec, int ind0, int ind1, double scale, const LwPair &p)
 {
     const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
@@ -278,6 +351,7 @@ __device__ __forceinline__ void key4(PW &pw, const LwBand &B, int sec, int ind0,
     pw.add(o1, scale * p.fac01);
     pw.add(o1 + ng, scale * p.fac11);
 }
+template <class PW>
 __device__ __forceinline__ void lerp2(PW &pw, const LwBand &B, int sec, int row, double frac, double scale)
 {
     const int ng = B.ng, o = (B.sec[sec] + row - 1) * ng;
@@ -285,6 +359,7 @@ __device__ __forceinline__ void lerp2(PW &pw, const LwBand &B, int sec, int row,
     pw.add(o + ng, scale * frac);
 }
 // minor gas with eta dimension, Fortran (neta,19,ng): 4-point (eta, T) interpolation
+template <class PW>
 __device__ __forceinline__ void minor_eta(PW &pw, const LwBand &B, int sec, int neta, int jm, double fm, int indm,
                                           double mf, double scale)
 {
@@ -296,6 +371,7 @@ __device__ __forceinline__ void minor_eta(PW &pw, const LwBand &B, int sec, int 
 }
 // lower-atmosphere binary-species key term: 3-point stencil near eta = 0 / 1, else 2-point
 // (template block repeated in taugb3,4,5,7,9,12,13,15,16, e.g. taumol.f90:548-606)
+template <class PW>
 __device__ __forceinline__ void stencil_lower(PW &pw, const LwBand &B, int ind, const Eta &e, double facA, double facB)
 {
     const int ng = B.ng, o = (B.sec[LS_ABSA] + ind - 1) * ng;
@@ -326,6 +402,7 @@ __device__ __forceinline__ void stencil_lower(PW &pw, const LwBand &B, int ind, 
     }
 }
 // upper-atmosphere binary key term (nspb = 5): always 2-point (e.g. taumol.f90:739-750)
+template <class PW>
 __device__ __forceinline__ void stencil_upper(PW &pw, const LwBand &B, int ind, const Eta &e, double facA, double facB)
 {
     const int ng = B.ng, o = (B.sec[LS_ABSB] + ind - 1) * ng;
@@ -335,13 +412,14 @@ __device__ __forceinline__ void stencil_upper(PW &pw, const LwBand &B, int ind, 
     pw.add(o + 5 * ng, sc * ((1. - e.fs) * facB));
     pw.add(o + 6 * ng, sc * (e.fs * facB));
 }
-__device__ __forceinline__ void frac_const(PW &pw, const LwBand &B, int sec) { pw.addf(B.sec[sec] * B.ng, 1.0); }
+template <class PW>
+__device__ __forceinline__ void frac_const(PW &pw, const LwBand &B, int sec) { pw.frac1(B.sec[sec] * B.ng); }
+template <class PW>
 __device__ __forceinline__ void frac_eta(PW &pw, const LwBand &B, int sec, double colA, double refrat, double colB, double mult)
 {
     const Eta e = binary(colA, refrat, colB, mult);
     const int o = (B.sec[sec] + e.js - 1) * B.ng;
-    pw.addf(o, 1. - e.fs);
-    pw.addf(o + B.ng, e.fs);
+    pw.frac2(o, 1. - e.fs, o + B.ng, e.fs);
 }
 // high-CO2 / high-N2O column adjustment (e.g. taumol.f90:529-535)
 __device__ __forceinline__ double adjcol(double col, double coldry, double chiref, double thresh, double a, double ex)
@@ -360,14 +438,17 @@ __device__ __forceinline__ double adjcol(double col, double coldry, double chire
 #define IND0B(nsp) (((p.jp - 13) * 5 + (p.jt - 1)) * (nsp))
 #define IND1B(nsp) (((p.jp - 12) * 5 + (p.jt1 - 1)) * (nsp))
 
-__device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
+__host__ __device__ constexpr int lw_ng(int band)
 {
-    const LwBand &B = c_lw.band[band];
-    int gs = -1;
-    pw.n = 0;
-    pw.nf = 0;
-    switch (band) {
-    case 0: { // band 1: 10-350 cm-1, H2O; N2 continuum minor (:280-373)
+    constexpr int ng[16] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+    return ng[band];
+}
+
+template <int BAND, class PW>
+__device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &pw)
+{
+    const LwBand &B = c_lw.band[BAND];
+    if constexpr (BAND == 0) { // band 1: 10-350 cm-1, H2O; N2 continuum minor (:280-373)
         const double scalen2 = p.colbrd * p.scaleminorn2;
         if (lower) {
             double corradj = 1.;
@@ -384,8 +465,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, corradj * scalen2);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 1: { // band 2: 350-500, H2O (:376-445)
+    } else if constexpr (BAND == 1) { // band 2: 350-500, H2O (:376-445)
         if (lower) {
             const double corradj = 1. - .05 * (p.pavel - 100.) / 900.;
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, corradj * p.colh2o, p);
@@ -397,8 +477,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 2: { // band 3: 500-630, H2O/CO2 both regions; N2O minor (:448-760)
+    } else if constexpr (BAND == 2) { // band 3: 500-630, H2O/CO2 both regions; N2O minor (:448-760)
         const double chin2o = CHI(4, p.jp + 1);
         const double adj = adjcol(p.coln2o, p.coldry, chin2o, 1.5, 0.5, 0.65);
         if (lower) {
@@ -421,8 +500,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             minor_eta(pw, B, LS_MB1, 5, em.js, em.fs, p.indm, p.minorfrac, adj);
             frac_eta(pw, B, LS_FRACB, p.colh2o, B.refrat[1], p.colco2, 4.);
         }
-    } break;
-    case 3: { // band 4: 630-700, H2O/CO2 lower, O3/CO2 upper (:763-1019)
+    } else if constexpr (BAND == 3) { // band 4: 630-700, H2O/CO2 lower, O3/CO2 upper (:763-1019)
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp - 1], p.colco2, 8.);
             const Eta e1 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp], p.colco2, 8.);
@@ -437,10 +515,9 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             stencil_upper(pw, B, IND0B(5) + e0.js, e0, p.fac00, p.fac10);
             stencil_upper(pw, B, IND1B(5) + e1.js, e1, p.fac01, p.fac11);
             frac_eta(pw, B, LS_FRACB, p.colo3, B.refrat[1], p.colco2, 4.);
-            gs = B.sec[LS_GSCALE] * B.ng;   // stratospheric g-point scaling (:1009-1015)
+            pw.scale(B.sec[LS_GSCALE] * B.ng);   // stratospheric g-point scaling (:1009-1015)
         }
-    } break;
-    case 4: { // band 5: 700-820, H2O/CO2 lower, O3/CO2 upper; O3 minor, CCl4 (:1022-1294)
+    } else if constexpr (BAND == 4) { // band 5: 700-820, H2O/CO2 lower, O3/CO2 upper; O3 minor, CCl4 (:1022-1294)
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp - 1], p.colco2, 8.);
             const Eta e1 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp], p.colco2, 8.);
@@ -460,8 +537,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             pw.add(B.sec[LS_X1] * B.ng, p.wx1);
             frac_eta(pw, B, LS_FRACB, p.colo3, B.refrat[1], p.colco2, 4.);
         }
-    } break;
-    case 5: { // band 6: 820-980, H2O lower; CO2 minor, CFC11, CFC12 (:1297-1380)
+    } else if constexpr (BAND == 5) { // band 6: 820-980, H2O lower; CO2 minor, CFC11, CFC12 (:1297-1380)
         if (lower) {
             const double adj = adjcol(p.colco2, p.coldry, CHI(2, p.jp + 1), 3.0, 2.0, 0.77);
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
@@ -472,8 +548,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
         pw.add(B.sec[LS_X1] * B.ng, p.wx2);
         pw.add(B.sec[LS_X2] * B.ng, p.wx3);
         frac_const(pw, B, LS_FRACA);
-    } break;
-    case 6: { // band 7: 980-1080, H2O/O3 lower, O3 upper; CO2 minor (:1383-1654)
+    } else if constexpr (BAND == 6) { // band 7: 980-1080, H2O/O3 lower, O3 upper; CO2 minor (:1383-1654)
         if (lower) {
             const double adj = adjcol(p.colco2, p.coldry, CHI(2, p.jp + 1), 3.0, 3.0, 0.79);
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2oo3[p.jp - 1], p.colo3, 8.);
@@ -490,10 +565,9 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             key4(pw, B, LS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo3, p);
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, adj);
             frac_const(pw, B, LS_FRACB);
-            gs = B.sec[LS_GSCALE] * B.ng;   // (:1645-1650)
+            pw.scale(B.sec[LS_GSCALE] * B.ng);   // (:1645-1650)
         }
-    } break;
-    case 7: { // band 8: 1080-1180, H2O lower, O3 upper; CO2, O3, N2O minors; CFC12, CFC22 (:1657-1777)
+    } else if constexpr (BAND == 7) { // band 8: 1080-1180, H2O lower, O3 upper; CO2, O3, N2O minors; CFC12, CFC22 (:1657-1777)
         const double adj = adjcol(p.colco2, p.coldry, CHI(2, p.jp + 1), 3.0, 2.0, 0.65);
         if (lower) {
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
@@ -511,8 +585,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
         }
         pw.add(B.sec[LS_X1] * B.ng, p.wx3);
         pw.add(B.sec[LS_X2] * B.ng, p.wx4);
-    } break;
-    case 8: { // band 9: 1180-1390, H2O/CH4 lower, CH4 upper; N2O minor (:1780-2040)
+    } else if constexpr (BAND == 8) { // band 9: 1180-1390, H2O/CH4 lower, CH4 upper; N2O minor (:1780-2040)
         const double adj = adjcol(p.coln2o, p.coldry, CHI(4, p.jp + 1), 1.5, 0.5, 0.65);
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2och4[p.jp - 1], p.colch4, 8.);
@@ -529,8 +602,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, adj);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 9: { // band 10: 1390-1480, H2O (:2043-2107)
+    } else if constexpr (BAND == 9) { // band 10: 1390-1480, H2O (:2043-2107)
         if (lower) {
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
@@ -541,8 +613,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 10: { // band 11: 1480-1800, H2O; O2 minor (:2110-2187)
+    } else if constexpr (BAND == 10) { // band 11: 1480-1800, H2O; O2 minor (:2110-2187)
         const double scaleo2 = p.colo2 * p.scaleminor;
         if (lower) {
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
@@ -556,8 +627,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, scaleo2);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 11: { // band 12: 1800-2080, H2O/CO2 lower; nothing above (:2190-2392)
+    } else if constexpr (BAND == 11) { // band 12: 1800-2080, H2O/CO2 lower; nothing above (:2190-2392)
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp - 1], p.colco2, 8.);
             const Eta e1 = binary(p.colh2o, c_lw.rat_h2oco2[p.jp], p.colco2, 8.);
@@ -566,9 +636,10 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             frac_eta(pw, B, LS_FRACA, p.colh2o, B.refrat[0], p.colco2, 8.);
+        } else {
+            pw.fzero();
         }
-    } break;
-    case 12: { // band 13: 2080-2250, H2O/N2O lower; CO2 + CO minors; O3 minor above (:2395-2652)
+    } else if constexpr (BAND == 12) { // band 13: 2080-2250, H2O/N2O lower; CO2 + CO minors; O3 minor above (:2395-2652)
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2on2o[p.jp - 1], p.coln2o, 8.);
             const Eta e1 = binary(p.colh2o, c_lw.rat_h2on2o[p.jp], p.coln2o, 8.);
@@ -586,8 +657,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, p.colo3);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 13: { // band 14: 2250-2380, CO2 (:2655-2713)
+    } else if constexpr (BAND == 13) { // band 14: 2250-2380, CO2 (:2655-2713)
         if (lower) {
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colco2, p);
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
@@ -597,8 +667,7 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             key4(pw, B, LS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colco2, p);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    case 14: { // band 15: 2380-2600, N2O/CO2 lower; N2 minor; nothing above (:2716-2938)
+    } else if constexpr (BAND == 14) { // band 15: 2380-2600, N2O/CO2 lower; N2 minor; nothing above (:2716-2938)
         if (lower) {
             const Eta e0 = binary(p.coln2o, c_lw.rat_n2oco2[p.jp - 1], p.colco2, 8.);
             const Eta e1 = binary(p.coln2o, c_lw.rat_n2oco2[p.jp], p.colco2, 8.);
@@ -610,9 +679,10 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             minor_eta(pw, B, LS_MA1, 9, em.js, em.fs, p.indm, p.minorfrac, scalen2);
             frac_eta(pw, B, LS_FRACA, p.coln2o, B.refrat[0], p.colco2, 8.);
+        } else {
+            pw.fzero();
         }
-    } break;
-    default: { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:2941-3147)
+    } else { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:2941-3147)
         if (lower) {
             const Eta e0 = binary(p.colh2o, c_lw.rat_h2och4[p.jp - 1], p.colch4, 8.);
             const Eta e1 = binary(p.colh2o, c_lw.rat_h2och4[p.jp], p.colch4, 8.);
@@ -628,86 +698,85 @@ __device__ void lw_plan_band(int band, const LwPair &p, bool lower, PW &pw)
             key4(pw, B, LS_ABSB, IND0B(0) + 1, IND1B(0) + 1, p.colch4, p);
             frac_const(pw, B, LS_FRACB);
         }
-    } break;
-    }
-    pw.s->n[pw.t] = pw.n;
-    pw.s->nf[pw.t] = pw.nf;
-    pw.s->gs[pw.t] = gs;
-}
-
-template <int NG>
-__device__ __forceinline__ void lw_exec_band(const PlanSmem &s, const double *__restrict__ tab, int g0,
-                                             double *__restrict__ taug, double *__restrict__ fracs,
-                                             int c0, int nvalid, int lay, int nlay)
-{
-    for (int cell = threadIdx.x; cell < TP * NG; cell += TP) {
-        const int pr = cell / NG, ig = cell - pr * NG;
-        if (pr >= nvalid) break;
-        const int n = s.n[pr];
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc = fma(s.w[k][pr], __ldg(tab + s.off[k][pr] + ig), acc);
-        const int gs = s.gs[pr];
-        if (gs >= 0) acc = acc * __ldg(tab + gs + ig);
-        const int nf = s.nf[pr];
-        double fr = 0.0;
-        if (nf > 0) fr = s.wf[0][pr] * __ldg(tab + s.offf[0][pr] + ig);
-        if (nf > 1) fr = fma(s.wf[1][pr], __ldg(tab + s.offf[1][pr] + ig), fr);
-        const size_t o = ((size_t)(c0 + pr) * nlay + lay) * NGPTLW + g0 + ig;
-        taug[o] = acc;
-        fracs[o] = fr;
     }
 }
 
-__global__ void __launch_bounds__(TP) lw_taumol_kernel(LwTables T, LwWork w)
+// One band of one warp's 32 cells: accumulate in registers, transpose through the warp's slab, write the
+// 32 x NG block of taug and fracs with 16-byte stores (g fastest).
+template <int BAND>
+__device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool valid, bool lower, double *slab,
+                                        double *__restrict__ taug, double *__restrict__ fracs,
+                                        size_t cell0, size_t colstride, int nvalid)
 {
-    __shared__ PlanSmem s;
-    const int t = threadIdx.x;
-    const int c0 = blockIdx.x * TP;
-    const int lay = blockIdx.y;               // 0-based layer
+    constexpr int NG = lw_ng(BAND);
+    const int lane = threadIdx.x & 31;
+    const LwBand &B = c_lw.band[BAND];
+    double *st = slab + lane * TM_STRIDE;                       // taug row of this lane
+    double *sf = slab + (32 + lane) * TM_STRIDE;                // fracs row
+    if (valid) {
+        BandAcc<NG> pw;
+        pw.tab = T.tab + B.base;
+        pw.sf = sf;
+        pw.clear();
+        lw_band_terms<BAND>(p, lower, pw);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) reinterpret_cast<double2 *>(st)[j] = make_double2(pw.t[2 * j], pw.t[2 * j + 1]);
+    }
+    __syncwarp();
+    constexpr int HP = NG / 2;                                  // 16-byte pieces per cell
+    const int g0 = B.g0;
+#pragma unroll
+    for (int i = lane; i < 32 * HP; i += 32) {
+        const int c = i / HP, j = i - c * HP;
+        if (c < nvalid) {
+            const double2 a = reinterpret_cast<const double2 *>(slab + c * TM_STRIDE)[j];
+            const double2 b = reinterpret_cast<const double2 *>(slab + (32 + c) * TM_STRIDE)[j];
+            const size_t o = cell0 + (size_t)c * colstride + g0 + 2 * j;
+            *reinterpret_cast<double2 *>(taug + o) = a;
+            *reinterpret_cast<double2 *>(fracs + o) = b;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * TM_WARPS) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
+{
+    __shared__ __align__(16) double s_slab[TM_WARPS][64 * TM_STRIDE];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int lay = blockIdx.y * TM_WARPS + wid;     // 0-based layer
     const int nlay = w.nlay, nc = w.nc;
-    const int col = c0 + t;
+    if (lay >= nlay) return;                         // no block-level barrier below
+    const int col = c0 + lane;
     const bool valid = col < nc;
-    const int nvalid = min(TP, nc - c0);
+    const int nvalid = min(32, nc - c0);
 
     LwPair p;
     bool lower = false;
     if (valid) {
-        const size_t wo = (size_t)lay * nc + col;
-        const LwIdx ix = lw_unpack(w.idx[wo]);
-        p.jp = ix.jp; p.jt = ix.jt; p.jt1 = ix.jt1; p.inds = ix.inds; p.indf = ix.indf; p.indm = ix.indm;
-        p.fac00 = w.fld(LF_FAC00)[wo]; p.fac01 = w.fld(LF_FAC01)[wo];
-        p.fac10 = w.fld(LF_FAC10)[wo]; p.fac11 = w.fld(LF_FAC11)[wo];
-        p.colh2o = w.fld(LF_COLH2O)[wo]; p.colco2 = w.fld(LF_COLCO2)[wo]; p.colo3 = w.fld(LF_COLO3)[wo];
-        p.coln2o = w.fld(LF_COLN2O)[wo]; p.colco = w.fld(LF_COLCO)[wo]; p.colch4 = w.fld(LF_COLCH4)[wo];
-        p.colo2 = w.fld(LF_COLO2)[wo]; p.colbrd = w.fld(LF_COLBRD)[wo];
-        p.selffac = w.fld(LF_SELFFAC)[wo]; p.selffrac = w.fld(LF_SELFFRAC)[wo];
-        p.forfac = w.fld(LF_FORFAC)[wo]; p.forfrac = w.fld(LF_FORFRAC)[wo];
-        p.minorfrac = w.fld(LF_MINORFRAC)[wo]; p.scaleminor = w.fld(LF_SCALEMINOR)[wo];
-        p.scaleminorn2 = w.fld(LF_SCALEMINORN2)[wo]; p.coldry = w.fld(LF_COLDRY)[wo];
-        p.pavel = w.fld(LF_PAVEL)[wo];
-        p.wx1 = w.fld(LF_WX1)[wo]; p.wx2 = w.fld(LF_WX2)[wo]; p.wx3 = w.fld(LF_WX3)[wo]; p.wx4 = w.fld(LF_WX4)[wo];
+        double wkl1;
+        lw_cell(in, col, lay, p, wkl1);
         lower = (lay + 1) <= w.laytrop[col];
     }
-    PW pw;
-    pw.s = &s;
-    pw.t = t;
-    for (int band = 0; band < NBNDLW; ++band) {
-        if (valid) lw_plan_band(band, p, lower, pw);
-        __syncthreads();
-        const LwBand &B = c_lw.band[band];
-        const double *tab = T.tab + B.base;
-        switch (B.ng) {
-        case 16: lw_exec_band<16>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 14: lw_exec_band<14>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 12: lw_exec_band<12>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 10: lw_exec_band<10>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 8: lw_exec_band<8>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 6: lw_exec_band<6>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        case 4: lw_exec_band<4>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        default: lw_exec_band<2>(s, tab, B.g0, w.taug, w.fracs, c0, nvalid, lay, nlay); break;
-        }
-        __syncthreads();
-    }
+    double *slab = s_slab[wid];
+    const size_t colstride = (size_t)nlay * NGPTLW;
+    const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTLW;
+    lw_band<0>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<1>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<2>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<3>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<4>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<5>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<6>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<7>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<8>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<9>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<10>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<11>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<12>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<13>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<14>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
+    lw_band<15>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
 }
 
 // =====================================================================================================
@@ -829,9 +898,9 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
     ktimer_begin(K_LW_PREP, s);
     lw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(t, in, w);
     ktimer_end(s);
-    dim3 grid((w.nc + TP - 1) / TP, w.nlay);
+    dim3 grid((w.nc + 31) / 32, (w.nlay + TM_WARPS - 1) / TM_WARPS);
     ktimer_begin(K_LW_TAUMOL, s);
-    lw_taumol_kernel<<<grid, TP, 0, s>>>(t, w);
+    lw_taumol_kernel<<<grid, 32 * TM_WARPS, 0, s>>>(t, in, w);
     ktimer_end(s);
     if (cap) {
         const size_t n = (size_t)w.nc * w.nlay * NGPTLW;
@@ -839,7 +908,11 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
         cudaMemcpyAsync(cap + n, w.fracs, n * 8, cudaMemcpyDeviceToDevice, s);
     }
     ktimer_begin(K_LW_RTRN, s);
-    lw_rtrn_kernel<<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w);
+    {
+        const size_t pad = (size_t)g_tune.lw_rtrn_pad_kb * 1024;
+        cudaFuncSetAttribute(lw_rtrn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        lw_rtrn_kernel<<<w.nc, RT_THREADS, pad, s>>>(t, in, out, w);
+    }
     ktimer_end(s);
     return 3;
 }

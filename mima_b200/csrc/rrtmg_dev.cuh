@@ -222,6 +222,11 @@ enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_
 void ktimer_begin(int id, cudaStream_t s);
 void ktimer_end(cudaStream_t s);
 
+// launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb"): extra dynamic shared memory per block,
+// used to cap the resident blocks per SM so that the sweeps' per-thread state stays L2-resident
+struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb; };
+extern Tuning g_tune;
+
 // kernel launchers (defined in lw_kernels.cu / sw_kernels.cu); each returns the number of launches
 int lw_upload_const(const LwConst &c);
 int sw_upload_const(const SwConst &c);

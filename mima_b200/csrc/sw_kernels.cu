@@ -30,105 +30,125 @@ int sw_upload_const(const SwConst &c)
 
 constexpr double ZEPZEN = 1.e-10;
 
+// Interpolation state of one (column, layer) cell: what setcoef_sw hands to taumol_sw.
+struct SwPair {
+    int jp, jt, jt1, inds, indf;
+    double fac00, fac01, fac10, fac11;
+    double colh2o, colco2, colo3, colch4, colo2, colmol, coln2o;
+    double selffac, selffrac, forfac, forfrac;
+};
+
 // =====================================================================================================
-// prep: inatm_sw (SW/src/rrtmg_sw_rad.nomcica.f90:761-1101) + setcoef_sw (SW/src/rrtmg_sw_setcoef.f90:30-286)
-//       + solar-source layer selection of taumol16..29 (SW/src/rrtmg_sw_taumol.f90, "laysolfr" logic)
+// inatm_sw (SW/src/rrtmg_sw_rad.nomcica.f90:761-1101) + setcoef_sw (SW/src/rrtmg_sw_setcoef.f90:30-286)
+// for one (column, layer) cell; shared by the prep kernel (column-integrated quantities) and the taumol
+// kernel (which evaluates the cell state in place).  Returns true when the layer counts towards laytrop.
+// =====================================================================================================
+__device__ __forceinline__ bool sw_cell(const SwIn &in, int col, int l, SwPair &p)
+{
+    const double amd = 28.9660, amw = 18.0160, amdw = 1.607793, amdo = 0.603428;
+    const double grav = 9.8066, avogad = 6.02214199e+23;
+    const double stpfac = 296. / 1013.;
+    const size_t ld = (size_t)in.ld;
+    const size_t o = col + (size_t)l * ld;
+    const double pavel = in.play[o], tavel = in.tlay[o];
+    const double pzm = in.plev[o], pz = in.plev[o + ld];
+    const double q = in.h2o[o];
+    double wkl1 = (q / (1. - q)) * amdw;
+    double wkl2 = in.co2[o];
+    double wkl3 = in.o3[o] * amdo;
+    double wkl4 = in.n2o ? in.n2o[o] : 0.0;
+    double wkl6 = in.ch4 ? in.ch4[o] : 0.0;
+    double wkl7 = in.o2 ? in.o2[o] : 0.0;
+    const double amm = (1. - wkl1) * amd + wkl1 * amw;
+    const double coldry = (pzm - pz) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + wkl1));
+    wkl1 = coldry * wkl1; wkl2 = coldry * wkl2; wkl3 = coldry * wkl3; wkl4 = coldry * wkl4;
+    wkl6 = coldry * wkl6; wkl7 = coldry * wkl7;
+
+    const double plog = log(pavel);
+    int jp = (int)(36. - 5 * (plog + 0.04));
+    jp = jp < 1 ? 1 : (jp > 58 ? 58 : jp);
+    const double fp = 5. * (c_sw.preflog[jp - 1] - plog);
+    const double tr0 = (tavel - c_sw.tref[jp - 1]) / 15.;
+    int jt = (int)(3. + tr0);
+    jt = jt < 1 ? 1 : (jt > 4 ? 4 : jt);
+    const double ft = tr0 - (double)(jt - 3);
+    const double tr1 = (tavel - c_sw.tref[jp]) / 15.;
+    int jt1 = (int)(3. + tr1);
+    jt1 = jt1 < 1 ? 1 : (jt1 > 4 ? 4 : jt1);
+    const double ft1 = tr1 - (double)(jt1 - 3);
+    const double water = wkl1 / coldry;
+    const double scalefac = pavel * stpfac / tavel;
+    const double forfac = scalefac / (1. + water);
+    double forfrac, selffac = 0.0, selffrac = 0.0, factor;
+    int indfor, indself = 0;
+    const bool lower = !(plog <= 4.56);
+    if (lower) {
+        factor = (332.0 - tavel) / 36.0;
+        indfor = (int)factor;
+        indfor = indfor < 1 ? 1 : (indfor > 2 ? 2 : indfor);
+        forfrac = factor - (double)indfor;
+        selffac = water * forfac;
+        factor = (tavel - 188.0) / 7.2;
+        indself = (int)factor - 7;
+        indself = indself < 1 ? 1 : (indself > 9 ? 9 : indself);
+        selffrac = factor - (double)(indself + 7);
+    } else {
+        factor = (tavel - 188.0) / 36.0;
+        indfor = 3;
+        forfrac = factor - 1.0;
+    }
+    p.colh2o = 1.e-20 * wkl1;
+    double colco2 = 1.e-20 * wkl2;
+    p.colo3 = 1.e-20 * wkl3;
+    double coln2o = 1.e-20 * wkl4, colch4 = 1.e-20 * wkl6, colo2 = 1.e-20 * wkl7;
+    p.colmol = 1.e-20 * coldry + p.colh2o;
+    if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+    if (coln2o == 0.) coln2o = 1.e-32 * coldry;
+    if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+    if (colo2 == 0.) colo2 = 1.e-32 * coldry;
+    p.colco2 = colco2; p.coln2o = coln2o; p.colch4 = colch4; p.colo2 = colo2;
+    const double compfp = 1. - fp;
+    p.jp = jp; p.jt = jt; p.jt1 = jt1; p.inds = indself; p.indf = indfor;
+    p.fac10 = compfp * ft;
+    p.fac00 = compfp * (1. - ft);
+    p.fac11 = fp * ft1;
+    p.fac01 = fp * (1. - ft1);
+    p.selffac = selffac; p.selffrac = selffrac; p.forfac = forfac; p.forfrac = forfrac;
+    return lower;
+}
+
+// =====================================================================================================
+// prep: per column -- night marker, laytrop (setcoef.f90), and the layer whose binary-species parameter
+//       selects the solar source of each band (SW/src/rrtmg_sw_taumol.f90, "laysolfr" logic).
+//       With w.f != nullptr (stage capture, test hook) the per-cell setcoef state is also written out.
 // =====================================================================================================
 __global__ void __launch_bounds__(128) sw_prep_kernel(SwIn in, SwWork w)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= w.nc) return;
     const int nlay = w.nlay, nc = w.nc;
-    const size_t ld = (size_t)in.ld;
     if (in.coszen[col] < ZEPZEN) {
         w.laytrop[col] = -1;    // night column marker
         return;
     }
-    const double amd = 28.9660, amw = 18.0160, amdw = 1.607793, amdo = 0.603428;
-    const double grav = 9.8066, avogad = 6.02214199e+23;
-    const double stpfac = 296. / 1013.;
     unsigned char jpv[MAXLAY + 2];
-    double pzm = in.plev[col];
     int laytrop = 0;
     jpv[0] = 0;
     for (int l = 0; l < nlay; ++l) {
-        const size_t o = col + (size_t)l * ld;
-        const size_t wo = (size_t)l * nc + col;
-        const double pavel = in.play[o], tavel = in.tlay[o];
-        const double pz = in.plev[o + ld];
-        const double q = in.h2o[o];
-        double wkl1 = (q / (1. - q)) * amdw;
-        double wkl2 = in.co2[o];
-        double wkl3 = in.o3[o] * amdo;
-        double wkl4 = in.n2o ? in.n2o[o] : 0.0;
-        double wkl6 = in.ch4 ? in.ch4[o] : 0.0;
-        double wkl7 = in.o2 ? in.o2[o] : 0.0;
-        const double amm = (1. - wkl1) * amd + wkl1 * amw;
-        const double coldry = (pzm - pz) * 1.e3 * avogad / (1.e2 * grav * amm * (1. + wkl1));
-        pzm = pz;
-        wkl1 = coldry * wkl1; wkl2 = coldry * wkl2; wkl3 = coldry * wkl3; wkl4 = coldry * wkl4;
-        wkl6 = coldry * wkl6; wkl7 = coldry * wkl7;
-
-        const double plog = log(pavel);
-        int jp = (int)(36. - 5 * (plog + 0.04));
-        jp = jp < 1 ? 1 : (jp > 58 ? 58 : jp);
-        jpv[l + 1] = (unsigned char)jp;
-        const double fp = 5. * (c_sw.preflog[jp - 1] - plog);
-        const double tr0 = (tavel - c_sw.tref[jp - 1]) / 15.;
-        int jt = (int)(3. + tr0);
-        jt = jt < 1 ? 1 : (jt > 4 ? 4 : jt);
-        const double ft = tr0 - (double)(jt - 3);
-        const double tr1 = (tavel - c_sw.tref[jp]) / 15.;
-        int jt1 = (int)(3. + tr1);
-        jt1 = jt1 < 1 ? 1 : (jt1 > 4 ? 4 : jt1);
-        const double ft1 = tr1 - (double)(jt1 - 3);
-        const double water = wkl1 / coldry;
-        const double scalefac = pavel * stpfac / tavel;
-        const double forfac = scalefac / (1. + water);
-        double forfrac, selffac = 0.0, selffrac = 0.0, factor;
-        int indfor, indself = 0;
-        if (!(plog <= 4.56)) {
-            laytrop = laytrop + 1;
-            factor = (332.0 - tavel) / 36.0;
-            indfor = (int)factor;
-            indfor = indfor < 1 ? 1 : (indfor > 2 ? 2 : indfor);
-            forfrac = factor - (double)indfor;
-            selffac = water * forfac;
-            factor = (tavel - 188.0) / 7.2;
-            indself = (int)factor - 7;
-            indself = indself < 1 ? 1 : (indself > 9 ? 9 : indself);
-            selffrac = factor - (double)(indself + 7);
-        } else {
-            factor = (tavel - 188.0) / 36.0;
-            indfor = 3;
-            forfrac = factor - 1.0;
+        SwPair p;
+        if (sw_cell(in, col, l, p)) laytrop = laytrop + 1;
+        jpv[l + 1] = (unsigned char)p.jp;
+        if (w.f) {
+            const size_t wo = (size_t)l * nc + col;
+            w.idx[wo] = sw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf);
+            w.fld(SF_FAC00)[wo] = p.fac00; w.fld(SF_FAC01)[wo] = p.fac01;
+            w.fld(SF_FAC10)[wo] = p.fac10; w.fld(SF_FAC11)[wo] = p.fac11;
+            w.fld(SF_COLH2O)[wo] = p.colh2o; w.fld(SF_COLCO2)[wo] = p.colco2; w.fld(SF_COLO3)[wo] = p.colo3;
+            w.fld(SF_COLCH4)[wo] = p.colch4; w.fld(SF_COLO2)[wo] = p.colo2; w.fld(SF_COLMOL)[wo] = p.colmol;
+            w.fld(SF_COLN2O)[wo] = p.coln2o;
+            w.fld(SF_SELFFAC)[wo] = p.selffac; w.fld(SF_SELFFRAC)[wo] = p.selffrac;
+            w.fld(SF_FORFAC)[wo] = p.forfac; w.fld(SF_FORFRAC)[wo] = p.forfrac;
         }
-        const double colh2o = 1.e-20 * wkl1;
-        double colco2 = 1.e-20 * wkl2;
-        const double colo3 = 1.e-20 * wkl3;
-        double coln2o = 1.e-20 * wkl4, colch4 = 1.e-20 * wkl6, colo2 = 1.e-20 * wkl7;
-        const double colmol = 1.e-20 * coldry + colh2o;
-        if (colco2 == 0.) colco2 = 1.e-32 * coldry;
-        if (coln2o == 0.) coln2o = 1.e-32 * coldry;
-        if (colch4 == 0.) colch4 = 1.e-32 * coldry;
-        if (colo2 == 0.) colo2 = 1.e-32 * coldry;
-        const double compfp = 1. - fp;
-        w.idx[wo] = sw_pack(jp, jt, jt1, indself, indfor);
-        w.fld(SF_FAC10)[wo] = compfp * ft;
-        w.fld(SF_FAC00)[wo] = compfp * (1. - ft);
-        w.fld(SF_FAC11)[wo] = fp * ft1;
-        w.fld(SF_FAC01)[wo] = fp * (1. - ft1);
-        w.fld(SF_COLH2O)[wo] = colh2o;
-        w.fld(SF_COLCO2)[wo] = colco2;
-        w.fld(SF_COLO3)[wo] = colo3;
-        w.fld(SF_COLCH4)[wo] = colch4;
-        w.fld(SF_COLO2)[wo] = colo2;
-        w.fld(SF_COLMOL)[wo] = colmol;
-        w.fld(SF_COLN2O)[wo] = coln2o;
-        w.fld(SF_SELFFAC)[wo] = selffac;
-        w.fld(SF_SELFFRAC)[wo] = selffrac;
-        w.fld(SF_FORFAC)[wo] = forfac;
-        w.fld(SF_FORFRAC)[wo] = forfrac;
     }
     jpv[nlay + 1] = 0;
     w.laytrop[col] = laytrop;
@@ -162,36 +182,69 @@ __global__ void __launch_bounds__(128) sw_prep_kernel(SwIn in, SwWork w)
 }
 
 // =====================================================================================================
-// taumol_sw: SW/src/rrtmg_sw_taumol.f90:223-1536 (taumol16..29)
+// taumol_sw: SW/src/rrtmg_sw_taumol.f90:223-1536 (taumol16..29).  Same structure as the LW taumol kernel:
+// thread <-> (column, layer) cell, register accumulators per band, per-warp slab transpose to
+// [col][lay][g].  taur (Rayleigh) is a one- or two-row product and goes straight to the slab; the solar
+// source sfluxzen is written by the single cell the reference leaves it from (laysolfr).
 // =====================================================================================================
-constexpr int TP = 128;
-constexpr int KMAX = 14;   // band 24 lower: 8 + 1 + 2 + 2
+constexpr int TM_WARPS = 4;
+constexpr int TM_STRIDE = 18;
 
-struct PlanSmem {
-    double w[KMAX][TP];
-    int off[KMAX][TP];
-    double wr[2][TP];   // Rayleigh terms
-    int offr[2][TP];
-    double ws[2][TP];   // solar-source terms (only at the laysolfr layer)
-    int offs[2][TP];
-    double cst[TP];
-    int n[TP], nr[TP], ns[TP];
-};
-
-struct PW {
-    PlanSmem *s;
-    int t, n, nr, ns;
-    double cst;
-    __device__ __forceinline__ void add(int off, double wgt) { s->w[n][t] = wgt; s->off[n][t] = off; ++n; }
-    __device__ __forceinline__ void addr(int off, double wgt) { s->wr[nr][t] = wgt; s->offr[nr][t] = off; ++nr; }
-    __device__ __forceinline__ void adds(int off, double wgt) { s->ws[ns][t] = wgt; s->offs[ns][t] = off; ++ns; }
-};
-
-struct SwPair {
-    int jp, jt, jt1, inds, indf;
-    double fac00, fac01, fac10, fac11;
-    double colh2o, colco2, colo3, colch4, colo2, colmol;
-    double selffac, selffrac, forfac, forfrac;
+template <int NG>
+struct BandAcc {
+    double t[NG];
+    const double *__restrict__ tab;
+    double *sr;                      // this lane's taur row in the slab
+    double *sflx;                    // this cell's column slot in sfluxzen (+ g0)
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) t[g] = 0.0;
+    }
+    __device__ __forceinline__ void add(int off, double wgt)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            t[2 * j] = fma(wgt, v.x, t[2 * j]);
+            t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
+        }
+    }
+    __device__ __forceinline__ void addc(double c)
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) t[g] = t[g] + c;
+    }
+    __device__ __forceinline__ void rayl1(int off, double wgt)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            reinterpret_cast<double2 *>(sr)[j] = make_double2(wgt * v.x, wgt * v.y);
+        }
+    }
+    __device__ __forceinline__ void rayl2(int o0, double w0, int o1, double w1)
+    {
+        const double2 *__restrict__ q0 = reinterpret_cast<const double2 *>(tab + o0);
+        const double2 *__restrict__ q1 = reinterpret_cast<const double2 *>(tab + o1);
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) {
+            const double2 a = __ldg(q0 + j), b = __ldg(q1 + j);
+            reinterpret_cast<double2 *>(sr)[j] = make_double2(fma(w1, b.x, w0 * a.x), fma(w1, b.y, w0 * a.y));
+        }
+    }
+    __device__ __forceinline__ void sflux1(int off, double wgt)
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) sflx[g] = wgt * __ldg(tab + off + g);
+    }
+    __device__ __forceinline__ void sflux2(int o0, double w0, int o1, double w1)
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) sflx[g] = fma(w1, __ldg(tab + o1 + g), w0 * __ldg(tab + o0 + g));
+    }
 };
 
 struct Eta { double speccomb, fs; int js; };
@@ -207,6 +260,7 @@ __device__ __forceinline__ Eta binary(double colA, double strrat, double colB, d
     e.fs = specmult - (double)i;
     return e;
 }
+template <class PW>
 __device__ __forceinline__ void key4(PW &pw, const SwBand &B, int sec, int ind0, int ind1, double scale, const SwPair &p)
 {
     const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
@@ -216,6 +270,7 @@ __device__ __forceinline__ void key4(PW &pw, const SwBand &B, int sec, int ind0,
     pw.add(o1 + ng, scale * p.fac11);
 }
 // 8-point binary key term; one eta for both pressure levels; dT = 9 (lower) / 5 (upper)
+template <class PW>
 __device__ __forceinline__ void key8(PW &pw, const SwBand &B, int sec, int ind0, int ind1, int dT, const Eta &e, const SwPair &p)
 {
     const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
@@ -229,23 +284,26 @@ __device__ __forceinline__ void key8(PW &pw, const SwBand &B, int sec, int ind0,
     pw.add(o1 + dT * ng, sc * (a * p.fac11));
     pw.add(o1 + (dT + 1) * ng, sc * (b * p.fac11));
 }
+template <class PW>
 __device__ __forceinline__ void lerp2(PW &pw, const SwBand &B, int sec, int row, double frac, double scale)
 {
     const int ng = B.ng, o = (B.sec[sec] + row - 1) * ng;
     pw.add(o, scale * (1. - frac));
     pw.add(o + ng, scale * frac);
 }
+template <class PW>
 __device__ __forceinline__ void selffor(PW &pw, const SwBand &B, const SwPair &p, double scale)
 {
     lerp2(pw, B, SS_SELF, p.inds, p.selffrac, scale * p.selffac);
     lerp2(pw, B, SS_FOR, p.indf, p.forfrac, scale * p.forfac);
 }
-__device__ __forceinline__ void sflux_const(PW &pw, const SwBand &B, double scale) { pw.adds(B.sec[SS_SFLUX] * B.ng, scale); }
+template <class PW>
+__device__ __forceinline__ void sflux_const(PW &pw, const SwBand &B, double scale) { pw.sflux1(B.sec[SS_SFLUX] * B.ng, scale); }
+template <class PW>
 __device__ __forceinline__ void sflux_eta(PW &pw, const SwBand &B, const Eta &e)
 {
     const int o = (B.sec[SS_SFLUX] + e.js - 1) * B.ng;
-    pw.adds(o, 1. - e.fs);
-    pw.adds(o + B.ng, e.fs);
+    pw.sflux2(o, 1. - e.fs, o + B.ng, e.fs);
 }
 
 #define IND0A(nsp) (((p.jp - 1) * 5 + (p.jt - 1)) * (nsp))
@@ -253,15 +311,20 @@ __device__ __forceinline__ void sflux_eta(PW &pw, const SwBand &B, const Eta &e)
 #define IND0B(nsp) (((p.jp - 13) * 5 + (p.jt - 1)) * (nsp))
 #define IND1B(nsp) (((p.jp - 12) * 5 + (p.jt1 - 1)) * (nsp))
 
-// `solar` = this layer is the one whose values the reference leaves in sfluxzen for this band
-__device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, PW &pw)
+__host__ __device__ constexpr int sw_ng(int band)
 {
-    const SwBand &B = c_sw.band[band];
-    pw.n = 0; pw.nr = 0; pw.ns = 0; pw.cst = 0.0;
+    constexpr int ng[14] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};
+    return ng[band];
+}
+
+// `solar` = this layer is the one whose values the reference leaves in sfluxzen for this band
+template <int BAND, class PW>
+__device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool solar, PW &pw)
+{
+    const SwBand &B = c_sw.band[BAND];
     // Rayleigh: scalar-rayl bands carry one row filled with the scalar; band 24 lower is eta-interpolated
-    bool rayl_done = false;
-    switch (band) {
-    case 0: { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:243-339)
+    if constexpr (BAND != 8) pw.rayl1(B.sec[SS_RAYL] * B.ng, p.colmol);
+    if constexpr (BAND == 0) { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:243-339)
         if (lower) {
             const Eta e = binary(p.colh2o, 252.131, p.colch4, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -270,8 +333,7 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colch4, p);
             if (solar) sflux_const(pw, B, 1.0);
         }
-    } break;
-    case 1: { // band 17: 3250-4000, H2O/CO2 both (:342-462)
+    } else if constexpr (BAND == 1) { // band 17: 3250-4000, H2O/CO2 both (:342-462)
         if (lower) {
             const Eta e = binary(p.colh2o, 0.364641, p.colco2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -282,10 +344,9 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             lerp2(pw, B, SS_FOR, p.indf, p.forfrac, p.colh2o * p.forfac);
             if (solar) sflux_eta(pw, B, e);
         }
-    } break;
-    case 2: case 3: { // band 18: 4000-4650 H2O/CH4, CH4 (:465-561); band 19: 4650-5150 H2O/CO2, CO2 (:564-660)
-        const double strrat = band == 2 ? 38.9589 : 5.49281;
-        const double colB = band == 2 ? p.colch4 : p.colco2;
+    } else if constexpr (BAND == 2 || BAND == 3) { // band 18: 4000-4650 H2O/CH4, CH4 (:465-561); band 19: 4650-5150 H2O/CO2, CO2 (:564-660)
+        const double strrat = BAND == 2 ? 38.9589 : 5.49281;
+        const double colB = BAND == 2 ? p.colch4 : p.colco2;
         if (lower) {
             const Eta e = binary(p.colh2o, strrat, colB, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -294,8 +355,7 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, colB, p);
         }
-    } break;
-    case 4: { // band 20: 5150-6150, H2O + CH4 (:663-746)
+    } else if constexpr (BAND == 4) { // band 20: 5150-6150, H2O + CH4 (:663-746)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             selffor(pw, B, p, p.colh2o);
@@ -305,8 +365,7 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             lerp2(pw, B, SS_FOR, p.indf, p.forfrac, p.colh2o * p.forfac);
         }
         pw.add(B.sec[SS_X1] * B.ng, p.colch4);
-    } break;
-    case 5: { // band 21: 6150-7700, H2O/CO2 both (:749-868)
+    } else if constexpr (BAND == 5) { // band 21: 6150-7700, H2O/CO2 both (:749-868)
         if (lower) {
             const Eta e = binary(p.colh2o, 0.0045321, p.colco2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -317,10 +376,8 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             key8(pw, B, SS_ABSB, IND0B(5) + e.js, IND1B(5) + e.js, 5, e, p);
             lerp2(pw, B, SS_FOR, p.indf, p.forfrac, p.colh2o * p.forfac);
         }
-    } break;
-    case 6: { // band 22: 7700-8050, H2O/O2 lower, O2 upper, O2 continuum (:871-977)
+    } else if constexpr (BAND == 6) { // band 22: 7700-8050, H2O/O2 lower, O2 upper, O2 continuum (:871-977)
         const double o2adj = 1.6;
-        pw.cst = 4.35e-4 * p.colo2 / (350.0 * 2.0);
         if (lower) {
             const Eta e = binary(p.colh2o, o2adj * 0.022708, p.colo2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -329,15 +386,14 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo2 * o2adj, p);
         }
-    } break;
-    case 7: { // band 23: 8050-12850, H2O lower (Giver factor), nothing above (:980-1051)
+        pw.addc(4.35e-4 * p.colo2 / (350.0 * 2.0));
+    } else if constexpr (BAND == 7) { // band 23: 8050-12850, H2O lower (Giver factor), nothing above (:980-1051)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o * 1.029, p);
             selffor(pw, B, p, p.colh2o);
             if (solar) sflux_const(pw, B, 1.0);
         }
-    } break;
-    case 8: { // band 24: 12850-16000, H2O/O2 lower, O2 upper, O3 (:1054-1153)
+    } else if constexpr (BAND == 8) { // band 24: 12850-16000, H2O/O2 lower, O2 upper, O3 (:1054-1153)
         if (lower) {
             const Eta e = binary(p.colh2o, 0.124692, p.colo2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -345,16 +401,13 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             selffor(pw, B, p, p.colh2o);
             if (solar) sflux_eta(pw, B, e);
             const int o = (B.sec[SS_RAYL] + e.js - 1) * B.ng;
-            pw.addr(o, p.colmol * (1. - e.fs));
-            pw.addr(o + B.ng, p.colmol * e.fs);
+            pw.rayl2(o, p.colmol * (1. - e.fs), o + B.ng, p.colmol * e.fs);
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo2, p);
             pw.add(B.sec[SS_X2] * B.ng, p.colo3);
-            pw.addr(B.sec[SS_RAYLB] * B.ng, p.colmol);
+            pw.rayl1(B.sec[SS_RAYLB] * B.ng, p.colmol);
         }
-        rayl_done = true;
-    } break;
-    case 9: { // band 25: 16000-22650, H2O lower, O3 (:1156-1217)
+    } else if constexpr (BAND == 9) { // band 25: 16000-22650, H2O lower, O3 (:1156-1217)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             pw.add(B.sec[SS_X1] * B.ng, p.colo3);
@@ -362,19 +415,16 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
         } else {
             pw.add(B.sec[SS_X2] * B.ng, p.colo3);
         }
-    } break;
-    case 10: { // band 26: 22650-29000, Rayleigh only (:1220-1268)
+    } else if constexpr (BAND == 10) { // band 26: 22650-29000, Rayleigh only (:1220-1268)
         if (lower && solar) sflux_const(pw, B, 1.0);
-    } break;
-    case 11: { // band 27: 29000-38000, O3 (:1271-1347)
+    } else if constexpr (BAND == 11) { // band 27: 29000-38000, O3 (:1271-1347)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colo3, p);
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo3, p);
             if (solar) sflux_const(pw, B, 50.15 / 48.37);
         }
-    } break;
-    case 12: { // band 28: 38000-50000, O3/O2 both (:1350-1455)
+    } else if constexpr (BAND == 12) { // band 28: 38000-50000, O3/O2 both (:1350-1455)
         if (lower) {
             const Eta e = binary(p.colo3, 6.67029e-07, p.colo2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
@@ -383,8 +433,7 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             key8(pw, B, SS_ABSB, IND0B(5) + e.js, IND1B(5) + e.js, 5, e, p);
             if (solar) sflux_eta(pw, B, e);
         }
-    } break;
-    default: { // band 29: 820-2600, H2O lower + CO2, CO2 upper + H2O (:1458-1536)
+    } else { // band 29: 820-2600, H2O lower + CO2, CO2 upper + H2O (:1458-1536)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             selffor(pw, B, p, p.colh2o);
@@ -394,91 +443,78 @@ __device__ void sw_plan_band(int band, const SwPair &p, bool lower, bool solar, 
             pw.add(B.sec[SS_X1] * B.ng, p.colh2o);
             if (solar) sflux_const(pw, B, 1.0);
         }
-    } break;
     }
-    if (!rayl_done) pw.addr(B.sec[SS_RAYL] * B.ng, p.colmol);
-    pw.s->n[pw.t] = pw.n;
-    pw.s->nr[pw.t] = pw.nr;
-    pw.s->ns[pw.t] = pw.ns;
-    pw.s->cst[pw.t] = pw.cst;
 }
 
-template <int NG>
-__device__ __forceinline__ void sw_exec_band(const PlanSmem &s, const double *__restrict__ tab, int g0,
-                                             double *__restrict__ taug, double *__restrict__ taur,
-                                             double *__restrict__ sflx, int c0, int nvalid, int lay, int nlay)
+template <int BAND>
+__device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool valid, bool lower, int lay1,
+                                        const int *__restrict__ laysolfr, double *slab,
+                                        double *__restrict__ taug, double *__restrict__ taur, double *sflx_col,
+                                        size_t cell0, size_t colstride, unsigned vmask)
 {
-    for (int cell = threadIdx.x; cell < TP * NG; cell += TP) {
-        const int pr = cell / NG, ig = cell - pr * NG;
-        if (pr >= nvalid) break;
-        const int n = s.n[pr];
-        if (n < 0) continue;          // night column
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc = fma(s.w[k][pr], __ldg(tab + s.off[k][pr] + ig), acc);
-        acc = acc + s.cst[pr];
-        double r = s.wr[0][pr] * __ldg(tab + s.offr[0][pr] + ig);
-        if (s.nr[pr] > 1) r = fma(s.wr[1][pr], __ldg(tab + s.offr[1][pr] + ig), r);
-        const size_t o = ((size_t)(c0 + pr) * nlay + lay) * NGPTSW + g0 + ig;
-        taug[o] = acc;
-        taur[o] = r;
-        const int ns = s.ns[pr];
-        if (ns > 0) {
-            double f = s.ws[0][pr] * __ldg(tab + s.offs[0][pr] + ig);
-            if (ns > 1) f = fma(s.ws[1][pr], __ldg(tab + s.offs[1][pr] + ig), f);
-            sflx[(size_t)(c0 + pr) * NGPTSW + g0 + ig] = f;
+    constexpr int NG = sw_ng(BAND);
+    const int lane = threadIdx.x & 31;
+    const SwBand &B = c_sw.band[BAND];
+    const int g0 = B.g0;
+    if (valid) {
+        BandAcc<NG> pw;
+        pw.tab = T.tab + B.base;
+        pw.sr = slab + (32 + lane) * TM_STRIDE;
+        pw.sflx = sflx_col + g0;
+        pw.clear();
+        sw_band_terms<BAND>(p, lower, laysolfr[BAND] == lay1, pw);
+        double *st = slab + lane * TM_STRIDE;
+#pragma unroll
+        for (int j = 0; j < NG / 2; ++j) reinterpret_cast<double2 *>(st)[j] = make_double2(pw.t[2 * j], pw.t[2 * j + 1]);
+    }
+    __syncwarp();
+    constexpr int HP = NG / 2;
+#pragma unroll
+    for (int i = lane; i < 32 * HP; i += 32) {
+        const int c = i / HP, j = i - c * HP;
+        if ((vmask >> c) & 1u) {
+            const double2 a = reinterpret_cast<const double2 *>(slab + c * TM_STRIDE)[j];
+            const double2 b = reinterpret_cast<const double2 *>(slab + (32 + c) * TM_STRIDE)[j];
+            const size_t o = cell0 + (size_t)c * colstride + g0 + 2 * j;
+            *reinterpret_cast<double2 *>(taug + o) = a;
+            *reinterpret_cast<double2 *>(taur + o) = b;
         }
     }
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(TP) sw_taumol_kernel(SwTables T, SwWork w)
+__global__ void __launch_bounds__(32 * TM_WARPS) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
 {
-    __shared__ PlanSmem s;
-    const int t = threadIdx.x;
-    const int c0 = blockIdx.x * TP;
-    const int lay = blockIdx.y;
+    __shared__ __align__(16) double s_slab[TM_WARPS][64 * TM_STRIDE];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int lay = blockIdx.y * TM_WARPS + wid;
     const int nlay = w.nlay, nc = w.nc;
-    const int col = c0 + t;
+    if (lay >= nlay) return;                         // no block-level barrier below
+    const int col = c0 + lane;
     bool valid = col < nc;
-    const int nvalid = min(TP, nc - c0);
-    SwPair p;
-    bool lower = false;
     int laytrop = 0;
     if (valid) {
         laytrop = w.laytrop[col];
-        if (laytrop < 0) { valid = false; s.n[t] = -1; }
+        if (laytrop < 0) valid = false;              // night column: the solver never reads its staging
     }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (vmask == 0u) return;
+    SwPair p;
+    bool lower = false;
     if (valid) {
-        const size_t wo = (size_t)lay * nc + col;
-        const uint32_t v = w.idx[wo];
-        p.jp = v & 63; p.jt = (v >> 6) & 7; p.jt1 = (v >> 9) & 7; p.inds = (v >> 12) & 15; p.indf = (v >> 16) & 3;
-        p.fac00 = w.fld(SF_FAC00)[wo]; p.fac01 = w.fld(SF_FAC01)[wo];
-        p.fac10 = w.fld(SF_FAC10)[wo]; p.fac11 = w.fld(SF_FAC11)[wo];
-        p.colh2o = w.fld(SF_COLH2O)[wo]; p.colco2 = w.fld(SF_COLCO2)[wo]; p.colo3 = w.fld(SF_COLO3)[wo];
-        p.colch4 = w.fld(SF_COLCH4)[wo]; p.colo2 = w.fld(SF_COLO2)[wo]; p.colmol = w.fld(SF_COLMOL)[wo];
-        p.selffac = w.fld(SF_SELFFAC)[wo]; p.selffrac = w.fld(SF_SELFFRAC)[wo];
-        p.forfac = w.fld(SF_FORFAC)[wo]; p.forfrac = w.fld(SF_FORFRAC)[wo];
+        sw_cell(in, col, lay, p);
         lower = (lay + 1) <= laytrop;
     }
-    PW pw;
-    pw.s = &s;
-    pw.t = t;
-    for (int band = 0; band < NBNDSW; ++band) {
-        if (valid) {
-            const bool solar = (w.laysolfr[(size_t)col * 14 + band] == lay + 1);
-            sw_plan_band(band, p, lower, solar, pw);
-        }
-        __syncthreads();
-        const SwBand &B = c_sw.band[band];
-        const double *tab = T.tab + B.base;
-        switch (B.ng) {
-        case 12: sw_exec_band<12>(s, tab, B.g0, w.taug, w.taur, w.sfluxzen, c0, nvalid, lay, nlay); break;
-        case 10: sw_exec_band<10>(s, tab, B.g0, w.taug, w.taur, w.sfluxzen, c0, nvalid, lay, nlay); break;
-        case 8: sw_exec_band<8>(s, tab, B.g0, w.taug, w.taur, w.sfluxzen, c0, nvalid, lay, nlay); break;
-        case 6: sw_exec_band<6>(s, tab, B.g0, w.taug, w.taur, w.sfluxzen, c0, nvalid, lay, nlay); break;
-        default: sw_exec_band<2>(s, tab, B.g0, w.taug, w.taur, w.sfluxzen, c0, nvalid, lay, nlay); break;
-        }
-        __syncthreads();
-    }
+    double *slab = s_slab[wid];
+    const int *ls = w.laysolfr + (size_t)(valid ? col : 0) * 14;
+    double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
+    const size_t colstride = (size_t)nlay * NGPTSW;
+    const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTSW;
+#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, w.taur, sflx, cell0, colstride, vmask)
+    SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
+    SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
+#undef SW_BAND
 }
 
 // =====================================================================================================
@@ -692,13 +728,21 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_begin(K_SW_PREP, s);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
     ktimer_end(s);
-    dim3 grid((w.nc + TP - 1) / TP, w.nlay);
+    dim3 grid((w.nc + 31) / 32, (w.nlay + TM_WARPS - 1) / TM_WARPS);
     ktimer_begin(K_SW_TAUMOL, s);
-    sw_taumol_kernel<<<grid, TP, 0, s>>>(t, w);
+    sw_taumol_kernel<<<grid, 32 * TM_WARPS, 0, s>>>(t, in, w);
     ktimer_end(s);
     ktimer_begin(K_SW_SOLVER, s);
-    if (w.nlay <= 64) sw_solver_kernel<64><<<w.nc, SV_THREADS, 0, s>>>(t, in, out, w);
-    else sw_solver_kernel<MAXLAY><<<w.nc, SV_THREADS, 0, s>>>(t, in, out, w);
+    {
+        const size_t pad = (size_t)g_tune.sw_solver_pad_kb * 1024;
+        if (w.nlay <= 64) {
+            cudaFuncSetAttribute(sw_solver_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            sw_solver_kernel<64><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
+        } else {
+            cudaFuncSetAttribute(sw_solver_kernel<MAXLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            sw_solver_kernel<MAXLAY><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
+        }
+    }
     ktimer_end(s);
     return 3;
 }
