@@ -15,14 +15,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librrtmg_b200.so")
-SOURCES = ["api.cu", "lw_kernels.cu", "sw_kernels.cu"]
+# (source, FMA contraction).  setcoef/taumol decide table indices and branches from FP64 arithmetic and are
+# compiled with -fmad=false so that those decisions match an IEEE host evaluation bit for bit (fused
+# multiply-adds appear only where written as fma()); the solvers carry no such decisions and may contract.
+SOURCES = [("api.cu", False), ("lw_kernels.cu", False), ("sw_kernels.cu", False),
+           ("lw_solver.cu", True), ("sw_solver.cu", True)]
 HEADERS = ["rrtmg_dev.cuh", os.path.join("..", "..", "include", "rrtmg_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
-    "-shared",
 ]
 
 
@@ -37,7 +40,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in [x for x, _ in SOURCES] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -45,19 +48,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    env = dict(os.environ)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    cc = [nvcc()]
     # the image exports CC/CXX pointing at a gcc wrapper without OpenMP specs; nvcc only needs a host g++
-    for host in ("/usr/bin/g++",):
-        if os.path.exists(host):
-            cmd[1:1] = ["-ccbin", host]
-            break
-    r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+    if os.path.exists("/usr/bin/g++"):
+        cc += ["-ccbin", "/usr/bin/g++"]
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(item):
+        src, fmad = item
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = cc + NVCC_FLAGS + ["-fmad=true" if fmad else "-fmad=false"] + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        return obj, r
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for obj, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building " + obj)
+        if verbose:
+            sys.stderr.write(r.stderr)
+    r = subprocess.run(cc + ["-shared", "-o", LIB] + [o for o, _ in results], cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building librrtmg_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking librrtmg_b200.so")
     return LIB
 
 

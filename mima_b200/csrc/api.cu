@@ -614,7 +614,7 @@ struct Stager {
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0};
+Tuning g_tune = {0, 0, 0};
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -977,6 +977,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
+    if (k == "sw_solver_store") { g_tune.sw_solver_store = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "kernel_timing") { KT.collect(); KT.on = value != 0; return RRTMG_B200_OK; }
     return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "unknown option " + k);

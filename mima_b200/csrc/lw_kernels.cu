@@ -4,14 +4,11 @@
 // GPU-first design:
 //   lw_prep_kernel    thread <-> column, one sweep over layers: unit conversion, column amounts,
 //                     p/T interpolation indices and weights, Planck sources.  Coalesced column-major reads.
-//   lw_taumol_kernel  tile = 128 adjacent columns of one layer.  For each of the 16 bands:
-//                       plan    (thread <-> column): turn the band formula of taugbN into a short list of
-//                               (table row, weight) terms in shared memory -- every gas optical depth of
-//                               RRTMG is a weighted sum of k-table rows;
-//                       execute (thread <-> (column, g-point), g fastest): tau = sum_k w_k * T[row_k][g],
-//                               table rows read as contiguous g-segments through the read-only path.
-//   lw_rtrn_kernel    block <-> column, thread <-> g-point: down sweep, surface, up sweep; per-level warp
-//                     shuffle reduction over g-points, cross-warp reduction through shared memory.
+//   lw_taumol_kernel  thread <-> (column, layer) cell, lanes = 32 adjacent columns; blockIdx.z selects a band
+//                     slice, so that the blocks resident on an SM at any time run the same few bands (their
+//                     code fits the instruction cache and their k-tables the L1).  Terms of the band
+//                     formula are consumed into register accumulators as they are produced.
+//   lw_rtrn_kernel    (lw_solver.cu) block <-> column, thread <-> g-point.
 // Compiled with -fmad=false: fused multiply-adds appear only where written as fma().
 #include "rrtmg_dev.cuh"
 
@@ -27,7 +24,7 @@ int lw_upload_const(const LwConst &c)
         for (int i = 0; i < c.band[b].ng; ++i) ngb[c.band[b].g0 + i] = (unsigned char)b;
     if (cudaMemcpyToSymbol(c_lw, &c, sizeof(LwConst)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_lw_ngb, ngb, sizeof ngb) != cudaSuccess) return -1;
-    return 0;
+    return lw_solver_upload_const(c, ngb);
 }
 
 #define CHI(m, j) c_lw.chi_mls[((j) - 1) * 7 + ((m) - 1)]
@@ -267,7 +264,6 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
 // through a per-warp shared-memory slab so that the staging fields are written [col][lay][g] (g
 // fastest, what the solver's g-lanes read) in 16-byte pieces.
 // =====================================================================================================
-constexpr int TM_WARPS = 4;        // warps per block; warp <-> one layer of a 32-column tile
 constexpr int TM_STRIDE = 18;      // slab row stride in doubles (36 words: conflict-free 16-byte accesses)
 
 template <int NG>
@@ -374,31 +370,26 @@ __device__ __forceinline__ void minor_eta(PW &pw, const LwBand &B, int sec, int 
 template <class PW>
 __device__ __forceinline__ void stencil_lower(PW &pw, const LwBand &B, int ind, const Eta &e, double facA, double facB)
 {
-    const int ng = B.ng, o = (B.sec[LS_ABSA] + ind - 1) * ng;
+    // One instruction stream for the three cases: rows (o, o+1[, o+2]) and (o+9, o+10[, o+11]) with
+    //   eta < 0.125 : o = ind,     weights (fk0, fk1, fk2)
+    //   eta > 0.875 : o = ind - 1, weights (fk2, fk1, fk0)
+    //   otherwise   : o = ind,     weights (1-fs, fs)
+    const int ng = B.ng;
     const double sc = e.speccomb;
-    if (e.specparm < 0.125) {
-        const double p = e.fs - 1, p4 = (p * p) * (p * p);
-        const double fk0 = p4, fk1 = 1 - p - 2.0 * p4, fk2 = p + p4;
-        pw.add(o, sc * (fk0 * facA));
-        pw.add(o + ng, sc * (fk1 * facA));
-        pw.add(o + 2 * ng, sc * (fk2 * facA));
-        pw.add(o + 9 * ng, sc * (fk0 * facB));
-        pw.add(o + 10 * ng, sc * (fk1 * facB));
-        pw.add(o + 11 * ng, sc * (fk2 * facB));
-    } else if (e.specparm > 0.875) {
-        const double p = -e.fs, p4 = (p * p) * (p * p);
-        const double fk0 = p4, fk1 = 1 - p - 2.0 * p4, fk2 = p + p4;
-        pw.add(o - ng, sc * (fk2 * facA));
-        pw.add(o, sc * (fk1 * facA));
-        pw.add(o + ng, sc * (fk0 * facA));
-        pw.add(o + 8 * ng, sc * (fk2 * facB));
-        pw.add(o + 9 * ng, sc * (fk1 * facB));
-        pw.add(o + 10 * ng, sc * (fk0 * facB));
-    } else {
-        pw.add(o, sc * ((1. - e.fs) * facA));
-        pw.add(o + ng, sc * (e.fs * facA));
-        pw.add(o + 9 * ng, sc * ((1. - e.fs) * facB));
-        pw.add(o + 10 * ng, sc * (e.fs * facB));
+    const bool lo = e.specparm < 0.125, hi = e.specparm > 0.875;
+    const double p = lo ? e.fs - 1 : -e.fs, p4 = (p * p) * (p * p);
+    const double fk0 = p4, fk1 = 1 - p - 2.0 * p4, fk2 = p + p4;
+    const double w0 = lo ? fk0 : (hi ? fk2 : 1. - e.fs);
+    const double w1 = (lo || hi) ? fk1 : e.fs;
+    const double w2 = lo ? fk2 : fk0;
+    const int o = (B.sec[LS_ABSA] + ind - 1 - (hi ? 1 : 0)) * ng;
+    pw.add(o, sc * (w0 * facA));
+    pw.add(o + ng, sc * (w1 * facA));
+    pw.add(o + 9 * ng, sc * (w0 * facB));
+    pw.add(o + 10 * ng, sc * (w1 * facB));
+    if (lo || hi) {
+        pw.add(o + 2 * ng, sc * (w2 * facA));
+        pw.add(o + 11 * ng, sc * (w2 * facB));
     }
 }
 // upper-atmosphere binary key term (nspb = 5): always 2-point (e.g. taumol.f90:739-750)
@@ -739,17 +730,25 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * TM_WARPS) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
+// The 16 warps of a block walk through the bands together (one barrier per band): the straight-line band
+// code (~300 KB for all bands) is then fetched once per block instead of once per warp -- with
+// independent warps the kernel was bound by instruction-cache misses.  Work items are (32-column tile,
+// layer) pairs, linearised so that no warp idles when nlay is not a multiple of the block's warp count.
+constexpr int TM_BLOCK_WARPS = 16;
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 1) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
 {
-    __shared__ __align__(16) double s_slab[TM_WARPS][64 * TM_STRIDE];
+    extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32;
-    const int lay = blockIdx.y * TM_WARPS + wid;     // 0-based layer
     const int nlay = w.nlay, nc = w.nc;
-    if (lay >= nlay) return;                         // no block-level barrier below
+    const int ntile = (nc + 31) / 32;
+    const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
+    const bool live = item < (long)ntile * nlay;
+    const int tile = live ? (int)(item / nlay) : 0;
+    const int lay = live ? (int)(item - (long)tile * nlay) : 0;     // 0-based layer
+    const int c0 = tile * 32;
     const int col = c0 + lane;
-    const bool valid = col < nc;
-    const int nvalid = min(32, nc - c0);
+    const bool valid = live && col < nc;
+    const int nvalid = live ? min(32, nc - c0) : 0;
 
     LwPair p;
     bool lower = false;
@@ -758,139 +757,13 @@ __global__ void __launch_bounds__(32 * TM_WARPS) lw_taumol_kernel(LwTables T, Lw
         lw_cell(in, col, lay, p, wkl1);
         lower = (lay + 1) <= w.laytrop[col];
     }
-    double *slab = s_slab[wid];
+    double *slab = s_dyn + (size_t)wid * (64 * TM_STRIDE);
     const size_t colstride = (size_t)nlay * NGPTLW;
     const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTLW;
-    lw_band<0>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<1>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<2>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<3>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<4>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<5>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<6>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<7>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<8>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<9>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<10>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<11>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<12>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<13>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<14>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-    lw_band<15>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid);
-}
-
-// =====================================================================================================
-// rtrn: clear-sky radiative transfer, LW/src/rrtmg_lw_rtrnmr.f90:481-777 ("Clear layer" branches; identical
-// in rtrnmc.f90:407-432,481-503).  taut = taug + tauaer (rad.nomcica:514-519, iaer = 10 forced).
-// The staging fields are overwritten in place: taug -> atrans, fracs -> bbugas (needed by the up sweep).
-// =====================================================================================================
-constexpr int RT_THREADS = 160;   // 140 g-points -> 5 warps
-constexpr int RT_S = 141;         // tile row stride (odd)
-
-__global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
-{
-    __shared__ double s_tile[16 * RT_S];
-    __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
-    __shared__ double s_dn[MAXLAY + 1], s_up[MAXLAY + 1];
-    const int col = blockIdx.x;
-    const int nlay = w.nlay;
-    const int g = threadIdx.x;
-    const bool active = g < NGPTLW;
-    const int band = active ? c_lw_ngb[g] : 0;
-    const double secd = w.secdiff[(size_t)col * 16 + band];
-    const double wgt = active ? 0.5 * c_lw.delwave[band] : 0.0;     // wtdiff * delwave
-    const double bpade = c_lw.bpade;
-    const double rec_6 = 0.166667;
-    const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
-    double *taug = w.taug + (size_t)col * nlay * NGPTLW + g;
-    double *fracs = w.fracs + (size_t)col * nlay * NGPTLW + g;
-    const double *pl = w.planklay + (size_t)col * nlay * 16 + band;
-    const double *pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
-    const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
-
-    // ---- downward sweep (:505-618); batches of 16 levels go through tile_reduce16
-    double radld = 0.0;
-    double plfrac1 = 0.0;
-    for (int k = 0; k < nlay; ++k) {
-        const int lev = nlay - k;
-        const int slot = k & 15;
-        if (active) {
-            const size_t o = (size_t)(lev - 1) * NGPTLW;
-            const double plfrac = fracs[o];
-            const double blay = pl[(lev - 1) * 16];
-            const double dplankup = pv[lev * 16] - blay;
-            const double dplankdn = pv[(lev - 1) * 16] - blay;
-            double taut = taug[o];
-            if (taer) taut = taut + taer[(size_t)(lev - 1) * in.ld];
-            double odepth = secd * taut;
-            if (odepth < 0.0) odepth = 0.0;
-            double atrans, bbd, bbugas;
-            if (odepth <= 0.06) {
-                atrans = odepth - 0.5 * odepth * odepth;
-                odepth = rec_6 * odepth;
-                bbd = plfrac * (blay + dplankdn * odepth);
-                bbugas = plfrac * (blay + dplankup * odepth);
-            } else {
-                const double tblind = odepth * rcp_fast(bpade + odepth);
-                const int itr = (int)(10000.0 * tblind + 0.5);
-                const double2 e = __ldg(et + itr);
-                atrans = 1. - e.x;
-                bbd = plfrac * (blay + e.y * dplankdn);
-                bbugas = plfrac * (blay + e.y * dplankup);
-            }
-            radld = fma(bbd - radld, atrans, radld);
-            taug[o] = atrans;
-            fracs[o] = bbugas;
-            s_tile[slot * RT_S + g] = radld * wgt;
-            if (lev == 1) plfrac1 = plfrac;
-        }
-        if (slot == 15 || k == nlay - 1) {
-            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
-            const int kk = (k & ~15) + threadIdx.x;
-            if (threadIdx.x < 16 && kk <= k) s_dn[nlay - 1 - kk] = sum * c_lw.fluxfac;
-        }
-    }
-    if (threadIdx.x == 0) s_dn[nlay] = 0.0;   // no downward flux enters at the top (drad(nlayers) = 0)
-
-    // ---- surface (:628-636) and upward sweep (:649-711); level k = 0 is the surface
-    double radlu = 0.0;
-    for (int k = 0; k <= nlay; ++k) {
-        const int slot = k & 15;
-        if (active) {
-            if (k == 0) {
-                const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
-                const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
-                const double reflect = 1. - semiss;
-                radlu = rad0 + reflect * radld;
-            } else {
-                const size_t o = (size_t)(k - 1) * NGPTLW;
-                const double atrans = taug[o], bbugas = fracs[o];
-                radlu = fma(bbugas - radlu, atrans, radlu);
-            }
-            s_tile[slot * RT_S + g] = radlu * wgt;
-        }
-        if (slot == 15 || k == nlay) {
-            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
-            const int kk = (k & ~15) + threadIdx.x;
-            if (threadIdx.x < 16 && kk <= k) s_up[kk] = sum * c_lw.fluxfac;
-        }
-    }
-    __syncthreads();
-
-    // ---- fluxes and heating rates (:751-777), copy-out (rad.nomcica:546-555)
-    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
-        const size_t o = col + (size_t)lev * out.ld;
-        const double u = s_up[lev], d = s_dn[lev];
-        out.uflx[o] = u; out.dflx[o] = d;
-        out.uflxc[o] = u; out.dflxc[o] = d;
-        if (lev < nlay) {
-            const double fnet0 = u - d, fnet1 = s_up[lev + 1] - s_dn[lev + 1];
-            const double pz0 = in.plev[col + (size_t)lev * in.ld], pz1 = in.plev[col + (size_t)(lev + 1) * in.ld];
-            const double h = c_lw.heatfac * (fnet0 - fnet1) / (pz0 - pz1);
-            out.hr[o] = h;
-            out.hrc[o] = h;
-        }
-    }
+#define LW_BAND(b) lw_band<b>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid); __syncthreads()
+    LW_BAND(0); LW_BAND(1); LW_BAND(2); LW_BAND(3); LW_BAND(4); LW_BAND(5); LW_BAND(6); LW_BAND(7);
+    LW_BAND(8); LW_BAND(9); LW_BAND(10); LW_BAND(11); LW_BAND(12); LW_BAND(13); LW_BAND(14); LW_BAND(15);
+#undef LW_BAND
 }
 
 int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, double *cap)
@@ -898,21 +771,21 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
     ktimer_begin(K_LW_PREP, s);
     lw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(t, in, w);
     ktimer_end(s);
-    dim3 grid((w.nc + 31) / 32, (w.nlay + TM_WARPS - 1) / TM_WARPS);
-    ktimer_begin(K_LW_TAUMOL, s);
-    lw_taumol_kernel<<<grid, 32 * TM_WARPS, 0, s>>>(t, in, w);
-    ktimer_end(s);
+    {
+        const long items = (long)((w.nc + 31) / 32) * w.nlay;
+        const size_t smem = (size_t)TM_BLOCK_WARPS * 64 * TM_STRIDE * sizeof(double);
+        cudaFuncSetAttribute(lw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ktimer_begin(K_LW_TAUMOL, s);
+        lw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w);
+        ktimer_end(s);
+    }
     if (cap) {
         const size_t n = (size_t)w.nc * w.nlay * NGPTLW;
         cudaMemcpyAsync(cap, w.taug, n * 8, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(cap + n, w.fracs, n * 8, cudaMemcpyDeviceToDevice, s);
     }
     ktimer_begin(K_LW_RTRN, s);
-    {
-        const size_t pad = (size_t)g_tune.lw_rtrn_pad_kb * 1024;
-        cudaFuncSetAttribute(lw_rtrn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        lw_rtrn_kernel<<<w.nc, RT_THREADS, pad, s>>>(t, in, out, w);
-    }
+    lw_launch_rtrn(t, in, out, w, s);
     ktimer_end(s);
     return 3;
 }

@@ -1,0 +1,179 @@
+// lw_solver.cu -- RRTMG longwave clear-sky radiative transfer on sm_100a.
+//
+// rtrn: LW/src/rrtmg_lw_rtrnmr.f90:481-777 ("Clear layer" branches; identical in rtrnmc.f90:407-432,481-503).
+//       taut = taug + tauaer (rad.nomcica:514-519, iaer = 10 forced).
+//
+// Block <-> column, thread <-> g-point (the staging fields are [col][lay][g], so one level step of a warp
+// reads 256 contiguous bytes per field).  Levels are processed four at a time: the eight staging loads of
+// a group are issued before any of its arithmetic, which is what keeps enough bytes in flight to stream
+// from HBM.  The up sweep recomputes the layer transmittance and source from taug/fracs instead of
+// storing them (a second read of 16 B per cell instead of a write plus a read).  The sum over g-points
+// goes through shared memory in batches of 16 levels (tile_reduce16, fixed summation order).
+//
+// This translation unit is compiled with FMA contraction on (build.py): the flux arithmetic has no
+// index/branch decisions that depend on the last bit, unlike setcoef in lw_kernels.cu.
+#include "rrtmg_dev.cuh"
+
+namespace rrtmg {
+
+struct LwSolverConst {
+    double delwave[NBNDLW];
+    double heatfac, fluxfac, bpade;
+    unsigned char ngb[NGPTLW];
+};
+__constant__ LwSolverConst c_ls;
+
+int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb)
+{
+    LwSolverConst h;
+    for (int b = 0; b < NBNDLW; ++b) h.delwave[b] = c.delwave[b];
+    h.heatfac = c.heatfac; h.fluxfac = c.fluxfac; h.bpade = c.bpade;
+    for (int g = 0; g < NGPTLW; ++g) h.ngb[g] = ngb[g];
+    return cudaMemcpyToSymbol(c_ls, &h, sizeof h) == cudaSuccess ? 0 : -1;
+}
+
+constexpr int RT_THREADS = 160;   // 140 g-points -> 5 warps
+constexpr int RT_S = 141;         // tile row stride (odd)
+constexpr int RT_U = 4;           // levels per load group
+
+// layer transmittance and Planck-weighted sources of one (g, layer) cell (:589-607)
+__device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double bpade, double secd, double taut,
+                                         double plfrac, double blay, double dplankup, double dplankdn,
+                                         double &atrans, double &bbd, double &bbugas)
+{
+    const double rec_6 = 0.166667;
+    double odepth = secd * taut;
+    if (odepth < 0.0) odepth = 0.0;
+    if (odepth <= 0.06) {
+        atrans = odepth - 0.5 * odepth * odepth;
+        odepth = rec_6 * odepth;
+        bbd = plfrac * (blay + dplankdn * odepth);
+        bbugas = plfrac * (blay + dplankup * odepth);
+    } else {
+        const double tblind = odepth * rcp_fast(bpade + odepth);
+        const int itr = (int)(10000.0 * tblind + 0.5);
+        const double2 e = __ldg(et + itr);
+        atrans = 1. - e.x;
+        bbd = plfrac * (blay + e.y * dplankdn);
+        bbugas = plfrac * (blay + e.y * dplankup);
+    }
+}
+
+__global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
+{
+    __shared__ double s_tile[16 * RT_S];
+    __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
+    __shared__ double s_dn[MAXLAY + 1], s_up[MAXLAY + 1];
+    const int col = blockIdx.x;
+    const int nlay = w.nlay;
+    const int g = threadIdx.x;
+    const bool active = g < NGPTLW;
+    const int band = active ? c_ls.ngb[g] : 0;
+    const double secd = w.secdiff[(size_t)col * 16 + band];
+    const double wgt = active ? 0.5 * c_ls.delwave[band] : 0.0;     // wtdiff * delwave
+    const double bpade = c_ls.bpade;
+    const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
+    const double *__restrict__ taug = w.taug + (size_t)col * nlay * NGPTLW + (active ? g : 0);
+    const double *__restrict__ fracs = w.fracs + (size_t)col * nlay * NGPTLW + (active ? g : 0);
+    const double *__restrict__ pl = w.planklay + (size_t)col * nlay * 16 + band;
+    const double *__restrict__ pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
+    const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
+
+    // ---- downward sweep (:505-618), k counts layers from the top
+    double radld = 0.0;
+    double plfrac1 = 0.0;
+    for (int k0 = 0; k0 < nlay; k0 += RT_U) {
+        double tg[RT_U], fr[RT_U], bl[RT_U], pu[RT_U], pd[RT_U];
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) {
+            const int lay = max(nlay - 1 - (k0 + j), 0);            // 0-based layer (clamped in the ragged tail)
+            tg[j] = taug[(size_t)lay * NGPTLW];
+            fr[j] = fracs[(size_t)lay * NGPTLW];
+            if (taer) tg[j] = tg[j] + taer[(size_t)lay * in.ld];
+            bl[j] = pl[lay * 16];
+            pu[j] = pv[(lay + 1) * 16];
+            pd[j] = pv[lay * 16];
+        }
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) {
+            const int k = k0 + j;
+            if (k < nlay) {
+                double atrans, bbd, bbugas;
+                lw_layer(et, bpade, secd, tg[j], fr[j], bl[j], pu[j] - bl[j], pd[j] - bl[j], atrans, bbd, bbugas);
+                radld = radld + (bbd - radld) * atrans;
+                if (active) s_tile[(k & 15) * RT_S + g] = radld * wgt;
+                if (k == nlay - 1) plfrac1 = fr[j];
+            }
+        }
+        const int klast = min(k0 + RT_U, nlay) - 1;
+        if ((klast & 15) == 15 || klast == nlay - 1) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (klast & ~15) + threadIdx.x;
+            if (threadIdx.x < 16 && kk <= klast) s_dn[nlay - 1 - kk] = sum * c_ls.fluxfac;
+        }
+    }
+    if (threadIdx.x == 0) s_dn[nlay] = 0.0;   // no downward flux enters at the top (drad(nlayers) = 0)
+
+    // ---- surface (:628-636) and upward sweep (:649-711); level k = 0 is the surface, level k > 0 the top
+    //      of layer k (1-based).  Groups are aligned to the 16-level batches of the reduction.
+    double radlu = 0.0;
+    for (int k0 = 0; k0 <= nlay; k0 += RT_U) {
+        double tg[RT_U], fr[RT_U], bl[RT_U], pu[RT_U];
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) {
+            const int lay = min(max(k0 + j, 1), nlay) - 1;
+            tg[j] = taug[(size_t)lay * NGPTLW];
+            fr[j] = fracs[(size_t)lay * NGPTLW];
+            if (taer) tg[j] = tg[j] + taer[(size_t)lay * in.ld];
+            bl[j] = pl[lay * 16];
+            pu[j] = pv[(lay + 1) * 16];
+        }
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) {
+            const int k = k0 + j;
+            if (k == 0) {
+                const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
+                const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
+                const double reflect = 1. - semiss;
+                radlu = rad0 + reflect * radld;
+                if (active) s_tile[g] = radlu * wgt;
+            } else if (k <= nlay) {
+                double atrans, bbd, bbugas;
+                lw_layer(et, bpade, secd, tg[j], fr[j], bl[j], pu[j] - bl[j], 0.0, atrans, bbd, bbugas);
+                radlu = radlu + (bbugas - radlu) * atrans;
+                if (active) s_tile[(k & 15) * RT_S + g] = radlu * wgt;
+            }
+        }
+        const int klast = min(k0 + RT_U - 1, nlay);
+        if ((klast & 15) == 15 || klast == nlay) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (klast & ~15) + threadIdx.x;
+            if (threadIdx.x < 16 && kk <= klast) s_up[kk] = sum * c_ls.fluxfac;
+        }
+    }
+    __syncthreads();
+
+    // ---- fluxes and heating rates (:751-777), copy-out (rad.nomcica:546-555)
+    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
+        const size_t o = col + (size_t)lev * out.ld;
+        const double u = s_up[lev], d = s_dn[lev];
+        out.uflx[o] = u; out.dflx[o] = d;
+        out.uflxc[o] = u; out.dflxc[o] = d;
+        if (lev < nlay) {
+            const double fnet0 = u - d, fnet1 = s_up[lev + 1] - s_dn[lev + 1];
+            const double pz0 = in.plev[col + (size_t)lev * in.ld], pz1 = in.plev[col + (size_t)(lev + 1) * in.ld];
+            const double h = c_ls.heatfac * (fnet0 - fnet1) / (pz0 - pz1);
+            out.hr[o] = h;
+            out.hrc[o] = h;
+        }
+    }
+}
+
+void lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
+{
+    const size_t pad = (size_t)g_tune.lw_rtrn_pad_kb * 1024;
+    if (pad) cudaFuncSetAttribute(lw_rtrn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    lw_rtrn_kernel<<<w.nc, RT_THREADS, pad, s>>>(t, in, out, w);
+}
+
+} // namespace rrtmg

@@ -222,10 +222,16 @@ enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_
 void ktimer_begin(int id, cudaStream_t s);
 void ktimer_end(cudaStream_t s);
 
-// launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb"): extra dynamic shared memory per block,
+// launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb", "sw_solver_store"): extra dynamic shared memory per block,
 // used to cap the resident blocks per SM so that the sweeps' per-thread state stays L2-resident
-struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb; };
+struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store; };
 extern Tuning g_tune;
+
+// solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)
+int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb);
+int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb);
+void lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s);
+void sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s);
 
 // kernel launchers (defined in lw_kernels.cu / sw_kernels.cu); each returns the number of launches
 int lw_upload_const(const LwConst &c);

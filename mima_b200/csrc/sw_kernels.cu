@@ -25,7 +25,7 @@ int sw_upload_const(const SwConst &c)
         for (int i = 0; i < c.band[b].ng; ++i) ngb[c.band[b].g0 + i] = (unsigned char)b;
     if (cudaMemcpyToSymbol(c_sw, &c, sizeof(SwConst)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_sw_ngb, ngb, sizeof ngb) != cudaSuccess) return -1;
-    return 0;
+    return sw_solver_upload_const(c, ngb);
 }
 
 constexpr double ZEPZEN = 1.e-10;
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(128) sw_prep_kernel(SwIn in, SwWork w)
 // [col][lay][g].  taur (Rayleigh) is a one- or two-row product and goes straight to the slab; the solar
 // source sfluxzen is written by the single cell the reference leaves it from (laysolfr).
 // =====================================================================================================
-constexpr int TM_WARPS = 4;
 constexpr int TM_STRIDE = 18;
 
 template <int NG>
@@ -483,244 +482,43 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * TM_WARPS) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
+// As in the LW kernel: 16 warps per block step through the bands together (instruction-cache reuse);
+// work items are linearised (32-column tile, layer) pairs.
+constexpr int TM_BLOCK_WARPS = 16;
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 1) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
 {
-    __shared__ __align__(16) double s_slab[TM_WARPS][64 * TM_STRIDE];
+    extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32;
-    const int lay = blockIdx.y * TM_WARPS + wid;
     const int nlay = w.nlay, nc = w.nc;
-    if (lay >= nlay) return;                         // no block-level barrier below
+    const int ntile = (nc + 31) / 32;
+    const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
+    const bool live = item < (long)ntile * nlay;
+    const int tile = live ? (int)(item / nlay) : 0;
+    const int lay = live ? (int)(item - (long)tile * nlay) : 0;
+    const int c0 = tile * 32;
     const int col = c0 + lane;
-    bool valid = col < nc;
+    bool valid = live && col < nc;
     int laytrop = 0;
     if (valid) {
         laytrop = w.laytrop[col];
         if (laytrop < 0) valid = false;              // night column: the solver never reads its staging
     }
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (vmask == 0u) return;
     SwPair p;
     bool lower = false;
     if (valid) {
         sw_cell(in, col, lay, p);
         lower = (lay + 1) <= laytrop;
     }
-    double *slab = s_slab[wid];
+    double *slab = s_dyn + (size_t)wid * (64 * TM_STRIDE);
     const int *ls = w.laysolfr + (size_t)(valid ? col : 0) * 14;
     double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
     const size_t colstride = (size_t)nlay * NGPTSW;
     const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTSW;
-#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, w.taur, sflx, cell0, colstride, vmask)
+#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, w.taur, sflx, cell0, colstride, vmask); __syncthreads()
     SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
     SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
 #undef SW_BAND
-}
-
-// =====================================================================================================
-// solver: spcvrt_sw (SW/src/rrtmg_sw_spcvrt.f90:296-619) + reftra_sw (rrtmg_sw_reftra.f90:129-300, kmodts=2)
-//         + vrtqdr_sw (rrtmg_sw_vrtqdr.f90:103-150) + heating (rrtmg_sw_rad.nomcica.f90:686-727).
-// icld = 0 and iaer = 0: the aerosol/cloud terms of the layer assembly are exact identities
-// (tau_a = 0, omega_a = 1, g = 0 => delta scaling is the identity) and the total-sky stream equals the
-// clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
-//
-// Block <-> column, thread <-> g-point.  Two sweeps instead of the reference's four loops:
-//   up   (surface -> top): layer R/T (reftra) fused with the bottom-up adding recurrence (vrtqdr :103-121);
-//        keeps ref, refd, tra, trad, dbt per layer and rup, rupd per level in per-thread local arrays;
-//   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
-//        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
-//        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
-// The direct-beam transmittance of spcvrt :519-531 is the same table look-up as reftra's exp(-tau/mu0)
-// (for tau/mu0 > 500 both hit the 1e-20 floor of exp_tbl), so it is taken from there.
-// Divides go through rcp_fast/sqrt_fast; zbeta is folded into zdend's denominator.
-// The sum over g-points goes through shared memory in batches of 8 levels (tile_reduce16).
-// =====================================================================================================
-constexpr int SV_THREADS = 128;   // 112 g-points -> 3.5 warps
-constexpr int SV_S = 113;         // tile row stride (odd)
-
-// exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
-__device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
-{
-    if (ze <= 0.06) {
-        const double em = 1. - ze + 0.5 * ze * ze;
-        recip = rcp_fast(em);
-        return em;
-    }
-    const double tblind = ze * rcp_fast(bpade + ze);
-    const int itind = (int)(10000.0 * tblind + 0.5);
-    const double2 e = __ldg(tb + itind);
-    recip = e.y;
-    return e.x;
-}
-
-template <int LMAX>
-__global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
-{
-    __shared__ double s_tile[16 * SV_S];
-    __shared__ double s_part[16 * (SV_THREADS / 16 + 1)];
-    __shared__ double s_up[LMAX + 1], s_dn[LMAX + 1];
-    const int col = blockIdx.x;
-    const int klev = w.nlay;
-    const int g = threadIdx.x;
-    const size_t old = (size_t)out.ld;
-
-    const double prmu0 = in.coszen[col];
-    if (prmu0 < ZEPZEN) {
-        // night column: zero everything (rad.nomcica:502-510)
-        for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
-            const size_t o = col + (size_t)lev * old;
-            out.uflx[o] = 0.; out.dflx[o] = 0.; out.uflxc[o] = 0.; out.dflxc[o] = 0.;
-            if (lev < klev) { out.hr[o] = 0.; out.hrc[o] = 0.; }
-        }
-        return;
-    }
-    const bool active = g < NGPTSW;
-    const int band = active ? c_sw_ngb[g] : 0;
-    const double bpade = c_sw.bpade;
-    const double eps = 1.e-08, zwcrit = 0.9999995;
-    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
-    const double rmu0 = 1. / prmu0;
-
-    // band albedos (rad.nomcica:565-578): bands 16-24 and 29 near-IR, 25-28 UV/visible
-    const bool uvvis = band >= 9 && band <= 12;
-    const double albd = uvvis ? in.asdif[col] : in.aldif[col];   // palbd: diffuse
-    const double albp = uvvis ? in.asdir[col] : in.aldir[col];   // palbp: direct
-
-    // per-thread state, index = layer / level counted from the surface
-    double zref[LMAX], zrefd[LMAX], ztra[LMAX], ztrad[LMAX], zdbt[LMAX];
-    double zrup[LMAX + 1], zrupd[LMAX + 1];
-    double zincflx = 0.0;
-
-    if (active) {
-        zincflx = in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0;
-        const double *taug = w.taug + (size_t)col * klev * NGPTSW + g;
-        const double *taur = w.taur + (size_t)col * klev * NGPTSW + g;
-        double rup = albp, rupd = albd;      // zrup(klev+1) = palbp, zrupd(klev+1) = palbd
-        zrup[0] = rup;
-        zrupd[0] = rupd;
-#pragma unroll 2
-        for (int l = 0; l < klev; ++l) {
-            const double tr = taur[(size_t)l * NGPTSW];
-            const double zto1 = tr + taug[(size_t)l * NGPTSW];      // ztauc
-            const double zw = tr * rcp_fast(zto1);                   // zomcc
-            // ---- reftra, zg = 0: gamma3 = gamma4 = 1/2, zwo = zw
-            const double zgamma1 = (8. - zw * 5.) * 0.25;
-            const double zgamma2 = 3. * zw * 0.25;
-            const double zed = zto1 * rmu0;                          // direct-beam optical path
-            double ref, refd, tra, trad, dbt;
-            if (zw >= zwcrit) {
-                // conservative scattering (:162-214)
-                const double za1 = zgamma1 * prmu0 - 0.5;
-                const double zgt = zgamma1 * zto1;
-                double rcp;
-                const double ze2 = sw_exp(tb, fmin(zed, 500.), bpade, rcp);
-                const double rg = rcp_fast(1. + zgt);
-                ref = (zgt - za1 * (1. - ze2)) * rg;
-                tra = 1. - ref;
-                refd = zgt * rg;
-                trad = 1. - refd;
-                if (ze2 == 1.0) { ref = 0.0; tra = 1.0; refd = 0.0; trad = 1.0; }
-                dbt = ze2;
-            } else {
-                const double za1 = (zgamma1 + zgamma2) * 0.5;        // = za2
-                const double zrk = sqrt_fast(zgamma1 * zgamma1 - zgamma2 * zgamma2);
-                const double zrp = zrk * prmu0;
-                const double zrp1 = 1. + zrp;
-                const double zrm1 = 1. - zrp;
-                const double zrk2 = 2. * zrk;
-                const double zrpp = 1. - zrp * zrp;
-                const double zrkg = zrk + zgamma1;
-                const double hA = fma(zrk, 0.5, za1), hB = fma(zrk, -0.5, za1);
-                const double zr1 = zrm1 * hA;
-                const double zr2 = zrp1 * hB;
-                const double zr3 = zrk2 * (0.5 - za1 * prmu0);
-                const double zr4 = zrpp * zrkg;
-                const double zr5 = zrpp * (zrk - zgamma1);
-                const double zt1 = zrp1 * hA;
-                const double zt2 = zrm1 * hB;
-                const double zt3 = zrk2 * (0.5 + za1 * prmu0);
-                double zep1, zep2;
-                const double zem1 = sw_exp(tb, fmin(zrk * zto1, 500.), bpade, zep1);
-                const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
-                const double zdenr = fma(zr4, zep1, zr5 * zem1);     // = zdent (zt4 = zr4, zt5 = zr5)
-                if (zdenr >= -eps && zdenr <= eps) {
-                    ref = eps;
-                    tra = zem2;
-                } else {
-                    const double rd = zw * rcp_fast(zdenr);
-                    ref = (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * rd;
-                    tra = zem2 - zem2 * ((zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * rd);
-                }
-                const double zemm = zem1 * zem1;
-                // zdend = 1/((1 - zbeta*zemm)*zrkg), zbeta = (gamma1 - zrk)/zrkg
-                const double zdend = rcp_fast(fma(-(zgamma1 - zrk), zemm, zrkg));
-                refd = zgamma2 * (1. - zemm) * zdend;
-                trad = zrk2 * zem1 * zdend;
-                dbt = zem2;
-            }
-            zref[l] = ref; zrefd[l] = refd; ztra[l] = tra; ztrad[l] = trad; zdbt[l] = dbt;
-            // ---- vrtqdr, bottom -> top (:103-121)
-            const double zreflect = rcp_fast(1. - rupd * refd);
-            const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
-            const double rupd_n = refd + trad * trad * rupd * zreflect;
-            rup = rup_n;
-            rupd = rupd_n;
-            zrup[l + 1] = rup;
-            zrupd[l + 1] = rupd;
-        }
-    }
-
-    // ---- top -> bottom: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
-    double ztdn = 1., zrdnd = 0., ztdbt = 1.;
-    for (int k = 0; k <= klev; ++k) {
-        const int s = klev - k;            // level counted from the surface
-        const int slot = k & 7;
-        if (active) {
-            const double ru = zrup[s], rud = zrupd[s];
-            const double zreflect = rcp_fast(1. - zrdnd * rud);
-            const double dif = ztdn - ztdbt;
-            const double pfu = (ztdbt * ru + dif * rud) * zreflect;
-            const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
-            s_tile[(2 * slot) * SV_S + g] = zincflx * pfu;
-            s_tile[(2 * slot + 1) * SV_S + g] = zincflx * pfd;
-            if (s > 0) {
-                const int l = s - 1;
-                const double ref = zref[l], refd = zrefd[l], tra = ztra[l], trad = ztrad[l], dbt = zdbt[l];
-                const double zr = rcp_fast(1. - refd * zrdnd);
-                const double ztdn_n = ztdbt * tra + (trad * (dif + ztdbt * ref * zrdnd)) * zr;
-                const double zrdnd_n = refd + trad * trad * zrdnd * zr;
-                ztdbt = dbt * ztdbt;
-                ztdn = ztdn_n;
-                zrdnd = zrdnd_n;
-            }
-        }
-        if (slot == 7 || k == klev) {
-            const double sum = tile_reduce16<SV_THREADS, NGPTSW, SV_S>(s_tile, s_part);
-            if (threadIdx.x < 16) {
-                const int kk = (k & ~7) + (threadIdx.x >> 1);
-                if (kk <= k) {
-                    if (threadIdx.x & 1) s_dn[klev - kk] = sum;
-                    else s_up[klev - kk] = sum;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
-        const double u = s_up[lev], d = s_dn[lev];
-        const size_t o = col + (size_t)lev * old;
-        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
-    }
-    for (int lay = threadIdx.x; lay < klev; lay += SV_THREADS) {
-        const size_t o = col + (size_t)lay * old;
-        double h = 0.0;
-        if (lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
-            const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
-            h = ((s_dn[lay + 1] - s_up[lay + 1]) - (s_dn[lay] - s_up[lay])) * (c_sw.heatfac / pdp);
-        }
-        out.hr[o] = h;
-        out.hrc[o] = h;
-    }
 }
 
 int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
@@ -728,21 +526,16 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_begin(K_SW_PREP, s);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
     ktimer_end(s);
-    dim3 grid((w.nc + 31) / 32, (w.nlay + TM_WARPS - 1) / TM_WARPS);
-    ktimer_begin(K_SW_TAUMOL, s);
-    sw_taumol_kernel<<<grid, 32 * TM_WARPS, 0, s>>>(t, in, w);
-    ktimer_end(s);
-    ktimer_begin(K_SW_SOLVER, s);
     {
-        const size_t pad = (size_t)g_tune.sw_solver_pad_kb * 1024;
-        if (w.nlay <= 64) {
-            cudaFuncSetAttribute(sw_solver_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-            sw_solver_kernel<64><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
-        } else {
-            cudaFuncSetAttribute(sw_solver_kernel<MAXLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-            sw_solver_kernel<MAXLAY><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
-        }
+        const long items = (long)((w.nc + 31) / 32) * w.nlay;
+        const size_t smem = (size_t)TM_BLOCK_WARPS * 64 * TM_STRIDE * sizeof(double);
+        cudaFuncSetAttribute(sw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ktimer_begin(K_SW_TAUMOL, s);
+        sw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w);
+        ktimer_end(s);
     }
+    ktimer_begin(K_SW_SOLVER, s);
+    sw_launch_solver(t, in, out, w, s);
     ktimer_end(s);
     return 3;
 }

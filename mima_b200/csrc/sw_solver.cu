@@ -1,0 +1,280 @@
+// sw_solver.cu -- RRTMG shortwave two-stream solver on sm_100a (clear sky, no aerosol: the MiMA configuration).
+//
+// spcvrt_sw (SW/src/rrtmg_sw_spcvrt.f90:296-619) + reftra_sw (rrtmg_sw_reftra.f90:129-300, kmodts=2)
+//         + vrtqdr_sw (rrtmg_sw_vrtqdr.f90:103-150) + heating (rrtmg_sw_rad.nomcica.f90:686-727).
+// icld = 0 and iaer = 0: the aerosol/cloud terms of the layer assembly are exact identities
+// (tau_a = 0, omega_a = 1, g = 0 => delta scaling is the identity) and the total-sky stream equals the
+// clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
+//
+// Block <-> column, thread <-> g-point.  Two sweeps instead of the reference's four loops:
+//   up   (surface -> top): layer R/T (reftra) fused with the bottom-up adding recurrence (vrtqdr :103-121);
+//        keeps rup, rupd per level in a per-thread local array;
+//   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
+//        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
+//        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
+// The five layer properties (ref, refd, tra, trad, dbt) are needed by both sweeps.  STORE = true keeps them
+// in per-thread local arrays (40 B written + 40 B read per cell, which at full occupancy streams through
+// HBM); STORE = false evaluates reftra again in the down sweep from the staged (taur, taug) pair
+// (16 B re-read per cell, ~90 more FP64 operations).  Which is faster depends on the HBM/FP64 balance and
+// is chosen at launch (option "sw_solver_store").
+// The direct-beam transmittance of spcvrt :519-531 is the same table look-up as reftra's exp(-tau/mu0)
+// (for tau/mu0 > 500 both hit the 1e-20 floor of exp_tbl), so it is taken from there.
+// Divides go through rcp_fast/sqrt_fast; zbeta is folded into zdend's denominator.
+// The sum over g-points goes through shared memory in batches of 8 levels (tile_reduce16).
+//
+// This translation unit is compiled with FMA contraction on (build.py).
+#include "rrtmg_dev.cuh"
+
+namespace rrtmg {
+
+struct SwSolverConst {
+    double heatfac, bpade;
+    unsigned char ngb[NGPTSW];
+};
+__constant__ SwSolverConst c_ss;
+
+int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb)
+{
+    SwSolverConst h;
+    h.heatfac = c.heatfac; h.bpade = c.bpade;
+    for (int g = 0; g < NGPTSW; ++g) h.ngb[g] = ngb[g];
+    return cudaMemcpyToSymbol(c_ss, &h, sizeof h) == cudaSuccess ? 0 : -1;
+}
+
+constexpr double ZEPZEN = 1.e-10;
+constexpr int SV_THREADS = 128;   // 112 g-points -> 3.5 warps
+constexpr int SV_S = 113;         // tile row stride (odd)
+constexpr int SV_U = 2;           // layers per load group
+
+// exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
+__device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
+{
+    if (ze <= 0.06) {
+        const double em = 1. - ze + 0.5 * ze * ze;
+        recip = rcp_fast(em);
+        return em;
+    }
+    const double tblind = ze * rcp_fast(bpade + ze);
+    const int itind = (int)(10000.0 * tblind + 0.5);
+    const double2 e = __ldg(tb + itind);
+    recip = e.y;
+    return e.x;
+}
+
+// reftra_sw for one clear-sky (g, layer) cell with asymmetry 0 (gamma3 = gamma4 = 1/2, zwo = zw), plus the
+// direct-beam transmittance dbt = exp(-tau/mu0).
+__device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double bpade, double prmu0, double rmu0,
+                                          double tr, double tg, double &ref, double &refd, double &tra,
+                                          double &trad, double &dbt)
+{
+    const double eps = 1.e-08, zwcrit = 0.9999995;
+    const double zto1 = tr + tg;                             // ztauc
+    const double zw = tr * rcp_fast(zto1);                   // zomcc
+    const double zgamma1 = (8. - zw * 5.) * 0.25;
+    const double zgamma2 = 3. * zw * 0.25;
+    const double zed = zto1 * rmu0;                          // direct-beam optical path
+    if (zw >= zwcrit) {
+        // conservative scattering (:162-214)
+        const double za1 = zgamma1 * prmu0 - 0.5;
+        const double zgt = zgamma1 * zto1;
+        double rcp;
+        const double ze2 = sw_exp(tb, fmin(zed, 500.), bpade, rcp);
+        const double rg = rcp_fast(1. + zgt);
+        ref = (zgt - za1 * (1. - ze2)) * rg;
+        tra = 1. - ref;
+        refd = zgt * rg;
+        trad = 1. - refd;
+        if (ze2 == 1.0) { ref = 0.0; tra = 1.0; refd = 0.0; trad = 1.0; }
+        dbt = ze2;
+    } else {
+        const double za1 = (zgamma1 + zgamma2) * 0.5;        // = za2
+        const double zrk = sqrt_fast(zgamma1 * zgamma1 - zgamma2 * zgamma2);
+        const double zrp = zrk * prmu0;
+        const double zrp1 = 1. + zrp;
+        const double zrm1 = 1. - zrp;
+        const double zrk2 = 2. * zrk;
+        const double zrpp = 1. - zrp * zrp;
+        const double zrkg = zrk + zgamma1;
+        const double hA = fma(zrk, 0.5, za1), hB = fma(zrk, -0.5, za1);
+        const double zr1 = zrm1 * hA;
+        const double zr2 = zrp1 * hB;
+        const double zr3 = zrk2 * (0.5 - za1 * prmu0);
+        const double zr4 = zrpp * zrkg;
+        const double zr5 = zrpp * (zrk - zgamma1);
+        const double zt1 = zrp1 * hA;
+        const double zt2 = zrm1 * hB;
+        const double zt3 = zrk2 * (0.5 + za1 * prmu0);
+        double zep1, zep2;
+        const double zem1 = sw_exp(tb, fmin(zrk * zto1, 500.), bpade, zep1);
+        const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
+        const double zdenr = fma(zr4, zep1, zr5 * zem1);     // = zdent (zt4 = zr4, zt5 = zr5)
+        if (zdenr >= -eps && zdenr <= eps) {
+            ref = eps;
+            tra = zem2;
+        } else {
+            const double rd = zw * rcp_fast(zdenr);
+            ref = (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * rd;
+            tra = zem2 - zem2 * ((zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * rd);
+        }
+        const double zemm = zem1 * zem1;
+        // zdend = 1/((1 - zbeta*zemm)*zrkg), zbeta = (gamma1 - zrk)/zrkg
+        const double zdend = rcp_fast(fma(-(zgamma1 - zrk), zemm, zrkg));
+        refd = zgamma2 * (1. - zemm) * zdend;
+        trad = zrk2 * zem1 * zdend;
+        dbt = zem2;
+    }
+}
+
+template <int LMAX, bool STORE>
+__global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
+{
+    __shared__ double s_tile[16 * SV_S];
+    __shared__ double s_part[16 * (SV_THREADS / 16 + 1)];
+    __shared__ double s_up[LMAX + 1], s_dn[LMAX + 1];
+    const int col = blockIdx.x;
+    const int klev = w.nlay;
+    const int g = threadIdx.x;
+    const size_t old = (size_t)out.ld;
+
+    const double prmu0 = in.coszen[col];
+    if (prmu0 < ZEPZEN) {
+        // night column: zero everything (rad.nomcica:502-510)
+        for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
+            const size_t o = col + (size_t)lev * old;
+            out.uflx[o] = 0.; out.dflx[o] = 0.; out.uflxc[o] = 0.; out.dflxc[o] = 0.;
+            if (lev < klev) { out.hr[o] = 0.; out.hrc[o] = 0.; }
+        }
+        return;
+    }
+    const bool active = g < NGPTSW;
+    const int band = active ? c_ss.ngb[g] : 0;
+    const double bpade = c_ss.bpade;
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
+    const double rmu0 = 1. / prmu0;
+
+    // band albedos (rad.nomcica:565-578): bands 16-24 and 29 near-IR, 25-28 UV/visible
+    const bool uvvis = band >= 9 && band <= 12;
+    const double albd = uvvis ? in.asdif[col] : in.aldif[col];   // palbd: diffuse
+    const double albp = uvvis ? in.asdir[col] : in.aldir[col];   // palbp: direct
+
+    // per-thread state, index = layer / level counted from the surface
+    constexpr int LP = STORE ? LMAX : 1;
+    double zref[LP], zrefd[LP], ztra[LP], ztrad[LP], zdbt[LP];
+    double zrup[LMAX + 1], zrupd[LMAX + 1];
+    const double *__restrict__ taug = w.taug + (size_t)col * klev * NGPTSW + (active ? g : 0);
+    const double *__restrict__ taur = w.taur + (size_t)col * klev * NGPTSW + (active ? g : 0);
+    const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0 : 0.0;
+
+    // ---- up sweep: reftra + vrtqdr bottom -> top (:103-121)
+    {
+        double rup = albp, rupd = albd;      // zrup(klev+1) = palbp, zrupd(klev+1) = palbd
+        zrup[0] = rup;
+        zrupd[0] = rupd;
+        for (int l0 = 0; l0 < klev; l0 += SV_U) {
+            double tr[SV_U], tg[SV_U];
+#pragma unroll
+            for (int j = 0; j < SV_U; ++j) {
+                const int l = min(l0 + j, klev - 1);
+                tr[j] = taur[(size_t)l * NGPTSW];
+                tg[j] = taug[(size_t)l * NGPTSW];
+            }
+#pragma unroll
+            for (int j = 0; j < SV_U; ++j) {
+                const int l = l0 + j;
+                if (l < klev) {
+                    double ref, refd, tra, trad, dbt;
+                    sw_reftra(tb, bpade, prmu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
+                    if (STORE) { zref[l] = ref; zrefd[l] = refd; ztra[l] = tra; ztrad[l] = trad; zdbt[l] = dbt; }
+                    const double zreflect = rcp_fast(1. - rupd * refd);
+                    const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
+                    const double rupd_n = refd + trad * trad * rupd * zreflect;
+                    rup = rup_n;
+                    rupd = rupd_n;
+                    zrup[l + 1] = rup;
+                    zrupd[l + 1] = rupd;
+                }
+            }
+        }
+    }
+
+    // ---- down sweep: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
+    double ztdn = 1., zrdnd = 0., ztdbt = 1.;
+    for (int k = 0; k <= klev; ++k) {
+        const int s = klev - k;            // level counted from the surface
+        const int slot = k & 7;
+        {
+            const double ru = zrup[s], rud = zrupd[s];
+            const double zreflect = rcp_fast(1. - zrdnd * rud);
+            const double dif = ztdn - ztdbt;
+            const double pfu = (ztdbt * ru + dif * rud) * zreflect;
+            const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
+            if (active) {
+                s_tile[(2 * slot) * SV_S + g] = zincflx * pfu;
+                s_tile[(2 * slot + 1) * SV_S + g] = zincflx * pfd;
+            }
+            if (s > 0) {
+                const int l = s - 1;
+                double ref, refd, tra, trad, dbt;
+                if (STORE) {
+                    ref = zref[l]; refd = zrefd[l]; tra = ztra[l]; trad = ztrad[l]; dbt = zdbt[l];
+                } else {
+                    sw_reftra(tb, bpade, prmu0, rmu0, taur[(size_t)l * NGPTSW], taug[(size_t)l * NGPTSW], ref, refd, tra, trad, dbt);
+                }
+                const double zr = rcp_fast(1. - refd * zrdnd);
+                const double ztdn_n = ztdbt * tra + (trad * (dif + ztdbt * ref * zrdnd)) * zr;
+                const double zrdnd_n = refd + trad * trad * zrdnd * zr;
+                ztdbt = dbt * ztdbt;
+                ztdn = ztdn_n;
+                zrdnd = zrdnd_n;
+            }
+        }
+        if (slot == 7 || k == klev) {
+            const double sum = tile_reduce16<SV_THREADS, NGPTSW, SV_S>(s_tile, s_part);
+            if (threadIdx.x < 16) {
+                const int kk = (k & ~7) + (threadIdx.x >> 1);
+                if (kk <= k) {
+                    if (threadIdx.x & 1) s_dn[klev - kk] = sum;
+                    else s_up[klev - kk] = sum;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
+        const double u = s_up[lev], d = s_dn[lev];
+        const size_t o = col + (size_t)lev * old;
+        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
+    }
+    for (int lay = threadIdx.x; lay < klev; lay += SV_THREADS) {
+        const size_t o = col + (size_t)lay * old;
+        double h = 0.0;
+        if (lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
+            const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
+            h = ((s_dn[lay + 1] - s_up[lay + 1]) - (s_dn[lay] - s_up[lay])) * (c_ss.heatfac / pdp);
+        }
+        out.hr[o] = h;
+        out.hrc[o] = h;
+    }
+}
+
+template <int LMAX, bool STORE>
+static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
+{
+    const size_t pad = (size_t)g_tune.sw_solver_pad_kb * 1024;
+    if (pad) cudaFuncSetAttribute(sw_solver_kernel<LMAX, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    sw_solver_kernel<LMAX, STORE><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
+}
+
+void sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
+{
+    const bool store = g_tune.sw_solver_store != 0;
+    if (w.nlay <= 64) {
+        if (store) launch<64, true>(t, in, out, w, s);
+        else launch<64, false>(t, in, out, w, s);
+    } else {
+        if (store) launch<MAXLAY, true>(t, in, out, w, s);
+        else launch<MAXLAY, false>(t, in, out, w, s);
+    }
+}
+
+} // namespace rrtmg

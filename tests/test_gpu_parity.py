@@ -103,6 +103,7 @@ def test_lw_stages(gpu, t42):
 
 def test_sw_stages(gpu, t42):
     cols, _, osw = t42
+    gpu.set_option("capture_stages", 1)
     gpu.set_option("chunk", 1 << 20)
     try:
         got = gpu.sw_from_columns(cols)
@@ -121,6 +122,7 @@ def test_sw_stages(gpu, t42):
         assert np.allclose(gpu.get_stage("sw.sfluxzen", (nc, 112)), st["sfluxzen"], rtol=1e-14)
         _check_outputs(got, osw, SW_OUT)
     finally:
+        gpu.set_option("capture_stages", 0)
         gpu.set_option("chunk", 0)
 
 
