@@ -37,6 +37,7 @@ constexpr int RT_S = 141;         // tile row stride (odd)
 constexpr int RT_U = 4;           // levels per load group
 
 // layer transmittance and Planck-weighted sources of one (g, layer) cell (:589-607)
+template <bool DOWN>
 __device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double bpade, double secd, double taut,
                                          double plfrac, double blay, double dplankup, double dplankdn,
                                          double &atrans, double &bbd, double &bbugas)
@@ -47,59 +48,86 @@ __device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double 
     if (odepth <= 0.06) {
         atrans = odepth - 0.5 * odepth * odepth;
         odepth = rec_6 * odepth;
-        bbd = plfrac * (blay + dplankdn * odepth);
-        bbugas = plfrac * (blay + dplankup * odepth);
+        if (DOWN) bbd = plfrac * (blay + dplankdn * odepth);
+        else bbugas = plfrac * (blay + dplankup * odepth);
     } else {
         const double tblind = odepth * rcp_fast(bpade + odepth);
         const int itr = (int)(10000.0 * tblind + 0.5);
         const double2 e = __ldg(et + itr);
         atrans = 1. - e.x;
-        bbd = plfrac * (blay + e.y * dplankdn);
-        bbugas = plfrac * (blay + e.y * dplankup);
+        if (DOWN) bbd = plfrac * (blay + e.y * dplankdn);
+        else bbugas = plfrac * (blay + e.y * dplankup);
     }
 }
 
+// The Planck sources of the column ([lay][16] and [lev][16], 16 KB at 60 layers) are staged in shared memory
+// once per block: the 140 g-threads need them 2-3 times per level and they are shared by all g-points of a band.
+template <bool AER>
 __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
 {
     __shared__ double s_tile[16 * RT_S];
     __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
     __shared__ double s_dn[MAXLAY + 1], s_up[MAXLAY + 1];
+    extern __shared__ __align__(16) double s_planck[];          // pl[nlay][16] then pv[nlay+1][16]
     const int col = blockIdx.x;
     const int nlay = w.nlay;
     const int g = threadIdx.x;
     const bool active = g < NGPTLW;
     const int band = active ? c_ls.ngb[g] : 0;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(w.planklay + (size_t)col * nlay * 16);
+        double2 *dst = reinterpret_cast<double2 *>(s_planck);
+        for (int i = threadIdx.x; i < nlay * 8; i += RT_THREADS) dst[i] = src[i];
+        src = reinterpret_cast<const double2 *>(w.planklev + (size_t)col * (nlay + 1) * 16);
+        dst = reinterpret_cast<double2 *>(s_planck + nlay * 16);
+        for (int i = threadIdx.x; i < (nlay + 1) * 8; i += RT_THREADS) dst[i] = src[i];
+    }
     const double secd = w.secdiff[(size_t)col * 16 + band];
     const double wgt = active ? 0.5 * c_ls.delwave[band] : 0.0;     // wtdiff * delwave
     const double bpade = c_ls.bpade;
     const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
     const double *__restrict__ taug = w.taug + (size_t)col * nlay * NGPTLW + (active ? g : 0);
     const double *__restrict__ fracs = w.fracs + (size_t)col * nlay * NGPTLW + (active ? g : 0);
-    const double *__restrict__ pl = w.planklay + (size_t)col * nlay * 16 + band;
-    const double *__restrict__ pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
-    const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
+    const double *pl = s_planck + band;
+    const double *pv = s_planck + nlay * 16 + band;
+    const double *taer = AER ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
+    __syncthreads();
 
     // ---- downward sweep (:505-618), k counts layers from the top
     double radld = 0.0;
     double plfrac1 = 0.0;
-    for (int k0 = 0; k0 < nlay; k0 += RT_U) {
-        double tg[RT_U], fr[RT_U], bl[RT_U], pu[RT_U], pd[RT_U];
+    double pup = pv[nlay * 16];                       // Planck at the upper interface of the current layer
+    double tgn[RT_U], frn[RT_U];          // loads of the next group, issued before the current group's arithmetic
 #pragma unroll
-        for (int j = 0; j < RT_U; ++j) {
-            const int lay = max(nlay - 1 - (k0 + j), 0);            // 0-based layer (clamped in the ragged tail)
-            tg[j] = taug[(size_t)lay * NGPTLW];
-            fr[j] = fracs[(size_t)lay * NGPTLW];
-            if (taer) tg[j] = tg[j] + taer[(size_t)lay * in.ld];
-            bl[j] = pl[lay * 16];
-            pu[j] = pv[(lay + 1) * 16];
-            pd[j] = pv[lay * 16];
+    for (int j = 0; j < RT_U; ++j) {
+        const int lay = max(nlay - 1 - j, 0);
+        tgn[j] = taug[(size_t)lay * NGPTLW];
+        frn[j] = fracs[(size_t)lay * NGPTLW];
+        if (AER) tgn[j] = tgn[j] + taer[(size_t)lay * in.ld];
+    }
+    for (int k0 = 0; k0 < nlay; k0 += RT_U) {
+        double tg[RT_U], fr[RT_U];
+        const bool full = k0 + RT_U <= nlay;
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) { tg[j] = tgn[j]; fr[j] = frn[j]; }
+        if (k0 + RT_U < nlay) {
+#pragma unroll
+            for (int j = 0; j < RT_U; ++j) {
+                const int lay = max(nlay - 1 - (k0 + RT_U + j), 0);      // clamped in the ragged tail
+                tgn[j] = taug[(size_t)lay * NGPTLW];
+                frn[j] = fracs[(size_t)lay * NGPTLW];
+                if (AER) tgn[j] = tgn[j] + taer[(size_t)lay * in.ld];
+            }
         }
 #pragma unroll
         for (int j = 0; j < RT_U; ++j) {
             const int k = k0 + j;
-            if (k < nlay) {
+            if (full || k < nlay) {
+                const int lay = nlay - 1 - k;
+                const double blay = pl[lay * 16], pdn = pv[lay * 16];
                 double atrans, bbd, bbugas;
-                lw_layer(et, bpade, secd, tg[j], fr[j], bl[j], pu[j] - bl[j], pd[j] - bl[j], atrans, bbd, bbugas);
+                lw_layer<true>(et, bpade, secd, tg[j], fr[j], blay, pup - blay, pdn - blay, atrans, bbd, bbugas);
+                pup = pdn;
                 radld = radld + (bbd - radld) * atrans;
                 if (active) s_tile[(k & 15) * RT_S + g] = radld * wgt;
                 if (k == nlay - 1) plfrac1 = fr[j];
@@ -117,29 +145,41 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
     // ---- surface (:628-636) and upward sweep (:649-711); level k = 0 is the surface, level k > 0 the top
     //      of layer k (1-based).  Groups are aligned to the 16-level batches of the reduction.
     double radlu = 0.0;
-    for (int k0 = 0; k0 <= nlay; k0 += RT_U) {
-        double tg[RT_U], fr[RT_U], bl[RT_U], pu[RT_U];
 #pragma unroll
-        for (int j = 0; j < RT_U; ++j) {
-            const int lay = min(max(k0 + j, 1), nlay) - 1;
-            tg[j] = taug[(size_t)lay * NGPTLW];
-            fr[j] = fracs[(size_t)lay * NGPTLW];
-            if (taer) tg[j] = tg[j] + taer[(size_t)lay * in.ld];
-            bl[j] = pl[lay * 16];
-            pu[j] = pv[(lay + 1) * 16];
+    for (int j = 0; j < RT_U; ++j) {
+        const int lay = min(max(j, 1), nlay) - 1;
+        tgn[j] = taug[(size_t)lay * NGPTLW];
+        frn[j] = fracs[(size_t)lay * NGPTLW];
+        if (AER) tgn[j] = tgn[j] + taer[(size_t)lay * in.ld];
+    }
+    for (int k0 = 0; k0 <= nlay; k0 += RT_U) {
+        double tg[RT_U], fr[RT_U];
+        const bool full = k0 > 0 && k0 + RT_U - 1 <= nlay;
+#pragma unroll
+        for (int j = 0; j < RT_U; ++j) { tg[j] = tgn[j]; fr[j] = frn[j]; }
+        if (k0 + RT_U <= nlay) {
+#pragma unroll
+            for (int j = 0; j < RT_U; ++j) {
+                const int lay = min(k0 + RT_U + j, nlay) - 1;
+                tgn[j] = taug[(size_t)lay * NGPTLW];
+                frn[j] = fracs[(size_t)lay * NGPTLW];
+                if (AER) tgn[j] = tgn[j] + taer[(size_t)lay * in.ld];
+            }
         }
 #pragma unroll
         for (int j = 0; j < RT_U; ++j) {
             const int k = k0 + j;
-            if (k == 0) {
+            if (!full && k == 0) {
                 const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
                 const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
                 const double reflect = 1. - semiss;
                 radlu = rad0 + reflect * radld;
                 if (active) s_tile[g] = radlu * wgt;
-            } else if (k <= nlay) {
+            } else if (full || k <= nlay) {
+                const int lay = k - 1;
+                const double blay = pl[lay * 16];
                 double atrans, bbd, bbugas;
-                lw_layer(et, bpade, secd, tg[j], fr[j], bl[j], pu[j] - bl[j], 0.0, atrans, bbd, bbugas);
+                lw_layer<false>(et, bpade, secd, tg[j], fr[j], blay, pv[(lay + 1) * 16] - blay, 0.0, atrans, bbd, bbugas);
                 radlu = radlu + (bbugas - radlu) * atrans;
                 if (active) s_tile[(k & 15) * RT_S + g] = radlu * wgt;
             }
@@ -171,9 +211,14 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
 
 void lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
-    const size_t pad = (size_t)g_tune.lw_rtrn_pad_kb * 1024;
-    if (pad) cudaFuncSetAttribute(lw_rtrn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-    lw_rtrn_kernel<<<w.nc, RT_THREADS, pad, s>>>(t, in, out, w);
+    const size_t smem = (size_t)(2 * w.nlay + 1) * 16 * sizeof(double) + (size_t)g_tune.lw_rtrn_pad_kb * 1024;
+    if (in.tauaer) {
+        cudaFuncSetAttribute(lw_rtrn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lw_rtrn_kernel<true><<<w.nc, RT_THREADS, smem, s>>>(t, in, out, w);
+    } else {
+        cudaFuncSetAttribute(lw_rtrn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lw_rtrn_kernel<false><<<w.nc, RT_THREADS, smem, s>>>(t, in, out, w);
+    }
 }
 
 } // namespace rrtmg

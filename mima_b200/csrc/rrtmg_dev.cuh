@@ -191,16 +191,17 @@ __device__ __forceinline__ double sqrt_fast(double a)
     return fma(g, r, g);
 }
 
-// Sum over the g-points of one column (threads of a block) of R = 16 rows of per-thread values that the
-// caller has stored in `tile` as tile[row * S + thread] (S odd, >= NACT).  Stage 1: thread t sums the
-// strided elements of row (t & 15); stage 2: threads 0..15 combine the NT/16 partials in a fixed order,
-// so the result is bitwise reproducible.  Two barriers; `tile` may be refilled right after the call.
-// Returns the row sum in threads 0..15.
-template <int NT, int NACT, int S>
-__device__ __forceinline__ double tile_reduce16(const double *tile, double *part)
+// Sum over g-points of R rows (R = 16 or 32) of per-thread values that the caller has stored in `tile` as
+// tile[row * S + g] (S odd, >= NACT).  Stage 1: thread t sums the strided elements of row (t % R) --
+// conflict-free because the lanes of a half-warp hold different rows and S is odd; stage 2: threads 0..R-1
+// combine the NT/R partials in a fixed order, so the result is bitwise reproducible.  Two barriers; `tile`
+// may be refilled right after the call.  Returns the row sum in threads 0..R-1 (row = threadIdx.x).
+template <int NT, int R, int NACT, int S>
+__device__ __forceinline__ double tile_reduce(const double *tile, double *part)
 {
-    constexpr int P = NT / 16;
-    const int t = threadIdx.x, row = t & 15, p = t >> 4;
+    static_assert(NT % R == 0 && (R & (R - 1)) == 0, "threads must be a multiple of the row count");
+    constexpr int P = NT / R;
+    const int t = threadIdx.x, row = t & (R - 1), p = t / R;
     __syncthreads();
     double acc = 0.0;
     const double *src = tile + row * S;
@@ -209,11 +210,16 @@ __device__ __forceinline__ double tile_reduce16(const double *tile, double *part
     part[row * (P + 1) + p] = acc;
     __syncthreads();
     double sum = 0.0;
-    if (t < 16) {
+    if (t < R) {
 #pragma unroll
         for (int k = 0; k < P; ++k) sum += part[t * (P + 1) + k];
     }
-    return sum;     // valid in threads 0..15 (row = threadIdx.x)
+    return sum;
+}
+template <int NT, int NACT, int S>
+__device__ __forceinline__ double tile_reduce16(const double *tile, double *part)
+{
+    return tile_reduce<NT, 16, NACT, S>(tile, part);
 }
 #endif
 

@@ -6,7 +6,8 @@
 // (tau_a = 0, omega_a = 1, g = 0 => delta scaling is the identity) and the total-sky stream equals the
 // clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
 //
-// Block <-> column, thread <-> g-point.  Two sweeps instead of the reference's four loops:
+// Block <-> two columns (2 x 112 g-points = 7 full warps: a half-empty warp would cost the FP64 pipe as much
+// as a full one), thread <-> (column, g-point).  Two sweeps instead of the reference's four loops:
 //   up   (surface -> top): layer R/T (reftra) fused with the bottom-up adding recurrence (vrtqdr :103-121);
 //        keeps rup, rupd per level in a per-thread local array;
 //   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
@@ -20,7 +21,7 @@
 // The direct-beam transmittance of spcvrt :519-531 is the same table look-up as reftra's exp(-tau/mu0)
 // (for tau/mu0 > 500 both hit the 1e-20 floor of exp_tbl), so it is taken from there.
 // Divides go through rcp_fast/sqrt_fast; zbeta is folded into zdend's denominator.
-// The sum over g-points goes through shared memory in batches of 8 levels (tile_reduce16).
+// The sum over g-points goes through shared memory in batches of 8 levels (tile_reduce, 32 rows).
 //
 // This translation unit is compiled with FMA contraction on (build.py).
 #include "rrtmg_dev.cuh"
@@ -42,9 +43,11 @@ int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb)
 }
 
 constexpr double ZEPZEN = 1.e-10;
-constexpr int SV_THREADS = 128;   // 112 g-points -> 3.5 warps
-constexpr int SV_S = 113;         // tile row stride (odd)
-constexpr int SV_U = 2;           // layers per load group
+constexpr int SV_COLS = 2;                      // columns per block: 2 x 112 g-points = 7 full warps
+constexpr int SV_THREADS = SV_COLS * NGPTSW;    // 224
+constexpr int SV_S = 113;                       // tile row stride (odd)
+constexpr int SV_R = 32;                        // tile rows: 8 levels x {up, down} x 2 columns
+constexpr int SV_U = 2;                         // layers per load group
 
 // exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
 __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
@@ -128,62 +131,69 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
 template <int LMAX, bool STORE>
 __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
 {
-    __shared__ double s_tile[16 * SV_S];
-    __shared__ double s_part[16 * (SV_THREADS / 16 + 1)];
-    __shared__ double s_up[LMAX + 1], s_dn[LMAX + 1];
-    const int col = blockIdx.x;
+    __shared__ double s_tile[SV_R * SV_S];
+    __shared__ double s_part[SV_R * (SV_THREADS / SV_R + 1)];
+    __shared__ double s_up[SV_COLS][LMAX + 1], s_dn[SV_COLS][LMAX + 1];
     const int klev = w.nlay;
-    const int g = threadIdx.x;
+    const int cb = threadIdx.x / NGPTSW;           // column of the block this thread works on
+    const int g = threadIdx.x - cb * NGPTSW;
+    const int col = blockIdx.x * SV_COLS + cb;
     const size_t old = (size_t)out.ld;
+    const bool incol = col < w.nc;
 
-    const double prmu0 = in.coszen[col];
-    if (prmu0 < ZEPZEN) {
-        // night column: zero everything (rad.nomcica:502-510)
-        for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
-            const size_t o = col + (size_t)lev * old;
-            out.uflx[o] = 0.; out.dflx[o] = 0.; out.uflxc[o] = 0.; out.dflxc[o] = 0.;
-            if (lev < klev) { out.hr[o] = 0.; out.hrc[o] = 0.; }
-        }
-        return;
-    }
-    const bool active = g < NGPTSW;
-    const int band = active ? c_ss.ngb[g] : 0;
+    const double prmu0 = incol ? in.coszen[col] : 0.0;
+    const bool active = incol && !(prmu0 < ZEPZEN);      // night columns: zeros (rad.nomcica:502-510)
+    const int colr = incol ? col : 0;
+    const int band = c_ss.ngb[g];
     const double bpade = c_ss.bpade;
     const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
-    const double rmu0 = 1. / prmu0;
+    const double mu0 = active ? prmu0 : 1.0;
+    const double rmu0 = 1. / mu0;
 
     // band albedos (rad.nomcica:565-578): bands 16-24 and 29 near-IR, 25-28 UV/visible
     const bool uvvis = band >= 9 && band <= 12;
-    const double albd = uvvis ? in.asdif[col] : in.aldif[col];   // palbd: diffuse
-    const double albp = uvvis ? in.asdir[col] : in.aldir[col];   // palbp: direct
+    const double albd = uvvis ? in.asdif[colr] : in.aldif[colr];   // palbd: diffuse
+    const double albp = uvvis ? in.asdir[colr] : in.aldir[colr];   // palbp: direct
 
     // per-thread state, index = layer / level counted from the surface
     constexpr int LP = STORE ? LMAX : 1;
     double zref[LP], zrefd[LP], ztra[LP], ztrad[LP], zdbt[LP];
     double zrup[LMAX + 1], zrupd[LMAX + 1];
-    const double *__restrict__ taug = w.taug + (size_t)col * klev * NGPTSW + (active ? g : 0);
-    const double *__restrict__ taur = w.taur + (size_t)col * klev * NGPTSW + (active ? g : 0);
+    const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
+    const double *__restrict__ taur = w.taur + (size_t)colr * klev * NGPTSW + g;
     const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0 : 0.0;
 
-    // ---- up sweep: reftra + vrtqdr bottom -> top (:103-121)
-    {
+    // ---- up sweep: reftra + vrtqdr bottom -> top (:103-121); the loads of the next layer group are issued
+    //      before the arithmetic of the current one
+    if (active) {
         double rup = albp, rupd = albd;      // zrup(klev+1) = palbp, zrupd(klev+1) = palbd
         zrup[0] = rup;
         zrupd[0] = rupd;
+        double trn[SV_U], tgn[SV_U];
+#pragma unroll
+        for (int j = 0; j < SV_U; ++j) {
+            const int l = min(j, klev - 1);
+            trn[j] = taur[(size_t)l * NGPTSW];
+            tgn[j] = taug[(size_t)l * NGPTSW];
+        }
         for (int l0 = 0; l0 < klev; l0 += SV_U) {
             double tr[SV_U], tg[SV_U];
 #pragma unroll
-            for (int j = 0; j < SV_U; ++j) {
-                const int l = min(l0 + j, klev - 1);
-                tr[j] = taur[(size_t)l * NGPTSW];
-                tg[j] = taug[(size_t)l * NGPTSW];
+            for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+            if (l0 + SV_U < klev) {
+#pragma unroll
+                for (int j = 0; j < SV_U; ++j) {
+                    const int l = min(l0 + SV_U + j, klev - 1);
+                    trn[j] = taur[(size_t)l * NGPTSW];
+                    tgn[j] = taug[(size_t)l * NGPTSW];
+                }
             }
 #pragma unroll
             for (int j = 0; j < SV_U; ++j) {
                 const int l = l0 + j;
                 if (l < klev) {
                     double ref, refd, tra, trad, dbt;
-                    sw_reftra(tb, bpade, prmu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
+                    sw_reftra(tb, bpade, mu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
                     if (STORE) { zref[l] = ref; zrefd[l] = refd; ztra[l] = tra; ztrad[l] = trad; zdbt[l] = dbt; }
                     const double zreflect = rcp_fast(1. - rupd * refd);
                     const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
@@ -199,26 +209,28 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
 
     // ---- down sweep: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
     double ztdn = 1., zrdnd = 0., ztdbt = 1.;
+    double trn = 0., tgn = 0.;
+    if (active && !STORE) { trn = taur[(size_t)(klev - 1) * NGPTSW]; tgn = taug[(size_t)(klev - 1) * NGPTSW]; }
     for (int k = 0; k <= klev; ++k) {
         const int s = klev - k;            // level counted from the surface
         const int slot = k & 7;
-        {
+        if (active) {
             const double ru = zrup[s], rud = zrupd[s];
+            const double tr = trn, tg = tgn;
+            if (!STORE && s > 1) { trn = taur[(size_t)(s - 2) * NGPTSW]; tgn = taug[(size_t)(s - 2) * NGPTSW]; }
             const double zreflect = rcp_fast(1. - zrdnd * rud);
             const double dif = ztdn - ztdbt;
             const double pfu = (ztdbt * ru + dif * rud) * zreflect;
             const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
-            if (active) {
-                s_tile[(2 * slot) * SV_S + g] = zincflx * pfu;
-                s_tile[(2 * slot + 1) * SV_S + g] = zincflx * pfd;
-            }
+            s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = zincflx * pfu;
+            s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = zincflx * pfd;
             if (s > 0) {
                 const int l = s - 1;
                 double ref, refd, tra, trad, dbt;
                 if (STORE) {
                     ref = zref[l]; refd = zrefd[l]; tra = ztra[l]; trad = ztrad[l]; dbt = zdbt[l];
                 } else {
-                    sw_reftra(tb, bpade, prmu0, rmu0, taur[(size_t)l * NGPTSW], taug[(size_t)l * NGPTSW], ref, refd, tra, trad, dbt);
+                    sw_reftra(tb, bpade, mu0, rmu0, tr, tg, ref, refd, tra, trad, dbt);
                 }
                 const double zr = rcp_fast(1. - refd * zrdnd);
                 const double ztdn_n = ztdbt * tra + (trad * (dif + ztdbt * ref * zrdnd)) * zr;
@@ -227,33 +239,40 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
                 ztdn = ztdn_n;
                 zrdnd = zrdnd_n;
             }
+        } else {
+            s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = 0.0;
+            s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = 0.0;
         }
         if (slot == 7 || k == klev) {
-            const double sum = tile_reduce16<SV_THREADS, NGPTSW, SV_S>(s_tile, s_part);
-            if (threadIdx.x < 16) {
-                const int kk = (k & ~7) + (threadIdx.x >> 1);
+            const double sum = tile_reduce<SV_THREADS, SV_R, NGPTSW, SV_S>(s_tile, s_part);
+            if (threadIdx.x < SV_R) {
+                // row = ((2*slot + dir) * SV_COLS + column)
+                const int c = threadIdx.x % SV_COLS, sd = threadIdx.x / SV_COLS;
+                const int kk = (k & ~7) + (sd >> 1);
                 if (kk <= k) {
-                    if (threadIdx.x & 1) s_dn[klev - kk] = sum;
-                    else s_up[klev - kk] = sum;
+                    if (sd & 1) s_dn[c][klev - kk] = sum;
+                    else s_up[c][klev - kk] = sum;
                 }
             }
         }
     }
     __syncthreads();
-    for (int lev = threadIdx.x; lev <= klev; lev += SV_THREADS) {
-        const double u = s_up[lev], d = s_dn[lev];
-        const size_t o = col + (size_t)lev * old;
-        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
-    }
-    for (int lay = threadIdx.x; lay < klev; lay += SV_THREADS) {
-        const size_t o = col + (size_t)lay * old;
-        double h = 0.0;
-        if (lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
-            const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
-            h = ((s_dn[lay + 1] - s_up[lay + 1]) - (s_dn[lay] - s_up[lay])) * (c_ss.heatfac / pdp);
+    if (incol) {
+        for (int lev = g; lev <= klev; lev += NGPTSW) {
+            const double u = s_up[cb][lev], d = s_dn[cb][lev];
+            const size_t o = col + (size_t)lev * old;
+            out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
         }
-        out.hr[o] = h;
-        out.hrc[o] = h;
+        for (int lay = g; lay < klev; lay += NGPTSW) {
+            const size_t o = col + (size_t)lay * old;
+            double h = 0.0;
+            if (active && lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
+                const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
+                h = ((s_dn[cb][lay + 1] - s_up[cb][lay + 1]) - (s_dn[cb][lay] - s_up[cb][lay])) * (c_ss.heatfac / pdp);
+            }
+            out.hr[o] = h;
+            out.hrc[o] = h;
+        }
     }
 }
 
@@ -262,7 +281,7 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
 {
     const size_t pad = (size_t)g_tune.sw_solver_pad_kb * 1024;
     if (pad) cudaFuncSetAttribute(sw_solver_kernel<LMAX, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-    sw_solver_kernel<LMAX, STORE><<<w.nc, SV_THREADS, pad, s>>>(t, in, out, w);
+    sw_solver_kernel<LMAX, STORE><<<(w.nc + SV_COLS - 1) / SV_COLS, SV_THREADS, pad, s>>>(t, in, out, w);
 }
 
 void sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
