@@ -210,23 +210,26 @@ const HostArr *reduce_named(const std::string &pfx, const char *oname, const cha
 }
 
 // Append a reduced (rows, ng) Fortran array (g last) or (ng, rows) (g first) to the band table as
-// [row][ig]; returns the first row index.
+// [row][rs] (rs >= ng, zero padded); returns the first row index.
+int pow2_at_least(int n) { int r = 2; while (r < n) r *= 2; return r; }
 int append_rows(std::vector<double> &tab, int base, int ng, const HostArr *a, bool gfirst)
 {
-    const int row0 = (int)((tab.size() - base) / ng);
+    const int rs = pow2_at_least(ng);
+    const int row0 = (int)((tab.size() - base) / rs);
     if (!a) return -1;
     const long rows = a->size() / ng;
     const size_t o = tab.size();
-    tab.resize(o + (size_t)rows * ng);
+    tab.resize(o + (size_t)rows * rs, 0.0);
     for (long r = 0; r < rows; ++r)
         for (int ig = 0; ig < ng; ++ig)
-            tab[o + (size_t)r * ng + ig] = gfirst ? a->data[(size_t)r * ng + ig] : a->data[(size_t)ig * rows + r];
+            tab[o + (size_t)r * rs + ig] = gfirst ? a->data[(size_t)r * ng + ig] : a->data[(size_t)ig * rows + r];
     return row0;
 }
 int append_const_row(std::vector<double> &tab, int base, int ng, const double *vals)
 {
-    const int row0 = (int)((tab.size() - base) / ng);
-    for (int ig = 0; ig < ng; ++ig) tab.push_back(vals[ig]);
+    const int rs = pow2_at_least(ng);
+    const int row0 = (int)((tab.size() - base) / rs);
+    for (int ig = 0; ig < rs; ++ig) tab.push_back(ig < ng ? vals[ig] : 0.0);
     return row0;
 }
 
@@ -291,8 +294,10 @@ int lw_init_impl(double cpdair)
         const GMap m = make_gmap(kLwNgc[b], kLwNgn[b]);
         const int ng = m.ngc;
         B.ng = ng;
+        B.rs = pow2_at_least(ng);
         B.g0 = g0;
         g0 += ng;
+        while (tab.size() % 16) tab.push_back(0.0);      // 128-byte aligned band base
         B.base = (int)tab.size();
         for (int k = 0; k < 5; ++k) B.refrat[k] = rr[b][k];
         for (int k = 0; k < LS_COUNT; ++k) B.sec[k] = -1;
@@ -392,8 +397,10 @@ int sw_init_impl(double cpdair)
         const GMap m = make_gmap(kSwNgc[b], kSwNgn[b]);
         const int ng = m.ngc;
         B.ng = ng;
+        B.rs = pow2_at_least(ng);
         B.g0 = g0;
         g0 += ng;
+        while (tab.size() % 16) tab.push_back(0.0);      // 128-byte aligned band base
         B.base = (int)tab.size();
         for (int k = 0; k < SS_COUNT; ++k) B.sec[k] = -1;
         auto add = [&](int sec, const char *o, const char *r, bool gfirst) {

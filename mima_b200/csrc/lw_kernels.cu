@@ -341,7 +341,7 @@ __device__ __forceinline__ Eta binary(double colA, double rat, double colB, doub
 template <class PW>
 __device__ __forceinline__ void key4(PW &pw, const LwBand &B, int sec, int ind0, int ind1, double scale, const LwPair &p)
 {
-    const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
+    const int ng = B.rs, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
     pw.add(o0, scale * p.fac00);
     pw.add(o0 + ng, scale * p.fac10);
     pw.add(o1, scale * p.fac01);
@@ -350,7 +350,7 @@ __device__ __forceinline__ void key4(PW &pw, const LwBand &B, int sec, int ind0,
 template <class PW>
 __device__ __forceinline__ void lerp2(PW &pw, const LwBand &B, int sec, int row, double frac, double scale)
 {
-    const int ng = B.ng, o = (B.sec[sec] + row - 1) * ng;
+    const int ng = B.rs, o = (B.sec[sec] + row - 1) * ng;
     pw.add(o, scale * (1. - frac));
     pw.add(o + ng, scale * frac);
 }
@@ -359,7 +359,7 @@ template <class PW>
 __device__ __forceinline__ void minor_eta(PW &pw, const LwBand &B, int sec, int neta, int jm, double fm, int indm,
                                           double mf, double scale)
 {
-    const int ng = B.ng, o = (B.sec[sec] + (indm - 1) * neta + (jm - 1)) * ng;
+    const int ng = B.rs, o = (B.sec[sec] + (indm - 1) * neta + (jm - 1)) * ng;
     pw.add(o, scale * ((1. - mf) * (1. - fm)));
     pw.add(o + ng, scale * ((1. - mf) * fm));
     pw.add(o + neta * ng, scale * (mf * (1. - fm)));
@@ -374,7 +374,7 @@ __device__ __forceinline__ void stencil_lower(PW &pw, const LwBand &B, int ind, 
     //   eta < 0.125 : o = ind,     weights (fk0, fk1, fk2)
     //   eta > 0.875 : o = ind - 1, weights (fk2, fk1, fk0)
     //   otherwise   : o = ind,     weights (1-fs, fs)
-    const int ng = B.ng;
+    const int ng = B.rs;
     const double sc = e.speccomb;
     const bool lo = e.specparm < 0.125, hi = e.specparm > 0.875;
     const double p = lo ? e.fs - 1 : -e.fs, p4 = (p * p) * (p * p);
@@ -396,7 +396,7 @@ __device__ __forceinline__ void stencil_lower(PW &pw, const LwBand &B, int ind, 
 template <class PW>
 __device__ __forceinline__ void stencil_upper(PW &pw, const LwBand &B, int ind, const Eta &e, double facA, double facB)
 {
-    const int ng = B.ng, o = (B.sec[LS_ABSB] + ind - 1) * ng;
+    const int ng = B.rs, o = (B.sec[LS_ABSB] + ind - 1) * ng;
     const double sc = e.speccomb;
     pw.add(o, sc * ((1. - e.fs) * facA));
     pw.add(o + ng, sc * (e.fs * facA));
@@ -404,13 +404,13 @@ __device__ __forceinline__ void stencil_upper(PW &pw, const LwBand &B, int ind, 
     pw.add(o + 6 * ng, sc * (e.fs * facB));
 }
 template <class PW>
-__device__ __forceinline__ void frac_const(PW &pw, const LwBand &B, int sec) { pw.frac1(B.sec[sec] * B.ng); }
+__device__ __forceinline__ void frac_const(PW &pw, const LwBand &B, int sec) { pw.frac1(B.sec[sec] * B.rs); }
 template <class PW>
 __device__ __forceinline__ void frac_eta(PW &pw, const LwBand &B, int sec, double colA, double refrat, double colB, double mult)
 {
     const Eta e = binary(colA, refrat, colB, mult);
-    const int o = (B.sec[sec] + e.js - 1) * B.ng;
-    pw.frac2(o, 1. - e.fs, o + B.ng, e.fs);
+    const int o = (B.sec[sec] + e.js - 1) * B.rs;
+    pw.frac2(o, 1. - e.fs, o + B.rs, e.fs);
 }
 // high-CO2 / high-N2O column adjustment (e.g. taumol.f90:529-535)
 __device__ __forceinline__ double adjcol(double col, double coldry, double chiref, double thresh, double a, double ex)
@@ -506,7 +506,7 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             stencil_upper(pw, B, IND0B(5) + e0.js, e0, p.fac00, p.fac10);
             stencil_upper(pw, B, IND1B(5) + e1.js, e1, p.fac01, p.fac11);
             frac_eta(pw, B, LS_FRACB, p.colo3, B.refrat[1], p.colco2, 4.);
-            pw.scale(B.sec[LS_GSCALE] * B.ng);   // stratospheric g-point scaling (:1009-1015)
+            pw.scale(B.sec[LS_GSCALE] * B.rs);   // stratospheric g-point scaling (:1009-1015)
         }
     } else if constexpr (BAND == 4) { // band 5: 700-820, H2O/CO2 lower, O3/CO2 upper; O3 minor, CCl4 (:1022-1294)
         if (lower) {
@@ -518,14 +518,14 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             minor_eta(pw, B, LS_MA1, 9, em.js, em.fs, p.indm, p.minorfrac, p.colo3);
-            pw.add(B.sec[LS_X1] * B.ng, p.wx1);
+            pw.add(B.sec[LS_X1] * B.rs, p.wx1);
             frac_eta(pw, B, LS_FRACA, p.colh2o, B.refrat[0], p.colco2, 8.);
         } else {
             const Eta e0 = binary(p.colo3, c_lw.rat_o3co2[p.jp - 1], p.colco2, 4.);
             const Eta e1 = binary(p.colo3, c_lw.rat_o3co2[p.jp], p.colco2, 4.);
             stencil_upper(pw, B, IND0B(5) + e0.js, e0, p.fac00, p.fac10);
             stencil_upper(pw, B, IND1B(5) + e1.js, e1, p.fac01, p.fac11);
-            pw.add(B.sec[LS_X1] * B.ng, p.wx1);
+            pw.add(B.sec[LS_X1] * B.rs, p.wx1);
             frac_eta(pw, B, LS_FRACB, p.colo3, B.refrat[1], p.colco2, 4.);
         }
     } else if constexpr (BAND == 5) { // band 6: 820-980, H2O lower; CO2 minor, CFC11, CFC12 (:1297-1380)
@@ -536,8 +536,8 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             lerp2(pw, B, LS_MA1, p.indm, p.minorfrac, adj);
         }
-        pw.add(B.sec[LS_X1] * B.ng, p.wx2);
-        pw.add(B.sec[LS_X2] * B.ng, p.wx3);
+        pw.add(B.sec[LS_X1] * B.rs, p.wx2);
+        pw.add(B.sec[LS_X2] * B.rs, p.wx3);
         frac_const(pw, B, LS_FRACA);
     } else if constexpr (BAND == 6) { // band 7: 980-1080, H2O/O3 lower, O3 upper; CO2 minor (:1383-1654)
         if (lower) {
@@ -556,7 +556,7 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             key4(pw, B, LS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo3, p);
             lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, adj);
             frac_const(pw, B, LS_FRACB);
-            pw.scale(B.sec[LS_GSCALE] * B.ng);   // (:1645-1650)
+            pw.scale(B.sec[LS_GSCALE] * B.rs);   // (:1645-1650)
         }
     } else if constexpr (BAND == 7) { // band 8: 1080-1180, H2O lower, O3 upper; CO2, O3, N2O minors; CFC12, CFC22 (:1657-1777)
         const double adj = adjcol(p.colco2, p.coldry, CHI(2, p.jp + 1), 3.0, 2.0, 0.65);
@@ -574,8 +574,8 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_MB2, p.indm, p.minorfrac, p.coln2o);
             frac_const(pw, B, LS_FRACB);
         }
-        pw.add(B.sec[LS_X1] * B.ng, p.wx3);
-        pw.add(B.sec[LS_X2] * B.ng, p.wx4);
+        pw.add(B.sec[LS_X1] * B.rs, p.wx3);
+        pw.add(B.sec[LS_X2] * B.rs, p.wx4);
     } else if constexpr (BAND == 8) { // band 9: 1180-1390, H2O/CH4 lower, CH4 upper; N2O minor (:1780-2040)
         const double adj = adjcol(p.coln2o, p.coldry, CHI(4, p.jp + 1), 1.5, 0.5, 0.65);
         if (lower) {
@@ -734,8 +734,8 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
 // code (~300 KB for all bands) is then fetched once per block instead of once per warp -- with
 // independent warps the kernel was bound by instruction-cache misses.  Work items are (32-column tile,
 // layer) pairs, linearised so that no warp idles when nlay is not a multiple of the block's warp count.
-constexpr int TM_BLOCK_WARPS = 16;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 1) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
+constexpr int TM_BLOCK_WARPS = 8;
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -54,6 +54,8 @@ enum LwSec {
 
 struct LwBand {
     int ng;            // reduced g-points in the band
+    int rs;            // row stride of the band table in doubles (ng rounded up to a power of two: a row never
+                       // straddles a 128-byte line, so one interpolation term costs one L1 wavefront per distinct row)
     int g0;            // first g-point (0-based) in the 140-vector
     int base;          // element offset of the band table in LwTables::tab
     int sec[LS_COUNT]; // row offsets
@@ -71,7 +73,7 @@ struct LwConst {
 };
 
 struct LwTables {             // device pointers
-    const double *tab;        // all band tables, [row][ig]
+    const double *tab;        // all band tables, [row][rs] (band bases 128-byte aligned)
     const double *totplnk;    // (181,16) column-major as in the Fortran
     const double *exptfn;     // interleaved {exp_tbl[i], tfn_tbl[i]}, i = 0..NTBL
 };
@@ -122,7 +124,7 @@ enum SwSec {
 };
 
 struct SwBand {
-    int ng, g0, base;
+    int ng, rs, g0, base;   // rs: padded row stride, see LwBand
     int sec[SS_COUNT];
     int nsflux;        // number of sfluxref rows (1, 5 or 9)
     int nrayl;         // number of rayl rows (1 or 9)

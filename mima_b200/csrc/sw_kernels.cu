@@ -262,7 +262,7 @@ __device__ __forceinline__ Eta binary(double colA, double strrat, double colB, d
 template <class PW>
 __device__ __forceinline__ void key4(PW &pw, const SwBand &B, int sec, int ind0, int ind1, double scale, const SwPair &p)
 {
-    const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
+    const int ng = B.rs, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
     pw.add(o0, scale * p.fac00);
     pw.add(o0 + ng, scale * p.fac10);
     pw.add(o1, scale * p.fac01);
@@ -272,7 +272,7 @@ __device__ __forceinline__ void key4(PW &pw, const SwBand &B, int sec, int ind0,
 template <class PW>
 __device__ __forceinline__ void key8(PW &pw, const SwBand &B, int sec, int ind0, int ind1, int dT, const Eta &e, const SwPair &p)
 {
-    const int ng = B.ng, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
+    const int ng = B.rs, o0 = (B.sec[sec] + ind0 - 1) * ng, o1 = (B.sec[sec] + ind1 - 1) * ng;
     const double sc = e.speccomb, a = 1. - e.fs, b = e.fs;
     pw.add(o0, sc * (a * p.fac00));
     pw.add(o0 + ng, sc * (b * p.fac00));
@@ -286,7 +286,7 @@ __device__ __forceinline__ void key8(PW &pw, const SwBand &B, int sec, int ind0,
 template <class PW>
 __device__ __forceinline__ void lerp2(PW &pw, const SwBand &B, int sec, int row, double frac, double scale)
 {
-    const int ng = B.ng, o = (B.sec[sec] + row - 1) * ng;
+    const int ng = B.rs, o = (B.sec[sec] + row - 1) * ng;
     pw.add(o, scale * (1. - frac));
     pw.add(o + ng, scale * frac);
 }
@@ -297,12 +297,12 @@ __device__ __forceinline__ void selffor(PW &pw, const SwBand &B, const SwPair &p
     lerp2(pw, B, SS_FOR, p.indf, p.forfrac, scale * p.forfac);
 }
 template <class PW>
-__device__ __forceinline__ void sflux_const(PW &pw, const SwBand &B, double scale) { pw.sflux1(B.sec[SS_SFLUX] * B.ng, scale); }
+__device__ __forceinline__ void sflux_const(PW &pw, const SwBand &B, double scale) { pw.sflux1(B.sec[SS_SFLUX] * B.rs, scale); }
 template <class PW>
 __device__ __forceinline__ void sflux_eta(PW &pw, const SwBand &B, const Eta &e)
 {
-    const int o = (B.sec[SS_SFLUX] + e.js - 1) * B.ng;
-    pw.sflux2(o, 1. - e.fs, o + B.ng, e.fs);
+    const int o = (B.sec[SS_SFLUX] + e.js - 1) * B.rs;
+    pw.sflux2(o, 1. - e.fs, o + B.rs, e.fs);
 }
 
 #define IND0A(nsp) (((p.jp - 1) * 5 + (p.jt - 1)) * (nsp))
@@ -322,7 +322,7 @@ __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool 
 {
     const SwBand &B = c_sw.band[BAND];
     // Rayleigh: scalar-rayl bands carry one row filled with the scalar; band 24 lower is eta-interpolated
-    if constexpr (BAND != 8) pw.rayl1(B.sec[SS_RAYL] * B.ng, p.colmol);
+    if constexpr (BAND != 8) pw.rayl1(B.sec[SS_RAYL] * B.rs, p.colmol);
     if constexpr (BAND == 0) { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:243-339)
         if (lower) {
             const Eta e = binary(p.colh2o, 252.131, p.colch4, 8.);
@@ -363,7 +363,7 @@ __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool 
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colh2o, p);
             lerp2(pw, B, SS_FOR, p.indf, p.forfrac, p.colh2o * p.forfac);
         }
-        pw.add(B.sec[SS_X1] * B.ng, p.colch4);
+        pw.add(B.sec[SS_X1] * B.rs, p.colch4);
     } else if constexpr (BAND == 5) { // band 21: 6150-7700, H2O/CO2 both (:749-868)
         if (lower) {
             const Eta e = binary(p.colh2o, 0.0045321, p.colco2, 8.);
@@ -396,23 +396,23 @@ __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool 
         if (lower) {
             const Eta e = binary(p.colh2o, 0.124692, p.colo2, 8.);
             key8(pw, B, SS_ABSA, IND0A(9) + e.js, IND1A(9) + e.js, 9, e, p);
-            pw.add(B.sec[SS_X1] * B.ng, p.colo3);
+            pw.add(B.sec[SS_X1] * B.rs, p.colo3);
             selffor(pw, B, p, p.colh2o);
             if (solar) sflux_eta(pw, B, e);
-            const int o = (B.sec[SS_RAYL] + e.js - 1) * B.ng;
-            pw.rayl2(o, p.colmol * (1. - e.fs), o + B.ng, p.colmol * e.fs);
+            const int o = (B.sec[SS_RAYL] + e.js - 1) * B.rs;
+            pw.rayl2(o, p.colmol * (1. - e.fs), o + B.rs, p.colmol * e.fs);
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colo2, p);
-            pw.add(B.sec[SS_X2] * B.ng, p.colo3);
-            pw.rayl1(B.sec[SS_RAYLB] * B.ng, p.colmol);
+            pw.add(B.sec[SS_X2] * B.rs, p.colo3);
+            pw.rayl1(B.sec[SS_RAYLB] * B.rs, p.colmol);
         }
     } else if constexpr (BAND == 9) { // band 25: 16000-22650, H2O lower, O3 (:1156-1217)
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
-            pw.add(B.sec[SS_X1] * B.ng, p.colo3);
+            pw.add(B.sec[SS_X1] * B.rs, p.colo3);
             if (solar) sflux_const(pw, B, 1.0);
         } else {
-            pw.add(B.sec[SS_X2] * B.ng, p.colo3);
+            pw.add(B.sec[SS_X2] * B.rs, p.colo3);
         }
     } else if constexpr (BAND == 10) { // band 26: 22650-29000, Rayleigh only (:1220-1268)
         if (lower && solar) sflux_const(pw, B, 1.0);
@@ -436,10 +436,10 @@ __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool 
         if (lower) {
             key4(pw, B, SS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             selffor(pw, B, p, p.colh2o);
-            pw.add(B.sec[SS_X2] * B.ng, p.colco2);
+            pw.add(B.sec[SS_X2] * B.rs, p.colco2);
         } else {
             key4(pw, B, SS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colco2, p);
-            pw.add(B.sec[SS_X1] * B.ng, p.colh2o);
+            pw.add(B.sec[SS_X1] * B.rs, p.colh2o);
             if (solar) sflux_const(pw, B, 1.0);
         }
     }
@@ -484,8 +484,8 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
 
 // As in the LW kernel: 16 warps per block step through the bands together (instruction-cache reuse);
 // work items are linearised (32-column tile, layer) pairs.
-constexpr int TM_BLOCK_WARPS = 16;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 1) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
+constexpr int TM_BLOCK_WARPS = 4;
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
