@@ -501,7 +501,9 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
     w.idx = fields ? c.take<uint32_t>(np) : nullptr;
     w.f = fields ? c.take<double>(np * SF_COUNT) : nullptr;
     w.taug = c.take<double>(np * NGPTSW);
-    w.taur = c.take<double>(np * NGPTSW);
+    w.colmol = c.take<double>(np);
+    w.taur24 = c.take<double>(np * 8);
+    w.taur = fields ? c.take<double>(np * NGPTSW) : nullptr;      // expanded from rdesc (test hook)
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
     return c.off + 256;
 }
@@ -958,7 +960,7 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
         const double *base = (const double *)G.lw_cap.p + (f == "fracs" ? np * NGPTLW : 0);
         n = transposed(base, NGPTLW, nlay);
     } else if (sw && f == "taug") n = transposed(G.sw_last.taug, NGPTSW, nlay);
-    else if (sw && f == "taur") n = transposed(G.sw_last.taur, NGPTSW, nlay);
+    else if (sw && f == "taur") { if (!G.sw_last.taur) return -1; n = transposed(G.sw_last.taur, NGPTSW, nlay); }
     else if (sw && f == "sfluxzen") n = transposed(G.sw_last.sfluxzen, NGPTSW, 1);
     else if (sw && f == "laysolfr") {
         std::vector<double> t;

@@ -160,7 +160,10 @@ struct SwWork {
     int *laytrop;             // [col]
     int *laysolfr;            // [col][14]: layer (1-based) whose eta selects the solar source; 0 = never written
     double *f;                // SF_COUNT fields, each [lay][col]
-    double *taug, *taur;      // [col][lay][112]
+    double *taug;             // [col][lay][112]
+    double *colmol;           // [col][lay]: taur(g) = colmol * rayl(g) for every band but 24 (evaluated by the solver)
+    double *taur24;           // [col][lay][8]: taur of band 24, whose Rayleigh coefficient depends on the cell
+    double *taur;             // [col][lay][112], expanded from rdesc only for the stage-capture test hook
     double *sfluxzen;         // [col][112]
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }

@@ -193,7 +193,7 @@ template <int NG>
 struct BandAcc {
     double t[NG];
     const double *__restrict__ tab;
-    double *sr;                      // this lane's taur row in the slab
+    double *t24;                     // band 24 only: this cell's slot in taur24
     double *sflx;                    // this cell's column slot in sfluxzen (+ g0)
     __device__ __forceinline__ void clear()
     {
@@ -215,23 +215,21 @@ struct BandAcc {
 #pragma unroll
         for (int g = 0; g < NG; ++g) t[g] = t[g] + c;
     }
+    // Rayleigh optical depth is not materialised per g-point for the bands where taur(g) = colmol * rayl(g)
+    // with one table row rayl per band: the solver evaluates that.  Band 24's coefficient depends on the
+    // cell (eta-interpolated below laytrop) and goes to the small side array taur24[col][lay][8].
     __device__ __forceinline__ void rayl1(int off, double wgt)
     {
-        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+        if (t24) {
 #pragma unroll
-        for (int j = 0; j < NG / 2; ++j) {
-            const double2 v = __ldg(q + j);
-            reinterpret_cast<double2 *>(sr)[j] = make_double2(wgt * v.x, wgt * v.y);
+            for (int g = 0; g < (NG < 8 ? NG : 8); ++g) t24[g] = wgt * __ldg(tab + off + g);
         }
     }
     __device__ __forceinline__ void rayl2(int o0, double w0, int o1, double w1)
     {
-        const double2 *__restrict__ q0 = reinterpret_cast<const double2 *>(tab + o0);
-        const double2 *__restrict__ q1 = reinterpret_cast<const double2 *>(tab + o1);
+        if (t24) {
 #pragma unroll
-        for (int j = 0; j < NG / 2; ++j) {
-            const double2 a = __ldg(q0 + j), b = __ldg(q1 + j);
-            reinterpret_cast<double2 *>(sr)[j] = make_double2(fma(w1, b.x, w0 * a.x), fma(w1, b.y, w0 * a.y));
+            for (int g = 0; g < (NG < 8 ? NG : 8); ++g) t24[g] = fma(w1, __ldg(tab + o1 + g), w0 * __ldg(tab + o0 + g));
         }
     }
     __device__ __forceinline__ void sflux1(int off, double wgt)
@@ -321,8 +319,8 @@ template <int BAND, class PW>
 __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool solar, PW &pw)
 {
     const SwBand &B = c_sw.band[BAND];
-    // Rayleigh: scalar-rayl bands carry one row filled with the scalar; band 24 lower is eta-interpolated
-    if constexpr (BAND != 8) pw.rayl1(B.sec[SS_RAYL] * B.rs, p.colmol);
+    // Rayleigh: every band but 24 is colmol times one table row (scalar-rayl bands carry a row filled with
+    // the scalar) and is evaluated by the solver; band 24 lower is eta-interpolated
     if constexpr (BAND == 0) { // band 16: 2600-3250, H2O/CH4 lower, CH4 upper (:243-339)
         if (lower) {
             const Eta e = binary(p.colh2o, 252.131, p.colch4, 8.);
@@ -448,7 +446,7 @@ __device__ __forceinline__ void sw_band_terms(const SwPair &p, bool lower, bool 
 template <int BAND>
 __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool valid, bool lower, int lay1,
                                         const int *__restrict__ laysolfr, double *slab,
-                                        double *__restrict__ taug, double *__restrict__ taur, double *sflx_col,
+                                        double *__restrict__ taug, double *t24, double *sflx_col,
                                         size_t cell0, size_t colstride, unsigned vmask)
 {
     constexpr int NG = sw_ng(BAND);
@@ -458,7 +456,7 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
     if (valid) {
         BandAcc<NG> pw;
         pw.tab = T.tab + B.base;
-        pw.sr = slab + (32 + lane) * TM_STRIDE;
+        pw.t24 = BAND == 8 ? t24 : nullptr;
         pw.sflx = sflx_col + g0;
         pw.clear();
         sw_band_terms<BAND>(p, lower, laysolfr[BAND] == lay1, pw);
@@ -473,10 +471,7 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
         const int c = i / HP, j = i - c * HP;
         if ((vmask >> c) & 1u) {
             const double2 a = reinterpret_cast<const double2 *>(slab + c * TM_STRIDE)[j];
-            const double2 b = reinterpret_cast<const double2 *>(slab + (32 + c) * TM_STRIDE)[j];
-            const size_t o = cell0 + (size_t)c * colstride + g0 + 2 * j;
-            *reinterpret_cast<double2 *>(taug + o) = a;
-            *reinterpret_cast<double2 *>(taur + o) = b;
+            *reinterpret_cast<double2 *>(taug + cell0 + (size_t)c * colstride + g0 + 2 * j) = a;
         }
     }
     __syncwarp();
@@ -510,15 +505,37 @@ __global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTab
         sw_cell(in, col, lay, p);
         lower = (lay + 1) <= laytrop;
     }
-    double *slab = s_dyn + (size_t)wid * (64 * TM_STRIDE);
+    double *slab = s_dyn + (size_t)wid * (32 * TM_STRIDE);
+    double *t24 = w.taur24 + ((size_t)(valid ? col : 0) * nlay + lay) * 8;
+    if (valid) w.colmol[(size_t)col * nlay + lay] = p.colmol;
     const int *ls = w.laysolfr + (size_t)(valid ? col : 0) * 14;
     double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
     const size_t colstride = (size_t)nlay * NGPTSW;
     const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTSW;
-#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, w.taur, sflx, cell0, colstride, vmask); __syncthreads()
+#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, t24, sflx, cell0, colstride, vmask); __syncthreads()
     SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
     SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
 #undef SW_BAND
+}
+
+// Test hook (stage capture): expand the Rayleigh descriptors to taur[col][lay][112] exactly as the solver
+// evaluates them.
+__global__ void sw_expand_taur_kernel(SwTables T, SwWork w)
+{
+    const size_t n = (size_t)w.nc * w.nlay * NGPTSW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % NGPTSW);
+        const size_t cell = i / NGPTSW;
+        const int col = (int)(cell / w.nlay);
+        const int band = c_sw_ngb[g];
+        const SwBand &B = c_sw.band[band];
+        double tr = 0.0;
+        if (w.laytrop[col] >= 0) {
+            if (band == 8) tr = w.taur24[cell * 8 + g - B.g0];
+            else tr = w.colmol[cell] * T.tab[B.base + B.sec[SS_RAYL] * B.rs + g - B.g0];
+        }
+        w.taur[i] = tr;
+    }
 }
 
 int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
@@ -528,12 +545,13 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_end(s);
     {
         const long items = (long)((w.nc + 31) / 32) * w.nlay;
-        const size_t smem = (size_t)TM_BLOCK_WARPS * 64 * TM_STRIDE * sizeof(double);
+        const size_t smem = (size_t)TM_BLOCK_WARPS * 32 * TM_STRIDE * sizeof(double);
         cudaFuncSetAttribute(sw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ktimer_begin(K_SW_TAUMOL, s);
         sw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w);
         ktimer_end(s);
     }
+    if (w.taur) sw_expand_taur_kernel<<<1184, 256, 0, s>>>(t, w);
     ktimer_begin(K_SW_SOLVER, s);
     sw_launch_solver(t, in, out, w, s);
     ktimer_end(s);

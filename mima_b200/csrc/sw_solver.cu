@@ -30,6 +30,7 @@ namespace rrtmg {
 
 struct SwSolverConst {
     double heatfac, bpade;
+    int g0[NBNDSW], rs[NBNDSW], rayl[NBNDSW];   // first g-point, table row stride, element offset of the Rayleigh row
     unsigned char ngb[NGPTSW];
 };
 __constant__ SwSolverConst c_ss;
@@ -38,6 +39,10 @@ int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb)
 {
     SwSolverConst h;
     h.heatfac = c.heatfac; h.bpade = c.bpade;
+    for (int b = 0; b < NBNDSW; ++b) {
+        h.g0[b] = c.band[b].g0; h.rs[b] = c.band[b].rs;
+        h.rayl[b] = c.band[b].base + c.band[b].sec[SS_RAYL] * c.band[b].rs;
+    }
     for (int g = 0; g < NGPTSW; ++g) h.ngb[g] = ngb[g];
     return cudaMemcpyToSymbol(c_ss, &h, sizeof h) == cudaSuccess ? 0 : -1;
 }
@@ -129,7 +134,7 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
 }
 
 template <int LMAX, bool STORE>
-__global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
+__global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
 {
     __shared__ double s_tile[SV_R * SV_S];
     __shared__ double s_part[SV_R * (SV_THREADS / SV_R + 1)];
@@ -160,7 +165,13 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
     double zref[LP], zrefd[LP], ztra[LP], ztrad[LP], zdbt[LP];
     double zrup[LMAX + 1], zrupd[LMAX + 1];
     const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
-    const double *__restrict__ taur = w.taur + (size_t)colr * klev * NGPTSW + g;
+    // Rayleigh optical depth: colmol(col, lay) * rayl(g) (same product as taumol_sw's `taur = colmol * rayl`);
+    // band 24 reads its materialised value from taur24 (then raylg = 1).  One load per level either way.
+    const bool b24 = band == 8;
+    const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
+    const double *__restrict__ taur = b24 ? w.taur24 + (size_t)colr * klev * 8 + (g - c_ss.g0[band])
+                                          : w.colmol + (size_t)colr * klev;
+    const int trs = b24 ? 8 : 1;              // stride per layer
     const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0 : 0.0;
 
     // ---- up sweep: reftra + vrtqdr bottom -> top (:103-121); the loads of the next layer group are issued
@@ -173,8 +184,8 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
 #pragma unroll
         for (int j = 0; j < SV_U; ++j) {
             const int l = min(j, klev - 1);
-            trn[j] = taur[(size_t)l * NGPTSW];
-            tgn[j] = taug[(size_t)l * NGPTSW];
+            trn[j] = __ldg(taur + l * trs) * raylg;
+            tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
         }
         for (int l0 = 0; l0 < klev; l0 += SV_U) {
             double tr[SV_U], tg[SV_U];
@@ -184,8 +195,8 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
 #pragma unroll
                 for (int j = 0; j < SV_U; ++j) {
                     const int l = min(l0 + SV_U + j, klev - 1);
-                    trn[j] = taur[(size_t)l * NGPTSW];
-                    tgn[j] = taug[(size_t)l * NGPTSW];
+                    trn[j] = __ldg(taur + l * trs) * raylg;
+                    tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
                 }
             }
 #pragma unroll
@@ -210,14 +221,14 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_kernel(SwTables T, SwIn 
     // ---- down sweep: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
     double ztdn = 1., zrdnd = 0., ztdbt = 1.;
     double trn = 0., tgn = 0.;
-    if (active && !STORE) { trn = taur[(size_t)(klev - 1) * NGPTSW]; tgn = taug[(size_t)(klev - 1) * NGPTSW]; }
+    if (active && !STORE) { trn = __ldg(taur + (klev - 1) * trs) * raylg; tgn = __ldcs(taug + (size_t)(klev - 1) * NGPTSW); }
     for (int k = 0; k <= klev; ++k) {
         const int s = klev - k;            // level counted from the surface
         const int slot = k & 7;
         if (active) {
             const double ru = zrup[s], rud = zrupd[s];
             const double tr = trn, tg = tgn;
-            if (!STORE && s > 1) { trn = taur[(size_t)(s - 2) * NGPTSW]; tgn = taug[(size_t)(s - 2) * NGPTSW]; }
+            if (!STORE && s > 1) { trn = __ldg(taur + (s - 2) * trs) * raylg; tgn = __ldcs(taug + (size_t)(s - 2) * NGPTSW); }
             const double zreflect = rcp_fast(1. - zrdnd * rud);
             const double dif = ztdn - ztdbt;
             const double pfu = (ztdbt * ru + dif * rud) * zreflect;
