@@ -224,9 +224,15 @@ def main():
     stream = torch.cuda.current_stream()
     sh = C.c_void_p(stream.cuda_stream)
     NULL = None
+    # developer experiment: SW on a side stream, forked from / joined to the timing stream each step
+    two_streams = os.environ.get("RRTMG_TWO_STREAMS") == "1"
+    side = torch.cuda.Stream(device=dev) if two_streams else None
+    sh_sw = C.c_void_p(side.cuda_stream) if two_streams else sh
 
     def step_device():
         d = devt
+        if two_streams:
+            side.wait_stream(stream)
         rc = L_.rrtmg_b200_sw_device(C.c_int(ncol), C.c_int(nlay), C.byref(icld), C.byref(iaer),
                                      P(d["play"]), P(d["plev"]), P(d["tlay"]), P(d["tlev"]), P(d["tsfc"]),
                                      P(d["h2o"]), P(d["o3"]), P(d["co2"]), NULL, NULL, NULL,
@@ -234,7 +240,7 @@ def main():
                                      C.c_double(cols.adjes), C.c_int(cols.dyofyr), C.c_double(cols.scon),
                                      C.c_int(0), C.c_int(0), C.c_int(0), *([NULL] * 13),
                                      P(outs["sw_uflx"]), P(outs["sw_dflx"]), P(outs["sw_hr"]), P(outs["sw_uflxc"]),
-                                     P(outs["sw_dflxc"]), P(outs["sw_hrc"]), sh)
+                                     P(outs["sw_dflxc"]), P(outs["sw_hrc"]), sh_sw)
         if rc:
             raise RuntimeError(L_.rrtmg_b200_last_error().decode())
         rc = L_.rrtmg_b200_lw_device(C.c_int(ncol), C.c_int(nlay), C.byref(icld), C.c_int(0),
@@ -245,6 +251,8 @@ def main():
                                      P(outs["lw_dflxc"]), P(outs["lw_hrc"]), NULL, NULL, sh)
         if rc:
             raise RuntimeError(L_.rrtmg_b200_last_error().decode())
+        if two_streams:
+            stream.wait_stream(side)
 
     def HP(t):
         return C.c_void_p(t.data_ptr())
