@@ -162,7 +162,8 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
  * ~ chunk * nlay * 2.6 KB (LW) so that the taumol -> solver staging fields stay L2-resident. */
 int rrtmg_b200_set_chunk(int ncol_per_pass);
 
-/* Generic options: "chunk" (as above), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
+/* Generic options: "chunk" (as above), "host_chunk" (columns per pipeline stage of the host-pointer entry points,
+ * default 8192: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
  * LW solver otherwise overwrites in place; test hook), "kernel_timing" (see rrtmg_b200_kernel_times). */
 int rrtmg_b200_set_option(const char *key, long value);
 

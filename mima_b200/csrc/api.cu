@@ -48,19 +48,20 @@ struct State {
     std::string err;
     long launches = 0;
     int chunk = 0;
+    int host_chunk = 0;
     bool capture = false;
     // LW
     bool lw_ready = false;
     LwConst lwc;
     LwTables lwt{};
-    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_stage_in, lw_stage_out, lw_cap;
+    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_cap;
     LwWork lw_last{};
     int lw_last_ncol = 0;
     // SW
     bool sw_ready = false;
     SwConst swc;
     SwTables swt{};
-    DevBuf sw_tab, sw_exptbl, sw_work, sw_stage_in, sw_stage_out;
+    DevBuf sw_tab, sw_exptbl, sw_work;
     SwWork sw_last{};
     int sw_last_ncol = 0;
 };
@@ -515,43 +516,16 @@ int pick_chunk(int ncol)
 }
 
 // ------------------------------------------------------------------------------------------------
-int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st)
+int lw_validate(int ncol, int nlay, int *icld, int idrv)
 {
     if (!G.lw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_lw_init has not been called");
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;     // LW rad.nomcica:437
     if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: icld > 0 (cloudy-sky branch) is not built");
     if (idrv != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: idrv = 1 (flux derivatives) is not built");
-    if (ncol == 0) return RRTMG_B200_OK;
-    const int chunk = pick_chunk(ncol);
-    LwWork w;
-    const bool fields = G.capture && ncol <= chunk;
-    const size_t need = lw_carve(w, nullptr, chunk, nlay, fields);
-    if (G.lw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
-    for (int c0 = 0; c0 < ncol; c0 += chunk) {
-        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        lw_carve(w, G.lw_work.p, nc, nlay, fields);
-        LwIn in = in0;
-        LwOut out = out0;
-#define OFF(p) if (in.p) in.p += c0
-        OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
-        OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
-#undef OFF
-        out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
-        double *cap = nullptr;
-        if (G.capture && ncol <= chunk) {
-            if (G.lw_cap.ensure(2 * (size_t)nc * nlay * NGPTLW * 8)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (capture)");
-            cap = (double *)G.lw_cap.p;
-        }
-        G.launches += lw_run_pass(G.lwt, in, out, w, st, cap);
-        CUDA_OK(cudaGetLastError());
-    }
-    G.lw_last = w;
-    G.lw_last_ncol = (ncol <= chunk) ? ncol : 0;
     return RRTMG_B200_OK;
 }
-
-int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st)
+int sw_validate(int ncol, int nlay, int *icld, int *iaer)
 {
     if (!G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_sw_init has not been called");
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
@@ -559,15 +533,68 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
     if (iaer && *iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;            // SW rad.nomcica:473
     if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: icld > 0 (cloudy-sky branch) is not built");
     if (iaer && *iaer != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: iaer = 6/10 (aerosols) is not built");
+    return RRTMG_B200_OK;
+}
+
+// One device pass over nc columns whose interface arrays start at in/out (leading dimensions in in.ld/out.ld).
+// `work` must already hold lw_carve(., nc_max, nlay, fields) bytes.
+int lw_chunk(const LwIn &in, const LwOut &out, int nc, int nlay, void *work, bool fields, cudaStream_t st, bool last)
+{
+    LwWork w;
+    lw_carve(w, work, nc, nlay, fields);
+    double *cap = nullptr;
+    if (fields) {
+        if (G.lw_cap.ensure(2 * (size_t)nc * nlay * NGPTLW * 8)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (capture)");
+        cap = (double *)G.lw_cap.p;
+    }
+    G.launches += lw_run_pass(G.lwt, in, out, w, st, cap);
+    CUDA_OK(cudaGetLastError());
+    if (last) { G.lw_last = w; G.lw_last_ncol = fields ? nc : 0; }
+    return RRTMG_B200_OK;
+}
+int sw_chunk(const SwIn &in, const SwOut &out, int nc, int nlay, void *work, bool fields, cudaStream_t st, bool last)
+{
+    SwWork w;
+    sw_carve(w, work, nc, nlay, fields);
+    CUDA_OK(cudaMemsetAsync(w.sfluxzen, 0, (size_t)nc * NGPTSW * 8, st));
+    G.launches += sw_run_pass(G.swt, in, out, w, st);
+    CUDA_OK(cudaGetLastError());
+    if (last) { G.sw_last = w; G.sw_last_ncol = fields ? nc : 0; }
+    return RRTMG_B200_OK;
+}
+
+int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st)
+{
+    if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
+    if (ncol == 0) return RRTMG_B200_OK;
+    const int chunk = pick_chunk(ncol);
+    LwWork w;
+    const bool fields = G.capture && ncol <= chunk;
+    if (G.lw_work.ensure(lw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
+    for (int c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
+        LwIn in = in0;
+        LwOut out = out0;
+#define OFF(p) if (in.p) in.p += c0
+        OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
+        OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
+#undef OFF
+        out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
+        if (const int rc = lw_chunk(in, out, nc, nlay, G.lw_work.p, fields, st, c0 + nc >= ncol)) return rc;
+    }
+    return RRTMG_B200_OK;
+}
+
+int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st)
+{
+    if (const int rc = sw_validate(ncol, nlay, icld, iaer)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     SwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    const size_t need = sw_carve(w, nullptr, chunk, nlay, fields);
-    if (G.sw_work.ensure(need)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
+    if (G.sw_work.ensure(sw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
-        sw_carve(w, G.sw_work.p, nc, nlay, fields);
         SwIn in = in0;
         SwOut out = out0;
 #define OFF(p) if (in.p) in.p += c0
@@ -575,12 +602,8 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
         OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
 #undef OFF
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
-        CUDA_OK(cudaMemsetAsync(w.sfluxzen, 0, (size_t)nc * NGPTSW * 8, st));
-        G.launches += sw_run_pass(G.swt, in, out, w, st);
-        CUDA_OK(cudaGetLastError());
+        if (const int rc = sw_chunk(in, out, nc, nlay, G.sw_work.p, fields, st, c0 + nc >= ncol)) return rc;
     }
-    G.sw_last = w;
-    G.sw_last_ncol = (ncol <= chunk) ? ncol : 0;
     return RRTMG_B200_OK;
 }
 
@@ -598,27 +621,66 @@ double sw_adjflux(double adjes, int dyofyr, double scon)
     return adjflx * solvar;
 }
 
-// host staging helper: copies a host array to the device staging area (or keeps nullptr)
-struct Stager {
-    char *base;
-    size_t off = 0;
-    cudaStream_t st;
-    bool ok = true;
-    const double *up(const double *h, size_t n)
+// Host-pointer ABI: the batch is cut into column chunks that flow through a two-slot pipeline (two streams,
+// two sets of device buffers), so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of
+// chunk i.  A column chunk of a column-major (ncol, rows) array is a 2-D copy with source pitch ncol*8.
+struct Pipe {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    DevBuf in[2], out[2], work[2];
+    int ready()
     {
-        if (!h) return nullptr;
-        double *d = (double *)(base + off);
-        off += ((n * 8 + 255) & ~(size_t)255);
-        if (cudaMemcpyAsync(d, h, n * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
-        return d;
+        for (int i = 0; i < 2; ++i)
+            if (!st[i] && cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess) return -1;
+        return 0;
     }
-    double *out(size_t n)
+    void release()
     {
-        double *d = (double *)(base + off);
-        off += ((n * 8 + 255) & ~(size_t)255);
-        return d;
+        for (int i = 0; i < 2; ++i) {
+            in[i].release(); out[i].release(); work[i].release();
+            if (st[i]) { cudaStreamDestroy(st[i]); st[i] = nullptr; }
+        }
     }
 };
+Pipe P_lw, P_sw;
+
+struct Slot {                 // bump allocator over one slot's device buffer + the chunk being copied
+    char *base;
+    size_t off;
+    int c0, nc, ncol;
+    cudaStream_t st;
+    bool ok;
+    double *take(size_t rows)
+    {
+        double *d = (double *)(base + off);
+        off += (((size_t)nc * rows * 8 + 255) & ~(size_t)255);
+        return d;
+    }
+    const double *up(const double *h, size_t rows)          // host (ncol, rows) columns [c0, c0+nc) -> device (nc, rows)
+    {
+        if (!h) return nullptr;
+        double *d = take(rows);
+        const cudaError_t e = (nc == ncol)
+            ? cudaMemcpyAsync(d, h, (size_t)nc * rows * 8, cudaMemcpyHostToDevice, st)
+            : cudaMemcpy2DAsync(d, (size_t)nc * 8, h + c0, (size_t)ncol * 8, (size_t)nc * 8, rows, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) ok = false;
+        return d;
+    }
+    void down(double *h, const double *d, size_t rows)
+    {
+        const cudaError_t e = (nc == ncol)
+            ? cudaMemcpyAsync(h, d, (size_t)nc * rows * 8, cudaMemcpyDeviceToHost, st)
+            : cudaMemcpy2DAsync(h + c0, (size_t)ncol * 8, d, (size_t)nc * 8, (size_t)nc * 8, rows, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) ok = false;
+    }
+};
+
+int host_chunk(int ncol)
+{
+    if (G.capture) return ncol;                        // stage dumps need the whole batch in one pass
+    int hc = G.host_chunk > 0 ? G.host_chunk : 8192;
+    if (G.chunk > 0 && G.chunk < hc) hc = G.chunk;     // option "chunk" bounds every device pass
+    return hc < ncol ? hc : ncol;
+}
 
 } // namespace
 
@@ -735,9 +797,10 @@ int rrtmg_b200_sw_init(double cpdair)
 int rrtmg_b200_finalize(void)
 {
     std::lock_guard<std::mutex> lk(G.mu);
-    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_stage_in, &G.lw_stage_out, &G.lw_cap,
-                      &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_stage_in, &G.sw_stage_out})
+    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.sw_tab, &G.sw_exptbl, &G.sw_work})
         b->release();
+    P_lw.release();
+    P_sw.release();
     G.lw_ready = G.sw_ready = false;
     G.lw_last_ncol = G.sw_last_ncol = 0;
     G.reduced.clear();
@@ -793,36 +856,43 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                   double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                   double *duflx_dt, double *duflxc_dt)
 {
-    if (!G.lw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_lw_init has not been called");
-    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range");
+    (void)inflglw; (void)iceflglw; (void)liqflglw; (void)cldfr; (void)taucld; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
+    (void)duflx_dt; (void)duflxc_dt;
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
+        !uflxc || !dflxc || !hrc)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
+    if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
-    const size_t nl = (size_t)ncol * nlay, nv = (size_t)ncol * (nlay + 1);
-    const size_t in_bytes = (13 * nl + 2 * nv + ncol + 16 * (size_t)ncol + 16 * nl) * 8 + 64 * 256;
-    const size_t out_bytes = (4 * nv + 2 * nl) * 8 + 8 * 256;
-    if (G.lw_stage_in.ensure(in_bytes) || G.lw_stage_out.ensure(out_bytes))
-        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for LW staging");
-    cudaStream_t st = 0;
-    Stager s{(char *)G.lw_stage_in.p, 0, st};
-    const double *d_play = s.up(play, nl), *d_plev = s.up(plev, nv), *d_tlay = s.up(tlay, nl), *d_tlev = s.up(tlev, nv);
-    const double *d_tsfc = s.up(tsfc, ncol), *d_h2o = s.up(h2ovmr, nl), *d_o3 = s.up(o3vmr, nl), *d_co2 = s.up(co2vmr, nl);
-    const double *d_ch4 = s.up(ch4vmr, nl), *d_n2o = s.up(n2ovmr, nl), *d_o2 = s.up(o2vmr, nl);
-    const double *d_c11 = s.up(cfc11vmr, nl), *d_c12 = s.up(cfc12vmr, nl), *d_c22 = s.up(cfc22vmr, nl), *d_ccl4 = s.up(ccl4vmr, nl);
-    const double *d_emis = s.up(emis, 16 * (size_t)ncol), *d_taer = s.up(tauaer, 16 * nl);
-    if (!s.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
-    Stager o{(char *)G.lw_stage_out.p, 0, st};
-    double *d_uflx = o.out(nv), *d_dflx = o.out(nv), *d_hr = o.out(nl), *d_uflxc = o.out(nv), *d_dflxc = o.out(nv), *d_hrc = o.out(nl);
-    const int rc = rrtmg_b200_lw_device(ncol, nlay, icld, idrv, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2,
-                                        d_ch4, d_n2o, d_o2, d_c11, d_c12, d_c22, d_ccl4, d_emis, inflglw, iceflglw, liqflglw,
-                                        cldfr, taucld, cicewp, cliqwp, reice, reliq, d_taer, d_uflx, d_dflx, d_hr, d_uflxc,
-                                        d_dflxc, d_hrc, duflx_dt, duflxc_dt, (void *)st);
-    if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(uflx, d_uflx, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(dflx, d_dflx, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(hr, d_hr, nl * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(uflxc, d_uflxc, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(dflxc, d_dflxc, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(hrc, d_hrc, nl * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    if (P_lw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
+    const int hc = host_chunk(ncol);
+    const bool fields = G.capture;
+    const size_t L = nlay, V = nlay + 1;
+    const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L) * 8 + 32 * 256;
+    const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
+    LwWork wsz;
+    const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields);
+    const int nslot = hc < ncol ? 2 : 1;
+    for (int i = 0; i < nslot; ++i)
+        if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes))
+            return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW pipeline buffers");
+    int idx = 0;
+    for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
+        const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
+        const int slot = idx & 1;
+        cudaStream_t st = P_lw.st[slot];
+        Slot a{(char *)P_lw.in[slot].p, 0, c0, nc, ncol, st, true};
+        LwIn in{nc, a.up(play, L), a.up(plev, V), a.up(tlay, L), a.up(tlev, V), a.up(tsfc, 1),
+                a.up(h2ovmr, L), a.up(o3vmr, L), a.up(co2vmr, L), a.up(ch4vmr, L), a.up(n2ovmr, L), a.up(o2vmr, L),
+                a.up(cfc11vmr, L), a.up(cfc12vmr, L), a.up(cfc22vmr, L), a.up(ccl4vmr, L), a.up(emis, 16), a.up(tauaer, 16 * L)};
+        if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
+        Slot o{(char *)P_lw.out[slot].p, 0, c0, nc, ncol, st, true};
+        LwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
+        if (const int rc = lw_chunk(in, out, nc, nlay, P_lw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
+        o.down(uflx, out.uflx, V); o.down(dflx, out.dflx, V); o.down(hr, out.hr, L);
+        o.down(uflxc, out.uflxc, V); o.down(dflxc, out.dflxc, V); o.down(hrc, out.hrc, L);
+        if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)");
+    }
+    for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_lw.st[i]));
     return RRTMG_B200_OK;
 }
 
@@ -859,40 +929,52 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
                   const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                   double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc, double *swhrc)
 {
-    if (!G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_sw_init has not been called");
-    if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range");
+    (void)inflgsw; (void)iceflgsw; (void)liqflgsw; (void)cldfr; (void)taucld; (void)ssacld; (void)asmcld; (void)fsfcld;
+    (void)cicewp; (void)cliqwp; (void)reice; (void)reliq; (void)tauaer; (void)ssaaer; (void)asmaer; (void)ecaer;
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
+        !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
+    if (const int rc = sw_validate(ncol, nlay, icld, iaer)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
-    const size_t nl = (size_t)ncol * nlay, nv = (size_t)ncol * (nlay + 1);
-    const size_t in_bytes = (9 * nl + 2 * nv + 6 * (size_t)ncol) * 8 + 64 * 256;
-    const size_t out_bytes = (4 * nv + 2 * nl) * 8 + 8 * 256;
-    if (G.sw_stage_in.ensure(in_bytes) || G.sw_stage_out.ensure(out_bytes))
-        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for SW staging");
-    cudaStream_t st = 0;
-    Stager s{(char *)G.sw_stage_in.p, 0, st};
-    const double *d_play = s.up(play, nl), *d_plev = s.up(plev, nv), *d_tlay = s.up(tlay, nl), *d_tlev = s.up(tlev, nv);
-    const double *d_tsfc = s.up(tsfc, ncol), *d_h2o = s.up(h2ovmr, nl), *d_o3 = s.up(o3vmr, nl), *d_co2 = s.up(co2vmr, nl);
-    const double *d_ch4 = s.up(ch4vmr, nl), *d_n2o = s.up(n2ovmr, nl), *d_o2 = s.up(o2vmr, nl);
-    // MiMA passes the same albedo array four times (rrtm_radiation.f90:690): upload once per distinct pointer
-    const double *d_asdir = s.up(asdir, ncol);
-    const double *d_asdif = asdif == asdir ? d_asdir : s.up(asdif, ncol);
-    const double *d_aldir = aldir == asdir ? d_asdir : s.up(aldir, ncol);
-    const double *d_aldif = aldif == asdir ? d_asdir : (aldif == aldir ? d_aldir : s.up(aldif, ncol));
-    const double *d_cosz = s.up(coszen, ncol);
-    if (!s.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
-    Stager o{(char *)G.sw_stage_out.p, 0, st};
-    double *d_u = o.out(nv), *d_d = o.out(nv), *d_h = o.out(nl), *d_uc = o.out(nv), *d_dc = o.out(nv), *d_hc = o.out(nl);
-    const int rc = rrtmg_b200_sw_device(ncol, nlay, icld, iaer, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2,
-                                        d_ch4, d_n2o, d_o2, d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjes, dyofyr, scon,
-                                        inflgsw, iceflgsw, liqflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, cicewp, cliqwp,
-                                        reice, reliq, tauaer, ssaaer, asmaer, ecaer, d_u, d_d, d_h, d_uc, d_dc, d_hc, (void *)st);
-    if (rc) return rc;
-    CUDA_OK(cudaMemcpyAsync(swuflx, d_u, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(swdflx, d_d, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(swhr, d_h, nl * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(swuflxc, d_uc, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(swdflxc, d_dc, nv * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(swhrc, d_hc, nl * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    if (P_sw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
+    const int hc = host_chunk(ncol);
+    const bool fields = G.capture;
+    const size_t L = nlay, V = nlay + 1;
+    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6) * 8 + 32 * 256;
+    const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
+    SwWork wsz;
+    const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields);
+    const int nslot = hc < ncol ? 2 : 1;
+    for (int i = 0; i < nslot; ++i)
+        if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes))
+            return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW pipeline buffers");
+    const double adjflux = sw_adjflux(adjes, dyofyr, scon);
+    int idx = 0;
+    for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
+        const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
+        const int slot = idx & 1;
+        cudaStream_t st = P_sw.st[slot];
+        Slot a{(char *)P_sw.in[slot].p, 0, c0, nc, ncol, st, true};
+        const double *d_play = a.up(play, L), *d_plev = a.up(plev, V), *d_tlay = a.up(tlay, L), *d_tlev = a.up(tlev, V);
+        const double *d_tsfc = a.up(tsfc, 1), *d_h2o = a.up(h2ovmr, L), *d_o3 = a.up(o3vmr, L), *d_co2 = a.up(co2vmr, L);
+        const double *d_ch4 = a.up(ch4vmr, L), *d_n2o = a.up(n2ovmr, L), *d_o2 = a.up(o2vmr, L);
+        // MiMA passes the same albedo array four times (rrtm_radiation.f90:690): upload once per distinct pointer
+        const double *d_asdir = a.up(asdir, 1);
+        const double *d_asdif = asdif == asdir ? d_asdir : a.up(asdif, 1);
+        const double *d_aldir = aldir == asdir ? d_asdir : a.up(aldir, 1);
+        const double *d_aldif = aldif == asdir ? d_asdir : (aldif == aldir ? d_aldir : a.up(aldif, 1));
+        const double *d_cosz = a.up(coszen, 1);
+        if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
+        SwIn in{nc, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2, d_ch4, d_n2o, d_o2,
+                d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjflux};
+        Slot o{(char *)P_sw.out[slot].p, 0, c0, nc, ncol, st, true};
+        SwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
+        if (const int rc = sw_chunk(in, out, nc, nlay, P_sw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
+        o.down(swuflx, out.uflx, V); o.down(swdflx, out.dflx, V); o.down(swhr, out.hr, L);
+        o.down(swuflxc, out.uflxc, V); o.down(swdflxc, out.dflxc, V); o.down(swhrc, out.hrc, L);
+        if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (SW)");
+    }
+    for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_sw.st[i]));
     return RRTMG_B200_OK;
 }
 
@@ -984,6 +1066,7 @@ int rrtmg_b200_set_option(const char *key, long value)
 {
     const std::string k(key ? key : "");
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
+    if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_store") { g_tune.sw_solver_store = (int)value; return RRTMG_B200_OK; }
