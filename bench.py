@@ -59,6 +59,17 @@ def b_alg(L: int) -> int:
     return 8 * (1060 * L + 35)
 
 
+def measured_traffic(workload: str, kernel: str, ncol: int):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json: bytes per column per launch, measured on a full-size pass), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))[workload][kernel]
+        return t["dram_bytes_per_column"] * ncol
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -70,7 +81,7 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region (NVML; nvidia-smi as a fallback)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -79,28 +90,62 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                pass
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_reference_rate(workload: str, sample_cols: int, repeats: int, threads: int | None = None):
@@ -157,7 +202,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="T170L60")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -176,7 +221,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mima_b200 import rrtmg
+    from mima_b200 import rrtmg, sharding
     from mima_b200.columns import RESOLUTIONS, make_columns
 
     if not torch.cuda.is_available():
@@ -284,11 +329,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device=dev)
 
     # ---------------- device-resident timing
     for _ in range(args.warmup):
@@ -334,7 +375,7 @@ def main():
     peak, peak_src = measured_peak()
     ms_step = ms_dev / args.steps
     total_cols = ncol * world
-    value = total_cols / (ms_step * 1e-3)
+    value = sharding.aggregate_rate(ncol, world, ms_step)
     kab = kernel_alg_bytes(nlay)
     per_kernel = {}
     for i, k in enumerate(KERNELS):
@@ -348,7 +389,9 @@ def main():
     if dom:
         ach = per_kernel[dom]["gbs"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": measured_traffic(args.workload, dom, int(ncol * args.steps / kn[KERNELS.index(dom)])),
+                "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                "peak_source": peak_src,
                 "step_achieved": b_alg(nlay) * ncol / (ms_step * 1e-3) / 1e9,
                 "step_frac": b_alg(nlay) * ncol / (ms_step * 1e-3) / 1e9 / peak,
                 "kernel_share_of_step": per_kernel[dom]["ms_per_step"] / ms_step,

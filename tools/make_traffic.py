@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""profiles/traffic.json from `ncu --page raw --csv` dumps: DRAM bytes (read + write) per column and launch
+for each kernel.  usage: make_traffic.py WORKLOAD COLUMNS_PER_LAUNCH raw1.csv [raw2.csv ...]"""
+import csv, json, os, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+W, ncol = sys.argv[1], int(sys.argv[2])
+names = {"lw_prep": "lw_prep", "lw_taumol": "lw_taumol", "lw_rtrn": "lw_rtrn", "sw_prep": "sw_prep", "sw_taumol": "sw_taumol", "sw_solver": "sw_solver"}
+out_path = os.path.join(ROOT, "profiles", "traffic.json")
+out = json.load(open(out_path)) if os.path.exists(out_path) else {}
+out.setdefault(W, {})
+for f in sys.argv[3:]:
+    rows = list(csv.reader(open(f)))
+    hdr, units = rows[0], rows[1]
+    i = {h: k for k, h in enumerate(hdr)}
+    for r in rows[2:]:
+        k = next((v for n, v in names.items() if n in r[i["Kernel Name"]]), None)
+        if not k:
+            continue
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        rd = float(r[i["dram__bytes_read.sum"]]) * scale[units[i["dram__bytes_read.sum"]]]
+        wr = float(r[i["dram__bytes_write.sum"]]) * scale[units[i["dram__bytes_write.sum"]]]
+        out[W][k] = {"dram_bytes_per_column": (rd + wr) / ncol, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                     "columns_per_launch": ncol, "duration_ms_under_ncu": float(r[i["gpu__time_duration.sum"]]),
+                     "fp64_pipe_pct": float(r[i["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
+                     "l1tex_throughput_pct": float(r[i["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]]),
+                     "dram_throughput_pct": float(r[i["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+                     "issue_active_pct": float(r[i["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                     "registers_per_thread": int(float(r[i["launch__registers_per_thread"]])), "source": os.path.basename(f)}
+json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
+print(json.dumps(out[W], indent=1))
