@@ -235,9 +235,7 @@ def main():
     rrtmg.rrtmg_sw_ini()
     if args.chunk:
         rrtmg.set_option("chunk", args.chunk)
-    for kv in filter(None, os.environ.get("RRTMG_TUNE", "").split(",")):      # developer knob: key=value[,key=value]
-        k, v = kv.split("=")
-        rrtmg.set_option(k, int(v))
+    # (developer knob RRTMG_TUNE="key=value[,...]" is applied by rrtmg.lib() at load time)
     L_ = rrtmg.lib()
 
     nlon, nlat, nlay = RESOLUTIONS[args.workload]

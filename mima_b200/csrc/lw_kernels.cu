@@ -785,9 +785,9 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
         cudaMemcpyAsync(cap + n, w.fracs, n * 8, cudaMemcpyDeviceToDevice, s);
     }
     ktimer_begin(K_LW_RTRN, s);
-    lw_launch_rtrn(t, in, out, w, s);
+    const int nrt = lw_launch_rtrn(t, in, out, w, s);
     ktimer_end(s);
-    return 3;
+    return 2 + nrt;
 }
 
 } // namespace rrtmg

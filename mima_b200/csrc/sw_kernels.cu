@@ -553,9 +553,9 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     }
     if (w.taur) sw_expand_taur_kernel<<<1184, 256, 0, s>>>(t, w);
     ktimer_begin(K_SW_SOLVER, s);
-    sw_launch_solver(t, in, out, w, s);
+    const int nsv = sw_launch_solver(t, in, out, w, s);
     ktimer_end(s);
-    return 3;
+    return 2 + nsv;
 }
 
 } // namespace rrtmg

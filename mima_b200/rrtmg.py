@@ -59,6 +59,12 @@ def lib() -> C.CDLL:
         L.rrtmg_b200_sw_init.argtypes = [C.c_double]
         L.rrtmg_b200_set_option.argtypes = [C.c_char_p, C.c_long]
         _lib = L
+        # developer knob: RRTMG_TUNE="key=value[,key=value]" applies library options at load time
+        for kv in filter(None, os.environ.get("RRTMG_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            rc = L.rrtmg_b200_set_option(k.encode(), int(v))
+            if rc:
+                raise RRTMGError(rc, L.rrtmg_b200_last_error().decode())
     return _lib
 
 
