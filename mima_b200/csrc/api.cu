@@ -490,7 +490,6 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
     w.plankbnd = c.take<double>((size_t)nc * 16);
     w.taug = c.take<double>(np * NGPTLW);
     w.fracs = c.take<double>(np * NGPTLW);
-    w.part = c.take<double>((size_t)nc * 10 * (nlay + 1));
     return c.off + 256;
 }
 size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
@@ -507,7 +506,6 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
     w.taur24 = c.take<double>(np * 8);
     w.taur = fields ? c.take<double>(np * NGPTSW) : nullptr;      // expanded from rdesc (test hook)
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
-    w.part = c.take<double>((size_t)nc * 8 * (nlay + 1));
     return c.off + 256;
 }
 
@@ -687,7 +685,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 1, 0};
+Tuning g_tune = {0, 0, 0, 7};
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1071,7 +1069,6 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
-    if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_variant") { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_store") { g_tune.sw_solver_store = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }

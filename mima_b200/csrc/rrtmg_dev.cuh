@@ -100,7 +100,6 @@ struct LwWork {
     double *planklev;         // [col][lay+1][16]  (level 0 = surface)
     double *plankbnd;         // [col][16]
     double *taug, *fracs;     // [col][lay][140]
-    double *part;             // [col][5 slices][down, up][lay+1]: g-sums of the slice solver (lw_solver.cu)
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
@@ -166,7 +165,6 @@ struct SwWork {
     double *taur24;           // [col][lay][8]: taur of band 24, whose Rayleigh coefficient depends on the cell
     double *taur;             // [col][lay][112], expanded from rdesc only for the stage-capture test hook
     double *sfluxzen;         // [col][112]
-    double *part;             // [col][4 slices][up, down][lay+1]: g-sums of the slice solver (sw_solver.cu)
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
@@ -235,9 +233,9 @@ enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_
 void ktimer_begin(int id, cudaStream_t s);
 void ktimer_end(cudaStream_t s);
 
-// launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb", "sw_solver_store"): extra dynamic shared memory per block,
+// launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb", "sw_solver_store", "sw_solver_variant"): extra dynamic shared memory per block,
 // used to cap the resident blocks per SM so that the sweeps' per-thread state stays L2-resident
-struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, lw_rtrn_variant, sw_solver_variant; };
+struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant; };
 extern Tuning g_tune;
 
 // solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)

@@ -71,6 +71,16 @@ __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double 
 
 // reftra_sw for one clear-sky (g, layer) cell with asymmetry 0 (gamma3 = gamma4 = 1/2, zwo = zw), plus the
 // direct-beam transmittance dbt = exp(-tau/mu0).
+// one Newton step on the MUFU seed: relative error ~1e-12, enough wherever no table index depends on it
+__device__ __forceinline__ double rcp_1n(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-x, y, 1.0), y);
+}
+template <bool R1> __device__ __forceinline__ double rcp_sel(double x) { return R1 ? rcp_1n(x) : rcp_fast(x); }
+
+template <bool R1>
 __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double bpade, double prmu0, double rmu0,
                                           double tr, double tg, double &ref, double &refd, double &tra,
                                           double &trad, double &dbt)
@@ -120,24 +130,28 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
             ref = eps;
             tra = zem2;
         } else {
-            const double rd = zw * rcp_fast(zdenr);
+            const double rd = zw * rcp_sel<R1>(zdenr);
             ref = (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * rd;
             tra = zem2 - zem2 * ((zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * rd);
         }
         const double zemm = zem1 * zem1;
         // zdend = 1/((1 - zbeta*zemm)*zrkg), zbeta = (gamma1 - zrk)/zrkg
-        const double zdend = rcp_fast(fma(-(zgamma1 - zrk), zemm, zrkg));
+        const double zdend = rcp_sel<R1>(fma(-(zgamma1 - zrk), zemm, zrkg));
         refd = zgamma2 * (1. - zemm) * zdend;
         trad = zrk2 * zem1 * zdend;
         dbt = zem2;
     }
 }
 
-template <int LMAX, bool STORE>
+// OPT bit 0: one-Newton reciprocals outside the table-index paths; bit 1: g-sum in batches of 4 levels (half the tile)
+template <int LMAX, bool STORE, int OPT>
 __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
 {
-    __shared__ double s_tile[SV_R * SV_S];
-    __shared__ double s_part[SV_R * (SV_THREADS / SV_R + 1)];
+    constexpr bool R1 = (OPT & 1) != 0;
+    constexpr int NB = (OPT & 2) ? 4 : 8;          // levels per reduction batch
+    constexpr int NR = NB * 2 * SV_COLS;           // tile rows
+    __shared__ double s_tile[NR * SV_S];
+    __shared__ double s_part[NR * (SV_THREADS / NR + 1)];
     __shared__ double s_up[SV_COLS][LMAX + 1], s_dn[SV_COLS][LMAX + 1];
     const int klev = w.nlay;
     const int cb = threadIdx.x / NGPTSW;           // column of the block this thread works on
@@ -204,9 +218,9 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                 const int l = l0 + j;
                 if (l < klev) {
                     double ref, refd, tra, trad, dbt;
-                    sw_reftra(tb, bpade, mu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
+                    sw_reftra<R1>(tb, bpade, mu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
                     if (STORE) { zref[l] = ref; zrefd[l] = refd; ztra[l] = tra; ztrad[l] = trad; zdbt[l] = dbt; }
-                    const double zreflect = rcp_fast(1. - rupd * refd);
+                    const double zreflect = rcp_sel<R1>(1. - rupd * refd);
                     const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
                     const double rupd_n = refd + trad * trad * rupd * zreflect;
                     rup = rup_n;
@@ -224,12 +238,12 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     if (active && !STORE) { trn = __ldg(taur + (klev - 1) * trs) * raylg; tgn = __ldcs(taug + (size_t)(klev - 1) * NGPTSW); }
     for (int k = 0; k <= klev; ++k) {
         const int s = klev - k;            // level counted from the surface
-        const int slot = k & 7;
+        const int slot = k & (NB - 1);
         if (active) {
             const double ru = zrup[s], rud = zrupd[s];
             const double tr = trn, tg = tgn;
             if (!STORE && s > 1) { trn = __ldg(taur + (s - 2) * trs) * raylg; tgn = __ldcs(taug + (size_t)(s - 2) * NGPTSW); }
-            const double zreflect = rcp_fast(1. - zrdnd * rud);
+            const double zreflect = rcp_sel<R1>(1. - zrdnd * rud);
             const double dif = ztdn - ztdbt;
             const double pfu = (ztdbt * ru + dif * rud) * zreflect;
             const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
@@ -241,9 +255,9 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                 if (STORE) {
                     ref = zref[l]; refd = zrefd[l]; tra = ztra[l]; trad = ztrad[l]; dbt = zdbt[l];
                 } else {
-                    sw_reftra(tb, bpade, mu0, rmu0, tr, tg, ref, refd, tra, trad, dbt);
+                    sw_reftra<R1>(tb, bpade, mu0, rmu0, tr, tg, ref, refd, tra, trad, dbt);
                 }
-                const double zr = rcp_fast(1. - refd * zrdnd);
+                const double zr = rcp_sel<R1>(1. - refd * zrdnd);
                 const double ztdn_n = ztdbt * tra + (trad * (dif + ztdbt * ref * zrdnd)) * zr;
                 const double zrdnd_n = refd + trad * trad * zrdnd * zr;
                 ztdbt = dbt * ztdbt;
@@ -254,12 +268,12 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
             s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = 0.0;
             s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = 0.0;
         }
-        if (slot == 7 || k == klev) {
-            const double sum = tile_reduce<SV_THREADS, SV_R, NGPTSW, SV_S>(s_tile, s_part);
-            if (threadIdx.x < SV_R) {
+        if (slot == NB - 1 || k == klev) {
+            const double sum = tile_reduce<SV_THREADS, NR, NGPTSW, SV_S>(s_tile, s_part);
+            if (threadIdx.x < NR) {
                 // row = ((2*slot + dir) * SV_COLS + column)
                 const int c = threadIdx.x % SV_COLS, sd = threadIdx.x / SV_COLS;
-                const int kk = (k & ~7) + (sd >> 1);
+                const int kk = (k & ~(NB - 1)) + (sd >> 1);
                 if (kk <= k) {
                     if (sd & 1) s_dn[c][klev - kk] = sum;
                     else s_up[c][klev - kk] = sum;
@@ -287,379 +301,28 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     }
 }
 
-template <int LMAX, bool STORE>
+template <int LMAX, bool STORE, int OPT>
 static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
     const size_t pad = (size_t)g_tune.sw_solver_pad_kb * 1024;
-    if (pad) cudaFuncSetAttribute(sw_solver_kernel<LMAX, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-    sw_solver_kernel<LMAX, STORE><<<(w.nc + SV_COLS - 1) / SV_COLS, SV_THREADS, pad, s>>>(t, in, out, w);
+    if (pad) cudaFuncSetAttribute(sw_solver_kernel<LMAX, STORE, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    sw_solver_kernel<LMAX, STORE, OPT><<<(w.nc + SV_COLS - 1) / SV_COLS, SV_THREADS, pad, s>>>(t, in, out, w);
 }
-
-
-// =====================================================================================================
-// Variant 1 ("slice"): block = one warp <-> (column, slice of 28 g-points); 4 slices cover the 112 g-points.
-// Same two sweeps as above, but
-//   * no block barrier: the g-sum of a slice goes through a per-warp tile (4 levels x {up, down} x 28) that
-//     four lanes per row add up; the four slice partials of a column are combined in a fixed order by
-//     sw_flux_finish_kernel, which also writes the six interface arrays in 256-byte runs;
-//   * reftra is branch-free on the common path (conservative scattering and the degenerate denominator are
-//     evaluated only when some lane of the warp needs them), so the two layers of a group interleave and
-//     their table gathers overlap;
-//   * the down sweep also works on pairs of levels, and the saved (rup, rupd) of the next pair are loaded
-//     before the arithmetic of the current one;
-//   * shared memory per warp is 1.9 KB, which leaves the L1 to the 160 KB exp table.
-// =====================================================================================================
-constexpr int SS_W = 28;                   // g-points per slice
-constexpr int SS_NSL = NGPTSW / SS_W;      // 4
-constexpr int SS_TS = 29;                  // tile row stride
-static_assert(SS_W * SS_NSL == NGPTSW, "slices must tile the g-points");
-
-// sum of the 28 values of each of the 8 tile rows; lanes 4r..4r+3 return the sum of row r
-__device__ __forceinline__ double sw_slice_reduce8(const double *tile, int lane)
+template <int LMAX>
+static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    __syncwarp();
-    const double *src = tile + (lane >> 2) * SS_TS + (lane & 3);
-    double acc = src[0];
-#pragma unroll
-    for (int j = 1; j < 7; ++j) acc += src[4 * j];
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    __syncwarp();
-    return acc;
-}
-
-// exp(-ze) and exp(+ze) as in sw_exp, written with selects
-__device__ __forceinline__ double sw_exp2(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
-{
-    const bool small = ze <= 0.06;
-    const double ems = 1. - ze + 0.5 * ze * ze;
-    const double r = rcp_fast(small ? ems : bpade + ze);
-    const int itind = small ? 0 : (int)(10000.0 * (ze * r) + 0.5);
-    const double2 e = __ldg(tb + itind);
-    recip = small ? r : e.y;
-    return small ? ems : e.x;
-}
-
-// conservative-scattering branch of reftra (:162-214), asymmetry 0
-__device__ __forceinline__ void sw_reftra_cons(const double2 *__restrict__ tb, double bpade, double prmu0, double zgamma1,
-                                            double zto1, double zed, double &ref, double &refd, double &tra,
-                                            double &trad, double &dbt)
-{
-    const double za1 = zgamma1 * prmu0 - 0.5;
-    const double zgt = zgamma1 * zto1;
-    double rcp;
-    const double ze2 = sw_exp(tb, fmin(zed, 500.), bpade, rcp);
-    const double rg = rcp_fast(1. + zgt);
-    ref = (zgt - za1 * (1. - ze2)) * rg;
-    tra = 1. - ref;
-    refd = zgt * rg;
-    trad = 1. - refd;
-    if (ze2 == 1.0) { ref = 0.0; tra = 1.0; refd = 0.0; trad = 1.0; }
-    dbt = ze2;
-}
-
-// returns true when the cell is in the conservative-scattering regime (the outputs are then to be
-// replaced by sw_reftra_fix)
-__device__ __forceinline__ bool sw_reftra2(const double2 *__restrict__ tb, double bpade, double prmu0, double rmu0,
-                                           double tr, double tg, double &ref, double &refd, double &tra,
-                                           double &trad, double &dbt)
-{
-    const double eps = 1.e-08, zwcrit = 0.9999995;
-    const double zto1 = tr + tg;                             // ztauc
-    const double zw = tr * rcp_fast(zto1);                   // zomcc
-    const double zgamma1 = (8. - zw * 5.) * 0.25;
-    const double zgamma2 = 3. * zw * 0.25;
-    const double zed = zto1 * rmu0;                          // direct-beam optical path
-    const double za1 = (zgamma1 + zgamma2) * 0.5;            // = za2
-    const double zrk = sqrt_fast(zgamma1 * zgamma1 - zgamma2 * zgamma2);   // NaN/inf for zw -> 1 is discarded below
-    const double zrp = zrk * prmu0;
-    const double zrp1 = 1. + zrp;
-    const double zrm1 = 1. - zrp;
-    const double zrk2 = 2. * zrk;
-    const double zrpp = 1. - zrp * zrp;
-    const double zrkg = zrk + zgamma1;
-    const double hA = fma(zrk, 0.5, za1), hB = fma(zrk, -0.5, za1);
-    const double zr1 = zrm1 * hA;
-    const double zr2 = zrp1 * hB;
-    const double zr3 = zrk2 * (0.5 - za1 * prmu0);
-    const double zr4 = zrpp * zrkg;
-    const double zr5 = zrpp * (zrk - zgamma1);
-    const double zt1 = zrp1 * hA;
-    const double zt2 = zrm1 * hB;
-    const double zt3 = zrk2 * (0.5 + za1 * prmu0);
-    double zep1, zep2;
-    const double zem1 = sw_exp2(tb, fmin(zrk * zto1, 500.), bpade, zep1);
-    const double zem2 = sw_exp2(tb, fmin(zed, 500.), bpade, zep2);
-    const double zdenr = fma(zr4, zep1, zr5 * zem1);         // = zdent (zt4 = zr4, zt5 = zr5)
-    const bool degen = fabs(zdenr) <= eps;
-    const double rd = zw * rcp_fast(degen ? 1.0 : zdenr);
-    const double refn = (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * rd;
-    const double tran = zem2 - zem2 * ((zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * rd);
-    ref = degen ? eps : refn;
-    tra = degen ? zem2 : tran;
-    const double zemm = zem1 * zem1;
-    // zdend = 1/((1 - zbeta*zemm)*zrkg), zbeta = (gamma1 - zrk)/zrkg
-    const double zdend = rcp_fast(fma(-(zgamma1 - zrk), zemm, zrkg));
-    refd = zgamma2 * (1. - zemm) * zdend;
-    trad = zrk2 * zem1 * zdend;
-    dbt = zem2;
-    return zw >= zwcrit;
-}
-// the rare branch for the lanes that need it (the caller votes once per group of layers); results by value so
-// that the caller's per-layer arrays stay in registers
-struct SwLayer { double ref, refd, tra, trad, dbt; };
-__device__ __noinline__ SwLayer sw_reftra_fix(const double2 *__restrict__ tb, double bpade, double prmu0, double rmu0,
-                                              double tr, double tg)
-{
-    const double zto1 = tr + tg;
-    const double zw = tr * rcp_fast(zto1);
-    const double zgamma1 = (8. - zw * 5.) * 0.25;
-    SwLayer r;
-    sw_reftra_cons(tb, bpade, prmu0, zgamma1, zto1, zto1 * rmu0, r.ref, r.refd, r.tra, r.trad, r.dbt);
-    return r;
-}
-
-template <int LMAX, int MINB>
-__global__ void __launch_bounds__(32, MINB) sw_solver_slice_kernel(SwTables T, SwIn in, SwWork w, double *__restrict__ part)
-{
-    __shared__ double s_tile[8 * SS_TS];
-    const int klev = w.nlay;
-    const int lane = threadIdx.x;
-    const int col = blockIdx.x / SS_NSL, sl = blockIdx.x - col * SS_NSL;
-    const double prmu0 = in.coszen[col];
-    if (prmu0 < ZEPZEN) return;                // night column: the finish kernel writes zeros
-    const bool act = lane < SS_W;
-    const int gl = act ? lane : SS_W - 1;      // idle lanes shadow the last g-point (no stores)
-    const int g = sl * SS_W + gl;
-    const int band = c_ss.ngb[g];
-    const double bpade = c_ss.bpade;
-    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
-    const double rmu0 = 1. / prmu0;
-
-    const bool uvvis = band >= 9 && band <= 12;
-    const double albd = uvvis ? in.asdif[col] : in.aldif[col];
-    const double albp = uvvis ? in.asdir[col] : in.aldir[col];
-
-    double zrup[LMAX + 1], zrupd[LMAX + 1];
-    const double *__restrict__ taug = w.taug + (size_t)col * klev * NGPTSW + g;
-    const bool b24 = band == 8;
-    const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
-    const double *__restrict__ taur = b24 ? w.taur24 + (size_t)col * klev * 8 + (g - c_ss.g0[band])
-                                          : w.colmol + (size_t)col * klev;
-    const int trs = b24 ? 8 : 1;
-    const double zincflx = in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0;
-    double *pup = part + ((size_t)(col * SS_NSL + sl) * 2) * (klev + 1);   // upward partials [lev]
-    double *pdn = pup + (klev + 1);
-
-    // ---- up sweep
-    {
-        double rup = albp, rupd = albd;
-        zrup[0] = rup;
-        zrupd[0] = rupd;
-        double trn[SV_U], tgn[SV_U];
-#pragma unroll
-        for (int j = 0; j < SV_U; ++j) {
-            const int l = min(j, klev - 1);
-            trn[j] = __ldg(taur + l * trs) * raylg;
-            tgn[j] = __ldg(taug + (size_t)l * NGPTSW);
-        }
-        for (int l0 = 0; l0 < klev; l0 += SV_U) {
-            double tr[SV_U], tg[SV_U];
-#pragma unroll
-            for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
-            if (l0 + SV_U < klev) {
-#pragma unroll
-                for (int j = 0; j < SV_U; ++j) {
-                    const int l = min(l0 + SV_U + j, klev - 1);
-                    trn[j] = __ldg(taur + l * trs) * raylg;
-                    tgn[j] = __ldg(taug + (size_t)l * NGPTSW);
-                }
-            }
-            double ref[SV_U], refd[SV_U], tra[SV_U], trad[SV_U], dbt[SV_U];
-            bool cons[SV_U], anyc = false;
-#pragma unroll
-            for (int j = 0; j < SV_U; ++j) {
-                cons[j] = sw_reftra2(tb, bpade, prmu0, rmu0, tr[j], tg[j], ref[j], refd[j], tra[j], trad[j], dbt[j]);
-                anyc |= cons[j];
-            }
-            if (__any_sync(0xffffffffu, anyc)) {
-#pragma unroll
-                for (int j = 0; j < SV_U; ++j)
-                    if (cons[j]) {
-                        const SwLayer r = sw_reftra_fix(tb, bpade, prmu0, rmu0, tr[j], tg[j]);
-                        ref[j] = r.ref; refd[j] = r.refd; tra[j] = r.tra; trad[j] = r.trad; dbt[j] = r.dbt;
-                    }
-            }
-#pragma unroll
-            for (int j = 0; j < SV_U; ++j) {
-                const int l = l0 + j;
-                if (l < klev) {
-                    const double zreflect = rcp_fast(1. - rupd * refd[j]);
-                    const double rup_n = ref[j] + (trad[j] * ((tra[j] - dbt[j]) * rupd + dbt[j] * rup)) * zreflect;
-                    const double rupd_n = refd[j] + trad[j] * trad[j] * rupd * zreflect;
-                    rup = rup_n;
-                    rupd = rupd_n;
-                    zrup[l + 1] = rup;
-                    zrupd[l + 1] = rupd;
-                }
-            }
-        }
-    }
-
-    // ---- down sweep, two levels per iteration; level index s counted from the surface, k = klev - s
-    double ztdn = 1., zrdnd = 0., ztdbt = 1.;
-    double trn[SV_U], tgn[SV_U], run[SV_U], rudn[SV_U];
-#pragma unroll
-    for (int j = 0; j < SV_U; ++j) {
-        const int s = max(klev - j, 0);
-        const int l = max(s - 1, 0);
-        trn[j] = __ldg(taur + l * trs) * raylg;
-        tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
-        run[j] = zrup[s];
-        rudn[j] = zrupd[s];
-    }
-    for (int k0 = 0; k0 <= klev; k0 += SV_U) {
-        double tr[SV_U], tg[SV_U], ru[SV_U], rud[SV_U];
-#pragma unroll
-        for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; ru[j] = run[j]; rud[j] = rudn[j]; }
-        if (k0 + SV_U <= klev) {
-#pragma unroll
-            for (int j = 0; j < SV_U; ++j) {
-                const int s = max(klev - (k0 + SV_U + j), 0);
-                const int l = max(s - 1, 0);
-                trn[j] = __ldg(taur + l * trs) * raylg;
-                tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
-                run[j] = zrup[s];
-                rudn[j] = zrupd[s];
-            }
-        }
-        double ref[SV_U], refd[SV_U], tra[SV_U], trad[SV_U], dbt[SV_U];
-        bool cons[SV_U], anyc = false;
-#pragma unroll
-        for (int j = 0; j < SV_U; ++j) {
-            cons[j] = sw_reftra2(tb, bpade, prmu0, rmu0, tr[j], tg[j], ref[j], refd[j], tra[j], trad[j], dbt[j]);
-            anyc |= cons[j];
-        }
-        if (__any_sync(0xffffffffu, anyc)) {
-#pragma unroll
-            for (int j = 0; j < SV_U; ++j)
-                if (cons[j]) {
-                        const SwLayer r = sw_reftra_fix(tb, bpade, prmu0, rmu0, tr[j], tg[j]);
-                        ref[j] = r.ref; refd[j] = r.refd; tra[j] = r.tra; trad[j] = r.trad; dbt[j] = r.dbt;
-                    }
-        }
-#pragma unroll
-        for (int j = 0; j < SV_U; ++j) {
-            const int k = k0 + j;
-            if (k <= klev) {
-                const int s = klev - k;
-                const int slot = k & 3;
-                const double zreflect = rcp_fast(1. - zrdnd * rud[j]);
-                const double dif = ztdn - ztdbt;
-                const double pfu = (ztdbt * ru[j] + dif * rud[j]) * zreflect;
-                const double pfd = ztdbt + (dif + ztdbt * ru[j] * zrdnd) * zreflect;
-                if (act) {
-                    s_tile[(2 * slot) * SS_TS + lane] = zincflx * pfu;
-                    s_tile[(2 * slot + 1) * SS_TS + lane] = zincflx * pfd;
-                }
-                if (s > 0) {
-                    const double zr = rcp_fast(1. - refd[j] * zrdnd);
-                    const double ztdn_n = ztdbt * tra[j] + (trad[j] * (dif + ztdbt * ref[j] * zrdnd)) * zr;
-                    const double zrdnd_n = refd[j] + trad[j] * trad[j] * zrdnd * zr;
-                    ztdbt = dbt[j] * ztdbt;
-                    ztdn = ztdn_n;
-                    zrdnd = zrdnd_n;
-                }
-            }
-        }
-        const int klast = min(k0 + SV_U - 1, klev);
-        if ((klast & 3) == 3 || klast == klev) {
-            const double sum = sw_slice_reduce8(s_tile, lane);
-            // row = 2*slot + dir
-            const int row = lane >> 2;
-            const int kk = (klast & ~3) + (row >> 1);
-            if ((lane & 3) == 0 && kk <= klast) {
-                if (row & 1) pdn[klev - kk] = sum;
-                else pup[klev - kk] = sum;
-            }
-        }
-    }
-}
-
-// Sum of the slice partials, heating rates (rad.nomcica:686-727) and copy-out; night columns get zeros.
-constexpr int SF_COLS = 32;
-__global__ void __launch_bounds__(256) sw_flux_finish_kernel(SwIn in, SwOut out, SwWork w, const double *__restrict__ part)
-{
-    extern __shared__ double s_flux[];                         // [2][klev+1][SF_COLS+1]
-    const int klev = w.nlay, nlev = klev + 1;
-    const int c0 = blockIdx.x * SF_COLS;
-    const int ncb = min(SF_COLS, w.nc - c0);
-    double *s_up = s_flux, *s_dn = s_flux + (size_t)nlev * (SF_COLS + 1);
-    for (int i = threadIdx.x; i < ncb * nlev; i += blockDim.x) {
-        const int c = i / nlev, lev = i - c * nlev;
-        double dn = 0.0, up = 0.0;
-        if (!(in.coszen[c0 + c] < ZEPZEN)) {
-            const double *p = part + (size_t)(c0 + c) * SS_NSL * 2 * nlev + lev;
-#pragma unroll
-            for (int s = 0; s < SS_NSL; ++s) {
-                up += p[(size_t)(2 * s) * nlev];
-                dn += p[(size_t)(2 * s + 1) * nlev];
-            }
-        }
-        s_up[lev * (SF_COLS + 1) + c] = up;
-        s_dn[lev * (SF_COLS + 1) + c] = dn;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nlev * SF_COLS; i += blockDim.x) {
-        const int lev = i / SF_COLS, c = i - lev * SF_COLS;
-        if (c >= ncb) continue;
-        const int col = c0 + c;
-        const size_t o = col + (size_t)lev * out.ld;
-        const double u = s_up[lev * (SF_COLS + 1) + c], d = s_dn[lev * (SF_COLS + 1) + c];
-        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
-        if (lev < klev) {
-            double h = 0.0;
-            if (lev < klev - 1 && !(in.coszen[col] < ZEPZEN)) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
-                const double pdp = in.plev[col + (size_t)lev * in.ld] - in.plev[col + (size_t)(lev + 1) * in.ld];
-                const double u1 = s_up[(lev + 1) * (SF_COLS + 1) + c], d1 = s_dn[(lev + 1) * (SF_COLS + 1) + c];
-                h = ((d1 - u1) - (d - u)) * (c_ss.heatfac / pdp);
-            }
-            out.hr[o] = h;
-            out.hrc[o] = h;
-        }
-    }
-}
-
-static void launch_solver_slice(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
-{
-    const unsigned nblk = (unsigned)w.nc * SS_NSL;
-    // variant 1: 28 warps per SM (72 registers, a few spills); 2: 20 warps (96 registers); 3: 16 warps (128 registers)
-    const int v = g_tune.sw_solver_variant;
-    if (w.nlay <= 64) {
-        if (v == 3) sw_solver_slice_kernel<64, 16><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-        else if (v == 2) sw_solver_slice_kernel<64, 20><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-        else sw_solver_slice_kernel<64, 28><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-    } else {
-        if (v == 3) sw_solver_slice_kernel<MAXLAY, 16><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-        else if (v == 2) sw_solver_slice_kernel<MAXLAY, 20><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-        else sw_solver_slice_kernel<MAXLAY, 28><<<nblk, 32, 0, s>>>(t, in, w, w.part);
-    }
-    const size_t fsmem = (size_t)2 * (w.nlay + 1) * (SF_COLS + 1) * sizeof(double);
-    cudaFuncSetAttribute(sw_flux_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-    sw_flux_finish_kernel<<<(w.nc + SF_COLS - 1) / SF_COLS, 256, fsmem, s>>>(in, out, w, w.part);
+    const int v = g_tune.sw_solver_variant;       // 0 baseline; 7: OPT 1; 8: OPT 2; 9: OPT 3
+    if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
+    if (v == 7) launch<LMAX, false, 1>(t, in, out, w, s);
+    else if (v == 8) launch<LMAX, false, 2>(t, in, out, w, s);
+    else if (v == 9) launch<LMAX, false, 3>(t, in, out, w, s);
+    else launch<LMAX, false, 0>(t, in, out, w, s);
 }
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    if (g_tune.sw_solver_variant >= 1) { launch_solver_slice(t, in, out, w, s); return 2; }
-    const bool store = g_tune.sw_solver_store != 0;
-    if (w.nlay <= 64) {
-        if (store) launch<64, true>(t, in, out, w, s);
-        else launch<64, false>(t, in, out, w, s);
-    } else {
-        if (store) launch<MAXLAY, true>(t, in, out, w, s);
-        else launch<MAXLAY, false>(t, in, out, w, s);
-    }
+    if (w.nlay <= 64) launch_opt<64>(t, in, out, w, s);
+    else launch_opt<MAXLAY>(t, in, out, w, s);
     return 1;
 }
 
