@@ -685,7 +685,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 7};
+Tuning g_tune = {0, 0, 0, 1, 1};
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1069,6 +1069,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
+    if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_variant") { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_store") { g_tune.sw_solver_store = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }

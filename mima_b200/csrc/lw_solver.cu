@@ -35,6 +35,23 @@ int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb)
 constexpr int RT_THREADS = 160;   // 140 g-points -> 5 warps
 constexpr int RT_S = 141;         // tile row stride (odd)
 constexpr int RT_U = 4;           // levels per load group
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_WS = 34;         // row stride of the warp-local tile (upper half-warp shifted by one: conflict-free)
+
+// sum over the 32 lanes of each of the 8 rows of a warp-private tile; lanes 4r..4r+3 return the sum of row r
+__device__ __forceinline__ double warp_rows8(const double *tile, int lane)
+{
+    __syncwarp();
+    const int q = lane & 3;
+    const double *src = tile + (lane >> 2) * RT_WS + 17 * (q >> 1) + 8 * (q & 1);
+    double acc = src[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) acc += src[j];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    __syncwarp();
+    return acc;
+}
 
 // layer transmittance and Planck-weighted sources of one (g, layer) cell (:589-607)
 template <bool DOWN>
@@ -62,12 +79,17 @@ __device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double 
 
 // The Planck sources of the column ([lay][16] and [lev][16], 16 KB at 60 layers) are staged in shared memory
 // once per block: the 140 g-threads need them 2-3 times per level and they are shared by all g-points of a band.
-template <bool AER>
+// WR: warp-local g-sums -- every warp adds up its own 32 lanes per level (batches of 8 levels through a
+// 2 KB warp-private tile, no block barrier inside the sweeps) and the five warp partials of a level are
+// combined in a fixed order once at the end.
+template <bool AER, bool WR>
 __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
 {
-    __shared__ double s_tile[16 * RT_S];
-    __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
+    __shared__ double s_tile[WR ? RT_WARPS * 8 * RT_WS : 16 * RT_S];
+    __shared__ double s_part[WR ? RT_WARPS * 2 * (MAXLAY + 1) : 16 * (RT_THREADS / 16 + 1)];
     __shared__ double s_dn[MAXLAY + 1], s_up[MAXLAY + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *wt = s_tile + (WR ? wid * 8 * RT_WS + lane + (lane >> 4) : 0);
     extern __shared__ __align__(16) double s_planck[];          // pl[nlay][16] then pv[nlay+1][16]
     const int col = blockIdx.x;
     const int nlay = w.nlay;
@@ -129,18 +151,26 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
                 lw_layer<true>(et, bpade, secd, tg[j], fr[j], blay, pup - blay, pdn - blay, atrans, bbd, bbugas);
                 pup = pdn;
                 radld = radld + (bbd - radld) * atrans;
-                if (active) s_tile[(k & 15) * RT_S + g] = radld * wgt;
+                if (WR) wt[(k & 7) * RT_WS] = radld * wgt;
+                else if (active) s_tile[(k & 15) * RT_S + g] = radld * wgt;
                 if (k == nlay - 1) plfrac1 = fr[j];
             }
         }
         const int klast = min(k0 + RT_U, nlay) - 1;
-        if ((klast & 15) == 15 || klast == nlay - 1) {
+        if (WR) {
+            if ((klast & 7) == 7 || klast == nlay - 1) {
+                const double sum = warp_rows8(s_tile + wid * 8 * RT_WS, lane);
+                const int kk = (klast & ~7) + (lane >> 2);
+                if ((lane & 3) == 0 && kk <= klast) s_part[(wid * 2) * (MAXLAY + 1) + nlay - 1 - kk] = sum;
+            }
+        } else if ((klast & 15) == 15 || klast == nlay - 1) {
             const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
             const int kk = (klast & ~15) + threadIdx.x;
             if (threadIdx.x < 16 && kk <= klast) s_dn[nlay - 1 - kk] = sum * c_ls.fluxfac;
         }
     }
     if (threadIdx.x == 0) s_dn[nlay] = 0.0;   // no downward flux enters at the top (drad(nlayers) = 0)
+    if (WR && lane == 0) s_part[(wid * 2) * (MAXLAY + 1) + nlay] = 0.0;
 
     // ---- surface (:628-636) and upward sweep (:649-711); level k = 0 is the surface, level k > 0 the top
     //      of layer k (1-based).  Groups are aligned to the 16-level batches of the reduction.
@@ -174,24 +204,45 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
                 const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
                 const double reflect = 1. - semiss;
                 radlu = rad0 + reflect * radld;
-                if (active) s_tile[g] = radlu * wgt;
+                if (WR) wt[0] = radlu * wgt;
+                else if (active) s_tile[g] = radlu * wgt;
             } else if (full || k <= nlay) {
                 const int lay = k - 1;
                 const double blay = pl[lay * 16];
                 double atrans, bbd, bbugas;
                 lw_layer<false>(et, bpade, secd, tg[j], fr[j], blay, pv[(lay + 1) * 16] - blay, 0.0, atrans, bbd, bbugas);
                 radlu = radlu + (bbugas - radlu) * atrans;
-                if (active) s_tile[(k & 15) * RT_S + g] = radlu * wgt;
+                if (WR) wt[(k & 7) * RT_WS] = radlu * wgt;
+                else if (active) s_tile[(k & 15) * RT_S + g] = radlu * wgt;
             }
         }
         const int klast = min(k0 + RT_U - 1, nlay);
-        if ((klast & 15) == 15 || klast == nlay) {
+        if (WR) {
+            if ((klast & 7) == 7 || klast == nlay) {
+                const double sum = warp_rows8(s_tile + wid * 8 * RT_WS, lane);
+                const int kk = (klast & ~7) + (lane >> 2);
+                if ((lane & 3) == 0 && kk <= klast) s_part[(wid * 2 + 1) * (MAXLAY + 1) + kk] = sum;
+            }
+        } else if ((klast & 15) == 15 || klast == nlay) {
             const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
             const int kk = (klast & ~15) + threadIdx.x;
             if (threadIdx.x < 16 && kk <= klast) s_up[kk] = sum * c_ls.fluxfac;
         }
     }
     __syncthreads();
+    if (WR) {
+        for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
+            double d = 0.0, u = 0.0;
+#pragma unroll
+            for (int i = 0; i < RT_WARPS; ++i) {
+                d += s_part[(i * 2) * (MAXLAY + 1) + lev];
+                u += s_part[(i * 2 + 1) * (MAXLAY + 1) + lev];
+            }
+            s_dn[lev] = d * c_ls.fluxfac;
+            s_up[lev] = u * c_ls.fluxfac;
+        }
+        __syncthreads();
+    }
 
     // ---- fluxes and heating rates (:751-777), copy-out (rad.nomcica:546-555)
     for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
@@ -211,14 +262,15 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
 
 int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
+    // variant 1 (default): warp-local g-sums; 0: block-level g-sums (two barriers per 16 levels)
+    const bool wr = g_tune.lw_rtrn_variant != 0;
     const size_t smem = (size_t)(2 * w.nlay + 1) * 16 * sizeof(double) + (size_t)g_tune.lw_rtrn_pad_kb * 1024;
-    if (in.tauaer) {
-        cudaFuncSetAttribute(lw_rtrn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lw_rtrn_kernel<true><<<w.nc, RT_THREADS, smem, s>>>(t, in, out, w);
-    } else {
-        cudaFuncSetAttribute(lw_rtrn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lw_rtrn_kernel<false><<<w.nc, RT_THREADS, smem, s>>>(t, in, out, w);
-    }
+#define RT_LAUNCH(A, W) do { \
+        cudaFuncSetAttribute(lw_rtrn_kernel<A, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        lw_rtrn_kernel<A, W><<<w.nc, RT_THREADS, smem, s>>>(t, in, out, w); } while (0)
+    if (in.tauaer) { if (wr) RT_LAUNCH(true, true); else RT_LAUNCH(true, false); }
+    else { if (wr) RT_LAUNCH(false, true); else RT_LAUNCH(false, false); }
+#undef RT_LAUNCH
     return 1;
 }
 

@@ -51,8 +51,11 @@ constexpr double ZEPZEN = 1.e-10;
 constexpr int SV_COLS = 2;                      // columns per block: 2 x 112 g-points = 7 full warps
 constexpr int SV_THREADS = SV_COLS * NGPTSW;    // 224
 constexpr int SV_S = 113;                       // tile row stride (odd)
-constexpr int SV_R = 32;                        // tile rows: 8 levels x {up, down} x 2 columns
+
 constexpr int SV_U = 2;                         // layers per load group
+constexpr int SV_WARPS = SV_THREADS / 32;       // 7
+constexpr int SV_WS = 34;                       // row stride of the warp-local tile
+constexpr int SV_HPC = NGPTSW / 16;             // half-warps per column: 7
 
 // exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
 __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
@@ -143,16 +146,22 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
     }
 }
 
-// OPT bit 0: one-Newton reciprocals outside the table-index paths; bit 1: g-sum in batches of 4 levels (half the tile)
+// OPT bit 0: one-Newton reciprocals outside the table-index paths; bit 1: block-level g-sum in batches of 4 levels;
+// bit 2: warp-local g-sums (no block barrier inside the sweep)
 template <int LMAX, bool STORE, int OPT>
 __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
 {
     constexpr bool R1 = (OPT & 1) != 0;
-    constexpr int NB = (OPT & 2) ? 4 : 8;          // levels per reduction batch
-    constexpr int NR = NB * 2 * SV_COLS;           // tile rows
-    __shared__ double s_tile[NR * SV_S];
-    __shared__ double s_part[NR * (SV_THREADS / NR + 1)];
+    constexpr bool WR = (OPT & 4) != 0;            // warp-local g-sums (no block barrier inside the sweep)
+    constexpr int NB = (WR || (OPT & 2)) ? 4 : 8;  // levels per reduction batch
+    constexpr int NR = NB * 2 * SV_COLS;           // tile rows (block-level reduction)
+    __shared__ double s_tile[WR ? SV_WARPS * 8 * SV_WS : NR * SV_S];
+    __shared__ double s_part[WR ? SV_COLS * SV_HPC * 2 * (LMAX + 1) : NR * (SV_THREADS / NR + 1)];
     __shared__ double s_up[SV_COLS][LMAX + 1], s_dn[SV_COLS][LMAX + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // warp-local layout: row = 2*slot + dir, 34 doubles per row, the upper half-warp shifted by one slot so that
+    // the four lanes that add up one row (two per half-warp) hit distinct banks
+    double *wt = s_tile + (WR ? wid * 8 * SV_WS + lane + (lane >> 4) : 0);
     const int klev = w.nlay;
     const int cb = threadIdx.x / NGPTSW;           // column of the block this thread works on
     const int g = threadIdx.x - cb * NGPTSW;
@@ -247,8 +256,13 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
             const double dif = ztdn - ztdbt;
             const double pfu = (ztdbt * ru + dif * rud) * zreflect;
             const double pfd = ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect;
-            s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = zincflx * pfu;
-            s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = zincflx * pfd;
+            if (WR) {
+                wt[(2 * slot) * SV_WS] = zincflx * pfu;
+                wt[(2 * slot + 1) * SV_WS] = zincflx * pfd;
+            } else {
+                s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = zincflx * pfu;
+                s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = zincflx * pfd;
+            }
             if (s > 0) {
                 const int l = s - 1;
                 double ref, refd, tra, trad, dbt;
@@ -264,11 +278,33 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                 ztdn = ztdn_n;
                 zrdnd = zrdnd_n;
             }
+        } else if (WR) {
+            wt[(2 * slot) * SV_WS] = 0.0;
+            wt[(2 * slot + 1) * SV_WS] = 0.0;
         } else {
             s_tile[((2 * slot) * SV_COLS + cb) * SV_S + g] = 0.0;
             s_tile[((2 * slot + 1) * SV_COLS + cb) * SV_S + g] = 0.0;
         }
-        if (slot == NB - 1 || k == klev) {
+        if (WR) {
+            if (slot == NB - 1 || k == klev) {
+                // lanes 4r..4r+3 add up row r: two lanes per half-warp, eight values each, then one exchange;
+                // a half-warp never mixes columns (112 = 7 half-warps), so half-warp sums are the unit kept
+                __syncwarp();
+                const int row = lane >> 2, q = lane & 3, half = q >> 1;
+                const double *src = s_tile + (wid * 8 + row) * SV_WS + 17 * half + 8 * (q & 1);
+                double acc = src[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) acc += src[j];
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                const int kk = (k & ~3) + (row >> 1);
+                if ((q & 1) == 0 && kk <= k) {
+                    const int hw = 2 * wid + half;                   // half-warp of the block: 0..13
+                    const int c = hw / SV_HPC, i = hw - c * SV_HPC;
+                    s_part[((c * SV_HPC + i) * 2 + (row & 1)) * (LMAX + 1) + (klev - kk)] = acc;
+                }
+                __syncwarp();
+            }
+        } else if (slot == NB - 1 || k == klev) {
             const double sum = tile_reduce<SV_THREADS, NR, NGPTSW, SV_S>(s_tile, s_part);
             if (threadIdx.x < NR) {
                 // row = ((2*slot + dir) * SV_COLS + column)
@@ -282,6 +318,19 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
         }
     }
     __syncthreads();
+    if (WR) {
+        for (int lev = g; lev <= klev; lev += NGPTSW) {
+            double u = 0.0, d = 0.0;
+#pragma unroll
+            for (int i = 0; i < SV_HPC; ++i) {
+                u += s_part[((cb * SV_HPC + i) * 2) * (LMAX + 1) + lev];
+                d += s_part[((cb * SV_HPC + i) * 2 + 1) * (LMAX + 1) + lev];
+            }
+            s_up[cb][lev] = u;
+            s_dn[cb][lev] = d;
+        }
+        __syncthreads();
+    }
     if (incol) {
         for (int lev = g; lev <= klev; lev += NGPTSW) {
             const double u = s_up[cb][lev], d = s_dn[cb][lev];
@@ -311,12 +360,10 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
 template <int LMAX>
 static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    const int v = g_tune.sw_solver_variant;       // 0 baseline; 7: OPT 1; 8: OPT 2; 9: OPT 3
+    // variant 1 (default): one-Newton reciprocals + warp-local g-sums (OPT 5); 0: the first version of the kernel (OPT 0)
     if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
-    if (v == 7) launch<LMAX, false, 1>(t, in, out, w, s);
-    else if (v == 8) launch<LMAX, false, 2>(t, in, out, w, s);
-    else if (v == 9) launch<LMAX, false, 3>(t, in, out, w, s);
-    else launch<LMAX, false, 0>(t, in, out, w, s);
+    if (g_tune.sw_solver_variant == 0) launch<LMAX, false, 0>(t, in, out, w, s);
+    else launch<LMAX, false, 5>(t, in, out, w, s);
 }
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
