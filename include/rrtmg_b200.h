@@ -172,6 +172,72 @@ int rrtmg_b200_set_option(const char *key, long value);
  * lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver (arrays of 6). */
 int rrtmg_b200_kernel_times(double *ms, long *launches, int reset);
 
+/* ---- the radiation driver around the two calls ------------------
+ * Device-side replacement of the marshaling MiMA's run_rrtmg does on the host
+ * (src/atmos_param/rrtm_radiation/rrtm_radiation.f90:585-808), of interp_temp (:422-461) and of
+ * compute_zenith (src/atmos_param/rrtm_radiation/astro.f90:59-248).  The Fortran shim calls
+ * rrtmg_b200_run_rrtmg from run_rrtmg once the alarm has decided that this is a radiation step; the alarm,
+ * the netCDF interpolators and the diag manager stay in the model (FMS control plane).
+ *
+ * Fields are FMS-ordered (lon, lat, lev), column-major, level 1 = top, pressures in Pa -- exactly the dummy
+ * arguments of run_rrtmg (:471).  The struct mirrors the entries of rrtm_radiation_nml (:104-197) and
+ * astro_nml (astro.f90:24-33) that this part of run_rrtmg reads; rrtmg_b200_rad_config_default() sets the
+ * Fortran defaults. */
+typedef struct rrtmg_b200_rad_config {
+    int include_secondary_gases;   /* pass ch4_val..ccl4_val instead of zeros (:679-712, 721-748) */
+    int do_fixed_water;            /* :638-646 */
+    int do_zm_tracers;             /* feed the zonal mean of q (:622-626) */
+    int do_rad_time_avg;           /* average cos(zenith) over dt_rad_avg (:562-566) */
+    int dt_rad_avg;                /* seconds; already resolved as in rrtm_radiation_init :336-340 */
+    int lonstep;                   /* sub-sample longitudes (:163, :652) */
+    int do_zm_rad;                 /* zonal-mean heating and surface fluxes (:768-769, :800-802) */
+    int use_dyofyr;                /* astro_nml: let RRTMG compute the Earth-Sun distance from the day of year */
+    int solday;                    /* astro_nml: perpetual day if > 0 */
+    int days_per_year;             /* length_of_year() of the model calendar (360 for MiMA's thirty_day_months) */
+    double scale_ozone, o3_val;
+    double ch4_val, n2o_val, o2_val, cfc11_val, cfc12_val, cfc22_val, ccl4_val;
+    double h2o_lower_limit, temp_lower_limit, temp_upper_limit;
+    double co2ppmv;
+    double fixed_water, fixed_water_pres, fixed_water_lat;
+    double slowdown_rad;
+    double obliq, solr_cnst, solrad, equinox_day;   /* astro_nml */
+} rrtmg_b200_rad_config;
+
+void rrtmg_b200_rad_config_default(rrtmg_b200_rad_config *cfg);
+
+/* compute_zenith(Time, equinox_day, dt, lat, lon, cosz, dyofyr): Time as (seconds, days) of get_time();
+ * lat, lon, cosz (n) host arrays in radians; dt = 0 instantaneous, 0 < dt < 86400 average over dt seconds,
+ * dt >= 86400 daily mean. */
+int rrtmg_b200_compute_zenith(const rrtmg_b200_rad_config *cfg, int seconds, int days, int dt, int n,
+                              const double *lat, const double *lon, double *cosz, int *dyofyr);
+
+/* interp_temp(z_full, z_half, t_surf_rad, t): t_half (si, sj, sk+1), host arrays. */
+int rrtmg_b200_interp_temp(int si, int sj, int sk, const double *z_full, const double *z_half,
+                           const double *t_surf_rad, const double *t, double *t_half);
+
+/* The radiation step of run_rrtmg.  (seconds, days) = get_time(Time).
+ *   in : lat, lon, albedo, t_surf_rad (si, sj); p_full, q, t (si, sj, sk); p_half (si, sj, sk+1);
+ *        either t_half_in (si, sj, sk+1) or z_full (si, sj, sk) + z_half (si, sj, sk+1) for interp_temp;
+ *        o3f (si, sj, sk) = the ozone field of the interpolator (do_read_ozone) or NULL for o3_val.
+ *   inout: tdt (si, sj, sk) [K/s] += radiative heating.
+ *   out: coszen (si, sj); any of flux_sw, flux_lw, tdt_rad, tdt_sw, tdt_lw, olr, isr, t_half_out may be NULL.
+ * Host pointers; the *_device variant takes device pointers and a stream and is asynchronous. */
+int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int sk, int seconds, int days,
+                         const double *lat, const double *lon, const double *p_full, const double *p_half,
+                         const double *albedo, const double *q, const double *t, const double *t_surf_rad,
+                         const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
+                         double *tdt, double *coszen, double *flux_sw, double *flux_lw,
+                         double *tdt_rad, double *tdt_sw, double *tdt_lw, double *olr, double *isr,
+                         double *t_half_out);
+int rrtmg_b200_run_rrtmg_device(const rrtmg_b200_rad_config *cfg, int si, int sj, int sk, int seconds, int days,
+                                const double *lat, const double *lon, const double *p_full, const double *p_half,
+                                const double *albedo, const double *q, const double *t, const double *t_surf_rad,
+                                const double *z_full, const double *z_half, const double *t_half_in,
+                                const double *o3f,
+                                double *tdt, double *coszen, double *flux_sw, double *flux_lw,
+                                double *tdt_rad, double *tdt_sw, double *tdt_lw, double *olr, double *isr,
+                                double *t_half_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,3 +216,40 @@ def make_columns(resolution: str = "T42L40", *, seed: int = 20240917, co2_ppmv: 
         albedo=np.concatenate([c["alb"] for c in cols]),
         coszen=np.concatenate([c["cz"] for c in cols]),
     )
+
+
+def make_gcm_state(resolution: str = "T42L40", **kw) -> dict:
+    """The same synthetic atmosphere as make_columns(), in the layout MiMA's run_rrtmg receives
+    (rrtm_radiation.f90:471-503): fields (lon, lat, lev) with level 1 = top, pressures in Pa, p_half(top) = 0,
+    lat/lon in radians, plus geopotential heights for interp_temp (hydrostatic, z_half(k=1) = 0 as in the
+    model, rrtm_radiation.f90:433) and a zero tendency array."""
+    c = make_columns(resolution, **kw)
+    si, sj, sk = c.nlon, c.nlat, c.nlay
+
+    def fms(a):          # (ncol, n) surface-first -> (lon, lat, n) top-first
+        return np.asfortranarray(a.reshape((si, sj, a.shape[1]), order="F")[:, :, ::-1])
+
+    p_full = fms(c.play) * 100.0
+    p_half = fms(c.plev) * 100.0
+    p_half[:, :, 0] = 0.0
+    t = fms(c.tlay)
+    q = fms(c.h2o)
+    o3f = fms(c.o3)
+    t_surf = np.asfortranarray(c.tsfc.reshape((si, sj), order="F"))
+    albedo = np.asfortranarray(c.albedo.reshape((si, sj), order="F"))
+    nlat_full = RESOLUTIONS.get(resolution, (si, sj, sk))[1] if "nlat" not in kw else sj
+    lat1 = np.arcsin(np.linspace(-1.0 + 1.0 / nlat_full, 1.0 - 1.0 / nlat_full, nlat_full))
+    j0 = kw.get("lat_rows", (0, sj))[0]
+    lat = np.asfortranarray(np.broadcast_to(lat1[j0:j0 + sj][None, :], (si, sj)))
+    lon = np.asfortranarray(np.broadcast_to((np.arange(si) * (2.0 * np.pi / si))[:, None], (si, sj)))
+    rd_g = 287.04 / 9.80
+    z_half = np.zeros((si, sj, sk + 1), order="F")
+    z_full = np.zeros((si, sj, sk), order="F")
+    for k in range(sk - 1, -1, -1):          # integrate upwards from the surface
+        pb = p_half[:, :, k + 1]
+        z_full[:, :, k] = z_half[:, :, k + 1] + rd_g * t[:, :, k] * np.log(pb / p_full[:, :, k])
+        if k > 0:
+            z_half[:, :, k] = z_half[:, :, k + 1] + rd_g * t[:, :, k] * np.log(pb / p_half[:, :, k])
+    z_half[:, :, 0] = 0.0
+    return dict(si=si, sj=sj, sk=sk, lat=lat, lon=lon, p_full=p_full, p_half=p_half, t=t, q=q, o3f=o3f,
+                t_surf=t_surf, albedo=albedo, z_full=z_full, z_half=z_half, tdt=np.zeros((si, sj, sk), order="F"))

@@ -700,6 +700,147 @@ void ktimer_end(cudaStream_t s)
 }
 } // namespace rrtmg
 
+// ------------------------------------------------------------------------------------------------
+// radiation driver (run_rrtmg on the device)
+namespace {
+struct DrvState {
+    DevBuf in, out, gas, misc, host_in, host_out;
+    size_t gas_n = 0;
+    double gas_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool gas_set = false;
+    cudaStream_t st = nullptr;
+} D;
+
+struct ZenithHost { ZenithArgs a; int dyofyr; int sec_l, day_l; };
+
+// scalar part of compute_zenith (astro.f90:95-127) and Time_loc of run_rrtmg (rrtm_radiation.f90:550-558)
+ZenithHost zenith_scalars(const rrtmg_b200_rad_config &c, int seconds, int days, int dt)
+{
+    const double PI = 3.14159265358979323846;
+    ZenithHost z;
+    const double deg2rad = PI / 180.;
+    const int daysperyear = c.days_per_year;
+    const double radpersec = 2 * PI / 86400.;
+    const double radperday = 2 * PI / daysperyear;
+    z.a.radpersec = radpersec;
+    z.a.radsec = seconds * radpersec;
+    z.a.dt_pi = dt * radpersec;
+    z.a.dt = dt;
+    int d = days - (int)(c.equinox_day * daysperyear);
+    int dy = d % daysperyear;
+    if (dy < 0) dy += daysperyear;                    // modulo
+    z.dyofyr = dy;
+    const double radday = dy * radperday;
+    z.a.dec_sin = std::sin(c.obliq * deg2rad) * std::sin(radday);
+    const double dec = std::asin(z.a.dec_sin);
+    z.a.dec_cos = std::cos(dec);
+    z.a.dec_tan = std::tan(dec);
+    return z;
+}
+void local_time(const rrtmg_b200_rad_config &c, int seconds, int days, int &sec_l, int &day_l)
+{
+    sec_l = seconds; day_l = days;
+    if (c.solday > 0) { day_l = c.solday; return; }
+    if (c.slowdown_rad != 1.0) {
+        long long tot = (long long)days * 86400 + seconds;
+        tot = (long long)((double)tot * c.slowdown_rad);          // int(seconds*slowdown_rad)
+        sec_l = (int)(tot % 86400);
+        day_l = (int)(tot / 86400);
+    }
+}
+
+int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk, int seconds, int days,
+                          const double *lat, const double *lon, const double *p_full, const double *p_half,
+                          const double *albedo, const double *q, const double *t, const double *t_surf,
+                          const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
+                          double *tdt, double *coszen, double *flux_sw, double *flux_lw, double *tdt_rad,
+                          double *tdt_sw, double *tdt_lw, double *olr, double *isr, double *t_half_out,
+                          cudaStream_t st)
+{
+    if (!G.lw_ready || !G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "run_rrtmg: rrtmg_b200_lw_init / sw_init have not been called");
+    if (si < 1 || sj < 1 || sk < 2 || sk > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: grid extents out of range");
+    if (c.lonstep < 1 || si % c.lonstep != 0) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: lonstep must divide the number of longitudes");
+    if (c.days_per_year < 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: days_per_year must be positive");
+    if (!lat || !lon || !p_full || !p_half || !albedo || !q || !t || !t_surf || !coszen)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: required array is NULL");
+    if (!t_half_in && (!z_full || !z_half)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: need t_half or z_full + z_half");
+    RadGeom g{si, sj, sk, c.lonstep, si / c.lonstep, (si / c.lonstep) * sj};
+    const size_t np = (size_t)si * sj, L = sk, V = sk + 1, nc = g.ncols;
+    auto pad = [](size_t n) { return (n * 8 + 255) & ~(size_t)255; };
+    // packed RRTMG inputs + t_half + zonal-mean scratch
+    const size_t in_bytes = 4 * pad(nc * L) + 2 * pad(nc * V) + 3 * pad(nc) + pad(np * V) + pad((size_t)sj * sk + 2 * sj) + pad(sj * L) + 256;
+    const size_t out_bytes = 4 * pad(nc * V) + 2 * pad(nc * L) + 4 * pad(nc * V) + 2 * pad(nc * L);
+    if (D.in.ensure(in_bytes) || D.out.ensure(out_bytes)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg buffers)");
+    Carver ci(D.in.p), co(D.out.p);
+    double *pfull = ci.take<double>(nc * L), *tfull = ci.take<double>(nc * L), *h2o = ci.take<double>(nc * L), *o3 = ci.take<double>(nc * L);
+    double *phalf = ci.take<double>(nc * V), *thalf = ci.take<double>(nc * V);
+    double *cosz_rr = ci.take<double>(nc), *albedo_rr = ci.take<double>(nc), *tsrf = ci.take<double>(nc);
+    double *t_half_buf = ci.take<double>(np * V);
+    double *zm_buf = ci.take<double>((size_t)sj * sk + 2 * sj);
+    double *qzm_buf = ci.take<double>((size_t)sj * L);
+    int *flag = ci.take<int>(1);
+    double *swuflx = co.take<double>(nc * V), *swdflx = co.take<double>(nc * V), *swuflxc = co.take<double>(nc * V), *swdflxc = co.take<double>(nc * V);
+    double *swhr = co.take<double>(nc * L), *swhrc = co.take<double>(nc * L);
+    double *uflx = co.take<double>(nc * V), *dflx = co.take<double>(nc * V), *uflxc = co.take<double>(nc * V), *dflxc = co.take<double>(nc * V);
+    double *hr = co.take<double>(nc * L), *hrc = co.take<double>(nc * L);
+    // constant gas arrays: co2, and the seven secondary gases when requested (RR/rrtm_radiation.f90:360, 679-748)
+    const double gv[8] = {c.co2ppmv * 1.e-6, c.ch4_val, c.n2o_val, c.o2_val, c.cfc11_val, c.cfc12_val, c.cfc22_val, c.ccl4_val};
+    const int ngas = c.include_secondary_gases ? 8 : 1;
+    bool refill = !D.gas_set || D.gas_n != nc * L;
+    for (int i = 0; i < 8; ++i) refill = refill || D.gas_val[i] != gv[i];
+    if (D.gas.ensure(8 * pad(nc * L))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (gas arrays)");
+    Carver cg(D.gas.p);
+    double *gas[8];
+    for (int i = 0; i < 8; ++i) gas[i] = cg.take<double>(nc * L);
+    if (refill) {
+        for (int i = 0; i < 8; ++i) { G.launches += drv_fill(gas[i], nc * L, gv[i], st); D.gas_val[i] = gv[i]; }
+        D.gas_n = nc * L; D.gas_set = true;
+    }
+    // Time_loc, zenith angle (also an output)
+    int sec_l, day_l;
+    local_time(c, seconds, days, sec_l, day_l);
+    const int dt = c.do_rad_time_avg ? c.dt_rad_avg : 0;
+    ZenithHost z = zenith_scalars(c, sec_l, day_l, dt);
+    G.launches += drv_zenith((int)np, lat, lon, coszen, z.a, st);
+    const int dyofyr = c.use_dyofyr ? z.dyofyr : 0;                                    // :592
+    const double *t_half = t_half_in;
+    if (!t_half) {
+        double *dst = t_half_out ? t_half_out : t_half_buf;
+        G.launches += drv_interp_temp((int)np, sk, z_full, z_half, t_surf, t, dst, st);
+        t_half = dst;
+    } else if (t_half_out && t_half_out != t_half_in) {
+        CUDA_OK(cudaMemcpyAsync(t_half_out, t_half_in, np * V * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    PackArgs pa{};
+    pa.p_full = p_full; pa.p_half = p_half; pa.t = t; pa.t_half = t_half; pa.q = q; pa.o3f = o3f; pa.coszen = coszen;
+    pa.albedo = albedo; pa.t_surf = t_surf; pa.lat = lat; pa.qzm = nullptr; pa.top_flag = nullptr;
+    pa.pfull = pfull; pa.phalf = phalf; pa.tfull = tfull; pa.thalf = thalf; pa.h2o = h2o; pa.o3 = o3;
+    pa.cosz_rr = cosz_rr; pa.albedo_rr = albedo_rr; pa.tsrf = tsrf;
+    pa.qmin = c.h2o_lower_limit; pa.tmin = c.temp_lower_limit; pa.tmax = c.temp_upper_limit;
+    pa.scale_ozone = c.scale_ozone; pa.o3_val = c.o3_val;
+    pa.do_fixed_water = c.do_fixed_water; pa.fixed_water = c.fixed_water; pa.fixed_water_pres = c.fixed_water_pres;
+    pa.fixed_water_lat = c.fixed_water_lat;
+    G.launches += drv_pack(g, pa, c.do_zm_tracers ? qzm_buf : nullptr, flag, st);
+    // the two RRTMG calls with MiMA's fixed switches (icld = iaer = idrv = 0, emis = 1, tauaer = 0)
+    int icld = 0, iaer = 0;
+    SwIn sin{(int)nc, pfull, phalf, tfull, thalf, tsrf, h2o, o3, gas[0],
+             ngas > 1 ? gas[1] : nullptr, ngas > 1 ? gas[2] : nullptr, ngas > 1 ? gas[3] : nullptr,
+             albedo_rr, albedo_rr, albedo_rr, albedo_rr, cosz_rr, sw_adjflux(c.solrad, dyofyr, c.solr_cnst)};
+    SwOut sout{(int)nc, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
+    if (const int rc = sw_device_impl((int)nc, sk, &icld, &iaer, sin, sout, st)) return rc;
+    LwIn lin{(int)nc, pfull, phalf, tfull, thalf, tsrf, h2o, o3, gas[0],
+             ngas > 1 ? gas[1] : nullptr, ngas > 1 ? gas[2] : nullptr, ngas > 1 ? gas[3] : nullptr,
+             ngas > 1 ? gas[4] : nullptr, ngas > 1 ? gas[5] : nullptr, ngas > 1 ? gas[6] : nullptr, ngas > 1 ? gas[7] : nullptr,
+             nullptr, nullptr};
+    LwOut lout{(int)nc, uflx, dflx, hr, uflxc, dflxc, hrc};
+    if (const int rc = lw_device_impl((int)nc, sk, &icld, 0, lin, lout, st)) return rc;
+    UnpackArgs ua{swhr, swuflx, swdflx, hr, uflx, dflx, tdt, tdt_rad, tdt_sw, tdt_lw, flux_sw, flux_lw, olr, isr};
+    G.launches += drv_unpack(g, ua, c.do_zm_rad ? zm_buf : nullptr, st);
+    CUDA_OK(cudaGetLastError());
+    return RRTMG_B200_OK;
+}
+} // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -801,6 +942,9 @@ int rrtmg_b200_finalize(void)
         b->release();
     P_lw.release();
     P_sw.release();
+    for (DevBuf *b : {&D.in, &D.out, &D.gas, &D.misc, &D.host_in, &D.host_out}) b->release();
+    D.gas_set = false;
+    if (D.st) { cudaStreamDestroy(D.st); D.st = nullptr; }
     G.lw_ready = G.sw_ready = false;
     G.lw_last_ncol = G.sw_last_ncol = 0;
     G.reduced.clear();
@@ -1060,6 +1204,126 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity)
     if (n < 0) return -1;
     if (out && capacity >= n) std::memcpy(out, h.data(), (size_t)n * 8);
     return n;
+}
+
+void rrtmg_b200_rad_config_default(rrtmg_b200_rad_config *c)
+{
+    if (!c) return;
+    std::memset(c, 0, sizeof *c);
+    c->do_rad_time_avg = 1; c->dt_rad_avg = 86400; c->lonstep = 1; c->days_per_year = 360;
+    c->scale_ozone = 1.0;
+    c->h2o_lower_limit = 2.e-7; c->temp_lower_limit = 100.; c->temp_upper_limit = 370.;
+    c->co2ppmv = 300.;
+    c->fixed_water = 2.e-06; c->fixed_water_pres = 100.e02; c->fixed_water_lat = 90.;
+    c->slowdown_rad = 1.0;
+    c->obliq = 23.439; c->solr_cnst = 1368.22; c->solrad = 1.0; c->equinox_day = 0.25;
+}
+
+int rrtmg_b200_compute_zenith(const rrtmg_b200_rad_config *cfg, int seconds, int days, int dt, int n,
+                              const double *lat, const double *lon, double *cosz, int *dyofyr)
+{
+    if (!cfg || !lat || !lon || !cosz || n < 0) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "compute_zenith: bad argument");
+    if (cfg->days_per_year < 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "compute_zenith: days_per_year must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(RRTMG_B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    const ZenithHost z = zenith_scalars(*cfg, seconds, days, dt);
+    if (dyofyr) *dyofyr = z.dyofyr;
+    if (n == 0) return RRTMG_B200_OK;
+    if (D.misc.ensure((size_t)n * 24)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (compute_zenith)");
+    double *d = (double *)D.misc.p;
+    CUDA_OK(cudaMemcpy(d, lat, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d + n, lon, (size_t)n * 8, cudaMemcpyHostToDevice));
+    G.launches += drv_zenith(n, d, d + n, d + 2 * (size_t)n, z.a, nullptr);
+    CUDA_OK(cudaMemcpy(cosz, d + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_interp_temp(int si, int sj, int sk, const double *z_full, const double *z_half,
+                           const double *t_surf_rad, const double *t, double *t_half)
+{
+    if (si < 1 || sj < 1 || sk < 2 || !z_full || !z_half || !t_surf_rad || !t || !t_half)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "interp_temp: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(RRTMG_B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    const size_t np = (size_t)si * sj, L = sk, V = sk + 1;
+    if (D.misc.ensure((2 * np * L + 2 * np * V + np) * 8)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (interp_temp)");
+    double *zf = (double *)D.misc.p, *zh = zf + np * L, *tt = zh + np * V, *ts = tt + np * L, *th = ts + np;
+    CUDA_OK(cudaMemcpy(zf, z_full, np * L * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(zh, z_half, np * V * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(tt, t, np * L * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ts, t_surf_rad, np * 8, cudaMemcpyHostToDevice));
+    G.launches += drv_interp_temp((int)np, sk, zf, zh, ts, tt, th, nullptr);
+    CUDA_OK(cudaMemcpy(t_half, th, np * V * 8, cudaMemcpyDeviceToHost));
+    return RRTMG_B200_OK;
+}
+
+int rrtmg_b200_run_rrtmg_device(const rrtmg_b200_rad_config *cfg, int si, int sj, int sk, int seconds, int days,
+                                const double *lat, const double *lon, const double *p_full, const double *p_half,
+                                const double *albedo, const double *q, const double *t, const double *t_surf_rad,
+                                const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
+                                double *tdt, double *coszen, double *flux_sw, double *flux_lw,
+                                double *tdt_rad, double *tdt_sw, double *tdt_lw, double *olr, double *isr,
+                                double *t_half_out, void *stream)
+{
+    if (!cfg) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: config is NULL");
+    return run_rrtmg_device_impl(*cfg, si, sj, sk, seconds, days, lat, lon, p_full, p_half, albedo, q, t, t_surf_rad,
+                                 z_full, z_half, t_half_in, o3f, tdt, coszen, flux_sw, flux_lw, tdt_rad, tdt_sw, tdt_lw,
+                                 olr, isr, t_half_out, (cudaStream_t)stream);
+}
+
+int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int sk, int seconds, int days,
+                         const double *lat, const double *lon, const double *p_full, const double *p_half,
+                         const double *albedo, const double *q, const double *t, const double *t_surf_rad,
+                         const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
+                         double *tdt, double *coszen, double *flux_sw, double *flux_lw,
+                         double *tdt_rad, double *tdt_sw, double *tdt_lw, double *olr, double *isr,
+                         double *t_half_out)
+{
+    if (!cfg) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: config is NULL");
+    if (si < 1 || sj < 1 || sk < 2) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: grid extents out of range");
+    if (!lat || !lon || !p_full || !p_half || !albedo || !q || !t || !t_surf_rad || !coszen)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: required array is NULL");
+    if (!D.st && cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
+    cudaStream_t st = D.st;
+    const size_t np = (size_t)si * sj, L = sk, V = sk + 1;
+    auto pad = [](size_t n) { return (n * 8 + 255) & ~(size_t)255; };
+    const size_t hin = 5 * pad(np) + 6 * pad(np * L) + 3 * pad(np * V);
+    const size_t hout = 5 * pad(np) + 4 * pad(np * L) + pad(np * V);
+    if (D.host_in.ensure(hin) || D.host_out.ensure(hout)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg host staging)");
+    Carver ci(D.host_in.p), co(D.host_out.p);
+    bool ok = true;
+    auto up = [&](const double *h, size_t n) -> double * {
+        if (!h) return nullptr;
+        double *d = ci.take<double>(n);
+        if (cudaMemcpyAsync(d, h, n * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        return d;
+    };
+    const double *d_lat = up(lat, np), *d_lon = up(lon, np), *d_alb = up(albedo, np), *d_ts = up(t_surf_rad, np);
+    const double *d_pf = up(p_full, np * L), *d_ph = up(p_half, np * V), *d_q = up(q, np * L), *d_t = up(t, np * L);
+    const double *d_zf = t_half_in ? nullptr : up(z_full, np * L), *d_zh = t_half_in ? nullptr : up(z_half, np * V);
+    const double *d_th = up(t_half_in, np * V), *d_o3 = up(o3f, np * L);
+    double *d_tdt = tdt ? ci.take<double>(np * L) : nullptr;
+    if (tdt && cudaMemcpyAsync(d_tdt, tdt, np * L * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+    if (!ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (run_rrtmg)");
+    double *d_cz = co.take<double>(np);
+    double *d_fsw = flux_sw ? co.take<double>(np) : nullptr, *d_flw = flux_lw ? co.take<double>(np) : nullptr;
+    double *d_olr = olr ? co.take<double>(np) : nullptr, *d_isr = isr ? co.take<double>(np) : nullptr;
+    double *d_trad = tdt_rad ? co.take<double>(np * L) : nullptr, *d_tsw = tdt_sw ? co.take<double>(np * L) : nullptr;
+    double *d_tlw = tdt_lw ? co.take<double>(np * L) : nullptr;
+    double *d_tho = t_half_out ? co.take<double>(np * V) : nullptr;
+    if (const int rc = run_rrtmg_device_impl(*cfg, si, sj, sk, seconds, days, d_lat, d_lon, d_pf, d_ph, d_alb, d_q, d_t, d_ts,
+                                             d_zf, d_zh, d_th, d_o3, d_tdt, d_cz, d_fsw, d_flw, d_trad, d_tsw, d_tlw,
+                                             d_olr, d_isr, d_tho, st))
+        return rc;
+    auto down = [&](double *h, const double *d, size_t n) {
+        if (h && cudaMemcpyAsync(h, d, n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) ok = false;
+    };
+    down(tdt, d_tdt, np * L); down(coszen, d_cz, np); down(flux_sw, d_fsw, np); down(flux_lw, d_flw, np);
+    down(olr, d_olr, np); down(isr, d_isr, np); down(tdt_rad, d_trad, np * L); down(tdt_sw, d_tsw, np * L);
+    down(tdt_lw, d_tlw, np * L); down(t_half_out, d_tho, np * V);
+    if (!ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (run_rrtmg)");
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RRTMG_B200_OK;
 }
 
 int rrtmg_b200_set_option(const char *key, long value)

@@ -170,6 +170,40 @@ struct SwWork {
 };
 
 
+// ------------------------------------------------------------------------------------ radiation driver (driver.cu)
+struct RadGeom {
+    int si, sj, sk;           // GCM grid of the rank: lon, lat, levels
+    int ls;                   // lonstep
+    int ni;                   // si / lonstep
+    int ncols;                // ni * sj = ncols_rrt
+};
+struct ZenithArgs {           // scalars of compute_zenith (astro.f90:95-127), evaluated on the host
+    double radsec, dt_pi, radpersec, dec_sin, dec_cos, dec_tan;
+    int dt;
+};
+struct PackArgs {
+    // GCM state (si, sj, sk) / (si, sj, sk+1) / (si, sj); level 1 = top; Pa, K, kg/kg
+    const double *p_full, *p_half, *t, *t_half, *q, *o3f, *coszen, *albedo, *t_surf, *lat;
+    const double *qzm;        // zonal-mean q (sj, sk) or null
+    const int *top_flag;
+    // RRTMG inputs (ncols, sk) / (ncols, sk+1) / (ncols); level 1 = surface; hPa
+    double *pfull, *phalf, *tfull, *thalf, *h2o, *o3, *cosz_rr, *albedo_rr, *tsrf;
+    double qmin, tmin, tmax, scale_ozone, o3_val;
+    int do_fixed_water;
+    double fixed_water, fixed_water_pres, fixed_water_lat;
+};
+struct UnpackArgs {
+    const double *swhr, *swuflx, *swdflx, *lwhr, *lwuflx, *lwdflx;   // RRTMG outputs
+    double *tdt, *tdt_rad, *tdt_sw, *tdt_lw;                           // (si, sj, sk); any may be null
+    double *flux_sw, *flux_lw, *olr, *isr;                             // (si, sj); any may be null
+};
+int drv_zenith(int n, const double *lat, const double *lon, double *cosz, const ZenithArgs &a, cudaStream_t s);
+int drv_interp_temp(int np, int sk, const double *z_full, const double *z_half, const double *t_surf, const double *t,
+                    double *t_half, cudaStream_t s);
+int drv_pack(const RadGeom &g, const PackArgs &a, double *qzm_buf, int *flag, cudaStream_t s);
+int drv_fill(double *p, size_t n, double v, cudaStream_t s);
+int drv_unpack(const RadGeom &g, const UnpackArgs &a, double *zm_buf, cudaStream_t s);
+
 // ------------------------------------------------------------------------------------ device math
 #ifdef __CUDACC__
 // FP64 reciprocal and square root from the 20-bit MUFU seeds plus Newton steps written as fma().  They
