@@ -174,3 +174,56 @@ contains
     icld = icld_c; iaer = iaer_c
   end subroutine
 end module rrtmg_sw_rad
+
+! ---------------------------------------------------------------------------------------------------------
+! Optional second stage (SURVEY.md section 8f, ranks 1-2): the radiation step of run_rrtmg on the device.
+! With this module the body of run_rrtmg between "we know now that we want to run radiation"
+! (rrtm_radiation.f90:585) and write_diag_rrtm (:829) becomes ONE call: lon sub-sampling, the vertical flip,
+! Pa -> hPa, the clamps, interp_temp, compute_zenith, both RRTMG calls, K/day -> K/s, the lon
+! re-interpolation and the surface fluxes all run on the GPU, and only the GCM state crosses PCIe.
+! The alarm (dt_rad), the interpolator_mod reads (ozone, h2o, radiation files) and the diag manager stay as
+! they are.  type(b200_rad_config) mirrors struct rrtmg_b200_rad_config (include/rrtmg_b200.h) field by field.
+module rrtm_radiation_b200
+  use iso_c_binding
+  use rrtmg_b200_c, only: b200_check
+  implicit none
+  type, bind(c) :: b200_rad_config
+     integer(c_int) :: include_secondary_gases, do_fixed_water, do_zm_tracers, do_rad_time_avg, dt_rad_avg, &
+          lonstep, do_zm_rad, use_dyofyr, solday, days_per_year
+     real(c_double) :: scale_ozone, o3_val, ch4_val, n2o_val, o2_val, cfc11_val, cfc12_val, cfc22_val, ccl4_val, &
+          h2o_lower_limit, temp_lower_limit, temp_upper_limit, co2ppmv, fixed_water, fixed_water_pres, &
+          fixed_water_lat, slowdown_rad, obliq, solr_cnst, solrad, equinox_day
+  end type
+  interface
+     integer(c_int) function rrtmg_b200_run_rrtmg(cfg, si, sj, sk, seconds, days, lat, lon, p_full, p_half, albedo, &
+          q, t, t_surf_rad, z_full, z_half, t_half_in, o3f, tdt, coszen, flux_sw, flux_lw, tdt_rad, tdt_sw, tdt_lw, &
+          olr, isr, t_half_out) bind(c)
+       import
+       type(b200_rad_config), intent(in) :: cfg
+       integer(c_int), value :: si, sj, sk, seconds, days
+       type(c_ptr), value :: lat, lon, p_full, p_half, albedo, q, t, t_surf_rad, z_full, z_half, t_half_in, o3f, &
+            tdt, coszen, flux_sw, flux_lw, tdt_rad, tdt_sw, tdt_lw, olr, isr, t_half_out
+     end function
+  end interface
+contains
+  ! Called from run_rrtmg in place of rrtm_radiation.f90:585-808.  `cfg` is filled once in rrtm_radiation_init
+  ! from the namelist variables of rrtm_vars / rrtm_astro (logicals -> 0/1; dt_rad_avg after :336-340;
+  ! days_per_year from get_time(length_of_year())).
+  subroutine run_rrtmg_b200(cfg, seconds, days, lat, lon, p_full, p_half, albedo, q, t, t_surf_rad, z_full, z_half, &
+       o3f, have_o3, tdt, coszen, flux_sw, flux_lw, tdt_rad, t_half)
+    type(b200_rad_config), intent(in) :: cfg
+    integer, intent(in) :: seconds, days
+    real(c_double), contiguous, target, intent(in) :: lat(:,:), lon(:,:), albedo(:,:), t_surf_rad(:,:)
+    real(c_double), contiguous, target, intent(in) :: p_full(:,:,:), p_half(:,:,:), q(:,:,:), t(:,:,:)
+    real(c_double), contiguous, target, intent(in) :: z_full(:,:,:), z_half(:,:,:), o3f(:,:,:)
+    logical, intent(in) :: have_o3                        ! do_read_ozone
+    real(c_double), contiguous, target, intent(inout) :: tdt(:,:,:)
+    real(c_double), contiguous, target, intent(out) :: coszen(:,:), flux_sw(:,:), flux_lw(:,:), tdt_rad(:,:,:), t_half(:,:,:)
+    type(c_ptr) :: po3
+    po3 = c_null_ptr; if (have_o3) po3 = c_loc(o3f)
+    call b200_check(rrtmg_b200_run_rrtmg(cfg, size(t,1), size(t,2), size(t,3), seconds, days, &
+         c_loc(lat), c_loc(lon), c_loc(p_full), c_loc(p_half), c_loc(albedo), c_loc(q), c_loc(t), c_loc(t_surf_rad), &
+         c_loc(z_full), c_loc(z_half), c_null_ptr, po3, c_loc(tdt), c_loc(coszen), c_loc(flux_sw), c_loc(flux_lw), &
+         c_loc(tdt_rad), c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_loc(t_half)), 'run_rrtmg')
+  end subroutine
+end module rrtm_radiation_b200
