@@ -365,6 +365,35 @@ def main():
     h2d = 8 * (5 * nl + 2 * nv + 3 * ncol) + 8 * (5 * nl + 2 * nv + 1 * ncol)   # SW inputs + LW inputs
     d2h = 2 * 8 * (4 * nv + 2 * nl)
 
+    # ---------------- the whole radiation step of run_rrtmg through the C ABI (device-side marshaling, interp_temp
+    #                  and compute_zenith): GCM state in, heating rate + 2-D fields out
+    from mima_b200 import rrtm_radiation as rr
+    from mima_b200.columns import gcm_state_from_columns
+    gs = gcm_state_from_columns(cols)
+    gh = {k: pin(gs[k]) for k in ("lat", "lon", "p_full", "p_half", "albedo", "q", "t", "t_surf", "z_full", "z_half", "o3f", "tdt")}
+    go = {"coszen": torch.empty(ncol, dtype=torch.float64).pin_memory(), "flux_sw": torch.empty(ncol, dtype=torch.float64).pin_memory(),
+          "flux_lw": torch.empty(ncol, dtype=torch.float64).pin_memory(), "tdt_rad": torch.empty(nl, dtype=torch.float64).pin_memory()}
+    rcfg = rr.RadConfig(co2ppmv=390.0, solr_cnst=cols.scon).to_c()
+
+    def step_run_rrtmg():
+        rc = L_.rrtmg_b200_run_rrtmg(C.byref(rcfg), C.c_int(nlon), C.c_int(nlat), C.c_int(nlay), C.c_int(0), C.c_int(90),
+                                     HP(gh["lat"]), HP(gh["lon"]), HP(gh["p_full"]), HP(gh["p_half"]), HP(gh["albedo"]),
+                                     HP(gh["q"]), HP(gh["t"]), HP(gh["t_surf"]), HP(gh["z_full"]), HP(gh["z_half"]), NULL,
+                                     HP(gh["o3f"]), HP(gh["tdt"]), HP(go["coszen"]), HP(go["flux_sw"]), HP(go["flux_lw"]),
+                                     HP(go["tdt_rad"]), NULL, NULL, NULL, NULL, NULL)
+        if rc:
+            raise RuntimeError(L_.rrtmg_b200_last_error().decode())
+
+    step_run_rrtmg()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_run_rrtmg()
+    barrier()
+    ms_rr = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    rr_h2d = 8 * (6 * nl + 2 * nv + 4 * ncol)          # p_full q t z_full o3f tdt | p_half z_half | lat lon albedo t_surf
+    rr_d2h = 8 * (2 * nl + 3 * ncol)                   # tdt tdt_rad | coszen flux_sw flux_lw
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -410,6 +439,9 @@ def main():
                    "all_sunlit": True, "lw_tables": "synthetic (reference LW k_g file stripped)", "sw_tables": "reference"},
         "e2e": {"value": total_cols / (ms_e2e / e2e_steps * 1e-3), "unit": "columns/s", "ms_per_step": ms_e2e / e2e_steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "e2e_run_rrtmg": {"value": total_cols / (ms_rr / e2e_steps * 1e-3), "unit": "columns/s", "ms_per_step": ms_rr / e2e_steps,
+                          "h2d_bytes_per_step": rr_h2d, "d2h_bytes_per_step": rr_d2h, "steps": e2e_steps,
+                          "what": "rrtmg_b200_run_rrtmg with host buffers: marshaling + interp_temp + compute_zenith (daily-mean sun) + SW + LW"},
         "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
     }

@@ -220,11 +220,19 @@ def make_columns(resolution: str = "T42L40", *, seed: int = 20240917, co2_ppmv: 
 
 def make_gcm_state(resolution: str = "T42L40", **kw) -> dict:
     """The same synthetic atmosphere as make_columns(), in the layout MiMA's run_rrtmg receives
-    (rrtm_radiation.f90:471-503): fields (lon, lat, lev) with level 1 = top, pressures in Pa, p_half(top) = 0,
-    lat/lon in radians, plus geopotential heights for interp_temp (hydrostatic, z_half(k=1) = 0 as in the
-    model, rrtm_radiation.f90:433) and a zero tendency array."""
+    (see gcm_state_from_columns)."""
     c = make_columns(resolution, **kw)
+    nlat_full = kw["nlat"] if "nlat" in kw else RESOLUTIONS.get(resolution, (c.nlon, c.nlat, c.nlay))[1]
+    return gcm_state_from_columns(c, nlat_full=nlat_full, j0=kw.get("lat_rows", (0, c.nlat))[0])
+
+
+def gcm_state_from_columns(c: Columns, nlat_full: int | None = None, j0: int = 0) -> dict:
+    """A Columns batch rearranged into the dummy arguments of run_rrtmg (rrtm_radiation.f90:471-503): fields
+    (lon, lat, lev) with level 1 = top, pressures in Pa, p_half(top) = 0, lat/lon in radians, plus geopotential
+    heights for interp_temp (hydrostatic, z_half(k=1) = 0 as in the model, rrtm_radiation.f90:433) and a zero
+    tendency array."""
     si, sj, sk = c.nlon, c.nlat, c.nlay
+    nlat_full = nlat_full or sj
 
     def fms(a):          # (ncol, n) surface-first -> (lon, lat, n) top-first
         return np.asfortranarray(a.reshape((si, sj, a.shape[1]), order="F")[:, :, ::-1])
@@ -237,9 +245,7 @@ def make_gcm_state(resolution: str = "T42L40", **kw) -> dict:
     o3f = fms(c.o3)
     t_surf = np.asfortranarray(c.tsfc.reshape((si, sj), order="F"))
     albedo = np.asfortranarray(c.albedo.reshape((si, sj), order="F"))
-    nlat_full = RESOLUTIONS.get(resolution, (si, sj, sk))[1] if "nlat" not in kw else sj
     lat1 = np.arcsin(np.linspace(-1.0 + 1.0 / nlat_full, 1.0 - 1.0 / nlat_full, nlat_full))
-    j0 = kw.get("lat_rows", (0, sj))[0]
     lat = np.asfortranarray(np.broadcast_to(lat1[j0:j0 + sj][None, :], (si, sj)))
     lon = np.asfortranarray(np.broadcast_to((np.arange(si) * (2.0 * np.pi / si))[:, None], (si, sj)))
     rd_g = 287.04 / 9.80

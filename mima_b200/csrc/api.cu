@@ -563,14 +563,15 @@ int sw_chunk(const SwIn &in, const SwOut &out, int nc, int nlay, void *work, boo
     return RRTMG_B200_OK;
 }
 
-int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st)
+int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st, DevBuf *work = nullptr)
 {
+    DevBuf &wk = work ? *work : G.lw_work;
     if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     LwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    if (G.lw_work.ensure(lw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
+    if (wk.ensure(lw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         LwIn in = in0;
@@ -580,19 +581,20 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
         OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
 #undef OFF
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
-        if (const int rc = lw_chunk(in, out, nc, nlay, G.lw_work.p, fields, st, c0 + nc >= ncol)) return rc;
+        if (const int rc = lw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
     }
     return RRTMG_B200_OK;
 }
 
-int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st)
+int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st, DevBuf *work = nullptr)
 {
+    DevBuf &wk = work ? *work : G.sw_work;
     if (const int rc = sw_validate(ncol, nlay, icld, iaer)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     SwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    if (G.sw_work.ensure(sw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
+    if (wk.ensure(sw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         SwIn in = in0;
@@ -602,7 +604,7 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
         OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
 #undef OFF
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
-        if (const int rc = sw_chunk(in, out, nc, nlay, G.sw_work.p, fields, st, c0 + nc >= ncol)) return rc;
+        if (const int rc = sw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
     }
     return RRTMG_B200_OK;
 }
@@ -703,12 +705,16 @@ void ktimer_end(cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // radiation driver (run_rrtmg on the device)
 namespace {
+struct DrvSlot {                     // one stage of the host-pointer pipeline (and slot 0: the device-pointer entry)
+    DevBuf in, out, host_in, host_out, lw_work, sw_work;
+    cudaStream_t st = nullptr;
+};
 struct DrvState {
-    DevBuf in, out, gas, misc, host_in, host_out;
+    DrvSlot slot[2];
+    DevBuf gas, misc;
     size_t gas_n = 0;
     double gas_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool gas_set = false;
-    cudaStream_t st = nullptr;
 } D;
 
 struct ZenithHost { ZenithArgs a; int dyofyr; int sec_l, day_l; };
@@ -755,7 +761,7 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
                           const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
                           double *tdt, double *coszen, double *flux_sw, double *flux_lw, double *tdt_rad,
                           double *tdt_sw, double *tdt_lw, double *olr, double *isr, double *t_half_out,
-                          cudaStream_t st)
+                          cudaStream_t st, DrvSlot &S, bool own_work)
 {
     if (!G.lw_ready || !G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "run_rrtmg: rrtmg_b200_lw_init / sw_init have not been called");
     if (si < 1 || sj < 1 || sk < 2 || sk > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: grid extents out of range");
@@ -770,8 +776,8 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
     // packed RRTMG inputs + t_half + zonal-mean scratch
     const size_t in_bytes = 4 * pad(nc * L) + 2 * pad(nc * V) + 3 * pad(nc) + pad(np * V) + pad((size_t)sj * sk + 2 * sj) + pad(sj * L) + 256;
     const size_t out_bytes = 4 * pad(nc * V) + 2 * pad(nc * L) + 4 * pad(nc * V) + 2 * pad(nc * L);
-    if (D.in.ensure(in_bytes) || D.out.ensure(out_bytes)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg buffers)");
-    Carver ci(D.in.p), co(D.out.p);
+    if (S.in.ensure(in_bytes) || S.out.ensure(out_bytes)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg buffers)");
+    Carver ci(S.in.p), co(S.out.p);
     double *pfull = ci.take<double>(nc * L), *tfull = ci.take<double>(nc * L), *h2o = ci.take<double>(nc * L), *o3 = ci.take<double>(nc * L);
     double *phalf = ci.take<double>(nc * V), *thalf = ci.take<double>(nc * V);
     double *cosz_rr = ci.take<double>(nc), *albedo_rr = ci.take<double>(nc), *tsrf = ci.take<double>(nc);
@@ -786,15 +792,22 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
     // constant gas arrays: co2, and the seven secondary gases when requested (RR/rrtm_radiation.f90:360, 679-748)
     const double gv[8] = {c.co2ppmv * 1.e-6, c.ch4_val, c.n2o_val, c.o2_val, c.cfc11_val, c.cfc12_val, c.cfc22_val, c.ccl4_val};
     const int ngas = c.include_secondary_gases ? 8 : 1;
-    bool refill = !D.gas_set || D.gas_n != nc * L;
+    // (a prefix of a constant array is the same constant array: the capacity only grows, and the arrays are shared by
+    // the pipeline stages; the fill is ordered before every consumer by a device-wide sync, done only when values change)
+    bool refill = !D.gas_set || D.gas_n < nc * L;
     for (int i = 0; i < 8; ++i) refill = refill || D.gas_val[i] != gv[i];
-    if (D.gas.ensure(8 * pad(nc * L))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (gas arrays)");
+    const size_t gcap = refill ? (nc * L > D.gas_n ? nc * L : D.gas_n) : D.gas_n;
+    if (refill) {
+        CUDA_OK(cudaDeviceSynchronize());
+        if (D.gas.ensure(8 * pad(gcap))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (gas arrays)");
+    }
     Carver cg(D.gas.p);
     double *gas[8];
-    for (int i = 0; i < 8; ++i) gas[i] = cg.take<double>(nc * L);
+    for (int i = 0; i < 8; ++i) gas[i] = cg.take<double>(gcap);
     if (refill) {
-        for (int i = 0; i < 8; ++i) { G.launches += drv_fill(gas[i], nc * L, gv[i], st); D.gas_val[i] = gv[i]; }
-        D.gas_n = nc * L; D.gas_set = true;
+        for (int i = 0; i < 8; ++i) { G.launches += drv_fill(gas[i], gcap, gv[i], st); D.gas_val[i] = gv[i]; }
+        CUDA_OK(cudaStreamSynchronize(st));
+        D.gas_n = gcap; D.gas_set = true;
     }
     // Time_loc, zenith angle (also an output)
     int sec_l, day_l;
@@ -827,13 +840,13 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
              ngas > 1 ? gas[1] : nullptr, ngas > 1 ? gas[2] : nullptr, ngas > 1 ? gas[3] : nullptr,
              albedo_rr, albedo_rr, albedo_rr, albedo_rr, cosz_rr, sw_adjflux(c.solrad, dyofyr, c.solr_cnst)};
     SwOut sout{(int)nc, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
-    if (const int rc = sw_device_impl((int)nc, sk, &icld, &iaer, sin, sout, st)) return rc;
+    if (const int rc = sw_device_impl((int)nc, sk, &icld, &iaer, sin, sout, st, own_work ? &S.sw_work : nullptr)) return rc;
     LwIn lin{(int)nc, pfull, phalf, tfull, thalf, tsrf, h2o, o3, gas[0],
              ngas > 1 ? gas[1] : nullptr, ngas > 1 ? gas[2] : nullptr, ngas > 1 ? gas[3] : nullptr,
              ngas > 1 ? gas[4] : nullptr, ngas > 1 ? gas[5] : nullptr, ngas > 1 ? gas[6] : nullptr, ngas > 1 ? gas[7] : nullptr,
              nullptr, nullptr};
     LwOut lout{(int)nc, uflx, dflx, hr, uflxc, dflxc, hrc};
-    if (const int rc = lw_device_impl((int)nc, sk, &icld, 0, lin, lout, st)) return rc;
+    if (const int rc = lw_device_impl((int)nc, sk, &icld, 0, lin, lout, st, own_work ? &S.lw_work : nullptr)) return rc;
     UnpackArgs ua{swhr, swuflx, swdflx, hr, uflx, dflx, tdt, tdt_rad, tdt_sw, tdt_lw, flux_sw, flux_lw, olr, isr};
     G.launches += drv_unpack(g, ua, c.do_zm_rad ? zm_buf : nullptr, st);
     CUDA_OK(cudaGetLastError());
@@ -942,9 +955,12 @@ int rrtmg_b200_finalize(void)
         b->release();
     P_lw.release();
     P_sw.release();
-    for (DevBuf *b : {&D.in, &D.out, &D.gas, &D.misc, &D.host_in, &D.host_out}) b->release();
-    D.gas_set = false;
-    if (D.st) { cudaStreamDestroy(D.st); D.st = nullptr; }
+    for (DrvSlot &S : D.slot) {
+        for (DevBuf *b : {&S.in, &S.out, &S.host_in, &S.host_out, &S.lw_work, &S.sw_work}) b->release();
+        if (S.st) { cudaStreamDestroy(S.st); S.st = nullptr; }
+    }
+    D.gas.release(); D.misc.release();
+    D.gas_set = false; D.gas_n = 0;
     G.lw_ready = G.sw_ready = false;
     G.lw_last_ncol = G.sw_last_ncol = 0;
     G.reduced.clear();
@@ -1268,7 +1284,7 @@ int rrtmg_b200_run_rrtmg_device(const rrtmg_b200_rad_config *cfg, int si, int sj
     if (!cfg) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: config is NULL");
     return run_rrtmg_device_impl(*cfg, si, sj, sk, seconds, days, lat, lon, p_full, p_half, albedo, q, t, t_surf_rad,
                                  z_full, z_half, t_half_in, o3f, tdt, coszen, flux_sw, flux_lw, tdt_rad, tdt_sw, tdt_lw,
-                                 olr, isr, t_half_out, (cudaStream_t)stream);
+                                 olr, isr, t_half_out, (cudaStream_t)stream, D.slot[0], false);
 }
 
 int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int sk, int seconds, int days,
@@ -1283,46 +1299,62 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     if (si < 1 || sj < 1 || sk < 2) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: grid extents out of range");
     if (!lat || !lon || !p_full || !p_half || !albedo || !q || !t || !t_surf_rad || !coszen)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: required array is NULL");
-    if (!D.st && cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
-    cudaStream_t st = D.st;
-    const size_t np = (size_t)si * sj, L = sk, V = sk + 1;
+    if (cfg->lonstep < 1 || si % cfg->lonstep != 0) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: lonstep must divide the number of longitudes");
+    if (!t_half_in && (!z_full || !z_half)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: need t_half or z_full + z_half");
+    // Blocks of latitude rows flow through a two-stage pipeline (two streams, two buffer sets): the H2D copy of block
+    // i+1 and the D2H copy of block i-1 overlap the kernels of block i.  Everything in run_rrtmg is local to a
+    // latitude row (the zonal means too), and a row block of an (si, sj, n) field is n runs of si*rows doubles.
+    const size_t np_all = (size_t)si * sj, L = sk, V = sk + 1;
+    int target = G.chunk > 0 ? G.chunk : 32768;                   // RRTMG columns per block
+    int rows = (int)((long)target * cfg->lonstep / si);
+    if (rows < 1) rows = 1;
+    if (rows > sj) rows = sj;
+    const int nslot = rows < sj ? 2 : 1;
     auto pad = [](size_t n) { return (n * 8 + 255) & ~(size_t)255; };
-    const size_t hin = 5 * pad(np) + 6 * pad(np * L) + 3 * pad(np * V);
-    const size_t hout = 5 * pad(np) + 4 * pad(np * L) + pad(np * V);
-    if (D.host_in.ensure(hin) || D.host_out.ensure(hout)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg host staging)");
-    Carver ci(D.host_in.p), co(D.host_out.p);
-    bool ok = true;
-    auto up = [&](const double *h, size_t n) -> double * {
-        if (!h) return nullptr;
-        double *d = ci.take<double>(n);
-        if (cudaMemcpyAsync(d, h, n * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
-        return d;
-    };
-    const double *d_lat = up(lat, np), *d_lon = up(lon, np), *d_alb = up(albedo, np), *d_ts = up(t_surf_rad, np);
-    const double *d_pf = up(p_full, np * L), *d_ph = up(p_half, np * V), *d_q = up(q, np * L), *d_t = up(t, np * L);
-    const double *d_zf = t_half_in ? nullptr : up(z_full, np * L), *d_zh = t_half_in ? nullptr : up(z_half, np * V);
-    const double *d_th = up(t_half_in, np * V), *d_o3 = up(o3f, np * L);
-    double *d_tdt = tdt ? ci.take<double>(np * L) : nullptr;
-    if (tdt && cudaMemcpyAsync(d_tdt, tdt, np * L * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
-    if (!ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (run_rrtmg)");
-    double *d_cz = co.take<double>(np);
-    double *d_fsw = flux_sw ? co.take<double>(np) : nullptr, *d_flw = flux_lw ? co.take<double>(np) : nullptr;
-    double *d_olr = olr ? co.take<double>(np) : nullptr, *d_isr = isr ? co.take<double>(np) : nullptr;
-    double *d_trad = tdt_rad ? co.take<double>(np * L) : nullptr, *d_tsw = tdt_sw ? co.take<double>(np * L) : nullptr;
-    double *d_tlw = tdt_lw ? co.take<double>(np * L) : nullptr;
-    double *d_tho = t_half_out ? co.take<double>(np * V) : nullptr;
-    if (const int rc = run_rrtmg_device_impl(*cfg, si, sj, sk, seconds, days, d_lat, d_lon, d_pf, d_ph, d_alb, d_q, d_t, d_ts,
-                                             d_zf, d_zh, d_th, d_o3, d_tdt, d_cz, d_fsw, d_flw, d_trad, d_tsw, d_tlw,
-                                             d_olr, d_isr, d_tho, st))
-        return rc;
-    auto down = [&](double *h, const double *d, size_t n) {
-        if (h && cudaMemcpyAsync(h, d, n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) ok = false;
-    };
-    down(tdt, d_tdt, np * L); down(coszen, d_cz, np); down(flux_sw, d_fsw, np); down(flux_lw, d_flw, np);
-    down(olr, d_olr, np); down(isr, d_isr, np); down(tdt_rad, d_trad, np * L); down(tdt_sw, d_tsw, np * L);
-    down(tdt_lw, d_tlw, np * L); down(t_half_out, d_tho, np * V);
-    if (!ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (run_rrtmg)");
-    CUDA_OK(cudaStreamSynchronize(st));
+    const size_t npb = (size_t)si * rows;
+    const size_t hin = 5 * pad(npb) + 6 * pad(npb * L) + 3 * pad(npb * V);
+    const size_t hout = 5 * pad(npb) + 4 * pad(npb * L) + pad(npb * V);
+    for (int i = 0; i < nslot; ++i) {
+        DrvSlot &S = D.slot[i];
+        if (!S.st && cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
+        if (S.host_in.ensure(hin) || S.host_out.ensure(hout)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg host staging)");
+    }
+    int idx = 0;
+    for (int j0 = 0; j0 < sj; j0 += rows, ++idx) {
+        const int nr = (sj - j0 < rows) ? sj - j0 : rows;
+        DrvSlot &S = D.slot[idx & 1];
+        cudaStream_t st = S.st;
+        // a block is "columns" [j0*si, (j0+nr)*si) of a column-major (si*sj, n) array
+        Slot a{(char *)S.host_in.p, 0, j0 * si, nr * si, (int)np_all, st, true};
+        const double *d_lat = a.up(lat, 1), *d_lon = a.up(lon, 1), *d_alb = a.up(albedo, 1), *d_ts = a.up(t_surf_rad, 1);
+        const double *d_pf = a.up(p_full, L), *d_ph = a.up(p_half, V), *d_q = a.up(q, L), *d_t = a.up(t, L);
+        const double *d_zf = t_half_in ? nullptr : a.up(z_full, L), *d_zh = t_half_in ? nullptr : a.up(z_half, V);
+        const double *d_th = a.up(t_half_in, V), *d_o3 = a.up(o3f, L);
+        double *d_tdt = tdt ? const_cast<double *>(a.up(tdt, L)) : nullptr;
+        if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (run_rrtmg)");
+        Slot o{(char *)S.host_out.p, 0, j0 * si, nr * si, (int)np_all, st, true};
+        double *d_cz = o.take(1);
+        double *d_fsw = flux_sw ? o.take(1) : nullptr, *d_flw = flux_lw ? o.take(1) : nullptr;
+        double *d_olr = olr ? o.take(1) : nullptr, *d_isr = isr ? o.take(1) : nullptr;
+        double *d_trad = tdt_rad ? o.take(L) : nullptr, *d_tsw = tdt_sw ? o.take(L) : nullptr, *d_tlw = tdt_lw ? o.take(L) : nullptr;
+        double *d_tho = t_half_out ? o.take(V) : nullptr;
+        if (const int rc = run_rrtmg_device_impl(*cfg, si, nr, sk, seconds, days, d_lat, d_lon, d_pf, d_ph, d_alb, d_q, d_t, d_ts,
+                                                 d_zf, d_zh, d_th, d_o3, d_tdt, d_cz, d_fsw, d_flw, d_trad, d_tsw, d_tlw,
+                                                 d_olr, d_isr, d_tho, st, S, true))
+            return rc;
+        if (tdt) o.down(tdt, d_tdt, L);
+        o.down(coszen, d_cz, 1);
+        if (flux_sw) o.down(flux_sw, d_fsw, 1);
+        if (flux_lw) o.down(flux_lw, d_flw, 1);
+        if (olr) o.down(olr, d_olr, 1);
+        if (isr) o.down(isr, d_isr, 1);
+        if (tdt_rad) o.down(tdt_rad, d_trad, L);
+        if (tdt_sw) o.down(tdt_sw, d_tsw, L);
+        if (tdt_lw) o.down(tdt_lw, d_tlw, L);
+        if (t_half_out) o.down(t_half_out, d_tho, V);
+        if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (run_rrtmg)");
+    }
+    for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(D.slot[i].st));
     return RRTMG_B200_OK;
 }
 
