@@ -157,7 +157,12 @@ def cpu_reference_rate(workload: str, sample_cols: int, repeats: int, threads: i
     j0 = (nlat - rows) // 2
     cols = make_columns(workload, lat_rows=(j0, j0 + rows))
     orc = Oracle()
-    nt = threads or orc.max_threads
+    # all host cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    nt = threads or max(orc.max_threads, ncpu)
     best = None
     times = []
     for _ in range(repeats):
