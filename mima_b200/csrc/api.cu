@@ -687,7 +687,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 1, 1};
+Tuning g_tune = {0, 0, 0, 1, 2};
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;

@@ -260,9 +260,249 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
     }
 }
 
+
+// =====================================================================================================
+// Variant 2: the staging rows arrive by TMA.  The column streams through a ring of NST shared-memory stages
+// filled by cp.async.bulk (1-D bulk copies completing on an mbarrier): per stage the taug and fracs rows of
+// CH layers (2 x CH x 1120 B, contiguous in the [col][lay][g] staging layout) and the matching Planck rows
+// (planklay CH x 128 B, planklev (CH+1) x 128 B).  The five g-point warps wait on the stage's "full"
+// barrier, read everything with shared-memory loads and release the stage through an "empty" barrier (one
+// arrival per warp); a sixth warp (one lane) re-arms the barrier and issues the copies of the chunk NST
+// positions ahead (having the last g-point warp issue them instead measured 2 % slower).  No block barrier.  The chunk sequence of a column is fixed: down sweep top to bottom, then up sweep
+// bottom to top (second read, mostly L2).  What this buys: the streaming loads no longer occupy the L1
+// tag/miss path, which the 16-byte exp/tfn table gathers need (profiles/r01_summary.md), the Planck rows
+// need no per-block prologue, and 64 registers suffice.  Arithmetic, warp-local g-sums and epilogue are
+// those of lw_rtrn_kernel<., true>.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int CH> struct TmaGeom {
+    static constexpr int STAGE = CH * 2 * NGPTLW + CH * 16 + (CH + 1) * 16;   // doubles per stage
+};
+
+// chunk q of the column's sequence: layers [lo, lo + n)
+template <int CH>
+__device__ __forceinline__ void tma_chunk(int q, int nd, int nlay, int &lo, int &n)
+{
+    if (q < nd) { const int hi = nlay - 1 - q * CH; lo = max(hi - CH + 1, 0); n = hi - lo + 1; }
+    else { lo = (q - nd) * CH; n = min(CH, nlay - lo); }
+}
+template <int CH>
+__device__ __forceinline__ void tma_issue(const LwWork &w, int col, int nlay, int lo, int n, double *d, uint64_t *bar)
+{
+    const double *gt = w.taug + ((size_t)col * nlay + lo) * NGPTLW, *gf = w.fracs + ((size_t)col * nlay + lo) * NGPTLW;
+    const double *gl = w.planklay + ((size_t)col * nlay + lo) * 16, *gv = w.planklev + ((size_t)col * (nlay + 1) + lo) * 16;
+    mbar_expect_tx(bar, (uint32_t)(n * (2 * NGPTLW + 16) * 8 + (n + 1) * 128));
+    tma_load_1d(d, gt, (uint32_t)(n * NGPTLW * 8), bar);
+    tma_load_1d(d + CH * NGPTLW, gf, (uint32_t)(n * NGPTLW * 8), bar);
+    tma_load_1d(d + 2 * CH * NGPTLW, gl, (uint32_t)(n * 128), bar);
+    tma_load_1d(d + 2 * CH * NGPTLW + CH * 16, gv, (uint32_t)((n + 1) * 128), bar);
+}
+
+template <bool AER, int LMAX, int NST, int CH>
+__global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
+{
+    constexpr int STAGE = TmaGeom<CH>::STAGE;
+    extern __shared__ __align__(128) double s_stage[];           // NST stages of STAGE doubles
+    __shared__ __align__(8) uint64_t s_full[NST], s_empty[NST];
+    __shared__ double s_tile[RT_WARPS * 8 * RT_WS];
+    __shared__ double s_part[RT_WARPS * 2 * (LMAX + 1)];
+    __shared__ double s_dn[LMAX + 1], s_up[LMAX + 1];
+    const int col = blockIdx.x;
+    const int nlay = w.nlay;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nd = (nlay + CH - 1) / CH;                         // chunks per sweep
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RT_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (wid == RT_WARPS) {
+        // producer warp (one lane): chunk q goes to stage q % NST as soon as the five g-point warps have left it
+        if (lane == 0) {
+            for (int q = 0; q < 2 * nd; ++q) {
+                const int st = q % NST, it = q / NST;
+                int lo, n;
+                tma_chunk<CH>(q, nd, nlay, lo, n);
+                if (it > 0) mbar_wait(&s_empty[st], (uint32_t)((it - 1) & 1));
+                tma_issue<CH>(w, col, nlay, lo, n, s_stage + (size_t)st * STAGE, &s_full[st]);
+            }
+        }
+    } else {
+
+    const int g = threadIdx.x;
+    const bool active = g < NGPTLW;
+    const int gc = active ? g : 0;
+    const int band = c_ls.ngb[gc];
+    const double secd = w.secdiff[(size_t)col * 16 + band];
+    const double wgt = active ? 0.5 * c_ls.delwave[band] : 0.0;
+    const double bpade = c_ls.bpade;
+    const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
+    const double *taer = AER ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
+    double *wt = s_tile + wid * 8 * RT_WS + lane + (lane >> 4);
+    auto release = [&](int, int st) {           // this warp has read everything it needs from stage `st`
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+    };
+    double radld = 0.0, plfrac1 = 0.0;
+    int q = 0;
+    // downward sweep (:505-618)
+    for (; q < nd; ++q) {
+        const int st = q % NST, it = q / NST;
+        const int hi = nlay - 1 - q * CH, lo = max(hi - CH + 1, 0), n = hi - lo + 1;
+        mbar_wait(&s_full[st], (uint32_t)(it & 1));
+        const double *d = s_stage + (size_t)st * STAGE;
+        const double *stg = d + gc, *sfr = d + CH * NGPTLW + gc;
+        const double *spl = d + 2 * CH * NGPTLW + band, *spv = spl + CH * 16;
+        double at[CH], bd[CH], frv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int r = max(n - 1 - j, 0);                  // row inside the stage, top layer first
+            double tg = stg[r * NGPTLW];
+            if (AER) tg = tg + taer[(size_t)(lo + r) * in.ld];
+            frv[j] = sfr[r * NGPTLW];
+            const double blay = spl[r * 16];
+            double bbu;
+            lw_layer<true>(et, bpade, secd, tg, frv[j], blay, spv[(r + 1) * 16] - blay, spv[r * 16] - blay, at[j], bd[j], bbu);
+        }
+        release(q, st);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            if (j < n) {
+                const int k = nlay - 1 - (hi - j);
+                radld = radld + (bd[j] - radld) * at[j];
+                wt[(k & 7) * RT_WS] = radld * wgt;
+                if (k == nlay - 1) plfrac1 = frv[j];
+                if ((k & 7) == 7 || k == nlay - 1) {
+                    const double sum = warp_rows8(s_tile + wid * 8 * RT_WS, lane);
+                    const int kk = (k & ~7) + (lane >> 2);
+                    if ((lane & 3) == 0 && kk <= k) s_part[(wid * 2) * (LMAX + 1) + nlay - 1 - kk] = sum;
+                }
+            }
+        }
+    }
+    if (lane == 0) s_part[(wid * 2) * (LMAX + 1) + nlay] = 0.0;
+    // surface (:628-636)
+    double radlu;
+    {
+        const double semiss = in.emis ? in.emis[col + (size_t)band * in.ld] : 1.0;
+        const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
+        radlu = rad0 + (1. - semiss) * radld;
+        wt[0] = radlu * wgt;
+    }
+    // upward sweep (:649-711)
+    for (; q < 2 * nd; ++q) {
+        const int st = q % NST, it = q / NST;
+        const int lo = (q - nd) * CH, n = min(CH, nlay - lo);
+        mbar_wait(&s_full[st], (uint32_t)(it & 1));
+        const double *d = s_stage + (size_t)st * STAGE;
+        const double *stg = d + gc, *sfr = d + CH * NGPTLW + gc;
+        const double *spl = d + 2 * CH * NGPTLW + band, *spv = spl + CH * 16;
+        double at[CH], bu[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int r = min(j, n - 1);
+            double tg = stg[r * NGPTLW];
+            if (AER) tg = tg + taer[(size_t)(lo + r) * in.ld];
+            const double blay = spl[r * 16];
+            double bbd;
+            lw_layer<false>(et, bpade, secd, tg, sfr[r * NGPTLW], blay, spv[(r + 1) * 16] - blay, 0.0, at[j], bbd, bu[j]);
+        }
+        release(q, st);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            if (j < n) {
+                const int k = lo + j + 1;
+                radlu = radlu + (bu[j] - radlu) * at[j];
+                wt[(k & 7) * RT_WS] = radlu * wgt;
+                if ((k & 7) == 7 || k == nlay) {
+                    const double sum = warp_rows8(s_tile + wid * 8 * RT_WS, lane);
+                    const int kk = (k & ~7) + (lane >> 2);
+                    if ((lane & 3) == 0 && kk <= k) s_part[(wid * 2 + 1) * (LMAX + 1) + kk] = sum;
+                }
+            }
+        }
+    }
+    }
+    __syncthreads();
+    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS + 32) {
+        double d = 0.0, u = 0.0;
+#pragma unroll
+        for (int i = 0; i < RT_WARPS; ++i) {
+            d += s_part[(i * 2) * (LMAX + 1) + lev];
+            u += s_part[(i * 2 + 1) * (LMAX + 1) + lev];
+        }
+        s_dn[lev] = d * c_ls.fluxfac;
+        s_up[lev] = u * c_ls.fluxfac;
+    }
+    __syncthreads();
+    // fluxes and heating rates (:751-777), copy-out (rad.nomcica:546-555)
+    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS + 32) {
+        const size_t o = col + (size_t)lev * out.ld;
+        const double u = s_up[lev], d = s_dn[lev];
+        out.uflx[o] = u; out.dflx[o] = d;
+        out.uflxc[o] = u; out.dflxc[o] = d;
+        if (lev < nlay) {
+            const double fnet0 = u - d, fnet1 = s_up[lev + 1] - s_dn[lev + 1];
+            const double pz0 = in.plev[col + (size_t)lev * in.ld], pz1 = in.plev[col + (size_t)(lev + 1) * in.ld];
+            const double h = c_ls.heatfac * (fnet0 - fnet1) / (pz0 - pz1);
+            out.hr[o] = h;
+            out.hrc[o] = h;
+        }
+    }
+}
+
+template <bool AER, int LMAX, int NST, int CH>
+static void launch_tma(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
+{
+    const size_t smem = (size_t)NST * TmaGeom<CH>::STAGE * sizeof(double);
+    cudaFuncSetAttribute(lw_rtrn_tma_kernel<AER, LMAX, NST, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lw_rtrn_tma_kernel<AER, LMAX, NST, CH><<<w.nc, RT_THREADS + 32, smem, s>>>(t, in, out, w);
+}
+template <bool AER, int LMAX>
+static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, int v)
+{
+    // measured at T170L60 (stages x layers per stage): 2x4 7.60 ms, 2x3 7.68, 3x3 7.77, 2x5 8.02, 2x6 8.31, 3x4 8.39, 4x4 10.1
+    if (v == 3) launch_tma<AER, LMAX, 3, 4>(t, in, out, w, s);
+    else launch_tma<AER, LMAX, 2, 4>(t, in, out, w, s);
+}
+
 int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
-    // variant 1 (default): warp-local g-sums; 0: block-level g-sums (two barriers per 16 levels)
+    // variant 2 (default): TMA-fed ring of 2 stages x 4 layers, warp-local g-sums; 3: 3 stages; 1: direct loads, warp-local
+    // g-sums; 0: direct loads, block-level g-sums (two barriers per 16 levels)
+    if (g_tune.lw_rtrn_variant >= 2) {
+        const int v = g_tune.lw_rtrn_variant;
+        if (w.nlay <= 64) { if (in.tauaer) launch_tma_pick<true, 64>(t, in, out, w, s, v); else launch_tma_pick<false, 64>(t, in, out, w, s, v); }
+        else { if (in.tauaer) launch_tma_pick<true, MAXLAY>(t, in, out, w, s, v); else launch_tma_pick<false, MAXLAY>(t, in, out, w, s, v); }
+        return 1;
+    }
     const bool wr = g_tune.lw_rtrn_variant != 0;
     const size_t smem = (size_t)(2 * w.nlay + 1) * 16 * sizeof(double) + (size_t)g_tune.lw_rtrn_pad_kb * 1024;
 #define RT_LAUNCH(A, W) do { \
