@@ -366,7 +366,12 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
     const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
     const double *taer = AER ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
     double *wt = s_tile + wid * 8 * RT_WS + lane + (lane >> 4);
-    auto release = [&](int, int st) {           // this warp has read everything it needs from stage `st`
+    // This warp has read everything it needs from stage `st`.  The arrival goes through the barrier unit, not the
+    // load/store queue, so it must not be issued before the shared-memory loads have RETURNED (measured: without
+    // this, 1-3 columns per 16384 saw a stage refilled under their loads).  The caller pins the values computed
+    // from the stage with keep() (an empty asm that consumes the register) before calling release().
+    auto keep = [](double v) { asm volatile("" ::"d"(v) : "memory"); };
+    auto release = [&](int st) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
     };
@@ -391,7 +396,9 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
             double bbu;
             lw_layer<true>(et, bpade, secd, tg, frv[j], blay, spv[(r + 1) * 16] - blay, spv[r * 16] - blay, at[j], bd[j], bbu);
         }
-        release(q, st);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { keep(at[j]); keep(bd[j]); }      // every load of the stage feeds these
+        release(st);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             if (j < n) {
@@ -434,7 +441,9 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
             double bbd;
             lw_layer<false>(et, bpade, secd, tg, sfr[r * NGPTLW], blay, spv[(r + 1) * 16] - blay, 0.0, at[j], bbd, bu[j]);
         }
-        release(q, st);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { keep(at[j]); keep(bu[j]); }      // every load of the stage feeds these
+        release(st);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             if (j < n) {

@@ -108,3 +108,48 @@ def test_run_rrtmg_argument_errors(gpu):
     assert e.value.code == 4
     with pytest.raises(ValueError):
         rr.run_rrtmg(1, 1, (0, 0), *args)
+
+
+def test_run_rrtmg_row_block_pipeline_is_bitwise_invariant(gpu):
+    """The host-pointer entry cuts the grid into blocks of latitude rows (two-stage pipeline); every quantity of
+    run_rrtmg is local to a row, so any block size must give bit-identical results -- also with zonal means."""
+    from mima_b200 import rrtm_radiation as rr
+    g = make_gcm_state("T42L40", nlon=32, nlat=16)
+    args = (g["lat"], g["lon"], g["p_full"], g["p_half"], g["albedo"], g["q"], g["t"], g["t_surf"], g["tdt"])
+    for cfg in (rr.RadConfig(co2ppmv=390.0, lonstep=2, do_rad_time_avg=False),
+                rr.RadConfig(co2ppmv=390.0, do_zm_tracers=True, do_zm_rad=True)):
+        ref = rr.run_rrtmg(1, 1, (3600, 77), *args, cfg=cfg, z_full=g["z_full"], z_half=g["z_half"], o3f=g["o3f"], diagnostics=True)
+        for chunk in (32, 96, 200):
+            gpu.set_option("chunk", chunk)
+            try:
+                out = rr.run_rrtmg(1, 1, (3600, 77), *args, cfg=cfg, z_full=g["z_full"], z_half=g["z_half"], o3f=g["o3f"],
+                                   diagnostics=True)
+            finally:
+                gpu.set_option("chunk", 0)
+            for a, b in zip(ref[:4], out[:4]):
+                assert np.array_equal(a, b)
+            for k in ref[4]:
+                assert np.array_equal(ref[4][k], out[4][k]), k
+
+
+def test_run_rrtmg_full_size_t170(gpu):
+    """BASELINE config 3 (512 x 256 x 60) through the driver: finite, tendency = SW + LW parts, surface and TOA
+    diagnostics consistent, daily-mean sun never negative, polar night has no SW heating."""
+    from mima_b200 import rrtm_radiation as rr
+    g = make_gcm_state("T170L60")
+    cfg = rr.RadConfig(co2ppmv=390.0)
+    tdt, cz, fsw, flw, d = rr.run_rrtmg(1, 1, (0, 180), g["lat"], g["lon"], g["p_full"], g["p_half"], g["albedo"], g["q"], g["t"],
+                                        g["t_surf"], g["tdt"], cfg=cfg, z_full=g["z_full"], z_half=g["z_half"], o3f=g["o3f"],
+                                        diagnostics=True)
+    for a in (tdt, cz, fsw, flw, d["tdt_sw"], d["tdt_lw"], d["olr"], d["isr"]):
+        assert np.isfinite(a).all()
+    np.testing.assert_allclose(tdt, d["tdt_sw"] + d["tdt_lw"], rtol=1e-12, atol=1e-18)
+    np.testing.assert_array_equal(tdt, d["tdt_rad"])
+    assert (cz >= 0).all() and cz.max() <= 1.0
+    night = cz == 0.0
+    assert night.any()                                  # day 180 - 90 = northern solstice: southern polar night
+    assert (fsw[night] == 0).all() and (d["isr"][night] == 0).all() and (d["tdt_sw"][night] == 0).all()
+    # isr is the NET incoming SW at the top (down minus reflected, rrtm_radiation.f90:716): positive, below S0 cos(z)
+    assert (d["isr"][~night] > 0).all() and (d["isr"] <= cfg.solr_cnst * cz * (1 + 2e-5)).all()
+    assert (fsw <= d["isr"] * (1 + 1e-12)).all()            # the surface absorbs no more than enters at the top
+    assert (flw > 50).all() and (d["olr"] > 50).all()
