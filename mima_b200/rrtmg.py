@@ -99,7 +99,9 @@ _loaded = set()
 
 
 def _default_tables(kind: str):
-    files = {"lw": ["rrtmg_lw_ref.bin", "rrtmg_lw_kg_synth.bin"], "sw": ["rrtmg_sw_kg.bin"]}[kind]
+    # the real LW coefficients (tools/build_tables.py with MIMA_LW_KG=.../rrtmg_lw_k_g.f90) win over the synthetic blob
+    lw_kg = "rrtmg_lw_kg.bin" if os.path.exists(os.path.join(DATA_DIR, "rrtmg_lw_kg.bin")) else "rrtmg_lw_kg_synth.bin"
+    files = {"lw": ["rrtmg_lw_ref.bin", lw_kg], "sw": ["rrtmg_sw_kg.bin"]}[kind]
     for f in files:
         if f not in _loaded:
             load_tables(os.path.join(DATA_DIR, f))

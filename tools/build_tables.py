@@ -361,6 +361,72 @@ def build_lw_synth(seed=20240917):
     return out
 
 
+LW_ORIGINALS = ("selfrefo", "forrefo", "fracrefao", "fracrefbo", "ccl4o", "cfc11adjo", "cfc12o", "cfc22adjo")
+
+
+def lw_decls(b, params):
+    """The unreduced (16 g-point) arrays of LW band b as LW/modules/rrlw_kgNN.f90 declares them."""
+    decls = parse_decls(os.path.join(LW, f"modules/rrlw_kg{b:02d}.f90"), dict(params))
+    return {n: d for n, d in decls.items() if d[0] and (n.startswith(("kao", "kbo")) or n in LW_ORIGINALS)}
+
+
+def lw_params():
+    params = {}
+    for l in open(os.path.join(LW, "modules/parrrtm.f90")):
+        m = re.match(r"\s*integer\(kind=im\)\s*,\s*parameter\s*::\s*(\w+)\s*=\s*(\d+)", strip_comment(l))
+        if m:
+            params[m.group(1)] = int(m.group(2))
+    return params
+
+
+def build_lw_real(kg_path):
+    """Parse the real LW k-distribution file LW/src/rrtmg_lw_k_g.f90 (AER RRTMG_LW v4.85; subroutines lw_kgb01..16,
+    the same `name(:, j, k, ig) = (/ ... /)` literal format as rrtmg_sw_k_g.f90) into the lwNN.* arrays of the blob.
+    The file is stripped from the reference checkout (.MISSING_LARGE_BLOBS): this runs wherever it is available
+    (MIMA_LW_KG=/path/to/rrtmg_lw_k_g.f90) and is exercised here by a round trip through write_kg_fortran()."""
+    params = lw_params()
+    subs = split_subroutines(kg_path, r"lw_kgb(\d+)")
+    out = {}
+    for b in range(1, 17):
+        want = lw_decls(b, params)
+        arrs = parse_assignments(subs[f"{b:02d}"], want)
+        for n, a in arrs.items():
+            assert not np.isnan(a).any(), (b, n, int(np.isnan(a).sum()))
+            out[f"lw{b:02d}.{n}"] = a
+    return out
+
+
+def write_kg_fortran(path, arrays, prefix="lw", digits=17):
+    """Write arrays {"lwNN.name": ndarray} as Fortran source in the k_g literal format (one assignment per leading
+    column, continuation lines of five values, `_rb` kind suffix, subscripts with the declared lower bounds, e.g.
+    kbo(:, jt, 13:59, ig)).  Test helper for build_lw_real()."""
+    params = lw_params()
+    lows_of = {}
+    for b in range(1, 17):
+        for n, (shape, lows) in lw_decls(b, params).items():
+            lows_of[f"lw{b:02d}.{n}"] = lows
+    bands = sorted({k.split(".")[0] for k in arrays})
+    with open(path, "w") as f:
+        for bk in bands:
+            f.write(f"      subroutine {prefix}_kgb{bk[len(prefix):]}\n      implicit none\n      save\n\n")
+            for key in sorted(k for k in arrays if k.startswith(bk + ".")):
+                name = key.split(".")[1]
+                a = np.asfortranarray(arrays[key])
+                lead = a.shape[0]
+                rest = a.shape[1:]
+                for idx in np.ndindex(*rest[::-1]) if rest else [()]:
+                    idx = idx[::-1]
+                    col = a[(slice(None),) + idx]
+                    lows = lows_of.get(key, (1,) * a.ndim)
+                    sl = ",".join([":"] + [str(i + lows[d + 1]) for d, i in enumerate(idx)])
+                    f.write(f"      {name}({sl}) = (/ &\n")
+                    vals = [f"{v:.{digits}e}_rb" for v in col]
+                    for i in range(0, lead, 5):
+                        tail = ", &" if i + 5 < lead else " /)"
+                        f.write("        & " + ",".join(vals[i:i + 5]) + tail + "\n")
+            f.write("\n      end subroutine " + f"{prefix}_kgb{bk[len(prefix):]}\n\n")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sw = build_sw()
@@ -369,6 +435,13 @@ def main():
     write_blob(os.path.join(OUT, "rrtmg_lw_ref.bin"), lwref)
     lw = build_lw_synth()
     write_blob(os.path.join(OUT, "rrtmg_lw_kg_synth.bin"), lw)
+    # the real LW coefficients, wherever the file exists (it is stripped from the reference checkout)
+    kg = os.environ.get("MIMA_LW_KG", os.path.join(LW, "src/rrtmg_lw_k_g.f90"))
+    if os.path.exists(kg):
+        write_blob(os.path.join(OUT, "rrtmg_lw_kg.bin"), build_lw_real(kg))
+        print("wrote rrtmg_lw_kg.bin from", kg)
+    else:
+        print("no rrtmg_lw_k_g.f90 at", kg, "-> LW stays on the synthetic blob")
     # round-trip check
     for fn, src in (("rrtmg_sw_kg.bin", sw), ("rrtmg_lw_ref.bin", lwref), ("rrtmg_lw_kg_synth.bin", lw)):
         back = read_blob(os.path.join(OUT, fn))
