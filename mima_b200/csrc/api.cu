@@ -484,6 +484,9 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
     // per-cell setcoef state is only materialised for the stage-capture test hook
     w.idx = fields ? c.take<uint32_t>(np) : nullptr;
     w.f = fields ? c.take<double>(np * LF_COUNT) : nullptr;
+    w.cs_coldry = c.take<double>(np);
+    w.cs_wkl1 = c.take<double>(np);
+    w.cs_lower = c.take<unsigned char>(np);
     w.secdiff = c.take<double>((size_t)nc * 16);
     w.planklay = c.take<double>(np * 16);
     w.planklev = c.take<double>((size_t)nc * (nlay + 1) * 16);
@@ -499,6 +502,7 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
     const size_t np = (size_t)nc * nlay;
     w.laytrop = c.take<int>(nc);
     w.laysolfr = c.take<int>((size_t)nc * 14);
+    w.cs_jp = c.take<unsigned char>(np);
     w.idx = fields ? c.take<uint32_t>(np) : nullptr;
     w.f = fields ? c.take<double>(np * SF_COUNT) : nullptr;
     w.taug = c.take<double>(np * NGPTSW);

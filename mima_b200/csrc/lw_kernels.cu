@@ -2,8 +2,8 @@
 //
 // What is computed follows the reference routines (cited per kernel); how it is computed is a
 // GPU-first design:
-//   lw_prep_kernel    thread <-> column, one sweep over layers: unit conversion, column amounts,
-//                     p/T interpolation indices and weights, Planck sources.  Coalesced column-major reads.
+//   lw_prep_cell_kernel  thread <-> (column, layer): unit conversion, column amounts, Planck sources;
+//   lw_prep_kernel    thread <-> column: the column sums (laytrop, precipitable water -> secant), surface Planck terms.
 //   lw_taumol_kernel  thread <-> (column, layer) cell, lanes = 32 adjacent columns; blockIdx.z selects a band
 //                     slice, so that the blocks resident on an SM at any time run the same few bands (their
 //                     code fits the instruction cache and their k-tables the L1).  Terms of the band
@@ -150,6 +150,71 @@ __device__ __forceinline__ bool lw_cell(const LwIn &in, int col, int l, LwPair &
 //       diffusivity secant per band (rtrnmr.f90:259-280) -- and the Planck sources (setcoef.f90:154-249).
 //       With w.f != nullptr (stage capture, test hook) the per-cell setcoef state is also written out.
 // =====================================================================================================
+// Stage 1, thread <-> (column, layer) cell (lanes = adjacent columns): everything that is local to the cell -- the
+// Planck sources of the layer and of its upper interface, and the three numbers the column sums need (dry column,
+// H2O column, "below 100 hPa" flag).  60x more threads than a thread-per-column sweep: at T42 (8192 columns) the
+// old kernel occupied 64 of the 148 SMs with one latency-bound warp each.
+__global__ void __launch_bounds__(128) lw_prep_cell_kernel(LwTables T, LwIn in, LwWork w)
+{
+    const int nc = w.nc, nlay = w.nlay;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nc * nlay) return;
+    const int l = (int)(i / nc);
+    const int col = (int)(i - (size_t)l * nc);
+    const size_t ld = (size_t)in.ld;
+    const size_t o = col + (size_t)l * ld;
+    LwPair p;
+    double wkl1;
+    const bool lower = lw_cell(in, col, l, p, wkl1);
+    w.cs_coldry[i] = p.coldry;
+    w.cs_wkl1[i] = wkl1;
+    w.cs_lower[i] = lower ? 1 : 0;
+    if (w.f) {
+        const size_t wo = i;
+        w.idx[wo] = lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm);
+        w.fld(LF_FAC00)[wo] = p.fac00; w.fld(LF_FAC01)[wo] = p.fac01;
+        w.fld(LF_FAC10)[wo] = p.fac10; w.fld(LF_FAC11)[wo] = p.fac11;
+        w.fld(LF_COLH2O)[wo] = p.colh2o; w.fld(LF_COLCO2)[wo] = p.colco2; w.fld(LF_COLO3)[wo] = p.colo3;
+        w.fld(LF_COLN2O)[wo] = p.coln2o; w.fld(LF_COLCO)[wo] = p.colco; w.fld(LF_COLCH4)[wo] = p.colch4;
+        w.fld(LF_COLO2)[wo] = p.colo2; w.fld(LF_COLBRD)[wo] = p.colbrd;
+        w.fld(LF_SELFFAC)[wo] = p.selffac; w.fld(LF_SELFFRAC)[wo] = p.selffrac;
+        w.fld(LF_FORFAC)[wo] = p.forfac; w.fld(LF_FORFRAC)[wo] = p.forfrac;
+        w.fld(LF_MINORFRAC)[wo] = p.minorfrac; w.fld(LF_SCALEMINOR)[wo] = p.scaleminor;
+        w.fld(LF_SCALEMINORN2)[wo] = p.scaleminorn2; w.fld(LF_COLDRY)[wo] = p.coldry;
+        w.fld(LF_PAVEL)[wo] = p.pavel;
+        w.fld(LF_WX1)[wo] = p.wx1; w.fld(LF_WX2)[wo] = p.wx2; w.fld(LF_WX3)[wo] = p.wx3; w.fld(LF_WX4)[wo] = p.wx4;
+    }
+    // ---- setcoef: Planck sources (setcoef.f90:154-249)
+    const double tavel = in.tlay[o], tz = in.tlev[o + ld];
+    int indlay = (int)(tavel - 159.);
+    indlay = indlay < 1 ? 1 : (indlay > 180 ? 180 : indlay);
+    const double tlayfrac = tavel - 159. - (double)indlay;
+    int indlev = (int)(tz - 159.);
+    indlev = indlev < 1 ? 1 : (indlev > 180 ? 180 : indlev);
+    const double tlevfrac = tz - 159. - (double)indlev;
+    double2 *play2 = reinterpret_cast<double2 *>(w.planklay + ((size_t)col * nlay + l) * 16);
+    double2 *plev2 = reinterpret_cast<double2 *>(w.planklev + ((size_t)col * (nlay + 1) + l + 1) * 16);
+#pragma unroll 2
+    for (int ib = 0; ib < 16; ib += 2) {
+        double2 a, b;
+        const double *tp = T.totplnk + ib * 181;
+        double d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
+        a.x = __ldg(tp + indlay - 1) + tlayfrac * d;
+        d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
+        b.x = __ldg(tp + indlev - 1) + tlevfrac * d;
+        tp += 181;
+        d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
+        a.y = __ldg(tp + indlay - 1) + tlayfrac * d;
+        d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
+        b.y = __ldg(tp + indlev - 1) + tlevfrac * d;
+        play2[ib >> 1] = a;
+        plev2[ib >> 1] = b;
+    }
+}
+
+// Stage 2, thread <-> column: the column-integrated quantities in the reference's summation order -- laytrop
+// (setcoef.f90:293-294), precipitable water and the diffusivity secant per band (rtrnmr.f90:259-280) -- and the
+// surface / level-0 Planck terms.
 __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWork w)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,55 +249,12 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
             pl0[ib] = __ldg(tp + indlev0 - 1) + t0frac * dbdtlev;
         }
     }
-
     for (int l = 0; l < nlay; ++l) {
-        const size_t o = col + (size_t)l * ld;
-        LwPair p;
-        double wkl1;
-        if (lw_cell(in, col, l, p, wkl1)) laytrop = laytrop + 1;
-        amttl = amttl + p.coldry + wkl1;
+        const size_t i = (size_t)l * nc + col;
+        const double wkl1 = w.cs_wkl1[i];
+        if (w.cs_lower[i]) laytrop = laytrop + 1;
+        amttl = amttl + w.cs_coldry[i] + wkl1;
         wvttl = wvttl + wkl1;
-        if (w.f) {
-            const size_t wo = (size_t)l * nc + col;
-            w.idx[wo] = lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm);
-            w.fld(LF_FAC00)[wo] = p.fac00; w.fld(LF_FAC01)[wo] = p.fac01;
-            w.fld(LF_FAC10)[wo] = p.fac10; w.fld(LF_FAC11)[wo] = p.fac11;
-            w.fld(LF_COLH2O)[wo] = p.colh2o; w.fld(LF_COLCO2)[wo] = p.colco2; w.fld(LF_COLO3)[wo] = p.colo3;
-            w.fld(LF_COLN2O)[wo] = p.coln2o; w.fld(LF_COLCO)[wo] = p.colco; w.fld(LF_COLCH4)[wo] = p.colch4;
-            w.fld(LF_COLO2)[wo] = p.colo2; w.fld(LF_COLBRD)[wo] = p.colbrd;
-            w.fld(LF_SELFFAC)[wo] = p.selffac; w.fld(LF_SELFFRAC)[wo] = p.selffrac;
-            w.fld(LF_FORFAC)[wo] = p.forfac; w.fld(LF_FORFRAC)[wo] = p.forfrac;
-            w.fld(LF_MINORFRAC)[wo] = p.minorfrac; w.fld(LF_SCALEMINOR)[wo] = p.scaleminor;
-            w.fld(LF_SCALEMINORN2)[wo] = p.scaleminorn2; w.fld(LF_COLDRY)[wo] = p.coldry;
-            w.fld(LF_PAVEL)[wo] = p.pavel;
-            w.fld(LF_WX1)[wo] = p.wx1; w.fld(LF_WX2)[wo] = p.wx2; w.fld(LF_WX3)[wo] = p.wx3; w.fld(LF_WX4)[wo] = p.wx4;
-        }
-        // ---- setcoef: Planck sources
-        const double tavel = in.tlay[o], tz = in.tlev[o + ld];
-        int indlay = (int)(tavel - 159.);
-        indlay = indlay < 1 ? 1 : (indlay > 180 ? 180 : indlay);
-        const double tlayfrac = tavel - 159. - (double)indlay;
-        int indlev = (int)(tz - 159.);
-        indlev = indlev < 1 ? 1 : (indlev > 180 ? 180 : indlev);
-        const double tlevfrac = tz - 159. - (double)indlev;
-        double2 *play2 = reinterpret_cast<double2 *>(w.planklay + ((size_t)col * nlay + l) * 16);
-        double2 *plev2 = reinterpret_cast<double2 *>(w.planklev + ((size_t)col * (nlay + 1) + l + 1) * 16);
-#pragma unroll 2
-        for (int ib = 0; ib < 16; ib += 2) {
-            double2 a, b;
-            const double *tp = T.totplnk + ib * 181;
-            double d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
-            a.x = __ldg(tp + indlay - 1) + tlayfrac * d;
-            d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
-            b.x = __ldg(tp + indlev - 1) + tlevfrac * d;
-            tp += 181;
-            d = __ldg(tp + indlay) - __ldg(tp + indlay - 1);
-            a.y = __ldg(tp + indlay - 1) + tlayfrac * d;
-            d = __ldg(tp + indlev) - __ldg(tp + indlev - 1);
-            b.y = __ldg(tp + indlev - 1) + tlevfrac * d;
-            play2[ib >> 1] = a;
-            plev2[ib >> 1] = b;
-        }
     }
     w.laytrop[col] = laytrop;
     // precipitable water and diffusivity secant per band
@@ -769,6 +791,7 @@ __global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTab
 int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, double *cap)
 {
     ktimer_begin(K_LW_PREP, s);
+    lw_prep_cell_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(t, in, w);
     lw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(t, in, w);
     ktimer_end(s);
     {
@@ -787,7 +810,7 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
     ktimer_begin(K_LW_RTRN, s);
     const int nrt = lw_launch_rtrn(t, in, out, w, s);
     ktimer_end(s);
-    return 2 + nrt;
+    return 3 + nrt;
 }
 
 } // namespace rrtmg

@@ -94,6 +94,8 @@ struct LwWork {
     int nc, nlay;
     uint32_t *idx;            // [lay][col]
     int *laytrop;             // [col]
+    double *cs_coldry, *cs_wkl1;   // [lay][col]: per-cell terms of the column sums (lw_prep_cell -> lw_prep)
+    unsigned char *cs_lower;       // [lay][col]: plog > 4.56
     double *f;                // LF_COUNT fields, each [lay][col]
     double *secdiff;          // [col][16]
     double *planklay;         // [col][lay][16]
@@ -158,6 +160,7 @@ struct SwWork {
     int nc, nlay;
     uint32_t *idx;            // [lay][col]
     int *laytrop;             // [col]
+    unsigned char *cs_jp;     // [lay][col]: jp | 0x80 * (plog > 4.56)  (sw_prep_cell -> sw_prep)
     int *laysolfr;            // [col][14]: layer (1-based) whose eta selects the solar source; 0 = never written
     double *f;                // SF_COUNT fields, each [lay][col]
     double *taug;             // [col][lay][112]

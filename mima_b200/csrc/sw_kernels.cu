@@ -122,6 +122,33 @@ __device__ __forceinline__ bool sw_cell(const SwIn &in, int col, int l, SwPair &
 //       selects the solar source of each band (SW/src/rrtmg_sw_taumol.f90, "laysolfr" logic).
 //       With w.f != nullptr (stage capture, test hook) the per-cell setcoef state is also written out.
 // =====================================================================================================
+// Stage 1, thread <-> (column, layer): the cell's reference-pressure index and "below 100 hPa" flag (setcoef),
+// which is all the column logic below needs; stage capture also dumps the full setcoef state here.
+__global__ void __launch_bounds__(128) sw_prep_cell_kernel(SwIn in, SwWork w)
+{
+    const int nc = w.nc, nlay = w.nlay;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nc * nlay) return;
+    const int l = (int)(i / nc);
+    const int col = (int)(i - (size_t)l * nc);
+    if (in.coszen[col] < ZEPZEN) return;       // night column: nothing downstream reads it
+    SwPair p;
+    const bool lower = sw_cell(in, col, l, p);
+    w.cs_jp[i] = (unsigned char)(p.jp | (lower ? 0x80 : 0));
+    if (w.f) {
+        const size_t wo = i;
+        w.idx[wo] = sw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf);
+        w.fld(SF_FAC00)[wo] = p.fac00; w.fld(SF_FAC01)[wo] = p.fac01;
+        w.fld(SF_FAC10)[wo] = p.fac10; w.fld(SF_FAC11)[wo] = p.fac11;
+        w.fld(SF_COLH2O)[wo] = p.colh2o; w.fld(SF_COLCO2)[wo] = p.colco2; w.fld(SF_COLO3)[wo] = p.colo3;
+        w.fld(SF_COLCH4)[wo] = p.colch4; w.fld(SF_COLO2)[wo] = p.colo2; w.fld(SF_COLMOL)[wo] = p.colmol;
+        w.fld(SF_COLN2O)[wo] = p.coln2o;
+        w.fld(SF_SELFFAC)[wo] = p.selffac; w.fld(SF_SELFFRAC)[wo] = p.selffrac;
+        w.fld(SF_FORFAC)[wo] = p.forfac; w.fld(SF_FORFRAC)[wo] = p.forfrac;
+    }
+}
+
+// Stage 2, thread <-> column.
 __global__ void __launch_bounds__(128) sw_prep_kernel(SwIn in, SwWork w)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,20 +162,9 @@ __global__ void __launch_bounds__(128) sw_prep_kernel(SwIn in, SwWork w)
     int laytrop = 0;
     jpv[0] = 0;
     for (int l = 0; l < nlay; ++l) {
-        SwPair p;
-        if (sw_cell(in, col, l, p)) laytrop = laytrop + 1;
-        jpv[l + 1] = (unsigned char)p.jp;
-        if (w.f) {
-            const size_t wo = (size_t)l * nc + col;
-            w.idx[wo] = sw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf);
-            w.fld(SF_FAC00)[wo] = p.fac00; w.fld(SF_FAC01)[wo] = p.fac01;
-            w.fld(SF_FAC10)[wo] = p.fac10; w.fld(SF_FAC11)[wo] = p.fac11;
-            w.fld(SF_COLH2O)[wo] = p.colh2o; w.fld(SF_COLCO2)[wo] = p.colco2; w.fld(SF_COLO3)[wo] = p.colo3;
-            w.fld(SF_COLCH4)[wo] = p.colch4; w.fld(SF_COLO2)[wo] = p.colo2; w.fld(SF_COLMOL)[wo] = p.colmol;
-            w.fld(SF_COLN2O)[wo] = p.coln2o;
-            w.fld(SF_SELFFAC)[wo] = p.selffac; w.fld(SF_SELFFRAC)[wo] = p.selffrac;
-            w.fld(SF_FORFAC)[wo] = p.forfac; w.fld(SF_FORFRAC)[wo] = p.forfrac;
-        }
+        const unsigned char v = w.cs_jp[(size_t)l * nc + col];
+        if (v & 0x80) laytrop = laytrop + 1;
+        jpv[l + 1] = (unsigned char)(v & 0x7f);
     }
     jpv[nlay + 1] = 0;
     w.laytrop[col] = laytrop;
@@ -541,6 +557,7 @@ __global__ void sw_expand_taur_kernel(SwTables T, SwWork w)
 int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
     ktimer_begin(K_SW_PREP, s);
+    sw_prep_cell_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(in, w);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
     ktimer_end(s);
     {
@@ -555,7 +572,7 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_begin(K_SW_SOLVER, s);
     const int nsv = sw_launch_solver(t, in, out, w, s);
     ktimer_end(s);
-    return 2 + nsv;
+    return 3 + nsv;
 }
 
 } // namespace rrtmg
