@@ -49,6 +49,7 @@ struct State {
     long launches = 0;
     int chunk = 0;
     int host_chunk = 0;
+    int run_chunk = 0;
     bool capture = false;
     // LW
     bool lw_ready = false;
@@ -683,7 +684,7 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
 int host_chunk(int ncol)
 {
     if (G.capture) return ncol;                        // stage dumps need the whole batch in one pass
-    int hc = G.host_chunk > 0 ? G.host_chunk : 8192;
+    int hc = G.host_chunk > 0 ? G.host_chunk : 16384;     // measured e2e at T170L60: 4096 53.6, 8192 48.0, 16384 47.3, 32768 50.0 ms
     if (G.chunk > 0 && G.chunk < hc) hc = G.chunk;     // option "chunk" bounds every device pass
     return hc < ncol ? hc : ncol;
 }
@@ -1328,7 +1329,8 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     // i+1 and the D2H copy of block i-1 overlap the kernels of block i.  Everything in run_rrtmg is local to a
     // latitude row (the zonal means too), and a row block of an (si, sj, n) field is n runs of si*rows doubles.
     const size_t np_all = (size_t)si * sj, L = sk, V = sk + 1;
-    int target = G.chunk > 0 ? G.chunk : 32768;                   // RRTMG columns per block
+    int target = G.run_chunk > 0 ? G.run_chunk : 16384;           // RRTMG columns per block (e2e at T170L60: 8192 44.7, 16384 44.3, 32768 45.2 ms)
+    if (G.chunk > 0 && G.chunk < target) target = G.chunk;
     int rows = (int)((long)target * cfg->lonstep / si);
     if (rows < 1) rows = 1;
     if (rows > sj) rows = sj;
@@ -1386,6 +1388,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     const std::string k(key ? key : "");
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
     if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
+    if (k == "run_chunk") { G.run_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
