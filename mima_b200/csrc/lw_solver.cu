@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
     __shared__ __align__(8) uint64_t s_full[NST], s_empty[NST];
     __shared__ double s_tile[RT_WARPS * 8 * RT_WS];
     __shared__ double s_part[RT_WARPS * 2 * (LMAX + 1)];
-    __shared__ double s_dn[LMAX + 1], s_up[LMAX + 1];
+    static_assert(2 * (LMAX + 1) <= RT_WARPS * 8 * RT_WS, "the level fluxes reuse the tile storage");
+    double *s_dn = s_tile, *s_up = s_tile + LMAX + 1;           // only used after the sweeps
     const int col = blockIdx.x;
     const int nlay = w.nlay;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -366,12 +367,16 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
     const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
     const double *taer = AER ? in.tauaer + col + (size_t)band * nlay * in.ld : nullptr;
     double *wt = s_tile + wid * 8 * RT_WS + lane + (lane >> 4);
-    // This warp has read everything it needs from stage `st`.  The arrival goes through the barrier unit, not the
-    // load/store queue, so it must not be issued before the shared-memory loads have RETURNED (measured: without
-    // this, 1-3 columns per 16384 saw a stage refilled under their loads).  The caller pins the values computed
-    // from the stage with keep() (an empty asm that consumes the register) before calling release().
+    // This warp has read everything it needs from stage `st`.  The stage is then overwritten through the ASYNC proxy
+    // (TMA) while it was read through the generic proxy: the release needs fence.proxy.async before the arrival.
+    // Without it 1-3 columns per 16384 saw a stage refilled under their loads in about one call out of thirty
+    // (tools/stress_lw.py; tests/test_gpu_parity.py::test_repeated_calls_are_bitwise_reproducible).  The caller also
+    // pins the values computed from the stage with keep() (an empty asm that consumes the register) so that the
+    // shared-memory loads have returned before the arrival is issued.
     auto keep = [](double v) { asm volatile("" ::"d"(v) : "memory"); };
     auto release = [&](int st) {
+        // generic-proxy reads of the stage -> async-proxy (TMA) overwrite: cross-proxy ordering needs the proxy fence
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
     };
@@ -498,6 +503,7 @@ template <bool AER, int LMAX>
 static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, int v)
 {
     // measured at T170L60 (stages x layers per stage): 2x4 7.60 ms, 2x3 7.68, 3x3 7.77, 2x5 8.02, 2x6 8.31, 3x4 8.39, 4x4 10.1
+    // (a 56-register build that fits six blocks per SM measured 8.4 ms)
     if (v == 3) launch_tma<AER, LMAX, 3, 4>(t, in, out, w, s);
     else launch_tma<AER, LMAX, 2, 4>(t, in, out, w, s);
 }
