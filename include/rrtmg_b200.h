@@ -33,7 +33,7 @@
  *
  * Error behaviour: every function returns 0 on success or one of RRTMG_B200_ERR_*; nothing is ever
  * computed on the CPU and there is no fallback path.  The Fortran `stop 'PARTIAL CLOUD NOT ALLOWED'`
- * (SW rad.nomcica:537) and the unrestated branches (icld > 0, idrv = 1, SW iaer != 0) map to error codes.
+ * (SW rad.nomcica:537) and the unrestated branches (icld > 0, SW iaer != 0) map to error codes.
  */
 #ifndef RRTMG_B200_H
 #define RRTMG_B200_H
@@ -44,7 +44,7 @@ extern "C" {
 
 #define RRTMG_B200_OK 0
 #define RRTMG_B200_ERR_NOT_INITIALIZED 1 /* init not called (cf. FATAL at rrtm_radiation.f90:527-528) */
-#define RRTMG_B200_ERR_UNSUPPORTED 2     /* icld > 0, idrv = 1, SW iaer != 0: branch not built yet */
+#define RRTMG_B200_ERR_UNSUPPORTED 2     /* icld > 0, SW iaer != 0: branch not built yet */
 #define RRTMG_B200_ERR_PARTIAL_CLOUD 3   /* SW rad.nomcica:537 */
 #define RRTMG_B200_ERR_BAD_ARGUMENT 4
 #define RRTMG_B200_ERR_CUDA 5            /* see rrtmg_b200_last_error() */
@@ -85,7 +85,7 @@ long rrtmg_b200_launch_count(void);
  * play,tlay,h2ovmr..ccl4vmr,cldfr,cicewp,cliqwp,reice,reliq (ncol,nlay); plev,tlev (ncol,nlay+1);
  * tsfc (ncol); emis (ncol,16); taucld (16,ncol,nlay); tauaer (ncol,nlay,16);
  * uflx,dflx,uflxc,dflxc (ncol,nlay+1) W/m2; hr,hrc (ncol,nlay) K/day;
- * duflx_dt,duflxc_dt (ncol,nlay+1) only written when idrv == 1 (unsupported -> error). */
+ * duflx_dt,duflxc_dt (ncol,nlay+1) [W/m2/K]: written when idrv == 1 (then required), ignored for idrv == 0. */
 int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                   const double *play, const double *plev, const double *tlay, const double *tlev,
                   const double *tsfc,

@@ -364,13 +364,17 @@ int lw_init_impl(double cpdair)
         HostArr &he = G.reduced["lw.exp_tbl"]; he.dims = {NTBL + 1}; he.data = ex;
         HostArr &ht = G.reduced["lw.tfn_tbl"]; ht.dims = {NTBL + 1}; ht.data = tf;
     }
-    if (G.lw_tab.ensure(tab.size() * 8) || G.lw_totplnk.ensure(181 * 16 * 8) || G.lw_exptfn.ensure(et.size() * 8))
+    const HostArr *totplnkderiv = find("lwref.totplnkderiv");
+    if (!totplnkderiv || totplnkderiv->size() != 181 * 16) return fail(RRTMG_B200_ERR_TABLES, "lwref.totplnkderiv missing");
+    if (G.lw_tab.ensure(tab.size() * 8) || G.lw_totplnk.ensure(2 * 181 * 16 * 8) || G.lw_exptfn.ensure(et.size() * 8))
         return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for LW tables");
     CUDA_OK(cudaMemcpy(G.lw_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(G.lw_totplnk.p, totplnk->data.data(), 181 * 16 * 8, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(G.lw_exptfn.p, et.data(), et.size() * 8, cudaMemcpyHostToDevice));
     G.lwt.tab = (const double *)G.lw_tab.p;
+    CUDA_OK(cudaMemcpy((double *)G.lw_totplnk.p + 181 * 16, totplnkderiv->data.data(), 181 * 16 * 8, cudaMemcpyHostToDevice));
     G.lwt.totplnk = (const double *)G.lw_totplnk.p;
+    G.lwt.totplnkderiv = (const double *)G.lw_totplnk.p + 181 * 16;
     G.lwt.exptfn = (const double *)G.lw_exptfn.p;
     if (lw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_lw) failed");
     G.lw_ready = true;
@@ -485,6 +489,8 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
     // per-cell setcoef state is only materialised for the stage-capture test hook
     w.idx = fields ? c.take<uint32_t>(np) : nullptr;
     w.f = fields ? c.take<double>(np * LF_COUNT) : nullptr;
+    w.idrv = 0;
+    w.dplankbnd = c.take<double>((size_t)nc * 16);
     w.cs_coldry = c.take<double>(np);
     w.cs_wkl1 = c.take<double>(np);
     w.cs_lower = c.take<unsigned char>(np);
@@ -527,7 +533,7 @@ int lw_validate(int ncol, int nlay, int *icld, int idrv)
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;     // LW rad.nomcica:437
     if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: icld > 0 (cloudy-sky branch) is not built");
-    if (idrv != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: idrv = 1 (flux derivatives) is not built");
+    if (idrv != 0 && idrv != 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv must be 0 or 1");
     return RRTMG_B200_OK;
 }
 int sw_validate(int ncol, int nlay, int *icld, int *iaer)
@@ -547,6 +553,7 @@ int lw_chunk(const LwIn &in, const LwOut &out, int nc, int nlay, void *work, boo
 {
     LwWork w;
     lw_carve(w, work, nc, nlay, fields);
+    w.idrv = out.duflx_dt ? 1 : 0;
     double *cap = nullptr;
     if (fields) {
         if (G.lw_cap.ensure(2 * (size_t)nc * nlay * NGPTLW * 8)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (capture)");
@@ -572,6 +579,7 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
 {
     DevBuf &wk = work ? *work : G.lw_work;
     if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
+    if (idrv == 1 && (!out0.duflx_dt || !out0.duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     LwWork w;
@@ -586,6 +594,7 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
         OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
 #undef OFF
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
+        if (out.duflx_dt) { out.duflx_dt += c0; out.duflxc_dt += c0; }
         if (const int rc = lw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
     }
     return RRTMG_B200_OK;
@@ -1017,7 +1026,7 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
                          const double *, const double *,
                          const double *tauaer,
                          double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
-                         double *, double *, void *stream)
+                         double *duflx_dt, double *duflxc_dt, void *stream)
 {
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
         !uflxc || !dflxc || !hrc)
@@ -1025,6 +1034,7 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
     LwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer};
     LwOut out{ncol, uflx, dflx, hr, uflxc, dflxc, hrc};
+    if (idrv == 1) { out.duflx_dt = duflx_dt; out.duflxc_dt = duflxc_dt; }
     return lw_device_impl(ncol, nlay, icld, idrv, in, out, (cudaStream_t)stream);
 }
 
@@ -1041,18 +1051,18 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                   double *duflx_dt, double *duflxc_dt)
 {
     (void)inflglw; (void)iceflglw; (void)liqflglw; (void)cldfr; (void)taucld; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
-    (void)duflx_dt; (void)duflxc_dt;
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
         !uflxc || !dflxc || !hrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
     if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
+    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
     if (ncol == 0) return RRTMG_B200_OK;
     if (P_lw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
     const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L) * 8 + 32 * 256;
-    const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
+    const size_t out_bytes = (size_t)hc * (6 * V + 2 * L) * 8 + 10 * 256;
     LwWork wsz;
     const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields);
     const int nslot = hc < ncol ? 2 : 1;
@@ -1071,7 +1081,9 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
         if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
         Slot o{(char *)P_lw.out[slot].p, 0, c0, nc, ncol, st, true};
         LwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
+        if (idrv == 1) { out.duflx_dt = o.take(V); out.duflxc_dt = o.take(V); }
         if (const int rc = lw_chunk(in, out, nc, nlay, P_lw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
+        if (idrv == 1) { o.down(duflx_dt, out.duflx_dt, V); o.down(duflxc_dt, out.duflxc_dt, V); }
         o.down(uflx, out.uflx, V); o.down(dflx, out.dflx, V); o.down(hr, out.hr, L);
         o.down(uflxc, out.uflxc, V); o.down(dflxc, out.dflxc, V); o.down(hrc, out.hrc, L);
         if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)");

@@ -247,6 +247,11 @@ __global__ void __launch_bounds__(128) lw_prep_kernel(LwTables T, LwIn in, LwWor
             pb[ib] = semiss * (__ldg(tp + indbound - 1) + tbndfrac * dbdtlev);
             dbdtlev = __ldg(tp + indlev0) - __ldg(tp + indlev0 - 1);
             pl0[ib] = __ldg(tp + indlev0 - 1) + t0frac * dbdtlev;
+            if (w.idrv) {       // setcoef.f90:197-201
+                const double *td = T.totplnkderiv + ib * 181;
+                dbdtlev = __ldg(td + indbound) - __ldg(td + indbound - 1);
+                w.dplankbnd[(size_t)col * 16 + ib] = semiss * (__ldg(td + indbound - 1) + tbndfrac * dbdtlev);
+            }
         }
     }
     for (int l = 0; l < nlay; ++l) {

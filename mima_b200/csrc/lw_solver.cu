@@ -324,7 +324,10 @@ __device__ __forceinline__ void tma_issue(const LwWork &w, int col, int nlay, in
     tma_load_1d(d + 2 * CH * NGPTLW + CH * 16, gv, (uint32_t)((n + 1) * 128), bar);
 }
 
-template <bool AER, int LMAX, int NST, int CH>
+// DRV (idrv = 1): also the derivative of the upward flux with respect to the surface temperature
+// (rtrnmr.f90:629-646, 686-689, 736-746): d_radlu_dt starts as fracs(1) * dplankbnd_dt and is attenuated by
+// (1 - atrans) per layer; its g-sums go through a second warp tile.
+template <bool AER, int LMAX, int NST, int CH, bool DRV>
 __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
 {
     constexpr int STAGE = TmaGeom<CH>::STAGE;
@@ -333,6 +336,8 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
     __shared__ double s_tile[RT_WARPS * 8 * RT_WS];
     __shared__ double s_part[RT_WARPS * 2 * (LMAX + 1)];
     static_assert(2 * (LMAX + 1) <= RT_WARPS * 8 * RT_WS, "the level fluxes reuse the tile storage");
+    __shared__ double s_dtile[DRV ? RT_WARPS * 8 * RT_WS : 1];
+    __shared__ double s_dpart[DRV ? RT_WARPS * (LMAX + 1) : 1];
     double *s_dn = s_tile, *s_up = s_tile + LMAX + 1;           // only used after the sweeps
     const int col = blockIdx.x;
     const int nlay = w.nlay;
@@ -428,6 +433,12 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
         radlu = rad0 + (1. - semiss) * radld;
         wt[0] = radlu * wgt;
     }
+    double drad = 0.0;
+    double *dwt = s_dtile + (DRV ? wid * 8 * RT_WS + lane + (lane >> 4) : 0);
+    if (DRV) {
+        drad = plfrac1 * w.dplankbnd[(size_t)col * 16 + band];
+        dwt[0] = drad * wgt;
+    }
     // upward sweep (:649-711)
     for (; q < 2 * nd; ++q) {
         const int st = q % NST, it = q / NST;
@@ -455,10 +466,18 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
                 const int k = lo + j + 1;
                 radlu = radlu + (bu[j] - radlu) * at[j];
                 wt[(k & 7) * RT_WS] = radlu * wgt;
+                if (DRV) {
+                    drad = drad * (1.0 - at[j]);
+                    dwt[(k & 7) * RT_WS] = drad * wgt;
+                }
                 if ((k & 7) == 7 || k == nlay) {
                     const double sum = warp_rows8(s_tile + wid * 8 * RT_WS, lane);
                     const int kk = (k & ~7) + (lane >> 2);
                     if ((lane & 3) == 0 && kk <= k) s_part[(wid * 2 + 1) * (LMAX + 1) + kk] = sum;
+                    if (DRV) {
+                        const double dsum = warp_rows8(s_dtile + wid * 8 * RT_WS, lane);
+                        if ((lane & 3) == 0 && kk <= k) s_dpart[wid * (LMAX + 1) + kk] = dsum;
+                    }
                 }
             }
         }
@@ -489,6 +508,14 @@ __global__ void __launch_bounds__(RT_THREADS + 32) lw_rtrn_tma_kernel(LwTables T
             out.hr[o] = h;
             out.hrc[o] = h;
         }
+        if (DRV) {
+            double dd = 0.0;
+#pragma unroll
+            for (int i = 0; i < RT_WARPS; ++i) dd += s_dpart[i * (LMAX + 1) + lev];
+            dd = dd * c_ls.fluxfac;
+            out.duflx_dt[o] = dd;
+            out.duflxc_dt[o] = dd;
+        }
     }
 }
 
@@ -496,8 +523,13 @@ template <bool AER, int LMAX, int NST, int CH>
 static void launch_tma(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
     const size_t smem = (size_t)NST * TmaGeom<CH>::STAGE * sizeof(double);
-    cudaFuncSetAttribute(lw_rtrn_tma_kernel<AER, LMAX, NST, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lw_rtrn_tma_kernel<AER, LMAX, NST, CH><<<w.nc, RT_THREADS + 32, smem, s>>>(t, in, out, w);
+    if (w.idrv) {
+        cudaFuncSetAttribute(lw_rtrn_tma_kernel<AER, LMAX, NST, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lw_rtrn_tma_kernel<AER, LMAX, NST, CH, true><<<w.nc, RT_THREADS + 32, smem, s>>>(t, in, out, w);
+        return;
+    }
+    cudaFuncSetAttribute(lw_rtrn_tma_kernel<AER, LMAX, NST, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lw_rtrn_tma_kernel<AER, LMAX, NST, CH, false><<<w.nc, RT_THREADS + 32, smem, s>>>(t, in, out, w);
 }
 template <bool AER, int LMAX>
 static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, int v)
@@ -512,7 +544,7 @@ int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &
 {
     // variant 2 (default): TMA-fed ring of 2 stages x 4 layers, warp-local g-sums; 3: 3 stages; 1: direct loads, warp-local
     // g-sums; 0: direct loads, block-level g-sums (two barriers per 16 levels)
-    if (g_tune.lw_rtrn_variant >= 2) {
+    if (g_tune.lw_rtrn_variant >= 2 || w.idrv) {        // the derivative outputs are built in the TMA kernel only
         const int v = g_tune.lw_rtrn_variant;
         if (w.nlay <= 64) { if (in.tauaer) launch_tma_pick<true, 64>(t, in, out, w, s, v); else launch_tma_pick<false, 64>(t, in, out, w, s, v); }
         else { if (in.tauaer) launch_tma_pick<true, MAXLAY>(t, in, out, w, s, v); else launch_tma_pick<false, MAXLAY>(t, in, out, w, s, v); }

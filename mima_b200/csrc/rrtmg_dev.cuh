@@ -75,6 +75,7 @@ struct LwConst {
 struct LwTables {             // device pointers
     const double *tab;        // all band tables, [row][rs] (band bases 128-byte aligned)
     const double *totplnk;    // (181,16) column-major as in the Fortran
+    const double *totplnkderiv;   // (181,16): d(totplnk)/dT for idrv = 1
     const double *exptfn;     // interleaved {exp_tbl[i], tfn_tbl[i]}, i = 0..NTBL
 };
 
@@ -88,10 +89,13 @@ struct LwIn {                 // interface arrays of the current pass (device po
 struct LwOut {
     int ld;
     double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc;
+    double *duflx_dt = nullptr, *duflxc_dt = nullptr;   // (ld, nlay+1), written when idrv == 1
 };
 
 struct LwWork {
     int nc, nlay;
+    int idrv;                 // 1: also dF_up/dT_surface (rad.nomcica:143-152)
+    double *dplankbnd;        // [col][16]: semiss * d(Planck)/dT at the surface temperature (idrv = 1)
     uint32_t *idx;            // [lay][col]
     int *laytrop;             // [col]
     double *cs_coldry, *cs_wkl1;   // [lay][col]: per-cell terms of the column sums (lw_prep_cell -> lw_prep)

@@ -164,8 +164,10 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
              inflglw=0, iceflglw=0, liqflglw=0, cldfr=None,
              taucld=None, cicewp=None, cliqwp=None, reice=None, reliq=None,
              tauaer=None):
-    """Returns (uflx, dflx, hr, uflxc, dflxc, hrc); fluxes (ncol, nlay+1) W/m2, heating (ncol, nlay) K/day.
-    ch4vmr..ccl4vmr, emis, tauaer may be None (zeros / emissivity 1).  Cloud arrays are ignored (icld=0)."""
+    """Returns (uflx, dflx, hr, uflxc, dflxc, hrc); fluxes (ncol, nlay+1) W/m2, heating (ncol, nlay) K/day; with
+    idrv = 1 also (duflx_dt, duflxc_dt), the change of the upward flux per K of surface temperature (W/m2/K,
+    rad.nomcica:143-152, the Fortran's optional dummies).  ch4vmr..ccl4vmr, emis, tauaer may be None (zeros /
+    emissivity 1).  Cloud arrays are ignored (icld=0)."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
     keep = []
@@ -183,10 +185,12 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
     taer, ptaer = _in(tauaer, (ncol, nlay, NBNDLW), "tauaer", True)
     out = [np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F"),
            np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
+    if int(idrv) == 1:
+        out += [np.empty(V, order="F"), np.empty(V, order="F")]
     icld_c = C.c_int(int(icld))
     rc = lib().rrtmg_b200_lw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.c_int(int(idrv)), *ptrs,
                              C.c_int(inflglw), C.c_int(iceflglw), C.c_int(liqflglw), None, None, None, None, None, None,
-                             ptaer, *[o.ctypes.data_as(_dp) for o in out], None, None)
+                             ptaer, *[o.ctypes.data_as(_dp) for o in out], *([] if int(idrv) == 1 else [None, None]))
     _check(rc)
     return tuple(out)
 
@@ -233,8 +237,8 @@ def _opt(a):
     return None if (a is None or not np.any(a)) else a
 
 
-def lw_from_columns(c, tauaer=None):
-    return rrtmg_lw(c.ncol, c.nlay, 0, 0, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
+def lw_from_columns(c, tauaer=None, idrv=0):
+    return rrtmg_lw(c.ncol, c.nlay, 0, idrv, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), _opt(c.cfc11), _opt(c.cfc12), _opt(c.cfc22), _opt(c.ccl4),
                     None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer)
 

@@ -1,5 +1,5 @@
 /*
- * lw.c -- oracle restatement of RRTMG_LW as linked by MiMA (clear sky, icld=0, idrv=0).
+ * lw.c -- oracle restatement of RRTMG_LW as linked by MiMA (clear sky, icld=0; idrv = 0 and 1).
  * TEST INFRASTRUCTURE ONLY (see rrtmg_oracle.h).
  *
  * Follows  LW/src/rrtmg_lw_rad.nomcica.f90:80-569  (rrtmg_lw), :572-901 (inatm)
@@ -39,6 +39,8 @@ typedef struct {
     double wkl[8][NL], wx[5][NL], pwvcm, semiss[17], taua[NL][17];
     int jp[NL], jt[NL], jt1[NL], indself[NL], indfor[NL], indminor[NL];
     double planklay[NL][17], planklev[NL][17], plankbnd[17];
+    int idrv;
+    double dplankbnd_dt[17], dtotuflux_dt[NL], dtotuclfl_dt[NL];   /* idrv = 1 (setcoef.f90:197-201, rtrnmr.f90:629-742) */
     double colh2o[NL], colco2[NL], colo3[NL], coln2o[NL], colco[NL], colch4[NL], colo2[NL], colbrd[NL];
     double fac00[NL], fac01[NL], fac10[NL], fac11[NL];
     double rat_h2oco2[NL], rat_h2oco2_1[NL], rat_h2oo3[NL], rat_h2oo3_1[NL];
@@ -135,6 +137,7 @@ static void setcoef(lwcol_t *c, int istart)
     double stpfac, tbndfrac, t0frac, tlayfrac, tlevfrac, dbdtlev, dbdtlay;
     double plog, fp, ft, ft1, water, scalefac, factor, compfp;
 #define TOTPLNK(i, b) F2(S->totplnk, 181, i, b)
+#define TOTPLNKDERIV(i, b) F2(S->totplnkderiv, 181, i, b)
     (void)istart;
     stpfac = 296. / 1013.;
 
@@ -165,6 +168,10 @@ static void setcoef(lwcol_t *c, int istart)
                 c->plankbnd[iband] = c->semiss[iband] * (TOTPLNK(indbound, iband) + tbndfrac * dbdtlev);
                 dbdtlev = TOTPLNK(indlev0 + 1, iband) - TOTPLNK(indlev0, iband);
                 c->planklev[0][iband] = TOTPLNK(indlev0, iband) + t0frac * dbdtlev;
+                if (c->idrv == 1) { /* :197-201, :238-242 */
+                    dbdtlev = TOTPLNKDERIV(indbound + 1, iband) - TOTPLNKDERIV(indbound, iband);
+                    c->dplankbnd_dt[iband] = c->semiss[iband] * (TOTPLNKDERIV(indbound, iband) + tbndfrac * dbdtlev);
+                }
             }
             dbdtlev = TOTPLNK(indlev + 1, iband) - TOTPLNK(indlev, iband);
             dbdtlay = TOTPLNK(indlay + 1, iband) - TOTPLNK(indlay, iband);
@@ -985,6 +992,8 @@ static void rtrnmr_clear(lwcol_t *c)
     static const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
     static const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
     double secdiff[17], atrans[NL], bbugas[NL], urad[NL], drad[NL], clrurad[NL], clrdrad[NL];
+    double d_urad_dt[NL], d_clrurad_dt[NL];
+    const int idrv = c->idrv;
     double uflux, dflux, uclfl, dclfl;
     int igc, itr, lev, iband, ibnd, l;
 
@@ -1001,6 +1010,10 @@ static void rtrnmr_clear(lwcol_t *c)
     for (lev = 0; lev <= nlayers; ++lev) {
         urad[lev] = 0.0; drad[lev] = 0.0; clrurad[lev] = 0.0; clrdrad[lev] = 0.0;
         c->totuflux[lev] = 0.0; c->totdflux[lev] = 0.0; c->totuclfl[lev] = 0.0; c->totdclfl[lev] = 0.0;
+        if (idrv == 1) { /* :292-315 */
+            d_urad_dt[lev] = 0.0; d_clrurad_dt[lev] = 0.0;
+            c->dtotuflux_dt[lev] = 0.0; c->dtotuclfl_dt[lev] = 0.0;
+        }
     }
     igc = 1;
     for (iband = 1; iband <= 16; ++iband) {
@@ -1039,15 +1052,32 @@ static void rtrnmr_clear(lwcol_t *c)
             reflect = 1. - c->semiss[iband];
             radlu = rad0 + reflect * radld;
             radclru = rad0 + reflect * radclrd;
+            double d_rad0_dt = 0., d_radlu_dt = 0., d_radclru_dt = 0.;
+            if (idrv == 1) d_rad0_dt = c->fracs[igc][1] * c->dplankbnd_dt[iband];   /* :629-631 */
             urad[0] = urad[0] + radlu;
             clrurad[0] = clrurad[0] + radclru;
+            if (idrv == 1) { /* :642-647 */
+                d_radlu_dt = d_rad0_dt;
+                d_urad_dt[0] = d_urad_dt[0] + d_radlu_dt;
+                d_radclru_dt = d_rad0_dt;
+                d_clrurad_dt[0] = d_clrurad_dt[0] + d_radclru_dt;
+            }
             /* upward loop (:649-711), clear-layer branch :682-701 */
             for (lev = 1; lev <= nlayers; ++lev) {
                 radlu = radlu + (bbugas[lev] - radlu) * atrans[lev];
                 urad[lev] = urad[lev] + radlu;
+                if (idrv == 1) { /* clear layer :686-689 */
+                    d_radlu_dt = d_radlu_dt * (1.0 - atrans[lev]);
+                    d_urad_dt[lev] = d_urad_dt[lev] + d_radlu_dt;
+                }
                 radclru = radlu;
                 clrurad[lev] = urad[lev];
+                if (idrv == 1) { /* iclddn = 0 branch :706-709 */
+                    d_radclru_dt = d_radlu_dt;
+                    d_clrurad_dt[lev] = d_urad_dt[lev];
+                }
             }
+            (void)d_radclru_dt;
             igc = igc + 1;
         } while (igc <= ngs[iband - 1]);
 
@@ -1065,6 +1095,16 @@ static void rtrnmr_clear(lwcol_t *c)
             clrdrad[lev] = 0.0;
             c->totuclfl[lev] = c->totuclfl[lev] + uclfl * delwave[iband - 1];
             c->totdclfl[lev] = c->totdclfl[lev] + dclfl * delwave[iband - 1];
+        }
+        if (idrv == 1) { /* :736-746 */
+            for (lev = nlayers; lev >= 0; --lev) {
+                double duflux_dt = d_urad_dt[lev] * wtdiff;
+                d_urad_dt[lev] = 0.0;
+                c->dtotuflux_dt[lev] = c->dtotuflux_dt[lev] + duflux_dt * delwave[iband - 1] * c->fluxfac;
+                double duclfl_dt = d_clrurad_dt[lev] * wtdiff;
+                d_clrurad_dt[lev] = 0.0;
+                c->dtotuclfl_dt[lev] = c->dtotuclfl_dt[lev] + duclfl_dt * delwave[iband - 1] * c->fluxfac;
+            }
         }
     }
     /* fluxes and heating rates (:751-777) */
@@ -1106,10 +1146,12 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                 double *duflx_dt, double *duflxc_dt,
                  const orc_lw_stages_t *st, int nthreads)
 {
     if (!g_orc.ready) return 1;
-    if (icld != 0 || idrv != 0) return 2; /* cloudy / derivative branches are not restated */
+    if (icld != 0 || idrv < 0 || idrv > 1) return 2; /* the cloudy branches are not restated */
+    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return 3;
     if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
     if (nthreads < 1) nthreads = 1;
     const int iaer = 10; /* forced (:442) */
@@ -1129,6 +1171,7 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
 #pragma omp for schedule(static)
 #endif
         for (int iplon = 1; iplon <= ncol; ++iplon) {
+            c->idrv = idrv;
             inatm(c, iplon, ncol, nlay, iaer, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr,
                   n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer);
             /* cldprop with cldfrac=0: ncbands=1, taucloud=0 -- nothing to compute */
@@ -1153,6 +1196,11 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                 hr[(long)k * ncol + i0] = c->htr[k];
                 hrc[(long)k * ncol + i0] = c->htrc[k];
             }
+            if (idrv == 1) /* rad.nomcica:559-564 */
+                for (int k = 0; k <= nlay; ++k) {
+                    duflx_dt[(long)k * ncol + i0] = c->dtotuflux_dt[k];
+                    duflxc_dt[(long)k * ncol + i0] = c->dtotuclfl_dt[k];
+                }
             if (st) {
 #define PUT(dst, src) if (st->dst) for (int l = 1; l <= nlay; ++l) st->dst[(long)(l - 1) * ncol + i0] = c->src[l]
                 if (st->laytrop) st->laytrop[i0] = c->laytrop;

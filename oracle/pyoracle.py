@@ -76,7 +76,7 @@ class Oracle:
         return np.ctypeslib.as_array(p, shape=(n,)).copy()
 
     # ------------------------------------------------------------------ LW
-    def rrtmg_lw(self, cols, *, stages: bool = False, nthreads: int | None = None, tauaer=None):
+    def rrtmg_lw(self, cols, *, stages: bool = False, nthreads: int | None = None, tauaer=None, idrv: int = 0):
         ncol, nlay = cols.ncol, cols.nlay
         nthreads = nthreads or self.max_threads
         out = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("uflx", "dflx", "uflxc", "dflxc")}
@@ -100,9 +100,13 @@ class Oracle:
         ins = [_f(x) for x in (cols.play, cols.plev, cols.tlay, cols.tlev, cols.tsfc, cols.h2o, cols.o3, cols.co2,
                                cols.ch4, cols.n2o, cols.o2, cols.cfc11, cols.cfc12, cols.cfc22, cols.ccl4,
                                cols.emis, tauaer)]
-        rc = self.lib.orc_rrtmg_lw(C.c_int(ncol), C.c_int(nlay), C.c_int(0), C.c_int(0), *[_p(a) for a in ins],
+        if idrv:
+            out.update({k: np.zeros((ncol, nlay + 1), order="F") for k in ("duflx_dt", "duflxc_dt")})
+        rc = self.lib.orc_rrtmg_lw(C.c_int(ncol), C.c_int(nlay), C.c_int(0), C.c_int(int(idrv)), *[_p(a) for a in ins],
                                    _p(out["uflx"]), _p(out["dflx"]), _p(out["hr"]), _p(out["uflxc"]),
-                                   _p(out["dflxc"]), _p(out["hrc"]), stp, C.c_int(nthreads))
+                                   _p(out["dflxc"]), _p(out["hrc"]),
+                                   _p(out["duflx_dt"]) if idrv else None, _p(out["duflxc_dt"]) if idrv else None,
+                                   stp, C.c_int(nthreads))
         if rc:
             raise RuntimeError(f"orc_rrtmg_lw rc={rc}")
         if stages:

@@ -78,6 +78,7 @@ typedef struct {
     double lw_heatfac;
     double lw_pref[59], lw_preflog[59], lw_tref[59], chi_mls[7 * 59];
     double totplnk[181 * 16], totplk16[181];
+    double totplnkderiv[181 * 16];   /* rrtmg_lw_setcoef.f90 lwavplankderiv: d(totplnk)/dT, for idrv = 1 */
     double lw_rwgt[16 * 16];
     double tau_tbl[ORC_NTBL + 1], exp_tbl[ORC_NTBL + 1], tfn_tbl[ORC_NTBL + 1];
     double lw_bpade;
@@ -134,6 +135,7 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
+                 double *duflx_dt, double *duflxc_dt, /* (ncol, nlay+1), written when idrv == 1; may be NULL otherwise */
                  const orc_lw_stages_t *stages, int nthreads);
 
 /* rrtmg_sw (SW/src/rrtmg_sw_rad.nomcica.f90:78-731); icld=0, iaer=0 only. */

@@ -290,6 +290,7 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
     rc |= copy_arr(&bref, "lwref.tref", S->lw_tref, 59);
     rc |= copy_arr(&bref, "lwref.chi_mls", S->chi_mls, 7 * 59);
     rc |= copy_arr(&bref, "lwref.totplnk", S->totplnk, 181 * 16);
+    rc |= copy_arr(&bref, "lwref.totplnkderiv", S->totplnkderiv, 181 * 16);
     rc |= copy_arr(&bref, "lwref.totplk16", S->totplk16, 181);
     rc |= copy_arr(&bsw, "swref.pref", S->sw_pref, 59);
     rc |= copy_arr(&bsw, "swref.preflog", S->sw_preflog, 59);

@@ -186,8 +186,8 @@ def test_unsupported_options_fail_loudly(gpu):
         gpu.rrtmg_lw(c.ncol, c.nlay, 1, 0, *args, None, None, None, None, None)
     assert e.value.code == 2
     with pytest.raises(gpu.RRTMGError) as e:
-        gpu.rrtmg_lw(c.ncol, c.nlay, 0, 1, *args, None, None, None, None, None)
-    assert e.value.code == 2
+        gpu.rrtmg_lw(c.ncol, c.nlay, 0, 2, *args, None, None, None, None, None)      # idrv must be 0 or 1
+    assert e.value.code == 4
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_sw(c.ncol, c.nlay, 0, 10, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
     assert e.value.code == 2
@@ -236,3 +236,27 @@ def test_repeated_calls_are_bitwise_reproducible(gpu):
         sw = gpu.sw_from_columns(c)
         for a, b in zip(sw0, sw):
             assert np.array_equal(a, b)
+
+
+def test_idrv1_flux_derivative(gpu, oracle):
+    """idrv = 1 (rad.nomcica:143-152; setcoef.f90:197-201; rtrnmr.f90:629-746): the upward-flux derivative with respect
+    to the surface temperature.  GPU vs oracle at 1e-9, the six standard outputs unchanged bit for bit, and the
+    derivative against a centred finite difference of the forward model (known answer independent of the restatement;
+    3e-3: the Planck table is piecewise linear in 1 K steps)."""
+    import dataclasses
+    c = make_columns("T170L60", nlon=64, nlat=4)
+    rng = np.random.default_rng(11)
+    c.emis = np.asfortranarray(rng.uniform(0.9, 1.0, (c.ncol, 16)))
+    got = gpu.lw_from_columns(c, idrv=1)
+    ref = oracle.rrtmg_lw(c, idrv=1)
+    base = gpu.lw_from_columns(c)
+    for a, b in zip(got[:6], base):
+        assert np.array_equal(a, b)
+    for g, n in zip(got[6:], ("duflx_dt", "duflxc_dt")):
+        r = np.max(np.abs(g - ref[n]) / np.abs(ref[n]).max())
+        assert r < 1e-9, (n, float(r))
+    up = gpu.lw_from_columns(dataclasses.replace(c, tsfc=c.tsfc + 0.5))[0]
+    dn = gpu.lw_from_columns(dataclasses.replace(c, tsfc=c.tsfc - 0.5))[0]
+    fd = up - dn
+    assert np.max(np.abs(fd - got[6])) < 3e-3 * np.abs(fd).max()
+    assert (got[6] > 0).all() and (np.diff(got[6], axis=1) <= 1e-12).all()      # attenuated on the way up
