@@ -762,7 +762,7 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
 // independent warps the kernel was bound by instruction-cache misses.  Work items are (32-column tile,
 // layer) pairs, linearised so that no warp idles when nlay is not a multiple of the block's warp count.
 constexpr int TM_BLOCK_WARPS = 8;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTab
     double *slab = s_dyn + (size_t)wid * (64 * TM_STRIDE);
     const size_t colstride = (size_t)nlay * NGPTLW;
     const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTLW;
-#define LW_BAND(b) lw_band<b>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid); __syncthreads()
+#define LW_BAND(b) lw_band<b>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
     LW_BAND(0); LW_BAND(1); LW_BAND(2); LW_BAND(3); LW_BAND(4); LW_BAND(5); LW_BAND(6); LW_BAND(7);
     LW_BAND(8); LW_BAND(9); LW_BAND(10); LW_BAND(11); LW_BAND(12); LW_BAND(13); LW_BAND(14); LW_BAND(15);
 #undef LW_BAND
@@ -804,7 +804,7 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
         const size_t smem = (size_t)TM_BLOCK_WARPS * 64 * TM_STRIDE * sizeof(double);
         cudaFuncSetAttribute(lw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ktimer_begin(K_LW_TAUMOL, s);
-        lw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w);
+        lw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1);
         ktimer_end(s);
     }
     if (cap) {

@@ -276,7 +276,7 @@ void ktimer_end(cudaStream_t s);
 
 // launch tuning (api.cu; option keys "lw_rtrn_pad_kb", "sw_solver_pad_kb", "sw_solver_store", "sw_solver_variant"): extra dynamic shared memory per block,
 // used to cap the resident blocks per SM so that the sweeps' per-thread state stays L2-resident
-struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant, lw_rtrn_variant; };
+struct Tuning { int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant, lw_rtrn_variant, taumol_sync; };
 extern Tuning g_tune;
 
 // solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)

@@ -496,7 +496,7 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
 // As in the LW kernel: 16 warps per block step through the bands together (instruction-cache reuse);
 // work items are linearised (32-column tile, layer) pairs.
 constexpr int TM_BLOCK_WARPS = 4;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTab
     double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
     const size_t colstride = (size_t)nlay * NGPTSW;
     const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTSW;
-#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, t24, sflx, cell0, colstride, vmask); __syncthreads()
+#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, t24, sflx, cell0, colstride, vmask); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
     SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
     SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
 #undef SW_BAND
@@ -565,7 +565,7 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
         const size_t smem = (size_t)TM_BLOCK_WARPS * 32 * TM_STRIDE * sizeof(double);
         cudaFuncSetAttribute(sw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ktimer_begin(K_SW_TAUMOL, s);
-        sw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w);
+        sw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1);
         ktimer_end(s);
     }
     if (w.taur) sw_expand_taur_kernel<<<1184, 256, 0, s>>>(t, w);
