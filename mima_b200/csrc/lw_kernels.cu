@@ -762,7 +762,7 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
 // independent warps the kernel was bound by instruction-cache misses.  Work items are (32-column tile,
 // layer) pairs, linearised so that no warp idles when nlay is not a multiple of the block's warp count.
 constexpr int TM_BLOCK_WARPS = 8;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 3) lw_taumol_kernel(LwTables T, LwIn in, LwWork w, int g_tm_sync)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -496,7 +496,7 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
 // As in the LW kernel: 16 warps per block step through the bands together (instruction-cache reuse);
 // work items are linearised (32-column tile, layer) pairs.
 constexpr int TM_BLOCK_WARPS = 4;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 6) sw_taumol_kernel(SwTables T, SwIn in, SwWork w, int g_tm_sync)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
