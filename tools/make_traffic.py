@@ -12,6 +12,7 @@ for f in sys.argv[3:]:
     rows = list(csv.reader(open(f)))
     hdr, units = rows[0], rows[1]
     i = {h: k for k, h in enumerate(hdr)}
+    seen = set()
     for r in rows[2:]:
         k = next((v for n, v in names.items() if n in r[i["Kernel Name"]]), None)
         if not k:
@@ -19,12 +20,24 @@ for f in sys.argv[3:]:
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd = float(r[i["dram__bytes_read.sum"]]) * scale[units[i["dram__bytes_read.sum"]]]
         wr = float(r[i["dram__bytes_write.sum"]]) * scale[units[i["dram__bytes_write.sum"]]]
-        out[W][k] = {"dram_bytes_per_column": (rd + wr) / ncol, "dram_read_bytes": rd, "dram_write_bytes": wr,
-                     "columns_per_launch": ncol, "duration_ms_under_ncu": float(r[i["gpu__time_duration.sum"]]),
-                     "fp64_pipe_pct": float(r[i["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
-                     "l1tex_throughput_pct": float(r[i["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]]),
-                     "dram_throughput_pct": float(r[i["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
-                     "issue_active_pct": float(r[i["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
-                     "registers_per_thread": int(float(r[i["launch__registers_per_thread"]])), "source": os.path.basename(f)}
+        dur = float(r[i["gpu__time_duration.sum"]])
+        e = {"dram_bytes_per_column": (rd + wr) / ncol, "dram_read_bytes": rd, "dram_write_bytes": wr,
+             "columns_per_launch": ncol, "duration_ms_under_ncu": dur,
+             "fp64_pipe_pct": float(r[i["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
+             "l1tex_throughput_pct": float(r[i["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]]),
+             "dram_throughput_pct": float(r[i["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+             "issue_active_pct": float(r[i["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+             "registers_per_thread": int(float(r[i["launch__registers_per_thread"]])), "source": os.path.basename(f),
+             "kernels": [r[i["Kernel Name"]].split("(")[0]]}
+        if k in seen:          # a step made of two kernels (prep: per cell + per column): add traffic and time,
+            p = out[W][k]      # keep the utilisation figures of the longer one
+            for key in ("dram_bytes_per_column", "dram_read_bytes", "dram_write_bytes", "duration_ms_under_ncu"):
+                e[key] += p[key]
+            if p["duration_ms_under_ncu"] > dur:
+                for key in ("fp64_pipe_pct", "l1tex_throughput_pct", "dram_throughput_pct", "issue_active_pct", "registers_per_thread"):
+                    e[key] = p[key]
+            e["kernels"] = p["kernels"] + e["kernels"]
+        out[W][k] = e
+        seen.add(k)
 json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
 print(json.dumps(out[W], indent=1))
