@@ -62,7 +62,7 @@ struct State {
     bool sw_ready = false;
     SwConst swc;
     SwTables swt{};
-    DevBuf sw_tab, sw_exptbl, sw_work;
+    DevBuf sw_tab, sw_exptbl, sw_work, sw_err;
     SwWork sw_last{};
     int sw_last_ncol = 0;
 };
@@ -502,7 +502,7 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
     w.fracs = c.take<double>(np * NGPTLW);
     return c.off + 256;
 }
-size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
+size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool general = false)
 {
     Carver c(base);
     w.nc = nc; w.nlay = nlay;
@@ -517,6 +517,9 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields)
     w.taur24 = c.take<double>(np * 8);
     w.taur = fields ? c.take<double>(np * NGPTSW) : nullptr;      // expanded from rdesc (test hook)
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
+    w.opt = general ? c.take<double>(np * 14 * 6) : nullptr;
+    w.clfr = general ? c.take<double>(np) : nullptr;
+    w.err = general ? (int *)G.sw_err.p : nullptr;
     return c.off + 256;
 }
 
@@ -536,14 +539,27 @@ int lw_validate(int ncol, int nlay, int *icld, int idrv)
     if (idrv != 0 && idrv != 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv must be 0 or 1");
     return RRTMG_B200_OK;
 }
-int sw_validate(int ncol, int nlay, int *icld, int *iaer)
+// the optional cloud / aerosol arguments of rrtmg_sw (host or device pointers, as the entry point's other arrays)
+struct SwOpt {
+    int inflgsw = 0;
+    const double *cldfr = nullptr, *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;
+    const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;
+};
+int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt())
 {
     if (!G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_sw_init has not been called");
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;                           // SW rad.nomcica:468
     if (iaer && *iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;            // SW rad.nomcica:473
-    if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: icld > 0 (cloudy-sky branch) is not built");
-    if (iaer && *iaer != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: iaer = 6/10 (aerosols) is not built");
+    if (icld && *icld != 0) {
+        if (o.inflgsw != 0)
+            return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: inflgsw > 0 (cloud optics from water paths, cldprop_sw parameterisations) is not built");
+        if (!o.cldfr || !o.taucld || !o.ssacld || !o.asmcld || !o.fsfcld)
+            return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: icld > 0 needs cldfr, taucld, ssacld, asmcld, fsfcld");
+    }
+    if (iaer && *iaer == 6) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: iaer = 6 (ECMWF aerosol climatology) is not built");
+    if (iaer && *iaer == 10 && (!o.tauaer || !o.ssaaer || !o.asmaer))
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: iaer = 10 needs tauaer, ssaaer, asmaer");
     return RRTMG_B200_OK;
 }
 
@@ -567,11 +583,29 @@ int lw_chunk(const LwIn &in, const LwOut &out, int nc, int nlay, void *work, boo
 int sw_chunk(const SwIn &in, const SwOut &out, int nc, int nlay, void *work, bool fields, cudaStream_t st, bool last)
 {
     SwWork w;
-    sw_carve(w, work, nc, nlay, fields);
+    sw_carve(w, work, nc, nlay, fields, in.icld >= 1 || in.iaer == 10);
     CUDA_OK(cudaMemsetAsync(w.sfluxzen, 0, (size_t)nc * NGPTSW * 8, st));
     G.launches += sw_run_pass(G.swt, in, out, w, st);
     CUDA_OK(cudaGetLastError());
     if (last) { G.sw_last = w; G.sw_last_ncol = fields ? nc : 0; }
+    return RRTMG_B200_OK;
+}
+
+// general SW path: the partial-cloud flag (SW rad.nomcica:534-539) lives in one device word, cleared before the first
+// pass and read back (one stream synchronisation) after the last
+int sw_err_begin(bool general)
+{
+    if (!general) return RRTMG_B200_OK;
+    if (G.sw_err.ensure(256)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed");
+    CUDA_OK(cudaMemset(G.sw_err.p, 0, 4));
+    return RRTMG_B200_OK;
+}
+int sw_err_end(bool general)
+{
+    if (!general) return RRTMG_B200_OK;
+    int flag = 0;
+    CUDA_OK(cudaMemcpy(&flag, G.sw_err.p, 4, cudaMemcpyDeviceToHost));
+    if (flag & 1) return fail(RRTMG_B200_ERR_PARTIAL_CLOUD, "rrtmg_sw: PARTIAL CLOUD NOT ALLOWED (0 < cldfr < 1 with icld > 0)");
     return RRTMG_B200_OK;
 }
 
@@ -600,15 +634,18 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
     return RRTMG_B200_OK;
 }
 
-int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st, DevBuf *work = nullptr)
+int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st, DevBuf *work = nullptr,
+                   const SwOpt &opt = SwOpt())
 {
     DevBuf &wk = work ? *work : G.sw_work;
-    if (const int rc = sw_validate(ncol, nlay, icld, iaer)) return rc;
+    if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
     SwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    if (wk.ensure(sw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
+    const bool general = in0.icld >= 1 || in0.iaer == 10;
+    if (const int rc = sw_err_begin(general)) return rc;
+    if (wk.ensure(sw_carve(w, nullptr, chunk, nlay, fields, general))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         SwIn in = in0;
@@ -616,11 +653,24 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
 #define OFF(p) if (in.p) in.p += c0
         OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
         OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
+        OFF(cldfr); OFF(tauaer); OFF(ssaaer); OFF(asmaer);
 #undef OFF
+#define OFF14(p) if (in.p) in.p += (size_t)14 * c0
+        OFF14(taucld); OFF14(ssacld); OFF14(asmcld); OFF14(fsfcld);
+#undef OFF14
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
         if (const int rc = sw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
     }
-    return RRTMG_B200_OK;
+    if (general) CUDA_OK(cudaStreamSynchronize(st));
+    return sw_err_end(general);
+}
+
+void sw_set_optional(SwIn &in, const int *icld, const int *iaer, const SwOpt &o)
+{
+    in.icld = icld ? *icld : 0;
+    in.iaer = iaer ? *iaer : 0;
+    if (in.icld >= 1) { in.cldfr = o.cldfr; in.taucld = o.taucld; in.ssacld = o.ssacld; in.asmcld = o.asmcld; in.fsfcld = o.fsfcld; }
+    if (in.iaer == 10) { in.tauaer = o.tauaer; in.ssaaer = o.ssaaer; in.asmaer = o.asmaer; }
 }
 
 // adjflux (SW rad.nomcica:953-972, earth_sun :734-758)
@@ -678,6 +728,16 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
         const cudaError_t e = (nc == ncol)
             ? cudaMemcpyAsync(d, h, (size_t)nc * rows * 8, cudaMemcpyHostToDevice, st)
             : cudaMemcpy2DAsync(d, (size_t)nc * 8, h + c0, (size_t)ncol * 8, (size_t)nc * 8, rows, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) ok = false;
+        return d;
+    }
+    const double *up_banded(const double *h, size_t nb, size_t rows)   // host (nb, ncol, rows) -> device (nb, nc, rows)
+    {
+        if (!h) return nullptr;
+        double *d = take(nb * rows);
+        const cudaError_t e = (nc == ncol)
+            ? cudaMemcpyAsync(d, h, (size_t)nc * nb * rows * 8, cudaMemcpyHostToDevice, st)
+            : cudaMemcpy2DAsync(d, (size_t)nc * nb * 8, h + nb * c0, (size_t)ncol * nb * 8, (size_t)nc * nb * 8, rows, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) ok = false;
         return d;
     }
@@ -981,7 +1041,7 @@ int rrtmg_b200_sw_init(double cpdair)
 int rrtmg_b200_finalize(void)
 {
     std::lock_guard<std::mutex> lk(G.mu);
-    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.sw_tab, &G.sw_exptbl, &G.sw_work})
+    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_err})
         b->release();
     P_lw.release();
     P_sw.release();
@@ -1098,19 +1158,23 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
                          const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                          const double *asdir, const double *asdif, const double *aldir, const double *aldif,
                          const double *coszen, double adjes, int dyofyr, double scon,
-                         int, int, int, const double *, const double *, const double *, const double *,
-                         const double *, const double *, const double *, const double *, const double *,
+                         int inflgsw, int, int, const double *cldfr,
+                         const double *taucld, const double *ssacld, const double *asmcld, const double *fsfcld,
                          const double *, const double *, const double *, const double *,
+                         const double *tauaer, const double *ssaaer, const double *asmaer, const double *,
                          double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                          double *swhrc, void *stream)
 {
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
+    SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer};
+    if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;       // also normalises *icld, *iaer
     SwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             asdir, asdif, aldir, aldif, coszen, sw_adjflux(adjes, dyofyr, scon)};
+    sw_set_optional(in, icld, iaer, opt);
     SwOut out{ncol, swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc};
-    return sw_device_impl(ncol, nlay, icld, iaer, in, out, (cudaStream_t)stream);
+    return sw_device_impl(ncol, nlay, icld, iaer, in, out, (cudaStream_t)stream, nullptr, opt);
 }
 
 int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
@@ -1125,21 +1189,23 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
                   const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                   double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc, double *swhrc)
 {
-    (void)inflgsw; (void)iceflgsw; (void)liqflgsw; (void)cldfr; (void)taucld; (void)ssacld; (void)asmcld; (void)fsfcld;
-    (void)cicewp; (void)cliqwp; (void)reice; (void)reliq; (void)tauaer; (void)ssaaer; (void)asmaer; (void)ecaer;
+    (void)iceflgsw; (void)liqflgsw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq; (void)ecaer;
+    const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer};
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
-    if (const int rc = sw_validate(ncol, nlay, icld, iaer)) return rc;
+    if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     if (P_sw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
+    const bool cloud = icld && *icld >= 1, aer = iaer && *iaer == 10, general = cloud || aer;
+    if (const int rc = sw_err_begin(general)) return rc;
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
-    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6) * 8 + 32 * 256;
+    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6 + (cloud ? 57 * L : 0) + (aer ? 42 * L : 0)) * 8 + 48 * 256;
     const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
     SwWork wsz;
-    const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields);
+    const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields, general);
     const int nslot = hc < ncol ? 2 : 1;
     for (int i = 0; i < nslot; ++i)
         if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes))
@@ -1160,9 +1226,17 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
         const double *d_aldir = aldir == asdir ? d_asdir : a.up(aldir, 1);
         const double *d_aldif = aldif == asdir ? d_asdir : (aldif == aldir ? d_aldir : a.up(aldif, 1));
         const double *d_cosz = a.up(coszen, 1);
+        SwOpt dopt;
+        if (cloud) {
+            dopt.cldfr = a.up(cldfr, L);
+            dopt.taucld = a.up_banded(taucld, 14, L); dopt.ssacld = a.up_banded(ssacld, 14, L);
+            dopt.asmcld = a.up_banded(asmcld, 14, L); dopt.fsfcld = a.up_banded(fsfcld, 14, L);
+        }
+        if (aer) { dopt.tauaer = a.up(tauaer, 14 * L); dopt.ssaaer = a.up(ssaaer, 14 * L); dopt.asmaer = a.up(asmaer, 14 * L); }
         if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
         SwIn in{nc, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2, d_ch4, d_n2o, d_o2,
                 d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjflux};
+        sw_set_optional(in, icld, iaer, dopt);
         Slot o{(char *)P_sw.out[slot].p, 0, c0, nc, ncol, st, true};
         SwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
         if (const int rc = sw_chunk(in, out, nc, nlay, P_sw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
@@ -1171,7 +1245,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
         if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (SW)");
     }
     for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_sw.st[i]));
-    return RRTMG_B200_OK;
+    return sw_err_end(general);
 }
 
 // ---- stage dumps ---------------------------------------------------------------------------------

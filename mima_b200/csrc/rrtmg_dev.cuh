@@ -153,6 +153,11 @@ struct SwIn {
     const double *h2o, *o3, *co2, *ch4, *n2o, *o2;
     const double *asdir, *asdif, *aldir, *aldif, *coszen;
     double adjflux;           // adjflx * scon / rrsw_scon (same for all bands, rad.nomcica:953-972)
+    // optional branches of the interface (null / 0 for MiMA's configuration)
+    int icld = 0, iaer = 0;
+    const double *cldfr = nullptr;                                                  // (ld, nlay)
+    const double *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;   // (14, ld, nlay), inflgsw = 0
+    const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;           // (ld, nlay, 14), iaer = 10
 };
 
 struct SwOut {
@@ -172,6 +177,11 @@ struct SwWork {
     double *taur24;           // [col][lay][8]: taur of band 24, whose Rayleigh coefficient depends on the cell
     double *taur;             // [col][lay][112], expanded from rdesc only for the stage-capture test hook
     double *sfluxzen;         // [col][112]
+    // general path (icld >= 1 or iaer = 10): per (column, layer, band) {tauc, omgc, asyc (delta-M scaled, cldprop_sw
+    // inflag = 0), taua, omga, asya} and the layer cloud fraction; err: bit 0 = partial cloud found
+    double *opt;              // [col][lay][14][6] or null
+    double *clfr;             // [col][lay]
+    int *err;
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };

@@ -554,8 +554,55 @@ __global__ void sw_expand_taur_kernel(SwTables T, SwWork w)
     }
 }
 
+// General path only: cloud optical properties through cldprop_sw's inflag = 0 branch (delta-M scaling with the forward
+// scattering fraction, SW/src/rrtmg_sw_cldprop.f90:120-166), aerosol properties as given (iaer = 10,
+// rad.nomcica:633-640), transposed to [col][lay][band][6] so that the g-point lanes of a band read one address.
+// Also the `stop 'PARTIAL CLOUD NOT ALLOWED'` test of rad.nomcica:534-539 (flag, checked by the host).
+__global__ void __launch_bounds__(128) sw_optics_kernel(SwIn in, SwWork w)
+{
+    const int nc = w.nc, nlay = w.nlay;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nc * nlay) return;
+    const int l = (int)(i / nc);
+    const int col = (int)(i - (size_t)l * nc);
+    const size_t ld = (size_t)in.ld;
+    const double cldmin = 1.e-20, zepsec = 1.e-06;
+    double cf = 0.0;
+    double tauctot = 0.0;
+    if (in.icld >= 1) {
+        cf = in.cldfr[col + (size_t)l * ld];
+        if (cf > zepsec && cf < 1.0 - zepsec) atomicOr(w.err, 1);
+        for (int ib = 0; ib < 14; ++ib) tauctot = tauctot + in.taucld[ib + 14 * (col + (size_t)l * ld)];
+    }
+    const bool cloudy = in.icld >= 1 && cf >= cldmin && tauctot >= cldmin;    // cwp = 0 for directly specified optics
+    w.clfr[(size_t)col * nlay + l] = cf;
+    double *o = w.opt + ((size_t)col * nlay + l) * 14 * 6;
+    for (int ib = 0; ib < 14; ++ib) {
+        double tauc = 0.0, omgc = 1.0, asyc = 0.0;
+        if (cloudy) {
+            const size_t q = ib + 14 * (col + (size_t)l * ld);
+            const double taucldorig_a = in.taucld[q];
+            const double ffp = in.fsfcld[q];
+            const double ffp1 = 1.0 - ffp;
+            const double ffpssa = 1.0 - ffp * in.ssacld[q];
+            omgc = ffp1 * in.ssacld[q] / ffpssa;
+            tauc = ffpssa * taucldorig_a;
+            asyc = (in.asmcld[q] - ffp) / (ffp1);
+        }
+        double taua = 0.0, omga = 1.0, asya = 0.0;
+        if (in.iaer == 10) {
+            const size_t q = col + ld * (l + (size_t)nlay * ib);
+            taua = in.tauaer[q]; asya = in.asmaer[q]; omga = in.ssaaer[q];
+        }
+        o[ib * 6 + 0] = tauc; o[ib * 6 + 1] = omgc; o[ib * 6 + 2] = asyc;
+        o[ib * 6 + 3] = taua; o[ib * 6 + 4] = omga; o[ib * 6 + 5] = asya;
+    }
+}
+
 int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
+    int extra = 0;
+    if (w.opt) { sw_optics_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(in, w); extra = 1; }
     ktimer_begin(K_SW_PREP, s);
     sw_prep_cell_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(in, w);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
@@ -572,7 +619,7 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_begin(K_SW_SOLVER, s);
     const int nsv = sw_launch_solver(t, in, out, w, s);
     ktimer_end(s);
-    return 3 + nsv;
+    return 3 + nsv + extra;
 }
 
 } // namespace rrtmg

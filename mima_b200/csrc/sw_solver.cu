@@ -350,6 +350,261 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     }
 }
 
+
+// =====================================================================================================
+// General path of spcvrt_sw (SW/src/rrtmg_sw_spcvrt.f90:296-619): aerosols (iaer = 10) and clouds (icld >= 1, optical
+// properties given, layers clear or overcast).  Not MiMA's configuration and not tuned: the layout of
+// sw_solver_kernel (two columns per block, block-level g-sums) with reftra_sw in full (asymmetry != 0, delta
+// scaling :446-463), a clear-sky and a total-sky stream (CLOUD), and both direct-beam look-ups (:519-548).
+// =====================================================================================================
+__device__ __forceinline__ double sw_tbl_exp(const double2 *__restrict__ tb, double ze1, double bpade)
+{
+    if (ze1 <= 0.06) return 1. - ze1 + 0.5 * ze1 * ze1;
+    const double tblind = ze1 / (bpade + ze1);
+    const int itind = (int)(10000.0 * tblind + 0.5);
+    return __ldg(tb + itind).x;
+}
+// reftra_sw, kmodts = 2, one layer (reftra.f90:129-300); lrtchk false -> R = 0, T = 1 (:138-142)
+__device__ __noinline__ void sw_reftra_gen(const double2 *__restrict__ tb, double bpade, bool lrtchk, double zg, double prmuz,
+                                           double zto1, double zw, double &pref, double &prefd, double &ptra, double &ptrad)
+{
+    const double eps = 1.e-08, zwcrit = 0.9999995;
+    if (!lrtchk) { pref = 0.; ptra = 1.; prefd = 0.; ptrad = 1.; return; }
+    const double zg3 = 3. * zg;
+    const double zgamma1 = (8. - zw * (5. + zg3)) * 0.25;
+    const double zgamma2 = 3. * (zw * (1. - zg)) * 0.25;
+    const double zgamma3 = (2. - zg3 * prmuz) * 0.25;
+    const double zgamma4 = 1. - zgamma3;
+    const double t = zg / (1. - zg);
+    const double zwo = zw / (1. - (1. - zw) * (t * t));
+    if (zwo >= zwcrit) {
+        const double za = zgamma1 * prmuz;
+        const double za1 = za - zgamma3;
+        const double zgt = zgamma1 * zto1;
+        const double ze2 = sw_tbl_exp(tb, fmin(zto1 / prmuz, 500.), bpade);
+        pref = (zgt - za1 * (1. - ze2)) / (1. + zgt);
+        ptra = 1. - pref;
+        prefd = zgt / (1. + zgt);
+        ptrad = 1. - prefd;
+        if (ze2 == 1.0) { pref = 0.0; ptra = 1.0; prefd = 0.0; ptrad = 1.0; }
+        return;
+    }
+    const double za1 = zgamma1 * zgamma4 + zgamma2 * zgamma3;
+    const double za2 = zgamma1 * zgamma3 + zgamma2 * zgamma4;
+    const double zrk = sqrt(zgamma1 * zgamma1 - zgamma2 * zgamma2);
+    const double zrp = zrk * prmuz;
+    const double zrp1 = 1. + zrp;
+    const double zrm1 = 1. - zrp;
+    const double zrk2 = 2. * zrk;
+    const double zrpp = 1. - zrp * zrp;
+    const double zrkg = zrk + zgamma1;
+    const double zr1 = zrm1 * (za2 + zrk * zgamma3);
+    const double zr2 = zrp1 * (za2 - zrk * zgamma3);
+    const double zr3 = zrk2 * (zgamma3 - za2 * prmuz);
+    const double zr4 = zrpp * zrkg;
+    const double zr5 = zrpp * (zrk - zgamma1);
+    const double zt1 = zrp1 * (za1 + zrk * zgamma4);
+    const double zt2 = zrm1 * (za1 - zrk * zgamma4);
+    const double zt3 = zrk2 * (zgamma4 + za1 * prmuz);
+    const double zbeta = (zgamma1 - zrk) / zrkg;
+    const double zem1 = sw_tbl_exp(tb, fmin(zrk * zto1, 500.), bpade);
+    const double zep1 = 1. / zem1;
+    const double zem2 = sw_tbl_exp(tb, fmin(zto1 / prmuz, 500.), bpade);
+    const double zep2 = 1. / zem2;
+    const double zdenr = zr4 * zep1 + zr5 * zem1;
+    const double zdent = zdenr;                    // zt4 = zr4, zt5 = zr5
+    if (zdenr >= -eps && zdenr <= eps) {
+        pref = eps;
+        ptra = zem2;
+    } else {
+        pref = zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) / zdenr;
+        ptra = zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) / zdent;
+    }
+    const double zemm = zem1 * zem1;
+    const double zdend = 1. / ((1. - zbeta * zemm) * zrkg);
+    prefd = zgamma2 * (1. - zemm) * zdend;
+    ptrad = zrk2 * zem1 * zdend;
+}
+
+struct SwGenLayer { double refc, refdc, trac, tradc, dbtc, ref, refd, tra, trad, dbt; };
+
+// layer assembly of spcvrt (:386-463, 474-548) for one (g, layer) cell
+template <bool CLOUD>
+__device__ __forceinline__ void sw_gen_layer(const double2 *__restrict__ tb, double bpade, double prmu0, double taur, double taug,
+                                             const double *__restrict__ o, double pclfr, SwGenLayer &L)
+{
+    const double repclc = 1.e-12;
+    const double ptauc = o[0], pomgc = o[1], pasyc = o[2], ptaua = o[3], pomga = o[4], pasya = o[5];
+    double ztauc = taur + taug + ptaua;
+    double zomcc = taur * 1.0 + ptaua * pomga;
+    double zgcc = pasya * pomga * ptaua / zomcc;
+    zomcc = zomcc / ztauc;
+    double zf = zgcc * zgcc;
+    double zwf = zomcc * zf;
+    ztauc = (1.0 - zwf) * ztauc;
+    zomcc = (zomcc - zwf) / (1.0 - zwf);
+    zgcc = (zgcc - zf) / (1.0 - zf);
+    sw_reftra_gen(tb, bpade, true, zgcc, prmu0, ztauc, zomcc, L.refc, L.refdc, L.trac, L.tradc);
+    L.dbtc = sw_tbl_exp(tb, ztauc / prmu0, bpade);
+    if (CLOUD) {
+        const double ztauo = ztauc + ptauc;
+        double zomco = ztauc * zomcc + ptauc * pomgc;
+        const double zgco = (ptauc * pomgc * pasyc + ztauc * zomcc * zgcc) / zomco;
+        zomco = zomco / ztauo;
+        double refo, refdo, trao, trado;
+        sw_reftra_gen(tb, bpade, pclfr > repclc, zgco, prmu0, ztauo, zomco, refo, refdo, trao, trado);
+        const double zclear = 1.0 - pclfr, zcloud = pclfr;
+        L.ref = zclear * L.refc + zcloud * refo;
+        L.refd = zclear * L.refdc + zcloud * refdo;
+        L.tra = zclear * L.trac + zcloud * trao;
+        L.trad = zclear * L.tradc + zcloud * trado;
+        const double zdbtmo = sw_tbl_exp(tb, ztauo / prmu0, bpade);
+        L.dbt = zclear * L.dbtc + zcloud * zdbtmo;
+    } else {
+        L.ref = L.refc; L.refd = L.refdc; L.tra = L.trac; L.trad = L.tradc; L.dbt = L.dbtc;
+    }
+}
+
+template <int LMAX, bool CLOUD>
+__global__ void __launch_bounds__(SV_THREADS) sw_solver_gen_kernel(SwTables T, SwIn in, SwOut out, SwWork w)
+{
+    constexpr int NV = CLOUD ? 4 : 2;              // values per level: {up, down} x {total[, clear]}
+    constexpr int NB = CLOUD ? 4 : 8;              // levels per reduction batch
+    constexpr int NR = 32;                         // tile rows = NB * NV * SV_COLS
+    static_assert(NB * NV * SV_COLS == NR, "tile geometry");
+    constexpr int SG_S = 113;
+    __shared__ double s_tile[NR * SG_S];
+    __shared__ double s_part[NR * (SV_THREADS / NR + 1)];
+    __shared__ double s_flux[SV_COLS][4][LMAX + 1];      // up, down, upc, downc
+    const int klev = w.nlay;
+    const int cb = threadIdx.x / NGPTSW;
+    const int g = threadIdx.x - cb * NGPTSW;
+    const int col = blockIdx.x * SV_COLS + cb;
+    const size_t old = (size_t)out.ld;
+    const bool incol = col < w.nc;
+    const double prmu0 = incol ? in.coszen[col] : 0.0;
+    const bool active = incol && !(prmu0 < ZEPZEN);
+    const int colr = incol ? col : 0;
+    const int band = c_ss.ngb[g];
+    const double bpade = c_ss.bpade;
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
+    const double mu0 = active ? prmu0 : 1.0;
+    const bool uvvis = band >= 9 && band <= 12;
+    const double albd = uvvis ? in.asdif[colr] : in.aldif[colr];
+    const double albp = uvvis ? in.asdir[colr] : in.aldir[colr];
+    double zrup[LMAX + 1], zrupd[LMAX + 1];
+    double zrupc[CLOUD ? LMAX + 1 : 1], zrupdc[CLOUD ? LMAX + 1 : 1];
+    const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
+    const bool b24 = band == 8;
+    const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
+    const double *__restrict__ taur = b24 ? w.taur24 + (size_t)colr * klev * 8 + (g - c_ss.g0[band])
+                                          : w.colmol + (size_t)colr * klev;
+    const int trs = b24 ? 8 : 1;
+    const double *__restrict__ opt = w.opt + ((size_t)colr * klev * 14 + band) * 6;
+    const double *__restrict__ clfr = w.clfr + (size_t)colr * klev;
+    const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)col * NGPTSW + g] * prmu0 : 0.0;
+
+    // ---- up sweep (vrtqdr :103-121), both streams
+    if (active) {
+        double rup = albp, rupd = albd, rupc = albp, rupdc = albd;
+        zrup[0] = rup; zrupd[0] = rupd;
+        if (CLOUD) { zrupc[0] = rupc; zrupdc[0] = rupdc; }
+        for (int l = 0; l < klev; ++l) {
+            SwGenLayer L;
+            sw_gen_layer<CLOUD>(tb, bpade, mu0, __ldg(taur + l * trs) * raylg, taug[(size_t)l * NGPTSW], opt + (size_t)l * 14 * 6,
+                                CLOUD ? clfr[l] : 0.0, L);
+            {
+                const double zreflect = 1. / (1. - rupd * L.refd);
+                const double rup_n = L.ref + (L.trad * ((L.tra - L.dbt) * rupd + L.dbt * rup)) * zreflect;
+                const double rupd_n = L.refd + L.trad * L.trad * rupd * zreflect;
+                rup = rup_n; rupd = rupd_n;
+                zrup[l + 1] = rup; zrupd[l + 1] = rupd;
+            }
+            if (CLOUD) {
+                const double zreflect = 1. / (1. - rupdc * L.refdc);
+                const double rup_n = L.refc + (L.tradc * ((L.trac - L.dbtc) * rupdc + L.dbtc * rupc)) * zreflect;
+                const double rupd_n = L.refdc + L.tradc * L.tradc * rupdc * zreflect;
+                rupc = rup_n; rupdc = rupd_n;
+                zrupc[l + 1] = rupc; zrupdc[l + 1] = rupdc;
+            }
+        }
+    }
+    // ---- down sweep (:125-150) and spectral sums (spcvrt :570-619)
+    double ztdn = 1., zrdnd = 0., ztdbt = 1., ztdnc = 1., zrdndc = 0., ztdbtc = 1.;
+    for (int k = 0; k <= klev; ++k) {
+        const int s = klev - k;
+        const int slot = k & (NB - 1);
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (active) {
+            {
+                const double ru = zrup[s], rud = zrupd[s];
+                const double zreflect = 1. / (1. - zrdnd * rud);
+                const double dif = ztdn - ztdbt;
+                v[0] = zincflx * ((ztdbt * ru + dif * rud) * zreflect);
+                v[1] = zincflx * (ztdbt + (dif + ztdbt * ru * zrdnd) * zreflect);
+            }
+            if (CLOUD) {
+                const double ru = zrupc[s], rud = zrupdc[s];
+                const double zreflect = 1. / (1. - zrdndc * rud);
+                const double dif = ztdnc - ztdbtc;
+                v[2] = zincflx * ((ztdbtc * ru + dif * rud) * zreflect);
+                v[3] = zincflx * (ztdbtc + (dif + ztdbtc * ru * zrdndc) * zreflect);
+            }
+            if (s > 0) {
+                const int l = s - 1;
+                SwGenLayer L;
+                sw_gen_layer<CLOUD>(tb, bpade, mu0, __ldg(taur + l * trs) * raylg, taug[(size_t)l * NGPTSW], opt + (size_t)l * 14 * 6,
+                                    CLOUD ? clfr[l] : 0.0, L);
+                {
+                    const double zr = 1. / (1. - L.refd * zrdnd);
+                    const double dif = ztdn - ztdbt;
+                    const double ztdn_n = ztdbt * L.tra + (L.trad * (dif + ztdbt * L.ref * zrdnd)) * zr;
+                    const double zrdnd_n = L.refd + L.trad * L.trad * zrdnd * zr;
+                    ztdbt = L.dbt * ztdbt; ztdn = ztdn_n; zrdnd = zrdnd_n;
+                }
+                if (CLOUD) {
+                    const double zr = 1. / (1. - L.refdc * zrdndc);
+                    const double dif = ztdnc - ztdbtc;
+                    const double ztdn_n = ztdbtc * L.trac + (L.tradc * (dif + ztdbtc * L.refc * zrdndc)) * zr;
+                    const double zrdnd_n = L.refdc + L.tradc * L.tradc * zrdndc * zr;
+                    ztdbtc = L.dbtc * ztdbtc; ztdnc = ztdn_n; zrdndc = zrdnd_n;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) s_tile[((slot * NV + q) * SV_COLS + cb) * SG_S + g] = v[q];
+        if (slot == NB - 1 || k == klev) {
+            const double sum = tile_reduce<SV_THREADS, NR, NGPTSW, SG_S>(s_tile, s_part);
+            if (threadIdx.x < NR) {
+                const int c = threadIdx.x % SV_COLS, sq = threadIdx.x / SV_COLS;      // row = (slot*NV + q)*SV_COLS + c
+                const int q = sq % NV, sl = sq / NV;
+                const int kk = (k & ~(NB - 1)) + sl;
+                if (kk <= k) s_flux[c][q][klev - kk] = sum;
+            }
+        }
+    }
+    __syncthreads();
+    if (incol) {
+        for (int lev = g; lev <= klev; lev += NGPTSW) {
+            const double u = s_flux[cb][0][lev], d = s_flux[cb][1][lev];
+            const double uc = CLOUD ? s_flux[cb][2][lev] : u, dc = CLOUD ? s_flux[cb][3][lev] : d;
+            const size_t o = col + (size_t)lev * old;
+            out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
+        }
+        for (int lay = g; lay < klev; lay += NGPTSW) {
+            const size_t o = col + (size_t)lay * old;
+            double h = 0.0, hc = 0.0;
+            if (active && lay < klev - 1) {
+                const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
+                h = ((s_flux[cb][1][lay + 1] - s_flux[cb][0][lay + 1]) - (s_flux[cb][1][lay] - s_flux[cb][0][lay])) * (c_ss.heatfac / pdp);
+                hc = CLOUD ? ((s_flux[cb][3][lay + 1] - s_flux[cb][2][lay + 1]) - (s_flux[cb][3][lay] - s_flux[cb][2][lay])) * (c_ss.heatfac / pdp) : h;
+            }
+            out.hr[o] = h;
+            out.hrc[o] = hc;
+        }
+    }
+}
+
 template <int LMAX, bool STORE, int OPT>
 static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
@@ -368,6 +623,18 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
+    if (w.opt) {            // aerosols and/or clouds: the general kernel
+        const unsigned nb = (w.nc + SV_COLS - 1) / SV_COLS;
+        const bool cloud = in.icld >= 1;
+        if (w.nlay <= 64) {
+            if (cloud) sw_solver_gen_kernel<64, true><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);
+            else sw_solver_gen_kernel<64, false><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);
+        } else {
+            if (cloud) sw_solver_gen_kernel<MAXLAY, true><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);
+            else sw_solver_gen_kernel<MAXLAY, false><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);
+        }
+        return 1;
+    }
     if (w.nlay <= 64) launch_opt<64>(t, in, out, w, s);
     else launch_opt<MAXLAY>(t, in, out, w, s);
     return 1;

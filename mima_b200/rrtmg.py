@@ -204,11 +204,24 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
              taucld=None, ssacld=None, asmcld=None, fsfcld=None,
              cicewp=None, cliqwp=None, reice=None, reliq=None,
              tauaer=None, ssaaer=None, asmaer=None, ecaer=None):
-    """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc)."""
+    """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc).  icld >= 1 takes cloud optical properties
+    (inflgsw = 0: cldfr (ncol,nlay) 0 or 1, taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)); iaer = 10 takes
+    tauaer/ssaaer/asmaer (ncol,nlay,14).  Water-path cloud inputs (inflgsw > 0) and iaer = 6 raise
+    RRTMGError(2); a partially cloudy layer raises RRTMGError(3) like the reference's stop."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
+    B = (NBNDSW, ncol, nlay)
+    A = (ncol, nlay, NBNDSW)
     keep = []
     ptrs = []
+    optional = []
+    for a, shp, nm in ((cldfr, L, "cldfr"), (taucld, B, "taucld"), (ssacld, B, "ssacld"), (asmcld, B, "asmcld"),
+                       (fsfcld, B, "fsfcld"), (cicewp, L, "cicewp"), (cliqwp, L, "cliqwp"), (reice, L, "reice"),
+                       (reliq, L, "reliq"), (tauaer, A, "tauaer"), (ssaaer, A, "ssaaer"), (asmaer, A, "asmaer"),
+                       (ecaer, (ncol, nlay, 6), "ecaer")):
+        arr, p = _in(a, shp, nm, True)
+        keep.append(arr)
+        optional.append(p)
     for a, shp, nm, opt in ((play, L, "play", False), (plev, V, "plev", False), (tlay, L, "tlay", False),
                             (tlev, V, "tlev", False), (tsfc, (ncol,), "tsfc", False),
                             (h2ovmr, L, "h2ovmr", False), (o3vmr, L, "o3vmr", False), (co2vmr, L, "co2vmr", False),
@@ -225,8 +238,7 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
     rc = lib().rrtmg_b200_sw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.byref(iaer_c), *ptrs,
                              C.c_double(float(adjes)), C.c_int(int(dyofyr)), C.c_double(float(scon)),
                              C.c_int(inflgsw), C.c_int(iceflgsw), C.c_int(liqflgsw),
-                             None, None, None, None, None, None, None, None, None, None, None, None, None,
-                             *[o.ctypes.data_as(_dp) for o in out])
+                             *optional, *[o.ctypes.data_as(_dp) for o in out])
     _check(rc)
     return tuple(out)
 
@@ -243,7 +255,7 @@ def lw_from_columns(c, tauaer=None, idrv=0):
                     None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer)
 
 
-def sw_from_columns(c):
-    return rrtmg_sw(c.ncol, c.nlay, 0, 0, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
+def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0):
+    return rrtmg_sw(c.ncol, c.nlay, icld, iaer, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), c.albedo, c.albedo, c.albedo, c.albedo,
-                    c.coszen, c.adjes, c.dyofyr, c.scon)
+                    c.coszen, c.adjes, c.dyofyr, c.scon, inflgsw=inflgsw, **(clouds or {}), **(aerosols or {}))

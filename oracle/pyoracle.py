@@ -114,7 +114,10 @@ class Oracle:
         return out
 
     # ------------------------------------------------------------------ SW
-    def rrtmg_sw(self, cols, *, stages: bool = False, nthreads: int | None = None):
+    def rrtmg_sw(self, cols, *, stages: bool = False, nthreads: int | None = None, icld: int = 0, iaer: int = 0,
+                 clouds=None, aerosols=None):
+        """clouds = dict(cldfr (ncol,nlay), taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)) for icld >= 1 (inflgsw = 0);
+        aerosols = dict(tauaer/ssaaer/asmaer (ncol,nlay,14)) for iaer = 10."""
         ncol, nlay = cols.ncol, cols.nlay
         nthreads = nthreads or self.max_threads
         out = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
@@ -135,8 +138,13 @@ class Oracle:
         ins = [_f(x) for x in (cols.play, cols.plev, cols.tlay, cols.tlev, cols.tsfc, cols.h2o, cols.o3, cols.co2,
                                cols.ch4, cols.n2o, cols.o2, cols.albedo, cols.albedo, cols.albedo, cols.albedo,
                                cols.coszen)]
-        rc = self.lib.orc_rrtmg_sw(C.c_int(ncol), C.c_int(nlay), C.c_int(0), C.c_int(0), *[_p(a) for a in ins],
+        extra = []
+        for src, keys in ((clouds, ("cldfr", "taucld", "ssacld", "asmcld", "fsfcld")), (aerosols, ("tauaer", "ssaaer", "asmaer"))):
+            for k in keys:
+                extra.append(_f(src[k]) if src is not None else None)
+        rc = self.lib.orc_rrtmg_sw(C.c_int(ncol), C.c_int(nlay), C.c_int(int(icld)), C.c_int(int(iaer)), *[_p(a) for a in ins],
                                    C.c_double(cols.adjes), C.c_int(cols.dyofyr), C.c_double(cols.scon),
+                                   C.c_int(0), *[None if a is None else _p(a) for a in extra],
                                    _p(out["swuflx"]), _p(out["swdflx"]), _p(out["swhr"]), _p(out["swuflxc"]),
                                    _p(out["swdflxc"]), _p(out["swhrc"]), stp, C.c_int(nthreads))
         if rc:

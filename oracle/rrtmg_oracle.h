@@ -145,6 +145,8 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                  const double *asdir, const double *asdif, const double *aldir, const double *aldif,
                  const double *coszen, double adjes, int dyofyr, double scon,
+                 int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
+                 const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *stages, int nthreads);
 

@@ -1,5 +1,6 @@
 /*
- * sw.c -- oracle restatement of RRTMG_SW as linked by MiMA (clear sky icld=0, no aerosol iaer=0).
+ * sw.c -- oracle restatement of RRTMG_SW as linked by MiMA: clear sky (icld=0, iaer=0: what MiMA runs), plus the
+ * input-optical-property branches of the interface, iaer=10 and icld>=1 with inflgsw=0 (overcast or clear layers only).
  * TEST INFRASTRUCTURE ONLY (see rrtmg_oracle.h).
  *
  * Follows  SW/src/rrtmg_sw_rad.nomcica.f90:78-731 (rrtmg_sw), :734-758 (earth_sun), :761-1101 (inatm_sw)
@@ -39,6 +40,8 @@ typedef struct {
     double zbbfddir[NL], zbbcddir[NL], zuvfd[NL], zuvcd[NL], znifd[NL], znicd[NL];
     double zuvfddir[NL], zuvcddir[NL], znifddir[NL], znicddir[NL];
     double oneminus;
+    /* cloud and aerosol optical properties per (layer, band 1..14) as spcvrt_sw receives them (rad.nomcica:581-640) */
+    double pclfr[NL], ptauc[NL][15], pasyc[NL][15], pomgc[NL][15], ptaua[NL][15], pasya[NL][15], pomga[NL][15];
 } swcol_t;
 
 /* earth_sun (rad.nomcica:734-758) */
@@ -770,8 +773,6 @@ static void spcvrt_sw(swcol_t *c, const double *palbd, const double *palbp, doub
     const orc_state_t *S = &g_orc;
     const int klev = c->nlayers;
     const double od_lo = 0.06, tblint = 10000.0, bpade = S->sw_bpade, repclc = 1.e-12;
-    /* icld=0 / iaer=0 inputs as marshalled by rrtmg_sw (rad.nomcica:581-606) */
-    const double pclfr = 0., ptauc = 0., pasyc = 0., pomgc = 1., ptaua = 0., pasya = 0., pomga = 1.;
     const int icpr = 1, idelm = 1;
     int lrtchkclr[NL], lrtchkcld[NL];
     double zdbt[NL], zdbtc[NL], zgcc[NL], zgco[NL], zomcc[NL], zomco[NL];
@@ -820,6 +821,8 @@ static void spcvrt_sw(swcol_t *c, const double *palbd, const double *palbp, doub
             for (int jk = 1; jk <= klev; ++jk) {
                 ikl = klev + 1 - jk;
                 lrtchkclr[jk] = 1;
+                const double pclfr = c->pclfr[ikl], ptauc = c->ptauc[ikl][ibm], pasyc = c->pasyc[ikl][ibm], pomgc = c->pomgc[ikl][ibm];
+                const double ptaua = c->ptaua[ikl][ibm], pasya = c->pasya[ikl][ibm], pomga = c->pomga[ikl][ibm];
                 lrtchkcld[jk] = (pclfr > repclc);
                 /* clear-sky optical parameters including aerosols (:386-396) */
                 ztauc[jk] = c->ztaur[iw][ikl] + c->ztaug[iw][ikl] + ptaua;
@@ -843,8 +846,8 @@ static void spcvrt_sw(swcol_t *c, const double *palbd, const double *palbp, doub
 
             for (int jk = 1; jk <= klev; ++jk) {
                 ikl = klev + 1 - jk;
-                zclear = 1.0 - pclfr;
-                zcloud = pclfr;
+                zclear = 1.0 - c->pclfr[ikl];
+                zcloud = c->pclfr[ikl];
                 zref[jk] = zclear * zrefc[jk] + zcloud * zrefo[jk];
                 zrefd[jk] = zclear * zrefdc[jk] + zcloud * zrefdo[jk];
                 ztra[jk] = zclear * ztrac[jk] + zcloud * ztrao[jk];
@@ -908,11 +911,21 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                  const double *asdir, const double *asdif, const double *aldir, const double *aldif,
                  const double *coszen, double adjes, int dyofyr, double scon,
+                 int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
+                 const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *st, int nthreads)
 {
+    /* cldfr (ncol,nlay); taucld, ssacld, asmcld, fsfcld (14,ncol,nlay); tauaer, ssaaer, asmaer (ncol,nlay,14) */
     if (!g_orc.ready) return 1;
-    if (icld != 0 || iaer != 0) return 2;
+    if (icld < 0 || icld > 3) icld = 2;                              /* :468 */
+    if (iaer != 0 && iaer != 6 && iaer != 10) iaer = 0;              /* :473 */
+    if (iaer == 6) return 2;                                         /* ECMWF aerosol types: not restated */
+    if (icld >= 1 && (inflgsw != 0 || !cldfr || !taucld || !ssacld || !asmcld || !fsfcld)) return 2; /* inflag 2: not restated */
+    if (iaer == 10 && (!tauaer || !ssaaer || !asmaer)) return 3;
+    if (icld >= 1) /* without McICA: clear or overcast layers only (:534-539, `stop 'PARTIAL CLOUD NOT ALLOWED'`) */
+        for (long i = 0; i < (long)ncol * nlay; ++i)
+            if (cldfr[i] > 1.e-06 && cldfr[i] < 1.0 - 1.e-06) return 4;
     if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
     if (nthreads < 1) nthreads = 1;
     const double zepsec = 1.e-06, zepzen = 1.e-10;
@@ -945,7 +958,36 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
             memset(c->zsflxzen, 0, sizeof c->zsflxzen); /* deterministic if a band never reaches laysolfr */
             inatm_sw(c, iplon, ncol, nlay, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
                      adjes, dyofyr, scon);
-            /* cldprop_sw with cldfrac=0: taucloud=0, ssacloud=1, asmcloud=0 -- nothing to compute */
+            /* clouds: cldprop_sw, inflag = 0 branch (cldprop.f90:120-166) and the transfer at rad.nomcica:581-597 */
+            for (int lay = 1; lay <= nlay; ++lay) {
+                double tauctot = 0.0;
+                c->pclfr[lay] = icld >= 1 ? cldfr[(long)(lay - 1) * ncol + i0] : 0.0;
+                for (int ib = 1; ib <= 14; ++ib) {
+                    c->ptauc[lay][ib] = 0.0; c->pomgc[lay][ib] = 1.0; c->pasyc[lay][ib] = 0.0;
+                    if (icld >= 1) tauctot = tauctot + taucld[(ib - 1) + 14 * (i0 + (long)(lay - 1) * ncol)];
+                }
+                if (icld >= 1 && c->pclfr[lay] >= 1.e-20 && tauctot >= 1.e-20) {   /* cwp = 0 for inflag = 0 inputs */
+                    for (int ib = 1; ib <= 14; ++ib) {
+                        const long o = (ib - 1) + 14 * (i0 + (long)(lay - 1) * ncol);
+                        const double taucldorig_a = taucld[o];
+                        const double ffp = fsfcld[o];
+                        const double ffp1 = 1.0 - ffp;
+                        const double ffpssa = 1.0 - ffp * ssacld[o];
+                        c->pomgc[lay][ib] = ffp1 * ssacld[o] / ffpssa;
+                        c->ptauc[lay][ib] = ffpssa * taucldorig_a;
+                        c->pasyc[lay][ib] = (asmcld[o] - ffp) / (ffp1);
+                    }
+                }
+                /* aerosols (rad.nomcica:599-640) */
+                for (int ib = 1; ib <= 14; ++ib) {
+                    if (iaer == 10) {
+                        const long o = i0 + (long)ncol * ((lay - 1) + (long)nlay * (ib - 1));
+                        c->ptaua[lay][ib] = tauaer[o]; c->pasya[lay][ib] = asmaer[o]; c->pomga[lay][ib] = ssaaer[o];
+                    } else {
+                        c->ptaua[lay][ib] = 0.0; c->pasya[lay][ib] = 0.0; c->pomga[lay][ib] = 1.0;
+                    }
+                }
+            }
             setcoef_sw(c);
             cossza = coszen[i0];
             if (cossza < zepzen) cossza = zepzen;

@@ -189,8 +189,14 @@ def test_unsupported_options_fail_loudly(gpu):
         gpu.rrtmg_lw(c.ncol, c.nlay, 0, 2, *args, None, None, None, None, None)      # idrv must be 0 or 1
     assert e.value.code == 4
     with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_sw(c.ncol, c.nlay, 0, 6, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
+    assert e.value.code == 2                      # ECMWF aerosol climatology: not built
+    with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_sw(c.ncol, c.nlay, 0, 10, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
-    assert e.value.code == 2
+    assert e.value.code == 4                      # iaer = 10 without the aerosol arrays
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_sw(c.ncol, c.nlay, 2, 0, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0, inflgsw=2)
+    assert e.value.code == 2                      # cloud optics from water paths: not built
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_lw(c.ncol, 200, 0, 0, *args, None, None, None, None, None)
     assert e.value.code == 4

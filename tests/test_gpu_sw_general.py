@@ -1,0 +1,106 @@
+"""GPU parity of the general shortwave path: aerosols given per band (iaer = 10, SW rad.nomcica:633-640) and
+clouds given as optical properties (icld >= 1, inflgsw = 0: cldprop_sw's delta-M branch, rrtmg_sw_cldprop.f90:120-166;
+total-sky stream of spcvrt_sw.f90:455-548).  MiMA itself never takes these branches (rrtm_radiation.f90:703-717);
+they are the part of the rrtmg_sw interface around the hot path.  Same tolerances as test_gpu_parity."""
+import numpy as np
+import pytest
+
+from mima_b200.columns import make_columns
+from test_gpu_parity import SW_OUT, _check_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _aerosols(cols, rng, tau_max=0.3):
+    shp = (cols.ncol, cols.nlay, 14)
+    return dict(tauaer=np.asfortranarray(rng.uniform(0.0, tau_max, shp)),
+                ssaaer=np.asfortranarray(rng.uniform(0.6, 0.999, shp)),
+                asmaer=np.asfortranarray(rng.uniform(0.3, 0.8, shp)))
+
+
+def _clouds(cols, rng, frac=0.3, tau_max=20.0):
+    shp = (14, cols.ncol, cols.nlay)
+    cld = (rng.uniform(size=(cols.ncol, cols.nlay)) < frac).astype(np.float64)
+    asm = rng.uniform(0.7, 0.9, shp)
+    return dict(cldfr=np.asfortranarray(cld),
+                taucld=np.asfortranarray(rng.uniform(0.0, tau_max, shp) * cld[None]),
+                ssacld=np.asfortranarray(rng.uniform(0.5, 0.99999, shp)),
+                asmcld=np.asfortranarray(asm),
+                fsfcld=np.asfortranarray(asm * asm))
+
+
+@pytest.fixture(scope="module")
+def cols():
+    return make_columns("T42L40", nlon=64, nlat=8, night=True)
+
+
+def test_aerosols(gpu, oracle, cols):
+    aer = _aerosols(cols, np.random.default_rng(11))
+    got = gpu.sw_from_columns(cols, iaer=10, aerosols=aer)
+    _check_outputs(got, oracle.rrtmg_sw(cols, iaer=10, aerosols=aer), SW_OUT)
+    assert np.array_equal(got[0], got[3]) and np.array_equal(got[2], got[5])      # no clouds: total = clear
+    clear = gpu.sw_from_columns(cols)
+    day = cols.coszen > 0.1
+    assert (got[1][day, 0] < clear[1][day, 0]).all()            # aerosols dim the surface
+
+
+def test_zero_aerosol_reproduces_the_clear_path(gpu, cols):
+    """tauaer = 0 through the general kernel against MiMA's specialised kernel: the same numbers to rounding
+    (the two differ only in reciprocal refinement and summation order)."""
+    z = np.zeros((cols.ncol, cols.nlay, 14), order="F")
+    got = gpu.sw_from_columns(cols, iaer=10, aerosols=dict(tauaer=z, ssaaer=z + 0.9, asmaer=z + 0.5))
+    ref = gpu.sw_from_columns(cols)
+    for g, r, n in zip(got, ref, SW_OUT):
+        tol = 1e-7 if "hr" in n else 1e-9 * max(np.abs(r).max(), 1.0)
+        assert np.max(np.abs(g - r)) < tol, n
+
+
+@pytest.mark.parametrize("icld", [1, 2, 3])
+def test_clouds(gpu, oracle, cols, icld):
+    cl = _clouds(cols, np.random.default_rng(20 + icld))
+    got = gpu.sw_from_columns(cols, icld=icld, clouds=cl)
+    _check_outputs(got, oracle.rrtmg_sw(cols, icld=icld, clouds=cl), SW_OUT)
+    clear = gpu.sw_from_columns(cols)
+    for i in (3, 4, 5):          # the clear-sky stream does not see the clouds
+        tol = 1e-7 if i == 5 else 1e-9 * np.abs(clear[i]).max()
+        assert np.max(np.abs(got[i] - clear[i])) < tol
+    day = cols.coszen > 0.1
+    cloudy = day & (cl["cldfr"].sum(axis=1) > 0) & (cl["taucld"].sum(axis=(0, 2)) > 1.0)
+    assert cloudy.any() and (got[1][cloudy, 0] < got[4][cloudy, 0]).all()
+
+
+def test_clouds_and_aerosols_chunked(gpu, oracle, cols):
+    """Both branches at once, with host chunks and device passes smaller than the batch (ragged tail): the banded
+    (14, ncol, nlay) arrays are cut by columns."""
+    rng = np.random.default_rng(5)
+    c = cols.take(np.arange(301))
+    cl, aer = _clouds(c, rng), _aerosols(c, rng, 0.1)
+    ref = oracle.rrtmg_sw(c, icld=2, iaer=10, clouds=cl, aerosols=aer)
+    gpu.set_option("host_chunk", 64)
+    try:
+        _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=10, clouds=cl, aerosols=aer), ref, SW_OUT)
+    finally:
+        gpu.set_option("host_chunk", 0)
+    gpu.set_option("chunk", 50)
+    try:
+        _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=10, clouds=cl, aerosols=aer), ref, SW_OUT)
+    finally:
+        gpu.set_option("chunk", 0)
+
+
+def test_out_of_range_switches_are_reset(gpu, oracle, cols):
+    """icld outside 0..3 becomes 2, iaer outside {0, 6, 10} becomes 0 (rad.nomcica:468-473)."""
+    c = cols.take(np.arange(40))
+    cl = _clouds(c, np.random.default_rng(3))
+    got = gpu.sw_from_columns(c, icld=7, iaer=3, clouds=cl)
+    _check_outputs(got, oracle.rrtmg_sw(c, icld=2, clouds=cl), SW_OUT)
+
+
+def test_partial_cloud_is_an_error(gpu, cols):
+    c = cols.take(np.arange(16))
+    cl = _clouds(c, np.random.default_rng(4))
+    cl["cldfr"][5, 7] = 0.5
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.sw_from_columns(c, icld=2, clouds=cl)
+    assert e.value.code == 3
+    gpu.sw_from_columns(c)         # the library stays usable

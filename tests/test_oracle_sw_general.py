@@ -1,0 +1,79 @@
+"""CPU checks of the oracle's general shortwave path (aerosols iaer = 10, clouds icld >= 1 with inflgsw = 0).
+The reference holds no vectors for these branches (MiMA never takes them), so the restatement is anchored on its
+reduction to the pinned clear-sky path and on the physics the two-stream equations guarantee."""
+import numpy as np
+import pytest
+
+from mima_b200.columns import make_columns
+
+SW = ("swuflx", "swdflx", "swhr", "swuflxc", "swdflxc", "swhrc")
+
+
+@pytest.fixture(scope="module")
+def cols():
+    return make_columns("T42L40", nlon=16, nlat=4, night=True)
+
+
+def _clouds(cols, rng, frac=0.3):
+    shp = (14, cols.ncol, cols.nlay)
+    cld = (rng.uniform(size=(cols.ncol, cols.nlay)) < frac).astype(np.float64)
+    asm = rng.uniform(0.7, 0.9, shp)
+    return dict(cldfr=np.asfortranarray(cld), taucld=np.asfortranarray(rng.uniform(0.0, 20.0, shp) * cld[None]),
+                ssacld=np.asfortranarray(rng.uniform(0.5, 0.99999, shp)), asmcld=np.asfortranarray(asm),
+                fsfcld=np.asfortranarray(asm * asm))
+
+
+def test_zero_optical_depth_is_the_clear_path_bitwise(oracle, cols):
+    ref = oracle.rrtmg_sw(cols)
+    z = np.zeros((cols.ncol, cols.nlay, 14), order="F")
+    a = oracle.rrtmg_sw(cols, iaer=10, aerosols=dict(tauaer=z, ssaaer=z + 0.9, asmaer=z + 0.6))
+    zc = np.zeros((14, cols.ncol, cols.nlay), order="F")
+    c = oracle.rrtmg_sw(cols, icld=2, clouds=dict(cldfr=np.zeros((cols.ncol, cols.nlay), order="F"), taucld=zc + 5.0,
+                                                   ssacld=zc + 0.9, asmcld=zc + 0.8, fsfcld=zc + 0.64))
+    for k in SW:
+        assert np.array_equal(a[k], ref[k]), k
+        assert np.array_equal(c[k], ref[k]), k
+
+
+def test_clouds_leave_the_clear_stream_alone_and_dim_the_surface(oracle, cols):
+    cl = _clouds(cols, np.random.default_rng(1))
+    ref = oracle.rrtmg_sw(cols)
+    got = oracle.rrtmg_sw(cols, icld=2, clouds=cl)
+    for k in ("swuflxc", "swdflxc", "swhrc"):
+        assert np.array_equal(got[k], ref[k]), k
+    day = cols.coszen > 0.1
+    cloudy = day & (cl["taucld"].sum(axis=(0, 2)) > 1.0)
+    assert cloudy.any()
+    assert (got["swdflx"][cloudy, 0] < got["swdflxc"][cloudy, 0]).all()
+    # energy: nothing exceeds the incoming flux, absorbed + reflected = incoming at the top
+    top = got["swdflx"][:, -1]
+    assert (got["swuflx"] <= top[:, None] * (1 + 1e-12)).all()
+    assert (got["swdflx"] <= top[:, None] * (1 + 1e-12)).all()
+
+
+def test_absorbing_aerosol_heats_scattering_aerosol_reflects(oracle, cols):
+    shp = (cols.ncol, cols.nlay, 14)
+    tau = np.full(shp, 0.02, order="F")
+    ref = oracle.rrtmg_sw(cols)
+    absorbing = oracle.rrtmg_sw(cols, iaer=10, aerosols=dict(tauaer=tau, ssaaer=np.full(shp, 0.3, order="F"),
+                                                             asmaer=np.full(shp, 0.6, order="F")))
+    scattering = oracle.rrtmg_sw(cols, iaer=10, aerosols=dict(tauaer=tau, ssaaer=np.full(shp, 0.999999, order="F"),
+                                                              asmaer=np.full(shp, 0.6, order="F")))
+    day = cols.coszen > 0.2
+    net = lambda o: o["swdflx"] - o["swuflx"]
+    assert (net(absorbing)[day, -1] - net(absorbing)[day, 0] > net(ref)[day, -1] - net(ref)[day, 0]).all()
+    assert (scattering["swuflx"][day, -1] > ref["swuflx"][day, -1]).all()
+
+
+def test_switch_handling(oracle, cols):
+    c = cols.take(np.arange(8))
+    cl = _clouds(c, np.random.default_rng(2))
+    a = oracle.rrtmg_sw(c, icld=9, iaer=4, clouds=cl)           # reset to icld = 2, iaer = 0 (rad.nomcica:468-473)
+    b = oracle.rrtmg_sw(c, icld=2, clouds=cl)
+    for k in SW:
+        assert np.array_equal(a[k], b[k])
+    cl["cldfr"][2, 3] = 0.4
+    with pytest.raises(RuntimeError, match="rc=4"):             # stop 'PARTIAL CLOUD NOT ALLOWED' (:537)
+        oracle.rrtmg_sw(c, icld=2, clouds=cl)
+    with pytest.raises(RuntimeError, match="rc=2"):
+        oracle.rrtmg_sw(c, iaer=6)
