@@ -28,12 +28,23 @@
  *     (MiMA passes compile-time zeros/ones for these, rrtm_radiation.f90:700-712,737-748; the shim
  *     can skip the PCIe transfer.)
  *   - cloud and SW aerosol arrays are never dereferenced when icld == 0 / iaer == 0 (as in the
- *     reference) and may be NULL or of any extent.
+ *     reference) and may be NULL or of any extent; with icld > 0 / iaer = 10 the arrays listed under
+ *     "built" below are required (RRTMG_B200_ERR_BAD_ARGUMENT when NULL).
  *   - *_device variants take device pointers plus a cudaStream_t and run asynchronously.
+ *
+ * Branches beyond MiMA's configuration (icld = 0, iaer = 0, idrv = 0):
+ *   - built: idrv = 1 (LW flux derivative); LW icld = 1 (random overlap, rtrn) and icld = 2, 3
+ *     (maximum/random overlap, rtrnmr) with inflglw = 0 (cloud optical depth taucld given per band);
+ *     SW icld = 1..3 with inflgsw = 0 (taucld, ssacld, asmcld, fsfcld given per band; layers clear or
+ *     overcast, as the reference requires); SW iaer = 10 (tauaer, ssaaer, asmaer given per band).
+ *     These run in general kernels that are correct but not tuned like the clear-sky path.
+ *   - not built, RRTMG_B200_ERR_UNSUPPORTED: inflglw / inflgsw > 0 (cloud optics from water paths and
+ *     effective radii through the cldprop parameterisations), SW iaer = 6 (ECMWF aerosol climatology).
  *
  * Error behaviour: every function returns 0 on success or one of RRTMG_B200_ERR_*; nothing is ever
  * computed on the CPU and there is no fallback path.  The Fortran `stop 'PARTIAL CLOUD NOT ALLOWED'`
- * (SW rad.nomcica:537) and the unrestated branches (icld > 0, SW iaer != 0) map to error codes.
+ * (SW rad.nomcica:537) maps to RRTMG_B200_ERR_PARTIAL_CLOUD (the general SW path synchronises the
+ * stream to read that flag back, also in the *_device variant).
  */
 #ifndef RRTMG_B200_H
 #define RRTMG_B200_H
@@ -44,7 +55,7 @@ extern "C" {
 
 #define RRTMG_B200_OK 0
 #define RRTMG_B200_ERR_NOT_INITIALIZED 1 /* init not called (cf. FATAL at rrtm_radiation.f90:527-528) */
-#define RRTMG_B200_ERR_UNSUPPORTED 2     /* icld > 0, SW iaer != 0: branch not built yet */
+#define RRTMG_B200_ERR_UNSUPPORTED 2     /* inflglw/inflgsw > 0, SW iaer = 6: branch not built */
 #define RRTMG_B200_ERR_PARTIAL_CLOUD 3   /* SW rad.nomcica:537 */
 #define RRTMG_B200_ERR_BAD_ARGUMENT 4
 #define RRTMG_B200_ERR_CUDA 5            /* see rrtmg_b200_last_error() */

@@ -530,12 +530,20 @@ int pick_chunk(int ncol)
 }
 
 // ------------------------------------------------------------------------------------------------
-int lw_validate(int ncol, int nlay, int *icld, int idrv)
+struct LwOpt {                // the optional cloud arguments of rrtmg_lw
+    int inflglw = 0;
+    const double *cldfr = nullptr, *taucld = nullptr;
+};
+int lw_validate(int ncol, int nlay, int *icld, int idrv, const LwOpt &o = LwOpt())
 {
     if (!G.lw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "rrtmg_b200_lw_init has not been called");
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;     // LW rad.nomcica:437
-    if (icld && *icld != 0) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: icld > 0 (cloudy-sky branch) is not built");
+    if (icld && *icld != 0) {
+        if (o.inflglw != 0)
+            return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: inflglw > 0 (cloud optics from water paths, cldprop parameterisations) is not built");
+        if (!o.cldfr || !o.taucld) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: icld > 0 needs cldfr and taucld");
+    }
     if (idrv != 0 && idrv != 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv must be 0 or 1");
     return RRTMG_B200_OK;
 }
@@ -609,10 +617,11 @@ int sw_err_end(bool general)
     return RRTMG_B200_OK;
 }
 
-int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st, DevBuf *work = nullptr)
+int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st, DevBuf *work = nullptr,
+                   const LwOpt &opt = LwOpt())
 {
     DevBuf &wk = work ? *work : G.lw_work;
-    if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
+    if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;
     if (idrv == 1 && (!out0.duflx_dt || !out0.duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
     if (ncol == 0) return RRTMG_B200_OK;
     const int chunk = pick_chunk(ncol);
@@ -625,8 +634,9 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
         LwOut out = out0;
 #define OFF(p) if (in.p) in.p += c0
         OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
-        OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer);
+        OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer); OFF(cldfr);
 #undef OFF
+        if (in.taucld) in.taucld += (size_t)16 * c0;
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
         if (out.duflx_dt) { out.duflx_dt += c0; out.duflxc_dt += c0; }
         if (const int rc = lw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
@@ -1082,7 +1092,7 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
                          const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                          const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                          const double *ccl4vmr, const double *emis,
-                         int, int, int, const double *, const double *, const double *, const double *,
+                         int inflglw, int, int, const double *cldfr, const double *taucld, const double *, const double *,
                          const double *, const double *,
                          const double *tauaer,
                          double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
@@ -1093,9 +1103,12 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
     LwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer};
+    const LwOpt opt{inflglw, cldfr, taucld};
+    if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;       // also normalises *icld
+    if (icld && *icld >= 1) { in.icld = *icld; in.cldfr = cldfr; in.taucld = taucld; }
     LwOut out{ncol, uflx, dflx, hr, uflxc, dflxc, hrc};
     if (idrv == 1) { out.duflx_dt = duflx_dt; out.duflxc_dt = duflxc_dt; }
-    return lw_device_impl(ncol, nlay, icld, idrv, in, out, (cudaStream_t)stream);
+    return lw_device_impl(ncol, nlay, icld, idrv, in, out, (cudaStream_t)stream, nullptr, opt);
 }
 
 int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
@@ -1110,18 +1123,20 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                   double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                   double *duflx_dt, double *duflxc_dt)
 {
-    (void)inflglw; (void)iceflglw; (void)liqflglw; (void)cldfr; (void)taucld; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
+    (void)iceflglw; (void)liqflglw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
+    const LwOpt opt{inflglw, cldfr, taucld};
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
         !uflxc || !dflxc || !hrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
-    if (const int rc = lw_validate(ncol, nlay, icld, idrv)) return rc;
+    if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;
     if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
     if (ncol == 0) return RRTMG_B200_OK;
+    const bool cloud = icld && *icld >= 1;
     if (P_lw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
-    const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L) * 8 + 32 * 256;
+    const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L + (cloud ? 17 * L : 0)) * 8 + 32 * 256;
     const size_t out_bytes = (size_t)hc * (6 * V + 2 * L) * 8 + 10 * 256;
     LwWork wsz;
     const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields);
@@ -1138,6 +1153,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
         LwIn in{nc, a.up(play, L), a.up(plev, V), a.up(tlay, L), a.up(tlev, V), a.up(tsfc, 1),
                 a.up(h2ovmr, L), a.up(o3vmr, L), a.up(co2vmr, L), a.up(ch4vmr, L), a.up(n2ovmr, L), a.up(o2vmr, L),
                 a.up(cfc11vmr, L), a.up(cfc12vmr, L), a.up(cfc22vmr, L), a.up(ccl4vmr, L), a.up(emis, 16), a.up(tauaer, 16 * L)};
+        if (cloud) { in.icld = *icld; in.cldfr = a.up(cldfr, L); in.taucld = a.up_banded(taucld, 16, L); }
         if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
         Slot o{(char *)P_lw.out[slot].p, 0, c0, nc, ncol, st, true};
         LwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};

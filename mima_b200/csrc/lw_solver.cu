@@ -540,10 +540,412 @@ static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out,
     else launch_tma<AER, LMAX, 2, 4>(t, in, out, w, s);
 }
 
+// =====================================================================================================
+// Cloudy sky (icld >= 1, cloud optical depth given per band: cldprop's inflag = 0, rrtmg_lw_cldprop.f90:154-176).
+// MR = false: random overlap, rrtmg_lw_rtrn.f90:302-316, 371-375, 480-485.  MR = true: maximum/random overlap,
+// rrtmg_lw_rtrnmr.f90:316-479 (overlap factors, one thread per column), :569-588 and :653-674 (the cloudy and clear
+// parts of the radiance carried separately and re-partitioned at every cloudy level).  The layer optics are the three
+// branches of :516-567.  Not MiMA's configuration and not tuned: the layout of lw_rtrn_kernel (block <-> column,
+// thread <-> g-point, the up sweep recomputes the layer quantities), direct loads, block-level g-sums over four
+// values per level (total, clear, and with DRV the two surface-temperature derivatives).
+// =====================================================================================================
+struct LwCloudCell { double atrans, atot, bbd, bbdtot, gassrc, bbugas, bbutot; };
+
+__device__ __forceinline__ void lw_cloud_cell(const double2 *__restrict__ et, double bpade, double secd, double taut, double plfrac,
+                                              double blay, double dplankup, double dplankdn, bool cloudy, double odcld, LwCloudCell &c)
+{
+    const double rec_6 = 0.166667, tblint = 10000.0;
+    double odepth = secd * taut;
+    if (odepth < 0.0) odepth = 0.0;
+    c.atot = 0.0; c.bbdtot = 0.0; c.gassrc = 0.0; c.bbutot = 0.0;
+    if (cloudy) {
+        double odtot = odepth + odcld;
+        if (odtot < 0.06) {
+            c.atrans = odepth - 0.5 * odepth * odepth;
+            const double odepth_rec = rec_6 * odepth;
+            c.gassrc = plfrac * (blay + dplankdn * odepth_rec) * c.atrans;
+            c.atot = odtot - 0.5 * odtot * odtot;
+            const double odtot_rec = rec_6 * odtot;
+            c.bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+            c.bbd = plfrac * (blay + dplankdn * odepth_rec);
+            c.bbugas = plfrac * (blay + dplankup * odepth_rec);
+            c.bbutot = plfrac * (blay + dplankup * odtot_rec);
+        } else if (odepth <= 0.06) {
+            c.atrans = odepth - 0.5 * odepth * odepth;
+            const double odepth_rec = rec_6 * odepth;
+            c.gassrc = plfrac * (blay + dplankdn * odepth_rec) * c.atrans;
+            const double tblind = odtot / (bpade + odtot);
+            const int ittot = (int)(tblint * tblind + 0.5);
+            const double2 e = __ldg(et + ittot);
+            c.bbdtot = plfrac * (blay + e.y * dplankdn);
+            c.bbd = plfrac * (blay + dplankdn * odepth_rec);
+            c.atot = 1. - e.x;
+            c.bbugas = plfrac * (blay + dplankup * odepth_rec);
+            c.bbutot = plfrac * (blay + e.y * dplankup);
+        } else {
+            double tblind = odepth / (bpade + odepth);
+            const int itgas = (int)(tblint * tblind + 0.5);
+            // tau_tbl(itgas) (rrtmg_lw_init.f90:106-123), evaluated instead of stored
+            const double tfn = (double)itgas / tblint;
+            odepth = itgas >= 10000 ? 1.e10 : (itgas <= 0 ? 0.0 : bpade * tfn / (1.0 - tfn));
+            const double2 eg = __ldg(et + itgas);
+            c.atrans = 1. - eg.x;
+            c.gassrc = c.atrans * plfrac * (blay + eg.y * dplankdn);
+            odtot = odepth + odcld;
+            tblind = odtot / (bpade + odtot);
+            const int ittot = (int)(tblint * tblind + 0.5);
+            const double2 e = __ldg(et + ittot);
+            c.bbdtot = plfrac * (blay + e.y * dplankdn);
+            c.bbd = plfrac * (blay + eg.y * dplankdn);
+            c.atot = 1. - e.x;
+            c.bbugas = plfrac * (blay + eg.y * dplankup);
+            c.bbutot = plfrac * (blay + e.y * dplankup);
+        }
+    } else {
+        if (odepth <= 0.06) {
+            c.atrans = odepth - 0.5 * odepth * odepth;
+            odepth = rec_6 * odepth;
+            c.bbd = plfrac * (blay + dplankdn * odepth);
+            c.bbugas = plfrac * (blay + dplankup * odepth);
+        } else {
+            const double tblind = odepth / (bpade + odepth);
+            const int itr = (int)(tblint * tblind + 0.5);
+            const double2 e = __ldg(et + itr);
+            c.atrans = 1. - e.x;
+            c.bbd = plfrac * (blay + e.y * dplankdn);
+            c.bbugas = plfrac * (blay + e.y * dplankup);
+        }
+    }
+}
+
+enum { CF_CLD1, CF_CLD2, CF_CLR1, CF_CLR2, CF_CMB1, CF_CMB2, CF_CLD1D, CF_CLD2D, CF_CLR1D, CF_CLR2D, CF_CMB1D, CF_CMB2D, CF_COUNT };
+
+// maximum/random overlap factors of one column (rtrnmr.f90:326-479); arrays carry the Fortran indices 0..nlayers+1
+__device__ void lw_overlap_factors(int nlayers, const double *cldfrac, const unsigned char *icldlyr, unsigned char *istcld,
+                                   unsigned char *istcldd, double (*f)[MAXLAY + 2])
+{
+    double rat1 = 0., rat2 = 0.;
+    double *faccld1 = f[CF_CLD1], *faccld2 = f[CF_CLD2], *facclr1 = f[CF_CLR1], *facclr2 = f[CF_CLR2], *faccmb1 = f[CF_CMB1], *faccmb2 = f[CF_CMB2];
+    double *faccld1d = f[CF_CLD1D], *faccld2d = f[CF_CLD2D], *facclr1d = f[CF_CLR1D], *facclr2d = f[CF_CLR2D], *faccmb1d = f[CF_CMB1D], *faccmb2d = f[CF_CMB2D];
+    istcld[1] = 1;
+    istcldd[nlayers] = 1;
+    for (int lev = 1; lev <= nlayers; ++lev) {
+        if (icldlyr[lev]) {
+            istcld[lev + 1] = 0;
+            if (lev == nlayers) {
+                faccld1[lev + 1] = 0.; faccld2[lev + 1] = 0.; facclr1[lev + 1] = 0.;
+                facclr2[lev + 1] = 0.; faccmb1[lev + 1] = 0.; faccmb2[lev + 1] = 0.;
+            } else if (cldfrac[lev + 1] >= cldfrac[lev]) {
+                faccld1[lev + 1] = 0.;
+                faccld2[lev + 1] = 0.;
+                if (istcld[lev] == 1) {
+                    facclr1[lev + 1] = 0.;
+                    facclr2[lev + 1] = 0.;
+                    if (cldfrac[lev] < 1.) facclr2[lev + 1] = (cldfrac[lev + 1] - cldfrac[lev]) / (1. - cldfrac[lev]);
+                    facclr2[lev] = 0.;
+                    faccld2[lev] = 0.;
+                } else {
+                    const double fmx = fmax(cldfrac[lev], cldfrac[lev - 1]);
+                    if (cldfrac[lev + 1] > fmx) {
+                        facclr1[lev + 1] = rat2;
+                        facclr2[lev + 1] = (cldfrac[lev + 1] - fmx) / (1. - fmx);
+                    } else if (cldfrac[lev + 1] < fmx) {
+                        facclr1[lev + 1] = (cldfrac[lev + 1] - cldfrac[lev]) / (cldfrac[lev - 1] - cldfrac[lev]);
+                        facclr2[lev + 1] = 0.;
+                    } else {
+                        facclr1[lev + 1] = rat2;
+                        facclr2[lev + 1] = 0.;
+                    }
+                }
+                if (facclr1[lev + 1] > 0. || facclr2[lev + 1] > 0.) { rat1 = 1.; rat2 = 0.; }
+                else { rat1 = 0.; rat2 = 0.; }
+            } else {
+                facclr1[lev + 1] = 0.;
+                facclr2[lev + 1] = 0.;
+                if (istcld[lev] == 1) {
+                    faccld1[lev + 1] = 0.;
+                    faccld2[lev + 1] = (cldfrac[lev] - cldfrac[lev + 1]) / cldfrac[lev];
+                    facclr2[lev] = 0.;
+                    faccld2[lev] = 0.;
+                } else {
+                    const double fmn = fmin(cldfrac[lev], cldfrac[lev - 1]);
+                    if (cldfrac[lev + 1] <= fmn) {
+                        faccld1[lev + 1] = rat1;
+                        faccld2[lev + 1] = (fmn - cldfrac[lev + 1]) / fmn;
+                    } else {
+                        faccld1[lev + 1] = (cldfrac[lev] - cldfrac[lev + 1]) / (cldfrac[lev] - fmn);
+                        faccld2[lev + 1] = 0.;
+                    }
+                }
+                if (faccld1[lev + 1] > 0. || faccld2[lev + 1] > 0.) { rat1 = 0.; rat2 = 1.; }
+                else { rat1 = 0.; rat2 = 0.; }
+            }
+            faccmb1[lev + 1] = facclr1[lev + 1] * faccld2[lev] * cldfrac[lev - 1];
+            faccmb2[lev + 1] = faccld1[lev + 1] * facclr2[lev] * (1. - cldfrac[lev - 1]);
+        } else {
+            istcld[lev + 1] = 1;
+        }
+    }
+    for (int lev = nlayers; lev >= 1; --lev) {
+        if (icldlyr[lev]) {
+            istcldd[lev - 1] = 0;
+            if (lev == 1) {
+                faccld1d[lev - 1] = 0.; faccld2d[lev - 1] = 0.; facclr1d[lev - 1] = 0.;
+                facclr2d[lev - 1] = 0.; faccmb1d[lev - 1] = 0.; faccmb2d[lev - 1] = 0.;
+            } else if (cldfrac[lev - 1] >= cldfrac[lev]) {
+                faccld1d[lev - 1] = 0.;
+                faccld2d[lev - 1] = 0.;
+                if (istcldd[lev] == 1) {
+                    facclr1d[lev - 1] = 0.;
+                    facclr2d[lev - 1] = 0.;
+                    if (cldfrac[lev] < 1.) facclr2d[lev - 1] = (cldfrac[lev - 1] - cldfrac[lev]) / (1. - cldfrac[lev]);
+                    facclr2d[lev] = 0.;
+                    faccld2d[lev] = 0.;
+                } else {
+                    const double fmx = fmax(cldfrac[lev], cldfrac[lev + 1]);
+                    if (cldfrac[lev - 1] > fmx) {
+                        facclr1d[lev - 1] = rat2;
+                        facclr2d[lev - 1] = (cldfrac[lev - 1] - fmx) / (1. - fmx);
+                    } else if (cldfrac[lev - 1] < fmx) {
+                        facclr1d[lev - 1] = (cldfrac[lev - 1] - cldfrac[lev]) / (cldfrac[lev + 1] - cldfrac[lev]);
+                        facclr2d[lev - 1] = 0.;
+                    } else {
+                        facclr1d[lev - 1] = rat2;
+                        facclr2d[lev - 1] = 0.;
+                    }
+                }
+                if (facclr1d[lev - 1] > 0. || facclr2d[lev - 1] > 0.) { rat1 = 1.; rat2 = 0.; }
+                else { rat1 = 0.; rat2 = 0.; }
+            } else {
+                facclr1d[lev - 1] = 0.;
+                facclr2d[lev - 1] = 0.;
+                if (istcldd[lev] == 1) {
+                    faccld1d[lev - 1] = 0.;
+                    faccld2d[lev - 1] = (cldfrac[lev] - cldfrac[lev - 1]) / cldfrac[lev];
+                    facclr2d[lev] = 0.;
+                    faccld2d[lev] = 0.;
+                } else {
+                    const double fmn = fmin(cldfrac[lev], cldfrac[lev + 1]);
+                    if (cldfrac[lev - 1] <= fmn) {
+                        faccld1d[lev - 1] = rat1;
+                        faccld2d[lev - 1] = (fmn - cldfrac[lev - 1]) / fmn;
+                    } else {
+                        faccld1d[lev - 1] = (cldfrac[lev] - cldfrac[lev - 1]) / (cldfrac[lev] - fmn);
+                        faccld2d[lev - 1] = 0.;
+                    }
+                }
+                if (faccld1d[lev - 1] > 0. || faccld2d[lev - 1] > 0.) { rat1 = 0.; rat2 = 1.; }
+                else { rat1 = 0.; rat2 = 0.; }
+            }
+            faccmb1d[lev - 1] = facclr1d[lev - 1] * faccld2d[lev] * cldfrac[lev + 1];
+            faccmb2d[lev - 1] = faccld1d[lev - 1] * facclr2d[lev] * (1. - cldfrac[lev + 1]);
+        } else {
+            istcldd[lev - 1] = 1;
+        }
+    }
+}
+
+template <bool MR, bool DRV>
+__global__ void __launch_bounds__(RT_THREADS) lw_rtrn_cloud_kernel(LwTables T, LwIn in, LwOut out, LwWork w)
+{
+    __shared__ double s_tile[16 * RT_S];
+    __shared__ double s_part[16 * (RT_THREADS / 16 + 1)];
+    __shared__ double s_flux[6][MAXLAY + 1];                 // down, down clear, up, up clear, d up/dT, d up clear/dT
+    __shared__ double s_cf[MAXLAY + 2];                      // cldfrac(0:nlayers+1), zero at both ends
+    __shared__ double s_fac[MR ? CF_COUNT : 1][MAXLAY + 2];
+    __shared__ unsigned char s_cld[MAXLAY + 2], s_opt[MAXLAY + 2], s_st[MAXLAY + 2], s_std[MAXLAY + 2];
+    const int col = blockIdx.x;
+    const int nlay = w.nlay;
+    const int g = threadIdx.x;
+    const bool active = g < NGPTLW;
+    const int band = active ? c_ls.ngb[g] : 0;
+    const size_t ld = (size_t)in.ld;
+    // cloud fraction, cloudy-layer flag (:316-324) and cldprop's test for a layer with cloud optical depth (cldprop.f90:158-168)
+    for (int i = threadIdx.x; i <= nlay + 1; i += RT_THREADS) {
+        double cf = 0.0, tauctot = 0.0;
+        if (i >= 1 && i <= nlay) {
+            cf = in.cldfr[col + (size_t)(i - 1) * ld];
+            for (int ib = 0; ib < 16; ++ib) tauctot = tauctot + in.taucld[ib + 16 * (col + (size_t)(i - 1) * ld)];
+        }
+        s_cf[i] = cf;
+        s_cld[i] = cf >= 1.e-6;
+        s_opt[i] = cf >= 1.e-20 && tauctot >= 1.e-20;
+        s_st[i] = 0; s_std[i] = 0;
+        if (MR)
+            for (int q = 0; q < CF_COUNT; ++q) s_fac[q][i] = 0.0;
+    }
+    __syncthreads();
+    if (MR && threadIdx.x == 0) lw_overlap_factors(nlay, s_cf, s_cld, s_st, s_std, s_fac);
+    __syncthreads();
+
+    const double secd = w.secdiff[(size_t)col * 16 + band];
+    const double wgt = active ? 0.5 * c_ls.delwave[band] : 0.0;
+    const double bpade = c_ls.bpade;
+    const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
+    const double *__restrict__ taug = w.taug + (size_t)col * nlay * NGPTLW + (active ? g : 0);
+    const double *__restrict__ fracs = w.fracs + (size_t)col * nlay * NGPTLW + (active ? g : 0);
+    const double *__restrict__ pl = w.planklay + (size_t)col * nlay * 16 + band;
+    const double *__restrict__ pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
+    const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * ld : nullptr;
+    const double *tcld = in.taucld + band + 16 * (size_t)col;
+
+    auto cell = [&](int lay, LwCloudCell &c) {          // lay 0-based; Fortran lev = lay + 1
+        double taut = taug[(size_t)lay * NGPTLW];
+        if (taer) taut = taut + taer[(size_t)lay * ld];
+        const double blay = __ldg(pl + lay * 16);
+        const bool cloudy = s_cld[lay + 1];
+        const double odcld = cloudy && s_opt[lay + 1] ? secd * tcld[16 * (size_t)lay * ld] : 0.0;
+        lw_cloud_cell(et, bpade, secd, taut, fracs[(size_t)lay * NGPTLW], blay, __ldg(pv + (lay + 1) * 16) - blay,
+                      __ldg(pv + lay * 16) - blay, cloudy, odcld, c);
+        return odcld;
+    };
+
+    // ---- downward sweep
+    double radld = 0.0, radclrd = 0.0, cldradd = 0.0, clrradd = 0.0, rad = 0.0;
+    bool iclddn = false;
+    for (int k = 0; k < nlay; ++k) {
+        const int lay = nlay - 1 - k, lev = lay + 1;
+        LwCloudCell c;
+        const double odcld = cell(lay, c);
+        if (s_cld[lev]) {
+            iclddn = true;
+            const double cf = s_cf[lev];
+            if (MR) {
+                if (s_std[lev]) {
+                    cldradd = cf * radld;
+                    clrradd = radld - cldradd;
+                    rad = 0.;
+                }
+                const double ttot = 1. - c.atot;
+                const double cldsrc = c.bbdtot * c.atot;
+                cldradd = cldradd * ttot + cf * cldsrc;
+                clrradd = clrradd * (1. - c.atrans) + (1. - cf) * c.gassrc;
+                radld = cldradd + clrradd;
+                const double radmod = rad * (s_fac[MR ? CF_CLR1D : 0][lev - 1] * (1. - c.atrans) + s_fac[MR ? CF_CLD1D : 0][lev - 1] * ttot) -
+                                      s_fac[MR ? CF_CMB1D : 0][lev - 1] * c.gassrc + s_fac[MR ? CF_CMB2D : 0][lev - 1] * cldsrc;
+                const double oldcld = cldradd - radmod;
+                const double oldclr = clrradd + radmod;
+                rad = -radmod + s_fac[MR ? CF_CLR2D : 0][lev - 1] * oldclr - s_fac[MR ? CF_CLD2D : 0][lev - 1] * oldcld;
+                cldradd = cldradd + rad;
+                clrradd = clrradd - rad;
+            } else {
+                const double efclfrac = (1. - exp(-odcld)) * cf;
+                radld = radld - radld * (c.atrans + efclfrac * (1. - c.atrans)) + c.gassrc + cf * (c.bbdtot * c.atot - c.gassrc);
+            }
+        } else {
+            radld = radld + (c.bbd - radld) * c.atrans;
+        }
+        if (iclddn) radclrd = radclrd + (c.bbd - radclrd) * c.atrans;
+        else radclrd = radld;
+        if (active) {
+            s_tile[((k & 3) * 4 + 0) * RT_S + g] = radld * wgt;
+            s_tile[((k & 3) * 4 + 1) * RT_S + g] = radclrd * wgt;
+            s_tile[((k & 3) * 4 + 2) * RT_S + g] = 0.0;
+            s_tile[((k & 3) * 4 + 3) * RT_S + g] = 0.0;
+        }
+        if ((k & 3) == 3 || k == nlay - 1) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (k & ~3) + (threadIdx.x >> 2), q = threadIdx.x & 3;
+            if (threadIdx.x < 16 && kk <= k && q < 2) s_flux[q][nlay - 1 - kk] = sum * c_ls.fluxfac;
+        }
+    }
+    if (threadIdx.x < 2) s_flux[threadIdx.x][nlay] = 0.0;
+
+    // ---- surface (:628-647) and upward sweep
+    double radlu = 0.0, radclru = 0.0, cldradu = 0.0, clrradu = 0.0, d_radlu_dt = 0.0, d_radclru_dt = 0.0;
+    rad = 0.0;
+    for (int k = 0; k <= nlay; ++k) {
+        if (k == 0) {
+            const double semiss = in.emis ? in.emis[col + (size_t)band * ld] : 1.0;
+            const double plfrac1 = fracs[0];
+            const double rad0 = plfrac1 * w.plankbnd[(size_t)col * 16 + band];
+            const double reflect = 1. - semiss;
+            radlu = rad0 + reflect * radld;
+            radclru = rad0 + reflect * radclrd;
+            if (DRV) { d_radlu_dt = plfrac1 * w.dplankbnd[(size_t)col * 16 + band]; d_radclru_dt = d_radlu_dt; }
+        } else {
+            const int lay = k - 1, lev = k;
+            LwCloudCell c;
+            const double odcld = cell(lay, c);
+            if (s_cld[lev]) {
+                const double cf = s_cf[lev];
+                const double gassrc = c.bbugas * c.atrans;
+                if (MR) {
+                    if (s_st[lev]) {
+                        cldradu = cf * radlu;
+                        clrradu = radlu - cldradu;
+                        rad = 0.;
+                    }
+                    const double ttot = 1. - c.atot;
+                    const double cldsrc = c.bbutot * c.atot;
+                    cldradu = cldradu * ttot + cf * cldsrc;
+                    clrradu = clrradu * (1.0 - c.atrans) + (1. - cf) * gassrc;
+                    radlu = cldradu + clrradu;
+                    const double radmod = rad * (s_fac[MR ? CF_CLR1 : 0][lev + 1] * (1.0 - c.atrans) + s_fac[MR ? CF_CLD1 : 0][lev + 1] * ttot) -
+                                          s_fac[MR ? CF_CMB1 : 0][lev + 1] * gassrc + s_fac[MR ? CF_CMB2 : 0][lev + 1] * cldsrc;
+                    const double oldcld = cldradu - radmod;
+                    const double oldclr = clrradu + radmod;
+                    rad = -radmod + s_fac[MR ? CF_CLR2 : 0][lev + 1] * oldclr - s_fac[MR ? CF_CLD2 : 0][lev + 1] * oldcld;
+                    cldradu = cldradu + rad;
+                    clrradu = clrradu - rad;
+                } else {
+                    const double efclfrac = (1. - exp(-odcld)) * cf;
+                    radlu = radlu - radlu * (c.atrans + efclfrac * (1. - c.atrans)) + gassrc + cf * (c.bbutot * c.atot - gassrc);
+                }
+                if (DRV) d_radlu_dt = d_radlu_dt * cf * (1.0 - c.atot) + d_radlu_dt * (1.0 - cf) * (1.0 - c.atrans);
+            } else {
+                radlu = radlu + (c.bbugas - radlu) * c.atrans;
+                if (DRV) d_radlu_dt = d_radlu_dt * (1.0 - c.atrans);
+            }
+            if (iclddn) {
+                radclru = radclru + (c.bbugas - radclru) * c.atrans;
+                if (DRV) d_radclru_dt = d_radclru_dt * (1.0 - c.atrans);
+            } else {
+                radclru = radlu;
+                if (DRV) d_radclru_dt = d_radlu_dt;
+            }
+        }
+        if (active) {
+            s_tile[((k & 3) * 4 + 0) * RT_S + g] = radlu * wgt;
+            s_tile[((k & 3) * 4 + 1) * RT_S + g] = radclru * wgt;
+            s_tile[((k & 3) * 4 + 2) * RT_S + g] = d_radlu_dt * wgt;
+            s_tile[((k & 3) * 4 + 3) * RT_S + g] = d_radclru_dt * wgt;
+        }
+        if ((k & 3) == 3 || k == nlay) {
+            const double sum = tile_reduce16<RT_THREADS, NGPTLW, RT_S>(s_tile, s_part);
+            const int kk = (k & ~3) + (threadIdx.x >> 2), q = threadIdx.x & 3;
+            if (threadIdx.x < 16 && kk <= k) s_flux[2 + q][kk] = sum * c_ls.fluxfac;
+        }
+    }
+    __syncthreads();
+
+    // ---- fluxes and heating rates (:751-777), copy-out (rad.nomcica:546-564)
+    for (int lev = threadIdx.x; lev <= nlay; lev += RT_THREADS) {
+        const size_t o = col + (size_t)lev * out.ld;
+        const double u = s_flux[2][lev], d = s_flux[0][lev], uc = s_flux[3][lev], dc = s_flux[1][lev];
+        out.uflx[o] = u; out.dflx[o] = d;
+        out.uflxc[o] = uc; out.dflxc[o] = dc;
+        if (DRV) { out.duflx_dt[o] = s_flux[4][lev]; out.duflxc_dt[o] = s_flux[5][lev]; }
+        if (lev < nlay) {
+            const double pz0 = in.plev[col + (size_t)lev * ld], pz1 = in.plev[col + (size_t)(lev + 1) * ld];
+            out.hr[o] = c_ls.heatfac * ((u - d) - (s_flux[2][lev + 1] - s_flux[0][lev + 1])) / (pz0 - pz1);
+            out.hrc[o] = c_ls.heatfac * ((uc - dc) - (s_flux[3][lev + 1] - s_flux[1][lev + 1])) / (pz0 - pz1);
+        }
+    }
+}
+
 int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
     // variant 2 (default): TMA-fed ring of 2 stages x 4 layers, warp-local g-sums; 3: 3 stages; 1: direct loads, warp-local
     // g-sums; 0: direct loads, block-level g-sums (two barriers per 16 levels)
+    if (in.icld >= 1) {       // cloudy sky: rtrn (icld = 1) or rtrnmr (icld = 2, 3), rad.nomcica:527-541
+        const bool mr = in.icld != 1;
+        if (mr) { if (w.idrv) lw_rtrn_cloud_kernel<true, true><<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w);
+                  else lw_rtrn_cloud_kernel<true, false><<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w); }
+        else { if (w.idrv) lw_rtrn_cloud_kernel<false, true><<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w);
+               else lw_rtrn_cloud_kernel<false, false><<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w); }
+        return 1;
+    }
     if (g_tune.lw_rtrn_variant >= 2 || w.idrv) {        // the derivative outputs are built in the TMA kernel only
         const int v = g_tune.lw_rtrn_variant;
         if (w.nlay <= 64) { if (in.tauaer) launch_tma_pick<true, 64>(t, in, out, w, s, v); else launch_tma_pick<false, 64>(t, in, out, w, s, v); }

@@ -84,6 +84,10 @@ struct LwIn {                 // interface arrays of the current pass (device po
     const double *play, *plev, *tlay, *tlev, *tsfc;
     const double *h2o, *o3, *co2, *ch4, *n2o, *o2, *cfc11, *cfc12, *cfc22, *ccl4;
     const double *emis, *tauaer;  // emis (ld,16); tauaer (ld,nlay,16); either may be null
+    // clouds (icld >= 1, inflglw = 0): icld = 1 random overlap (rtrn), 2/3 maximum/random overlap (rtrnmr)
+    int icld = 0;
+    const double *cldfr = nullptr;    // (ld, nlay)
+    const double *taucld = nullptr;   // (16, ld, nlay)
 };
 
 struct LwOut {

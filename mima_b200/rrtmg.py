@@ -167,7 +167,9 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
     """Returns (uflx, dflx, hr, uflxc, dflxc, hrc); fluxes (ncol, nlay+1) W/m2, heating (ncol, nlay) K/day; with
     idrv = 1 also (duflx_dt, duflxc_dt), the change of the upward flux per K of surface temperature (W/m2/K,
     rad.nomcica:143-152, the Fortran's optional dummies).  ch4vmr..ccl4vmr, emis, tauaer may be None (zeros /
-    emissivity 1).  Cloud arrays are ignored (icld=0)."""
+    emissivity 1).  icld >= 1 takes the cloud fraction cldfr (ncol,nlay) and the band optical depths taucld
+    (16,ncol,nlay) (inflglw = 0): icld = 1 random overlap, 2/3 maximum/random overlap; water-path inputs
+    (inflglw > 0) raise RRTMGError(2)."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
     keep = []
@@ -183,13 +185,19 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
         keep.append(arr)
         ptrs.append(p)
     taer, ptaer = _in(tauaer, (ncol, nlay, NBNDLW), "tauaer", True)
+    cloudp = []
+    for a, shp, nm in ((cldfr, L, "cldfr"), (taucld, (NBNDLW, ncol, nlay), "taucld"), (cicewp, L, "cicewp"),
+                       (cliqwp, L, "cliqwp"), (reice, L, "reice"), (reliq, L, "reliq")):
+        arr, p = _in(a, shp, nm, True)
+        keep.append(arr)
+        cloudp.append(p)
     out = [np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F"),
            np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
     if int(idrv) == 1:
         out += [np.empty(V, order="F"), np.empty(V, order="F")]
     icld_c = C.c_int(int(icld))
     rc = lib().rrtmg_b200_lw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.c_int(int(idrv)), *ptrs,
-                             C.c_int(inflglw), C.c_int(iceflglw), C.c_int(liqflglw), None, None, None, None, None, None,
+                             C.c_int(inflglw), C.c_int(iceflglw), C.c_int(liqflglw), *cloudp,
                              ptaer, *[o.ctypes.data_as(_dp) for o in out], *([] if int(idrv) == 1 else [None, None]))
     _check(rc)
     return tuple(out)
@@ -249,10 +257,10 @@ def _opt(a):
     return None if (a is None or not np.any(a)) else a
 
 
-def lw_from_columns(c, tauaer=None, idrv=0):
-    return rrtmg_lw(c.ncol, c.nlay, 0, idrv, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
+def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0):
+    return rrtmg_lw(c.ncol, c.nlay, icld, idrv, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), _opt(c.cfc11), _opt(c.cfc12), _opt(c.cfc22), _opt(c.ccl4),
-                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer)
+                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, **(clouds or {}))
 
 
 def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0):

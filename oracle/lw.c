@@ -52,6 +52,9 @@ typedef struct {
     double totuflux[NL], totdflux[NL], fnet[NL], htr[NL];
     double totuclfl[NL], totdclfl[NL], fnetc[NL], htrc[NL];
     double oneminus, fluxfac;
+    /* clouds (icld >= 1): inatm :868-887, cldprop inflag = 0 (cldprop.f90:154-176); cldfrac[0] and cldfrac[nlayers+1]
+       are the out-of-range elements rtrnmr.f90:403-404, 472-473 multiply by factors that are zero there */
+    double cldfrac[NL + 2], taucloud[NL][17];
 } lwcol_t;
 
 /* ---------------------------------------------------------------- inatm (rad.nomcica:572-901) */
@@ -1129,6 +1132,421 @@ static void rtrnmr_clear(lwcol_t *c)
     c->htrc[nlayers] = 0.0;
 }
 
+/* ---------------------------------------------------------------- cloudy sky: rtrn (random overlap, icld = 1,
+   rrtmg_lw_rtrn.f90:262-588) and rtrnmr (maximum/random overlap, icld = 2, 3, rrtmg_lw_rtrnmr.f90:259-779) in one body:
+   the two share the layer optics (:514-567) and differ in how the cloudy and clear parts of a level are carried. */
+static void rtrn_cloudy(lwcol_t *c, int maxrandom)
+{
+    const orc_state_t *S = &g_orc;
+    const int nlayers = c->nlayers;
+    const double tblint = 10000.0, bpade = S->lw_bpade;
+    const double wtdiff = 0.5, rec_6 = 0.166667;
+    static const double a0[16] = {1.66, 1.55, 1.58, 1.66, 1.54, 1.454, 1.89, 1.33, 1.668, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66, 1.66};
+    static const double a1[16] = {0.00, 0.25, 0.22, 0.00, 0.13, 0.446, -0.10, 0.40, -0.006, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    static const double a2[16] = {0.00, -12.0, -11.7, 0.00, -0.72, -0.243, 0.19, -0.062, 0.414, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00, 0.00};
+    double secdiff[17], atrans[NL], atot[NL], bbugas[NL], bbutot[NL], urad[NL], drad[NL], clrurad[NL], clrdrad[NL];
+    double d_urad_dt[NL], d_clrurad_dt[NL];
+    static __thread double odcld[NL][17], abscld[NL][17], efclfrac[NL][17];
+    double faccld1[NL + 2], faccld2[NL + 2], facclr1[NL + 2], facclr2[NL + 2], faccmb1[NL + 2], faccmb2[NL + 2];
+    double faccld1d[NL + 2], faccld2d[NL + 2], facclr1d[NL + 2], facclr2d[NL + 2], faccmb1d[NL + 2], faccmb2d[NL + 2];
+    int icldlyr[NL + 2], istcld[NL + 2], istcldd[NL + 2];
+    const double *cldfrac = c->cldfrac;
+    const int idrv = c->idrv;
+    double rat1 = 0., rat2 = 0., fmx, fmn;
+    int igc, lev, iband, ibnd, l;
+
+    for (ibnd = 1; ibnd <= 16; ++ibnd) {
+        if (ibnd == 1 || ibnd == 4 || ibnd >= 10) {
+            secdiff[ibnd] = 1.66;
+        } else {
+            secdiff[ibnd] = a0[ibnd - 1] + a1[ibnd - 1] * exp(a2[ibnd - 1] * c->pwvcm);
+            if (secdiff[ibnd] > 1.80) secdiff[ibnd] = 1.80;
+            if (secdiff[ibnd] < 1.50) secdiff[ibnd] = 1.50;
+        }
+    }
+    for (lev = 0; lev <= nlayers + 1; ++lev) {
+        faccld1[lev] = faccld2[lev] = facclr1[lev] = facclr2[lev] = faccmb1[lev] = faccmb2[lev] = 0.;
+        faccld1d[lev] = faccld2d[lev] = facclr1d[lev] = facclr2d[lev] = faccmb1d[lev] = faccmb2d[lev] = 0.;
+        icldlyr[lev] = 0; istcld[lev] = 0; istcldd[lev] = 0;
+    }
+    for (lev = 0; lev <= nlayers; ++lev) {
+        urad[lev] = 0.0; drad[lev] = 0.0; clrurad[lev] = 0.0; clrdrad[lev] = 0.0;
+        c->totuflux[lev] = 0.0; c->totdflux[lev] = 0.0; c->totuclfl[lev] = 0.0; c->totdclfl[lev] = 0.0;
+        d_urad_dt[lev] = 0.0; d_clrurad_dt[lev] = 0.0;
+        c->dtotuflux_dt[lev] = 0.0; c->dtotuclfl_dt[lev] = 0.0;
+    }
+    /* cloud optical depth along the diffusivity angle (rtrnmr :316-324, rtrn :302-316); ncbands = 16 <=> ib = iband */
+    for (int lay = 1; lay <= nlayers; ++lay)
+        for (int ib = 1; ib <= 16; ++ib) {
+            if (cldfrac[lay] >= 1.e-6) {
+                odcld[lay][ib] = secdiff[ib] * c->taucloud[lay][ib];
+                if (!maxrandom) {
+                    double transcld = exp(-odcld[lay][ib]);
+                    abscld[lay][ib] = 1. - transcld;
+                    efclfrac[lay][ib] = abscld[lay][ib] * cldfrac[lay];
+                }
+                icldlyr[lay] = 1;
+            } else {
+                odcld[lay][ib] = 0.0;
+                abscld[lay][ib] = 0.0;
+                efclfrac[lay][ib] = 0.0;
+                icldlyr[lay] = 0;
+            }
+        }
+    if (maxrandom) {
+        /* maximum/random overlap factors, upward (:328-407) */
+        istcld[1] = 1;
+        istcldd[nlayers] = 1;
+        for (lev = 1; lev <= nlayers; ++lev) {
+            if (icldlyr[lev] == 1) {
+                istcld[lev + 1] = 0;
+                if (lev == nlayers) {
+                    faccld1[lev + 1] = 0.; faccld2[lev + 1] = 0.; facclr1[lev + 1] = 0.;
+                    facclr2[lev + 1] = 0.; faccmb1[lev + 1] = 0.; faccmb2[lev + 1] = 0.;
+                } else if (cldfrac[lev + 1] >= cldfrac[lev]) {
+                    faccld1[lev + 1] = 0.;
+                    faccld2[lev + 1] = 0.;
+                    if (istcld[lev] == 1) {
+                        facclr1[lev + 1] = 0.;
+                        facclr2[lev + 1] = 0.;
+                        if (cldfrac[lev] < 1.) facclr2[lev + 1] = (cldfrac[lev + 1] - cldfrac[lev]) / (1. - cldfrac[lev]);
+                        facclr2[lev] = 0.;
+                        faccld2[lev] = 0.;
+                    } else {
+                        fmx = fmax(cldfrac[lev], cldfrac[lev - 1]);
+                        if (cldfrac[lev + 1] > fmx) {
+                            facclr1[lev + 1] = rat2;
+                            facclr2[lev + 1] = (cldfrac[lev + 1] - fmx) / (1. - fmx);
+                        } else if (cldfrac[lev + 1] < fmx) {
+                            facclr1[lev + 1] = (cldfrac[lev + 1] - cldfrac[lev]) / (cldfrac[lev - 1] - cldfrac[lev]);
+                            facclr2[lev + 1] = 0.;
+                        } else {
+                            facclr1[lev + 1] = rat2;
+                            facclr2[lev + 1] = 0.;
+                        }
+                    }
+                    if (facclr1[lev + 1] > 0. || facclr2[lev + 1] > 0.) { rat1 = 1.; rat2 = 0.; }
+                    else { rat1 = 0.; rat2 = 0.; }
+                } else {
+                    facclr1[lev + 1] = 0.;
+                    facclr2[lev + 1] = 0.;
+                    if (istcld[lev] == 1) {
+                        faccld1[lev + 1] = 0.;
+                        faccld2[lev + 1] = (cldfrac[lev] - cldfrac[lev + 1]) / cldfrac[lev];
+                        facclr2[lev] = 0.;
+                        faccld2[lev] = 0.;
+                    } else {
+                        fmn = fmin(cldfrac[lev], cldfrac[lev - 1]);
+                        if (cldfrac[lev + 1] <= fmn) {
+                            faccld1[lev + 1] = rat1;
+                            faccld2[lev + 1] = (fmn - cldfrac[lev + 1]) / fmn;
+                        } else {
+                            faccld1[lev + 1] = (cldfrac[lev] - cldfrac[lev + 1]) / (cldfrac[lev] - fmn);
+                            faccld2[lev + 1] = 0.;
+                        }
+                    }
+                    if (faccld1[lev + 1] > 0. || faccld2[lev + 1] > 0.) { rat1 = 0.; rat2 = 1.; }
+                    else { rat1 = 0.; rat2 = 0.; }
+                }
+                faccmb1[lev + 1] = facclr1[lev + 1] * faccld2[lev] * cldfrac[lev - 1];
+                faccmb2[lev + 1] = faccld1[lev + 1] * facclr2[lev] * (1. - cldfrac[lev - 1]);
+            } else {
+                istcld[lev + 1] = 1;
+            }
+        }
+        /* downward (:409-479); rat1, rat2 carry over from the upward pass as in the Fortran */
+        for (lev = nlayers; lev >= 1; --lev) {
+            if (icldlyr[lev] == 1) {
+                istcldd[lev - 1] = 0;
+                if (lev == 1) {
+                    faccld1d[lev - 1] = 0.; faccld2d[lev - 1] = 0.; facclr1d[lev - 1] = 0.;
+                    facclr2d[lev - 1] = 0.; faccmb1d[lev - 1] = 0.; faccmb2d[lev - 1] = 0.;
+                } else if (cldfrac[lev - 1] >= cldfrac[lev]) {
+                    faccld1d[lev - 1] = 0.;
+                    faccld2d[lev - 1] = 0.;
+                    if (istcldd[lev] == 1) {
+                        facclr1d[lev - 1] = 0.;
+                        facclr2d[lev - 1] = 0.;
+                        if (cldfrac[lev] < 1.) facclr2d[lev - 1] = (cldfrac[lev - 1] - cldfrac[lev]) / (1. - cldfrac[lev]);
+                        facclr2d[lev] = 0.;
+                        faccld2d[lev] = 0.;
+                    } else {
+                        fmx = fmax(cldfrac[lev], cldfrac[lev + 1]);
+                        if (cldfrac[lev - 1] > fmx) {
+                            facclr1d[lev - 1] = rat2;
+                            facclr2d[lev - 1] = (cldfrac[lev - 1] - fmx) / (1. - fmx);
+                        } else if (cldfrac[lev - 1] < fmx) {
+                            facclr1d[lev - 1] = (cldfrac[lev - 1] - cldfrac[lev]) / (cldfrac[lev + 1] - cldfrac[lev]);
+                            facclr2d[lev - 1] = 0.;
+                        } else {
+                            facclr1d[lev - 1] = rat2;
+                            facclr2d[lev - 1] = 0.;
+                        }
+                    }
+                    if (facclr1d[lev - 1] > 0. || facclr2d[lev - 1] > 0.) { rat1 = 1.; rat2 = 0.; }
+                    else { rat1 = 0.; rat2 = 0.; }
+                } else {
+                    facclr1d[lev - 1] = 0.;
+                    facclr2d[lev - 1] = 0.;
+                    if (istcldd[lev] == 1) {
+                        faccld1d[lev - 1] = 0.;
+                        faccld2d[lev - 1] = (cldfrac[lev] - cldfrac[lev - 1]) / cldfrac[lev];
+                        facclr2d[lev] = 0.;
+                        faccld2d[lev] = 0.;
+                    } else {
+                        fmn = fmin(cldfrac[lev], cldfrac[lev + 1]);
+                        if (cldfrac[lev - 1] <= fmn) {
+                            faccld1d[lev - 1] = rat1;
+                            faccld2d[lev - 1] = (fmn - cldfrac[lev - 1]) / fmn;
+                        } else {
+                            faccld1d[lev - 1] = (cldfrac[lev] - cldfrac[lev - 1]) / (cldfrac[lev] - fmn);
+                            faccld2d[lev - 1] = 0.;
+                        }
+                    }
+                    if (faccld1d[lev - 1] > 0. || faccld2d[lev - 1] > 0.) { rat1 = 0.; rat2 = 1.; }
+                    else { rat1 = 0.; rat2 = 0.; }
+                }
+                faccmb1d[lev - 1] = facclr1d[lev - 1] * faccld2d[lev] * cldfrac[lev + 1];
+                faccmb2d[lev - 1] = faccld1d[lev - 1] * facclr2d[lev] * (1. - cldfrac[lev + 1]);
+            } else {
+                istcldd[lev - 1] = 1;
+            }
+        }
+    }
+
+    igc = 1;
+    for (iband = 1; iband <= 16; ++iband) {
+        const int ib = iband;            /* ipat(iband, 2), ncbands = 16 */
+        do {
+            double radld = 0., radclrd = 0., radlu, radclru, rad0, reflect;
+            double cldradd = 0., clrradd = 0., cldradu = 0., clrradu = 0., oldcld, oldclr, rad = 0., radmod;
+            int iclddn = 0;
+            for (lev = nlayers; lev >= 1; --lev) {
+                double plfrac = c->fracs[igc][lev];
+                double blay = c->planklay[lev][iband];
+                double dplankup = c->planklev[lev][iband] - blay;
+                double dplankdn = c->planklev[lev - 1][iband] - blay;
+                double odepth = secdiff[iband] * c->taut[igc][lev];
+                double bbd, gassrc = 0., bbdtot = 0.;
+                if (odepth < 0.0) odepth = 0.0;
+                if (icldlyr[lev] == 1) {
+                    iclddn = 1;
+                    double odtot = odepth + odcld[lev][ib];
+                    if (odtot < 0.06) {
+                        atrans[lev] = odepth - 0.5 * odepth * odepth;
+                        double odepth_rec = rec_6 * odepth;
+                        gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans[lev];
+                        atot[lev] = odtot - 0.5 * odtot * odtot;
+                        double odtot_rec = rec_6 * odtot;
+                        bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+                        bbd = plfrac * (blay + dplankdn * odepth_rec);
+                        bbugas[lev] = plfrac * (blay + dplankup * odepth_rec);
+                        bbutot[lev] = plfrac * (blay + dplankup * odtot_rec);
+                    } else if (odepth <= 0.06) {
+                        atrans[lev] = odepth - 0.5 * odepth * odepth;
+                        double odepth_rec = rec_6 * odepth;
+                        gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans[lev];
+                        odtot = odepth + odcld[lev][ib];
+                        double tblind = odtot / (bpade + odtot);
+                        int ittot = (int)(tblint * tblind + 0.5);
+                        double tfactot = S->tfn_tbl[ittot];
+                        bbdtot = plfrac * (blay + tfactot * dplankdn);
+                        bbd = plfrac * (blay + dplankdn * odepth_rec);
+                        atot[lev] = 1. - S->exp_tbl[ittot];
+                        bbugas[lev] = plfrac * (blay + dplankup * odepth_rec);
+                        bbutot[lev] = plfrac * (blay + tfactot * dplankup);
+                    } else {
+                        double tblind = odepth / (bpade + odepth);
+                        int itgas = (int)(tblint * tblind + 0.5);
+                        odepth = S->tau_tbl[itgas];
+                        atrans[lev] = 1. - S->exp_tbl[itgas];
+                        double tfacgas = S->tfn_tbl[itgas];
+                        gassrc = atrans[lev] * plfrac * (blay + tfacgas * dplankdn);
+                        odtot = odepth + odcld[lev][ib];
+                        tblind = odtot / (bpade + odtot);
+                        int ittot = (int)(tblint * tblind + 0.5);
+                        double tfactot = S->tfn_tbl[ittot];
+                        bbdtot = plfrac * (blay + tfactot * dplankdn);
+                        bbd = plfrac * (blay + tfacgas * dplankdn);
+                        atot[lev] = 1. - S->exp_tbl[ittot];
+                        bbugas[lev] = plfrac * (blay + tfacgas * dplankup);
+                        bbutot[lev] = plfrac * (blay + tfactot * dplankup);
+                    }
+                    if (maxrandom) { /* rtrnmr :569-588 */
+                        if (istcldd[lev] == 1) {
+                            cldradd = cldfrac[lev] * radld;
+                            clrradd = radld - cldradd;
+                            oldcld = cldradd;
+                            oldclr = clrradd;
+                            rad = 0.;
+                        }
+                        double ttot = 1. - atot[lev];
+                        double cldsrc = bbdtot * atot[lev];
+                        cldradd = cldradd * ttot + cldfrac[lev] * cldsrc;
+                        clrradd = clrradd * (1. - atrans[lev]) + (1. - cldfrac[lev]) * gassrc;
+                        radld = cldradd + clrradd;
+                        drad[lev - 1] = drad[lev - 1] + radld;
+                        radmod = rad * (facclr1d[lev - 1] * (1. - atrans[lev]) + faccld1d[lev - 1] * ttot) -
+                                 faccmb1d[lev - 1] * gassrc + faccmb2d[lev - 1] * cldsrc;
+                        oldcld = cldradd - radmod;
+                        oldclr = clrradd + radmod;
+                        rad = -radmod + facclr2d[lev - 1] * oldclr - faccld2d[lev - 1] * oldcld;
+                        cldradd = cldradd + rad;
+                        clrradd = clrradd - rad;
+                    } else { /* rtrn :371-375 (the same statement in its three branches) */
+                        radld = radld - radld * (atrans[lev] + efclfrac[lev][ib] * (1. - atrans[lev])) + gassrc +
+                                cldfrac[lev] * (bbdtot * atot[lev] - gassrc);
+                        drad[lev - 1] = drad[lev - 1] + radld;
+                    }
+                } else {
+                    if (odepth <= 0.06) {
+                        atrans[lev] = odepth - 0.5 * odepth * odepth;
+                        odepth = rec_6 * odepth;
+                        bbd = plfrac * (blay + dplankdn * odepth);
+                        bbugas[lev] = plfrac * (blay + dplankup * odepth);
+                    } else {
+                        double tblind = odepth / (bpade + odepth);
+                        int itr = (int)(tblint * tblind + 0.5);
+                        double transc = S->exp_tbl[itr];
+                        atrans[lev] = 1. - transc;
+                        double tausfac = S->tfn_tbl[itr];
+                        bbd = plfrac * (blay + tausfac * dplankdn);
+                        bbugas[lev] = plfrac * (blay + tausfac * dplankup);
+                    }
+                    radld = radld + (bbd - radld) * atrans[lev];
+                    drad[lev - 1] = drad[lev - 1] + radld;
+                }
+                if (iclddn == 1) {
+                    radclrd = radclrd + (bbd - radclrd) * atrans[lev];
+                    clrdrad[lev - 1] = clrdrad[lev - 1] + radclrd;
+                } else {
+                    radclrd = radld;
+                    clrdrad[lev - 1] = drad[lev - 1];
+                }
+            }
+            rad0 = c->fracs[igc][1] * c->plankbnd[iband];
+            reflect = 1. - c->semiss[iband];
+            radlu = rad0 + reflect * radld;
+            radclru = rad0 + reflect * radclrd;
+            double d_rad0_dt = 0., d_radlu_dt = 0., d_radclru_dt = 0.;
+            if (idrv == 1) d_rad0_dt = c->fracs[igc][1] * c->dplankbnd_dt[iband];
+            urad[0] = urad[0] + radlu;
+            clrurad[0] = clrurad[0] + radclru;
+            if (idrv == 1) {
+                d_radlu_dt = d_rad0_dt;
+                d_urad_dt[0] = d_urad_dt[0] + d_radlu_dt;
+                d_radclru_dt = d_rad0_dt;
+                d_clrurad_dt[0] = d_clrurad_dt[0] + d_radclru_dt;
+            }
+            for (lev = 1; lev <= nlayers; ++lev) {
+                if (icldlyr[lev] == 1) {
+                    double gassrc = bbugas[lev] * atrans[lev];
+                    if (maxrandom) { /* rtrnmr :653-674 */
+                        if (istcld[lev] == 1) {
+                            cldradu = cldfrac[lev] * radlu;
+                            clrradu = radlu - cldradu;
+                            oldcld = cldradu;
+                            oldclr = clrradu;
+                            rad = 0.;
+                        }
+                        double ttot = 1. - atot[lev];
+                        double cldsrc = bbutot[lev] * atot[lev];
+                        cldradu = cldradu * ttot + cldfrac[lev] * cldsrc;
+                        clrradu = clrradu * (1.0 - atrans[lev]) + (1. - cldfrac[lev]) * gassrc;
+                        radlu = cldradu + clrradu;
+                        urad[lev] = urad[lev] + radlu;
+                        radmod = rad * (facclr1[lev + 1] * (1.0 - atrans[lev]) + faccld1[lev + 1] * ttot) -
+                                 faccmb1[lev + 1] * gassrc + faccmb2[lev + 1] * cldsrc;
+                        oldcld = cldradu - radmod;
+                        oldclr = clrradu + radmod;
+                        rad = -radmod + facclr2[lev + 1] * oldclr - faccld2[lev + 1] * oldcld;
+                        cldradu = cldradu + rad;
+                        clrradu = clrradu - rad;
+                    } else { /* rtrn :480-485 */
+                        radlu = radlu - radlu * (atrans[lev] + efclfrac[lev][ib] * (1. - atrans[lev])) + gassrc +
+                                cldfrac[lev] * (bbutot[lev] * atot[lev] - gassrc);
+                        urad[lev] = urad[lev] + radlu;
+                    }
+                    if (idrv == 1) {
+                        d_radlu_dt = d_radlu_dt * cldfrac[lev] * (1.0 - atot[lev]) +
+                                     d_radlu_dt * (1.0 - cldfrac[lev]) * (1.0 - atrans[lev]);
+                        d_urad_dt[lev] = d_urad_dt[lev] + d_radlu_dt;
+                    }
+                } else {
+                    radlu = radlu + (bbugas[lev] - radlu) * atrans[lev];
+                    urad[lev] = urad[lev] + radlu;
+                    if (idrv == 1) {
+                        d_radlu_dt = d_radlu_dt * (1.0 - atrans[lev]);
+                        d_urad_dt[lev] = d_urad_dt[lev] + d_radlu_dt;
+                    }
+                }
+                if (iclddn == 1) {
+                    radclru = radclru + (bbugas[lev] - radclru) * atrans[lev];
+                    clrurad[lev] = clrurad[lev] + radclru;
+                } else {
+                    radclru = radlu;
+                    clrurad[lev] = urad[lev];
+                }
+                if (idrv == 1) {
+                    if (iclddn == 1) {
+                        d_radclru_dt = d_radclru_dt * (1.0 - atrans[lev]);
+                        d_clrurad_dt[lev] = d_clrurad_dt[lev] + d_radclru_dt;
+                    } else {
+                        d_radclru_dt = d_radlu_dt;
+                        d_clrurad_dt[lev] = d_urad_dt[lev];
+                    }
+                }
+            }
+            (void)oldcld; (void)oldclr;
+            igc = igc + 1;
+        } while (igc <= ngs[iband - 1]);
+
+        for (lev = nlayers; lev >= 0; --lev) {
+            double uflux = urad[lev] * wtdiff;
+            double dflux = drad[lev] * wtdiff;
+            urad[lev] = 0.0;
+            drad[lev] = 0.0;
+            c->totuflux[lev] = c->totuflux[lev] + uflux * delwave[iband - 1];
+            c->totdflux[lev] = c->totdflux[lev] + dflux * delwave[iband - 1];
+            double uclfl = clrurad[lev] * wtdiff;
+            double dclfl = clrdrad[lev] * wtdiff;
+            clrurad[lev] = 0.0;
+            clrdrad[lev] = 0.0;
+            c->totuclfl[lev] = c->totuclfl[lev] + uclfl * delwave[iband - 1];
+            c->totdclfl[lev] = c->totdclfl[lev] + dclfl * delwave[iband - 1];
+        }
+        if (idrv == 1) {
+            for (lev = nlayers; lev >= 0; --lev) {
+                double duflux_dt = d_urad_dt[lev] * wtdiff;
+                d_urad_dt[lev] = 0.0;
+                c->dtotuflux_dt[lev] = c->dtotuflux_dt[lev] + duflux_dt * delwave[iband - 1] * c->fluxfac;
+                double duclfl_dt = d_clrurad_dt[lev] * wtdiff;
+                d_clrurad_dt[lev] = 0.0;
+                c->dtotuclfl_dt[lev] = c->dtotuclfl_dt[lev] + duclfl_dt * delwave[iband - 1] * c->fluxfac;
+            }
+        }
+    }
+    c->totuflux[0] = c->totuflux[0] * c->fluxfac;
+    c->totdflux[0] = c->totdflux[0] * c->fluxfac;
+    c->fnet[0] = c->totuflux[0] - c->totdflux[0];
+    c->totuclfl[0] = c->totuclfl[0] * c->fluxfac;
+    c->totdclfl[0] = c->totdclfl[0] * c->fluxfac;
+    c->fnetc[0] = c->totuclfl[0] - c->totdclfl[0];
+    for (lev = 1; lev <= nlayers; ++lev) {
+        c->totuflux[lev] = c->totuflux[lev] * c->fluxfac;
+        c->totdflux[lev] = c->totdflux[lev] * c->fluxfac;
+        c->fnet[lev] = c->totuflux[lev] - c->totdflux[lev];
+        c->totuclfl[lev] = c->totuclfl[lev] * c->fluxfac;
+        c->totdclfl[lev] = c->totdclfl[lev] * c->fluxfac;
+        c->fnetc[lev] = c->totuclfl[lev] - c->totdclfl[lev];
+        l = lev - 1;
+        c->htr[l] = S->lw_heatfac * (c->fnet[l] - c->fnet[lev]) / (c->pz[l] - c->pz[lev]);
+        c->htrc[l] = S->lw_heatfac * (c->fnetc[l] - c->fnetc[lev]) / (c->pz[l] - c->pz[lev]);
+    }
+    c->htr[nlayers] = 0.0;
+    c->htrc[nlayers] = 0.0;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP
@@ -1145,12 +1563,16 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
+                 int inflglw, const double *cldfr, const double *taucld,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                  double *duflx_dt, double *duflxc_dt,
                  const orc_lw_stages_t *st, int nthreads)
 {
     if (!g_orc.ready) return 1;
-    if (icld != 0 || idrv < 0 || idrv > 1) return 2; /* the cloudy branches are not restated */
+    if (icld < 0 || icld > 3) icld = 2; /* :437 */
+    if (idrv < 0 || idrv > 1) return 2;
+    if (icld >= 1 && inflglw != 0) return 2; /* cldprop's water-path parameterisations are not restated */
+    if (icld >= 1 && (!cldfr || !taucld)) return 3;
     if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return 3;
     if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
     if (nthreads < 1) nthreads = 1;
@@ -1175,6 +1597,21 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
             inatm(c, iplon, ncol, nlay, iaer, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr,
                   n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer);
             /* cldprop with cldfrac=0: ncbands=1, taucloud=0 -- nothing to compute */
+            if (icld >= 1) {
+                /* inatm :868-887 and cldprop inflag = 0 (cldprop.f90:154-176, cwp = 0) */
+                const double cldmin = 1.e-20;
+                c->cldfrac[0] = 0.; c->cldfrac[nlay + 1] = 0.;
+                for (int l = 1; l <= nlay; ++l) {
+                    double tauctot = 0.;
+                    c->cldfrac[l] = cldfr[(long)(l - 1) * ncol + iplon - 1];
+                    for (int ib = 1; ib <= 16; ++ib) {
+                        c->taucloud[l][ib] = 0.0;
+                        tauctot = tauctot + taucld[(ib - 1) + 16 * ((iplon - 1) + (long)ncol * (l - 1))];
+                    }
+                    if (c->cldfrac[l] >= cldmin && tauctot >= cldmin)
+                        for (int ib = 1; ib <= 16; ++ib) c->taucloud[l][ib] = taucld[(ib - 1) + 16 * ((iplon - 1) + (long)ncol * (l - 1))];
+                }
+            }
             setcoef(c, istart);
             taumol(c);
             /* :514-519, iaer=10 */
@@ -1184,7 +1621,8 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                     while (ig > ngs[b]) ++b; /* ngb(ig) */
                     c->taut[ig][k] = c->taug[ig][k] + c->taua[k][b + 1];
                 }
-            rtrnmr_clear(c);
+            if (icld == 0) rtrnmr_clear(c);
+            else rtrn_cloudy(c, icld != 1); /* rad.nomcica:527-541 */
             const long i0 = iplon - 1;
             for (int k = 0; k <= nlay; ++k) {
                 uflx[(long)k * ncol + i0] = c->totuflux[k];

@@ -76,7 +76,10 @@ class Oracle:
         return np.ctypeslib.as_array(p, shape=(n,)).copy()
 
     # ------------------------------------------------------------------ LW
-    def rrtmg_lw(self, cols, *, stages: bool = False, nthreads: int | None = None, tauaer=None, idrv: int = 0):
+    def rrtmg_lw(self, cols, *, stages: bool = False, nthreads: int | None = None, tauaer=None, idrv: int = 0,
+                 icld: int = 0, clouds=None):
+        """clouds = dict(cldfr (ncol,nlay), taucld (16,ncol,nlay)) for icld >= 1 (inflglw = 0): icld = 1 random overlap
+        (rtrn), 2/3 maximum/random overlap (rtrnmr)."""
         ncol, nlay = cols.ncol, cols.nlay
         nthreads = nthreads or self.max_threads
         out = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("uflx", "dflx", "uflxc", "dflxc")}
@@ -102,7 +105,9 @@ class Oracle:
                                cols.emis, tauaer)]
         if idrv:
             out.update({k: np.zeros((ncol, nlay + 1), order="F") for k in ("duflx_dt", "duflxc_dt")})
-        rc = self.lib.orc_rrtmg_lw(C.c_int(ncol), C.c_int(nlay), C.c_int(0), C.c_int(int(idrv)), *[_p(a) for a in ins],
+        cl = [None, None] if clouds is None else [_f(clouds["cldfr"]), _f(clouds["taucld"])]
+        rc = self.lib.orc_rrtmg_lw(C.c_int(ncol), C.c_int(nlay), C.c_int(int(icld)), C.c_int(int(idrv)), *[_p(a) for a in ins],
+                                   C.c_int(0), *[None if a is None else _p(a) for a in cl],
                                    _p(out["uflx"]), _p(out["dflx"]), _p(out["hr"]), _p(out["uflxc"]),
                                    _p(out["dflxc"]), _p(out["hrc"]),
                                    _p(out["duflx_dt"]) if idrv else None, _p(out["duflxc_dt"]) if idrv else None,

@@ -134,6 +134,7 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
+                 int inflglw, const double *cldfr, const double *taucld,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                  double *duflx_dt, double *duflxc_dt, /* (ncol, nlay+1), written when idrv == 1; may be NULL otherwise */
                  const orc_lw_stages_t *stages, int nthreads);

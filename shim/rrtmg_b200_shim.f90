@@ -115,16 +115,25 @@ contains
     real(c_double), contiguous, target, intent(out) :: uflx(:,:), dflx(:,:), hr(:,:), uflxc(:,:), dflxc(:,:), hrc(:,:)
     real(c_double), contiguous, target, intent(out), optional :: duflx_dt(:,:), duflxc_dt(:,:)
     integer(c_int) :: icld_c
-    type(c_ptr) :: pemis, paer
+    type(c_ptr) :: pemis, paer, pcldfr, ptaucld, pdu, pduc
     icld_c = icld
     pemis = c_null_ptr; if (any(emis /= 1._c_double)) pemis = c_loc(emis)
     paer = c_null_ptr;  if (any(tauaer /= 0._c_double)) paer = c_loc(tauaer)
-    ! cloud arrays are never dereferenced for icld = 0 (as in the reference); pass NULL
+    ! cloud arrays are never dereferenced for icld = 0 (as in the reference); pass NULL.  With icld > 0 the library
+    ! takes the cloud fraction and the band optical depths (inflglw = 0); water-path inputs return error 2.
+    pcldfr = c_null_ptr; ptaucld = c_null_ptr
+    if (icld /= 0) then
+       pcldfr = c_loc(cldfr); ptaucld = c_loc(taucld)
+    endif
+    pdu = c_null_ptr; pduc = c_null_ptr
+    if (idrv == 1 .and. present(duflx_dt) .and. present(duflxc_dt)) then
+       pdu = c_loc(duflx_dt); pduc = c_loc(duflxc_dt)
+    endif
     call b200_check(rrtmg_b200_lw(ncol, nlay, icld_c, idrv, c_loc(play), c_loc(plev), c_loc(tlay), c_loc(tlev), &
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          opt2(cfc11vmr), opt2(cfc12vmr), opt2(cfc22vmr), opt2(ccl4vmr), pemis, inflglw, iceflglw, liqflglw, &
-         c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, paer, &
-         c_loc(uflx), c_loc(dflx), c_loc(hr), c_loc(uflxc), c_loc(dflxc), c_loc(hrc), c_null_ptr, c_null_ptr), 'rrtmg_lw')
+         pcldfr, ptaucld, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, paer, &
+         c_loc(uflx), c_loc(dflx), c_loc(hr), c_loc(uflxc), c_loc(dflxc), c_loc(hrc), pdu, pduc), 'rrtmg_lw')
     icld = icld_c
   end subroutine
 end module rrtmg_lw_rad
@@ -159,17 +168,26 @@ contains
     real(c_double), contiguous, target, intent(in) :: h2ovmr(:,:), o3vmr(:,:), co2vmr(:,:), ch4vmr(:,:), n2ovmr(:,:), o2vmr(:,:)
     real(c_double), contiguous, target, intent(in) :: asdir(:), asdif(:), aldir(:), aldif(:), coszen(:)
     ! cloud / aerosol dummies: MiMA passes LW-shaped arrays here (rrtm_radiation.f90:692-708); they are never
-    ! read for icld = 0 / iaer = 0, so they are declared assumed-size and not forwarded
-    real(c_double), intent(in) :: cldfr(*), taucld(*), ssacld(*), asmcld(*), fsfcld(*), cicewp(*), cliqwp(*), &
+    ! read for icld = 0 / iaer = 0, so they are declared assumed-size and forwarded only for icld > 0 (cldfr and the
+    ! four band arrays, inflgsw = 0) and iaer = 10 (the three band arrays)
+    real(c_double), target, intent(in) :: cldfr(*), taucld(*), ssacld(*), asmcld(*), fsfcld(*), cicewp(*), cliqwp(*), &
          reice(*), reliq(*), tauaer(*), ssaaer(*), asmaer(*), ecaer(*)
     real(c_double), contiguous, target, intent(out) :: swuflx(:,:), swdflx(:,:), swhr(:,:), swuflxc(:,:), swdflxc(:,:), swhrc(:,:)
     integer(c_int) :: icld_c, iaer_c
+    type(c_ptr) :: pc(5), pa(3)
     icld_c = icld; iaer_c = iaer
+    pc = c_null_ptr; pa = c_null_ptr
+    if (icld /= 0) then
+       pc(1) = c_loc(cldfr); pc(2) = c_loc(taucld); pc(3) = c_loc(ssacld); pc(4) = c_loc(asmcld); pc(5) = c_loc(fsfcld)
+    endif
+    if (iaer == 10) then
+       pa(1) = c_loc(tauaer); pa(2) = c_loc(ssaaer); pa(3) = c_loc(asmaer)
+    endif
     call b200_check(rrtmg_b200_sw(ncol, nlay, icld_c, iaer_c, c_loc(play), c_loc(plev), c_loc(tlay), c_loc(tlev), &
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          c_loc(asdir), c_loc(asdif), c_loc(aldir), c_loc(aldif), c_loc(coszen), adjes, dyofyr, scon, &
-         inflgsw, iceflgsw, liqflgsw, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
-         c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, &
+         inflgsw, iceflgsw, liqflgsw, pc(1), pc(2), pc(3), pc(4), pc(5), c_null_ptr, &
+         c_null_ptr, c_null_ptr, c_null_ptr, pa(1), pa(2), pa(3), c_null_ptr, &
          c_loc(swuflx), c_loc(swdflx), c_loc(swhr), c_loc(swuflxc), c_loc(swdflxc), c_loc(swhrc)), 'rrtmg_sw')
     icld = icld_c; iaer = iaer_c
   end subroutine
