@@ -30,6 +30,10 @@
  *   - cloud and SW aerosol arrays are never dereferenced when icld == 0 / iaer == 0 (as in the
  *     reference) and may be NULL or of any extent; with icld > 0 / iaer = 10 the arrays listed under
  *     "built" below are required (RRTMG_B200_ERR_BAD_ARGUMENT when NULL).
+ *   - the clear-sky outputs of the host-pointer entry points (uflxc, dflxc, hrc, duflxc_dt; swuflxc, swdflxc,
+ *     swhrc) may be NULL: they are then not copied back.  MiMA never reads them
+ *     (rrtm_radiation.f90:716, 752, 790-791 use the total-sky arrays only), so the shim passes NULL and halves
+ *     the device-to-host volume of the call.
  *   - *_device variants take device pointers plus a cudaStream_t and run asynchronously.
  *
  * Branches beyond MiMA's configuration (icld = 0, iaer = 0, idrv = 0):

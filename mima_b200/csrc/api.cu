@@ -751,8 +751,9 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
         if (e != cudaSuccess) ok = false;
         return d;
     }
-    void down(double *h, const double *d, size_t rows)
+    void down(double *h, const double *d, size_t rows)          // h == NULL: output not wanted
     {
+        if (!h) return;
         const cudaError_t e = (nc == ncol)
             ? cudaMemcpyAsync(h, d, (size_t)nc * rows * 8, cudaMemcpyDeviceToHost, st)
             : cudaMemcpy2DAsync(h + c0, (size_t)ncol * 8, d, (size_t)nc * 8, (size_t)nc * 8, rows, cudaMemcpyDeviceToHost, st);
@@ -1125,11 +1126,11 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
 {
     (void)iceflglw; (void)liqflglw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
     const LwOpt opt{inflglw, cldfr, taucld};
-    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr ||
-        !uflxc || !dflxc || !hrc)
+    // uflxc, dflxc, hrc (and duflxc_dt) may be NULL: the clear-sky result is then not copied back (MiMA never reads it)
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
     if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;
-    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
+    if (idrv == 1 && !duflx_dt) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt");
     if (ncol == 0) return RRTMG_B200_OK;
     const bool cloud = icld && *icld >= 1;
     if (P_lw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
@@ -1161,7 +1162,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
         if (const int rc = lw_chunk(in, out, nc, nlay, P_lw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
         if (idrv == 1) { o.down(duflx_dt, out.duflx_dt, V); o.down(duflxc_dt, out.duflxc_dt, V); }
         o.down(uflx, out.uflx, V); o.down(dflx, out.dflx, V); o.down(hr, out.hr, L);
-        o.down(uflxc, out.uflxc, V); o.down(dflxc, out.dflxc, V); o.down(hrc, out.hrc, L);
+        o.down(uflxc, out.uflxc, V); o.down(dflxc, out.dflxc, V); o.down(hrc, out.hrc, L);      // skipped when NULL
         if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)");
     }
     for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_lw.st[i]));
@@ -1207,8 +1208,9 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
 {
     (void)iceflgsw; (void)liqflgsw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq; (void)ecaer;
     const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer};
+    // swuflxc, swdflxc, swhrc may be NULL: the clear-sky result is then not copied back
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
-        !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
+        !aldif || !coszen || !swuflx || !swdflx || !swhr)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
     if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;

@@ -163,13 +163,14 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
              cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis,
              inflglw=0, iceflglw=0, liqflglw=0, cldfr=None,
              taucld=None, cicewp=None, cliqwp=None, reice=None, reliq=None,
-             tauaer=None):
+             tauaer=None, clear_sky=True):
     """Returns (uflx, dflx, hr, uflxc, dflxc, hrc); fluxes (ncol, nlay+1) W/m2, heating (ncol, nlay) K/day; with
     idrv = 1 also (duflx_dt, duflxc_dt), the change of the upward flux per K of surface temperature (W/m2/K,
     rad.nomcica:143-152, the Fortran's optional dummies).  ch4vmr..ccl4vmr, emis, tauaer may be None (zeros /
     emissivity 1).  icld >= 1 takes the cloud fraction cldfr (ncol,nlay) and the band optical depths taucld
     (16,ncol,nlay) (inflglw = 0): icld = 1 random overlap, 2/3 maximum/random overlap; water-path inputs
-    (inflglw > 0) raise RRTMGError(2)."""
+    (inflglw > 0) raise RRTMGError(2).  clear_sky=False does not fetch uflxc, dflxc, hrc (duflxc_dt): they come back as
+    None (MiMA never reads them; the C ABI takes NULL for them)."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
     keep = []
@@ -195,10 +196,15 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
            np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
     if int(idrv) == 1:
         out += [np.empty(V, order="F"), np.empty(V, order="F")]
+    if not clear_sky:
+        for i in (3, 4, 5, 7):
+            if i < len(out):
+                out[i] = None
     icld_c = C.c_int(int(icld))
     rc = lib().rrtmg_b200_lw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.c_int(int(idrv)), *ptrs,
                              C.c_int(inflglw), C.c_int(iceflglw), C.c_int(liqflglw), *cloudp,
-                             ptaer, *[o.ctypes.data_as(_dp) for o in out], *([] if int(idrv) == 1 else [None, None]))
+                             ptaer, *[None if o is None else o.ctypes.data_as(_dp) for o in out],
+                             *([] if int(idrv) == 1 else [None, None]))
     _check(rc)
     return tuple(out)
 
@@ -211,8 +217,8 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
              inflgsw=0, iceflgsw=0, liqflgsw=0, cldfr=None,
              taucld=None, ssacld=None, asmcld=None, fsfcld=None,
              cicewp=None, cliqwp=None, reice=None, reliq=None,
-             tauaer=None, ssaaer=None, asmaer=None, ecaer=None):
-    """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc).  icld >= 1 takes cloud optical properties
+             tauaer=None, ssaaer=None, asmaer=None, ecaer=None, clear_sky=True):
+    """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc); the last three are None with clear_sky=False.  icld >= 1 takes cloud optical properties
     (inflgsw = 0: cldfr (ncol,nlay) 0 or 1, taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)); iaer = 10 takes
     tauaer/ssaaer/asmaer (ncol,nlay,14).  Water-path cloud inputs (inflgsw > 0) and iaer = 6 raise
     RRTMGError(2); a partially cloudy layer raises RRTMGError(3) like the reference's stop."""
@@ -242,11 +248,13 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
         ptrs.append(p)
     out = [np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F"),
            np.empty(V, order="F"), np.empty(V, order="F"), np.empty(L, order="F")]
+    if not clear_sky:
+        out[3:] = [None, None, None]
     icld_c, iaer_c = C.c_int(int(icld)), C.c_int(int(iaer))
     rc = lib().rrtmg_b200_sw(C.c_int(ncol), C.c_int(nlay), C.byref(icld_c), C.byref(iaer_c), *ptrs,
                              C.c_double(float(adjes)), C.c_int(int(dyofyr)), C.c_double(float(scon)),
                              C.c_int(inflgsw), C.c_int(iceflgsw), C.c_int(liqflgsw),
-                             *optional, *[o.ctypes.data_as(_dp) for o in out])
+                             *optional, *[None if o is None else o.ctypes.data_as(_dp) for o in out])
     _check(rc)
     return tuple(out)
 
@@ -257,13 +265,13 @@ def _opt(a):
     return None if (a is None or not np.any(a)) else a
 
 
-def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0):
+def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0, clear_sky=True):
     return rrtmg_lw(c.ncol, c.nlay, icld, idrv, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), _opt(c.cfc11), _opt(c.cfc12), _opt(c.cfc22), _opt(c.ccl4),
-                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, **(clouds or {}))
+                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, clear_sky=clear_sky, **(clouds or {}))
 
 
-def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0):
+def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0, clear_sky=True):
     return rrtmg_sw(c.ncol, c.nlay, icld, iaer, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), c.albedo, c.albedo, c.albedo, c.albedo,
-                    c.coszen, c.adjes, c.dyofyr, c.scon, inflgsw=inflgsw, **(clouds or {}), **(aerosols or {}))
+                    c.coszen, c.adjes, c.dyofyr, c.scon, inflgsw=inflgsw, clear_sky=clear_sky, **(clouds or {}), **(aerosols or {}))

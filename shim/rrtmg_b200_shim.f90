@@ -57,7 +57,17 @@ module rrtmg_b200_c
        import; type(c_ptr) :: p
      end function
   end interface
+  ! MiMA never reads the clear-sky outputs of either routine (rrtm_radiation.f90:716, 752, 790-791 use swuflx,
+  ! swdflx, swhr, uflx, dflx, hr only).  Setting this to .false. passes C_NULL_PTR for uflxc, dflxc, hrc / swuflxc,
+  ! swdflxc, swhrc: the library then leaves those dummies untouched and does not copy them back over PCIe.
+  logical, save :: b200_clear_sky_outputs = .true.
 contains
+  function optout(a) result(p)      ! clear-sky output wanted?
+    real(c_double), contiguous, target, intent(inout) :: a(:,:)
+    type(c_ptr) :: p
+    p = c_null_ptr
+    if (b200_clear_sky_outputs) p = c_loc(a)
+  end function
   subroutine b200_check(rc, where)
     ! C status -> the model's fatal-error convention (cf. error_mesg(...,FATAL), rrtm_radiation.f90:527-528)
     use fms_mod, only: error_mesg, FATAL
@@ -112,7 +122,7 @@ contains
          n2ovmr(:,:), o2vmr(:,:), cfc11vmr(:,:), cfc12vmr(:,:), cfc22vmr(:,:), ccl4vmr(:,:), emis(:,:)
     real(c_double), contiguous, target, intent(in) :: cldfr(:,:), cicewp(:,:), cliqwp(:,:), reice(:,:), reliq(:,:)
     real(c_double), contiguous, target, intent(in) :: taucld(:,:,:), tauaer(:,:,:)
-    real(c_double), contiguous, target, intent(out) :: uflx(:,:), dflx(:,:), hr(:,:), uflxc(:,:), dflxc(:,:), hrc(:,:)
+    real(c_double), contiguous, target, intent(inout) :: uflx(:,:), dflx(:,:), hr(:,:), uflxc(:,:), dflxc(:,:), hrc(:,:)
     real(c_double), contiguous, target, intent(out), optional :: duflx_dt(:,:), duflxc_dt(:,:)
     integer(c_int) :: icld_c
     type(c_ptr) :: pemis, paer, pcldfr, ptaucld, pdu, pduc
@@ -133,7 +143,7 @@ contains
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          opt2(cfc11vmr), opt2(cfc12vmr), opt2(cfc22vmr), opt2(ccl4vmr), pemis, inflglw, iceflglw, liqflglw, &
          pcldfr, ptaucld, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, paer, &
-         c_loc(uflx), c_loc(dflx), c_loc(hr), c_loc(uflxc), c_loc(dflxc), c_loc(hrc), pdu, pduc), 'rrtmg_lw')
+         c_loc(uflx), c_loc(dflx), c_loc(hr), optout(uflxc), optout(dflxc), optout(hrc), pdu, pduc), 'rrtmg_lw')
     icld = icld_c
   end subroutine
 end module rrtmg_lw_rad
@@ -172,7 +182,7 @@ contains
     ! four band arrays, inflgsw = 0) and iaer = 10 (the three band arrays)
     real(c_double), target, intent(in) :: cldfr(*), taucld(*), ssacld(*), asmcld(*), fsfcld(*), cicewp(*), cliqwp(*), &
          reice(*), reliq(*), tauaer(*), ssaaer(*), asmaer(*), ecaer(*)
-    real(c_double), contiguous, target, intent(out) :: swuflx(:,:), swdflx(:,:), swhr(:,:), swuflxc(:,:), swdflxc(:,:), swhrc(:,:)
+    real(c_double), contiguous, target, intent(inout) :: swuflx(:,:), swdflx(:,:), swhr(:,:), swuflxc(:,:), swdflxc(:,:), swhrc(:,:)
     integer(c_int) :: icld_c, iaer_c
     type(c_ptr) :: pc(5), pa(3)
     icld_c = icld; iaer_c = iaer
@@ -188,7 +198,7 @@ contains
          c_loc(asdir), c_loc(asdif), c_loc(aldir), c_loc(aldif), c_loc(coszen), adjes, dyofyr, scon, &
          inflgsw, iceflgsw, liqflgsw, pc(1), pc(2), pc(3), pc(4), pc(5), c_null_ptr, &
          c_null_ptr, c_null_ptr, c_null_ptr, pa(1), pa(2), pa(3), c_null_ptr, &
-         c_loc(swuflx), c_loc(swdflx), c_loc(swhr), c_loc(swuflxc), c_loc(swdflxc), c_loc(swhrc)), 'rrtmg_sw')
+         c_loc(swuflx), c_loc(swdflx), c_loc(swhr), optout(swuflxc), optout(swdflxc), optout(swhrc)), 'rrtmg_sw')
     icld = icld_c; iaer = iaer_c
   end subroutine
 end module rrtmg_sw_rad

@@ -269,3 +269,19 @@ def test_idrv1_flux_derivative(gpu, oracle):
     fd = up - dn
     assert np.max(np.abs(fd - got[6])) < 3e-3 * np.abs(fd).max()
     assert (got[6] > 0).all() and (np.diff(got[6], axis=1) <= 1e-12).all()      # attenuated on the way up
+
+
+def test_clear_sky_outputs_are_optional(gpu):
+    """NULL for the clear-sky output arrays of the host-pointer ABI: the total-sky results are unchanged, bit for bit."""
+    c = make_columns("T42L40", nlon=64, nlat=4, night=True)
+    gpu.set_option("host_chunk", 100)
+    try:
+        for full, part in ((gpu.lw_from_columns(c, idrv=1), gpu.lw_from_columns(c, idrv=1, clear_sky=False)),
+                           (gpu.sw_from_columns(c), gpu.sw_from_columns(c, clear_sky=False))):
+            assert all(p is None for p in (part[3], part[4], part[5]))
+            for i in (0, 1, 2):
+                assert np.array_equal(full[i], part[i])
+            if len(full) == 8:
+                assert np.array_equal(full[6], part[6]) and part[7] is None
+    finally:
+        gpu.set_option("host_chunk", 0)
