@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8192, help="columns in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--split", action="store_true",
+                    help="strong scaling: the batch of the named resolution is split by latitude rows over the ranks "
+                         "(e.g. T341L80 on 8 GPUs = 65536 columns per GPU); default is weak scaling, one full batch per rank")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,7 +248,14 @@ def main():
 
     nlon, nlat, nlay = RESOLUTIONS[args.workload]
     # weak scaling: every rank holds one full batch; rank r uses its own seed = its own latitude-row block
-    cols = make_columns(args.workload, seed=20240917 + rank)
+    if args.split and world > 1:
+        if nlat % world:
+            raise SystemExit(f"bench.py --split: {nlat} latitude rows do not divide over {world} ranks")
+        rows = nlat // world
+        cols = make_columns(args.workload, seed=20240917, lat_rows=(rank * rows, (rank + 1) * rows))
+        nlat = rows
+    else:
+        cols = make_columns(args.workload, seed=20240917 + rank)
     ncol = cols.ncol
 
     def pin(a):
@@ -280,11 +290,12 @@ def main():
     side = torch.cuda.Stream(device=dev) if two_streams else None
     sh_sw = C.c_void_p(side.cuda_stream) if two_streams else sh
 
-    def step_device():
-        d = devt
+    def step_device(d=None, n=None):
+        d = devt if d is None else d
+        n = ncol if n is None else n
         if two_streams:
             side.wait_stream(stream)
-        rc = L_.rrtmg_b200_sw_device(C.c_int(ncol), C.c_int(nlay), C.byref(icld), C.byref(iaer),
+        rc = L_.rrtmg_b200_sw_device(C.c_int(n), C.c_int(nlay), C.byref(icld), C.byref(iaer),
                                      P(d["play"]), P(d["plev"]), P(d["tlay"]), P(d["tlev"]), P(d["tsfc"]),
                                      P(d["h2o"]), P(d["o3"]), P(d["co2"]), NULL, NULL, NULL,
                                      P(d["albedo"]), P(d["albedo"]), P(d["albedo"]), P(d["albedo"]), P(d["coszen"]),
@@ -294,7 +305,7 @@ def main():
                                      P(outs["sw_dflxc"]), P(outs["sw_hrc"]), sh_sw)
         if rc:
             raise RuntimeError(L_.rrtmg_b200_last_error().decode())
-        rc = L_.rrtmg_b200_lw_device(C.c_int(ncol), C.c_int(nlay), C.byref(icld), C.c_int(0),
+        rc = L_.rrtmg_b200_lw_device(C.c_int(n), C.c_int(nlay), C.byref(icld), C.c_int(0),
                                      P(d["play"]), P(d["plev"]), P(d["tlay"]), P(d["tlev"]), P(d["tsfc"]),
                                      P(d["h2o"]), P(d["o3"]), P(d["co2"]), *([NULL] * 8),
                                      C.c_int(0), C.c_int(0), C.c_int(0), *([NULL] * 6), NULL,
@@ -361,6 +372,30 @@ def main():
     L_.rrtmg_b200_kernel_times(kms, kn, C.c_int(1))
     L_.rrtmg_b200_set_option(b"kernel_timing", C.c_long(0))
     sampler.join(timeout=2)
+
+    # ---------------- strong scaling (extra): the ONE batch of the named resolution cut into `world` blocks of latitude
+    #                  rows, every rank timing its block (BASELINE.json: "T170L60 sharded by latitude rows at 1/2/4/8")
+    strong = None
+    if world > 1 and nlat % world == 0 and not args.split:
+        nsub = ncol // world
+        dsub = {}
+        for k, t in devt.items():
+            rows = t.numel() // ncol
+            dsub[k] = t.view(rows, ncol)[:, :nsub].contiguous().view(-1)
+        for _ in range(args.warmup):
+            step_device(dsub, nsub)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            step_device(dsub, nsub)
+        s1.record(stream)
+        barrier()
+        ms_strong = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        strong = {"columns_total": ncol, "columns_per_gpu": nsub, "ms_per_step": ms_strong,
+                  "value": ncol / (ms_strong * 1e-3), "unit": "columns/s",
+                  "what": "one batch of the named resolution, latitude rows split over the ranks, device-resident"}
+        del dsub
 
     # ---------------- the same step with SW and LW on two streams (extra, untimed for `value`)
     ms_two = None
@@ -503,7 +538,7 @@ def main():
     line = {
         "metric": "RRTMG LW+SW columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if (args.split and world > 1) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "columns_per_gpu": ncol, "layers": nlay, "grid": f"{nlon}x{nlat}",
                    "sharding": "latitude-row blocks, one rank per GPU, no collective",
                    "l2": "inputs + staging per step exceed the 126 MB L2 (no flush needed)",
@@ -516,6 +551,7 @@ def main():
         "e2e_run_rrtmg": {"value": total_cols / (ms_rr / e2e_steps * 1e-3), "unit": "columns/s", "ms_per_step": ms_rr / e2e_steps,
                           "h2d_bytes_per_step": rr_h2d, "d2h_bytes_per_step": rr_d2h, "steps": e2e_steps,
                           "what": "rrtmg_b200_run_rrtmg with host buffers: marshaling + interp_temp + compute_zenith (daily-mean sun) + SW + LW"},
+        "strong_scaling": strong,
         "two_streams_ms_per_step": ms_two,
         "realistic_night": None if ms_night is None else {"ms_per_step": ms_night, "night_fraction": night_frac,
                                                            "value": total_cols / (ms_night * 1e-3), "unit": "columns/s"},

@@ -90,3 +90,10 @@ def test_argument_errors(gpu, cols):
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=2)  # water-path cloud optics: not built
     assert e.value.code == 2
+
+
+def test_eighty_layers(gpu, oracle):
+    c = make_columns("T341L80", nlon=32, nlat=4)
+    cl = cloud_field(c, np.random.default_rng(6))
+    for icld in (1, 2):
+        _check_outputs(gpu.lw_from_columns(c, icld=icld, clouds=cl), oracle.rrtmg_lw(c, icld=icld, clouds=cl))

@@ -111,3 +111,13 @@ def test_partial_cloud_is_an_error(gpu, cols):
         gpu.sw_from_columns(c, icld=2, clouds=cl)
     assert e.value.code == 3
     gpu.sw_from_columns(c)         # the library stays usable
+
+
+def test_eighty_layers(gpu, oracle):
+    """L80 takes the kernels' 128-layer instantiation."""
+    c = make_columns("T341L80", nlon=32, nlat=4, night=True)
+    rng = np.random.default_rng(8)
+    cl, aer = _clouds(c, rng), _aerosols(c, rng, 0.1)
+    _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=10, clouds=cl, aerosols=aer),
+                   oracle.rrtmg_sw(c, icld=2, iaer=10, clouds=cl, aerosols=aer), SW_OUT)
+    _check_outputs(gpu.sw_from_columns(c, iaer=10, aerosols=aer), oracle.rrtmg_sw(c, iaer=10, aerosols=aer), SW_OUT)
