@@ -152,3 +152,32 @@ def test_lw_k_g_parser_round_trip(tmp_path):
     back = bt.build_lw_real(str(src))
     for k in synth:
         np.testing.assert_allclose(back[k], synth[k], rtol=5e-5)
+
+
+def test_lw_netcdf_reader_round_trip(tmp_path):
+    """the reader for rrtmg_lw.nc (schema of LW/src/rrtmg_lw_read_nc.f90 and
+    LW/modules/rrlw_ncpar.f90: eight variables, every module array one hyperslab at (absorber,) band, g-point set 1).
+    The synthetic LW arrays are written in that layout and must come back bit for bit; an array placed in the file
+    by hand at the Fortran start/count of read_nc.f90 must land in the module array the Fortran would fill."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_tables", os.path.join(ROOT, "tools", "build_tables.py"))
+    bt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bt)
+    synth = bt.read_blob(os.path.join(ROOT, "mima_b200", "data", "rrtmg_lw_kg_synth.bin"))
+    nc = tmp_path / "rrtmg_lw.nc"
+    bt.write_lw_nc(str(nc), synth)
+    back = bt.build_lw_from_nc(str(nc))
+    assert set(back) == set(synth)
+    for k in synth:
+        assert back[k].shape == synth[k].shape and np.array_equal(back[k], synth[k]), k
+    # independent placement, straight from the Fortran: band 5 ccl4o = AbsorptionCoefficientsLowerAtmos with
+    # start (1,1,1,ab('CCL4'),5,1), count (1,1,16,1,1,1) (read_nc.f90:318-322); band 3 kbo_mn2o = ...UpperAtmos with
+    # start (1,1,1,ab('N2O'),3,1), count (keyupper,T,16,1,1,1)
+    from scipy.io import netcdf_file
+    f = netcdf_file(str(nc), "r", mmap=False)
+    lo = np.array(f.variables["AbsorptionCoefficientsLowerAtmos"][:])     # file order: (gset, band, absorber, g, T, key)
+    up = np.array(f.variables["AbsorptionCoefficientsUpperAtmos"][:])
+    f.close()
+    assert lo.shape == (2, 16, 12, 16, 19, 9) and up.shape == (2, 16, 12, 16, 19, 5)
+    assert np.array_equal(lo[0, 4, 1, :, 0, 0], synth["lw05.ccl4o"])
+    assert np.array_equal(up[0, 2, 8, :, :, :].transpose(2, 1, 0), synth["lw03.kbo_mn2o"])

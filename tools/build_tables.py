@@ -427,6 +427,108 @@ def write_kg_fortran(path, arrays, prefix="lw", digits=17):
             f.write("\n      end subroutine " + f"{prefix}_kgb{bk[len(prefix):]}\n\n")
 
 
+# ---- rrtmg_lw.nc: the netCDF form of the same coefficients (LW/src/rrtmg_lw_read_nc.f90, LW/modules/rrlw_ncpar.f90)
+# Eight variables hold all bands; every module array is one hyperslab of one variable, read with start = 1 everywhere
+# except (absorber,) band, g-point set 1, and count = the array's own extents padded with ones on the left
+# (read_nc.f90:30-110 for band 1, the other bands alike).  Dimension order below is the Fortran one (first fastest);
+# the file stores the reverse.
+NC_DIMS = {"keylower": 9, "keyupper": 5, "Tdiff": 5, "plower": 13, "pupper": 47, "Tself": 10, "Tforeign": 4, "T": 19,
+           "band": 16, "GPoint": 16, "GPointSet": 2, "Absorber": 12}
+NC_ABSORBERS = ["N2", "CCL4", "CFC11", "CFC12", "CFC22", "H2O", "CO2", "O3", "N2O", "CO", "CH4", "O2"]      # rrlw_ncpar.f90
+NC_VARS = {
+    "PlanckFractionLowerAtmos": ("GPoint", "keylower", "band", "GPointSet"),
+    "PlanckFractionUpperAtmos": ("GPoint", "keyupper", "band", "GPointSet"),
+    "KeySpeciesAbsorptionCoefficientsLowerAtmos": ("keylower", "Tdiff", "plower", "GPoint", "band", "GPointSet"),
+    "KeySpeciesAbsorptionCoefficientsUpperAtmos": ("keyupper", "Tdiff", "pupper", "GPoint", "band", "GPointSet"),
+    "H20SelfAbsorptionCoefficients": ("Tself", "GPoint", "band", "GPointSet"),
+    "H20ForeignAbsorptionCoefficients": ("Tforeign", "GPoint", "band", "GPointSet"),
+    "AbsorptionCoefficientsLowerAtmos": ("keylower", "T", "GPoint", "Absorber", "band", "GPointSet"),
+    "AbsorptionCoefficientsUpperAtmos": ("keyupper", "T", "GPoint", "Absorber", "band", "GPointSet"),
+}
+NC_MINOR = {"mn2": "N2", "mn2o": "N2O", "mo3": "O3", "mco2": "CO2", "mco": "CO", "mo2": "O2"}
+NC_XSEC = {"ccl4o": "CCL4", "cfc11adjo": "CFC11", "cfc12o": "CFC12", "cfc22adjo": "CFC22"}
+
+
+def nc_slab(name, shape, band):
+    """(variable, index tuple in Fortran dimension order) of module array `name` (extents `shape`) of LW band `band`."""
+    b, gs = band - 1, 0
+    if name in ("fracrefao", "fracrefbo"):
+        var = "PlanckFractionLowerAtmos" if name == "fracrefao" else "PlanckFractionUpperAtmos"
+        k = slice(0, shape[1]) if len(shape) == 2 else 0
+        return var, (slice(0, shape[0]), k, b, gs)
+    if name in ("kao", "kbo"):
+        var = "KeySpeciesAbsorptionCoefficients" + ("LowerAtmos" if name == "kao" else "UpperAtmos")
+        lead = (slice(0, shape[0]),) if len(shape) == 4 else (0,)
+        t, pr, g = shape[-3:]
+        return var, lead + (slice(0, t), slice(0, pr), slice(0, g), b, gs)
+    if name == "selfrefo":
+        return "H20SelfAbsorptionCoefficients", (slice(0, shape[0]), slice(0, shape[1]), b, gs)
+    if name == "forrefo":
+        return "H20ForeignAbsorptionCoefficients", (slice(0, shape[0]), slice(0, shape[1]), b, gs)
+    if name in NC_XSEC:
+        return "AbsorptionCoefficientsLowerAtmos", (0, 0, slice(0, shape[0]), NC_ABSORBERS.index(NC_XSEC[name]), b, gs)
+    m = re.match(r"k([ab])o_(m\w+)$", name)
+    if m and m.group(2) in NC_MINOR:
+        var = "AbsorptionCoefficients" + ("LowerAtmos" if m.group(1) == "a" else "UpperAtmos")
+        lead = (slice(0, shape[0]),) if len(shape) == 3 else (0,)
+        t, g = shape[-2:]
+        return var, lead + (slice(0, t), slice(0, g), NC_ABSORBERS.index(NC_MINOR[m.group(2)]), b, gs)
+    raise KeyError(name)
+
+
+def lw_template():
+    """Names and declared extents of every unreduced LW array, from the synthetic blob (built from rrlw_kgNN.f90)."""
+    return {k: v.shape for k, v in read_blob(os.path.join(OUT, "rrtmg_lw_kg_synth.bin")).items()}
+
+
+def build_lw_from_nc(nc_path, template=None):
+    """Read rrtmg_lw.nc (netCDF classic / 64-bit offset, through scipy.io) into the lwNN.* arrays of the blob, as
+    lw_kgb01..16 of rrtmg_lw_read_nc.f90 fill the rrlw_kgNN modules.  SURVEY.md section 8f rank 3.  The file is not
+    part of the reference checkout; exercised by a round trip through write_lw_nc()."""
+    from scipy.io import netcdf_file
+    template = template or lw_template()
+    try:
+        f = netcdf_file(nc_path, "r", mmap=False)
+    except (TypeError, ValueError) as e:
+        raise SystemExit(f"{nc_path}: not a netCDF classic file ({e}); convert with `nccopy -k classic`")
+    out = {}
+    try:
+        cache = {}
+        for key, shape in template.items():
+            band, name = int(key[2:4]), key.split(".")[1]
+            var, idx = nc_slab(name, shape, band)
+            if var not in cache:
+                v = f.variables[var]
+                want = tuple(NC_DIMS[d] for d in NC_VARS[var])[::-1]
+                if tuple(v.shape) != want:
+                    raise SystemExit(f"{nc_path}: {var} has shape {tuple(v.shape)}, expected {want}")
+                cache[var] = np.array(v[:], dtype=np.float64).T          # Fortran dimension order
+            a = np.asfortranarray(cache[var][idx])
+            assert a.shape == tuple(shape), (key, a.shape, shape)
+            out[key] = a
+    finally:
+        f.close()
+    return out
+
+
+def write_lw_nc(nc_path, arrays):
+    """Write {"lwNN.name": ndarray} in the rrtmg_lw.nc layout (test helper for build_lw_from_nc)."""
+    from scipy.io import netcdf_file
+    full = {v: np.zeros(tuple(NC_DIMS[d] for d in dims), order="F") for v, dims in NC_VARS.items()}
+    for key, a in arrays.items():
+        var, idx = nc_slab(key.split(".")[1], a.shape, int(key[2:4]))
+        full[var][idx] = a
+    f = netcdf_file(nc_path, "w")
+    try:
+        for d, n in NC_DIMS.items():
+            f.createDimension(d, n)
+        for v, dims in NC_VARS.items():
+            nv = f.createVariable(v, "d", dims[::-1])
+            nv[:] = full[v].T
+    finally:
+        f.close()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sw = build_sw()
@@ -440,6 +542,9 @@ def main():
     if os.path.exists(kg):
         write_blob(os.path.join(OUT, "rrtmg_lw_kg.bin"), build_lw_real(kg))
         print("wrote rrtmg_lw_kg.bin from", kg)
+    elif os.environ.get("MIMA_LW_NC") and os.path.exists(os.environ["MIMA_LW_NC"]):
+        write_blob(os.path.join(OUT, "rrtmg_lw_kg.bin"), build_lw_from_nc(os.environ["MIMA_LW_NC"]))
+        print("wrote rrtmg_lw_kg.bin from", os.environ["MIMA_LW_NC"])
     else:
         print("no rrtmg_lw_k_g.f90 at", kg, "-> LW stays on the synthetic blob")
     # round-trip check
