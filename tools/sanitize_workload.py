@@ -1,0 +1,28 @@
+import numpy as np, sys
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+from mima_b200 import rrtmg
+from mima_b200.columns import make_columns
+from test_oracle_lw_clouds import cloud_field
+rrtmg.set_device(0); rrtmg.rrtmg_lw_ini(); rrtmg.rrtmg_sw_ini()
+c = make_columns("T42L40", nlon=32, nlat=4, night=True)
+rng = np.random.default_rng(1)
+cl = cloud_field(c, rng)
+rrtmg.lw_from_columns(c); rrtmg.sw_from_columns(c)
+import os
+if not os.environ.get("SAN_NO_TMA"):
+    rrtmg.lw_from_columns(c, idrv=1)
+for icld in (1, 2):
+    rrtmg.lw_from_columns(c, icld=icld, clouds=cl, idrv=1)
+shp = (14, c.ncol, c.nlay)
+cld = (rng.uniform(size=(c.ncol, c.nlay)) < 0.3).astype(float)
+asm = rng.uniform(0.7, 0.9, shp)
+swcl = dict(cldfr=np.asfortranarray(cld), taucld=np.asfortranarray(rng.uniform(0, 20, shp) * cld[None]),
+            ssacld=np.asfortranarray(rng.uniform(0.5, 0.99999, shp)), asmcld=np.asfortranarray(asm), fsfcld=np.asfortranarray(asm * asm))
+a3 = (c.ncol, c.nlay, 14)
+aer = dict(tauaer=np.asfortranarray(rng.uniform(0, 0.3, a3)), ssaaer=np.asfortranarray(rng.uniform(0.6, 0.999, a3)), asmaer=np.asfortranarray(rng.uniform(0.3, 0.8, a3)))
+rrtmg.sw_from_columns(c, icld=2, iaer=10, clouds=swcl, aerosols=aer)
+rrtmg.sw_from_columns(c, iaer=10, aerosols=aer)
+c80 = make_columns("T341L80", nlon=32, nlat=2, night=True)
+rrtmg.lw_from_columns(c80); rrtmg.sw_from_columns(c80)
+from mima_b200 import rrtm_radiation as rr
+print("sanitizer workload done")
