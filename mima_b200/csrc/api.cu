@@ -440,6 +440,17 @@ int sw_init_impl(double cpdair)
         if (b + 16 == 24 || b + 16 == 25) { add(SS_X1, "abso3ao", "abso3a", true); add(SS_X2, "abso3bo", "abso3b", true); }
         if (b + 16 == 29) { add(SS_X1, "absh2oo", "absh2o", true); add(SS_X2, "absco2o", "absco2", true); }
     }
+    // ECMWF aerosol optical properties (swaerpr), (nbndsw, naerec) column-major
+    {
+        const HostArr *ta = find("swaer.rsrtaua"), *pa = find("swaer.rsrpiza"), *ga = find("swaer.rsrasya");
+        c.have_aer = ta && pa && ga && ta->size() == 84 && pa->size() == 84 && ga->size() == 84;
+        for (int ib = 0; ib < 14; ++ib)
+            for (int ia = 0; ia < 6; ++ia) {
+                c.rsrtaua[ib][ia] = c.have_aer ? ta->data[ib + 14 * ia] : 0.0;
+                c.rsrpiza[ib][ia] = c.have_aer ? pa->data[ib + 14 * ia] : 0.0;
+                c.rsrasya[ib][ia] = c.have_aer ? ga->data[ib + 14 * ia] : 0.0;
+            }
+    }
     // exp_tbl (rrtmg_sw_init.f90:96-105), interleaved with its reciprocal
     std::vector<double> et(2 * (NTBL + 1));
     {
@@ -552,6 +563,7 @@ struct SwOpt {
     int inflgsw = 0;
     const double *cldfr = nullptr, *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;
     const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;
+    const double *ecaer = nullptr;
 };
 int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt())
 {
@@ -565,7 +577,10 @@ int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt
         if (!o.cldfr || !o.taucld || !o.ssacld || !o.asmcld || !o.fsfcld)
             return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: icld > 0 needs cldfr, taucld, ssacld, asmcld, fsfcld");
     }
-    if (iaer && *iaer == 6) return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: iaer = 6 (ECMWF aerosol climatology) is not built");
+    if (iaer && *iaer == 6) {
+        if (!G.swc.have_aer) return fail(RRTMG_B200_ERR_TABLES, "rrtmg_sw: iaer = 6 needs the swaer.rsrtaua/rsrpiza/rsrasya tables");
+        if (!o.ecaer) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: iaer = 6 needs ecaer");
+    }
     if (iaer && *iaer == 10 && (!o.tauaer || !o.ssaaer || !o.asmaer))
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: iaer = 10 needs tauaer, ssaaer, asmaer");
     return RRTMG_B200_OK;
@@ -591,7 +606,7 @@ int lw_chunk(const LwIn &in, const LwOut &out, int nc, int nlay, void *work, boo
 int sw_chunk(const SwIn &in, const SwOut &out, int nc, int nlay, void *work, bool fields, cudaStream_t st, bool last)
 {
     SwWork w;
-    sw_carve(w, work, nc, nlay, fields, in.icld >= 1 || in.iaer == 10);
+    sw_carve(w, work, nc, nlay, fields, in.icld >= 1 || in.iaer != 0);
     CUDA_OK(cudaMemsetAsync(w.sfluxzen, 0, (size_t)nc * NGPTSW * 8, st));
     G.launches += sw_run_pass(G.swt, in, out, w, st);
     CUDA_OK(cudaGetLastError());
@@ -653,7 +668,7 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
     const int chunk = pick_chunk(ncol);
     SwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    const bool general = in0.icld >= 1 || in0.iaer == 10;
+    const bool general = in0.icld >= 1 || in0.iaer != 0;
     if (const int rc = sw_err_begin(general)) return rc;
     if (wk.ensure(sw_carve(w, nullptr, chunk, nlay, fields, general))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
@@ -663,7 +678,7 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
 #define OFF(p) if (in.p) in.p += c0
         OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
         OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
-        OFF(cldfr); OFF(tauaer); OFF(ssaaer); OFF(asmaer);
+        OFF(cldfr); OFF(tauaer); OFF(ssaaer); OFF(asmaer); OFF(ecaer);
 #undef OFF
 #define OFF14(p) if (in.p) in.p += (size_t)14 * c0
         OFF14(taucld); OFF14(ssacld); OFF14(asmcld); OFF14(fsfcld);
@@ -681,6 +696,7 @@ void sw_set_optional(SwIn &in, const int *icld, const int *iaer, const SwOpt &o)
     in.iaer = iaer ? *iaer : 0;
     if (in.icld >= 1) { in.cldfr = o.cldfr; in.taucld = o.taucld; in.ssacld = o.ssacld; in.asmcld = o.asmcld; in.fsfcld = o.fsfcld; }
     if (in.iaer == 10) { in.tauaer = o.tauaer; in.ssaaer = o.ssaaer; in.asmaer = o.asmaer; }
+    if (in.iaer == 6) in.ecaer = o.ecaer;
 }
 
 // adjflux (SW rad.nomcica:953-972, earth_sun :734-758)
@@ -1178,14 +1194,14 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
                          int inflgsw, int, int, const double *cldfr,
                          const double *taucld, const double *ssacld, const double *asmcld, const double *fsfcld,
                          const double *, const double *, const double *, const double *,
-                         const double *tauaer, const double *ssaaer, const double *asmaer, const double *,
+                         const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                          double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                          double *swhrc, void *stream)
 {
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
-    SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer};
+    SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer};
     if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;       // also normalises *icld, *iaer
     SwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             asdir, asdif, aldir, aldif, coszen, sw_adjflux(adjes, dyofyr, scon)};
@@ -1206,8 +1222,8 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
                   const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                   double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc, double *swhrc)
 {
-    (void)iceflgsw; (void)liqflgsw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq; (void)ecaer;
-    const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer};
+    (void)iceflgsw; (void)liqflgsw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
+    const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer};
     // swuflxc, swdflxc, swhrc may be NULL: the clear-sky result is then not copied back
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr)
@@ -1215,12 +1231,12 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
     if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
     if (P_sw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
-    const bool cloud = icld && *icld >= 1, aer = iaer && *iaer == 10, general = cloud || aer;
+    const bool cloud = icld && *icld >= 1, aer = iaer && *iaer == 10, aer6 = iaer && *iaer == 6, general = cloud || aer || aer6;
     if (const int rc = sw_err_begin(general)) return rc;
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
-    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6 + (cloud ? 57 * L : 0) + (aer ? 42 * L : 0)) * 8 + 48 * 256;
+    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6 + (cloud ? 57 * L : 0) + (aer ? 42 * L : 0) + (aer6 ? 6 * L : 0)) * 8 + 48 * 256;
     const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
     SwWork wsz;
     const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields, general);
@@ -1251,6 +1267,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
             dopt.asmcld = a.up_banded(asmcld, 14, L); dopt.fsfcld = a.up_banded(fsfcld, 14, L);
         }
         if (aer) { dopt.tauaer = a.up(tauaer, 14 * L); dopt.ssaaer = a.up(ssaaer, 14 * L); dopt.asmaer = a.up(asmaer, 14 * L); }
+        if (aer6) dopt.ecaer = a.up(ecaer, 6 * L);
         if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
         SwIn in{nc, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2, d_ch4, d_n2o, d_o2,
                 d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjflux};

@@ -144,6 +144,8 @@ struct SwConst {
     SwBand band[NBNDSW];
     double preflog[59], tref[59];
     double heatfac, oneminus, bpade;
+    double rsrtaua[14][6], rsrpiza[14][6], rsrasya[14][6];   // ECMWF aerosol types (iaer = 6), rrtmg_sw_init.f90:370-470
+    int have_aer;                                            // the three tables above were found
 };
 
 struct SwTables {
@@ -162,6 +164,7 @@ struct SwIn {
     const double *cldfr = nullptr;                                                  // (ld, nlay)
     const double *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;   // (14, ld, nlay), inflgsw = 0
     const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;           // (ld, nlay, 14), iaer = 10
+    const double *ecaer = nullptr;                                                  // (ld, nlay, 6), iaer = 6
 };
 
 struct SwOut {

@@ -593,6 +593,20 @@ __global__ void __launch_bounds__(128) sw_optics_kernel(SwIn in, SwWork w)
         if (in.iaer == 10) {
             const size_t q = col + ld * (l + (size_t)nlay * ib);
             taua = in.tauaer[q]; asya = in.asmaer[q]; omga = in.ssaaer[q];
+        } else if (in.iaer == 6) {            // six ECMWF aerosol types (rad.nomcica:608-640)
+            taua = 0.0; asya = 0.0; omga = 0.0;
+            for (int ia = 0; ia < 6; ++ia) {
+                const double e = in.ecaer[col + ld * (l + (size_t)nlay * ia)];
+                taua = taua + c_sw.rsrtaua[ib][ia] * e;
+                omga = omga + c_sw.rsrtaua[ib][ia] * e * c_sw.rsrpiza[ib][ia];
+                asya = asya + c_sw.rsrtaua[ib][ia] * e * c_sw.rsrpiza[ib][ia] * c_sw.rsrasya[ib][ia];
+            }
+            if (taua == 0.0) {
+                asya = 0.0; omga = 1.0;
+            } else {
+                if (omga != 0.0) asya = asya / omga;
+                omga = omga / taua;
+            }
         }
         o[ib * 6 + 0] = tauc; o[ib * 6 + 1] = omgc; o[ib * 6 + 2] = asyc;
         o[ib * 6 + 3] = taua; o[ib * 6 + 4] = omga; o[ib * 6 + 5] = asya;

@@ -625,7 +625,7 @@ int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork
 {
     if (w.opt) {            // aerosols and/or clouds: the general kernel
         const unsigned nb = (w.nc + SV_COLS - 1) / SV_COLS;
-        const bool cloud = in.icld >= 1;
+        const bool cloud = in.icld >= 1;                // iaer = 6 / 10: aerosol properties per band in w.opt
         if (w.nlay <= 64) {
             if (cloud) sw_solver_gen_kernel<64, true><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);
             else sw_solver_gen_kernel<64, false><<<nb, SV_THREADS, 0, s>>>(t, in, out, w);

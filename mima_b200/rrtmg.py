@@ -220,8 +220,9 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
              tauaer=None, ssaaer=None, asmaer=None, ecaer=None, clear_sky=True):
     """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc); the last three are None with clear_sky=False.  icld >= 1 takes cloud optical properties
     (inflgsw = 0: cldfr (ncol,nlay) 0 or 1, taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)); iaer = 10 takes
-    tauaer/ssaaer/asmaer (ncol,nlay,14).  Water-path cloud inputs (inflgsw > 0) and iaer = 6 raise
-    RRTMGError(2); a partially cloudy layer raises RRTMGError(3) like the reference's stop."""
+    tauaer/ssaaer/asmaer (ncol,nlay,14); iaer = 6 takes ecaer (ncol,nlay,6), the optical depth at 0.55 micron of the six
+    ECMWF aerosol types.  Water-path cloud inputs (inflgsw > 0) raise RRTMGError(2); a partially cloudy layer raises
+    RRTMGError(3) like the reference's stop."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
     B = (NBNDSW, ncol, nlay)

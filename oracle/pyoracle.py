@@ -122,7 +122,7 @@ class Oracle:
     def rrtmg_sw(self, cols, *, stages: bool = False, nthreads: int | None = None, icld: int = 0, iaer: int = 0,
                  clouds=None, aerosols=None):
         """clouds = dict(cldfr (ncol,nlay), taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)) for icld >= 1 (inflgsw = 0);
-        aerosols = dict(tauaer/ssaaer/asmaer (ncol,nlay,14)) for iaer = 10."""
+        aerosols = dict(tauaer/ssaaer/asmaer (ncol,nlay,14)) for iaer = 10, dict(ecaer (ncol,nlay,6)) for iaer = 6."""
         ncol, nlay = cols.ncol, cols.nlay
         nthreads = nthreads or self.max_threads
         out = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("swuflx", "swdflx", "swuflxc", "swdflxc")}
@@ -144,9 +144,9 @@ class Oracle:
                                cols.ch4, cols.n2o, cols.o2, cols.albedo, cols.albedo, cols.albedo, cols.albedo,
                                cols.coszen)]
         extra = []
-        for src, keys in ((clouds, ("cldfr", "taucld", "ssacld", "asmcld", "fsfcld")), (aerosols, ("tauaer", "ssaaer", "asmaer"))):
+        for src, keys in ((clouds, ("cldfr", "taucld", "ssacld", "asmcld", "fsfcld")), (aerosols, ("tauaer", "ssaaer", "asmaer", "ecaer"))):
             for k in keys:
-                extra.append(_f(src[k]) if src is not None else None)
+                extra.append(_f(src[k]) if src is not None and k in src else None)
         rc = self.lib.orc_rrtmg_sw(C.c_int(ncol), C.c_int(nlay), C.c_int(int(icld)), C.c_int(int(iaer)), *[_p(a) for a in ins],
                                    C.c_double(cols.adjes), C.c_int(cols.dyofyr), C.c_double(cols.scon),
                                    C.c_int(0), *[None if a is None else _p(a) for a in extra],

@@ -89,6 +89,7 @@ typedef struct {
     double sw_rwgt[14 * 16];
     double sw_exp_tbl[ORC_NTBL + 1];
     double sw_bpade;
+    double rsrtaua[14][6], rsrpiza[14][6], rsrasya[14][6];   /* ECMWF aerosol types (iaer = 6), rrtmg_sw_init.f90:370-470 */
     orc_sw_kg_t sw[ORC_NBNDSW];
 } orc_state_t;
 
@@ -148,6 +149,7 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  const double *coszen, double adjes, int dyofyr, double scon,
                  int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
                  const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
+                 const double *ecaer,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *stages, int nthreads);
 

@@ -913,6 +913,7 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  const double *coszen, double adjes, int dyofyr, double scon,
                  int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
                  const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
+                 const double *ecaer,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *st, int nthreads)
 {
@@ -920,7 +921,7 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
     if (!g_orc.ready) return 1;
     if (icld < 0 || icld > 3) icld = 2;                              /* :468 */
     if (iaer != 0 && iaer != 6 && iaer != 10) iaer = 0;              /* :473 */
-    if (iaer == 6) return 2;                                         /* ECMWF aerosol types: not restated */
+    if (iaer == 6 && !ecaer) return 3;                               /* ecaer (ncol,nlay,6) */
     if (icld >= 1 && (inflgsw != 0 || !cldfr || !taucld || !ssacld || !asmcld || !fsfcld)) return 2; /* inflag 2: not restated */
     if (iaer == 10 && (!tauaer || !ssaaer || !asmaer)) return 3;
     if (icld >= 1) /* without McICA: clear or overcast layers only (:534-539, `stop 'PARTIAL CLOUD NOT ALLOWED'`) */
@@ -983,6 +984,22 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                     if (iaer == 10) {
                         const long o = i0 + (long)ncol * ((lay - 1) + (long)nlay * (ib - 1));
                         c->ptaua[lay][ib] = tauaer[o]; c->pasya[lay][ib] = asmaer[o]; c->pomga[lay][ib] = ssaaer[o];
+                    } else if (iaer == 6) { /* six ECMWF aerosol types (:608-640) */
+                        const orc_state_t *S = &g_orc;
+                        double ztaua = 0., zasya = 0., zomga = 0.;
+                        for (int ia = 1; ia <= 6; ++ia) {
+                            const double e = ecaer[i0 + (long)ncol * ((lay - 1) + (long)nlay * (ia - 1))];
+                            ztaua = ztaua + S->rsrtaua[ib - 1][ia - 1] * e;
+                            zomga = zomga + S->rsrtaua[ib - 1][ia - 1] * e * S->rsrpiza[ib - 1][ia - 1];
+                            zasya = zasya + S->rsrtaua[ib - 1][ia - 1] * e * S->rsrpiza[ib - 1][ia - 1] * S->rsrasya[ib - 1][ia - 1];
+                        }
+                        if (ztaua == 0.) {
+                            ztaua = 0.; zasya = 0.; zomga = 1.;
+                        } else {
+                            if (zomga != 0.) zasya = zasya / zomga;
+                            if (ztaua != 0.) zomga = zomga / ztaua;
+                        }
+                        c->ptaua[lay][ib] = ztaua; c->pasya[lay][ib] = zasya; c->pomga[lay][ib] = zomga;
                     } else {
                         c->ptaua[lay][ib] = 0.0; c->pasya[lay][ib] = 0.0; c->pomga[lay][ib] = 1.0;
                     }

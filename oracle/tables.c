@@ -396,6 +396,22 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
         K->rayl = ra ? ra->data[0] : 0.0;
         if (!K->sfluxref) return 6;
     }
+    /* ECMWF aerosol optical properties (swaerpr), (nbndsw, naerec) column-major in the blob */
+    {
+        const char *nm3[3] = {"swaer.rsrtaua", "swaer.rsrpiza", "swaer.rsrasya"};
+        double (*dst[3])[6] = {S->rsrtaua, S->rsrpiza, S->rsrasya};
+        for (int q = 0; q < 3; ++q) {
+            const orc_array_t *a = orc_blob_find(&bsw, nm3[q]);
+            if (!a) return 6;
+            for (int ib = 0; ib < 14; ++ib)
+                for (int ia = 0; ia < 6; ++ia) dst[q][ib][ia] = a->data[ib + 14 * ia];
+            reg_t *r = &g_reg[g_nreg++];               /* visible through orc_get_table, column-major as in the blob */
+            snprintf(r->name, sizeof r->name, "%s", nm3[q]);
+            r->n = 84;
+            r->data = (double *)malloc(sizeof(double) * 84);
+            memcpy(r->data, a->data, sizeof(double) * 84);
+        }
+    }
     /* export the lookup tables through the same registry (copies, so finalize can free them) */
     {
         const struct { const char *name; const double *src; } lut[3] = {

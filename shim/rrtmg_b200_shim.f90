@@ -184,9 +184,10 @@ contains
          reice(*), reliq(*), tauaer(*), ssaaer(*), asmaer(*), ecaer(*)
     real(c_double), contiguous, target, intent(inout) :: swuflx(:,:), swdflx(:,:), swhr(:,:), swuflxc(:,:), swdflxc(:,:), swhrc(:,:)
     integer(c_int) :: icld_c, iaer_c
-    type(c_ptr) :: pc(5), pa(3)
+    type(c_ptr) :: pc(5), pa(3), pec
     icld_c = icld; iaer_c = iaer
-    pc = c_null_ptr; pa = c_null_ptr
+    pc = c_null_ptr; pa = c_null_ptr; pec = c_null_ptr
+    if (iaer == 6) pec = c_loc(ecaer)
     if (icld /= 0) then
        pc(1) = c_loc(cldfr); pc(2) = c_loc(taucld); pc(3) = c_loc(ssacld); pc(4) = c_loc(asmcld); pc(5) = c_loc(fsfcld)
     endif
@@ -197,7 +198,7 @@ contains
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          c_loc(asdir), c_loc(asdif), c_loc(aldir), c_loc(aldif), c_loc(coszen), adjes, dyofyr, scon, &
          inflgsw, iceflgsw, liqflgsw, pc(1), pc(2), pc(3), pc(4), pc(5), c_null_ptr, &
-         c_null_ptr, c_null_ptr, c_null_ptr, pa(1), pa(2), pa(3), c_null_ptr, &
+         c_null_ptr, c_null_ptr, c_null_ptr, pa(1), pa(2), pa(3), pec, &
          c_loc(swuflx), c_loc(swdflx), c_loc(swhr), optout(swuflxc), optout(swdflxc), optout(swhrc)), 'rrtmg_sw')
     icld = icld_c; iaer = iaer_c
   end subroutine

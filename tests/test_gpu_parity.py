@@ -193,7 +193,7 @@ def test_unsupported_options_fail_loudly(gpu):
     assert e.value.code == 4
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_sw(c.ncol, c.nlay, 0, 6, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
-    assert e.value.code == 2                      # ECMWF aerosol climatology: not built
+    assert e.value.code == 4                      # iaer = 6 without ecaer
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_sw(c.ncol, c.nlay, 0, 10, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
     assert e.value.code == 4                      # iaer = 10 without the aerosol arrays

@@ -51,6 +51,27 @@ def test_aerosols(gpu, oracle, cols):
     assert (got[1][day, 0] < clear[1][day, 0]).all()            # aerosols dim the surface
 
 
+def test_ecmwf_aerosol_types(gpu, oracle, cols):
+    """iaer = 6: optical depths at 0.55 micron of the six ECMWF aerosol types, spectral properties from the swaerpr tables
+    (rrtmg_sw_init.f90:370-470, rad.nomcica:608-640); also together with clouds and in chunks."""
+    rng = np.random.default_rng(17)
+    aer = dict(ecaer=np.asfortranarray(rng.uniform(0.0, 0.05, (cols.ncol, cols.nlay, 6)) * (rng.uniform(size=(cols.ncol, cols.nlay, 1)) < 0.7)))
+    got = gpu.sw_from_columns(cols, iaer=6, aerosols=aer)
+    _check_outputs(got, oracle.rrtmg_sw(cols, iaer=6, aerosols=aer), SW_OUT)
+    clear = gpu.sw_from_columns(cols)
+    day = cols.coszen > 0.1
+    assert (got[1][day, 0] < clear[1][day, 0]).all()
+    c = cols.take(np.arange(150))
+    aer = dict(ecaer=np.asfortranarray(aer["ecaer"][:150]))
+    cl = _clouds(c, rng)
+    gpu.set_option("host_chunk", 64)
+    try:
+        _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=6, clouds=cl, aerosols=aer),
+                       oracle.rrtmg_sw(c, icld=2, iaer=6, clouds=cl, aerosols=aer), SW_OUT)
+    finally:
+        gpu.set_option("host_chunk", 0)
+
+
 def test_zero_aerosol_reproduces_the_clear_path(gpu, cols):
     """tauaer = 0 through the general kernel against MiMA's specialised kernel: the same numbers to rounding
     (the two differ only in reciprocal refinement and summation order)."""

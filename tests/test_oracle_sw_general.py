@@ -75,5 +75,32 @@ def test_switch_handling(oracle, cols):
     cl["cldfr"][2, 3] = 0.4
     with pytest.raises(RuntimeError, match="rc=4"):             # stop 'PARTIAL CLOUD NOT ALLOWED' (:537)
         oracle.rrtmg_sw(c, icld=2, clouds=cl)
-    with pytest.raises(RuntimeError, match="rc=2"):
-        oracle.rrtmg_sw(c, iaer=6)
+    with pytest.raises(RuntimeError, match="rc=3"):
+        oracle.rrtmg_sw(c, iaer=6)                               # needs ecaer
+
+
+def test_ecmwf_aerosol_types(oracle, cols):
+    """iaer = 6 (rad.nomcica:608-640): zero amounts are the clear path bit for bit; one type alone reproduces iaer = 10
+    fed with that type's band properties from the swaerpr tables."""
+    ref = oracle.rrtmg_sw(cols)
+    z = np.zeros((cols.ncol, cols.nlay, 6), order="F")
+    got = oracle.rrtmg_sw(cols, iaer=6, aerosols=dict(ecaer=z))
+    for k in SW:
+        assert np.array_equal(got[k], ref[k]), k
+    tau = oracle.table("swaer.rsrtaua").reshape(14, 6, order="F")
+    piz = oracle.table("swaer.rsrpiza").reshape(14, 6, order="F")
+    asy = oracle.table("swaer.rsrasya").reshape(14, 6, order="F")
+    assert tau[9, 0] == 1.69446 and piz[0, 5] == .2355667 and asy[13, 1] == 0.818871      # swaerpr literals
+    e = np.zeros((cols.ncol, cols.nlay, 6), order="F")
+    e[:, :12, 2] = 0.03                                          # type 3 in the lowest 12 layers
+    six = oracle.rrtmg_sw(cols, iaer=6, aerosols=dict(ecaer=e))
+    shp = (cols.ncol, cols.nlay, 14)
+    on = (e[:, :, 2] > 0)[:, :, None]
+    ten = oracle.rrtmg_sw(cols, iaer=10, aerosols=dict(
+        tauaer=np.asfortranarray(np.broadcast_to(tau[None, None, :, 2], shp) * e[:, :, 2:3]),
+        ssaaer=np.asfortranarray(np.where(on, np.broadcast_to(piz[None, None, :, 2], shp), 1.0)),
+        asmaer=np.asfortranarray(np.where(on, np.broadcast_to(asy[None, None, :, 2], shp), 0.0))))
+    for k in SW:
+        scale = max(np.abs(ten[k]).max(), 1.0)
+        assert np.max(np.abs(six[k] - ten[k])) < 1e-12 * scale, k
+    assert (six["swdflx"][cols.coszen > 0.1, 0] < ref["swdflx"][cols.coszen > 0.1, 0]).all()

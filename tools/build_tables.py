@@ -260,6 +260,16 @@ def build_sw():
     for n, a in arrs.items():
         assert not np.isnan(a).any()
         out[f"swref.{n}"] = a
+    # ECMWF aerosol optical properties per band and aerosol type (iaer = 6): rsrtaua/rsrpiza/rsrasya(nbndsw, naerec),
+    # written row by row as `name(ib, :) = (/ six values /)` in swaerpr (rrtmg_sw_init.f90:370-470)
+    subs = split_subroutines(os.path.join(SW, "src/rrtmg_sw_init.f90"), r"(swaerpr)")
+    text = " ".join(strip_comment(l).replace("&", " ") for l in subs["swaerpr"])
+    for name in ("rsrtaua", "rsrpiza", "rsrasya"):
+        a = np.full((14, 6), np.nan, order="F")
+        for m in re.finditer(name + r"\(\s*(\d+)\s*,\s*:\s*\)\s*=\s*\(/(.*?)/\)", text, re.S):
+            a[int(m.group(1)) - 1, :] = parse_numbers(m.group(2))
+        assert not np.isnan(a).any(), name
+        out[f"swaer.{name}"] = a
     return out
 
 
