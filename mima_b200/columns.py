@@ -171,7 +171,7 @@ def make_columns(resolution: str = "T42L40", *, seed: int = 20240917, co2_ppmv: 
         w = (lph[:, 1:-1] - lp[:, :-1]) / (lp[:, 1:] - lp[:, :-1])
         Th[:, 1:-1] = T[:, :-1] * (1 - w) + T[:, 1:] * w
         Th[:, -1] = Ts
-        Th[:, 0] = 0.5 * (3.0 * T[:, 0] - T[:, 1])
+        Th[:, 0] = 0.5 * (3.0 * T[:, 0] - T[:, 1]) if L > 1 else T[:, 0]      # a single layer has nothing to extrapolate from
         Th = np.clip(Th, 100.0, 370.0)
         q = 0.8 * _qsat(T, pf) * (pf / ps[:, None]) ** 3 * np.exp(0.2 * rng.standard_normal((n, L)))
         qstrat = (2.0 + 2.0 * rng.random((n, L))) * 1e-6
