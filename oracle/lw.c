@@ -55,6 +55,7 @@ typedef struct {
     /* clouds (icld >= 1): inatm :868-887, cldprop inflag = 0 (cldprop.f90:154-176); cldfrac[0] and cldfrac[nlayers+1]
        are the out-of-range elements rtrnmr.f90:403-404, 472-473 multiply by factors that are zero there */
     double cldfrac[NL + 2], taucloud[NL][17];
+    int ncbands;   /* 1, 5 or 16: what cldprop leaves behind for the column; selects ipat in rtrn / rtrnmr */
 } lwcol_t;
 
 /* ---------------------------------------------------------------- inatm (rad.nomcica:572-901) */
@@ -1132,6 +1133,103 @@ static void rtrnmr_clear(lwcol_t *c)
     c->htrc[nlayers] = 0.0;
 }
 
+/* ---------------------------------------------------------------- cldprop (rrtmg_lw_cldprop.f90:31-276)
+   returns 0, or the number of the Fortran `stop`: 1 ICE RADIUS TOO SMALL (:193), 2 ICE RADIUS OUT OF BOUNDS (:198, :209),
+   3 ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS (:225), 4 LIQUID EFFECTIVE RADIUS OUT OF BOUNDS (:253) */
+static int cldprop(lwcol_t *c, int inflag, int iceflag, int liqflag, const double *tauc /* [lay][ib] 1-based */,
+                   const double *ciwp, const double *clwp, const double *rei, const double *rel)
+{
+    const orc_state_t *S = &g_orc;
+    const int nlayers = c->nlayers;
+    const double cldmin = 1.e-20;
+    /* icb (:147-149): spectral region of band ib for iceind / liqind = 0, 1, 2 */
+    static const int icb[3][17] = {{0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+                                   {0, 1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5},
+                                   {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16}};
+    double abscoice[17], abscoliq[17], tauctot[NL];
+    int ncbands = 1, iceind = 0, liqind = 0, index;
+    double factor, fint, radice, radliq, cwp;
+    for (int ib = 0; ib <= 16; ++ib) { abscoice[ib] = 0.; abscoliq[ib] = 0.; }
+    for (int lay = 1; lay <= nlayers; ++lay) {
+        tauctot[lay] = 0.;
+        for (int ib = 1; ib <= 16; ++ib) {
+            c->taucloud[lay][ib] = 0.0;
+            tauctot[lay] = tauctot[lay] + tauc[lay * 17 + ib];
+        }
+    }
+    for (int lay = 1; lay <= nlayers; ++lay) {
+        cwp = ciwp[lay] + clwp[lay];
+        if (c->cldfrac[lay] >= cldmin && (cwp >= cldmin || tauctot[lay] >= cldmin)) {
+            if (inflag == 0) {
+                ncbands = 16;
+                for (int ib = 1; ib <= ncbands; ++ib) c->taucloud[lay][ib] = tauc[lay * 17 + ib];
+            } else if (inflag == 1) {
+                ncbands = 16;
+                for (int ib = 1; ib <= ncbands; ++ib) c->taucloud[lay][ib] = S->abscld1 * cwp;
+            } else if (inflag == 2) {
+                radice = rei[lay];
+                if (ciwp[lay] == 0.0) {
+                    abscoice[1] = 0.0;
+                    iceind = 0;
+                } else if (iceflag == 0) {
+                    if (radice < 10.0) return 1;
+                    abscoice[1] = S->absice0[1] + S->absice0[2] / radice;
+                    iceind = 0;
+                } else if (iceflag == 1) {
+                    if (radice < 13.0 || radice > 130.) return 2;
+                    ncbands = 5;
+                    for (int ib = 1; ib <= ncbands; ++ib) abscoice[ib] = S->absice1[1][ib] + S->absice1[2][ib] / radice;
+                    iceind = 1;
+                } else if (iceflag == 2) {
+                    if (radice < 5.0 || radice > 131.0) return 2;
+                    ncbands = 16;
+                    factor = (radice - 2.) / 3.;
+                    index = (int)factor;
+                    if (index == 43) index = 42;
+                    fint = factor - (double)index;
+                    for (int ib = 1; ib <= ncbands; ++ib)
+                        abscoice[ib] = S->absice2[index][ib] + fint * (S->absice2[index + 1][ib] - (S->absice2[index][ib]));
+                    iceind = 2;
+                } else if (iceflag == 3) {
+                    if (radice < 5.0 || radice > 140.0) return 3;
+                    ncbands = 16;
+                    factor = (radice - 2.) / 3.;
+                    index = (int)factor;
+                    if (index == 46) index = 45;
+                    fint = factor - (double)index;
+                    for (int ib = 1; ib <= ncbands; ++ib)
+                        abscoice[ib] = S->absice3[index][ib] + fint * (S->absice3[index + 1][ib] - (S->absice3[index][ib]));
+                    iceind = 2;
+                }
+                if (clwp[lay] == 0.0) {
+                    abscoliq[1] = 0.0;
+                    liqind = 0;
+                    if (iceind == 1) iceind = 2;
+                } else if (liqflag == 0) {
+                    abscoliq[1] = S->absliq0;
+                    liqind = 0;
+                    if (iceind == 1) iceind = 2;
+                } else if (liqflag == 1) {
+                    radliq = rel[lay];
+                    if (radliq < 2.5 || radliq > 60.) return 4;
+                    index = (int)(radliq - 1.5);
+                    if (index == 0) index = 1;
+                    if (index == 58) index = 57;
+                    fint = radliq - 1.5 - (double)index;
+                    ncbands = 16;
+                    for (int ib = 1; ib <= ncbands; ++ib)
+                        abscoliq[ib] = S->absliq1[index][ib] + fint * (S->absliq1[index + 1][ib] - (S->absliq1[index][ib]));
+                    liqind = 2;
+                }
+                for (int ib = 1; ib <= ncbands; ++ib)
+                    c->taucloud[lay][ib] = ciwp[lay] * abscoice[icb[iceind][ib]] + clwp[lay] * abscoliq[icb[liqind][ib]];
+            }
+        }
+    }
+    c->ncbands = ncbands;
+    return 0;
+}
+
 /* ---------------------------------------------------------------- cloudy sky: rtrn (random overlap, icld = 1,
    rrtmg_lw_rtrn.f90:262-588) and rtrnmr (maximum/random overlap, icld = 2, 3, rrtmg_lw_rtrnmr.f90:259-779) in one body:
    the two share the layer optics (:514-567) and differ in how the cloudy and clear parts of a level are carried. */
@@ -1175,9 +1273,11 @@ static void rtrn_cloudy(lwcol_t *c, int maxrandom)
         d_urad_dt[lev] = 0.0; d_clrurad_dt[lev] = 0.0;
         c->dtotuflux_dt[lev] = 0.0; c->dtotuclfl_dt[lev] = 0.0;
     }
-    /* cloud optical depth along the diffusivity angle (rtrnmr :316-324, rtrn :302-316); ncbands = 16 <=> ib = iband */
-    for (int lay = 1; lay <= nlayers; ++lay)
-        for (int ib = 1; ib <= 16; ++ib) {
+    /* cloud optical depth along the diffusivity angle (rtrnmr :316-324, rtrn :302-316), for the column's ncbands */
+    for (int lay = 1; lay <= nlayers; ++lay) {
+        icldlyr[lay] = cldfrac[lay] >= 1.e-6;          /* set inside the ib loop in the Fortran (ncbands >= 1) */
+        for (int ib = 1; ib <= 16; ++ib) { odcld[lay][ib] = 0.0; abscld[lay][ib] = 0.0; efclfrac[lay][ib] = 0.0; }
+        for (int ib = 1; ib <= c->ncbands; ++ib) {
             if (cldfrac[lay] >= 1.e-6) {
                 odcld[lay][ib] = secdiff[ib] * c->taucloud[lay][ib];
                 if (!maxrandom) {
@@ -1193,6 +1293,7 @@ static void rtrn_cloudy(lwcol_t *c, int maxrandom)
                 icldlyr[lay] = 0;
             }
         }
+    }
     if (maxrandom) {
         /* maximum/random overlap factors, upward (:328-407) */
         istcld[1] = 1;
@@ -1316,7 +1417,9 @@ static void rtrn_cloudy(lwcol_t *c, int maxrandom)
 
     igc = 1;
     for (iband = 1; iband <= 16; ++iband) {
-        const int ib = iband;            /* ipat(iband, 2), ncbands = 16 */
+        /* ipat (rtrnmr.f90:243-245): cloud band of spectral band iband for ncbands = 1, 5, 16 */
+        static const int ipat5[17] = {0, 1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
+        const int ib = c->ncbands == 16 ? iband : (c->ncbands == 5 ? ipat5[iband] : 1);
         do {
             double radld = 0., radclrd = 0., radlu, radclru, rad0, reflect;
             double cldradd = 0., clrradd = 0., cldradu = 0., clrradu = 0., oldcld, oldclr, rad = 0., radmod;
@@ -1564,6 +1667,7 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
                  int inflglw, const double *cldfr, const double *taucld,
+                 int iceflglw, int liqflglw, const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                  double *duflx_dt, double *duflxc_dt,
                  const orc_lw_stages_t *st, int nthreads)
@@ -1571,8 +1675,11 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
     if (!g_orc.ready) return 1;
     if (icld < 0 || icld > 3) icld = 2; /* :437 */
     if (idrv < 0 || idrv > 1) return 2;
-    if (icld >= 1 && inflglw != 0) return 2; /* cldprop's water-path parameterisations are not restated */
+    if (icld >= 1 && (inflglw < 0 || inflglw > 2)) return 2;
     if (icld >= 1 && (!cldfr || !taucld)) return 3;
+    if (icld >= 1 && inflglw >= 1 && (!cicewp || !cliqwp)) return 3;
+    if (icld >= 1 && inflglw == 2 && (!reice || !reliq)) return 3;
+    int cld_stop = 0; /* number of the cldprop `stop` hit by some column (10 + n is returned) */
     if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return 3;
     if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
     if (nthreads < 1) nthreads = 1;
@@ -1598,18 +1705,23 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                   n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer);
             /* cldprop with cldfrac=0: ncbands=1, taucloud=0 -- nothing to compute */
             if (icld >= 1) {
-                /* inatm :868-887 and cldprop inflag = 0 (cldprop.f90:154-176, cwp = 0) */
-                const double cldmin = 1.e-20;
+                /* inatm :868-887, then cldprop */
+                static __thread double tauc[NL * 17], ciwp[NL], clwp[NL], rei[NL], rel[NL];
                 c->cldfrac[0] = 0.; c->cldfrac[nlay + 1] = 0.;
                 for (int l = 1; l <= nlay; ++l) {
-                    double tauctot = 0.;
-                    c->cldfrac[l] = cldfr[(long)(l - 1) * ncol + iplon - 1];
-                    for (int ib = 1; ib <= 16; ++ib) {
-                        c->taucloud[l][ib] = 0.0;
-                        tauctot = tauctot + taucld[(ib - 1) + 16 * ((iplon - 1) + (long)ncol * (l - 1))];
-                    }
-                    if (c->cldfrac[l] >= cldmin && tauctot >= cldmin)
-                        for (int ib = 1; ib <= 16; ++ib) c->taucloud[l][ib] = taucld[(ib - 1) + 16 * ((iplon - 1) + (long)ncol * (l - 1))];
+                    const long o = (long)(l - 1) * ncol + iplon - 1;
+                    c->cldfrac[l] = cldfr[o];
+                    ciwp[l] = cicewp ? cicewp[o] : 0.; clwp[l] = cliqwp ? cliqwp[o] : 0.;
+                    rei[l] = reice ? reice[o] : 0.; rel[l] = reliq ? reliq[o] : 0.;
+                    for (int ib = 1; ib <= 16; ++ib) tauc[l * 17 + ib] = taucld[(ib - 1) + 16 * ((iplon - 1) + (long)ncol * (l - 1))];
+                }
+                const int stop = cldprop(c, inflglw, iceflglw, liqflglw, tauc, ciwp, clwp, rei, rel);
+                if (stop) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+                    cld_stop = stop;
+                    continue;
                 }
             }
             setcoef(c, istart);
@@ -1669,5 +1781,5 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
         }
         free(c);
     }
-    return 0;
+    return cld_stop ? 10 + cld_stop : 0;
 }

@@ -77,9 +77,10 @@ class Oracle:
 
     # ------------------------------------------------------------------ LW
     def rrtmg_lw(self, cols, *, stages: bool = False, nthreads: int | None = None, tauaer=None, idrv: int = 0,
-                 icld: int = 0, clouds=None):
+                 icld: int = 0, clouds=None, inflglw: int = 0, iceflglw: int = 0, liqflglw: int = 0):
         """clouds = dict(cldfr (ncol,nlay), taucld (16,ncol,nlay)) for icld >= 1 (inflglw = 0): icld = 1 random overlap
-        (rtrn), 2/3 maximum/random overlap (rtrnmr)."""
+        (rtrn), 2/3 maximum/random overlap (rtrnmr); with inflglw = 1, 2 also cicewp, cliqwp (g/m2) and reice, reliq
+        (microns), all (ncol,nlay) (cldprop's parameterisations).  A Fortran `stop` of cldprop comes back as rc = 10 + n."""
         ncol, nlay = cols.ncol, cols.nlay
         nthreads = nthreads or self.max_threads
         out = {k: np.zeros((ncol, nlay + 1), order="F") for k in ("uflx", "dflx", "uflxc", "dflxc")}
@@ -105,9 +106,14 @@ class Oracle:
                                cols.emis, tauaer)]
         if idrv:
             out.update({k: np.zeros((ncol, nlay + 1), order="F") for k in ("duflx_dt", "duflxc_dt")})
-        cl = [None, None] if clouds is None else [_f(clouds["cldfr"]), _f(clouds["taucld"])]
+        clouds = clouds or {}
+        if clouds and "taucld" not in clouds:
+            clouds = dict(clouds, taucld=np.zeros((16, ncol, nlay), order="F"))
+        cl = [_f(clouds[k]) if k in clouds else None for k in ("cldfr", "taucld")]
+        wp = [_f(clouds[k]) if k in clouds else None for k in ("cicewp", "cliqwp", "reice", "reliq")]
         rc = self.lib.orc_rrtmg_lw(C.c_int(ncol), C.c_int(nlay), C.c_int(int(icld)), C.c_int(int(idrv)), *[_p(a) for a in ins],
-                                   C.c_int(0), *[None if a is None else _p(a) for a in cl],
+                                   C.c_int(int(inflglw)), *[None if a is None else _p(a) for a in cl],
+                                   C.c_int(int(iceflglw)), C.c_int(int(liqflglw)), *[None if a is None else _p(a) for a in wp],
                                    _p(out["uflx"]), _p(out["dflx"]), _p(out["hr"]), _p(out["uflxc"]),
                                    _p(out["dflxc"]), _p(out["hrc"]),
                                    _p(out["duflx_dt"]) if idrv else None, _p(out["duflxc_dt"]) if idrv else None,

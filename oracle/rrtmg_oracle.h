@@ -90,6 +90,8 @@ typedef struct {
     double sw_exp_tbl[ORC_NTBL + 1];
     double sw_bpade;
     double rsrtaua[14][6], rsrpiza[14][6], rsrasya[14][6];   /* ECMWF aerosol types (iaer = 6), rrtmg_sw_init.f90:370-470 */
+    /* LW cloud absorption coefficients (lwcldpr, rrtmg_lw_init.f90:2018-2656), Fortran 1-based indices kept */
+    double abscld1, absliq0, absice0[3], absice1[3][6], absice2[44][17], absice3[47][17], absliq1[59][17];
     orc_sw_kg_t sw[ORC_NBNDSW];
 } orc_state_t;
 
@@ -136,6 +138,7 @@ int orc_rrtmg_lw(int ncol, int nlay, int icld, int idrv,
                  const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                  const double *ccl4vmr, const double *emis, const double *tauaer,
                  int inflglw, const double *cldfr, const double *taucld,
+                 int iceflglw, int liqflglw, const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                  double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                  double *duflx_dt, double *duflxc_dt, /* (ncol, nlay+1), written when idrv == 1; may be NULL otherwise */
                  const orc_lw_stages_t *stages, int nthreads);

@@ -396,6 +396,28 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
         K->rayl = ra ? ra->data[0] : 0.0;
         if (!K->sfluxref) return 6;
     }
+    /* LW cloud absorption coefficients (lwcldpr) */
+    {
+        const orc_array_t *a;
+        if (!(a = orc_blob_find(&bref, "lwcld.abscld1"))) return 7;
+        S->abscld1 = a->data[0];
+        if (!(a = orc_blob_find(&bref, "lwcld.absliq0"))) return 7;
+        S->absliq0 = a->data[0];
+        if (!(a = orc_blob_find(&bref, "lwcld.absice0"))) return 7;
+        for (int i = 1; i <= 2; ++i) S->absice0[i] = a->data[i - 1];
+        if (!(a = orc_blob_find(&bref, "lwcld.absice1"))) return 7;
+        for (int i = 1; i <= 2; ++i)
+            for (int ib = 1; ib <= 5; ++ib) S->absice1[i][ib] = a->data[(i - 1) + 2 * (ib - 1)];
+        if (!(a = orc_blob_find(&bref, "lwcld.absice2"))) return 7;
+        for (int i = 1; i <= 43; ++i)
+            for (int ib = 1; ib <= 16; ++ib) S->absice2[i][ib] = a->data[(i - 1) + 43 * (ib - 1)];
+        if (!(a = orc_blob_find(&bref, "lwcld.absice3"))) return 7;
+        for (int i = 1; i <= 46; ++i)
+            for (int ib = 1; ib <= 16; ++ib) S->absice3[i][ib] = a->data[(i - 1) + 46 * (ib - 1)];
+        if (!(a = orc_blob_find(&bref, "lwcld.absliq1"))) return 7;
+        for (int i = 1; i <= 58; ++i)
+            for (int ib = 1; ib <= 16; ++ib) S->absliq1[i][ib] = a->data[(i - 1) + 58 * (ib - 1)];
+    }
     /* ECMWF aerosol optical properties (swaerpr), (nbndsw, naerec) column-major in the blob */
     {
         const char *nm3[3] = {"swaer.rsrtaua", "swaer.rsrpiza", "swaer.rsrasya"};

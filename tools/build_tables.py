@@ -293,6 +293,22 @@ def build_lw_ref():
     for n, a in arrs.items():
         assert not np.isnan(a).any(), n
         out[f"lwref.{n}"] = a
+    # cloud absorption coefficients of cldprop's parameterisations (lwcldpr, rrtmg_lw_init.f90:2018-2656)
+    subs = split_subroutines(os.path.join(LW, "src/rrtmg_lw_init.f90"), r"(lwcldpr)")
+    decls = {"absice0": ((2,), (1,)), "absice2": ((43, 16), (1, 1)), "absice3": ((46, 16), (1, 1)), "absliq1": ((58, 16), (1, 1))}
+    arrs = parse_assignments(subs["lwcldpr"], decls)
+    for n, a in arrs.items():
+        assert not np.isnan(a).any(), n
+        out[f"lwcld.{n}"] = a
+    text = " ".join(strip_comment(l).replace("&", " ") for l in subs["lwcldpr"])
+    a1 = np.full((2, 5), np.nan, order="F")
+    for m in re.finditer(r"absice1\(\s*(\d+)\s*,\s*:\s*\)\s*=\s*\(/(.*?)/\)", text, re.S):
+        a1[int(m.group(1)) - 1, :] = parse_numbers(m.group(2))
+    assert not np.isnan(a1).any()
+    out["lwcld.absice1"] = a1
+    for name in ("abscld1", "absliq0"):
+        m = re.search(name + r"\s*=\s*([-+0-9.eEdD]+)_rb", text)
+        out[f"lwcld.{name}"] = np.array([float(m.group(1).replace("d", "e").replace("D", "e"))])
     return out
 
 
