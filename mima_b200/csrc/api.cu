@@ -55,7 +55,8 @@ struct State {
     bool lw_ready = false;
     LwConst lwc;
     LwTables lwt{};
-    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_cap;
+    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_cap, lw_err;
+    bool lw_have_cld = false;
     LwWork lw_last{};
     int lw_last_ncol = 0;
     // SW
@@ -377,6 +378,21 @@ int lw_init_impl(double cpdair)
     G.lwt.totplnkderiv = (const double *)G.lw_totplnk.p + 181 * 16;
     G.lwt.exptfn = (const double *)G.lw_exptfn.p;
     if (lw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_lw) failed");
+    {   // cloud absorption coefficients of cldprop (lwcldpr); optional: needed for inflglw > 0 only
+        static LwCldConst k;
+        const HostArr *a1 = find("lwcld.abscld1"), *l0 = find("lwcld.absliq0"), *i0 = find("lwcld.absice0"), *i1 = find("lwcld.absice1"),
+                      *i2 = find("lwcld.absice2"), *i3 = find("lwcld.absice3"), *l1 = find("lwcld.absliq1");
+        k.have = a1 && l0 && i0 && i1 && i2 && i3 && l1 && i0->size() == 2 && i1->size() == 10 && i2->size() == 43 * 16 &&
+                 i3->size() == 46 * 16 && l1->size() == 58 * 16;
+        if (k.have) {
+            k.abscld1 = a1->data[0]; k.absliq0 = l0->data[0];
+            std::memcpy(k.absice0, i0->data.data(), sizeof k.absice0); std::memcpy(k.absice1, i1->data.data(), sizeof k.absice1);
+            std::memcpy(k.absice2, i2->data.data(), sizeof k.absice2); std::memcpy(k.absice3, i3->data.data(), sizeof k.absice3);
+            std::memcpy(k.absliq1, l1->data.data(), sizeof k.absliq1);
+            if (lw_upload_cld(k)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(d_lwcld) failed");
+        }
+        G.lw_have_cld = k.have != 0;
+    }
     G.lw_ready = true;
     return RRTMG_B200_OK;
 }
@@ -491,7 +507,7 @@ struct Carver {
         return r;
     }
 };
-size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
+size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields, bool cloud = false)
 {
     Carver c(base);
     w.nc = nc; w.nlay = nlay;
@@ -511,6 +527,9 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields)
     w.plankbnd = c.take<double>((size_t)nc * 16);
     w.taug = c.take<double>(np * NGPTLW);
     w.fracs = c.take<double>(np * NGPTLW);
+    w.taucloud = cloud ? c.take<double>(np * 16) : nullptr;
+    w.ncbands = cloud ? c.take<int>(nc) : nullptr;
+    w.err = cloud ? (int *)G.lw_err.p : nullptr;
     return c.off + 256;
 }
 size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool general = false)
@@ -544,6 +563,8 @@ int pick_chunk(int ncol)
 struct LwOpt {                // the optional cloud arguments of rrtmg_lw
     int inflglw = 0;
     const double *cldfr = nullptr, *taucld = nullptr;
+    int iceflglw = 0, liqflglw = 0;
+    const double *cicewp = nullptr, *cliqwp = nullptr, *reice = nullptr, *reliq = nullptr;
 };
 int lw_validate(int ncol, int nlay, int *icld, int idrv, const LwOpt &o = LwOpt())
 {
@@ -551,9 +572,13 @@ int lw_validate(int ncol, int nlay, int *icld, int idrv, const LwOpt &o = LwOpt(
     if (ncol < 0 || nlay < 1 || nlay > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "ncol/nlay out of range (1 <= nlay <= 128)");
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;     // LW rad.nomcica:437
     if (icld && *icld != 0) {
-        if (o.inflglw != 0)
-            return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_lw: inflglw > 0 (cloud optics from water paths, cldprop parameterisations) is not built");
+        if (o.inflglw < 0 || o.inflglw > 2) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: inflglw must be 0, 1 or 2");
         if (!o.cldfr || !o.taucld) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: icld > 0 needs cldfr and taucld");
+        if (o.inflglw >= 1 && (!o.cicewp || !o.cliqwp)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: inflglw > 0 needs cicewp and cliqwp");
+        if (o.inflglw == 2 && (o.iceflglw < 0 || o.iceflglw > 3 || o.liqflglw < 0 || o.liqflglw > 1))
+            return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: iceflglw must be 0..3 and liqflglw 0..1");
+        if (o.inflglw == 2 && (!o.reice || !o.reliq)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: inflglw = 2 needs reice and reliq");
+        if (o.inflglw >= 1 && !G.lw_have_cld) return fail(RRTMG_B200_ERR_TABLES, "rrtmg_lw: inflglw > 0 needs the lwcld.* tables");
     }
     if (idrv != 0 && idrv != 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv must be 0 or 1");
     return RRTMG_B200_OK;
@@ -591,7 +616,7 @@ int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt
 int lw_chunk(const LwIn &in, const LwOut &out, int nc, int nlay, void *work, bool fields, cudaStream_t st, bool last)
 {
     LwWork w;
-    lw_carve(w, work, nc, nlay, fields);
+    lw_carve(w, work, nc, nlay, fields, in.icld >= 1);
     w.idrv = out.duflx_dt ? 1 : 0;
     double *cap = nullptr;
     if (fields) {
@@ -632,6 +657,33 @@ int sw_err_end(bool general)
     return RRTMG_B200_OK;
 }
 
+// cloudy LW: cldprop's Fortran `stop`s (radii out of range) come back through one device word
+int lw_err_begin(bool cloud)
+{
+    if (!cloud) return RRTMG_B200_OK;
+    if (G.lw_err.ensure(256)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed");
+    CUDA_OK(cudaMemset(G.lw_err.p, 0, 4));
+    return RRTMG_B200_OK;
+}
+int lw_err_end(bool cloud)
+{
+    if (!cloud) return RRTMG_B200_OK;
+    int flag = 0;
+    CUDA_OK(cudaMemcpy(&flag, G.lw_err.p, 4, cudaMemcpyDeviceToHost));
+    static const char *msg[5] = {"", "ICE RADIUS TOO SMALL", "ICE RADIUS OUT OF BOUNDS", "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS",
+                                 "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS"};
+    if (flag >= 1 && flag <= 4) return fail(RRTMG_B200_ERR_CLOUD_INPUT, std::string("rrtmg_lw cldprop: ") + msg[flag]);
+    return RRTMG_B200_OK;
+}
+void lw_set_optional(LwIn &in, const int *icld, const LwOpt &o)
+{
+    if (!icld || *icld < 1) return;
+    in.icld = *icld; in.cldfr = o.cldfr; in.taucld = o.taucld;
+    in.inflg = o.inflglw; in.iceflg = o.iceflglw; in.liqflg = o.liqflglw;
+    if (o.inflglw >= 1) { in.cicewp = o.cicewp; in.cliqwp = o.cliqwp; }
+    if (o.inflglw == 2) { in.reice = o.reice; in.reliq = o.reliq; }
+}
+
 int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, const LwOut &out0, cudaStream_t st, DevBuf *work = nullptr,
                    const LwOpt &opt = LwOpt())
 {
@@ -642,7 +694,9 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
     const int chunk = pick_chunk(ncol);
     LwWork w;
     const bool fields = G.capture && ncol <= chunk;
-    if (wk.ensure(lw_carve(w, nullptr, chunk, nlay, fields))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
+    const bool cloudy = in0.icld >= 1;
+    if (const int rc = lw_err_begin(cloudy)) return rc;
+    if (wk.ensure(lw_carve(w, nullptr, chunk, nlay, fields, cloudy))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
         const int nc = (ncol - c0 < chunk) ? ncol - c0 : chunk;
         LwIn in = in0;
@@ -650,13 +704,15 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
 #define OFF(p) if (in.p) in.p += c0
         OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
         OFF(o2); OFF(cfc11); OFF(cfc12); OFF(cfc22); OFF(ccl4); OFF(emis); OFF(tauaer); OFF(cldfr);
+        OFF(cicewp); OFF(cliqwp); OFF(reice); OFF(reliq);
 #undef OFF
         if (in.taucld) in.taucld += (size_t)16 * c0;
         out.uflx += c0; out.dflx += c0; out.hr += c0; out.uflxc += c0; out.dflxc += c0; out.hrc += c0;
         if (out.duflx_dt) { out.duflx_dt += c0; out.duflxc_dt += c0; }
         if (const int rc = lw_chunk(in, out, nc, nlay, wk.p, fields, st, c0 + nc >= ncol)) return rc;
     }
-    return RRTMG_B200_OK;
+    if (cloudy) CUDA_OK(cudaStreamSynchronize(st));
+    return lw_err_end(cloudy);
 }
 
 int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, const SwOut &out0, cudaStream_t st, DevBuf *work = nullptr,
@@ -1068,7 +1124,7 @@ int rrtmg_b200_sw_init(double cpdair)
 int rrtmg_b200_finalize(void)
 {
     std::lock_guard<std::mutex> lk(G.mu);
-    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_err})
+    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.lw_err, &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_err})
         b->release();
     P_lw.release();
     P_sw.release();
@@ -1109,8 +1165,8 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
                          const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                          const double *cfc11vmr, const double *cfc12vmr, const double *cfc22vmr,
                          const double *ccl4vmr, const double *emis,
-                         int inflglw, int, int, const double *cldfr, const double *taucld, const double *, const double *,
-                         const double *, const double *,
+                         int inflglw, int iceflglw, int liqflglw, const double *cldfr, const double *taucld,
+                         const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                          const double *tauaer,
                          double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                          double *duflx_dt, double *duflxc_dt, void *stream)
@@ -1120,9 +1176,9 @@ int rrtmg_b200_lw_device(int ncol, int nlay, int *icld, int idrv,
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
     LwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, tauaer};
-    const LwOpt opt{inflglw, cldfr, taucld};
+    const LwOpt opt{inflglw, cldfr, taucld, iceflglw, liqflglw, cicewp, cliqwp, reice, reliq};
     if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;       // also normalises *icld
-    if (icld && *icld >= 1) { in.icld = *icld; in.cldfr = cldfr; in.taucld = taucld; }
+    lw_set_optional(in, icld, opt);
     LwOut out{ncol, uflx, dflx, hr, uflxc, dflxc, hrc};
     if (idrv == 1) { out.duflx_dt = duflx_dt; out.duflxc_dt = duflxc_dt; }
     return lw_device_impl(ncol, nlay, icld, idrv, in, out, (cudaStream_t)stream, nullptr, opt);
@@ -1140,8 +1196,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                   double *uflx, double *dflx, double *hr, double *uflxc, double *dflxc, double *hrc,
                   double *duflx_dt, double *duflxc_dt)
 {
-    (void)iceflglw; (void)liqflglw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
-    const LwOpt opt{inflglw, cldfr, taucld};
+    const LwOpt opt{inflglw, cldfr, taucld, iceflglw, liqflglw, cicewp, cliqwp, reice, reliq};
     // uflxc, dflxc, hrc (and duflxc_dt) may be NULL: the clear-sky result is then not copied back (MiMA never reads it)
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !uflx || !dflx || !hr)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: required array is NULL");
@@ -1149,14 +1204,15 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
     if (idrv == 1 && !duflx_dt) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt");
     if (ncol == 0) return RRTMG_B200_OK;
     const bool cloud = icld && *icld >= 1;
+    if (const int rc = lw_err_begin(cloud)) return rc;
     if (P_lw.ready()) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
-    const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L + (cloud ? 17 * L : 0)) * 8 + 32 * 256;
+    const size_t in_bytes = (size_t)hc * (13 * L + 2 * V + 1 + 16 + 16 * L + (cloud ? 21 * L : 0)) * 8 + 40 * 256;
     const size_t out_bytes = (size_t)hc * (6 * V + 2 * L) * 8 + 10 * 256;
     LwWork wsz;
-    const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields);
+    const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields, cloud);
     const int nslot = hc < ncol ? 2 : 1;
     for (int i = 0; i < nslot; ++i)
         if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes))
@@ -1170,7 +1226,12 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
         LwIn in{nc, a.up(play, L), a.up(plev, V), a.up(tlay, L), a.up(tlev, V), a.up(tsfc, 1),
                 a.up(h2ovmr, L), a.up(o3vmr, L), a.up(co2vmr, L), a.up(ch4vmr, L), a.up(n2ovmr, L), a.up(o2vmr, L),
                 a.up(cfc11vmr, L), a.up(cfc12vmr, L), a.up(cfc22vmr, L), a.up(ccl4vmr, L), a.up(emis, 16), a.up(tauaer, 16 * L)};
-        if (cloud) { in.icld = *icld; in.cldfr = a.up(cldfr, L); in.taucld = a.up_banded(taucld, 16, L); }
+        if (cloud) {
+            LwOpt dopt{inflglw, a.up(cldfr, L), a.up_banded(taucld, 16, L), iceflglw, liqflglw,
+                       inflglw >= 1 ? a.up(cicewp, L) : nullptr, inflglw >= 1 ? a.up(cliqwp, L) : nullptr,
+                       inflglw == 2 ? a.up(reice, L) : nullptr, inflglw == 2 ? a.up(reliq, L) : nullptr};
+            lw_set_optional(in, icld, dopt);
+        }
         if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
         Slot o{(char *)P_lw.out[slot].p, 0, c0, nc, ncol, st, true};
         LwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
@@ -1182,7 +1243,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
         if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)");
     }
     for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_lw.st[i]));
-    return RRTMG_B200_OK;
+    return lw_err_end(cloud);
 }
 
 int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,

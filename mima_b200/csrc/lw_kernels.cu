@@ -17,6 +17,9 @@ namespace rrtmg {
 __constant__ LwConst c_lw;
 __constant__ unsigned char c_lw_ngb[NGPTLW];   // band (0-based) of each g-point
 
+__device__ LwCldConst d_lwcld;          // 19 KB: global memory, read through the read-only path
+int lw_upload_cld(const LwCldConst &c) { return cudaMemcpyToSymbol(d_lwcld, &c, sizeof c) == cudaSuccess ? 0 : -1; }
+
 int lw_upload_const(const LwConst &c)
 {
     unsigned char ngb[NGPTLW];
@@ -793,6 +796,115 @@ __global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTab
 #undef LW_BAND
 }
 
+// =====================================================================================================
+// cldprop (rrtmg_lw_cldprop.f90:31-276), thread <-> column: the routine carries state from layer to layer (ncbands, the
+// abscoice / abscoliq vectors), so the layers of a column are walked in order.  inflag = 0: optical depth as given;
+// 1: abscld1 * water path; 2: ice (iceflag 0-3) and liquid (liqflag 0-1) parameterisations in the effective radii.
+// Out: taucloud [col][lay][16] (zero where the layer is not cloudy), ncbands per column (selects ipat in rtrn/rtrnmr),
+// and the number of the Fortran `stop` a column ran into (w.err, atomicMax): 1 ICE RADIUS TOO SMALL, 2 ICE RADIUS OUT
+// OF BOUNDS, 3 ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS, 4 LIQUID EFFECTIVE RADIUS OUT OF BOUNDS.
+// =====================================================================================================
+__global__ void __launch_bounds__(64) lw_cldprop_kernel(LwIn in, LwWork w)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= w.nc) return;
+    const int nlay = w.nlay;
+    const size_t ld = (size_t)in.ld;
+    const double cldmin = 1.e-20;
+    const LwCldConst &K = d_lwcld;
+    double abscoice[17], abscoliq[17];
+    for (int ib = 0; ib <= 16; ++ib) { abscoice[ib] = 0.; abscoliq[ib] = 0.; }
+    int ncbands = 1, iceind = 0, liqind = 0, stop = 0;
+    auto icb = [](int ib, int ind) {           // :147-149, ib 1-based
+        if (ind == 0) return 1;
+        if (ind == 2) return ib;
+        return ib <= 2 ? ib : (ib <= 5 ? 3 : (ib <= 8 ? 4 : 5));
+    };
+    for (int lay = 0; lay < nlay && !stop; ++lay) {
+        const size_t o = col + (size_t)lay * ld;
+        double *tc = w.taucloud + ((size_t)col * nlay + lay) * 16;
+        double tauctot = 0.;
+        for (int ib = 0; ib < 16; ++ib) {
+            tc[ib] = 0.0;
+            tauctot = tauctot + in.taucld[ib + 16 * o];
+        }
+        const double ciwp = in.cicewp ? in.cicewp[o] : 0., clwp = in.cliqwp ? in.cliqwp[o] : 0.;
+        const double cwp = ciwp + clwp;
+        if (!(in.cldfr[o] >= cldmin && (cwp >= cldmin || tauctot >= cldmin))) continue;
+        if (in.inflg == 0) {
+            ncbands = 16;
+            for (int ib = 0; ib < 16; ++ib) tc[ib] = in.taucld[ib + 16 * o];
+        } else if (in.inflg == 1) {
+            ncbands = 16;
+            for (int ib = 0; ib < 16; ++ib) tc[ib] = K.abscld1 * cwp;
+        } else {
+            const double radice = in.reice ? in.reice[o] : 0.;
+            if (ciwp == 0.0) {
+                abscoice[1] = 0.0;
+                iceind = 0;
+            } else if (in.iceflg == 0) {
+                if (radice < 10.0) { stop = 1; break; }
+                abscoice[1] = K.absice0[0] + K.absice0[1] / radice;
+                iceind = 0;
+            } else if (in.iceflg == 1) {
+                if (radice < 13.0 || radice > 130.) { stop = 2; break; }
+                ncbands = 5;
+                for (int ib = 1; ib <= 5; ++ib) abscoice[ib] = K.absice1[0 + 2 * (ib - 1)] + K.absice1[1 + 2 * (ib - 1)] / radice;
+                iceind = 1;
+            } else if (in.iceflg == 2) {
+                if (radice < 5.0 || radice > 131.0) { stop = 2; break; }
+                ncbands = 16;
+                const double factor = (radice - 2.) / 3.;
+                int index = (int)factor;
+                if (index == 43) index = 42;
+                const double fint = factor - (double)index;
+                for (int ib = 1; ib <= 16; ++ib) {
+                    const double a0 = K.absice2[(index - 1) + 43 * (ib - 1)], a1 = K.absice2[index + 43 * (ib - 1)];
+                    abscoice[ib] = a0 + fint * (a1 - (a0));
+                }
+                iceind = 2;
+            } else if (in.iceflg == 3) {
+                if (radice < 5.0 || radice > 140.0) { stop = 3; break; }
+                ncbands = 16;
+                const double factor = (radice - 2.) / 3.;
+                int index = (int)factor;
+                if (index == 46) index = 45;
+                const double fint = factor - (double)index;
+                for (int ib = 1; ib <= 16; ++ib) {
+                    const double a0 = K.absice3[(index - 1) + 46 * (ib - 1)], a1 = K.absice3[index + 46 * (ib - 1)];
+                    abscoice[ib] = a0 + fint * (a1 - (a0));
+                }
+                iceind = 2;
+            }
+            if (clwp == 0.0) {
+                abscoliq[1] = 0.0;
+                liqind = 0;
+                if (iceind == 1) iceind = 2;
+            } else if (in.liqflg == 0) {
+                abscoliq[1] = K.absliq0;
+                liqind = 0;
+                if (iceind == 1) iceind = 2;
+            } else if (in.liqflg == 1) {
+                const double radliq = in.reliq ? in.reliq[o] : 0.;
+                if (radliq < 2.5 || radliq > 60.) { stop = 4; break; }
+                int index = (int)(radliq - 1.5);
+                if (index == 0) index = 1;
+                if (index == 58) index = 57;
+                const double fint = radliq - 1.5 - (double)index;
+                ncbands = 16;
+                for (int ib = 1; ib <= 16; ++ib) {
+                    const double a0 = K.absliq1[(index - 1) + 58 * (ib - 1)], a1 = K.absliq1[index + 58 * (ib - 1)];
+                    abscoliq[ib] = a0 + fint * (a1 - (a0));
+                }
+                liqind = 2;
+            }
+            for (int ib = 1; ib <= ncbands; ++ib) tc[ib - 1] = ciwp * abscoice[icb(ib, iceind)] + clwp * abscoliq[icb(ib, liqind)];
+        }
+    }
+    w.ncbands[col] = ncbands;
+    if (stop) atomicMax(w.err, stop);
+}
+
 int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, double *cap)
 {
     ktimer_begin(K_LW_PREP, s);
@@ -812,10 +924,12 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
         cudaMemcpyAsync(cap, w.taug, n * 8, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(cap + n, w.fracs, n * 8, cudaMemcpyDeviceToDevice, s);
     }
+    int ncld = 0;
+    if (in.icld >= 1) { lw_cldprop_kernel<<<(w.nc + 63) / 64, 64, 0, s>>>(in, w); ncld = 1; }
     ktimer_begin(K_LW_RTRN, s);
     const int nrt = lw_launch_rtrn(t, in, out, w, s);
     ktimer_end(s);
-    return 3 + nrt;
+    return 3 + nrt + ncld;
 }
 
 } // namespace rrtmg

@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_cloud_kernel(LwTables T, L
     __shared__ double s_flux[6][MAXLAY + 1];                 // down, down clear, up, up clear, d up/dT, d up clear/dT
     __shared__ double s_cf[MAXLAY + 2];                      // cldfrac(0:nlayers+1), zero at both ends
     __shared__ double s_fac[MR ? CF_COUNT : 1][MAXLAY + 2];
-    __shared__ unsigned char s_cld[MAXLAY + 2], s_opt[MAXLAY + 2], s_st[MAXLAY + 2], s_std[MAXLAY + 2];
+    __shared__ unsigned char s_cld[MAXLAY + 2], s_st[MAXLAY + 2], s_std[MAXLAY + 2];
     const int col = blockIdx.x;
     const int nlay = w.nlay;
     const int g = threadIdx.x;
@@ -762,14 +762,10 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_cloud_kernel(LwTables T, L
     const size_t ld = (size_t)in.ld;
     // cloud fraction, cloudy-layer flag (:316-324) and cldprop's test for a layer with cloud optical depth (cldprop.f90:158-168)
     for (int i = threadIdx.x; i <= nlay + 1; i += RT_THREADS) {
-        double cf = 0.0, tauctot = 0.0;
-        if (i >= 1 && i <= nlay) {
-            cf = in.cldfr[col + (size_t)(i - 1) * ld];
-            for (int ib = 0; ib < 16; ++ib) tauctot = tauctot + in.taucld[ib + 16 * (col + (size_t)(i - 1) * ld)];
-        }
+        double cf = 0.0;
+        if (i >= 1 && i <= nlay) cf = in.cldfr[col + (size_t)(i - 1) * ld];
         s_cf[i] = cf;
         s_cld[i] = cf >= 1.e-6;
-        s_opt[i] = cf >= 1.e-20 && tauctot >= 1.e-20;
         s_st[i] = 0; s_std[i] = 0;
         if (MR)
             for (int q = 0; q < CF_COUNT; ++q) s_fac[q][i] = 0.0;
@@ -787,14 +783,18 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_cloud_kernel(LwTables T, L
     const double *__restrict__ pl = w.planklay + (size_t)col * nlay * 16 + band;
     const double *__restrict__ pv = w.planklev + (size_t)col * (nlay + 1) * 16 + band;
     const double *taer = in.tauaer ? in.tauaer + col + (size_t)band * nlay * ld : nullptr;
-    const double *tcld = in.taucld + band + 16 * (size_t)col;
+    // cloud band of this g-point's spectral band (ipat, rtrnmr.f90:243-245) for the ncbands cldprop left behind
+    const int ncb = w.ncbands[col];
+    const int ibc = ncb == 16 ? band : (ncb == 5 ? (band <= 1 ? band : (band <= 4 ? 2 : (band <= 7 ? 3 : 4))) : 0);
+    const double *tcld = w.taucloud + (size_t)col * nlay * 16 + ibc;
+    const double secdc = w.secdiff[(size_t)col * 16 + ibc];          // odcld(lay, ib) = secdiff(ib) * taucloud(lay, ib), ib the CLOUD band
 
     auto cell = [&](int lay, LwCloudCell &c) {          // lay 0-based; Fortran lev = lay + 1
         double taut = taug[(size_t)lay * NGPTLW];
         if (taer) taut = taut + taer[(size_t)lay * ld];
         const double blay = __ldg(pl + lay * 16);
         const bool cloudy = s_cld[lay + 1];
-        const double odcld = cloudy && s_opt[lay + 1] ? secd * tcld[16 * (size_t)lay * ld] : 0.0;
+        const double odcld = cloudy ? secdc * tcld[16 * (size_t)lay] : 0.0;
         lw_cloud_cell(et, bpade, secd, taut, fracs[(size_t)lay * NGPTLW], blay, __ldg(pv + (lay + 1) * 16) - blay,
                       __ldg(pv + lay * 16) - blay, cloudy, odcld, c);
         return odcld;

@@ -88,7 +88,17 @@ struct LwIn {                 // interface arrays of the current pass (device po
     int icld = 0;
     const double *cldfr = nullptr;    // (ld, nlay)
     const double *taucld = nullptr;   // (16, ld, nlay)
+    // cloud optics from water paths (cldprop, inflglw = 1, 2): g/m2 and microns, (ld, nlay)
+    int inflg = 0, iceflg = 0, liqflg = 0;
+    const double *cicewp = nullptr, *cliqwp = nullptr, *reice = nullptr, *reliq = nullptr;
 };
+
+// cloud absorption coefficients of cldprop's parameterisations (lwcldpr, rrtmg_lw_init.f90:2018-2656), Fortran order
+struct LwCldConst {
+    double abscld1, absliq0, absice0[2], absice1[2 * 5], absice2[43 * 16], absice3[46 * 16], absliq1[58 * 16];
+    int have;
+};
+int lw_upload_cld(const LwCldConst &c);
 
 struct LwOut {
     int ld;
@@ -97,6 +107,11 @@ struct LwOut {
 };
 
 struct LwWork {
+    // cloudy sky (null otherwise): band optical depths out of cldprop [col][lay][16], ncbands (1, 5, 16) per column,
+    // and the number of the Fortran `stop` some column ran into (0 = none)
+    double *taucloud = nullptr;
+    int *ncbands = nullptr;
+    int *err = nullptr;
     int nc, nlay;
     int idrv;                 // 1: also dF_up/dT_surface (rad.nomcica:143-152)
     double *dplankbnd;        // [col][16]: semiss * d(Planck)/dT at the surface temperature (idrv = 1)

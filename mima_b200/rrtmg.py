@@ -27,7 +27,7 @@ DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 _dp = C.POINTER(C.c_double)
 _ERR = {1: "not initialised", 2: "unsupported option", 3: "PARTIAL CLOUD NOT ALLOWED", 4: "bad argument",
-        5: "CUDA error", 6: "coefficient tables"}
+        5: "CUDA error", 6: "coefficient tables", 7: "cloud input out of range (a Fortran stop of cldprop)"}
 
 
 class RRTMGError(RuntimeError):
@@ -168,8 +168,9 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
     idrv = 1 also (duflx_dt, duflxc_dt), the change of the upward flux per K of surface temperature (W/m2/K,
     rad.nomcica:143-152, the Fortran's optional dummies).  ch4vmr..ccl4vmr, emis, tauaer may be None (zeros /
     emissivity 1).  icld >= 1 takes the cloud fraction cldfr (ncol,nlay) and the band optical depths taucld
-    (16,ncol,nlay) (inflglw = 0): icld = 1 random overlap, 2/3 maximum/random overlap; water-path inputs
-    (inflglw > 0) raise RRTMGError(2).  clear_sky=False does not fetch uflxc, dflxc, hrc (duflxc_dt): they come back as
+    (16,ncol,nlay) (inflglw = 0): icld = 1 random overlap, 2/3 maximum/random overlap; inflglw = 1, 2 take the ice / liquid
+    water paths cicewp, cliqwp (g/m2) and, for 2, the effective radii reice, reliq (microns) with iceflglw 0..3 and
+    liqflglw 0..1 (cldprop's parameterisations; a radius outside the parameterisation's range raises RRTMGError(7)).  clear_sky=False does not fetch uflxc, dflxc, hrc (duflxc_dt): they come back as
     None (MiMA never reads them; the C ABI takes NULL for them)."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
@@ -186,6 +187,8 @@ def rrtmg_lw(ncol, nlay, icld, idrv,
         keep.append(arr)
         ptrs.append(p)
     taer, ptaer = _in(tauaer, (ncol, nlay, NBNDLW), "tauaer", True)
+    if int(icld) != 0 and taucld is None and cldfr is not None:
+        taucld = np.zeros((NBNDLW, ncol, nlay), order="F")        # the Fortran dummy always exists
     cloudp = []
     for a, shp, nm in ((cldfr, L, "cldfr"), (taucld, (NBNDLW, ncol, nlay), "taucld"), (cicewp, L, "cicewp"),
                        (cliqwp, L, "cliqwp"), (reice, L, "reice"), (reliq, L, "reliq")):
@@ -266,10 +269,10 @@ def _opt(a):
     return None if (a is None or not np.any(a)) else a
 
 
-def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0, clear_sky=True):
+def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0, clear_sky=True, iceflglw=0, liqflglw=0):
     return rrtmg_lw(c.ncol, c.nlay, icld, idrv, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), _opt(c.cfc11), _opt(c.cfc12), _opt(c.cfc22), _opt(c.ccl4),
-                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, clear_sky=clear_sky, **(clouds or {}))
+                    None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, iceflglw=iceflglw, liqflglw=liqflglw, clear_sky=clear_sky, **(clouds or {}))
 
 
 def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0, clear_sky=True):

@@ -125,15 +125,18 @@ contains
     real(c_double), contiguous, target, intent(inout) :: uflx(:,:), dflx(:,:), hr(:,:), uflxc(:,:), dflxc(:,:), hrc(:,:)
     real(c_double), contiguous, target, intent(out), optional :: duflx_dt(:,:), duflxc_dt(:,:)
     integer(c_int) :: icld_c
-    type(c_ptr) :: pemis, paer, pcldfr, ptaucld, pdu, pduc
+    type(c_ptr) :: pemis, paer, pcldfr, ptaucld, pdu, pduc, pwp(4)
     icld_c = icld
     pemis = c_null_ptr; if (any(emis /= 1._c_double)) pemis = c_loc(emis)
     paer = c_null_ptr;  if (any(tauaer /= 0._c_double)) paer = c_loc(tauaer)
     ! cloud arrays are never dereferenced for icld = 0 (as in the reference); pass NULL.  With icld > 0 the library
     ! takes the cloud fraction and the band optical depths (inflglw = 0); water-path inputs return error 2.
-    pcldfr = c_null_ptr; ptaucld = c_null_ptr
+    pcldfr = c_null_ptr; ptaucld = c_null_ptr; pwp = c_null_ptr
     if (icld /= 0) then
        pcldfr = c_loc(cldfr); ptaucld = c_loc(taucld)
+       if (inflglw >= 1) then
+          pwp(1) = c_loc(cicewp); pwp(2) = c_loc(cliqwp); pwp(3) = c_loc(reice); pwp(4) = c_loc(reliq)
+       endif
     endif
     pdu = c_null_ptr; pduc = c_null_ptr
     if (idrv == 1 .and. present(duflx_dt) .and. present(duflxc_dt)) then
@@ -142,7 +145,7 @@ contains
     call b200_check(rrtmg_b200_lw(ncol, nlay, icld_c, idrv, c_loc(play), c_loc(plev), c_loc(tlay), c_loc(tlev), &
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          opt2(cfc11vmr), opt2(cfc12vmr), opt2(cfc22vmr), opt2(ccl4vmr), pemis, inflglw, iceflglw, liqflglw, &
-         pcldfr, ptaucld, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr, paer, &
+         pcldfr, ptaucld, pwp(1), pwp(2), pwp(3), pwp(4), paer, &
          c_loc(uflx), c_loc(dflx), c_loc(hr), optout(uflxc), optout(dflxc), optout(hrc), pdu, pduc), 'rrtmg_lw')
     icld = icld_c
   end subroutine

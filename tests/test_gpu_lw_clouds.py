@@ -88,8 +88,48 @@ def test_argument_errors(gpu, cols):
         gpu.lw_from_columns(c, icld=2)                       # no cloud arrays
     assert e.value.code == 4
     with pytest.raises(gpu.RRTMGError) as e:
-        gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=2)  # water-path cloud optics: not built
-    assert e.value.code == 2
+        gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=2)  # water-path cloud optics without the water paths
+    assert e.value.code == 4
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=3)
+    assert e.value.code == 4
+
+
+def _water_clouds(c, rng):
+    shp = (c.ncol, c.nlay)
+    cf = np.asfortranarray((rng.uniform(size=shp) < 0.3) * rng.uniform(0.1, 1.0, shp))
+    return dict(cldfr=cf,
+                cicewp=np.asfortranarray(rng.uniform(0, 30, shp) * (rng.uniform(size=shp) < 0.7)),
+                cliqwp=np.asfortranarray(rng.uniform(0, 60, shp) * (rng.uniform(size=shp) < 0.7)),
+                reice=np.asfortranarray(rng.uniform(14, 120, shp)), reliq=np.asfortranarray(rng.uniform(3, 50, shp)))
+
+
+@pytest.mark.parametrize("flags", [(1, 0, 0), (2, 0, 0), (2, 1, 0), (2, 1, 1), (2, 2, 1), (2, 3, 1), (2, 2, 0)])
+def test_cloud_optics_from_water_paths(gpu, oracle, cols, flags):
+    """cldprop's parameterisations (cldprop.f90:176-270): inflglw = 1 (one absorption coefficient), 2 with the four ice
+    and two liquid options; ncbands = 1, 5 or 16 decides which cloud band a spectral band reads (ipat)."""
+    infl, ice, liq = flags
+    cl = _water_clouds(cols, np.random.default_rng(40 + 10 * ice + liq))
+    for icld in (1, 2):
+        got = gpu.lw_from_columns(cols, icld=icld, clouds=cl, inflglw=infl, iceflglw=ice, liqflglw=liq, idrv=1)
+        ref = oracle.rrtmg_lw(cols, icld=icld, clouds=cl, inflglw=infl, iceflglw=ice, liqflglw=liq, idrv=1)
+        _check_outputs(got, ref, LW_OUT + ("duflx_dt", "duflxc_dt"))
+
+
+def test_radius_out_of_range_is_an_error(gpu, cols):
+    c = cols.take(np.arange(40))
+    cl = _water_clouds(c, np.random.default_rng(2))
+    cl["cldfr"][3, 5] = 0.5; cl["cicewp"][3, 5] = 10.0; cl["reice"][3, 5] = 4.0
+    for ice, code in ((0, 7), (1, 7), (2, 7), (3, 7)):
+        with pytest.raises(gpu.RRTMGError) as e:
+            gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=2, iceflglw=ice, liqflglw=1)
+        assert e.value.code == code
+    cl["reice"][3, 5] = 50.0
+    cl["cliqwp"][3, 5] = 5.0; cl["reliq"][3, 5] = 70.0
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.lw_from_columns(c, icld=2, clouds=cl, inflglw=2, iceflglw=2, liqflglw=1)
+    assert e.value.code == 7 and "LIQUID" in str(e.value)
+    gpu.lw_from_columns(c)          # the library stays usable
 
 
 def test_eighty_layers(gpu, oracle):

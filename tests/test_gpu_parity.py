@@ -186,8 +186,8 @@ def test_unsupported_options_fail_loudly(gpu):
         gpu.rrtmg_lw(c.ncol, c.nlay, 1, 0, *args, None, None, None, None, None)
     assert e.value.code == 4                      # icld > 0 without the cloud arrays
     with pytest.raises(gpu.RRTMGError) as e:
-        gpu.rrtmg_lw(c.ncol, c.nlay, 1, 0, *args, None, None, None, None, None, inflglw=2)
-    assert e.value.code == 2                      # cloud optics from water paths: not built
+        gpu.rrtmg_lw(c.ncol, c.nlay, 1, 0, *args, None, None, None, None, None, inflglw=2, cldfr=c.tlay * 0)
+    assert e.value.code == 4                      # inflglw = 2 without the water paths / radii
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_lw(c.ncol, c.nlay, 0, 2, *args, None, None, None, None, None)      # idrv must be 0 or 1
     assert e.value.code == 4

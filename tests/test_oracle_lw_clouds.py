@@ -102,3 +102,35 @@ def test_switch_handling(oracle, cols):
         assert np.array_equal(a[k], b[k]) and np.array_equal(d[k], b[k])
     with pytest.raises(RuntimeError, match="rc=3"):
         oracle.rrtmg_lw(c, icld=2)
+
+
+def test_cldprop_parameterisations(oracle, cols):
+    """inflglw = 1 is inflglw = 0 fed with abscld1 * (ice + liquid water path) in every band (cldprop.f90:176-180); an
+    iceflglw = 0, liqflglw = 0 cloud is grey as well (one coefficient for all bands, icb(:,0) = 1); the Fortran stops come
+    back as return codes."""
+    rng = np.random.default_rng(5)
+    shp = (cols.ncol, cols.nlay)
+    cf = np.asfortranarray((rng.uniform(size=shp) < 0.3) * rng.uniform(0.1, 1.0, shp))
+    iwp = np.asfortranarray(rng.uniform(0, 30, shp))
+    lwp = np.asfortranarray(rng.uniform(0, 60, shp))
+    cl = dict(cldfr=cf, cicewp=iwp, cliqwp=lwp, reice=np.full(shp, 40.0, order="F"), reliq=np.full(shp, 10.0, order="F"))
+    a = oracle.rrtmg_lw(cols, icld=2, clouds=cl, inflglw=1)
+    tau = np.asfortranarray(np.broadcast_to((0.0602410 * (iwp + lwp))[None], (16,) + shp))
+    b = oracle.rrtmg_lw(cols, icld=2, clouds=dict(cldfr=cf, taucld=tau))
+    for k in LW:
+        assert np.array_equal(a[k], b[k]), k
+    g = oracle.rrtmg_lw(cols, icld=2, clouds=cl, inflglw=2, iceflglw=0, liqflglw=0)
+    tau = np.asfortranarray(np.broadcast_to((iwp * (0.005 + 1.0 / 40.0) + lwp * 0.0903614)[None], (16,) + shp))
+    h = oracle.rrtmg_lw(cols, icld=2, clouds=dict(cldfr=cf, taucld=tau))
+    for k in ("uflx", "dflx"):
+        # same optical depths, but ncbands = 1: every band reads secdiff(1) * taucloud(:,1) instead of its own secant
+        assert np.max(np.abs(g[k] - h[k])) < 3.0 and np.max(np.abs(g[k] - h[k])) > 0.0, k
+    cl["cldfr"][2, 3] = 0.5; cl["cldfr"][1, 1] = 0.5            # make sure the two cells below are cloudy
+    cl["reice"][2, 3] = 4.0
+    for ice, rc in ((0, 11), (1, 12), (2, 12), (3, 13)):
+        with pytest.raises(RuntimeError, match=f"rc={rc}"):
+            oracle.rrtmg_lw(cols, icld=2, clouds=cl, inflglw=2, iceflglw=ice, liqflglw=1)
+    cl["reice"][2, 3] = 40.0
+    cl["reliq"][1, 1] = 61.0
+    with pytest.raises(RuntimeError, match="rc=14"):
+        oracle.rrtmg_lw(cols, icld=2, clouds=cl, inflglw=2, iceflglw=2, liqflglw=1)
