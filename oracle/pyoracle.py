@@ -126,7 +126,7 @@ class Oracle:
 
     # ------------------------------------------------------------------ SW
     def rrtmg_sw(self, cols, *, stages: bool = False, nthreads: int | None = None, icld: int = 0, iaer: int = 0,
-                 clouds=None, aerosols=None):
+                 clouds=None, aerosols=None, inflgsw: int = 0, iceflgsw: int = 0, liqflgsw: int = 0):
         """clouds = dict(cldfr (ncol,nlay), taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)) for icld >= 1 (inflgsw = 0);
         aerosols = dict(tauaer/ssaaer/asmaer (ncol,nlay,14)) for iaer = 10, dict(ecaer (ncol,nlay,6)) for iaer = 6."""
         ncol, nlay = cols.ncol, cols.nlay
@@ -150,12 +150,17 @@ class Oracle:
                                cols.ch4, cols.n2o, cols.o2, cols.albedo, cols.albedo, cols.albedo, cols.albedo,
                                cols.coszen)]
         extra = []
+        if clouds is not None and "taucld" not in clouds:      # water-path input: the optical-property dummies still exist
+            z = np.zeros((14, ncol, nlay), order="F")
+            clouds = dict(clouds, taucld=z, ssacld=z, asmcld=z, fsfcld=z)
         for src, keys in ((clouds, ("cldfr", "taucld", "ssacld", "asmcld", "fsfcld")), (aerosols, ("tauaer", "ssaaer", "asmaer", "ecaer"))):
             for k in keys:
                 extra.append(_f(src[k]) if src is not None and k in src else None)
+        wp = [_f(clouds[k]) if clouds is not None and k in clouds else None for k in ("cicewp", "cliqwp", "reice", "reliq")]
         rc = self.lib.orc_rrtmg_sw(C.c_int(ncol), C.c_int(nlay), C.c_int(int(icld)), C.c_int(int(iaer)), *[_p(a) for a in ins],
                                    C.c_double(cols.adjes), C.c_int(cols.dyofyr), C.c_double(cols.scon),
-                                   C.c_int(0), *[None if a is None else _p(a) for a in extra],
+                                   C.c_int(int(inflgsw)), *[None if a is None else _p(a) for a in extra],
+                                   C.c_int(int(iceflgsw)), C.c_int(int(liqflgsw)), *[None if a is None else _p(a) for a in wp],
                                    _p(out["swuflx"]), _p(out["swdflx"]), _p(out["swhr"]), _p(out["swuflxc"]),
                                    _p(out["swdflxc"]), _p(out["swhrc"]), stp, C.c_int(nthreads))
         if rc:

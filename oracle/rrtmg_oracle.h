@@ -90,6 +90,10 @@ typedef struct {
     double sw_exp_tbl[ORC_NTBL + 1];
     double sw_bpade;
     double rsrtaua[14][6], rsrpiza[14][6], rsrasya[14][6];   /* ECMWF aerosol types (iaer = 6), rrtmg_sw_init.f90:370-470 */
+    /* SW cloud optical properties (swcldpr, rrtmg_sw_init.f90:1519-3341): [radius index 1-based][band 1..14] */
+    double extliq1[59][15], ssaliq1[59][15], asyliq1[59][15], extice2[44][15], ssaice2[44][15], asyice2[44][15];
+    double extice3[47][15], ssaice3[47][15], asyice3[47][15], fdlice3[47][15];
+    double abari[6], bbari[6], cbari[6], dbari[6], ebari[6], fbari[6];
     /* LW cloud absorption coefficients (lwcldpr, rrtmg_lw_init.f90:2018-2656), Fortran 1-based indices kept */
     double abscld1, absliq0, absice0[3], absice1[3][6], absice2[44][17], absice3[47][17], absliq1[59][17];
     orc_sw_kg_t sw[ORC_NBNDSW];
@@ -153,6 +157,7 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
                  const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
                  const double *ecaer,
+                 int iceflgsw, int liqflgsw, const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *stages, int nthreads);
 

@@ -904,6 +904,112 @@ static void spcvrt_sw(swcol_t *c, const double *palbd, const double *palbp, doub
     (void)idelm; (void)icpr;
 }
 
+/* ---------------------------------------------------------------- cldprop_sw, inflag = 2 (rrtmg_sw_cldprop.f90:168-345)
+   one layer; ptauc/pomgc/pasyc[1..14] out.  Returns 0 or the number of the Fortran `stop`: 1 ICE RADIUS OUT OF BOUNDS,
+   2 ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS, 3 LIQUID EFFECTIVE RADIUS OUT OF BOUNDS, 4 one of the range checks on
+   the interpolated properties (extinction < 0, single-scattering albedo or asymmetry outside [0, 1], fdelta). */
+static int cldprop_sw_layer(int iceflag, int liqflag, double ciwp, double clwp, double radice, double radliq,
+                            double *ptauc, double *pomgc, double *pasyc)
+{
+    const orc_state_t *S = &g_orc;
+    const double eps = 1.e-06, cldmin = 1.e-20;
+    static const double wavenum2[15] = {0., 3250., 4000., 4650., 5150., 6150., 7700., 8050., 12850., 16000., 22650., 29000.,
+                                        38000., 50000., 2600.};
+    double extcoice[15], gice[15], ssacoice[15], forwice[15], extcoliq[15], gliq[15], ssacoliq[15], forwliq[15], fdelta[15];
+    double factor, fint;
+    int index, icx = 0;
+    for (int ib = 1; ib <= 14; ++ib) {
+        extcoice[ib] = 0.; ssacoice[ib] = 0.; gice[ib] = 0.; forwice[ib] = 0.;
+        extcoliq[ib] = 0.; ssacoliq[ib] = 0.; gliq[ib] = 0.; forwliq[ib] = 0.;
+    }
+    if (ciwp == 0.0) {
+        /* zeros */
+    } else if (iceflag == 1) {
+        if (radice < 13.0 || radice > 130.) return 1;
+        for (int ib = 1; ib <= 14; ++ib) {
+            if (wavenum2[ib] > 1.43e04) icx = 1;
+            else if (wavenum2[ib] > 7.7e03) icx = 2;
+            else if (wavenum2[ib] > 5.3e03) icx = 3;
+            else if (wavenum2[ib] > 4.0e03) icx = 4;
+            else if (wavenum2[ib] >= 2.5e03) icx = 5;
+            extcoice[ib] = S->abari[icx] + S->bbari[icx] / radice;
+            ssacoice[ib] = 1. - S->cbari[icx] - S->dbari[icx] * radice;
+            gice[ib] = S->ebari[icx] + S->fbari[icx] * radice;
+            if (gice[ib] >= 1.0) gice[ib] = 1.0 - eps;
+            forwice[ib] = gice[ib] * gice[ib];
+            if (extcoice[ib] < 0.0 || ssacoice[ib] > 1.0 || ssacoice[ib] < 0.0 || gice[ib] > 1.0 || gice[ib] < 0.0) return 4;
+        }
+    } else if (iceflag == 2) {
+        if (radice < 5.0 || radice > 131.0) return 1;
+        factor = (radice - 2.) / 3.;
+        index = (int)factor;
+        if (index == 43) index = 42;
+        fint = factor - (double)index;
+        for (int ib = 1; ib <= 14; ++ib) {
+            extcoice[ib] = S->extice2[index][ib] + fint * (S->extice2[index + 1][ib] - S->extice2[index][ib]);
+            ssacoice[ib] = S->ssaice2[index][ib] + fint * (S->ssaice2[index + 1][ib] - S->ssaice2[index][ib]);
+            gice[ib] = S->asyice2[index][ib] + fint * (S->asyice2[index + 1][ib] - S->asyice2[index][ib]);
+            forwice[ib] = gice[ib] * gice[ib];
+            if (extcoice[ib] < 0.0 || ssacoice[ib] > 1.0 || ssacoice[ib] < 0.0 || gice[ib] > 1.0 || gice[ib] < 0.0) return 4;
+        }
+    } else if (iceflag == 3) {
+        if (radice < 5.0 || radice > 140.0) return 2;
+        factor = (radice - 2.) / 3.;
+        index = (int)factor;
+        if (index == 46) index = 45;
+        fint = factor - (double)index;
+        for (int ib = 1; ib <= 14; ++ib) {
+            extcoice[ib] = S->extice3[index][ib] + fint * (S->extice3[index + 1][ib] - S->extice3[index][ib]);
+            ssacoice[ib] = S->ssaice3[index][ib] + fint * (S->ssaice3[index + 1][ib] - S->ssaice3[index][ib]);
+            gice[ib] = S->asyice3[index][ib] + fint * (S->asyice3[index + 1][ib] - S->asyice3[index][ib]);
+            fdelta[ib] = S->fdlice3[index][ib] + fint * (S->fdlice3[index + 1][ib] - S->fdlice3[index][ib]);
+            if (fdelta[ib] < 0.0 || fdelta[ib] > 1.0) return 4;
+            forwice[ib] = fdelta[ib] + 0.5 / ssacoice[ib];
+            if (forwice[ib] > gice[ib]) forwice[ib] = gice[ib];
+            if (extcoice[ib] < 0.0 || ssacoice[ib] > 1.0 || ssacoice[ib] < 0.0 || gice[ib] > 1.0 || gice[ib] < 0.0) return 4;
+        }
+    }
+    if (clwp == 0.0) {
+        /* zeros */
+    } else if (liqflag == 1) {
+        if (radliq < 2.5 || radliq > 60.) return 3;
+        index = (int)(radliq - 1.5);
+        if (index == 0) index = 1;
+        if (index == 58) index = 57;
+        fint = radliq - 1.5 - (double)index;
+        for (int ib = 1; ib <= 14; ++ib) {
+            extcoliq[ib] = S->extliq1[index][ib] + fint * (S->extliq1[index + 1][ib] - S->extliq1[index][ib]);
+            ssacoliq[ib] = S->ssaliq1[index][ib] + fint * (S->ssaliq1[index + 1][ib] - S->ssaliq1[index][ib]);
+            if (fint < 0. && ssacoliq[ib] > 1.) ssacoliq[ib] = S->ssaliq1[index][ib];
+            gliq[ib] = S->asyliq1[index][ib] + fint * (S->asyliq1[index + 1][ib] - S->asyliq1[index][ib]);
+            forwliq[ib] = gliq[ib] * gliq[ib];
+            if (extcoliq[ib] < 0.0 || ssacoliq[ib] > 1.0 || ssacoliq[ib] < 0.0 || gliq[ib] > 1.0 || gliq[ib] < 0.0) return 4;
+        }
+    }
+    for (int ib = 1; ib <= 14; ++ib) {
+        const double tauliqorig = clwp * extcoliq[ib];
+        const double tauiceorig = ciwp * extcoice[ib];
+        const double ssaliq = ssacoliq[ib] * (1.0 - forwliq[ib]) / (1.0 - forwliq[ib] * ssacoliq[ib]);
+        const double tauliq = (1.0 - forwliq[ib] * ssacoliq[ib]) * tauliqorig;
+        const double ssaice = ssacoice[ib] * (1.0 - forwice[ib]) / (1.0 - forwice[ib] * ssacoice[ib]);
+        const double tauice = (1.0 - forwice[ib] * ssacoice[ib]) * tauiceorig;
+        const double scatliq = ssaliq * tauliq;
+        double scatice = ssaice * tauice;
+        double taucloud = tauliq + tauice;
+        if (taucloud == 0.0) taucloud = cldmin;
+        if (scatice == 0.0) scatice = cldmin;
+        ptauc[ib] = taucloud;
+        pomgc[ib] = (scatliq + scatice) / taucloud;
+        if (iceflag == 3)
+            pasyc[ib] = (1.0 / (scatliq + scatice)) *
+                        (scatliq * (gliq[ib] - forwliq[ib]) / (1.0 - forwliq[ib]) + scatice * ((gice[ib] - forwice[ib]) / (1.0 - forwice[ib])));
+        else
+            pasyc[ib] = (scatliq * (gliq[ib] - forwliq[ib]) / (1.0 - forwliq[ib]) + scatice * (gice[ib] - forwice[ib]) / (1.0 - forwice[ib])) /
+                        (scatliq + scatice);
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- rrtmg_sw (rad.nomcica:78-731) */
 int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  const double *play, const double *plev, const double *tlay, const double *tlev,
@@ -914,6 +1020,7 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                  int inflgsw, const double *cldfr, const double *taucld, const double *ssacld, const double *asmcld,
                  const double *fsfcld, const double *tauaer, const double *ssaaer, const double *asmaer,
                  const double *ecaer,
+                 int iceflgsw, int liqflgsw, const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                  double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                  double *swhrc, const orc_sw_stages_t *st, int nthreads)
 {
@@ -922,7 +1029,10 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
     if (icld < 0 || icld > 3) icld = 2;                              /* :468 */
     if (iaer != 0 && iaer != 6 && iaer != 10) iaer = 0;              /* :473 */
     if (iaer == 6 && !ecaer) return 3;                               /* ecaer (ncol,nlay,6) */
-    if (icld >= 1 && (inflgsw != 0 || !cldfr || !taucld || !ssacld || !asmcld || !fsfcld)) return 2; /* inflag 2: not restated */
+    if (icld >= 1 && inflgsw != 0 && inflgsw != 2) return 2;
+    if (icld >= 1 && (!cldfr || !taucld || !ssacld || !asmcld || !fsfcld)) return 3;
+    if (icld >= 1 && inflgsw == 2 && (!cicewp || !cliqwp || !reice || !reliq || iceflgsw < 1 || iceflgsw > 3 || liqflgsw != 1)) return 3;
+    int cld_stop = 0;
     if (iaer == 10 && (!tauaer || !ssaaer || !asmaer)) return 3;
     if (icld >= 1) /* without McICA: clear or overcast layers only (:534-539, `stop 'PARTIAL CLOUD NOT ALLOWED'`) */
         for (long i = 0; i < (long)ncol * nlay; ++i)
@@ -967,7 +1077,18 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
                     c->ptauc[lay][ib] = 0.0; c->pomgc[lay][ib] = 1.0; c->pasyc[lay][ib] = 0.0;
                     if (icld >= 1) tauctot = tauctot + taucld[(ib - 1) + 14 * (i0 + (long)(lay - 1) * ncol)];
                 }
-                if (icld >= 1 && c->pclfr[lay] >= 1.e-20 && tauctot >= 1.e-20) {   /* cwp = 0 for inflag = 0 inputs */
+                const long ol = (long)(lay - 1) * ncol + i0;
+                const double cwp = (icld >= 1 && inflgsw == 2) ? cicewp[ol] + cliqwp[ol] : 0.0;
+                if (icld >= 1 && inflgsw == 2 && c->pclfr[lay] >= 1.e-20 && (cwp >= 1.e-20 || tauctot >= 1.e-20)) {
+                    const int stop = cldprop_sw_layer(iceflgsw, liqflgsw, cicewp[ol], cliqwp[ol], reice[ol], reliq[ol],
+                                                      c->ptauc[lay], c->pomgc[lay], c->pasyc[lay]);
+                    if (stop) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+                        cld_stop = stop;
+                    }
+                } else if (icld >= 1 && inflgsw == 0 && c->pclfr[lay] >= 1.e-20 && tauctot >= 1.e-20) {   /* cwp = 0 for inflag = 0 inputs */
                     for (int ib = 1; ib <= 14; ++ib) {
                         const long o = (ib - 1) + 14 * (i0 + (long)(lay - 1) * ncol);
                         const double taucldorig_a = taucld[o];
@@ -1055,5 +1176,5 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
         }
         free(c);
     }
-    return 0;
+    return cld_stop ? 10 + cld_stop : 0;
 }

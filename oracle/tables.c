@@ -396,6 +396,27 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
         K->rayl = ra ? ra->data[0] : 0.0;
         if (!K->sfluxref) return 6;
     }
+    /* SW cloud optical properties (swcldpr) */
+    {
+        struct { const char *nm; double *dst; int n; } t2[10] = {
+            {"swcld.extliq1", &S->extliq1[0][0], 58}, {"swcld.ssaliq1", &S->ssaliq1[0][0], 58}, {"swcld.asyliq1", &S->asyliq1[0][0], 58},
+            {"swcld.extice2", &S->extice2[0][0], 43}, {"swcld.ssaice2", &S->ssaice2[0][0], 43}, {"swcld.asyice2", &S->asyice2[0][0], 43},
+            {"swcld.extice3", &S->extice3[0][0], 46}, {"swcld.ssaice3", &S->ssaice3[0][0], 46}, {"swcld.asyice3", &S->asyice3[0][0], 46},
+            {"swcld.fdlice3", &S->fdlice3[0][0], 46}};
+        for (int q = 0; q < 10; ++q) {
+            const orc_array_t *a = orc_blob_find(&bsw, t2[q].nm);
+            if (!a) return 8;
+            for (int i = 1; i <= t2[q].n; ++i)
+                for (int ib = 1; ib <= 14; ++ib) t2[q].dst[i * 15 + ib] = a->data[(i - 1) + t2[q].n * (ib - 1)];
+        }
+        struct { const char *nm; double *dst; } t1[6] = {{"swcld.abari", S->abari}, {"swcld.bbari", S->bbari}, {"swcld.cbari", S->cbari},
+                                                           {"swcld.dbari", S->dbari}, {"swcld.ebari", S->ebari}, {"swcld.fbari", S->fbari}};
+        for (int q = 0; q < 6; ++q) {
+            const orc_array_t *a = orc_blob_find(&bsw, t1[q].nm);
+            if (!a) return 8;
+            for (int i = 1; i <= 5; ++i) t1[q].dst[i] = a->data[i - 1];
+        }
+    }
     /* LW cloud absorption coefficients (lwcldpr) */
     {
         const orc_array_t *a;

@@ -270,6 +270,17 @@ def build_sw():
             a[int(m.group(1)) - 1, :] = parse_numbers(m.group(2))
         assert not np.isnan(a).any(), name
         out[f"swaer.{name}"] = a
+    # cloud optical properties of cldprop_sw's parameterisations (swcldpr, rrtmg_sw_init.f90:1519-3341)
+    subs = split_subroutines(os.path.join(SW, "src/rrtmg_sw_init.f90"), r"(swcldpr)")
+    decls = {n: ((58, 14), (1, 16)) for n in ("extliq1", "ssaliq1", "asyliq1")}
+    decls.update({n: ((43, 14), (1, 16)) for n in ("extice2", "ssaice2", "asyice2")})
+    decls.update({n: ((46, 14), (1, 16)) for n in ("extice3", "ssaice3", "asyice3", "fdlice3")})
+    decls.update({n: ((5,), (1,)) for n in ("abari", "bbari", "cbari", "dbari", "ebari", "fbari")})
+    arrs = parse_assignments(subs["swcldpr"], decls)
+    assert set(arrs) == set(decls), sorted(set(decls) - set(arrs))
+    for n, a in arrs.items():
+        assert not np.isnan(a).any(), n
+        out[f"swcld.{n}"] = a
     return out
 
 
