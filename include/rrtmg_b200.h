@@ -42,13 +42,14 @@
  *     inflglw = 1 (one absorption coefficient times cicewp + cliqwp) and inflglw = 2 (cldprop's ice options
  *     iceflglw = 0..3 in reice and liquid options liqflglw = 0..1 in reliq; a radius outside an option's range
  *     is the Fortran `stop` and returns RRTMG_B200_ERR_CLOUD_INPUT);
- *     SW icld = 1..3 with inflgsw = 0 (taucld, ssacld, asmcld, fsfcld given per band; layers clear or
- *     overcast, as the reference requires); SW iaer = 10 (tauaer, ssaaer, asmaer given per band) and
+ *     SW icld = 1..3 with inflgsw = 0 (taucld, ssacld, asmcld, fsfcld given per band) or inflgsw = 2
+ *     (cldprop_sw's parameterisations: cicewp, cliqwp, reice, reliq with iceflgsw = 1..3 and liqflgsw = 1;
+ *     a radius outside its range returns RRTMG_B200_ERR_CLOUD_INPUT); layers clear or overcast, as the
+ *     reference requires, tested like the Fortran on sunlit columns only; SW iaer = 10 (tauaer, ssaaer, asmaer given per band) and
  *     iaer = 6 (ecaer: optical depth at 0.55 micron of the six ECMWF aerosol types; spectral properties from
  *     the swaer.rsrtaua/rsrpiza/rsrasya tables of the SW coefficient blob).
  *     These run in general kernels that are correct but not tuned like the clear-sky path.
- *   - not built, RRTMG_B200_ERR_UNSUPPORTED: inflgsw > 0 (shortwave cloud optics from water paths and
- *     effective radii through the cldprop_sw parameterisations).
+ *   - RRTMG_B200_ERR_UNSUPPORTED: inflgsw = 1, for which cldprop_sw has no branch.
  *
  * Error behaviour: every function returns 0 on success or one of RRTMG_B200_ERR_*; nothing is ever
  * computed on the CPU and there is no fallback path.  The Fortran `stop 'PARTIAL CLOUD NOT ALLOWED'`
@@ -64,12 +65,12 @@ extern "C" {
 
 #define RRTMG_B200_OK 0
 #define RRTMG_B200_ERR_NOT_INITIALIZED 1 /* init not called (cf. FATAL at rrtm_radiation.f90:527-528) */
-#define RRTMG_B200_ERR_UNSUPPORTED 2     /* inflgsw > 0: branch not built */
+#define RRTMG_B200_ERR_UNSUPPORTED 2     /* an option the reference itself has no branch for (inflgsw = 1) */
 #define RRTMG_B200_ERR_PARTIAL_CLOUD 3   /* SW rad.nomcica:537 */
 #define RRTMG_B200_ERR_BAD_ARGUMENT 4
 #define RRTMG_B200_ERR_CUDA 5            /* see rrtmg_b200_last_error() */
 #define RRTMG_B200_ERR_TABLES 6          /* a coefficient array is missing or has the wrong shape */
-#define RRTMG_B200_ERR_CLOUD_INPUT 7     /* a Fortran `stop` of cldprop: effective radius out of range (LW cldprop.f90:193-253) */
+#define RRTMG_B200_ERR_CLOUD_INPUT 7     /* a Fortran `stop` of cldprop / cldprop_sw: effective radius out of range */
 
 #define RRTMG_B200_NBNDLW 16
 #define RRTMG_B200_NGPTLW 140

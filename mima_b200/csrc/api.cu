@@ -64,6 +64,7 @@ struct State {
     SwConst swc;
     SwTables swt{};
     DevBuf sw_tab, sw_exptbl, sw_work, sw_err;
+    bool sw_have_cld = false;
     SwWork sw_last{};
     int sw_last_ncol = 0;
 };
@@ -489,6 +490,23 @@ int sw_init_impl(double cpdair)
     G.swt.tab = (const double *)G.sw_tab.p;
     G.swt.exptbl = (const double *)G.sw_exptbl.p;
     if (sw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_sw) failed");
+    {   // cloud optical properties of cldprop_sw (swcldpr); optional: needed for inflgsw = 2 only
+        static SwCldConst k;
+        struct { const char *nm; double *dst; size_t n; } t[16] = {
+            {"swcld.extliq1", k.extliq1, 58 * 14}, {"swcld.ssaliq1", k.ssaliq1, 58 * 14}, {"swcld.asyliq1", k.asyliq1, 58 * 14},
+            {"swcld.extice2", k.extice2, 43 * 14}, {"swcld.ssaice2", k.ssaice2, 43 * 14}, {"swcld.asyice2", k.asyice2, 43 * 14},
+            {"swcld.extice3", k.extice3, 46 * 14}, {"swcld.ssaice3", k.ssaice3, 46 * 14}, {"swcld.asyice3", k.asyice3, 46 * 14},
+            {"swcld.fdlice3", k.fdlice3, 46 * 14}, {"swcld.abari", k.abari, 5}, {"swcld.bbari", k.bbari, 5}, {"swcld.cbari", k.cbari, 5},
+            {"swcld.dbari", k.dbari, 5}, {"swcld.ebari", k.ebari, 5}, {"swcld.fbari", k.fbari, 5}};
+        k.have = 1;
+        for (auto &e : t) {
+            const HostArr *a = find(e.nm);
+            if (!a || (size_t)a->size() != e.n) { k.have = 0; break; }
+            std::memcpy(e.dst, a->data.data(), e.n * sizeof(double));
+        }
+        if (k.have && sw_upload_cld(k)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(d_swcld) failed");
+        G.sw_have_cld = k.have != 0;
+    }
     G.sw_ready = true;
     return RRTMG_B200_OK;
 }
@@ -589,6 +607,8 @@ struct SwOpt {
     const double *cldfr = nullptr, *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;
     const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;
     const double *ecaer = nullptr;
+    int iceflgsw = 0, liqflgsw = 0;
+    const double *cicewp = nullptr, *cliqwp = nullptr, *reice = nullptr, *reliq = nullptr;
 };
 int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt())
 {
@@ -597,10 +617,18 @@ int sw_validate(int ncol, int nlay, int *icld, int *iaer, const SwOpt &o = SwOpt
     if (icld && (*icld < 0 || *icld > 3)) *icld = 2;                           // SW rad.nomcica:468
     if (iaer && *iaer != 0 && *iaer != 6 && *iaer != 10) *iaer = 0;            // SW rad.nomcica:473
     if (icld && *icld != 0) {
-        if (o.inflgsw != 0)
-            return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: inflgsw > 0 (cloud optics from water paths, cldprop_sw parameterisations) is not built");
-        if (!o.cldfr || !o.taucld || !o.ssacld || !o.asmcld || !o.fsfcld)
-            return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: icld > 0 needs cldfr, taucld, ssacld, asmcld, fsfcld");
+        if (o.inflgsw != 0 && o.inflgsw != 2)
+            return fail(RRTMG_B200_ERR_UNSUPPORTED, "rrtmg_sw: inflgsw must be 0 (optical properties given) or 2 (water paths and radii); cldprop_sw has no other branch");
+        if (!o.cldfr) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: icld > 0 needs cldfr");
+        if (o.inflgsw == 0 && (!o.taucld || !o.ssacld || !o.asmcld || !o.fsfcld))
+            return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: icld > 0 with inflgsw = 0 needs taucld, ssacld, asmcld, fsfcld");
+        if (o.inflgsw == 2) {
+            if (!o.cicewp || !o.cliqwp || !o.reice || !o.reliq)
+                return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: inflgsw = 2 needs cicewp, cliqwp, reice, reliq");
+            if (o.iceflgsw < 1 || o.iceflgsw > 3 || o.liqflgsw != 1)
+                return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: inflgsw = 2 needs iceflgsw in 1..3 and liqflgsw = 1 (the options cldprop_sw defines)");
+            if (!G.sw_have_cld) return fail(RRTMG_B200_ERR_TABLES, "rrtmg_sw: inflgsw = 2 needs the swcld.* tables");
+        }
     }
     if (iaer && *iaer == 6) {
         if (!G.swc.have_aer) return fail(RRTMG_B200_ERR_TABLES, "rrtmg_sw: iaer = 6 needs the swaer.rsrtaua/rsrpiza/rsrasya tables");
@@ -645,15 +673,18 @@ int sw_err_begin(bool general)
 {
     if (!general) return RRTMG_B200_OK;
     if (G.sw_err.ensure(256)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed");
-    CUDA_OK(cudaMemset(G.sw_err.p, 0, 4));
+    CUDA_OK(cudaMemset(G.sw_err.p, 0, 8));
     return RRTMG_B200_OK;
 }
 int sw_err_end(bool general)
 {
     if (!general) return RRTMG_B200_OK;
-    int flag = 0;
-    CUDA_OK(cudaMemcpy(&flag, G.sw_err.p, 4, cudaMemcpyDeviceToHost));
-    if (flag & 1) return fail(RRTMG_B200_ERR_PARTIAL_CLOUD, "rrtmg_sw: PARTIAL CLOUD NOT ALLOWED (0 < cldfr < 1 with icld > 0)");
+    int flag[2] = {0, 0};
+    CUDA_OK(cudaMemcpy(flag, G.sw_err.p, 8, cudaMemcpyDeviceToHost));
+    if (flag[0] & 1) return fail(RRTMG_B200_ERR_PARTIAL_CLOUD, "rrtmg_sw: PARTIAL CLOUD NOT ALLOWED (0 < cldfr < 1 with icld > 0)");
+    static const char *msg[5] = {"", "ICE RADIUS OUT OF BOUNDS", "ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS",
+                                 "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS", "an interpolated cloud property is out of range"};
+    if (flag[1] >= 1 && flag[1] <= 4) return fail(RRTMG_B200_ERR_CLOUD_INPUT, std::string("rrtmg_sw cldprop_sw: ") + msg[flag[1]]);
     return RRTMG_B200_OK;
 }
 
@@ -734,7 +765,7 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
 #define OFF(p) if (in.p) in.p += c0
         OFF(play); OFF(plev); OFF(tlay); OFF(tlev); OFF(tsfc); OFF(h2o); OFF(o3); OFF(co2); OFF(ch4); OFF(n2o);
         OFF(o2); OFF(asdir); OFF(asdif); OFF(aldir); OFF(aldif); OFF(coszen);
-        OFF(cldfr); OFF(tauaer); OFF(ssaaer); OFF(asmaer); OFF(ecaer);
+        OFF(cldfr); OFF(tauaer); OFF(ssaaer); OFF(asmaer); OFF(ecaer); OFF(cicewp); OFF(cliqwp); OFF(reice); OFF(reliq);
 #undef OFF
 #define OFF14(p) if (in.p) in.p += (size_t)14 * c0
         OFF14(taucld); OFF14(ssacld); OFF14(asmcld); OFF14(fsfcld);
@@ -750,7 +781,11 @@ void sw_set_optional(SwIn &in, const int *icld, const int *iaer, const SwOpt &o)
 {
     in.icld = icld ? *icld : 0;
     in.iaer = iaer ? *iaer : 0;
-    if (in.icld >= 1) { in.cldfr = o.cldfr; in.taucld = o.taucld; in.ssacld = o.ssacld; in.asmcld = o.asmcld; in.fsfcld = o.fsfcld; }
+    if (in.icld >= 1) {
+        in.cldfr = o.cldfr; in.inflg = o.inflgsw;
+        if (o.inflgsw == 0) { in.taucld = o.taucld; in.ssacld = o.ssacld; in.asmcld = o.asmcld; in.fsfcld = o.fsfcld; }
+        else { in.iceflg = o.iceflgsw; in.liqflg = o.liqflgsw; in.cicewp = o.cicewp; in.cliqwp = o.cliqwp; in.reice = o.reice; in.reliq = o.reliq; }
+    }
     if (in.iaer == 10) { in.tauaer = o.tauaer; in.ssaaer = o.ssaaer; in.asmaer = o.asmaer; }
     if (in.iaer == 6) in.ecaer = o.ecaer;
 }
@@ -1252,9 +1287,9 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
                          const double *ch4vmr, const double *n2ovmr, const double *o2vmr,
                          const double *asdir, const double *asdif, const double *aldir, const double *aldif,
                          const double *coszen, double adjes, int dyofyr, double scon,
-                         int inflgsw, int, int, const double *cldfr,
+                         int inflgsw, int iceflgsw, int liqflgsw, const double *cldfr,
                          const double *taucld, const double *ssacld, const double *asmcld, const double *fsfcld,
-                         const double *, const double *, const double *, const double *,
+                         const double *cicewp, const double *cliqwp, const double *reice, const double *reliq,
                          const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                          double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc,
                          double *swhrc, void *stream)
@@ -1262,7 +1297,7 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr || !swuflxc || !swdflxc || !swhrc)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_sw: required array is NULL");
-    SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer};
+    SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer, iceflgsw, liqflgsw, cicewp, cliqwp, reice, reliq};
     if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;       // also normalises *icld, *iaer
     SwIn in{ncol, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
             asdir, asdif, aldir, aldif, coszen, sw_adjflux(adjes, dyofyr, scon)};
@@ -1283,8 +1318,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
                   const double *tauaer, const double *ssaaer, const double *asmaer, const double *ecaer,
                   double *swuflx, double *swdflx, double *swhr, double *swuflxc, double *swdflxc, double *swhrc)
 {
-    (void)iceflgsw; (void)liqflgsw; (void)cicewp; (void)cliqwp; (void)reice; (void)reliq;
-    const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer};
+    const SwOpt opt{inflgsw, cldfr, taucld, ssacld, asmcld, fsfcld, tauaer, ssaaer, asmaer, ecaer, iceflgsw, liqflgsw, cicewp, cliqwp, reice, reliq};
     // swuflxc, swdflxc, swhrc may be NULL: the clear-sky result is then not copied back
     if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !asdir || !asdif || !aldir ||
         !aldif || !coszen || !swuflx || !swdflx || !swhr)
@@ -1297,7 +1331,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
     const int hc = host_chunk(ncol);
     const bool fields = G.capture;
     const size_t L = nlay, V = nlay + 1;
-    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6 + (cloud ? 57 * L : 0) + (aer ? 42 * L : 0) + (aer6 ? 6 * L : 0)) * 8 + 48 * 256;
+    const size_t in_bytes = (size_t)hc * (9 * L + 2 * V + 6 + (cloud ? 57 * L : 0) + (aer ? 42 * L : 0) + (aer6 ? 6 * L : 0)) * 8 + 56 * 256;
     const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
     SwWork wsz;
     const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields, general);
@@ -1324,8 +1358,13 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
         SwOpt dopt;
         if (cloud) {
             dopt.cldfr = a.up(cldfr, L);
-            dopt.taucld = a.up_banded(taucld, 14, L); dopt.ssacld = a.up_banded(ssacld, 14, L);
-            dopt.asmcld = a.up_banded(asmcld, 14, L); dopt.fsfcld = a.up_banded(fsfcld, 14, L);
+            dopt.inflgsw = inflgsw; dopt.iceflgsw = iceflgsw; dopt.liqflgsw = liqflgsw;
+            if (inflgsw == 0) {
+                dopt.taucld = a.up_banded(taucld, 14, L); dopt.ssacld = a.up_banded(ssacld, 14, L);
+                dopt.asmcld = a.up_banded(asmcld, 14, L); dopt.fsfcld = a.up_banded(fsfcld, 14, L);
+            } else {
+                dopt.cicewp = a.up(cicewp, L); dopt.cliqwp = a.up(cliqwp, L); dopt.reice = a.up(reice, L); dopt.reliq = a.up(reliq, L);
+            }
         }
         if (aer) { dopt.tauaer = a.up(tauaer, 14 * L); dopt.ssaaer = a.up(ssaaer, 14 * L); dopt.asmaer = a.up(asmaer, 14 * L); }
         if (aer6) dopt.ecaer = a.up(ecaer, 6 * L);

@@ -180,7 +180,21 @@ struct SwIn {
     const double *taucld = nullptr, *ssacld = nullptr, *asmcld = nullptr, *fsfcld = nullptr;   // (14, ld, nlay), inflgsw = 0
     const double *tauaer = nullptr, *ssaaer = nullptr, *asmaer = nullptr;           // (ld, nlay, 14), iaer = 10
     const double *ecaer = nullptr;                                                  // (ld, nlay, 6), iaer = 6
+    // cloud optics from water paths (cldprop_sw, inflgsw = 2): g/m2 and microns, (ld, nlay)
+    int inflg = 0, iceflg = 0, liqflg = 0;
+    const double *cicewp = nullptr, *cliqwp = nullptr, *reice = nullptr, *reliq = nullptr;
 };
+
+// cloud optical properties of cldprop_sw's parameterisations (swcldpr, rrtmg_sw_init.f90:1519-3341), Fortran order
+// (radius index, band 16..29)
+struct SwCldConst {
+    double extliq1[58 * 14], ssaliq1[58 * 14], asyliq1[58 * 14];
+    double extice2[43 * 14], ssaice2[43 * 14], asyice2[43 * 14];
+    double extice3[46 * 14], ssaice3[46 * 14], asyice3[46 * 14], fdlice3[46 * 14];
+    double abari[5], bbari[5], cbari[5], dbari[5], ebari[5], fbari[5];
+    int have;
+};
+int sw_upload_cld(const SwCldConst &c);
 
 struct SwOut {
     int ld;
@@ -200,7 +214,8 @@ struct SwWork {
     double *taur;             // [col][lay][112], expanded from rdesc only for the stage-capture test hook
     double *sfluxzen;         // [col][112]
     // general path (icld >= 1 or iaer = 10): per (column, layer, band) {tauc, omgc, asyc (delta-M scaled, cldprop_sw
-    // inflag = 0), taua, omga, asya} and the layer cloud fraction; err: bit 0 = partial cloud found
+    // inflag = 0), taua, omga, asya} and the layer cloud fraction; err[0]: bit 0 = partial cloud found, err[1]: number of
+    // the cldprop_sw `stop` some cell ran into
     double *opt;              // [col][lay][14][6] or null
     double *clfr;             // [col][lay]
     int *err;

@@ -558,6 +558,96 @@ __global__ void sw_expand_taur_kernel(SwTables T, SwWork w)
 // scattering fraction, SW/src/rrtmg_sw_cldprop.f90:120-166), aerosol properties as given (iaer = 10,
 // rad.nomcica:633-640), transposed to [col][lay][band][6] so that the g-point lanes of a band read one address.
 // Also the `stop 'PARTIAL CLOUD NOT ALLOWED'` test of rad.nomcica:534-539 (flag, checked by the host).
+__device__ SwCldConst d_swcld;          // 55 KB: global memory, read through the read-only path
+int sw_upload_cld(const SwCldConst &c) { return cudaMemcpyToSymbol(d_swcld, &c, sizeof c) == cudaSuccess ? 0 : -1; }
+
+// cldprop_sw, inflag = 2, one (layer, band) (rrtmg_sw_cldprop.f90:168-345): ice option 1 (Ebert and Curry), 2 (Streamer),
+// 3 (Fu), liquid option 1 (Hu and Stamnes), then the delta-scaled combination.  Returns 0 or the number of the Fortran
+// `stop`: 1 ICE RADIUS OUT OF BOUNDS, 2 ICE GENERALIZED EFFECTIVE SIZE OUT OF BOUNDS, 3 LIQUID EFFECTIVE RADIUS OUT OF
+// BOUNDS, 4 a range check on an interpolated property.
+__device__ int sw_cldprop_band(int ib, int iceflag, double ciwp, double clwp, double radice, double radliq,
+                               double &tauc, double &omgc, double &asyc)
+{
+    const SwCldConst &K = d_swcld;
+    const double eps = 1.e-06, cldmin = 1.e-20;
+    double extcoice = 0., ssacoice = 0., gice = 0., forwice = 0., extcoliq = 0., ssacoliq = 0., gliq = 0., forwliq = 0.;
+    if (ciwp == 0.0) {
+    } else if (iceflag == 1) {
+        if (radice < 13.0 || radice > 130.) return 1;
+        const double wavenum2[14] = {3250., 4000., 4650., 5150., 6150., 7700., 8050., 12850., 16000., 22650., 29000., 38000., 50000., 2600.};
+        int icx = 4;
+        if (wavenum2[ib] > 1.43e04) icx = 0;
+        else if (wavenum2[ib] > 7.7e03) icx = 1;
+        else if (wavenum2[ib] > 5.3e03) icx = 2;
+        else if (wavenum2[ib] > 4.0e03) icx = 3;
+        extcoice = K.abari[icx] + K.bbari[icx] / radice;
+        ssacoice = 1. - K.cbari[icx] - K.dbari[icx] * radice;
+        gice = K.ebari[icx] + K.fbari[icx] * radice;
+        if (gice >= 1.0) gice = 1.0 - eps;
+        forwice = gice * gice;
+        if (extcoice < 0.0 || ssacoice > 1.0 || ssacoice < 0.0 || gice > 1.0 || gice < 0.0) return 4;
+    } else if (iceflag == 2) {
+        if (radice < 5.0 || radice > 131.0) return 1;
+        const double factor = (radice - 2.) / 3.;
+        int index = (int)factor;
+        if (index == 43) index = 42;
+        const double fint = factor - (double)index;
+        const int o = (index - 1) + 43 * ib;
+        extcoice = K.extice2[o] + fint * (K.extice2[o + 1] - K.extice2[o]);
+        ssacoice = K.ssaice2[o] + fint * (K.ssaice2[o + 1] - K.ssaice2[o]);
+        gice = K.asyice2[o] + fint * (K.asyice2[o + 1] - K.asyice2[o]);
+        forwice = gice * gice;
+        if (extcoice < 0.0 || ssacoice > 1.0 || ssacoice < 0.0 || gice > 1.0 || gice < 0.0) return 4;
+    } else {
+        if (radice < 5.0 || radice > 140.0) return 2;
+        const double factor = (radice - 2.) / 3.;
+        int index = (int)factor;
+        if (index == 46) index = 45;
+        const double fint = factor - (double)index;
+        const int o = (index - 1) + 46 * ib;
+        extcoice = K.extice3[o] + fint * (K.extice3[o + 1] - K.extice3[o]);
+        ssacoice = K.ssaice3[o] + fint * (K.ssaice3[o + 1] - K.ssaice3[o]);
+        gice = K.asyice3[o] + fint * (K.asyice3[o + 1] - K.asyice3[o]);
+        const double fdelta = K.fdlice3[o] + fint * (K.fdlice3[o + 1] - K.fdlice3[o]);
+        if (fdelta < 0.0 || fdelta > 1.0) return 4;
+        forwice = fdelta + 0.5 / ssacoice;
+        if (forwice > gice) forwice = gice;
+        if (extcoice < 0.0 || ssacoice > 1.0 || ssacoice < 0.0 || gice > 1.0 || gice < 0.0) return 4;
+    }
+    if (clwp != 0.0) {
+        if (radliq < 2.5 || radliq > 60.) return 3;
+        int index = (int)(radliq - 1.5);
+        if (index == 0) index = 1;
+        if (index == 58) index = 57;
+        const double fint = radliq - 1.5 - (double)index;
+        const int o = (index - 1) + 58 * ib;
+        extcoliq = K.extliq1[o] + fint * (K.extliq1[o + 1] - K.extliq1[o]);
+        ssacoliq = K.ssaliq1[o] + fint * (K.ssaliq1[o + 1] - K.ssaliq1[o]);
+        if (fint < 0. && ssacoliq > 1.) ssacoliq = K.ssaliq1[o];
+        gliq = K.asyliq1[o] + fint * (K.asyliq1[o + 1] - K.asyliq1[o]);
+        forwliq = gliq * gliq;
+        if (extcoliq < 0.0 || ssacoliq > 1.0 || ssacoliq < 0.0 || gliq > 1.0 || gliq < 0.0) return 4;
+    }
+    const double tauliqorig = clwp * extcoliq;
+    const double tauiceorig = ciwp * extcoice;
+    const double ssaliq = ssacoliq * (1.0 - forwliq) / (1.0 - forwliq * ssacoliq);
+    const double tauliq = (1.0 - forwliq * ssacoliq) * tauliqorig;
+    const double ssaice = ssacoice * (1.0 - forwice) / (1.0 - forwice * ssacoice);
+    const double tauice = (1.0 - forwice * ssacoice) * tauiceorig;
+    const double scatliq = ssaliq * tauliq;
+    double scatice = ssaice * tauice;
+    double taucloud = tauliq + tauice;
+    if (taucloud == 0.0) taucloud = cldmin;
+    if (scatice == 0.0) scatice = cldmin;
+    tauc = taucloud;
+    omgc = (scatliq + scatice) / taucloud;
+    if (iceflag == 3)
+        asyc = (1.0 / (scatliq + scatice)) * (scatliq * (gliq - forwliq) / (1.0 - forwliq) + scatice * ((gice - forwice) / (1.0 - forwice)));
+    else
+        asyc = (scatliq * (gliq - forwliq) / (1.0 - forwliq) + scatice * (gice - forwice) / (1.0 - forwice)) / (scatliq + scatice);
+    return 0;
+}
+
 __global__ void __launch_bounds__(128) sw_optics_kernel(SwIn in, SwWork w)
 {
     const int nc = w.nc, nlay = w.nlay;
@@ -566,20 +656,28 @@ __global__ void __launch_bounds__(128) sw_optics_kernel(SwIn in, SwWork w)
     const int l = (int)(i / nc);
     const int col = (int)(i - (size_t)l * nc);
     const size_t ld = (size_t)in.ld;
+    if (in.coszen[col] < ZEPZEN) return;      // night column: skipped before the cloud tests in the reference too (rad.nomcica:497-505)
     const double cldmin = 1.e-20, zepsec = 1.e-06;
     double cf = 0.0;
     double tauctot = 0.0;
     if (in.icld >= 1) {
         cf = in.cldfr[col + (size_t)l * ld];
         if (cf > zepsec && cf < 1.0 - zepsec) atomicOr(w.err, 1);
-        for (int ib = 0; ib < 14; ++ib) tauctot = tauctot + in.taucld[ib + 14 * (col + (size_t)l * ld)];
+        if (in.taucld)
+            for (int ib = 0; ib < 14; ++ib) tauctot = tauctot + in.taucld[ib + 14 * (col + (size_t)l * ld)];
     }
-    const bool cloudy = in.icld >= 1 && cf >= cldmin && tauctot >= cldmin;    // cwp = 0 for directly specified optics
+    const size_t ol = col + (size_t)l * ld;
+    const bool wp = in.icld >= 1 && in.inflg == 2;
+    const double ciwp = wp ? in.cicewp[ol] : 0.0, clwp = wp ? in.cliqwp[ol] : 0.0;
+    const bool cloudy = in.icld >= 1 && cf >= cldmin && ((ciwp + clwp) >= cldmin || tauctot >= cldmin);
     w.clfr[(size_t)col * nlay + l] = cf;
     double *o = w.opt + ((size_t)col * nlay + l) * 14 * 6;
     for (int ib = 0; ib < 14; ++ib) {
         double tauc = 0.0, omgc = 1.0, asyc = 0.0;
-        if (cloudy) {
+        if (cloudy && wp) {
+            const int stop = sw_cldprop_band(ib, in.iceflg, ciwp, clwp, in.reice[ol], in.reliq[ol], tauc, omgc, asyc);
+            if (stop) atomicMax(w.err + 1, stop);
+        } else if (cloudy) {
             const size_t q = ib + 14 * (col + (size_t)l * ld);
             const double taucldorig_a = in.taucld[q];
             const double ffp = in.fsfcld[q];

@@ -224,8 +224,9 @@ def rrtmg_sw(ncol, nlay, icld, iaer,
     """Returns (swuflx, swdflx, swhr, swuflxc, swdflxc, swhrc); the last three are None with clear_sky=False.  icld >= 1 takes cloud optical properties
     (inflgsw = 0: cldfr (ncol,nlay) 0 or 1, taucld/ssacld/asmcld/fsfcld (14,ncol,nlay)); iaer = 10 takes
     tauaer/ssaaer/asmaer (ncol,nlay,14); iaer = 6 takes ecaer (ncol,nlay,6), the optical depth at 0.55 micron of the six
-    ECMWF aerosol types.  Water-path cloud inputs (inflgsw > 0) raise RRTMGError(2); a partially cloudy layer raises
-    RRTMGError(3) like the reference's stop."""
+    ECMWF aerosol types.  inflgsw = 2 takes the water paths cicewp, cliqwp (g/m2) and effective radii reice, reliq (microns)
+    with iceflgsw 1..3 and liqflgsw = 1 (cldprop_sw's parameterisations; a radius outside its range raises RRTMGError(7));
+    a partially cloudy layer raises RRTMGError(3) like the reference's stop."""
     L = (ncol, nlay)
     V = (ncol, nlay + 1)
     B = (NBNDSW, ncol, nlay)
@@ -275,7 +276,8 @@ def lw_from_columns(c, tauaer=None, idrv=0, icld=0, clouds=None, inflglw=0, clea
                     None if np.all(c.emis == 1.0) else c.emis, tauaer=tauaer, inflglw=inflglw, iceflglw=iceflglw, liqflglw=liqflglw, clear_sky=clear_sky, **(clouds or {}))
 
 
-def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0, clear_sky=True):
+def sw_from_columns(c, icld=0, iaer=0, clouds=None, aerosols=None, inflgsw=0, clear_sky=True, iceflgsw=0, liqflgsw=0):
     return rrtmg_sw(c.ncol, c.nlay, icld, iaer, c.play, c.plev, c.tlay, c.tlev, c.tsfc, c.h2o, c.o3, c.co2,
                     _opt(c.ch4), _opt(c.n2o), _opt(c.o2), c.albedo, c.albedo, c.albedo, c.albedo,
-                    c.coszen, c.adjes, c.dyofyr, c.scon, inflgsw=inflgsw, clear_sky=clear_sky, **(clouds or {}), **(aerosols or {}))
+                    c.coszen, c.adjes, c.dyofyr, c.scon, inflgsw=inflgsw, iceflgsw=iceflgsw, liqflgsw=liqflgsw, clear_sky=clear_sky,
+                    **(clouds or {}), **(aerosols or {}))

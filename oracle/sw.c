@@ -1034,9 +1034,10 @@ int orc_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
     if (icld >= 1 && inflgsw == 2 && (!cicewp || !cliqwp || !reice || !reliq || iceflgsw < 1 || iceflgsw > 3 || liqflgsw != 1)) return 3;
     int cld_stop = 0;
     if (iaer == 10 && (!tauaer || !ssaaer || !asmaer)) return 3;
-    if (icld >= 1) /* without McICA: clear or overcast layers only (:534-539, `stop 'PARTIAL CLOUD NOT ALLOWED'`) */
+    if (icld >= 1) /* without McICA: clear or overcast layers only (:534-539, `stop 'PARTIAL CLOUD NOT ALLOWED'`); the test sits
+                      behind the night-column skip (:497-505), so only sunlit columns are looked at */
         for (long i = 0; i < (long)ncol * nlay; ++i)
-            if (cldfr[i] > 1.e-06 && cldfr[i] < 1.0 - 1.e-06) return 4;
+            if (!(coszen[i % ncol] < 1.e-10) && cldfr[i] > 1.e-06 && cldfr[i] < 1.0 - 1.e-06) return 4;
     if (nlay < 1 || nlay > ORC_MAXLAY) return 3;
     if (nthreads < 1) nthreads = 1;
     const double zepsec = 1.e-06, zepzen = 1.e-10;

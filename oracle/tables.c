@@ -408,6 +408,11 @@ int orc_init(const char *lw_ref_blob, const char *lw_kg_blob, const char *sw_kg_
             if (!a) return 8;
             for (int i = 1; i <= t2[q].n; ++i)
                 for (int ib = 1; ib <= 14; ++ib) t2[q].dst[i * 15 + ib] = a->data[(i - 1) + t2[q].n * (ib - 1)];
+            reg_t *r = &g_reg[g_nreg++];               /* visible through orc_get_table, column-major as in the blob */
+            snprintf(r->name, sizeof r->name, "%s", t2[q].nm);
+            r->n = t2[q].n * 14;
+            r->data = (double *)malloc(sizeof(double) * r->n);
+            memcpy(r->data, a->data, sizeof(double) * r->n);
         }
         struct { const char *nm; double *dst; } t1[6] = {{"swcld.abari", S->abari}, {"swcld.bbari", S->bbari}, {"swcld.cbari", S->cbari},
                                                            {"swcld.dbari", S->dbari}, {"swcld.ebari", S->ebari}, {"swcld.fbari", S->fbari}};

@@ -187,9 +187,12 @@ contains
          reice(*), reliq(*), tauaer(*), ssaaer(*), asmaer(*), ecaer(*)
     real(c_double), contiguous, target, intent(inout) :: swuflx(:,:), swdflx(:,:), swhr(:,:), swuflxc(:,:), swdflxc(:,:), swhrc(:,:)
     integer(c_int) :: icld_c, iaer_c
-    type(c_ptr) :: pc(5), pa(3), pec
+    type(c_ptr) :: pc(5), pa(3), pec, pw(4)
     icld_c = icld; iaer_c = iaer
-    pc = c_null_ptr; pa = c_null_ptr; pec = c_null_ptr
+    pc = c_null_ptr; pa = c_null_ptr; pec = c_null_ptr; pw = c_null_ptr
+    if (icld /= 0 .and. inflgsw == 2) then
+       pw(1) = c_loc(cicewp); pw(2) = c_loc(cliqwp); pw(3) = c_loc(reice); pw(4) = c_loc(reliq)
+    endif
     if (iaer == 6) pec = c_loc(ecaer)
     if (icld /= 0) then
        pc(1) = c_loc(cldfr); pc(2) = c_loc(taucld); pc(3) = c_loc(ssacld); pc(4) = c_loc(asmcld); pc(5) = c_loc(fsfcld)
@@ -200,8 +203,8 @@ contains
     call b200_check(rrtmg_b200_sw(ncol, nlay, icld_c, iaer_c, c_loc(play), c_loc(plev), c_loc(tlay), c_loc(tlev), &
          c_loc(tsfc), c_loc(h2ovmr), c_loc(o3vmr), c_loc(co2vmr), opt2(ch4vmr), opt2(n2ovmr), opt2(o2vmr), &
          c_loc(asdir), c_loc(asdif), c_loc(aldir), c_loc(aldif), c_loc(coszen), adjes, dyofyr, scon, &
-         inflgsw, iceflgsw, liqflgsw, pc(1), pc(2), pc(3), pc(4), pc(5), c_null_ptr, &
-         c_null_ptr, c_null_ptr, c_null_ptr, pa(1), pa(2), pa(3), pec, &
+         inflgsw, iceflgsw, liqflgsw, pc(1), pc(2), pc(3), pc(4), pc(5), pw(1), &
+         pw(2), pw(3), pw(4), pa(1), pa(2), pa(3), pec, &
          c_loc(swuflx), c_loc(swdflx), c_loc(swhr), optout(swuflxc), optout(swdflxc), optout(swhrc)), 'rrtmg_sw')
     icld = icld_c; iaer = iaer_c
   end subroutine

@@ -198,8 +198,13 @@ def test_unsupported_options_fail_loudly(gpu):
         gpu.rrtmg_sw(c.ncol, c.nlay, 0, 10, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0)
     assert e.value.code == 4                      # iaer = 10 without the aerosol arrays
     with pytest.raises(gpu.RRTMGError) as e:
-        gpu.rrtmg_sw(c.ncol, c.nlay, 2, 0, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0, inflgsw=2)
-    assert e.value.code == 2                      # cloud optics from water paths: not built
+        gpu.rrtmg_sw(c.ncol, c.nlay, 2, 0, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0, inflgsw=2,
+                     cldfr=c.tlay * 0)
+    assert e.value.code == 4                      # inflgsw = 2 without the water paths / radii
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.rrtmg_sw(c.ncol, c.nlay, 2, 0, *args, c.albedo, c.albedo, c.albedo, c.albedo, c.coszen, 1.0, 0, 1370.0, inflgsw=1,
+                     cldfr=c.tlay * 0)
+    assert e.value.code == 2                      # cldprop_sw has no inflag = 1 branch
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.rrtmg_lw(c.ncol, 200, 0, 0, *args, None, None, None, None, None)
     assert e.value.code == 4

@@ -125,8 +125,10 @@ def test_out_of_range_switches_are_reset(gpu, oracle, cols):
 
 
 def test_partial_cloud_is_an_error(gpu, cols):
-    c = cols.take(np.arange(16))
+    c = cols.take(np.flatnonzero(cols.coszen > 0.1)[:12].tolist() + np.flatnonzero(cols.coszen == 0)[:4].tolist())
     cl = _clouds(c, np.random.default_rng(4))
+    cl["cldfr"][14, 7] = 0.5                   # in a night column: not an error, the column is skipped first
+    gpu.sw_from_columns(c, icld=2, clouds=cl)
     cl["cldfr"][5, 7] = 0.5
     with pytest.raises(gpu.RRTMGError) as e:
         gpu.sw_from_columns(c, icld=2, clouds=cl)
@@ -142,3 +144,53 @@ def test_eighty_layers(gpu, oracle):
     _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=10, clouds=cl, aerosols=aer),
                    oracle.rrtmg_sw(c, icld=2, iaer=10, clouds=cl, aerosols=aer), SW_OUT)
     _check_outputs(gpu.sw_from_columns(c, iaer=10, aerosols=aer), oracle.rrtmg_sw(c, iaer=10, aerosols=aer), SW_OUT)
+
+
+def _water_clouds(c, rng):
+    shp = (c.ncol, c.nlay)
+    return dict(cldfr=np.asfortranarray((rng.uniform(size=shp) < 0.3).astype(np.float64)),
+                cicewp=np.asfortranarray(rng.uniform(0, 30, shp) * (rng.uniform(size=shp) < 0.7)),
+                cliqwp=np.asfortranarray(rng.uniform(0, 60, shp) * (rng.uniform(size=shp) < 0.7)),
+                reice=np.asfortranarray(rng.uniform(14, 120, shp)), reliq=np.asfortranarray(rng.uniform(3, 50, shp)))
+
+
+@pytest.mark.parametrize("iceflg", [1, 2, 3])
+def test_cloud_optics_from_water_paths(gpu, oracle, cols, iceflg):
+    """cldprop_sw's inflag = 2 (rrtmg_sw_cldprop.f90:168-345): Ebert-Curry / Streamer / Fu ice, Hu-Stamnes liquid, and their
+    delta-scaled combination; also with aerosols and in chunks."""
+    rng = np.random.default_rng(60 + iceflg)
+    cl = _water_clouds(cols, rng)
+    got = gpu.sw_from_columns(cols, icld=2, inflgsw=2, iceflgsw=iceflg, liqflgsw=1, clouds=cl)
+    _check_outputs(got, oracle.rrtmg_sw(cols, icld=2, inflgsw=2, iceflgsw=iceflg, liqflgsw=1, clouds=cl), SW_OUT)
+    clear = gpu.sw_from_columns(cols)
+    assert np.max(np.abs(got[4] - clear[4])) < 1e-9 * np.abs(clear[4]).max()
+    c = cols.take(np.arange(170))
+    cl = {k: np.asfortranarray(v[:170]) for k, v in cl.items()}
+    aer = dict(ecaer=np.asfortranarray(rng.uniform(0.0, 0.05, (c.ncol, c.nlay, 6))))
+    ref = oracle.rrtmg_sw(c, icld=2, iaer=6, inflgsw=2, iceflgsw=iceflg, liqflgsw=1, clouds=cl, aerosols=aer)
+    gpu.set_option("host_chunk", 64)
+    try:
+        _check_outputs(gpu.sw_from_columns(c, icld=2, iaer=6, inflgsw=2, iceflgsw=iceflg, liqflgsw=1, clouds=cl, aerosols=aer), ref, SW_OUT)
+    finally:
+        gpu.set_option("host_chunk", 0)
+
+
+def test_radius_out_of_range_is_an_error(gpu, cols):
+    c = cols.take(np.flatnonzero(cols.coszen > 0.1)[:30].tolist() + np.flatnonzero(cols.coszen == 0)[:10].tolist())
+    cl = _water_clouds(c, np.random.default_rng(2))
+    cl["cldfr"][35, 5] = 1.0; cl["cicewp"][35, 5] = 10.0; cl["reice"][35, 5] = 4.0     # a night column: never looked at (rad.nomcica:497-505)
+    gpu.sw_from_columns(c, icld=2, inflgsw=2, iceflgsw=2, liqflgsw=1, clouds=cl)
+    cl["cldfr"][3, 5] = 1.0; cl["cicewp"][3, 5] = 10.0; cl["reice"][3, 5] = 4.0
+    for ice in (1, 2, 3):
+        with pytest.raises(gpu.RRTMGError) as e:
+            gpu.sw_from_columns(c, icld=2, inflgsw=2, iceflgsw=ice, liqflgsw=1, clouds=cl)
+        assert e.value.code == 7 and "ICE" in str(e.value)
+    cl["reice"][3, 5] = 50.0
+    cl["cliqwp"][3, 5] = 5.0; cl["reliq"][3, 5] = 2.0
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.sw_from_columns(c, icld=2, inflgsw=2, iceflgsw=2, liqflgsw=1, clouds=cl)
+    assert e.value.code == 7 and "LIQUID" in str(e.value)
+    with pytest.raises(gpu.RRTMGError) as e:
+        gpu.sw_from_columns(c, icld=2, inflgsw=2, iceflgsw=0, liqflgsw=1, clouds=cl)      # cldprop_sw defines ice options 1..3 only
+    assert e.value.code == 4
+    gpu.sw_from_columns(c)

@@ -72,7 +72,10 @@ def test_switch_handling(oracle, cols):
     b = oracle.rrtmg_sw(c, icld=2, clouds=cl)
     for k in SW:
         assert np.array_equal(a[k], b[k])
-    cl["cldfr"][2, 3] = 0.4
+    night, day = int(np.flatnonzero(c.coszen == 0)[0]), int(np.flatnonzero(c.coszen > 0)[0])
+    cl["cldfr"][night, 3] = 0.4                                  # a night column is skipped before the test (:497-505)
+    oracle.rrtmg_sw(c, icld=2, clouds=cl)
+    cl["cldfr"][day, 3] = 0.4
     with pytest.raises(RuntimeError, match="rc=4"):             # stop 'PARTIAL CLOUD NOT ALLOWED' (:537)
         oracle.rrtmg_sw(c, icld=2, clouds=cl)
     with pytest.raises(RuntimeError, match="rc=3"):
@@ -104,3 +107,35 @@ def test_ecmwf_aerosol_types(oracle, cols):
         scale = max(np.abs(ten[k]).max(), 1.0)
         assert np.max(np.abs(six[k] - ten[k])) < 1e-12 * scale, k
     assert (six["swdflx"][cols.coszen > 0.1, 0] < ref["swdflx"][cols.coszen > 0.1, 0]).all()
+
+
+def test_cldprop_sw_parameterisations(oracle, cols):
+    """inflgsw = 2: a pure liquid cloud reproduces inflgsw = 0 fed with the Hu-Stamnes properties read off the table at an
+    integer radius (extinction x path, ssa, g, forward fraction g^2); the Fortran stops come back as return codes."""
+    shp = (cols.ncol, cols.nlay)
+    cf = np.zeros(shp, order="F"); cf[:, 4:7] = 1.0
+    lwp = np.asfortranarray(np.full(shp, 25.0) * cf)
+    cl = dict(cldfr=cf, cicewp=np.zeros(shp, order="F"), cliqwp=lwp, reice=np.full(shp, 40.0, order="F"),
+              reliq=np.full(shp, 11.5, order="F"))                       # index = int(11.5 - 1.5) = 10, fint = 0
+    a = oracle.rrtmg_sw(cols, icld=2, inflgsw=2, iceflgsw=2, liqflgsw=1, clouds=cl)
+    ext = oracle.table("swcld.extliq1").reshape(58, 14, order="F")[9]
+    ssa = oracle.table("swcld.ssaliq1").reshape(58, 14, order="F")[9]
+    asy = oracle.table("swcld.asyliq1").reshape(58, 14, order="F")[9]
+    full = (14,) + shp
+    b = oracle.rrtmg_sw(cols, icld=2, clouds=dict(
+        cldfr=cf, taucld=np.asfortranarray(ext[:, None, None] * lwp[None]), ssacld=np.asfortranarray(np.broadcast_to(ssa[:, None, None], full)),
+        asmcld=np.asfortranarray(np.broadcast_to(asy[:, None, None], full)),
+        fsfcld=np.asfortranarray(np.broadcast_to((asy * asy)[:, None, None], full))))
+    for k in SW:
+        scale = max(np.abs(b[k]).max(), 1.0)
+        assert np.max(np.abs(a[k] - b[k])) < 1e-9 * scale, k
+    d0, d1 = np.flatnonzero(cols.coszen > 0.1)[:2]                        # night columns never reach cldprop_sw
+    cl["cicewp"][d0, 5] = 3.0
+    cl["reice"][d0, 5] = 4.0
+    for ice, rc in ((1, 11), (2, 11), (3, 12)):
+        with pytest.raises(RuntimeError, match=f"rc={rc}"):
+            oracle.rrtmg_sw(cols, icld=2, inflgsw=2, iceflgsw=ice, liqflgsw=1, clouds=cl)
+    cl["reice"][d0, 5] = 40.0
+    cl["reliq"][d1, 4] = 61.0
+    with pytest.raises(RuntimeError, match="rc=13"):
+        oracle.rrtmg_sw(cols, icld=2, inflgsw=2, iceflgsw=2, liqflgsw=1, clouds=cl)
