@@ -22,6 +22,16 @@ a3 = (c.ncol, c.nlay, 14)
 aer = dict(tauaer=np.asfortranarray(rng.uniform(0, 0.3, a3)), ssaaer=np.asfortranarray(rng.uniform(0.6, 0.999, a3)), asmaer=np.asfortranarray(rng.uniform(0.3, 0.8, a3)))
 rrtmg.sw_from_columns(c, icld=2, iaer=10, clouds=swcl, aerosols=aer)
 rrtmg.sw_from_columns(c, iaer=10, aerosols=aer)
+shp2 = (c.ncol, c.nlay)
+wcl = dict(cldfr=np.asfortranarray((rng.uniform(size=shp2) < 0.3).astype(float)),
+           cicewp=np.asfortranarray(rng.uniform(0, 30, shp2)), cliqwp=np.asfortranarray(rng.uniform(0, 60, shp2)),
+           reice=np.asfortranarray(rng.uniform(14, 120, shp2)), reliq=np.asfortranarray(rng.uniform(3, 50, shp2)))
+for ice in (1, 2, 3):
+    rrtmg.sw_from_columns(c, icld=2, inflgsw=2, iceflgsw=ice, liqflgsw=1, clouds=wcl)
+for infl, ice, liq in ((1, 0, 0), (2, 0, 0), (2, 1, 1), (2, 2, 1), (2, 3, 1)):
+    rrtmg.lw_from_columns(c, icld=2, inflglw=infl, iceflglw=ice, liqflglw=liq, clouds=wcl)
+aer6 = dict(ecaer=np.asfortranarray(rng.uniform(0, 0.05, (c.ncol, c.nlay, 6))))
+rrtmg.sw_from_columns(c, iaer=6, aerosols=aer6)
 c80 = make_columns("T341L80", nlon=32, nlat=2, night=True)
 rrtmg.lw_from_columns(c80); rrtmg.sw_from_columns(c80)
 from mima_b200 import rrtm_radiation as rr
