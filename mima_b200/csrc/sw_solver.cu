@@ -13,7 +13,17 @@
 //   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
 //        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
 //        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
-// The five layer properties (ref, refd, tra, trad, dbt) are needed by both sweeps.  STORE = true keeps them
+// Default (OPT bit 3, "flux propagation"): the up sweep also keeps, per layer, the three coefficients of
+//   D_below = fa * D_above + fb * S_above,  S_below = dbt * S_above      (D diffuse, S direct downward flux)
+// with fa = trad * zreflect, fb = ((tra - dbt) + refd * rup * dbt) * zreflect and zreflect = 1/(1 - refd * rupd)
+// the factor the bottom-up recurrence has just computed (interaction principle at the lower boundary of the
+// layer, given the reflectances rup, rupd of everything below).  The upward flux at a level is rupd*D + rup*S.
+// This is algebraically vrtqdr's result ((tdbt*rup + (tdn - tdbt)*rupd)/(1 - rdnd*rupd) and its pfd companion)
+// without the top-down (ztdn, prdnd) recurrence, so the down sweep needs no layer property, no reciprocal and no
+// table look-up: five stored values and six FP64 operations per cell instead of reftra again (~100).  Agreement
+// with the oracle's literal formulas: 1e-13 relative (tests assert 1e-9).
+// The other two modes evaluate the reference's top-down recurrence literally and need the five layer properties
+// (ref, refd, tra, trad, dbt) in both sweeps.  STORE = true keeps them
 // in per-thread local arrays (40 B written + 40 B read per cell, which at full occupancy streams through
 // HBM); STORE = false evaluates reftra again in the down sweep from the staged (taur, taug) pair
 // (16 B re-read per cell, ~90 more FP64 operations).  Which is faster depends on the HBM/FP64 balance and
@@ -153,6 +163,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
 {
     constexpr bool R1 = (OPT & 1) != 0;
     constexpr bool WR = (OPT & 4) != 0;            // warp-local g-sums (no block barrier inside the sweep)
+    constexpr bool FP = (OPT & 8) != 0;            // flux propagation: the down sweep needs no layer properties
+    static_assert(!(FP && STORE) && (!FP || WR), "flux propagation keeps its own per-layer coefficients and uses the warp-local sums");
     constexpr int NB = (WR || (OPT & 2)) ? 4 : 8;  // levels per reduction batch
     constexpr int NR = NB * 2 * SV_COLS;           // tile rows (block-level reduction)
     __shared__ double s_tile[WR ? SV_WARPS * 8 * SV_WS : NR * SV_S];
@@ -187,6 +199,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     constexpr int LP = STORE ? LMAX : 1;
     double zref[LP], zrefd[LP], ztra[LP], ztrad[LP], zdbt[LP];
     double zrup[LMAX + 1], zrupd[LMAX + 1];
+    constexpr int LF = FP ? LMAX : 1;
+    double zfa[LF], zfb[LF], zfs[LF];               // FP: D_below = zfa*D_above + zfb*S_above, S_below = zfs*S_above
     const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
     // Rayleigh optical depth: colmol(col, lay) * rayl(g) (same product as taumol_sw's `taur = colmol * rayl`);
     // band 24 reads its materialised value from taur24 (then raylg = 1).  One load per level either way.
@@ -232,6 +246,11 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                     const double zreflect = rcp_sel<R1>(1. - rupd * refd);
                     const double rup_n = ref + (trad * ((tra - dbt) * rupd + dbt * rup)) * zreflect;
                     const double rupd_n = refd + trad * trad * rupd * zreflect;
+                    if (FP) {
+                        zfa[l] = trad * zreflect;
+                        zfb[l] = ((tra - dbt) + refd * (rup * dbt)) * zreflect;
+                        zfs[l] = dbt;
+                    }
                     rup = rup_n;
                     rupd = rupd_n;
                     zrup[l + 1] = rup;
@@ -244,8 +263,60 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     // ---- down sweep: ztdn, prdnd, cumulative direct beam; fluxes at every level (:125-150)
     double ztdn = 1., zrdnd = 0., ztdbt = 1.;
     double trn = 0., tgn = 0.;
-    if (active && !STORE) { trn = __ldg(taur + (klev - 1) * trs) * raylg; tgn = __ldcs(taug + (size_t)(klev - 1) * NGPTSW); }
-    for (int k = 0; k <= klev; ++k) {
+    if (active && !STORE && !FP) { trn = __ldg(taur + (klev - 1) * trs) * raylg; tgn = __ldcs(taug + (size_t)(klev - 1) * NGPTSW); }
+    if (FP) {
+        // Flux propagation (OPT bit 3).  With zreflect = 1/(1 - refd*rupd(below)) of the up sweep, the diffuse and
+        // direct downward fluxes for unit incidence obey D_below = zfa*D_above + zfb*S_above, S_below = dbt*S_above
+        // (interaction principle at the lower boundary of the layer), and the upward flux is rupd*D + rup*S:
+        // algebraically the vrtqdr result (:125-150) without the top-down (ztdn, prdnd) recurrence, so the down
+        // sweep needs no layer property -- five stored values and six FP64 operations per cell.  The loads of a
+        // batch of four levels are issued together.
+        double fD = 0., fS = 1.;
+        for (int k0 = 0; k0 <= klev; k0 += 4) {
+            double ru[4], rud[4], fa[4], fb[4], fs[4];
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = max(klev - k0 - j, 0), l = max(s - 1, 0);
+                    ru[j] = zrup[s]; rud[j] = zrupd[s];
+                    fa[j] = zfa[l]; fb[j] = zfb[l]; fs[j] = zfs[l];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = klev - k0 - j;
+                double pfu = 0., pfd = 0.;
+                if (active && s >= 0) {
+                    pfu = zincflx * fma(rud[j], fD, ru[j] * fS);
+                    pfd = zincflx * (fD + fS);
+                    if (s > 0) {
+                        fD = fma(fa[j], fD, fb[j] * fS);
+                        fS = fs[j] * fS;
+                    }
+                }
+                wt[(2 * j) * SV_WS] = pfu;
+                wt[(2 * j + 1) * SV_WS] = pfd;
+            }
+            {
+                const int k = min(k0 + 3, klev);
+                __syncwarp();
+                const int row = lane >> 2, q = lane & 3, half = q >> 1;
+                const double *src = s_tile + (wid * 8 + row) * SV_WS + 17 * half + 8 * (q & 1);
+                double acc = src[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) acc += src[j];
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                const int kk = k0 + (row >> 1);
+                if ((q & 1) == 0 && kk <= k) {
+                    const int hw = 2 * wid + half;                   // half-warp of the block: 0..13
+                    const int c = hw / SV_HPC, i = hw - c * SV_HPC;
+                    s_part[((c * SV_HPC + i) * 2 + (row & 1)) * (LMAX + 1) + (klev - kk)] = acc;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    for (int k = FP ? klev + 1 : 0; k <= klev; ++k) {
         const int s = klev - k;            // level counted from the surface
         const int slot = k & (NB - 1);
         if (active) {
@@ -615,10 +686,12 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
 template <int LMAX>
 static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    // variant 1 (default): one-Newton reciprocals + warp-local g-sums (OPT 5); 0: the first version of the kernel (OPT 0)
+    // variant 2 (default): flux propagation in the down sweep + one-Newton reciprocals + warp-local g-sums (OPT 13);
+    // 1: reftra recomputed in the down sweep (OPT 5); 0: the first version of the kernel (OPT 0)
     if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 0) launch<LMAX, false, 0>(t, in, out, w, s);
-    else launch<LMAX, false, 5>(t, in, out, w, s);
+    else if (g_tune.sw_solver_variant == 1) launch<LMAX, false, 5>(t, in, out, w, s);
+    else launch<LMAX, false, 13>(t, in, out, w, s);
 }
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
