@@ -71,13 +71,13 @@ int main(int argc, char **argv)
                        out[6], out[7], out[8], out[9], out[10], out[11], NULL, NULL);
     if (rc) die("rrtmg_b200_lw", rc);
 
-    /* error path: a call the library must refuse (water-path cloud optics) */
+    /* error path: a call the library must refuse (water-path cloud optics without the water-path arrays) */
     icld = 2;
     rc = rrtmg_b200_lw(ncol, nlay, &icld, 0, play, plev, tlay, tlev, tsfc, h2o, o3, co2, NULL, NULL, NULL,
                        NULL, NULL, NULL, NULL, NULL,
                        2, 0, 0, tlay, tlay, NULL, NULL, NULL, NULL, NULL,
                        out[6], out[7], out[8], out[9], out[10], out[11], NULL, NULL);
-    if (rc != RRTMG_B200_ERR_UNSUPPORTED) { fprintf(stderr, "c_client: expected ERR_UNSUPPORTED, got %d\n", rc); return 3; }
+    if (rc != RRTMG_B200_ERR_BAD_ARGUMENT) { fprintf(stderr, "c_client: expected ERR_BAD_ARGUMENT, got %d\n", rc); return 3; }
 
     f = fopen(argv[3], "wb");
     if (!f) { perror(argv[3]); return 2; }

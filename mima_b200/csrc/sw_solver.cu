@@ -13,7 +13,9 @@
 //   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
 //        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
 //        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
-// Default (OPT bit 3, "flux propagation"): the up sweep also keeps, per layer, the three coefficients of
+// Default (OPT bit 4, "top-down first"; described at its code below): the first sweep is the reference's top-down
+// recurrence fused with reftra, the second a two-term upward flux recurrence on three stored values per cell.
+// OPT bit 3 ("flux propagation", bottom-up first): the up sweep also keeps, per layer, the three coefficients of
 //   D_below = fa * D_above + fb * S_above,  S_below = dbt * S_above      (D diffuse, S direct downward flux)
 // with fa = trad * zreflect, fb = ((tra - dbt) + refd * rup * dbt) * zreflect and zreflect = 1/(1 - refd * rupd)
 // the factor the bottom-up recurrence has just computed (interaction principle at the lower boundary of the
@@ -164,7 +166,9 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     constexpr bool R1 = (OPT & 1) != 0;
     constexpr bool WR = (OPT & 4) != 0;            // warp-local g-sums (no block barrier inside the sweep)
     constexpr bool FP = (OPT & 8) != 0;            // flux propagation: the down sweep needs no layer properties
+    constexpr bool F2 = (OPT & 16) != 0;           // top-down first: three stored values per cell (see below)
     static_assert(!(FP && STORE) && (!FP || WR), "flux propagation keeps its own per-layer coefficients and uses the warp-local sums");
+    static_assert(!(F2 && (STORE || FP)) && (!F2 || WR), "the top-down-first mode is a mode of its own");
     constexpr int NB = (WR || (OPT & 2)) ? 4 : 8;  // levels per reduction batch
     constexpr int NR = NB * 2 * SV_COLS;           // tile rows (block-level reduction)
     __shared__ double s_tile[WR ? SV_WARPS * 8 * SV_WS : NR * SV_S];
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     constexpr int LP = STORE ? LMAX : 1;
     double zref[LP], zrefd[LP], ztra[LP], ztrad[LP], zdbt[LP];
     double zrup[LMAX + 1], zrupd[LMAX + 1];
+    constexpr int L2A = F2 ? LMAX : 1;
+    double zp[L2A], zq[L2A], zr[L2A + 1];           // F2: u_above = zp*u_below + zq; rdnd per level
     constexpr int LF = FP ? LMAX : 1;
     double zfa[LF], zfb[LF], zfs[LF];               // FP: D_below = zfa*D_above + zfb*S_above, S_below = zfs*S_above
     const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
@@ -213,7 +219,119 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
 
     // ---- up sweep: reftra + vrtqdr bottom -> top (:103-121); the loads of the next layer group are issued
     //      before the arithmetic of the current one
-    if (active) {
+    if (F2) {
+        // ---- Top-down first (OPT bit 4).  Pass 1 runs vrtqdr's top-down recurrence (:125-140) fused with reftra; at
+        // the upper boundary a of a layer the direct beam S_a = tdbt_a and the diffuse flux of the atmosphere above
+        // over a black lower half-space E_a = tdn_a - tdbt_a are then known numbers, and with the diffuse downward
+        // flux D_a = E_a + rdnd_a*U_a the layer equation U_a = ref*S_a + refd*D_a + trad*U_b becomes
+        //     U_a = zp*U_b + zq,  zp = trad*zreflect,  zq = (ref*tdbt_a + refd*(tdn_a - tdbt_a))*zreflect,
+        // zreflect = 1/(1 - refd*rdnd_a) being the factor the top-down recurrence computes anyway.  At the surface
+        // U_0 = (albp*tdbt_0 + albd*(tdn_0 - tdbt_0))/(1 - albd*rdnd_0) (= the reference's pfu there), and the total
+        // downward flux is tdn_a + rdnd_a*U_a.  The sum over g of incflx*tdn is taken in pass 1, so pass 2 (bottom-up)
+        // reads three stored values per cell (zp, zq scaled by the incident flux, rdnd) and does three FP64
+        // operations: algebraically vrtqdr's fluxes (:144-150), no second reftra, 24 B per cell kept.
+        auto warp_rows = [&](auto store) {
+            // lanes 4r..4r+3 add up row r of the warp tile (see the classic sweep below); store(row, half-warp, sum)
+            __syncwarp();
+            const int row = lane >> 2, q = lane & 3, half = q >> 1;
+            const double *src = s_tile + (wid * 8 + row) * SV_WS + 17 * half + 8 * (q & 1);
+            double acc = src[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) acc += src[j];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if ((q & 1) == 0) store(row, 2 * wid + half, acc);
+            __syncwarp();
+        };
+        double tdn = 1., rdnd = 0., tdbt = 1., u = 0.;
+        double trn[SV_U], tgn[SV_U];
+#pragma unroll
+        for (int j = 0; j < SV_U; ++j) {
+            const int l = max(klev - 1 - j, 0);
+            trn[j] = active ? __ldg(taur + l * trs) * raylg : 0.;
+            tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
+        }
+        for (int kg = 0; kg <= klev; kg += SV_U) {
+            double tr[SV_U], tg[SV_U];
+#pragma unroll
+            for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+            if (active && kg + SV_U < klev) {
+#pragma unroll
+                for (int j = 0; j < SV_U; ++j) {
+                    const int l = max(klev - 1 - (kg + SV_U + j), 0);
+                    trn[j] = __ldg(taur + l * trs) * raylg;
+                    tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SV_U; ++j) {
+                const int k = kg + j, s = klev - k;      // level s counted from the surface, layer s - 1 below it
+                double row = 0.;
+                if (active && s >= 0) {
+                    row = zincflx * tdn;
+                    zr[s] = rdnd;
+                    const double dif = tdn - tdbt;
+                    if (s > 0) {
+                        double ref, refd, tra, trad, dbt;
+                        sw_reftra<R1>(tb, bpade, mu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
+                        const double zreflect = rcp_sel<R1>(1. - refd * rdnd);
+                        zp[s - 1] = trad * zreflect;
+                        zq[s - 1] = zincflx * ((ref * tdbt + refd * dif) * zreflect);
+                        const double tdn_n = tdbt * tra + (trad * (dif + tdbt * ref * rdnd)) * zreflect;
+                        const double rdnd_n = refd + trad * trad * rdnd * zreflect;
+                        tdbt = dbt * tdbt;
+                        tdn = tdn_n;
+                        rdnd = rdnd_n;
+                    } else {
+                        u = zincflx * ((albp * tdbt + albd * dif) * rcp_sel<R1>(1. - albd * rdnd));
+                    }
+                }
+                wt[(k & 7) * SV_WS] = row;
+            }
+            const int kl = min(kg + SV_U - 1, klev);
+            if ((kl & 7) == 7 || kl == klev) {
+                const int kb = kl & ~7;
+                warp_rows([&](int row, int hw, double acc) {
+                    if (kb + row <= kl) s_part[(hw * 2 + 1) * (LMAX + 1) + (klev - kb - row)] = acc;
+                });
+            }
+        }
+        // pass 2, bottom-up: u = incflx * U; the loads of F2_G levels are issued together, sums in batches of four
+        constexpr int F2_G = 8;
+        for (int s0 = 0; s0 <= klev; s0 += F2_G) {
+            double p[F2_G], q[F2_G], r[F2_G];
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < F2_G; ++j) {
+                    const int sj = min(s0 + j, klev), l = max(sj - 1, 0);
+                    p[j] = zp[l]; q[j] = zq[l]; r[j] = zr[sj];
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < F2_G; h += 4) {
+                if (s0 + h <= klev) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sj = s0 + h + j;
+                        double pu = 0., pd = 0.;
+                        if (active && sj <= klev) {
+                            if (sj > 0) u = fma(p[h + j], u, q[h + j]);
+                            pu = u;
+                            pd = r[h + j] * u;
+                        }
+                        wt[(2 * j) * SV_WS] = pu;
+                        wt[(2 * j + 1) * SV_WS] = pd;
+                    }
+                    warp_rows([&](int row, int hw, double acc) {
+                        const int lev = s0 + h + (row >> 1);
+                        if (lev <= klev) {
+                            double *dst = s_part + (hw * 2 + (row & 1)) * (LMAX + 1) + lev;
+                            *dst = (row & 1) ? *dst + acc : acc;
+                        }
+                    });
+                }
+            }
+        }
+    } else if (active) {
         double rup = albp, rupd = albd;      // zrup(klev+1) = palbp, zrupd(klev+1) = palbd
         zrup[0] = rup;
         zrupd[0] = rupd;
@@ -316,7 +434,7 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
             }
         }
     }
-    for (int k = FP ? klev + 1 : 0; k <= klev; ++k) {
+    for (int k = (FP || F2) ? klev + 1 : 0; k <= klev; ++k) {
         const int s = klev - k;            // level counted from the surface
         const int slot = k & (NB - 1);
         if (active) {
@@ -686,12 +804,14 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
 template <int LMAX>
 static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    // variant 2 (default): flux propagation in the down sweep + one-Newton reciprocals + warp-local g-sums (OPT 13);
-    // 1: reftra recomputed in the down sweep (OPT 5); 0: the first version of the kernel (OPT 0)
+    // variant 3 (default): top-down first, three stored values per cell (OPT 21); 2: bottom-up first, five stored values
+    // (OPT 13); 1: reftra recomputed in the second sweep, the reference's recurrences literally (OPT 5); 0: the first
+    // version of the kernel (OPT 0).  All use one-Newton reciprocals + warp-local g-sums except 0.
     if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 0) launch<LMAX, false, 0>(t, in, out, w, s);
     else if (g_tune.sw_solver_variant == 1) launch<LMAX, false, 5>(t, in, out, w, s);
-    else launch<LMAX, false, 13>(t, in, out, w, s);
+    else if (g_tune.sw_solver_variant == 2) launch<LMAX, false, 13>(t, in, out, w, s);
+    else launch<LMAX, false, 21>(t, in, out, w, s);
 }
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
