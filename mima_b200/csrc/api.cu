@@ -565,6 +565,7 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool gener
     w.taur24 = c.take<double>(np * 8);
     w.taur = fields ? c.take<double>(np * NGPTSW) : nullptr;      // expanded from rdesc (test hook)
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
+    w.part = c.take<double>((size_t)nc * (NGPTSW / 16) * 2 * (nlay + 1));
     w.opt = general ? c.take<double>(np * 14 * 6) : nullptr;
     w.clfr = general ? c.take<double>(np) : nullptr;
     w.err = general ? (int *)G.sw_err.p : nullptr;
@@ -879,7 +880,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 3, 2, 4};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
+Tuning g_tune = {0, 0, 0, 4, 2, 4};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;

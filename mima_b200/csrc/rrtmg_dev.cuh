@@ -213,6 +213,7 @@ struct SwWork {
     double *taur24;           // [col][lay][8]: taur of band 24, whose Rayleigh coefficient depends on the cell
     double *taur;             // [col][lay][112], expanded from rdesc only for the stage-capture test hook
     double *sfluxzen;         // [col][112]
+    double *part;             // [col][7 half-warps][up, down][lev]: g-point partial sums (sw_solver_warp -> sw_finish)
     // general path (icld >= 1 or iaer = 10): per (column, layer, band) {tauc, omgc, asyc (delta-M scaled, cldprop_sw
     // inflag = 0), taua, omga, asya} and the layer cloud fraction; err[0]: bit 0 = partial cloud found, err[1]: number of
     // the cldprop_sw `stop` some cell ran into

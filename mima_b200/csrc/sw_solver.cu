@@ -196,8 +196,9 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
 
     // band albedos (rad.nomcica:565-578): bands 16-24 and 29 near-IR, 25-28 UV/visible
     const bool uvvis = band >= 9 && band <= 12;
-    const double albd = uvvis ? in.asdif[colr] : in.aldif[colr];   // palbd: diffuse
-    const double albp = uvvis ? in.asdir[colr] : in.aldir[colr];   // palbp: direct
+    // (the top-down-first mode needs them after its first sweep only and loads them there)
+    const double albd = F2 ? 0. : (uvvis ? in.asdif[colr] : in.aldif[colr]);   // palbd: diffuse
+    const double albp = F2 ? 0. : (uvvis ? in.asdir[colr] : in.aldir[colr]);   // palbp: direct
 
     // per-thread state, index = layer / level counted from the surface
     constexpr int LP = STORE ? LMAX : 1;
@@ -242,25 +243,19 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
             if ((q & 1) == 0) store(row, 2 * wid + half, acc);
             __syncwarp();
         };
-        double tdn = 1., rdnd = 0., tdbt = 1., u = 0.;
-        double trn[SV_U], tgn[SV_U];
+        // The gas optical depths are loaded one group of SV_U layers ahead and not touched until their group comes
+        // up; the Rayleigh term (colmol: one value per layer and column, L1-resident) is loaded where it is used.
+        double tdn = 1., rdnd = 0., tdbt = 1.;
+        double tgn[SV_U];
 #pragma unroll
-        for (int j = 0; j < SV_U; ++j) {
-            const int l = max(klev - 1 - j, 0);
-            trn[j] = active ? __ldg(taur + l * trs) * raylg : 0.;
-            tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
-        }
+        for (int j = 0; j < SV_U; ++j) tgn[j] = __ldcs(taug + (size_t)max(klev - 1 - j, 0) * NGPTSW);
         for (int kg = 0; kg <= klev; kg += SV_U) {
-            double tr[SV_U], tg[SV_U];
+            double tg[SV_U];
 #pragma unroll
-            for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
-            if (active && kg + SV_U < klev) {
+            for (int j = 0; j < SV_U; ++j) tg[j] = tgn[j];
+            if (kg + SV_U < klev) {
 #pragma unroll
-                for (int j = 0; j < SV_U; ++j) {
-                    const int l = max(klev - 1 - (kg + SV_U + j), 0);
-                    trn[j] = __ldg(taur + l * trs) * raylg;
-                    tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
-                }
+                for (int j = 0; j < SV_U; ++j) tgn[j] = __ldcs(taug + (size_t)max(klev - 1 - (kg + SV_U + j), 0) * NGPTSW);
             }
 #pragma unroll
             for (int j = 0; j < SV_U; ++j) {
@@ -272,7 +267,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                     const double dif = tdn - tdbt;
                     if (s > 0) {
                         double ref, refd, tra, trad, dbt;
-                        sw_reftra<R1>(tb, bpade, mu0, rmu0, tr[j], tg[j], ref, refd, tra, trad, dbt);
+                        const double trj = __ldg(taur + (s - 1) * trs) * raylg;
+                        sw_reftra<R1>(tb, bpade, mu0, rmu0, trj, tg[j], ref, refd, tra, trad, dbt);
                         const double zreflect = rcp_sel<R1>(1. - refd * rdnd);
                         zp[s - 1] = trad * zreflect;
                         zq[s - 1] = zincflx * ((ref * tdbt + refd * dif) * zreflect);
@@ -281,8 +277,6 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                         tdbt = dbt * tdbt;
                         tdn = tdn_n;
                         rdnd = rdnd_n;
-                    } else {
-                        u = zincflx * ((albp * tdbt + albd * dif) * rcp_sel<R1>(1. - albd * rdnd));
                     }
                 }
                 wt[(k & 7) * SV_WS] = row;
@@ -294,6 +288,13 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
                     if (kb + row <= kl) s_part[(hw * 2 + 1) * (LMAX + 1) + (klev - kb - row)] = acc;
                 });
             }
+        }
+        // surface (level 0): the state of pass 1 is now that of the lowest level
+        double u = 0.;
+        if (active) {
+            const double sd = uvvis ? in.asdif[colr] : in.aldif[colr];   // palbd: diffuse
+            const double sp = uvvis ? in.asdir[colr] : in.aldir[colr];   // palbp: direct
+            u = zincflx * ((sp * tdbt + sd * (tdn - tdbt)) * rcp_sel<R1>(1. - sd * rdnd));
         }
         // pass 2, bottom-up: u = incflx * U; the loads of F2_G levels are issued together, sums in batches of four
         constexpr int F2_G = 8;
@@ -532,6 +533,205 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
             if (active && lay < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
                 const double pdp = in.plev[col + (size_t)lay * in.ld] - in.plev[col + (size_t)(lay + 1) * in.ld];
                 h = ((s_dn[cb][lay + 1] - s_up[cb][lay + 1]) - (s_dn[cb][lay] - s_up[cb][lay])) * (c_ss.heatfac / pdp);
+            }
+            out.hr[o] = h;
+            out.hrc[o] = h;
+        }
+    }
+}
+
+
+// =====================================================================================================
+// The default clear-sky solver: the top-down-first scheme of sw_solver_kernel (OPT bit 4, derivation there) with one
+// warp per block.  Thread <-> (column, g-point) in the flat order col * 112 + g, so a warp holds two half-warps of
+// 16 g-points, each inside one column (112 = 7 x 16).  Registers and shared memory of a block are only released
+// when its slowest warp is done, and the warps of a column differ by +-20 % in instructions (bands differ in how
+// their lanes split between the branches of reftra): with 7-warp blocks 18 % of the stall samples sat at the final
+// block barrier.  One-warp blocks retire individually.  The half-warp sums over g go to w.part
+// ([col][half-warp][up, down][lev]); sw_finish_kernel adds the seven partials of a column in the fixed order the
+// block-level kernel used (bitwise the same sums), writes the fluxes and the heating rates.
+// =====================================================================================================
+// WPB: resident one-warp blocks per SM the register allocation aims at (28 -> 72 registers, 32 -> 64)
+template <int LMAX, int WPB>
+__global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwIn in, SwWork w)
+{
+    constexpr bool R1 = true;
+    __shared__ double s_tile[8 * SV_WS];
+    __shared__ double s_dn0[2][LMAX + 1];
+    const int lane = threadIdx.x;
+    double *wt = s_tile + lane + (lane >> 4);
+    const int klev = w.nlay;
+    const long long t = (long long)blockIdx.x * 32 + lane;
+    const int col = (int)(t / NGPTSW);
+    const int g = (int)(t - (long long)col * NGPTSW);
+    const bool incol = col < w.nc;
+    const double prmu0 = incol ? in.coszen[col] : 0.0;
+    const bool active = incol && !(prmu0 < ZEPZEN);      // night columns: zeros (rad.nomcica:502-510)
+    const int colr = incol ? col : 0;
+    const int band = c_ss.ngb[g];
+    const double bpade = c_ss.bpade;
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
+    const double mu0 = active ? prmu0 : 1.0;
+    const double rmu0 = 1. / mu0;
+    const bool uvvis = band >= 9 && band <= 12;          // bands 25-28 take the UV/visible albedos (rad.nomcica:565-578)
+    double zp[LMAX], zq[LMAX], zr[LMAX + 1];             // u_above = zp*u_below + zq; rdnd per level
+    const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
+    const bool b24 = band == 8;
+    const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
+    const double *__restrict__ taur = b24 ? w.taur24 + (size_t)colr * klev * 8 + (g - c_ss.g0[band])
+                                          : w.colmol + (size_t)colr * klev;
+    const int trs = b24 ? 8 : 1;
+    const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)colr * NGPTSW + g] * prmu0 : 0.0;
+
+    auto warp_rows = [&](auto store) {
+        // lanes 4r..4r+3 add up row r of the tile: two lanes per half-warp, eight values each, then one exchange
+        __syncwarp();
+        const int row = lane >> 2, q = lane & 3, half = q >> 1;
+        const double *src = s_tile + row * SV_WS + 17 * half + 8 * (q & 1);
+        double acc = src[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc += src[j];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if ((q & 1) == 0) store(row, half, acc);
+        __syncwarp();
+    };
+
+    // ---- pass 1, top -> surface: reftra + vrtqdr's top-down recurrence; sum over g of incflx * tdn
+    double tdn = 1., rdnd = 0., tdbt = 1.;
+    double trn[SV_U], tgn[SV_U];
+#pragma unroll
+    for (int j = 0; j < SV_U; ++j) {
+        const int l = max(klev - 1 - j, 0);
+        trn[j] = __ldg(taur + l * trs);
+        tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+    }
+    for (int kg = 0; kg <= klev; kg += SV_U) {
+        double tr[SV_U], tg[SV_U];
+#pragma unroll
+        for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+        if (kg + SV_U < klev) {
+#pragma unroll
+            for (int j = 0; j < SV_U; ++j) {
+                const int l = max(klev - 1 - (kg + SV_U + j), 0);
+                trn[j] = __ldg(taur + l * trs);
+                tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SV_U; ++j) {
+            const int k = kg + j, s = klev - k;          // level s counted from the surface, layer s - 1 below it
+            double row = 0.;
+            if (active && s >= 0) {
+                row = zincflx * tdn;
+                zr[s] = rdnd;
+                if (s > 0) {
+                    const double dif = tdn - tdbt;
+                    double ref, refd, tra, trad, dbt;
+                    sw_reftra<R1>(tb, bpade, mu0, rmu0, tr[j] * raylg, tg[j], ref, refd, tra, trad, dbt);
+                    const double zreflect = rcp_sel<R1>(1. - refd * rdnd);
+                    zp[s - 1] = trad * zreflect;
+                    zq[s - 1] = zincflx * ((ref * tdbt + refd * dif) * zreflect);
+                    const double tdn_n = tdbt * tra + (trad * (dif + tdbt * ref * rdnd)) * zreflect;
+                    const double rdnd_n = refd + trad * trad * rdnd * zreflect;
+                    tdbt = dbt * tdbt;
+                    tdn = tdn_n;
+                    rdnd = rdnd_n;
+                }
+            }
+            wt[(k & 7) * SV_WS] = row;
+        }
+        const int kl = min(kg + SV_U - 1, klev);
+        if ((kl & 7) == 7 || kl == klev) {
+            const int kb = kl & ~7;
+            warp_rows([&](int row, int half, double acc) {
+                if (kb + row <= kl) s_dn0[half][klev - kb - row] = acc;
+            });
+        }
+    }
+    // surface (level 0): upward flux from the albedos (the reference's pfu there)
+    double u = 0.;
+    if (active) {
+        const double sd = uvvis ? in.asdif[colr] : in.aldif[colr];   // palbd: diffuse
+        const double sp = uvvis ? in.asdir[colr] : in.aldir[colr];   // palbp: direct
+        u = zincflx * ((sp * tdbt + sd * (tdn - tdbt)) * rcp_sel<R1>(1. - sd * rdnd));
+    }
+    // ---- pass 2, surface -> top: u = incflx * U; loads of eight levels issued together, sums in batches of four
+    const long long hw0 = (long long)blockIdx.x * 2;                 // first half-warp of this warp, = col * 7 + i
+    const long long nhw = (long long)w.nc * SV_HPC;
+    constexpr int G8 = 8;
+    for (int s0 = 0; s0 <= klev; s0 += G8) {
+        double p[G8], q[G8], r[G8];
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < G8; ++j) {
+                const int sj = min(s0 + j, klev), l = max(sj - 1, 0);
+                p[j] = zp[l]; q[j] = zq[l]; r[j] = zr[sj];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < G8; h += 4) {
+            if (s0 + h <= klev) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sj = s0 + h + j;
+                    double pu = 0., pd = 0.;
+                    if (active && sj <= klev) {
+                        if (sj > 0) u = fma(p[h + j], u, q[h + j]);
+                        pu = u;
+                        pd = r[h + j] * u;
+                    }
+                    wt[(2 * j) * SV_WS] = pu;
+                    wt[(2 * j + 1) * SV_WS] = pd;
+                }
+                warp_rows([&](int row, int half, double acc) {
+                    const int lev = s0 + h + (row >> 1);
+                    if (lev <= klev && hw0 + half < nhw) {
+                        double *dst = w.part + ((hw0 + half) * 2 + (row & 1)) * (klev + 1) + lev;
+                        *dst = (row & 1) ? s_dn0[half][lev] + acc : acc;
+                    }
+                });
+            }
+        }
+    }
+}
+
+// Adds the seven half-warp partials of a column and level, writes the fluxes and heating rates
+// (rrtmg_sw_rad.nomcica.f90:686-727; clear == total for icld = 0).  A block takes TC columns: the partials are read
+// with the level index fastest, the outputs written with the column index fastest (transpose through shared memory).
+template <int LMAX, int TC>
+__global__ void __launch_bounds__(256) sw_finish_kernel(SwIn in, SwOut out, SwWork w)
+{
+    __shared__ double s_u[LMAX + 1][TC + 1], s_d[LMAX + 1][TC + 1];
+    const int klev = w.nlay, nlev = klev + 1;
+    const int c0 = blockIdx.x * TC;
+    for (int i = threadIdx.x; i < TC * nlev; i += 256) {
+        const int c = i / nlev, lev = i - c * nlev;
+        double u = 0.0, d = 0.0;
+        if (c0 + c < w.nc) {
+            const double *src = w.part + (size_t)(c0 + c) * SV_HPC * 2 * nlev + lev;
+#pragma unroll
+            for (int h = 0; h < SV_HPC; ++h) {
+                u += src[(size_t)(2 * h) * nlev];
+                d += src[(size_t)(2 * h + 1) * nlev];
+            }
+        }
+        s_u[lev][c] = u;
+        s_d[lev][c] = d;
+    }
+    __syncthreads();
+    const size_t old = (size_t)out.ld;
+    for (int i = threadIdx.x; i < TC * nlev; i += 256) {
+        const int lev = i / TC, c = i - lev * TC, col = c0 + c;
+        if (col >= w.nc) continue;
+        const double u = s_u[lev][c], d = s_d[lev][c];
+        const size_t o = col + (size_t)lev * old;
+        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = u; out.dflxc[o] = d;
+        if (lev < klev) {
+            double h = 0.0;
+            const bool active = !(in.coszen[col] < ZEPZEN);
+            if (active && lev < klev - 1) {      // MiMA: no heating in the top layer (rad.nomcica:724-726)
+                const double pdp = in.plev[col + (size_t)lev * in.ld] - in.plev[col + (size_t)(lev + 1) * in.ld];
+                h = ((s_d[lev + 1][c] - s_u[lev + 1][c]) - (d - u)) * (c_ss.heatfac / pdp);
             }
             out.hr[o] = h;
             out.hrc[o] = h;
@@ -811,7 +1011,15 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
     if (g_tune.sw_solver_variant == 0) launch<LMAX, false, 0>(t, in, out, w, s);
     else if (g_tune.sw_solver_variant == 1) launch<LMAX, false, 5>(t, in, out, w, s);
     else if (g_tune.sw_solver_variant == 2) launch<LMAX, false, 13>(t, in, out, w, s);
-    else launch<LMAX, false, 21>(t, in, out, w, s);
+    else if (g_tune.sw_solver_variant == 3) launch<LMAX, false, 21>(t, in, out, w, s);
+    else {
+        // variant 4: variant 3 with one warp per block + sw_finish_kernel
+        constexpr int TC = LMAX <= 64 ? 32 : 16;
+        const long long nthr = (long long)w.nc * NGPTSW;
+        if (g_tune.sw_solver_variant == 5) sw_solver_warp_kernel<LMAX, 24><<<(unsigned)((nthr + 31) / 32), 32, 0, s>>>(t, in, w);
+        else sw_solver_warp_kernel<LMAX, 28><<<(unsigned)((nthr + 31) / 32), 32, 0, s>>>(t, in, w);
+        sw_finish_kernel<LMAX, TC><<<(w.nc + TC - 1) / TC, 256, 0, s>>>(in, out, w);
+    }
 }
 
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
@@ -830,7 +1038,7 @@ int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork
     }
     if (w.nlay <= 64) launch_opt<64>(t, in, out, w, s);
     else launch_opt<MAXLAY>(t, in, out, w, s);
-    return 1;
+    return (!g_tune.sw_solver_store && g_tune.sw_solver_variant >= 4) ? 2 : 1;
 }
 
 } // namespace rrtmg
