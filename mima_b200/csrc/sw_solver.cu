@@ -106,12 +106,15 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
     const double zgamma1 = (8. - zw * 5.) * 0.25;
     const double zgamma2 = 3. * zw * 0.25;
     const double zed = zto1 * rmu0;                          // direct-beam optical path
+    // exp(-tau/mu0) is needed by both branches; a warp usually holds lanes of both (two thirds of the warps of the
+    // bench workload enter the conservative branch), so it is looked up once, before the branch
+    double zep2;
+    const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
     if (zw >= zwcrit) {
         // conservative scattering (:162-214)
         const double za1 = zgamma1 * prmu0 - 0.5;
         const double zgt = zgamma1 * zto1;
-        double rcp;
-        const double ze2 = sw_exp(tb, fmin(zed, 500.), bpade, rcp);
+        const double ze2 = zem2;
         const double rg = rcp_fast(1. + zgt);
         ref = (zgt - za1 * (1. - ze2)) * rg;
         tra = 1. - ref;
@@ -137,9 +140,8 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
         const double zt1 = zrp1 * hA;
         const double zt2 = zrm1 * hB;
         const double zt3 = zrk2 * (0.5 + za1 * prmu0);
-        double zep1, zep2;
+        double zep1;
         const double zem1 = sw_exp(tb, fmin(zrk * zto1, 500.), bpade, zep1);
-        const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
         const double zdenr = fma(zr4, zep1, zr5 * zem1);     // = zdent (zt4 = zr4, zt5 = zr5)
         if (zdenr >= -eps && zdenr <= eps) {
             ref = eps;
@@ -1016,8 +1018,7 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
         // variant 4: variant 3 with one warp per block + sw_finish_kernel
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nthr = (long long)w.nc * NGPTSW;
-        if (g_tune.sw_solver_variant == 5) sw_solver_warp_kernel<LMAX, 24><<<(unsigned)((nthr + 31) / 32), 32, 0, s>>>(t, in, w);
-        else sw_solver_warp_kernel<LMAX, 28><<<(unsigned)((nthr + 31) / 32), 32, 0, s>>>(t, in, w);
+        sw_solver_warp_kernel<LMAX, 28><<<(unsigned)((nthr + 31) / 32), 32, 0, s>>>(t, in, w);
         sw_finish_kernel<LMAX, TC><<<(w.nc + TC - 1) / TC, 256, 0, s>>>(in, out, w);
     }
 }

@@ -236,7 +236,7 @@ def test_unsupported_options_fail_loudly(gpu):
 
 @pytest.mark.parametrize("res", ["T85L40", "T170L60"])
 def test_full_size_properties(gpu, res):
-    """BASELINE configs 2 and 3 at full size (32768 x 40, 131072 x 60: four device passes), checked through
+    """BASELINE configs 2 and 3 at full size (32768 x 40, 131072 x 60: two device passes), checked through
     size-independent properties: shard invariance (any split of the batch gives bit-identical columns), heating =
     flux divergence, TOA insolation = S0 cos(z), surface reflection, clear == total."""
     c = make_columns(res)
