@@ -250,12 +250,12 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
         double tdn = 1., rdnd = 0., tdbt = 1.;
         double tgn[SV_U];
 #pragma unroll
-        for (int j = 0; j < SV_U; ++j) tgn[j] = __ldcs(taug + (size_t)max(klev - 1 - j, 0) * NGPTSW);
+        for (int j = 0; j < SV_U; ++j) tgn[j] = active ? __ldcs(taug + (size_t)max(klev - 1 - j, 0) * NGPTSW) : 0.;
         for (int kg = 0; kg <= klev; kg += SV_U) {
             double tg[SV_U];
 #pragma unroll
             for (int j = 0; j < SV_U; ++j) tg[j] = tgn[j];
-            if (kg + SV_U < klev) {
+            if (active && kg + SV_U < klev) {      // night columns have no staged optical depths
 #pragma unroll
                 for (int j = 0; j < SV_U; ++j) tgn[j] = __ldcs(taug + (size_t)max(klev - 1 - (kg + SV_U + j), 0) * NGPTSW);
             }
@@ -604,14 +604,14 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwI
 #pragma unroll
     for (int j = 0; j < SV_U; ++j) {
         const int l = max(klev - 1 - j, 0);
-        trn[j] = __ldg(taur + l * trs);
-        tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+        trn[j] = active ? __ldg(taur + l * trs) : 0.;          // night columns have no staged optical depths
+        tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
     }
     for (int kg = 0; kg <= klev; kg += SV_U) {
         double tr[SV_U], tg[SV_U];
 #pragma unroll
         for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
-        if (kg + SV_U < klev) {
+        if (active && kg + SV_U < klev) {
 #pragma unroll
             for (int j = 0; j < SV_U; ++j) {
                 const int l = max(klev - 1 - (kg + SV_U + j), 0);
