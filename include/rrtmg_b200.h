@@ -180,13 +180,16 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
  * "lw.laytrop","sw.laytrop" (ncol).  Output is column-major with ncol leading, FP64. */
 long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
 
-/* Columns per device pass (0 = automatic).  The working set of one pass is
- * ~ chunk * nlay * 2.6 KB (LW) so that the taumol -> solver staging fields stay L2-resident. */
+/* Columns per device pass (0 = automatic: 65536).  The workspace of one pass is ~ chunk * nlay * 2.5 KB (LW) +
+ * chunk * nlay * 1.8 KB (SW): 17 GB at 65536 columns x 60 layers. */
 int rrtmg_b200_set_chunk(int ncol_per_pass);
 
 /* Generic options: "chunk" (as above), "host_chunk" (columns per pipeline stage of the host-pointer entry points,
- * default 8192: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
- * LW solver otherwise overwrites in place; test hook), "kernel_timing" (see rrtmg_b200_kernel_times). */
+ * default 16384: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
+ * LW solver otherwise overwrites in place; test hook), "kernel_timing" (see rrtmg_b200_kernel_times),
+ * "sw_solver_variant" (clear-sky SW solver: 4 = default, one warp per block, top-down sweep first and a two-term upward
+ * recurrence on three stored values per cell; 3 = the same in 7-warp blocks; 2 = bottom-up first, five stored values;
+ * 1 = the reference's two recurrences literally, reftra evaluated in both sweeps; 0 = first version of the kernel). */
 int rrtmg_b200_set_option(const char *key, long value);
 
 /* With option "kernel_timing" = 1 every kernel launch is bracketed by CUDA events on its stream.  Returns the
