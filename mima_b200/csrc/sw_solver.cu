@@ -6,30 +6,31 @@
 // (tau_a = 0, omega_a = 1, g = 0 => delta scaling is the identity) and the total-sky stream equals the
 // clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
 //
-// Block <-> two columns (2 x 112 g-points = 7 full warps: a half-empty warp would cost the FP64 pipe as much
-// as a full one), thread <-> (column, g-point).  Two sweeps instead of the reference's four loops:
-//   up   (surface -> top): layer R/T (reftra) fused with the bottom-up adding recurrence (vrtqdr :103-121);
-//        keeps rup, rupd per level in a per-thread local array;
-//   down (top -> surface): top-down recurrence (:125-140) fused with the level fluxes (:144-150) and the
-//        spectral accumulation (spcvrt :570-619).  The lowest-layer and top-layer special cases of the
-//        reference are the general formulas evaluated at rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).
-// Default (OPT bit 4, "top-down first"; described at its code below): the first sweep is the reference's top-down
-// recurrence fused with reftra, the second a two-term upward flux recurrence on three stored values per cell.
-// OPT bit 3 ("flux propagation", bottom-up first): the up sweep also keeps, per layer, the three coefficients of
-//   D_below = fa * D_above + fb * S_above,  S_below = dbt * S_above      (D diffuse, S direct downward flux)
-// with fa = trad * zreflect, fb = ((tra - dbt) + refd * rup * dbt) * zreflect and zreflect = 1/(1 - refd * rupd)
-// the factor the bottom-up recurrence has just computed (interaction principle at the lower boundary of the
-// layer, given the reflectances rup, rupd of everything below).  The upward flux at a level is rupd*D + rup*S.
-// This is algebraically vrtqdr's result ((tdbt*rup + (tdn - tdbt)*rupd)/(1 - rdnd*rupd) and its pfd companion)
-// without the top-down (ztdn, prdnd) recurrence, so the down sweep needs no layer property, no reciprocal and no
-// table look-up: five stored values and six FP64 operations per cell instead of reftra again (~100).  Agreement
-// with the oracle's literal formulas: 1e-13 relative (tests assert 1e-9).
-// The other two modes evaluate the reference's top-down recurrence literally and need the five layer properties
-// (ref, refd, tra, trad, dbt) in both sweeps.  STORE = true keeps them
-// in per-thread local arrays (40 B written + 40 B read per cell, which at full occupancy streams through
-// HBM); STORE = false evaluates reftra again in the down sweep from the staged (taur, taug) pair
-// (16 B re-read per cell, ~90 more FP64 operations).  Which is faster depends on the HBM/FP64 balance and
-// is chosen at launch (option "sw_solver_store").
+// Kernels in this file:
+//   sw_solver_warp_kernel + sw_finish_kernel  the default (option sw_solver_variant = 4): one warp per block, the
+//        reference's top-down recurrence first, then a two-term upward flux recurrence on three stored values per
+//        cell -- reftra is evaluated once per cell.  Derivation at "Top-down first" in sw_solver_kernel, layout and
+//        the reason for one-warp blocks at sw_solver_warp_kernel.
+//   sw_solver_kernel<LMAX, STORE, OPT>  the earlier forms, selectable for comparison and run by the tests:
+//        block <-> two columns (2 x 112 g-points = 7 full warps), thread <-> (column, g-point);
+//        OPT bit 4 (variant 3)  the default scheme in 7-warp blocks;
+//        OPT bit 3 (variant 2)  "flux propagation", bottom-up first: the up sweep (reftra fused with vrtqdr :103-121,
+//            keeps rup, rupd per level) also keeps, per layer, the coefficients of
+//              D_below = fa * D_above + fb * S_above,  S_below = dbt * S_above   (D diffuse, S direct downward flux)
+//            with fa = trad * zreflect, fb = ((tra - dbt) + refd * rup * dbt) * zreflect, zreflect = 1/(1 - refd * rupd)
+//            being the factor the bottom-up recurrence has just computed (interaction principle at the lower boundary
+//            of the layer); the upward flux at a level is rupd*D + rup*S.  Algebraically vrtqdr's result
+//            ((tdbt*rup + (tdn - tdbt)*rupd)/(1 - rdnd*rupd) and its pfd companion) without the (ztdn, prdnd)
+//            recurrence: five stored values and six FP64 operations per cell in the down sweep;
+//        variants 1, 0 and STORE  the reference's two recurrences literally: up sweep as above, down sweep = top-down
+//            recurrence (:125-140) fused with the level fluxes (:144-150) and the spectral accumulation (spcvrt
+//            :570-619); the lowest-layer and top-layer special cases of the reference are the general formulas at
+//            rup = albedo resp. tdn = 1, rdnd = 0 (bitwise).  The five layer properties (ref, refd, tra, trad, dbt)
+//            are needed by both sweeps: STORE = true keeps them in per-thread local arrays (40 B written + 40 B read
+//            per cell, which at full occupancy streams through HBM), STORE = false evaluates reftra again (16 B
+//            re-read per cell, ~90 more FP64 operations).
+//   sw_solver_gen_kernel  aerosols / clouds (not MiMA's configuration), further down.
+// All forms agree with the oracle's literal formulas to 1e-13 relative on the fluxes (tests assert 1e-9).
 // The direct-beam transmittance of spcvrt :519-531 is the same table look-up as reftra's exp(-tau/mu0)
 // (for tau/mu0 > 500 both hit the 1e-20 floor of exp_tbl), so it is taken from there.
 // Divides go through rcp_fast/sqrt_fast; zbeta is folded into zdend's denominator.
