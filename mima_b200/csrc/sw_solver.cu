@@ -554,8 +554,9 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
 // ([col][half-warp][up, down][lev]); sw_finish_kernel adds the seven partials of a column in the fixed order the
 // block-level kernel used (bitwise the same sums), writes the fluxes and the heating rates.
 // =====================================================================================================
-// WPB: resident one-warp blocks per SM the register allocation aims at (28 -> 72 registers, 32 -> 64)
-template <int LMAX, int WPB>
+// WPB: resident one-warp blocks per SM the register allocation aims at (28 -> 72 registers, 32 -> 64);
+// U: layers per load group (measured at T170L60: U = 1 11.16 ms, 2 10.79 ms, 4 11.41 ms with 108 B of spills)
+template <int LMAX, int WPB, int U = SV_U>
 __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwIn in, SwWork w)
 {
     constexpr bool R1 = true;
@@ -601,27 +602,27 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwI
 
     // ---- pass 1, top -> surface: reftra + vrtqdr's top-down recurrence; sum over g of incflx * tdn
     double tdn = 1., rdnd = 0., tdbt = 1.;
-    double trn[SV_U], tgn[SV_U];
+    double trn[U], tgn[U];
 #pragma unroll
-    for (int j = 0; j < SV_U; ++j) {
+    for (int j = 0; j < U; ++j) {
         const int l = max(klev - 1 - j, 0);
         trn[j] = active ? __ldg(taur + l * trs) : 0.;          // night columns have no staged optical depths
         tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
     }
-    for (int kg = 0; kg <= klev; kg += SV_U) {
-        double tr[SV_U], tg[SV_U];
+    for (int kg = 0; kg <= klev; kg += U) {
+        double tr[U], tg[U];
 #pragma unroll
-        for (int j = 0; j < SV_U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
-        if (active && kg + SV_U < klev) {
+        for (int j = 0; j < U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+        if (active && kg + U < klev) {
 #pragma unroll
-            for (int j = 0; j < SV_U; ++j) {
-                const int l = max(klev - 1 - (kg + SV_U + j), 0);
+            for (int j = 0; j < U; ++j) {
+                const int l = max(klev - 1 - (kg + U + j), 0);
                 trn[j] = __ldg(taur + l * trs);
                 tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
             }
         }
 #pragma unroll
-        for (int j = 0; j < SV_U; ++j) {
+        for (int j = 0; j < U; ++j) {
             const int k = kg + j, s = klev - k;          // level s counted from the surface, layer s - 1 below it
             double row = 0.;
             if (active && s >= 0) {
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwI
             }
             wt[(k & 7) * SV_WS] = row;
         }
-        const int kl = min(kg + SV_U - 1, klev);
+        const int kl = min(kg + U - 1, klev);
         if ((kl & 7) == 7 || kl == klev) {
             const int kb = kl & ~7;
             warp_rows([&](int row, int half, double acc) {
