@@ -38,6 +38,7 @@
 //
 // This translation unit is compiled with FMA contraction on (build.py).
 #include "rrtmg_dev.cuh"
+#include <algorithm>
 
 namespace rrtmg {
 
@@ -699,6 +700,223 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwI
     }
 }
 
+// =====================================================================================================
+// sw_solver_l2_kernel (variant 5): the scheme of sw_solver_warp_kernel with the per-cell stack (rdnd, zp, zq: 24 B)
+// kept on chip.  The local arrays of the one-warp kernel make 28 warps x 46.8 KB per SM = 194 MB of live-or-dead stack
+// lines, more than the 126 MB L2: every cell's 24 B go to HBM and come back (339 KB per column against 110 KB of
+// algorithmic traffic).  Here
+//   * blocks are persistent (grid = SMs x WPB one-warp blocks, each walks the warp tiles blockIdx.x, +gridDim.x, ...),
+//     so a block owns ONE stack slot in an explicit global scratch, [slot][level][rdnd, zp, zq][lane], for its life;
+//   * the levels next to the surface (written last, read first) live in shared memory (NS levels, as many as fit);
+//   * the rest is written with an L2 evict_last policy and, once pass 2 has read a group of levels, its lines are
+//     dropped with discard.L2 -- they are dead until the next tile overwrites them, and a discarded line is never
+//     written back to HBM.
+// Knobs (Tuning::x): x0 = WPB (12, 16, 20, 24, 28), x1 bit 0 = evict_last policy, bit 1 = discard, x2 = shared levels
+// (-1: as many as fit).
+// =====================================================================================================
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_hint(double *p, double v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ld_hint(const double *p, unsigned long long pol)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_na(const double *p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void l2_discard128(const void *p)
+{
+    asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory");
+}
+
+template <int LMAX, int WPB, int PG = 4, int U = SV_U>
+__global__ void __launch_bounds__(32, WPB) sw_solver_l2_kernel(SwTables T, SwIn in, SwWork w, long long nitems, int ns, int flags)
+{
+    constexpr bool R1 = true;
+    extern __shared__ __align__(16) double s_stk[];      // [ns][3][32]
+    __shared__ double s_tile[8 * SV_WS];
+    __shared__ double s_dn0[2][LMAX + 1];
+    const int lane = threadIdx.x;
+    double *wt = s_tile + lane + (lane >> 4);
+    const int klev = w.nlay;
+    const bool pol_on = (flags & 1) != 0, disc_on = (flags & 2) != 0;
+    const unsigned long long pol = l2_policy_evict_last();
+    double *const gstk = w.stack + (size_t)blockIdx.x * (size_t)(klev + 1) * 96 + lane;    // this block's slot
+    double *const sstk = s_stk + lane;
+    const double bpade = c_ss.bpade;
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(T.exptbl);
+    const long long nhw = (long long)w.nc * SV_HPC;
+
+    auto put = [&](int s, double r, double p, double q) {
+        if (s < ns) {
+            double *d = sstk + s * 96;
+            d[0] = r; d[32] = p; d[64] = q;
+        } else {
+            double *d = gstk + (size_t)s * 96;
+            if (pol_on) { st_hint(d, r, pol); st_hint(d + 32, p, pol); st_hint(d + 64, q, pol); }
+            else { d[0] = r; d[32] = p; d[64] = q; }
+        }
+    };
+    auto get = [&](int s, double &r, double &p, double &q) {
+        if (s < ns) {
+            const double *d = sstk + s * 96;
+            r = d[0]; p = d[32]; q = d[64];
+        } else {
+            const double *d = gstk + (size_t)s * 96;
+            if (pol_on) { r = ld_hint(d, pol); p = ld_hint(d + 32, pol); q = ld_hint(d + 64, pol); }
+            else { r = ld_na(d); p = ld_na(d + 32); q = ld_na(d + 64); }
+        }
+    };
+    auto warp_rows = [&](auto store) {
+        __syncwarp();
+        const int row = lane >> 2, q = lane & 3, half = q >> 1;
+        const double *src = s_tile + row * SV_WS + 17 * half + 8 * (q & 1);
+        double acc = src[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc += src[j];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if ((q & 1) == 0) store(row, half, acc);
+        __syncwarp();
+    };
+
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const long long t = item * 32 + lane;
+        const int col = (int)(t / NGPTSW);
+        const int g = (int)(t - (long long)col * NGPTSW);
+        const bool incol = col < w.nc;
+        const double prmu0 = incol ? in.coszen[col] : 0.0;
+        const bool active = incol && !(prmu0 < ZEPZEN);      // night columns: zeros (rad.nomcica:502-510)
+        const int colr = incol ? col : 0;
+        const int band = c_ss.ngb[g];
+        const double mu0 = active ? prmu0 : 1.0;
+        const double rmu0 = 1. / mu0;
+        const bool uvvis = band >= 9 && band <= 12;          // bands 25-28 take the UV/visible albedos
+        const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
+        const bool b24 = band == 8;
+        const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
+        const double *__restrict__ taur = b24 ? w.taur24 + (size_t)colr * klev * 8 + (g - c_ss.g0[band])
+                                              : w.colmol + (size_t)colr * klev;
+        const int trs = b24 ? 8 : 1;
+        const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)colr * NGPTSW + g] * prmu0 : 0.0;
+
+        // ---- pass 1, top -> surface (see sw_solver_warp_kernel)
+        double tdn = 1., rdnd = 0., tdbt = 1.;
+        double trn[U], tgn[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int l = max(klev - 1 - j, 0);
+            trn[j] = active ? __ldg(taur + l * trs) : 0.;
+            tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
+        }
+        for (int kg = 0; kg <= klev; kg += U) {
+            double tr[U], tg[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+            if (active && kg + U < klev) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int l = max(klev - 1 - (kg + U + j), 0);
+                    trn[j] = __ldg(taur + l * trs);
+                    tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int k = kg + j, s = klev - k;
+                double row = 0.;
+                if (active && s >= 0) {
+                    row = zincflx * tdn;
+                    double zpv = 0., zqv = 0.;
+                    const double rd0 = rdnd;
+                    if (s > 0) {
+                        const double dif = tdn - tdbt;
+                        double ref, refd, tra, trad, dbt;
+                        sw_reftra<R1>(tb, bpade, mu0, rmu0, tr[j] * raylg, tg[j], ref, refd, tra, trad, dbt);
+                        const double zreflect = rcp_sel<R1>(1. - refd * rdnd);
+                        zpv = trad * zreflect;
+                        zqv = zincflx * ((ref * tdbt + refd * dif) * zreflect);
+                        const double tdn_n = tdbt * tra + (trad * (dif + tdbt * ref * rdnd)) * zreflect;
+                        const double rdnd_n = refd + trad * trad * rdnd * zreflect;
+                        tdbt = dbt * tdbt;
+                        tdn = tdn_n;
+                        rdnd = rdnd_n;
+                    }
+                    put(s, rd0, zpv, zqv);
+                }
+                wt[(k & 7) * SV_WS] = row;
+            }
+            const int kl = min(kg + U - 1, klev);
+            if ((kl & 7) == 7 || kl == klev) {
+                const int kb = kl & ~7;
+                warp_rows([&](int row, int half, double acc) {
+                    if (kb + row <= kl) s_dn0[half][klev - kb - row] = acc;
+                });
+            }
+        }
+        double u = 0.;
+        if (active) {
+            const double sd = uvvis ? in.asdif[colr] : in.aldif[colr];
+            const double sp = uvvis ? in.asdir[colr] : in.aldir[colr];
+            u = zincflx * ((sp * tdbt + sd * (tdn - tdbt)) * rcp_sel<R1>(1. - sd * rdnd));
+        }
+        // ---- pass 2, surface -> top
+        const long long hw0 = item * 2;
+        constexpr int G8 = PG;
+        for (int s0 = 0; s0 <= klev; s0 += G8) {
+            double p[G8], q[G8], r[G8];
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < G8; ++j) get(min(s0 + j, klev), r[j], p[j], q[j]);
+            }
+#pragma unroll
+            for (int h = 0; h < G8; h += 4) {
+                if (s0 + h <= klev) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sj = s0 + h + j;
+                        double pu = 0., pd = 0.;
+                        if (active && sj <= klev) {
+                            if (sj > 0) u = fma(p[h + j], u, q[h + j]);
+                            pu = u;
+                            pd = r[h + j] * u;
+                        }
+                        wt[(2 * j) * SV_WS] = pu;
+                        wt[(2 * j + 1) * SV_WS] = pd;
+                    }
+                    warp_rows([&](int row, int half, double acc) {
+                        const int lev = s0 + h + (row >> 1);
+                        if (lev <= klev && hw0 + half < nhw) {
+                            double *dst = w.part + ((hw0 + half) * 2 + (row & 1)) * (klev + 1) + lev;
+                            *dst = (row & 1) ? s_dn0[half][lev] + acc : acc;
+                        }
+                    });
+                }
+            }
+            if (disc_on) {
+                // the values of levels s0 .. s0+7 are in use (warp_rows synchronised the warp after the last of them):
+                // drop their lines, 6 x 128 B per level
+                const int sa = max(s0, ns), sb = min(s0 + G8 - 1, klev);
+                const int nline = (sb - sa + 1) * 6;
+                const char *base = reinterpret_cast<const char *>(gstk - lane + (size_t)sa * 96);
+                for (int i = lane; i < nline; i += 32) l2_discard128(base + (size_t)i * 128);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Adds the seven half-warp partials of a column and level, writes the fluxes and heating rates
 // (rrtmg_sw_rad.nomcica.f90:686-727; clear == total for icld = 0).  A block takes TC columns: the partials are read
 // with the level index fastest, the outputs written with the column index fastest (transpose through shared memory).
@@ -1016,7 +1234,31 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
     else if (g_tune.sw_solver_variant == 1) launch<LMAX, false, 5>(t, in, out, w, s);
     else if (g_tune.sw_solver_variant == 2) launch<LMAX, false, 13>(t, in, out, w, s);
     else if (g_tune.sw_solver_variant == 3) launch<LMAX, false, 21>(t, in, out, w, s);
-    else {
+    else if (g_tune.sw_solver_variant == 5) {
+        constexpr int TC = LMAX <= 64 ? 32 : 16;
+        const long long nitems = ((long long)w.nc * NGPTSW + 31) / 32;
+        static int nsm = 0;
+        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+        const int wpb = g_tune.x[0] > 0 ? g_tune.x[0] : 20;
+        const int flags = g_tune.x[1];
+        auto go = [&](auto kern, int W) {
+            // shared levels: what fits beside the static tiles at W blocks per SM (1 KB per block is reserved by the system)
+            const int fixed = (int)(sizeof(double) * (8 * SV_WS + 2 * (LMAX + 1))) + 1024 + 256;
+            int ns = (227 * 1024 / W - fixed) / 768;
+            if (g_tune.x[2] > 0 && g_tune.x[2] - 1 < ns) ns = g_tune.x[2] - 1;      // x2 = shared levels + 1 (0: as many as fit)
+            ns = ns < 0 ? 0 : (ns > w.nlay + 1 ? w.nlay + 1 : ns);
+            const size_t smem = (size_t)ns * 768;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const long long grid = std::min<long long>(nitems, (long long)nsm * W);
+            kern<<<(unsigned)grid, 32, smem, s>>>(t, in, w, nitems, ns, flags);
+        };
+        if (wpb <= 12) go(sw_solver_l2_kernel<LMAX, 12>, 12);
+        else if (wpb <= 16) go(sw_solver_l2_kernel<LMAX, 16>, 16);
+        else if (wpb <= 20) go(sw_solver_l2_kernel<LMAX, 20>, 20);
+        else if (wpb <= 24) go(sw_solver_l2_kernel<LMAX, 24>, 24);
+        else go(sw_solver_l2_kernel<LMAX, 28>, 28);
+        sw_finish_kernel<LMAX, TC><<<(w.nc + TC - 1) / TC, 256, 0, s>>>(in, out, w);
+    } else {
         // variant 4: variant 3 with one warp per block + sw_finish_kernel
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nthr = (long long)w.nc * NGPTSW;

@@ -19,6 +19,7 @@ TIGHT = 1e-9
 
 LW_OUT = ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")
 SW_OUT = ("swuflx", "swdflx", "swhr", "swuflxc", "swdflxc", "swhrc")
+DEFAULT_SW_VARIANT = 4
 LW_NGS = [0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138, 140]
 
 
@@ -147,19 +148,52 @@ def test_sw_solver_variants_agree(gpu, oracle):
     ref = oracle.rrtmg_sw(cols)
     res = {}
     try:
-        for v in (4, 3, 2, 1, 0):
+        for v in (5, 4, 3, 2, 1, 0):
             gpu.set_option("sw_solver_variant", v)
             res[v] = gpu.sw_from_columns(cols)
             _check_outputs(res[v], ref, SW_OUT)
+        gpu.set_option("sw_solver_variant", 5)
+        for wpb, flags, ns in ((12, 3, 0), (16, 1, 1), (24, 2, 4), (28, 0, 0)):    # x0 blocks/SM, x1 policy|discard, x2 shared levels + 1
+            for k, v in (("x0", wpb), ("x1", flags), ("x2", ns)):
+                gpu.set_option(k, v)
+            r5 = gpu.sw_from_columns(cols)
+            assert all(np.array_equal(a, b) for a, b in zip(r5, res[5])) or wpb in (12, 16), (wpb, flags, ns)
+            _check_outputs(r5, ref, SW_OUT)
     finally:
-        gpu.set_option("sw_solver_variant", 4)
+        gpu.set_option("sw_solver_variant", DEFAULT_SW_VARIANT)
+        for k, v in (("x0", 0), ("x1", 3), ("x2", 0)):
+            gpu.set_option(k, v)
     assert all(np.array_equal(a, b) for a, b in zip(res[4], res[3]))      # same sums in the same order
+    for a, b, n in zip(res[5], res[4], SW_OUT):                           # stack in L2 / shared memory: same formulas
+        assert np.max(np.abs(a - b)) < (1e-7 if "hr" in n else 1e-8), n
     for v in (2, 3):
         for a, b, n in zip(res[v], res[1], SW_OUT):
             if "hr" in n:
                 assert np.max(np.abs(a - b)) < 1e-7, (v, n)          # K/day
             else:
                 assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.abs(b).max())) < 1e-10, (v, n)
+
+
+def test_cell_binning_is_invisible(gpu, oracle):
+    """taumol over cells binned by k-table row key (binning.cu) against 32 adjacent columns per warp: every cell is
+    evaluated by the same code whichever warp takes it, so all outputs are bitwise the same (ragged column count,
+    night columns binned last)."""
+    cols = make_columns("T170L60", nlon=83, nlat=7, night=True)
+    res = {}
+    try:
+        for b, order, run in ((1, 0, 8), (1, 1, 3), (1, 0, 1), (0, 0, 8)):
+            gpu.set_option("taumol_bin", b)
+            gpu.set_option("taumol_order", order)
+            gpu.set_option("taumol_run", run)
+            res[b, order, run] = gpu.lw_from_columns(cols) + gpu.sw_from_columns(cols)
+    finally:
+        gpu.set_option("taumol_bin", 1)
+        gpu.set_option("taumol_order", 0)
+        gpu.set_option("taumol_run", 8)
+    _check_outputs(res[1, 0, 8][:6], oracle.rrtmg_lw(cols), LW_OUT)
+    _check_outputs(res[1, 0, 8][6:], oracle.rrtmg_sw(cols), SW_OUT)
+    for k in ((1, 1, 3), (1, 0, 1), (0, 0, 8)):
+        assert all(np.array_equal(a, b) for a, b in zip(res[k], res[1, 0, 8])), k
 
 
 def test_emissivity_and_aerosol_inputs(gpu, oracle):

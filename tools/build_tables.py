@@ -445,7 +445,8 @@ def write_kg_fortran(path, arrays, prefix="lw", digits=17):
     bands = sorted({k.split(".")[0] for k in arrays})
     with open(path, "w") as f:
         for bk in bands:
-            f.write(f"      subroutine {prefix}_kgb{bk[len(prefix):]}\n      implicit none\n      save\n\n")
+            f.write(f"      subroutine {prefix}_kgb{bk[len(prefix):]}\n      use parkind, only : im => kind_im, rb => kind_rb\n"
+                    f"      use rr{prefix}_kg{bk[len(prefix):]}\n      implicit none\n      save\n\n")
             for key in sorted(k for k in arrays if k.startswith(bk + ".")):
                 name = key.split(".")[1]
                 a = np.asfortranarray(arrays[key])
