@@ -266,3 +266,17 @@ int ref_rrtmg_sw(int ncol, int nlay, int icld, int iaer,
     J.uflx = swuflx; J.dflx = swdflx; J.hr = swhr; J.uflxc = swuflxc; J.dflxc = swdflxc; J.hrc = swhrc;
     return run_job(&J, nthreads);
 }
+
+/* ------------------------------------------------------------------------------------ stage hooks (one column) */
+/* taumol_sw (SW/src/rrtmg_sw_taumol.f90:31) on the setcoef_sw state of one column; taug/taur are (nlay, 112) column-major */
+int ref_sw_taumol(int nlay, double *colh2o, double *colco2, double *colch4, double *colo2, double *colo3, double *colmol,
+                  int laytrop, int *jp, int *jt, int *jt1, double *fac00, double *fac01, double *fac10, double *fac11,
+                  double *selffac, double *selffrac, int *indself, double *forfac, double *forfrac, int *indfor,
+                  double *sfluxzen, double *taug, double *taur)
+{
+    rrtmg_sw_taumol__taumol_sw(nlay, colh2o, nlay, colco2, nlay, colch4, nlay, colo2, nlay, colo3, nlay, colmol, nlay, laytrop,
+                               jp, nlay, jt, nlay, jt1, nlay, fac00, nlay, fac01, nlay, fac10, nlay, fac11, nlay,
+                               selffac, nlay, selffrac, nlay, indself, nlay, forfac, nlay, forfrac, nlay, indfor, nlay,
+                               sfluxzen, 112, taug, nlay, 112, taur, nlay, 112);
+    return 0;
+}

@@ -195,6 +195,11 @@ static void setcoef_sw(swcol_t *c)
 #define FORONLY(K, lay, indf, ig) \
     (c->forfac[lay] * (F2((K)->forref, (K)->nfor, indf, ig) + c->forfrac[lay] * \
         (F2((K)->forref, (K)->nfor, (indf) + 1, ig) - F2((K)->forref, (K)->nfor, indf, ig))))
+/* upper-atmosphere foreign continuum of bands 17 and 21: colh2o * forfac * (...), evaluated left to right
+ * (taumol.f90:451-454, :859-862) -- not colh2o * (forfac * (...)) as in the band-20 form above (:732-741) */
+#define FORUP(K, lay, indf, ig) \
+    (c->colh2o[lay] * c->forfac[lay] * (F2((K)->forref, (K)->nfor, indf, ig) + c->forfrac[lay] * \
+        (F2((K)->forref, (K)->nfor, (indf) + 1, ig) - F2((K)->forref, (K)->nfor, indf, ig))))
 #define KEY4(abs_, n_, ind0, ind1, ig) \
     (c->fac00[lay] * F2(abs_, n_, ind0, ig) + c->fac10[lay] * F2(abs_, n_, (ind0) + 1, ig) + \
      c->fac01[lay] * F2(abs_, n_, ind1, ig) + c->fac11[lay] * F2(abs_, n_, (ind1) + 1, ig))
@@ -296,7 +301,7 @@ static void taumol_sw(swcol_t *c)
             indf = c->indfor[lay];
             tauray = c->colmol[lay] * K->rayl;
             for (ig = 1; ig <= ngc[1]; ++ig) {
-                TAUG(o, ig) = b.speccomb * key8(&b, K->absb, 1175, ind0, ind1, 5, ig) + c->colh2o[lay] * FORONLY(K, lay, indf, ig);
+                TAUG(o, ig) = b.speccomb * key8(&b, K->absb, 1175, ind0, ind1, 5, ig) + FORUP(K, lay, indf, ig);
                 if (lay == laysolfr)
                     SFLX(o, ig) = F2(K->sfluxref, 12, ig, b.js) + b.fs * (F2(K->sfluxref, 12, ig, b.js + 1) - F2(K->sfluxref, 12, ig, b.js));
                 TAUR(o, ig) = tauray;
@@ -393,7 +398,7 @@ static void taumol_sw(swcol_t *c)
             indf = c->indfor[lay];
             tauray = c->colmol[lay] * K->rayl;
             for (ig = 1; ig <= ngc[5]; ++ig) {
-                TAUG(o, ig) = b.speccomb * key8(&b, K->absb, 1175, ind0, ind1, 5, ig) + c->colh2o[lay] * FORONLY(K, lay, indf, ig);
+                TAUG(o, ig) = b.speccomb * key8(&b, K->absb, 1175, ind0, ind1, 5, ig) + FORUP(K, lay, indf, ig);
                 TAUR(o, ig) = tauray;
             }
         }

@@ -115,3 +115,17 @@ def test_regression_vectors(oracle):
         assert np.allclose(lw[k], g["lw_" + k], rtol=1e-12, atol=1e-12), k
     for k in ("swuflx", "swdflx", "swhr"):
         assert np.allclose(sw[k], g["sw_" + k], rtol=1e-12, atol=1e-12), k
+
+
+def test_reference_vectors(oracle):
+    """tests/golden/ref_t42l40.npz holds outputs of the reference's own RRTMG code (machine-translated F90 -> C, see
+    tests/golden/make_ref_vectors.py) for config C4 columns: the oracle must reproduce them bit for bit.  Runs anywhere
+    (no oracle/_ref needed)."""
+    from tests.golden.make_ref_vectors import batch
+    g = np.load(os.path.join(GOLD, "ref_t42l40.npz"))
+    c = batch()
+    lw, sw = oracle.rrtmg_lw(c, idrv=1), oracle.rrtmg_sw(c)
+    for k in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc", "duflx_dt", "duflxc_dt"):
+        assert np.array_equal(lw[k], g[k]), k
+    for k in ("swuflx", "swdflx", "swhr", "swuflxc", "swdflxc", "swhrc"):
+        assert np.array_equal(sw[k], g[k]), k

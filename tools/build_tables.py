@@ -593,5 +593,18 @@ def main():
     print("round-trip ok")
 
 
+def emit_lw_kg(path):
+    """Write the LW coefficients the oracle and the CUDA library load (the real blob if there is one, else the synthetic
+    one) as Fortran source in the layout of the reference's stripped LW/src/rrtmg_lw_k_g.f90 (subroutines lw_kgb01..16
+    assigning the rrlw_kgNN module arrays).  oracle/Makefile translates it next to the reference sources, so that the
+    translated rrtmg_lw_ini finds the routines it calls (rrtmg_lw_init.f90:80-95)."""
+    real = os.path.join(OUT, "rrtmg_lw_kg.bin")
+    arrays = read_blob(real if os.path.exists(real) else os.path.join(OUT, "rrtmg_lw_kg_synth.bin"))
+    write_kg_fortran(path, arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "--emit-lw-kg":
+        emit_lw_kg(sys.argv[2])
+        sys.exit(0)
     sys.exit(main())

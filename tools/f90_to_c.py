@@ -307,7 +307,7 @@ class Parser:
                 return lo
         self.expect("op", ":")
         hi = step = None
-        if self.peek() not in (("op", ","), ("op", ")"), ("op", ":")):
+        if self.peek()[0] != "end" and self.peek() not in (("op", ","), ("op", ")"), ("op", ":")):
             hi = self.expr()
         if self.accept("op", ":"):
             step = self.expr()
@@ -518,6 +518,8 @@ class Program:
         if m and not text.startswith("module procedure"):
             u = Unit("module", m.group(1))
             u.path = path
+            if u.name in self.modules:          # parkind.f90 exists once per code (LW, SW): the later copy replaces the earlier
+                self.order.remove(self.modules[u.name])
             self.modules[u.name] = u
             self.order.append(u)
             stack.append(u)
