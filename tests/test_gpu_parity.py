@@ -144,7 +144,7 @@ def test_reference_golden_vectors(gpu):
     sources machine-translated F90 -> C and run on config C4 columns, tests/golden/make_ref_vectors.py) -- no oracle in
     between.  north_star tolerances, and the tighter regression bounds."""
     import os
-    from tests.golden.make_ref_vectors import batch
+    from golden.make_ref_vectors import batch
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_t42l40.npz"))
     c = batch()
     _check_outputs(gpu.lw_from_columns(c), g, LW_OUT)

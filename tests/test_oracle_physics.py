@@ -121,7 +121,7 @@ def test_reference_vectors(oracle):
     """tests/golden/ref_t42l40.npz holds outputs of the reference's own RRTMG code (machine-translated F90 -> C, see
     tests/golden/make_ref_vectors.py) for config C4 columns: the oracle must reproduce them bit for bit.  Runs anywhere
     (no oracle/_ref needed)."""
-    from tests.golden.make_ref_vectors import batch
+    from golden.make_ref_vectors import batch
     g = np.load(os.path.join(GOLD, "ref_t42l40.npz"))
     c = batch()
     lw, sw = oracle.rrtmg_lw(c, idrv=1), oracle.rrtmg_sw(c)

@@ -185,7 +185,7 @@ def test_extreme_columns(ref, oracle):
 
 
 def _lw_cloud_field(cols, rng):
-    from tests.test_oracle_lw_clouds import cloud_field
+    from test_oracle_lw_clouds import cloud_field
     return cloud_field(cols, rng)
 
 
@@ -269,7 +269,7 @@ def test_golden_vectors_come_from_the_reference(ref):
     import os
     path = os.path.join(os.path.dirname(__file__), "golden", "ref_t42l40.npz")
     g = np.load(path)
-    from tests.golden.make_ref_vectors import batch
+    from golden.make_ref_vectors import batch
     cols = batch()
     sw, lw = ref.rrtmg_sw(cols), ref.rrtmg_lw(cols, idrv=1)
     for k in SW:
