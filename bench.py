@@ -244,7 +244,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     rrtmg.set_device(local_rank)
-    rrtmg.rrtmg_lw_ini()
+    rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True)
     rrtmg.rrtmg_sw_ini()
     if args.chunk:
         rrtmg.set_option("chunk", args.chunk)

@@ -97,6 +97,11 @@ int rrtmg_b200_finalize(void);
 /* Export a reduced table as the device sees it, in the Fortran (column-major) order of the reduced
  * module array, e.g. "lw03.absa" (585,16).  Returns the element count, or -1. (test hook) */
 long rrtmg_b200_get_table(const char *name, double *out, long capacity);
+/* State of the coefficient registry.  *lw_synthetic = 1 when the registered LW k-distribution is the packaged synthetic
+ * stand-in (marker array "lwmeta.synthetic" of mima_b200/data/rrtmg_lw_kg_synth.bin): every LW flux is then an exercise
+ * of the algorithm, not physics.  The reference fills these tables in rrtmg_lw_ini from rrtmg_lw_k_g.f90
+ * (LW/src/rrtmg_lw_init.f90:80-95), which the MiMA checkout does not carry.  Any pointer may be NULL. */
+int rrtmg_b200_tables_info(int *lw_synthetic, int *lw_ready, int *sw_ready);
 
 const char *rrtmg_b200_last_error(void);
 

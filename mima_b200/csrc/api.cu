@@ -1610,6 +1610,16 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     return RRTMG_B200_OK;
 }
 
+int rrtmg_b200_tables_info(int *lw_synthetic, int *lw_ready, int *sw_ready)
+{
+    // the packaged LW k-distribution is a synthetic stand-in (the reference checkout has no rrtmg_lw_k_g.f90); its blob
+    // carries the marker "lwmeta.synthetic", real coefficient sets do not
+    if (lw_synthetic) *lw_synthetic = find("lwmeta.synthetic") != nullptr;
+    if (lw_ready) *lw_ready = G.lw_ready ? 1 : 0;
+    if (sw_ready) *sw_ready = G.sw_ready ? 1 : 0;
+    return RRTMG_B200_OK;
+}
+
 int rrtmg_b200_set_option(const char *key, long value)
 {
     const std::string k(key ? key : "");

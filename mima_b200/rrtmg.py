@@ -108,12 +108,35 @@ def _default_tables(kind: str):
             _loaded.add(f)
 
 
-def rrtmg_lw_ini(cpdair: float = CP_AIR, *, default_tables: bool = True):
-    """rrtmg_lw_ini(cpdair).  With default_tables the packaged blobs are registered first (the LW
-    k-distribution blob is SYNTHETIC -- the real rrtmg_lw_k_g.f90 is not in the reference checkout;
-    register real arrays with set_table()/load_tables() and pass default_tables=False to use them)."""
+class SyntheticTablesWarning(UserWarning):
+    pass
+
+
+def tables_info() -> dict:
+    a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    _check(lib().rrtmg_b200_tables_info(C.byref(a), C.byref(b), C.byref(c)))
+    return dict(lw_synthetic=bool(a.value), lw_ready=bool(b.value), sw_ready=bool(c.value))
+
+
+def rrtmg_lw_ini(cpdair: float = CP_AIR, *, default_tables: bool = True, allow_synthetic_lw: bool | None = None):
+    """rrtmg_lw_ini(cpdair) (LW/src/rrtmg_lw_init.f90:28).  With default_tables the packaged blobs are registered first.
+    The packaged LW k-distribution is SYNTHETIC (the reference checkout carries no rrtmg_lw_k_g.f90): fluxes computed with
+    it exercise the algorithm and mean nothing physically.  It is only used when the caller says so --
+    allow_synthetic_lw=True (tests, bench.py, smoke) or MIMA_B200_ALLOW_SYNTHETIC_LW=1 -- otherwise this raises; a real
+    coefficient set (mima_b200/data/rrtmg_lw_kg.bin from tools/build_tables.py, or arrays registered with set_table() /
+    load_tables() and default_tables=False) needs no switch.  tables_info() reports which set is active."""
+    if allow_synthetic_lw is None:
+        allow_synthetic_lw = os.environ.get("MIMA_B200_ALLOW_SYNTHETIC_LW", "") not in ("", "0")
     if default_tables:
         _default_tables("lw")
+    if tables_info()["lw_synthetic"]:
+        if not allow_synthetic_lw:
+            raise RRTMGError(6, "the registered LW k-distribution is the packaged synthetic stand-in; pass "
+                                "allow_synthetic_lw=True (or MIMA_B200_ALLOW_SYNTHETIC_LW=1) to run on it, or register the "
+                                "real rrtmg_lw_k_g coefficients (tools/build_tables.py, set_table/load_tables)")
+        import warnings
+        warnings.warn("RRTMG_LW runs on SYNTHETIC k-distribution tables: LW fluxes and heating rates are not physical",
+                      SyntheticTablesWarning, stacklevel=2)
     _check(lib().rrtmg_b200_lw_init(float(cpdair)))
 
 

@@ -25,6 +25,6 @@ def gpu():
     ge.build()
     from mima_b200 import rrtmg
     rrtmg.set_device(0)
-    rrtmg.rrtmg_lw_ini()
+    rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True)
     rrtmg.rrtmg_sw_ini()
     return rrtmg

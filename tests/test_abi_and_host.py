@@ -40,7 +40,7 @@ def _has_gpu():
 def test_no_gpu_means_error_not_fallback():
     from mima_b200 import rrtmg
     with pytest.raises(rrtmg.RRTMGError) as e:
-        rrtmg.rrtmg_lw_ini()
+        rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True)
     assert e.value.code == 5
     from mima_b200.columns import make_columns
     c = make_columns("T42L40", nlon=4, nlat=2)

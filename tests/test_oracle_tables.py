@@ -142,6 +142,7 @@ def test_lw_k_g_parser_round_trip(tmp_path):
     bt = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bt)
     synth = bt.read_blob(os.path.join(ROOT, "mima_b200", "data", "rrtmg_lw_kg_synth.bin"))
+    assert synth.pop("lwmeta.synthetic")[0] == 1.0          # the marker rrtmg_b200_tables_info() reports; not a coefficient
     src = tmp_path / "rrtmg_lw_k_g.f90"
     bt.write_kg_fortran(str(src), synth)
     back = bt.build_lw_real(str(src))
@@ -164,6 +165,7 @@ def test_lw_netcdf_reader_round_trip(tmp_path):
     bt = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bt)
     synth = bt.read_blob(os.path.join(ROOT, "mima_b200", "data", "rrtmg_lw_kg_synth.bin"))
+    synth.pop("lwmeta.synthetic")
     nc = tmp_path / "rrtmg_lw.nc"
     bt.write_lw_nc(str(nc), synth)
     back = bt.build_lw_from_nc(str(nc))

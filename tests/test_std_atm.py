@@ -78,13 +78,20 @@ def test_columns_from_a_tape5_case_run_through_the_oracle(oracle):
         np.testing.assert_allclose(out["uflx"][0, 0], c["uflx"][0], rtol=2e-3)     # Planck table x emissivity 1
 
 
-@pytest.mark.skipif(not os.path.exists(REAL_LW), reason="needs the real LW k-distribution (rrtmg_lw_k_g.f90 is stripped from "
-                    "the reference checkout); build mima_b200/data/rrtmg_lw_kg.bin with tools/build_tables.py")
+NEEDS_REAL = pytest.mark.xfail(not os.path.exists(REAL_LW), strict=True,
+                               reason="LW coefficients unpinned: the run uses the packaged SYNTHETIC k-distribution because "
+                               "rrtmg_lw_k_g.f90 is stripped from the reference checkout; build mima_b200/data/rrtmg_lw_kg.bin "
+                               "with tools/build_tables.py (MIMA_LW_KG=...) and these known answers must pass")
+
+
+@NEEDS_REAL
 @pytest.mark.parametrize("name", CASES)
 def test_known_answers_oracle(name):
+    """Expected to FAIL (xfail, strict) while only the synthetic tables exist -- reported on every run instead of hidden
+    behind a skip."""
     from oracle.pyoracle import Oracle
     c = _case(name)
-    out = Oracle(lw_kg=REAL_LW).rrtmg_lw(_columns(c))
+    out = Oracle(lw_kg=REAL_LW if os.path.exists(REAL_LW) else None).rrtmg_lw(_columns(c))
     scale = c["uflx"].max()
     assert np.max(np.abs(out["uflx"][0] - c["uflx"])) < 1e-2 * scale
     assert np.max(np.abs(out["dflx"][0] - c["dflx"])) < 1e-2 * scale
@@ -93,7 +100,7 @@ def test_known_answers_oracle(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(REAL_LW), reason="needs the real LW k-distribution (see above)")
+@NEEDS_REAL
 @pytest.mark.parametrize("name", CASES)
 def test_known_answers_gpu(gpu, name):
     c = _case(name)

@@ -395,6 +395,7 @@ def build_lw_synth(seed=20240917):
                 a = 40.0 * (1.0 + 0.4 * np.sin(0.7 * g + b)) * np.exp(0.05 * rng.standard_normal(shape))
             assert a.shape == shape and (a > 0).all(), (b, n)
             out[f"lw{b:02d}.{n}"] = np.asfortranarray(a)
+    out["lwmeta.synthetic"] = np.array([1.0])      # what rrtmg_b200_tables_info() reports: these are not AER coefficients
     return out
 
 
@@ -442,7 +443,7 @@ def write_kg_fortran(path, arrays, prefix="lw", digits=17):
     for b in range(1, 17):
         for n, (shape, lows) in lw_decls(b, params).items():
             lows_of[f"lw{b:02d}.{n}"] = lows
-    bands = sorted({k.split(".")[0] for k in arrays})
+    bands = sorted({k.split(".")[0] for k in arrays if re.match(r"^[a-z]+\d\d\.", k)})
     with open(path, "w") as f:
         for bk in bands:
             f.write(f"      subroutine {prefix}_kgb{bk[len(prefix):]}\n      use parkind, only : im => kind_im, rb => kind_rb\n"
@@ -516,7 +517,7 @@ def nc_slab(name, shape, band):
 
 def lw_template():
     """Names and declared extents of every unreduced LW array, from the synthetic blob (built from rrlw_kgNN.f90)."""
-    return {k: v.shape for k, v in read_blob(os.path.join(OUT, "rrtmg_lw_kg_synth.bin")).items()}
+    return {k: v.shape for k, v in read_blob(os.path.join(OUT, "rrtmg_lw_kg_synth.bin")).items() if not k.startswith("lwmeta.")}
 
 
 def build_lw_from_nc(nc_path, template=None):

@@ -35,7 +35,7 @@ def main():
     print(f"oracle: {time.time() - t:.2f}s on {orc.max_threads} threads")
 
     rrtmg.set_device(0)
-    rrtmg.rrtmg_lw_ini()
+    rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True)
     rrtmg.rrtmg_sw_ini()
     rrtmg.set_option("capture_stages", 1)
     rrtmg.set_option("chunk", 1 << 20)

@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 from mima_b200 import rrtmg
 from mima_b200.columns import make_columns
 from test_oracle_lw_clouds import cloud_field
-rrtmg.set_device(0); rrtmg.rrtmg_lw_ini(); rrtmg.rrtmg_sw_ini()
+rrtmg.set_device(0); rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True); rrtmg.rrtmg_sw_ini()
 c = make_columns("T42L40", nlon=32, nlat=4, night=True)
 rng = np.random.default_rng(1)
 cl = cloud_field(c, rng)

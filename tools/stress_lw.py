@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, '.')
 from mima_b200 import rrtmg
 from mima_b200.columns import make_columns
-rrtmg.set_device(0); rrtmg.rrtmg_lw_ini(); rrtmg.rrtmg_sw_ini()
+rrtmg.set_device(0); rrtmg.rrtmg_lw_ini(allow_synthetic_lw=True); rrtmg.rrtmg_sw_ini()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 for res, rows in (("T170L60", (48, 80)), ("T85L40", (0, 64)), ("T341L80", (100, 116))):
     c = make_columns(res, lat_rows=rows)
