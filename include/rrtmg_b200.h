@@ -92,6 +92,7 @@ int rrtmg_b200_set_table(const char *name, const double *data, int ndim, const i
 /* rrtmg_lw_ini / rrtmg_sw_ini: constants, lookup tables, 16 -> ngc g-point reduction, upload. */
 int rrtmg_b200_lw_init(double cpdair);
 int rrtmg_b200_sw_init(double cpdair);
+/* Releases every device buffer and forgets the registered coefficient arrays (register them again before a new init). */
 int rrtmg_b200_finalize(void);
 
 /* Export a reduced table as the device sees it, in the Fortran (column-major) order of the reduced

@@ -1181,6 +1181,7 @@ int rrtmg_b200_finalize(void)
     G.lw_ready = G.sw_ready = false;
     G.lw_last_ncol = G.sw_last_ncol = 0;
     G.reduced.clear();
+    G.reg.clear();            // registered coefficient arrays: a new init starts from what is registered after this call
     return RRTMG_B200_OK;
 }
 

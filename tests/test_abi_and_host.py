@@ -67,6 +67,32 @@ def test_table_registration_roundtrip_shapes():
     rrtmg.load_tables(os.path.join(rrtmg.DATA_DIR, "rrtmg_sw_kg.bin"))
 
 
+def test_fortran_table_registration_is_current_and_complete():
+    """shim/rrtmg_b200_tables.f90 (what rrtmg_lw_ini / rrtmg_sw_ini of the Fortran shim register) is generated from the blob
+    name lists: the committed file must be what the generator writes now, and name every array of the packaged blobs."""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("gen_shim_tables", os.path.join(ROOT, "tools", "gen_shim_tables.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    text = open(os.path.join(ROOT, "shim", "rrtmg_b200_tables.f90")).read()
+    assert text == g.generate(), "run tools/gen_shim_tables.py"
+    named = set(re.findall(r"call reg\('([a-z0-9]+\.[a-z0-9_]+)'", text))
+    want = {k for kind in ("lw", "sw") for (k, _, _, _) in g.table_list(kind)}
+    assert named == want and len(named) == 232
+    assert max(len(l) for l in text.splitlines()) <= 132                      # free-form line limit
+    # every `use <module>, only: tag_name => name` refers to a variable that module declares
+    ref = "/root/reference/src/atmos_param/rrtm_radiation"
+    if os.path.isdir(ref):
+        joined = re.sub(r"&\s*\n\s*", " ", text)
+        for mod, items in re.findall(r"use (rr[ls]w_\w+), only: (.*)", joined):
+            code = "rrtmg_lw" if mod.startswith("rrlw") else "rrtmg_sw"
+            src = open(os.path.join(ref, code, "gcm_model", "modules", mod + ".f90")).read().lower()
+            for it in items.split(","):
+                name = it.split("=>")[1].strip()
+                assert re.search(r"\b%s\b" % re.escape(name), src), (mod, name)
+
+
 def test_latitude_row_sharding_is_a_pointer_offset():
     """Column index = lon + nlon*(lat-1) (rrtm_radiation.f90:652): a block of latitude rows is a contiguous
     column range, and generating only that block reproduces the full-grid values."""

@@ -139,6 +139,41 @@ def test_end_to_end_parity(gpu, oracle, kw):
     _check_outputs(gpu.sw_from_columns(cols), oracle.rrtmg_sw(cols), SW_OUT)
 
 
+def test_set_table_path_gives_the_same_reduced_tables(gpu):
+    """What the Fortran shim's rrtmg_lw_ini / rrtmg_sw_ini do (shim/rrtmg_b200_tables.f90): every array of the generated list
+    through rrtmg_b200_set_table, then init -- the reduced tables must equal those of the load_tables path bit for bit."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_shim_tables", os.path.join(root, "tools", "gen_shim_tables.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    probe = ["lw01.absa", "lw03.absb", "lw05.ka_mo3", "lw07.kb_mco2", "lw13.ka_mco", "lw16.fracrefa", "lw.exp_tbl", "lw.tfn_tbl",
+             "sw16.absa", "sw17.absb", "sw24.rayla", "sw29.absco2", "sw27.sfluxref", "sw.exp_tbl"]
+    before = {n: gpu.get_table(n) for n in probe}
+    blobs = {}
+    for f in ("rrtmg_lw_ref.bin", "rrtmg_lw_kg_synth.bin", "rrtmg_sw_kg.bin"):
+        blobs.update(g.bt.read_blob(os.path.join(gpu.DATA_DIR, f)))
+    try:
+        gpu.finalize()
+        for kind in ("lw", "sw"):
+            for name, _, _, shape in g.table_list(kind):
+                gpu.set_table(name, np.asfortranarray(blobs[name]).reshape(shape, order="F"))
+        gpu.set_table("lwmeta.synthetic", np.array([1.0]))
+        gpu.rrtmg_lw_ini(default_tables=False, allow_synthetic_lw=True)
+        gpu.rrtmg_sw_ini(default_tables=False)
+        for n in probe:
+            assert np.array_equal(gpu.get_table(n), before[n]), n
+        cols = make_columns("T42L40", nlon=16, nlat=4)
+        a = gpu.lw_from_columns(cols) + gpu.sw_from_columns(cols)
+    finally:
+        gpu.finalize()
+        gpu.rrtmg_lw_ini(allow_synthetic_lw=True)
+        gpu.rrtmg_sw_ini()
+    b = gpu.lw_from_columns(cols) + gpu.sw_from_columns(cols)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_reference_golden_vectors(gpu):
     """The CUDA path against outputs of the reference's own code (tests/golden/ref_t42l40.npz: the reference's RRTMG
     sources machine-translated F90 -> C and run on config C4 columns, tests/golden/make_ref_vectors.py) -- no oracle in
