@@ -219,10 +219,11 @@ typedef struct rrtmg_b200_rad_config {
     int do_fixed_water;            /* :638-646 */
     int do_zm_tracers;             /* feed the zonal mean of q (:622-626) */
     int do_rad_time_avg;           /* average cos(zenith) over dt_rad_avg (:562-566) */
-    int dt_rad_avg;                /* seconds; already resolved as in rrtm_radiation_init :336-340 */
+    int dt_rad_avg;                /* seconds; already resolved as in rrtm_radiation_init :336-340 (< 0 is an error here) */
     int lonstep;                   /* sub-sample longitudes (:163, :652) */
     int do_zm_rad;                 /* zonal-mean heating and surface fluxes (:768-769, :800-802) */
-    int use_dyofyr;                /* astro_nml: let RRTMG compute the Earth-Sun distance from the day of year */
+    int use_dyofyr;                /* astro_nml: let RRTMG compute the Earth-Sun distance from the day of year; needs
+                                    * days_per_year = 365 (astro.f90:99-104 is FATAL otherwise; an error here) */
     int solday;                    /* astro_nml: perpetual day if > 0 */
     int days_per_year;             /* length_of_year() of the model calendar (360 for MiMA's thirty_day_months) */
     double scale_ozone, o3_val;

@@ -36,6 +36,17 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA sources and headers: profiles/traffic.json is stamped with it (tools/make_traffic.py), and
+    bench.py reports the ncu-measured DRAM traffic only while the stamp matches the tree it runs."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted([x for x, _ in SOURCES] + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -59,7 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(item):
         src, fmad = item
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = cc + NVCC_FLAGS + ["-fmad=true" if fmad else "-fmad=false"] + (["-Xptxas", "-v"] if verbose else []) + \
+        dev = ["-DRRTMG_B200_DEV_VARIANTS"] if os.environ.get("RRTMG_B200_DEV_VARIANTS") == "1" else []
+        cmd = cc + NVCC_FLAGS + dev + ["-fmad=true" if fmad else "-fmad=false"] + (["-Xptxas", "-v"] if verbose else []) + \
             ["-c", "-o", obj, src]
         r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         return obj, r
@@ -79,5 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# RRTMG_B200_DEV_VARIANTS=1 in the environment also compiles the earlier kernel forms (SW solver variants 0-3, the
+# direct-load lw_rtrn) that tests/test_gpu_parity.py::test_sw_solver_variants_agree compares when they are present.
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

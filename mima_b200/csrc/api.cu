@@ -67,6 +67,18 @@ struct State {
     bool sw_have_cld = false;
     SwWork sw_last{};
     int sw_last_ncol = 0;
+    // option "share_inputs": rrtmg_b200_sw keeps its device copies of the eleven arrays both codes read (play, plev, tlay,
+    // tlev, tsfc, h2o, o3, co2, ch4, n2o, o2) as full-batch arrays, and the rrtmg_b200_lw call that follows it with the
+    // same host pointers and sizes uses them instead of uploading again (run_rrtmg passes the same arrays to both,
+    // rrtm_radiation.f90:686-712 and 722-748).  One shot: any other call forgets the copies.
+    bool share_inputs = false;
+    struct Shared {
+        bool valid = false;
+        int ncol = 0, nlay = 0;
+        const double *host[11] = {};
+        double *dev[11] = {};
+        DevBuf buf;
+    } shared;
 };
 State G;
 
@@ -831,6 +843,13 @@ struct Pipe {
     }
 };
 Pipe P_lw, P_sw;
+// error exit of a pipelined host call: copies of the other block may still be in flight to or from the caller's buffers
+int drain(Pipe &P, int rc)
+{
+    for (int i = 0; i < 2; ++i)
+        if (P.st[i]) cudaStreamSynchronize(P.st[i]);
+    return rc;
+}
 
 struct Slot {                 // bump allocator over one slot's device buffer + the chunk being copied
     char *base;
@@ -853,6 +872,15 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
             : cudaMemcpy2DAsync(d, (size_t)nc * 8, h + c0, (size_t)ncol * 8, (size_t)nc * 8, rows, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) ok = false;
         return d;
+    }
+    // host (ncol, rows) columns [c0, c0+nc) -> the same columns of a full-batch device array (ncol, rows); returns the
+    // pointer to column c0 (leading dimension ncol)
+    const double *up_full(const double *h, double *dfull, size_t rows)
+    {
+        if (!h) return nullptr;
+        const cudaError_t e = cudaMemcpy2DAsync(dfull + c0, (size_t)ncol * 8, h + c0, (size_t)ncol * 8, (size_t)nc * 8, rows, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) ok = false;
+        return dfull + c0;
     }
     const double *up_banded(const double *h, size_t nb, size_t rows)   // host (nb, ncol, rows) -> device (nb, nc, rows)
     {
@@ -968,12 +996,19 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
                           const double *z_full, const double *z_half, const double *t_half_in, const double *o3f,
                           double *tdt, double *coszen, double *flux_sw, double *flux_lw, double *tdt_rad,
                           double *tdt_sw, double *tdt_lw, double *olr, double *isr, double *t_half_out,
-                          cudaStream_t st, DrvSlot &S, bool own_work)
+                          cudaStream_t st, DrvSlot &S, bool own_work, int top_flag = -1)
 {
     if (!G.lw_ready || !G.sw_ready) return fail(RRTMG_B200_ERR_NOT_INITIALIZED, "run_rrtmg: rrtmg_b200_lw_init / sw_init have not been called");
     if (si < 1 || sj < 1 || sk < 2 || sk > MAXLAY) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: grid extents out of range");
     if (c.lonstep < 1 || si % c.lonstep != 0) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: lonstep must divide the number of longitudes");
     if (c.days_per_year < 1) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: days_per_year must be positive");
+    // astro.f90:99-104: `use_dyofyr is TRUE but the calendar year does not have 365 days. STOPPING` (FATAL)
+    if (c.use_dyofyr && c.days_per_year != 365)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: use_dyofyr needs a 365-day calendar (astro.f90:99-104)");
+    // rrtm_radiation_init resolves dt_rad_avg < 0 to dt_rad (:336-340); dt_rad is not part of this interface, so the
+    // caller must pass the resolved value
+    if (c.do_rad_time_avg && c.dt_rad_avg < 0)
+        return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: dt_rad_avg < 0 must be resolved to dt_rad by the caller (rrtm_radiation.f90:336-340)");
     if (!lat || !lon || !p_full || !p_half || !albedo || !q || !t || !t_surf || !coszen)
         return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: required array is NULL");
     if (!t_half_in && (!z_full || !z_half)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "run_rrtmg: need t_half or z_full + z_half");
@@ -1040,7 +1075,7 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
     pa.scale_ozone = c.scale_ozone; pa.o3_val = c.o3_val;
     pa.do_fixed_water = c.do_fixed_water; pa.fixed_water = c.fixed_water; pa.fixed_water_pres = c.fixed_water_pres;
     pa.fixed_water_lat = c.fixed_water_lat;
-    G.launches += drv_pack(g, pa, c.do_zm_tracers ? qzm_buf : nullptr, flag, st);
+    G.launches += drv_pack(g, pa, c.do_zm_tracers ? qzm_buf : nullptr, flag, st, top_flag);
     // the two RRTMG calls with MiMA's fixed switches (icld = iaer = idrv = 0, emis = 1, tauaer = 0)
     int icld = 0, iaer = 0;
     SwIn sin{(int)nc, pfull, phalf, tfull, thalf, tsrf, h2o, o3, gas[0],
@@ -1177,6 +1212,7 @@ int rrtmg_b200_finalize(void)
         if (S.join) { cudaEventDestroy(S.join); S.join = nullptr; }
     }
     D.gas.release(); D.misc.release();
+    G.shared.buf.release(); G.shared.valid = false;
     D.gas_set = false; D.gas_n = 0;
     G.lw_ready = G.sw_ready = false;
     G.lw_last_ncol = G.sw_last_ncol = 0;
@@ -1259,14 +1295,23 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
     for (int i = 0; i < nslot; ++i)
         if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes))
             return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW pipeline buffers");
+    // inputs left on the device by the rrtmg_b200_sw call just before (option share_inputs)?
+    const double *hp[11] = {play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr};
+    bool shared = G.share_inputs && G.shared.valid && G.shared.ncol == ncol && G.shared.nlay == nlay;
+    for (int k = 0; shared && k < 11; ++k) shared = G.shared.host[k] == hp[k];
+    // the interface arrays of a block share one leading dimension: with LW-only array inputs (uploaded per block) present
+    // the shared full-batch copies are not used
+    if (cfc11vmr || cfc12vmr || cfc22vmr || ccl4vmr || emis || tauaer || cloud || fields) shared = false;
+    G.shared.valid = false;
     int idx = 0;
     for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
         const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
         const int slot = idx & 1;
         cudaStream_t st = P_lw.st[slot];
         Slot a{(char *)P_lw.in[slot].p, 0, c0, nc, ncol, st, true};
-        LwIn in{nc, a.up(play, L), a.up(plev, V), a.up(tlay, L), a.up(tlev, V), a.up(tsfc, 1),
-                a.up(h2ovmr, L), a.up(o3vmr, L), a.up(co2vmr, L), a.up(ch4vmr, L), a.up(n2ovmr, L), a.up(o2vmr, L),
+        auto in11 = [&](int k, const double *h, size_t rows) { return shared ? (h ? G.shared.dev[k] + c0 : nullptr) : a.up(h, rows); };
+        LwIn in{shared ? ncol : nc, in11(0, play, L), in11(1, plev, V), in11(2, tlay, L), in11(3, tlev, V), in11(4, tsfc, 1),
+                in11(5, h2ovmr, L), in11(6, o3vmr, L), in11(7, co2vmr, L), in11(8, ch4vmr, L), in11(9, n2ovmr, L), in11(10, o2vmr, L),
                 a.up(cfc11vmr, L), a.up(cfc12vmr, L), a.up(cfc22vmr, L), a.up(ccl4vmr, L), a.up(emis, 16), a.up(tauaer, 16 * L)};
         if (cloud) {
             LwOpt dopt{inflglw, a.up(cldfr, L), a.up_banded(taucld, 16, L), iceflglw, liqflglw,
@@ -1274,15 +1319,15 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
                        inflglw == 2 ? a.up(reice, L) : nullptr, inflglw == 2 ? a.up(reliq, L) : nullptr};
             lw_set_optional(in, icld, dopt);
         }
-        if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)");
+        if (!a.ok) return drain(P_lw, fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (LW)"));
         Slot o{(char *)P_lw.out[slot].p, 0, c0, nc, ncol, st, true};
         LwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
         if (idrv == 1) { out.duflx_dt = o.take(V); out.duflxc_dt = o.take(V); }
-        if (const int rc = lw_chunk(in, out, nc, nlay, P_lw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
+        if (const int rc = lw_chunk(in, out, nc, nlay, P_lw.work[slot].p, fields, st, c0 + nc >= ncol)) return drain(P_lw, rc);
         if (idrv == 1) { o.down(duflx_dt, out.duflx_dt, V); o.down(duflxc_dt, out.duflxc_dt, V); }
         o.down(uflx, out.uflx, V); o.down(dflx, out.dflx, V); o.down(hr, out.hr, L);
         o.down(uflxc, out.uflxc, V); o.down(dflxc, out.dflxc, V); o.down(hrc, out.hrc, L);      // skipped when NULL
-        if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)");
+        if (!o.ok) return drain(P_lw, fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (LW)"));
     }
     for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_lw.st[i]));
     return lw_err_end(cloud);
@@ -1347,15 +1392,33 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
         if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes))
             return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW pipeline buffers");
     const double adjflux = sw_adjflux(adjes, dyofyr, scon);
+    // option share_inputs: the eleven arrays rrtmg_lw reads too are uploaded into full-batch device arrays and kept
+    const bool share = G.share_inputs && !general && !fields;
+    G.shared.valid = false;
+    if (share) {
+        const size_t rows[11] = {L, V, L, V, 1, L, L, L, L, L, L};
+        const double *hp[11] = {play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr};
+        size_t total = 0;
+        for (int k = 0; k < 11; ++k) total += hp[k] ? (((size_t)ncol * rows[k] * 8 + 255) & ~(size_t)255) : 0;
+        if (G.shared.buf.ensure(total + 256)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the shared inputs");
+        size_t off = 0;
+        for (int k = 0; k < 11; ++k) {
+            G.shared.host[k] = hp[k];
+            G.shared.dev[k] = hp[k] ? (double *)((char *)G.shared.buf.p + off) : nullptr;
+            off += hp[k] ? (((size_t)ncol * rows[k] * 8 + 255) & ~(size_t)255) : 0;
+        }
+        G.shared.ncol = ncol; G.shared.nlay = nlay;
+    }
     int idx = 0;
     for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
         const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
         const int slot = idx & 1;
         cudaStream_t st = P_sw.st[slot];
         Slot a{(char *)P_sw.in[slot].p, 0, c0, nc, ncol, st, true};
-        const double *d_play = a.up(play, L), *d_plev = a.up(plev, V), *d_tlay = a.up(tlay, L), *d_tlev = a.up(tlev, V);
-        const double *d_tsfc = a.up(tsfc, 1), *d_h2o = a.up(h2ovmr, L), *d_o3 = a.up(o3vmr, L), *d_co2 = a.up(co2vmr, L);
-        const double *d_ch4 = a.up(ch4vmr, L), *d_n2o = a.up(n2ovmr, L), *d_o2 = a.up(o2vmr, L);
+        auto in11 = [&](int k, const double *h, size_t rows) { return share ? a.up_full(h, G.shared.dev[k], rows) : a.up(h, rows); };
+        const double *d_play = in11(0, play, L), *d_plev = in11(1, plev, V), *d_tlay = in11(2, tlay, L), *d_tlev = in11(3, tlev, V);
+        const double *d_tsfc = in11(4, tsfc, 1), *d_h2o = in11(5, h2ovmr, L), *d_o3 = in11(6, o3vmr, L), *d_co2 = in11(7, co2vmr, L);
+        const double *d_ch4 = in11(8, ch4vmr, L), *d_n2o = in11(9, n2ovmr, L), *d_o2 = in11(10, o2vmr, L);
         // MiMA passes the same albedo array four times (rrtm_radiation.f90:690): upload once per distinct pointer
         const double *d_asdir = a.up(asdir, 1);
         const double *d_asdif = asdif == asdir ? d_asdir : a.up(asdif, 1);
@@ -1375,18 +1438,19 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
         }
         if (aer) { dopt.tauaer = a.up(tauaer, 14 * L); dopt.ssaaer = a.up(ssaaer, 14 * L); dopt.asmaer = a.up(asmaer, 14 * L); }
         if (aer6) dopt.ecaer = a.up(ecaer, 6 * L);
-        if (!a.ok) return fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)");
-        SwIn in{nc, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2, d_ch4, d_n2o, d_o2,
+        if (!a.ok) return drain(P_sw, fail(RRTMG_B200_ERR_CUDA, "H2D copy failed (SW)"));
+        SwIn in{share ? ncol : nc, d_play, d_plev, d_tlay, d_tlev, d_tsfc, d_h2o, d_o3, d_co2, d_ch4, d_n2o, d_o2,
                 d_asdir, d_asdif, d_aldir, d_aldif, d_cosz, adjflux};
         sw_set_optional(in, icld, iaer, dopt);
         Slot o{(char *)P_sw.out[slot].p, 0, c0, nc, ncol, st, true};
         SwOut out{nc, o.take(V), o.take(V), o.take(L), o.take(V), o.take(V), o.take(L)};
-        if (const int rc = sw_chunk(in, out, nc, nlay, P_sw.work[slot].p, fields, st, c0 + nc >= ncol)) return rc;
+        if (const int rc = sw_chunk(in, out, nc, nlay, P_sw.work[slot].p, fields, st, c0 + nc >= ncol)) return drain(P_sw, rc);
         o.down(swuflx, out.uflx, V); o.down(swdflx, out.dflx, V); o.down(swhr, out.hr, L);
         o.down(swuflxc, out.uflxc, V); o.down(swdflxc, out.dflxc, V); o.down(swhrc, out.hrc, L);
-        if (!o.ok) return fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (SW)");
+        if (!o.ok) return drain(P_sw, fail(RRTMG_B200_ERR_CUDA, "D2H copy failed (SW)"));
     }
     for (int i = 0; i < nslot; ++i) CUDA_OK(cudaStreamSynchronize(P_sw.st[i]));
+    G.shared.valid = share;
     return sw_err_end(general);
 }
 
@@ -1572,6 +1636,12 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
         if (!S.st && cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess) return fail(RRTMG_B200_ERR_CUDA, "cudaStreamCreate failed");
         if (S.host_in.ensure(hin) || S.host_out.ensure(hout)) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed (run_rrtmg host staging)");
     }
+    // run_rrtmg replaces the top interface pressure of ALL the rank's columns when the smallest one is not positive
+    // (rrtm_radiation.f90:655-656): decided here over the whole field, not per row block
+    int top_flag = 0;
+    for (int j = 0; j < sj && !top_flag; ++j)
+        for (int ii = 0; ii < si; ii += cfg->lonstep)
+            if (p_half[(size_t)ii + (size_t)si * j] * 0.01 <= 0.0) { top_flag = 1; break; }
     int idx = 0;
     for (int j0 = 0; j0 < sj; j0 += rows, ++idx) {
         const int nr = (sj - j0 < rows) ? sj - j0 : rows;
@@ -1593,8 +1663,10 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
         double *d_tho = t_half_out ? o.take(V) : nullptr;
         if (const int rc = run_rrtmg_device_impl(*cfg, si, nr, sk, seconds, days, d_lat, d_lon, d_pf, d_ph, d_alb, d_q, d_t, d_ts,
                                                  d_zf, d_zh, d_th, d_o3, d_tdt, d_cz, d_fsw, d_flw, d_trad, d_tsw, d_tlw,
-                                                 d_olr, d_isr, d_tho, st, S, true))
+                                                 d_olr, d_isr, d_tho, st, S, true, top_flag)) {
+            for (int i = 0; i < nslot; ++i) cudaStreamSynchronize(D.slot[i].st);
             return rc;
+        }
         if (tdt) o.down(tdt, d_tdt, L);
         o.down(coszen, d_cz, 1);
         if (flux_sw) o.down(flux_sw, d_fsw, 1);
@@ -1628,11 +1700,20 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "run_chunk") { G.run_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
+    if (k == "share_inputs") { G.share_inputs = value != 0; G.shared.valid = false; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "taumol_sync") { g_tune.taumol_sync = (int)value; return RRTMG_B200_OK; }
+#ifdef RRTMG_B200_DEV_VARIANTS
+    if (k == "dev_variants") return RRTMG_B200_OK;
     if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_variant") { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
     if (k == "sw_solver_store") { g_tune.sw_solver_store = (int)value; return RRTMG_B200_OK; }
+#else
+    // the earlier kernel forms (SW solver variants 0-3, direct-load lw_rtrn) exist in development builds only
+    // (RRTMG_B200_DEV_VARIANTS=1 python -m mima_b200.build --force)
+    if (k == "lw_rtrn_variant" && value >= 2) { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
+    if (k == "sw_solver_variant" && value >= 4) { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
+#endif
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "taumol_bin") { g_tune.taumol_bin = (int)value; return RRTMG_B200_OK; }
     if (k == "taumol_order") { g_tune.taumol_order = (int)value; return RRTMG_B200_OK; }

@@ -263,12 +263,13 @@ int drv_interp_temp(int np, int sk, const double *z_full, const double *z_half, 
     interp_temp_kernel<<<nblk((size_t)np * (sk + 1), 256), 256, 0, s>>>(np, sk, z_full, z_half, t_surf, t, t_half);
     return 1;
 }
-int drv_pack(const RadGeom &g, const PackArgs &a, double *qzm_buf, int *flag, cudaStream_t s)
+int drv_pack(const RadGeom &g, const PackArgs &a, double *qzm_buf, int *flag, cudaStream_t s, int top_flag)
 {
     int n = 0;
     PackArgs b = a;
-    cudaMemsetAsync(flag, 0, sizeof(int), s);
-    top_flag_kernel<<<nblk(g.ncols, 256), 256, 0, s>>>(g, a.p_half, flag); ++n;
+    // top_flag >= 0: the caller has evaluated the test over the rank's whole field (a row block must not decide it alone)
+    cudaMemsetAsync(flag, top_flag > 0 ? 1 : 0, sizeof(int), s);
+    if (top_flag < 0) { top_flag_kernel<<<nblk(g.ncols, 256), 256, 0, s>>>(g, a.p_half, flag); ++n; }
     b.top_flag = flag;
     if (qzm_buf) {
         zonal_mean_kernel<<<nblk((size_t)g.sj * g.sk, 128), 128, 0, s>>>(g.si, g.sj * g.sk, a.q, qzm_buf); ++n;

@@ -77,6 +77,7 @@ __device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double 
     }
 }
 
+#ifdef RRTMG_B200_DEV_VARIANTS       // direct-load form of the clear-sky kernel (option lw_rtrn_variant = 0, 1): development builds only
 // The Planck sources of the column ([lay][16] and [lev][16], 16 KB at 60 layers) are staged in shared memory
 // once per block: the 140 g-threads need them 2-3 times per level and they are shared by all g-points of a band.
 // WR: warp-local g-sums -- every warp adds up its own 32 lanes per level (batches of 8 levels through a
@@ -260,6 +261,8 @@ __global__ void __launch_bounds__(RT_THREADS) lw_rtrn_kernel(LwTables T, LwIn in
     }
 }
 
+
+#endif  // RRTMG_B200_DEV_VARIANTS
 
 // =====================================================================================================
 // Variant 2: the staging rows arrive by TMA.  The column streams through a ring of NST shared-memory stages
@@ -946,12 +949,16 @@ int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &
                else lw_rtrn_cloud_kernel<false, false><<<w.nc, RT_THREADS, 0, s>>>(t, in, out, w); }
         return 1;
     }
-    if (g_tune.lw_rtrn_variant >= 2 || w.idrv) {        // the derivative outputs are built in the TMA kernel only
+#ifdef RRTMG_B200_DEV_VARIANTS
+    if (g_tune.lw_rtrn_variant >= 2 || w.idrv)          // the derivative outputs are built in the TMA kernel only
+#endif
+    {
         const int v = g_tune.lw_rtrn_variant;
         if (w.nlay <= 64) { if (in.tauaer) launch_tma_pick<true, 64>(t, in, out, w, s, v); else launch_tma_pick<false, 64>(t, in, out, w, s, v); }
         else { if (in.tauaer) launch_tma_pick<true, MAXLAY>(t, in, out, w, s, v); else launch_tma_pick<false, MAXLAY>(t, in, out, w, s, v); }
         return 1;
     }
+#ifdef RRTMG_B200_DEV_VARIANTS
     const bool wr = g_tune.lw_rtrn_variant != 0;
     const size_t smem = (size_t)(2 * w.nlay + 1) * 16 * sizeof(double) + (size_t)g_tune.lw_rtrn_pad_kb * 1024;
 #define RT_LAUNCH(A, W) do { \
@@ -961,6 +968,7 @@ int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &
     else { if (wr) RT_LAUNCH(false, true); else RT_LAUNCH(false, false); }
 #undef RT_LAUNCH
     return 1;
+#endif
 }
 
 } // namespace rrtmg

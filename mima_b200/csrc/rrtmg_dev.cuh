@@ -261,7 +261,7 @@ struct UnpackArgs {
 int drv_zenith(int n, const double *lat, const double *lon, double *cosz, const ZenithArgs &a, cudaStream_t s);
 int drv_interp_temp(int np, int sk, const double *z_full, const double *z_half, const double *t_surf, const double *t,
                     double *t_half, cudaStream_t s);
-int drv_pack(const RadGeom &g, const PackArgs &a, double *qzm_buf, int *flag, cudaStream_t s);
+int drv_pack(const RadGeom &g, const PackArgs &a, double *qzm_buf, int *flag, cudaStream_t s, int top_flag = -1);
 int drv_fill(double *p, size_t n, double v, cudaStream_t s);
 int drv_unpack(const RadGeom &g, const UnpackArgs &a, double *zm_buf, cudaStream_t s);
 

@@ -162,6 +162,7 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
     }
 }
 
+#ifdef RRTMG_B200_DEV_VARIANTS       // the earlier forms of the clear-sky solver (option sw_solver_variant = 0..3): development builds only
 // OPT bit 0: one-Newton reciprocals outside the table-index paths; bit 1: block-level g-sum in batches of 4 levels;
 // bit 2: warp-local g-sums (no block barrier inside the sweep)
 template <int LMAX, bool STORE, int OPT>
@@ -544,6 +545,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
     }
 }
 
+
+#endif  // RRTMG_B200_DEV_VARIANTS
 
 // =====================================================================================================
 // The default clear-sky solver: the top-down-first scheme of sw_solver_kernel (OPT bit 4, derivation there) with one
@@ -1216,6 +1219,7 @@ __global__ void __launch_bounds__(SV_THREADS) sw_solver_gen_kernel(SwTables T, S
     }
 }
 
+#ifdef RRTMG_B200_DEV_VARIANTS
 template <int LMAX, bool STORE, int OPT>
 static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
@@ -1223,18 +1227,21 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
     if (pad) cudaFuncSetAttribute(sw_solver_kernel<LMAX, STORE, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
     sw_solver_kernel<LMAX, STORE, OPT><<<(w.nc + SV_COLS - 1) / SV_COLS, SV_THREADS, pad, s>>>(t, in, out, w);
 }
+#endif
 template <int LMAX>
 static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
     // variant 3 (default): top-down first, three stored values per cell (OPT 21); 2: bottom-up first, five stored values
     // (OPT 13); 1: reftra recomputed in the second sweep, the reference's recurrences literally (OPT 5); 0: the first
     // version of the kernel (OPT 0).  All use one-Newton reciprocals + warp-local g-sums except 0.
+#ifdef RRTMG_B200_DEV_VARIANTS
     if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
-    if (g_tune.sw_solver_variant == 0) launch<LMAX, false, 0>(t, in, out, w, s);
-    else if (g_tune.sw_solver_variant == 1) launch<LMAX, false, 5>(t, in, out, w, s);
-    else if (g_tune.sw_solver_variant == 2) launch<LMAX, false, 13>(t, in, out, w, s);
-    else if (g_tune.sw_solver_variant == 3) launch<LMAX, false, 21>(t, in, out, w, s);
-    else if (g_tune.sw_solver_variant == 5) {
+    if (g_tune.sw_solver_variant == 0) { launch<LMAX, false, 0>(t, in, out, w, s); return; }
+    if (g_tune.sw_solver_variant == 1) { launch<LMAX, false, 5>(t, in, out, w, s); return; }
+    if (g_tune.sw_solver_variant == 2) { launch<LMAX, false, 13>(t, in, out, w, s); return; }
+    if (g_tune.sw_solver_variant == 3) { launch<LMAX, false, 21>(t, in, out, w, s); return; }
+#endif
+    if (g_tune.sw_solver_variant == 5) {
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nitems = ((long long)w.nc * NGPTSW + 31) / 32;
         static int nsm = 0;
@@ -1283,7 +1290,11 @@ int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork
     }
     if (w.nlay <= 64) launch_opt<64>(t, in, out, w, s);
     else launch_opt<MAXLAY>(t, in, out, w, s);
+#ifdef RRTMG_B200_DEV_VARIANTS
     return (!g_tune.sw_solver_store && g_tune.sw_solver_variant >= 4) ? 2 : 1;
+#else
+    return 2;
+#endif
 }
 
 } // namespace rrtmg

@@ -39,5 +39,11 @@ for f in sys.argv[3:]:
             e["kernels"] = p["kernels"] + e["kernels"]
         out[W][k] = e
         seen.add(k)
+# stamp: the tree these numbers were profiled on (bench.py reports them only while the CUDA sources are unchanged)
+sys.path.insert(0, ROOT)
+from mima_b200.build import source_hash  # noqa: E402
+import datetime  # noqa: E402
+out[W]["_stamp"] = {"csrc_sha256": source_hash(), "when": datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ"),
+                    "how": "ncu --set full --clock-control none, first pass of every kernel (tools/gpu_profile.sh)"}
 json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
-print(json.dumps(out[W], indent=1))
+print(json.dumps({k: v for k, v in out[W].items() if k != "_stamp"}, indent=1))
