@@ -551,8 +551,6 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields, bool cloud
     w.cs_coldry = c.take<double>(np);
     w.cs_wkl1 = c.take<double>(np);
     w.cs_lower = c.take<unsigned char>(np);
-    w.skey = g_tune.taumol_bin ? c.take<uint16_t>(np) : nullptr;
-    w.perm = g_tune.taumol_bin ? c.take<int>(np) : nullptr;
     w.secdiff = c.take<double>((size_t)nc * 16);
     w.planklay = c.take<double>(np * 16);
     w.planklev = c.take<double>((size_t)nc * (nlay + 1) * 16);
@@ -572,8 +570,6 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool gener
     w.laytrop = c.take<int>(nc);
     w.laysolfr = c.take<int>((size_t)nc * 14);
     w.cs_jp = c.take<unsigned char>(np);
-    w.skey = g_tune.taumol_bin ? c.take<uint16_t>(np) : nullptr;
-    w.perm = g_tune.taumol_bin ? c.take<int>(np) : nullptr;
     w.idx = fields ? c.take<uint32_t>(np) : nullptr;
     w.f = fields ? c.take<double>(np * SF_COUNT) : nullptr;
     w.taug = c.take<double>(np * NGPTSW);
@@ -913,7 +909,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 4, 2, 4, 1, 0, 8, {0, 3, 0, 0, 0, 0, 0, 0}};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
+Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1715,9 +1711,6 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "sw_solver_variant" && value >= 4) { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
 #endif
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }
-    if (k == "taumol_bin") { g_tune.taumol_bin = (int)value; return RRTMG_B200_OK; }
-    if (k == "taumol_order") { g_tune.taumol_order = (int)value; return RRTMG_B200_OK; }
-    if (k == "taumol_run") { g_tune.taumol_run = (int)value; return RRTMG_B200_OK; }
     if (k.size() == 2 && k[0] == 'x' && k[1] >= '0' && k[1] <= '7') { g_tune.x[k[1] - '0'] = (int)value; return RRTMG_B200_OK; }
     if (k == "kernel_timing") { KT.collect(); KT.on = value != 0; return RRTMG_B200_OK; }
     return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "unknown option " + k);

@@ -172,16 +172,6 @@ __global__ void __launch_bounds__(128) lw_prep_cell_kernel(LwTables T, LwIn in, 
     w.cs_coldry[i] = p.coldry;
     w.cs_wkl1[i] = wkl1;
     w.cs_lower[i] = lower ? 1 : 0;
-    if (w.skey) {
-        // row key for the cell binning (binning.cu): the binary-species index of the H2O/CO2 bands below, of the
-        // O3/CO2 bands above (taumol.f90, speccomb/specparm/js of taugb3-5)
-        const double a = lower ? p.colh2o : p.colo3;
-        const double rat = lower ? c_lw.rat_h2oco2[p.jp - 1] : c_lw.rat_o3co2[p.jp - 1];
-        double sp = a / (a + rat * p.colco2);
-        if (sp >= c_lw.oneminus) sp = c_lw.oneminus;
-        const int js = 1 + (int)((lower ? 8. : 4.) * sp);
-        w.skey[i] = (uint16_t)bin_key(lower, p.jp, p.jt, p.jt1, js);
-    }
     if (w.f) {
         const size_t wo = i;
         w.idx[wo] = lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm);
@@ -737,7 +727,7 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
 template <int BAND>
 __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool valid, bool lower, double *slab,
                                         double *__restrict__ taug, double *__restrict__ fracs,
-                                        int col, size_t layoff, size_t colstride, int nvalid)
+                                        size_t cell0, size_t colstride, int nvalid)
 {
     constexpr int NG = lw_ng(BAND);
     const int lane = threadIdx.x & 31;
@@ -759,11 +749,10 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
 #pragma unroll
     for (int i = lane; i < 32 * HP; i += 32) {
         const int c = i / HP, j = i - c * HP;
-        const int cc = __shfl_sync(0xffffffffu, col, c);         // column of cell c (binned order: any column)
         if (c < nvalid) {
             const double2 a = reinterpret_cast<const double2 *>(slab + c * TM_STRIDE)[j];
             const double2 b = reinterpret_cast<const double2 *>(slab + (32 + c) * TM_STRIDE)[j];
-            const size_t o = (size_t)cc * colstride + layoff + g0 + 2 * j;
+            const size_t o = cell0 + (size_t)c * colstride + g0 + 2 * j;
             *reinterpret_cast<double2 *>(taug + o) = a;
             *reinterpret_cast<double2 *>(fracs + o) = b;
         }
@@ -776,62 +765,35 @@ __device__ __forceinline__ void lw_band(const LwTables &T, const LwPair &p, bool
 // independent warps the kernel was bound by instruction-cache misses.  Work items are (32-column tile,
 // layer) pairs, linearised so that no warp idles when nlay is not a multiple of the block's warp count.
 constexpr int TM_BLOCK_WARPS = 8;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w, int g_tm_sync, int order, int run)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 2) lw_taumol_kernel(LwTables T, LwIn in, LwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nlay = w.nlay, nc = w.nc;
     const int ntile = (nc + 31) / 32;
+    const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
+    const bool live = item < (long)ntile * nlay;
+    const int tile = live ? (int)(item / nlay) : 0;
+    const int lay = live ? (int)(item - (long)tile * nlay) : 0;     // 0-based layer
+    const int c0 = tile * 32;
+    const int col = c0 + lane;
+    const bool valid = live && col < nc;
+    const int nvalid = live ? min(32, nc - c0) : 0;
+
+    LwPair p;
+    bool lower = false;
+    if (valid) {
+        double wkl1;
+        lw_cell(in, col, lay, p, wkl1);
+        lower = (lay + 1) <= w.laytrop[col];
+    }
     double *slab = s_dyn + (size_t)wid * (64 * TM_STRIDE);
     const size_t colstride = (size_t)nlay * NGPTLW;
-    // Binned cells (w.perm): a block takes `run` consecutive groups of TM_BLOCK_WARPS 32-cell tiles of ONE layer in key
-    // order -- its warps read the same few table rows, and from one group to the next the rows stay in L1 (a block that
-    // starts cold pays one L2 round trip per row with all its warps waiting for the same line).  Blocks are numbered
-    // layer-fastest (order 0) so that the blocks in flight spread over all layers: with one layer in flight every SM
-    // asks the same L2 lines.
-    const int bpl = (ntile + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;       // tile groups per layer
-    const int rpl = (bpl + run - 1) / run;                                // runs per layer
-    int lay0 = 0, tg0 = 0, tg1 = 1;
-    if (w.perm) {
-        const int r = order ? (int)(blockIdx.x % rpl) : (int)(blockIdx.x / nlay);
-        lay0 = order ? (int)(blockIdx.x / rpl) : (int)(blockIdx.x % nlay);
-        tg0 = r * run;
-        tg1 = min(bpl, tg0 + run);
-    }
-    for (int tg = tg0; tg < tg1; ++tg) {
-        bool live;
-        int tile, lay;
-        if (w.perm) {
-            lay = lay0;
-            tile = tg * TM_BLOCK_WARPS + wid;
-            live = tile < ntile;
-            if (!live) tile = 0;
-        } else {
-            // work items are (32-column tile, layer) pairs, linearised so that no warp idles when nlay is not a
-            // multiple of the block's warp count
-            const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
-            live = item < (long)ntile * nlay;
-            tile = live ? (int)(item / nlay) : 0;
-            lay = live ? (int)(item - (long)tile * nlay) : 0;     // 0-based layer
-        }
-        const int c0 = tile * 32;
-        const bool valid = live && c0 + lane < nc;
-        const int col = !valid ? 0 : (w.perm ? w.perm[(size_t)lay * nc + c0 + lane] : c0 + lane);
-        const int nvalid = live ? min(32, nc - c0) : 0;
-
-        LwPair p;
-        bool lower = false;
-        if (valid) {
-            double wkl1;
-            lw_cell(in, col, lay, p, wkl1);
-            lower = (lay + 1) <= w.laytrop[col];
-        }
-        const size_t layoff = (size_t)lay * NGPTLW;
-#define LW_BAND(b) lw_band<b>(T, p, valid, lower, slab, w.taug, w.fracs, col, layoff, colstride, nvalid); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
-        LW_BAND(0); LW_BAND(1); LW_BAND(2); LW_BAND(3); LW_BAND(4); LW_BAND(5); LW_BAND(6); LW_BAND(7);
-        LW_BAND(8); LW_BAND(9); LW_BAND(10); LW_BAND(11); LW_BAND(12); LW_BAND(13); LW_BAND(14); LW_BAND(15);
+    const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTLW;
+#define LW_BAND(b) lw_band<b>(T, p, valid, lower, slab, w.taug, w.fracs, cell0, colstride, nvalid); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
+    LW_BAND(0); LW_BAND(1); LW_BAND(2); LW_BAND(3); LW_BAND(4); LW_BAND(5); LW_BAND(6); LW_BAND(7);
+    LW_BAND(8); LW_BAND(9); LW_BAND(10); LW_BAND(11); LW_BAND(12); LW_BAND(13); LW_BAND(14); LW_BAND(15);
 #undef LW_BAND
-    }
 }
 
 // =====================================================================================================
@@ -948,19 +910,13 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
     ktimer_begin(K_LW_PREP, s);
     lw_prep_cell_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(t, in, w);
     lw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(t, in, w);
-    int nbin = 0;
-    if (w.perm) nbin = bin_cells(w.skey, w.perm, w.nc, w.nlay, s);
     ktimer_end(s);
     {
-        const int ntile = (w.nc + 31) / 32;
-        const long items = (long)ntile * w.nlay;
-        const int bpl = (ntile + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;
-        const int run = g_tune.taumol_run > 0 ? g_tune.taumol_run : 1;
-        const long nblk = w.perm ? (long)((bpl + run - 1) / run) * w.nlay : (items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;
+        const long items = (long)((w.nc + 31) / 32) * w.nlay;
         const size_t smem = (size_t)TM_BLOCK_WARPS * 64 * TM_STRIDE * sizeof(double);
         cudaFuncSetAttribute(lw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ktimer_begin(K_LW_TAUMOL, s);
-        lw_taumol_kernel<<<(unsigned)nblk, 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1, g_tune.taumol_order, run);
+        lw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1);
         ktimer_end(s);
     }
     if (cap) {
@@ -973,7 +929,7 @@ int lw_run_pass(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, 
     ktimer_begin(K_LW_RTRN, s);
     const int nrt = lw_launch_rtrn(t, in, out, w, s);
     ktimer_end(s);
-    return 3 + nbin + nrt + ncld;
+    return 3 + nrt + ncld;
 }
 
 } // namespace rrtmg

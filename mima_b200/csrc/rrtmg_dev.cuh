@@ -120,8 +120,6 @@ struct LwWork {
     int *laytrop;             // [col]
     double *cs_coldry, *cs_wkl1;   // [lay][col]: per-cell terms of the column sums (lw_prep_cell -> lw_prep)
     unsigned char *cs_lower;       // [lay][col]: plog > 4.56
-    uint16_t *skey;           // [lay][col]: k-table row key of the cell (cell binning, see binning.cu); null = off
-    int *perm;                // [lay][pos]: columns of the layer ordered by skey
     double *f;                // LF_COUNT fields, each [lay][col]
     double *secdiff;          // [col][16]
     double *planklay;         // [col][lay][16]
@@ -209,8 +207,6 @@ struct SwWork {
     uint32_t *idx;            // [lay][col]
     int *laytrop;             // [col]
     unsigned char *cs_jp;     // [lay][col]: jp | 0x80 * (plog > 4.56)  (sw_prep_cell -> sw_prep)
-    uint16_t *skey;           // [lay][col]: k-table row key of the cell (binning.cu; night cells = BIN_NIGHT); null = off
-    int *perm;                // [lay][pos]: columns of the layer ordered by skey
     int *laysolfr;            // [col][14]: layer (1-based) whose eta selects the solar source; 0 = never written
     double *f;                // SF_COUNT fields, each [lay][col]
     double *taug;             // [col][lay][112]
@@ -332,25 +328,9 @@ void ktimer_end(cudaStream_t s);
 // used to cap the resident blocks per SM so that the sweeps' per-thread state stays L2-resident
 struct Tuning {
     int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant, lw_rtrn_variant, taumol_sync;
-    int taumol_bin;           // 1: taumol warps take cells binned by k-table row key (binning.cu); 0: 32 adjacent columns
-    int taumol_order;         // block order of the binned taumol kernels: 0 layer fastest, 1 layer slowest
-    int taumol_run;           // consecutive tile groups of a layer per block of the binned taumol kernels
     int x[8];                 // experiment knobs ("x0".."x7")
 };
 extern Tuning g_tune;
-
-// ------------------------------------------------------------------------------------ cell binning (binning.cu)
-// A taumol warp reads the same k-table rows for all 32 lanes only if its cells share the interpolation indices.  The
-// prep kernels give every (layer, column) cell a 14-bit key
-//     lower:1 | jp-1:6 | jt-1:2 | jt1-1:2 | js-1:3      (js: binary-species index of the H2O/CO2 resp. O3/CO2 bands)
-// and bin_cells() orders the columns of each layer by it (counting sort in shared memory, one block per layer).
-constexpr int BIN_BITS = 14, BIN_COUNT = 1 << BIN_BITS;
-constexpr int BIN_NIGHT = BIN_COUNT - 1;      // SW: cells of night columns, ordered last and skipped
-__host__ __device__ inline int bin_key(bool lower, int jp, int jt, int jt1, int js)
-{
-    return ((lower ? 1 : 0) << 13) | ((jp - 1) << 7) | ((jt - 1) << 5) | ((jt1 - 1) << 3) | (js - 1);
-}
-int bin_cells(const uint16_t *skey, int *perm, int nc, int nlay, cudaStream_t s);   // returns the launch count
 
 // solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)
 int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb);

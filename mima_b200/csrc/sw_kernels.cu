@@ -131,22 +131,10 @@ __global__ void __launch_bounds__(128) sw_prep_cell_kernel(SwIn in, SwWork w)
     if (i >= (size_t)nc * nlay) return;
     const int l = (int)(i / nc);
     const int col = (int)(i - (size_t)l * nc);
-    if (in.coszen[col] < ZEPZEN) {             // night column: nothing downstream reads it
-        if (w.skey) w.skey[i] = (uint16_t)BIN_NIGHT;
-        return;
-    }
+    if (in.coszen[col] < ZEPZEN) return;       // night column: nothing downstream reads it
     SwPair p;
     const bool lower = sw_cell(in, col, l, p);
     w.cs_jp[i] = (unsigned char)(p.jp | (lower ? 0x80 : 0));
-    if (w.skey) {
-        // row key for the cell binning (binning.cu): the H2O/CO2 binary-species index of band 17 (taumol17,
-        // sw taumol.f90:342-462; strrat 0.364641), 8 intervals below laytrop and 4 above
-        double sp = p.colh2o / (p.colh2o + 0.364641 * p.colco2);
-        if (sp >= c_sw.oneminus) sp = c_sw.oneminus;
-        const int js = 1 + (int)((lower ? 8. : 4.) * sp);
-        int k = bin_key(lower, p.jp, p.jt, p.jt1, js);
-        w.skey[i] = (uint16_t)(k >= BIN_NIGHT ? BIN_NIGHT - 1 : k);
-    }
     if (w.f) {
         const size_t wo = i;
         w.idx[wo] = sw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf);
@@ -475,7 +463,7 @@ template <int BAND>
 __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool valid, bool lower, int lay1,
                                         const int *__restrict__ laysolfr, double *slab,
                                         double *__restrict__ taug, double *t24, double *sflx_col,
-                                        int col, size_t layoff, size_t colstride, unsigned vmask)
+                                        size_t cell0, size_t colstride, unsigned vmask)
 {
     constexpr int NG = sw_ng(BAND);
     const int lane = threadIdx.x & 31;
@@ -497,10 +485,9 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
 #pragma unroll
     for (int i = lane; i < 32 * HP; i += 32) {
         const int c = i / HP, j = i - c * HP;
-        const int cc = __shfl_sync(0xffffffffu, col, c);         // column of cell c (binned order: any column)
         if ((vmask >> c) & 1u) {
             const double2 a = reinterpret_cast<const double2 *>(slab + c * TM_STRIDE)[j];
-            *reinterpret_cast<double2 *>(taug + (size_t)cc * colstride + layoff + g0 + 2 * j) = a;
+            *reinterpret_cast<double2 *>(taug + cell0 + (size_t)c * colstride + g0 + 2 * j) = a;
         }
     }
     __syncwarp();
@@ -509,64 +496,42 @@ __device__ __forceinline__ void sw_band(const SwTables &T, const SwPair &p, bool
 // As in the LW kernel: 16 warps per block step through the bands together (instruction-cache reuse);
 // work items are linearised (32-column tile, layer) pairs.
 constexpr int TM_BLOCK_WARPS = 4;
-__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w, int g_tm_sync, int order, int run)
+__global__ void __launch_bounds__(32 * TM_BLOCK_WARPS, 4) sw_taumol_kernel(SwTables T, SwIn in, SwWork w, int g_tm_sync)
 {
     extern __shared__ __align__(16) double s_dyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nlay = w.nlay, nc = w.nc;
     const int ntile = (nc + 31) / 32;
+    const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
+    const bool live = item < (long)ntile * nlay;
+    const int tile = live ? (int)(item / nlay) : 0;
+    const int lay = live ? (int)(item - (long)tile * nlay) : 0;
+    const int c0 = tile * 32;
+    const int col = c0 + lane;
+    bool valid = live && col < nc;
+    int laytrop = 0;
+    if (valid) {
+        laytrop = w.laytrop[col];
+        if (laytrop < 0) valid = false;              // night column: the solver never reads its staging
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    SwPair p;
+    bool lower = false;
+    if (valid) {
+        sw_cell(in, col, lay, p);
+        lower = (lay + 1) <= laytrop;
+    }
     double *slab = s_dyn + (size_t)wid * (32 * TM_STRIDE);
+    double *t24 = w.taur24 + ((size_t)(valid ? col : 0) * nlay + lay) * 8;
+    if (valid) w.colmol[(size_t)col * nlay + lay] = p.colmol;
+    const int *ls = w.laysolfr + (size_t)(valid ? col : 0) * 14;
+    double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
     const size_t colstride = (size_t)nlay * NGPTSW;
-    // binned cells (see lw_taumol_kernel): `run` consecutive tile groups of one layer per block; the cells of night
-    // columns are ordered last
-    const int bpl = (ntile + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;
-    const int rpl = (bpl + run - 1) / run;
-    int lay0 = 0, tg0 = 0, tg1 = 1;
-    if (w.perm) {
-        const int r = order ? (int)(blockIdx.x % rpl) : (int)(blockIdx.x / nlay);
-        lay0 = order ? (int)(blockIdx.x / rpl) : (int)(blockIdx.x % nlay);
-        tg0 = r * run;
-        tg1 = min(bpl, tg0 + run);
-    }
-    for (int tg = tg0; tg < tg1; ++tg) {
-        bool live;
-        int tile, lay;
-        if (w.perm) {
-            lay = lay0;
-            tile = tg * TM_BLOCK_WARPS + wid;
-            live = tile < ntile;
-            if (!live) tile = 0;
-        } else {
-            const long item = (long)blockIdx.x * TM_BLOCK_WARPS + wid;
-            live = item < (long)ntile * nlay;
-            tile = live ? (int)(item / nlay) : 0;
-            lay = live ? (int)(item - (long)tile * nlay) : 0;
-        }
-        const int c0 = tile * 32;
-        bool valid = live && c0 + lane < nc;
-        const int col = !valid ? 0 : (w.perm ? w.perm[(size_t)lay * nc + c0 + lane] : c0 + lane);
-        int laytrop = 0;
-        if (valid) {
-            laytrop = w.laytrop[col];
-            if (laytrop < 0) valid = false;              // night column: the solver never reads its staging
-        }
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        SwPair p;
-        bool lower = false;
-        if (valid) {
-            sw_cell(in, col, lay, p);
-            lower = (lay + 1) <= laytrop;
-        }
-        double *t24 = w.taur24 + ((size_t)(valid ? col : 0) * nlay + lay) * 8;
-        if (valid) w.colmol[(size_t)col * nlay + lay] = p.colmol;
-        const int *ls = w.laysolfr + (size_t)(valid ? col : 0) * 14;
-        double *sflx = w.sfluxzen + (size_t)(valid ? col : 0) * NGPTSW;
-        const size_t layoff = (size_t)lay * NGPTSW;
-#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, t24, sflx, col, layoff, colstride, vmask); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
-        SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
-        SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
+    const size_t cell0 = ((size_t)c0 * nlay + lay) * NGPTSW;
+#define SW_BAND(b) sw_band<b>(T, p, valid, lower, lay + 1, ls, slab, w.taug, t24, sflx, cell0, colstride, vmask); if (((b) & (g_tm_sync - 1)) == g_tm_sync - 1) __syncthreads()
+    SW_BAND(0); SW_BAND(1); SW_BAND(2); SW_BAND(3); SW_BAND(4); SW_BAND(5); SW_BAND(6);
+    SW_BAND(7); SW_BAND(8); SW_BAND(9); SW_BAND(10); SW_BAND(11); SW_BAND(12); SW_BAND(13);
 #undef SW_BAND
-    }
 }
 
 // Test hook (stage capture): expand the Rayleigh descriptors to taur[col][lay][112] exactly as the solver
@@ -753,18 +718,13 @@ int sw_run_pass(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, 
     ktimer_begin(K_SW_PREP, s);
     sw_prep_cell_kernel<<<(unsigned)(((size_t)w.nc * w.nlay + 127) / 128), 128, 0, s>>>(in, w);
     sw_prep_kernel<<<(w.nc + 127) / 128, 128, 0, s>>>(in, w);
-    if (w.perm) extra += bin_cells(w.skey, w.perm, w.nc, w.nlay, s);
     ktimer_end(s);
     {
-        const int ntile = (w.nc + 31) / 32;
-        const long items = (long)ntile * w.nlay;
-        const int bpl = (ntile + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;
-        const int run = g_tune.taumol_run > 0 ? g_tune.taumol_run : 1;
-        const long nblk = w.perm ? (long)((bpl + run - 1) / run) * w.nlay : (items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS;
+        const long items = (long)((w.nc + 31) / 32) * w.nlay;
         const size_t smem = (size_t)TM_BLOCK_WARPS * 32 * TM_STRIDE * sizeof(double);
         cudaFuncSetAttribute(sw_taumol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ktimer_begin(K_SW_TAUMOL, s);
-        sw_taumol_kernel<<<(unsigned)nblk, 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1, g_tune.taumol_order, run);
+        sw_taumol_kernel<<<(unsigned)((items + TM_BLOCK_WARPS - 1) / TM_BLOCK_WARPS), 32 * TM_BLOCK_WARPS, smem, s>>>(t, in, w, g_tune.taumol_sync > 0 ? g_tune.taumol_sync : 1);
         ktimer_end(s);
     }
     if (w.taur) sw_expand_taur_kernel<<<1184, 256, 0, s>>>(t, w);

@@ -231,28 +231,6 @@ def test_sw_solver_variants_agree(gpu, oracle):
                     assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.abs(b).max())) < 1e-10, (v, n)
 
 
-def test_cell_binning_is_invisible(gpu, oracle):
-    """taumol over cells binned by k-table row key (binning.cu) against 32 adjacent columns per warp: every cell is
-    evaluated by the same code whichever warp takes it, so all outputs are bitwise the same (ragged column count,
-    night columns binned last)."""
-    cols = make_columns("T170L60", nlon=83, nlat=7, night=True)
-    res = {}
-    try:
-        for b, order, run in ((1, 0, 8), (1, 1, 3), (1, 0, 1), (0, 0, 8)):
-            gpu.set_option("taumol_bin", b)
-            gpu.set_option("taumol_order", order)
-            gpu.set_option("taumol_run", run)
-            res[b, order, run] = gpu.lw_from_columns(cols) + gpu.sw_from_columns(cols)
-    finally:
-        gpu.set_option("taumol_bin", 1)
-        gpu.set_option("taumol_order", 0)
-        gpu.set_option("taumol_run", 8)
-    _check_outputs(res[1, 0, 8][:6], oracle.rrtmg_lw(cols), LW_OUT)
-    _check_outputs(res[1, 0, 8][6:], oracle.rrtmg_sw(cols), SW_OUT)
-    for k in ((1, 1, 3), (1, 0, 1), (0, 0, 8)):
-        assert all(np.array_equal(a, b) for a, b in zip(res[k], res[1, 0, 8])), k
-
-
 def test_emissivity_and_aerosol_inputs(gpu, oracle):
     """Spectrally varying emissivity (reflection term, rtrnmr.f90:628-636) and a non-zero LW tauaer
     (iaer = 10 is forced, rad.nomcica:442, :514-519)."""
