@@ -190,12 +190,26 @@ long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
  * chunk * nlay * 1.8 KB (SW): 17 GB at 65536 columns x 60 layers. */
 int rrtmg_b200_set_chunk(int ncol_per_pass);
 
-/* Generic options: "chunk" (as above), "host_chunk" (columns per pipeline stage of the host-pointer entry points,
- * default 16384: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i), "capture_stages" (1: keep a copy of lw.taug / lw.fracs, which the
- * LW solver otherwise overwrites in place; test hook), "kernel_timing" (see rrtmg_b200_kernel_times),
- * "sw_solver_variant" (clear-sky SW solver: 4 = default, one warp per block, top-down sweep first and a two-term upward
- * recurrence on three stored values per cell; 3 = the same in 7-warp blocks; 2 = bottom-up first, five stored values;
- * 1 = the reference's two recurrences literally, reftra evaluated in both sweeps; 0 = first version of the kernel). */
+/* Generic options:
+ *   "chunk"          as rrtmg_b200_set_chunk.
+ *   "host_chunk"     columns per pipeline stage of the host-pointer entry points (default 16384: the H2D copy of block i+1
+ *                    and the D2H copy of block i-1 overlap the kernels of block i).
+ *   "run_chunk"      the same for rrtmg_b200_run_rrtmg (RRTMG columns per block of latitude rows).
+ *   "share_inputs"   1: rrtmg_b200_sw keeps its device copies of the eleven arrays both codes read (play, plev, tlay, tlev,
+ *                    tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr), and the rrtmg_b200_lw call that FOLLOWS it with
+ *                    the same host pointers, ncol and nlay uses them instead of uploading again -- run_rrtmg passes the same
+ *                    arrays to both calls (rrtm_radiation.f90:686-712, 722-748), so half of the host-to-device traffic of a
+ *                    radiation step is redundant.  The caller promises not to change those arrays between the two calls.
+ *                    One shot: the copies are forgotten after the LW call; an LW call with other pointers or with
+ *                    LW-only array inputs (CFCs, emis, tauaer, clouds) uploads everything itself.  Default 0.
+ *   "capture_stages" 1: keep a copy of lw.taug / lw.fracs, which the LW solver otherwise overwrites in place (test hook).
+ *   "kernel_timing"  see rrtmg_b200_kernel_times.
+ *   "sw_solver_variant", "lw_rtrn_variant", "x0".."x7"   development builds only (RRTMG_B200_DEV_VARIANTS=1 python -m mima_b200.build
+ *                    --force): the earlier and the experimental forms of the two solvers, kept for comparison (sw_solver.cu,
+ *                    lw_solver.cu; measurements in profiles/).  The default library carries one clear-sky form of each.
+ * Thread safety: the library keeps one set of workspaces and one error string per process (like the reference's module
+ * variables): ONE call in flight per process -- the *_device entry points are asynchronous on the caller's stream, but a
+ * second call must not be issued on another stream before the first has finished. */
 int rrtmg_b200_set_option(const char *key, long value);
 
 /* With option "kernel_timing" = 1 every kernel launch is bracketed by CUDA events on its stream.  Returns the

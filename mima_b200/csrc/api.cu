@@ -578,7 +578,11 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool gener
     w.taur = fields ? c.take<double>(np * NGPTSW) : nullptr;      // expanded from rdesc (test hook)
     w.sfluxzen = c.take<double>((size_t)nc * NGPTSW);
     w.part = c.take<double>((size_t)nc * (NGPTSW / 16) * 2 * (nlay + 1));
+#ifdef RRTMG_B200_DEV_VARIANTS
     w.stack = c.take<double>((size_t)SW_STACK_SLOTS * (nlay + 1) * 96);
+#else
+    w.stack = nullptr;
+#endif
     w.opt = general ? c.take<double>(np * 14 * 6) : nullptr;
     w.clfr = general ? c.take<double>(np) : nullptr;
     w.err = general ? (int *)G.sw_err.p : nullptr;
@@ -1708,7 +1712,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     // the earlier kernel forms (SW solver variants 0-3, direct-load lw_rtrn) exist in development builds only
     // (RRTMG_B200_DEV_VARIANTS=1 python -m mima_b200.build --force)
     if (k == "lw_rtrn_variant" && value >= 2) { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }
-    if (k == "sw_solver_variant" && value >= 4) { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
+    if (k == "sw_solver_variant" && value == 4) { g_tune.sw_solver_variant = (int)value; return RRTMG_B200_OK; }
 #endif
     if (k == "sw_solver_pad_kb") { g_tune.sw_solver_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k.size() == 2 && k[0] == 'x' && k[1] >= '0' && k[1] <= '7') { g_tune.x[k[1] - '0'] = (int)value; return RRTMG_B200_OK; }

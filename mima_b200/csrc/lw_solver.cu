@@ -539,8 +539,11 @@ static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out,
 {
     // measured at T170L60 (stages x layers per stage): 2x4 7.60 ms, 2x3 7.68, 3x3 7.77, 2x5 8.02, 2x6 8.31, 3x4 8.39, 4x4 10.1
     // (a 56-register build that fits six blocks per SM measured 8.4 ms)
-    if (v == 3) launch_tma<AER, LMAX, 3, 4>(t, in, out, w, s);
-    else launch_tma<AER, LMAX, 2, 4>(t, in, out, w, s);
+#ifdef RRTMG_B200_DEV_VARIANTS
+    if (v == 3) { launch_tma<AER, LMAX, 3, 4>(t, in, out, w, s); return; }
+#endif
+    (void)v;
+    launch_tma<AER, LMAX, 2, 4>(t, in, out, w, s);
 }
 
 // =====================================================================================================

@@ -72,6 +72,7 @@ constexpr int SV_WS = 34;                       // row stride of the warp-local 
 constexpr int SV_HPC = NGPTSW / 16;             // half-warps per column: 7
 
 // exp(-ze) by the reference's Pade-indexed table (ze > od_lo) or 2nd-order series; also returns exp(+ze)
+template <bool SMEM = false>
 __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double ze, double bpade, double &recip)
 {
     if (ze <= 0.06) {
@@ -81,7 +82,7 @@ __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double 
     }
     const double tblind = ze * rcp_fast(bpade + ze);
     const int itind = (int)(10000.0 * tblind + 0.5);
-    const double2 e = __ldg(tb + itind);
+    const double2 e = SMEM ? tb[itind] : __ldg(tb + itind);      // SMEM: tb is the block's shared-memory copy of the table
     recip = e.y;
     return e.x;
 }
@@ -97,7 +98,7 @@ __device__ __forceinline__ double rcp_1n(double x)
 }
 template <bool R1> __device__ __forceinline__ double rcp_sel(double x) { return R1 ? rcp_1n(x) : rcp_fast(x); }
 
-template <bool R1>
+template <bool R1, bool SMEM = false>
 __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double bpade, double prmu0, double rmu0,
                                           double tr, double tg, double &ref, double &refd, double &tra,
                                           double &trad, double &dbt)
@@ -111,7 +112,7 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
     // exp(-tau/mu0) is needed by both branches; a warp usually holds lanes of both (two thirds of the warps of the
     // bench workload enter the conservative branch), so it is looked up once, before the branch
     double zep2;
-    const double zem2 = sw_exp(tb, fmin(zed, 500.), bpade, zep2);
+    const double zem2 = sw_exp<SMEM>(tb, fmin(zed, 500.), bpade, zep2);
     if (zw >= zwcrit) {
         // conservative scattering (:162-214)
         const double za1 = zgamma1 * prmu0 - 0.5;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void sw_reftra(const double2 *__restrict__ tb, double
         const double zt2 = zrm1 * hB;
         const double zt3 = zrk2 * (0.5 + za1 * prmu0);
         double zep1;
-        const double zem1 = sw_exp(tb, fmin(zrk * zto1, 500.), bpade, zep1);
+        const double zem1 = sw_exp<SMEM>(tb, fmin(zrk * zto1, 500.), bpade, zep1);
         const double zdenr = fma(zr4, zep1, zr5 * zem1);     // = zdent (zt4 = zr4, zt5 = zr5)
         if (zdenr >= -eps && zdenr <= eps) {
             ref = eps;
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwI
     }
 }
 
+#ifdef RRTMG_B200_DEV_VARIANTS       // variants 5 and 6 (per-cell stack in an L2-resident scratch): measured, not faster -- development builds only
 // =====================================================================================================
 // sw_solver_l2_kernel (variant 5): the scheme of sw_solver_warp_kernel with the per-cell stack (rdnd, zp, zq: 24 B)
 // kept on chip.  The local arrays of the one-warp kernel make 28 warps x 46.8 KB per SM = 194 MB of live-or-dead stack
@@ -919,6 +921,188 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_l2_kernel(SwTables T, SwIn 
         __syncwarp();
     }
 }
+
+// =====================================================================================================
+// sw_solver_sm_kernel (variant 6): variant 5 with ONE persistent block of W warps per SM, so that the warps of an SM can
+// share a copy of the {exp, 1/exp} table in shared memory (160 KB): the two table look-ups of reftra sit on the critical
+// path of every cell, and from L1/L2 (the 160 KB table does not survive in L1 next to the streaming loads: hit rate
+// 13-25 %) they held a third of the stall samples.  Each warp still walks its own warp tiles; there is no block barrier
+// after the table copy.  The per-cell stack goes to the L2 scratch as in variant 5 (no shared-memory tier: the table
+// takes the room); pass 2 issues the loads of the next four levels before it works on the current four.  The downward
+// sum of pass 1 is parked in w.part instead of shared memory.
+// Knobs: x0 = warps per SM (16, 20, 24, 28), x1 bit 0 = evict_last policy, bit 1 = discard.
+// =====================================================================================================
+template <int LMAX, int W, int U = SV_U>
+__global__ void __launch_bounds__(32 * W, 1) sw_solver_sm_kernel(SwTables T, SwIn in, SwWork w, long long nitems, int flags)
+{
+    constexpr bool R1 = true;
+    extern __shared__ __align__(16) double2 s_exp[];      // [NTBL + 1] {exp, 1/exp}, then W warp tiles
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *s_tile = reinterpret_cast<double *>(s_exp + (NTBL + 1)) + wid * (8 * SV_WS);
+    double *wt = s_tile + lane + (lane >> 4);
+    {
+        const double2 *__restrict__ src = reinterpret_cast<const double2 *>(T.exptbl);
+        for (int i = threadIdx.x; i <= NTBL; i += 32 * W) s_exp[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int klev = w.nlay;
+    const bool pol_on = (flags & 1) != 0, disc_on = (flags & 2) != 0;
+    const unsigned long long pol = l2_policy_evict_last();
+    const long long slot = (long long)blockIdx.x * W + wid;
+    double *const gstk = w.stack + (size_t)slot * (size_t)(klev + 1) * 96 + lane;    // this warp's slot
+    const double bpade = c_ss.bpade;
+    const long long nhw = (long long)w.nc * SV_HPC;
+    const long long stride = (long long)gridDim.x * W;
+
+    auto put = [&](int s, double r, double p, double q) {
+        double *d = gstk + (size_t)s * 96;
+        if (pol_on) { st_hint(d, r, pol); st_hint(d + 32, p, pol); st_hint(d + 64, q, pol); }
+        else { d[0] = r; d[32] = p; d[64] = q; }
+    };
+    auto get = [&](int s, double &r, double &p, double &q) {
+        const double *d = gstk + (size_t)s * 96;
+        if (pol_on) { r = ld_hint(d, pol); p = ld_hint(d + 32, pol); q = ld_hint(d + 64, pol); }
+        else { r = ld_na(d); p = ld_na(d + 32); q = ld_na(d + 64); }
+    };
+    auto warp_rows = [&](auto store) {
+        __syncwarp();
+        const int row = lane >> 2, q = lane & 3, half = q >> 1;
+        const double *src = s_tile + row * SV_WS + 17 * half + 8 * (q & 1);
+        double acc = src[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc += src[j];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if ((q & 1) == 0) store(row, half, acc);
+        __syncwarp();
+    };
+
+    for (long long item = slot; item < nitems; item += stride) {
+        const long long t = item * 32 + lane;
+        const int col = (int)(t / NGPTSW);
+        const int g = (int)(t - (long long)col * NGPTSW);
+        const bool incol = col < w.nc;
+        const double prmu0 = incol ? in.coszen[col] : 0.0;
+        const bool active = incol && !(prmu0 < ZEPZEN);      // night columns: zeros (rad.nomcica:502-510)
+        const int colr = incol ? col : 0;
+        const int band = c_ss.ngb[g];
+        const double mu0 = active ? prmu0 : 1.0;
+        const double rmu0 = 1. / mu0;
+        const bool uvvis = band >= 9 && band <= 12;          // bands 25-28 take the UV/visible albedos
+        const double *__restrict__ taug = w.taug + (size_t)colr * klev * NGPTSW + g;
+        const bool b24 = band == 8;
+        const double raylg = b24 ? 1.0 : __ldg(T.tab + c_ss.rayl[band] + g - c_ss.g0[band]);
+        const double *__restrict__ taur = b24 ? w.taur24 + (size_t)colr * klev * 8 + (g - c_ss.g0[band])
+                                              : w.colmol + (size_t)colr * klev;
+        const int trs = b24 ? 8 : 1;
+        const double zincflx = active ? in.adjflux * w.sfluxzen[(size_t)colr * NGPTSW + g] * prmu0 : 0.0;
+        const long long hw0 = item * 2;                      // first half-warp of this warp tile, = col * 7 + i
+
+        // ---- pass 1, top -> surface (see sw_solver_warp_kernel)
+        double tdn = 1., rdnd = 0., tdbt = 1.;
+        double trn[U], tgn[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int l = max(klev - 1 - j, 0);
+            trn[j] = active ? __ldg(taur + l * trs) : 0.;
+            tgn[j] = active ? __ldcs(taug + (size_t)l * NGPTSW) : 0.;
+        }
+        for (int kg = 0; kg <= klev; kg += U) {
+            double tr[U], tg[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) { tr[j] = trn[j]; tg[j] = tgn[j]; }
+            if (active && kg + U < klev) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int l = max(klev - 1 - (kg + U + j), 0);
+                    trn[j] = __ldg(taur + l * trs);
+                    tgn[j] = __ldcs(taug + (size_t)l * NGPTSW);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int k = kg + j, s = klev - k;
+                double row = 0.;
+                if (active && s >= 0) {
+                    row = zincflx * tdn;
+                    double zpv = 0., zqv = 0.;
+                    const double rd0 = rdnd;
+                    if (s > 0) {
+                        const double dif = tdn - tdbt;
+                        double ref, refd, tra, trad, dbt;
+                        sw_reftra<R1, true>(s_exp, bpade, mu0, rmu0, tr[j] * raylg, tg[j], ref, refd, tra, trad, dbt);
+                        const double zreflect = rcp_sel<R1>(1. - refd * rdnd);
+                        zpv = trad * zreflect;
+                        zqv = zincflx * ((ref * tdbt + refd * dif) * zreflect);
+                        const double tdn_n = tdbt * tra + (trad * (dif + tdbt * ref * rdnd)) * zreflect;
+                        const double rdnd_n = refd + trad * trad * rdnd * zreflect;
+                        tdbt = dbt * tdbt;
+                        tdn = tdn_n;
+                        rdnd = rdnd_n;
+                    }
+                    put(s, rd0, zpv, zqv);
+                }
+                wt[(k & 7) * SV_WS] = row;
+            }
+            const int kl = min(kg + U - 1, klev);
+            if ((kl & 7) == 7 || kl == klev) {
+                const int kb = kl & ~7;
+                warp_rows([&](int row, int half, double acc) {
+                    if (kb + row <= kl && hw0 + half < nhw)
+                        w.part[((hw0 + half) * 2 + 1) * (klev + 1) + (klev - kb - row)] = acc;     // sum of incflx * tdn
+                });
+            }
+        }
+        double u = 0.;
+        if (active) {
+            const double sd = uvvis ? in.asdif[colr] : in.aldif[colr];
+            const double sp = uvvis ? in.asdir[colr] : in.aldir[colr];
+            u = zincflx * ((sp * tdbt + sd * (tdn - tdbt)) * rcp_sel<R1>(1. - sd * rdnd));
+        }
+        // ---- pass 2, surface -> top: the loads of levels s0+4 .. s0+7 are in flight while s0 .. s0+3 are worked on
+        double pn[4], qn[4], rn[4];
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) get(min(j, klev), rn[j], pn[j], qn[j]);
+        }
+        for (int s0 = 0; s0 <= klev; s0 += 4) {
+            double p[4], q[4], r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { p[j] = pn[j]; q[j] = qn[j]; r[j] = rn[j]; }
+            if (active && s0 + 4 <= klev) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) get(min(s0 + 4 + j, klev), rn[j], pn[j], qn[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sj = s0 + j;
+                double pu = 0., pd = 0.;
+                if (active && sj <= klev) {
+                    if (sj > 0) u = fma(p[j], u, q[j]);
+                    pu = u;
+                    pd = r[j] * u;
+                }
+                wt[(2 * j) * SV_WS] = pu;
+                wt[(2 * j + 1) * SV_WS] = pd;
+            }
+            warp_rows([&](int row, int half, double acc) {
+                const int lev = s0 + (row >> 1);
+                if (lev <= klev && hw0 + half < nhw) {
+                    double *dst = w.part + ((hw0 + half) * 2 + (row & 1)) * (klev + 1) + lev;
+                    *dst = (row & 1) ? *dst + acc : acc;
+                }
+            });
+            if (disc_on && s0 >= 4) {
+                // levels s0-4 .. s0-1 have been consumed (warp_rows synchronised the warp after their use): drop their lines
+                const int nline = 4 * 6;
+                const char *base = reinterpret_cast<const char *>(gstk - lane + (size_t)(s0 - 4) * 96);
+                if (lane < nline) l2_discard128(base + (size_t)lane * 128);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+#endif  // RRTMG_B200_DEV_VARIANTS
 
 // Adds the seven half-warp partials of a column and level, writes the fluxes and heating rates
 // (rrtmg_sw_rad.nomcica.f90:686-727; clear == total for icld = 0).  A block takes TC columns: the partials are read
@@ -1231,16 +1415,34 @@ static void launch(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &
 template <int LMAX>
 static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
-    // variant 3 (default): top-down first, three stored values per cell (OPT 21); 2: bottom-up first, five stored values
-    // (OPT 13); 1: reftra recomputed in the second sweep, the reference's recurrences literally (OPT 5); 0: the first
-    // version of the kernel (OPT 0).  All use one-Newton reciprocals + warp-local g-sums except 0.
+    // Default (variant 4): sw_solver_warp_kernel + sw_finish_kernel.  Development builds add 3: the same scheme in 7-warp
+    // blocks (OPT 21); 2: bottom-up first, five stored values (OPT 13); 1: reftra recomputed in the second sweep, the
+    // reference's recurrences literally (OPT 5); 0: the first version (OPT 0); 5, 6: the per-cell stack in an L2 scratch.
 #ifdef RRTMG_B200_DEV_VARIANTS
     if (g_tune.sw_solver_store) { launch<LMAX, true, 0>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 0) { launch<LMAX, false, 0>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 1) { launch<LMAX, false, 5>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 2) { launch<LMAX, false, 13>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 3) { launch<LMAX, false, 21>(t, in, out, w, s); return; }
-#endif
+    if (g_tune.sw_solver_variant == 6) {
+        constexpr int TC = LMAX <= 64 ? 32 : 16;
+        const long long nitems = ((long long)w.nc * NGPTSW + 31) / 32;
+        static int nsm6 = 0;
+        if (!nsm6) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm6, cudaDevAttrMultiProcessorCount, dev); }
+        const int wps = g_tune.x[0] > 0 ? g_tune.x[0] : 20;
+        auto go = [&](auto kern, int W) {
+            const size_t smem = (size_t)(NTBL + 1) * sizeof(double2) + (size_t)W * 8 * SV_WS * sizeof(double);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const long long grid = std::min<long long>((nitems + W - 1) / W, (long long)nsm6);
+            kern<<<(unsigned)grid, 32 * W, smem, s>>>(t, in, w, nitems, g_tune.x[1]);
+        };
+        if (wps <= 16) go(sw_solver_sm_kernel<LMAX, 16>, 16);
+        else if (wps <= 20) go(sw_solver_sm_kernel<LMAX, 20>, 20);
+        else if (wps <= 24) go(sw_solver_sm_kernel<LMAX, 24>, 24);
+        else go(sw_solver_sm_kernel<LMAX, 28>, 28);
+        sw_finish_kernel<LMAX, TC><<<(w.nc + TC - 1) / TC, 256, 0, s>>>(in, out, w);
+        return;
+    }
     if (g_tune.sw_solver_variant == 5) {
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nitems = ((long long)w.nc * NGPTSW + 31) / 32;
@@ -1265,7 +1467,10 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
         else if (wpb <= 24) go(sw_solver_l2_kernel<LMAX, 24>, 24);
         else go(sw_solver_l2_kernel<LMAX, 28>, 28);
         sw_finish_kernel<LMAX, TC><<<(w.nc + TC - 1) / TC, 256, 0, s>>>(in, out, w);
-    } else {
+        return;
+    }
+#endif
+    {
         // variant 4: variant 3 with one warp per block + sw_finish_kernel
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nthr = (long long)w.nc * NGPTSW;

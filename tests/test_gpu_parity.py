@@ -174,6 +174,30 @@ def test_set_table_path_gives_the_same_reduced_tables(gpu):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
+def test_share_inputs_option(gpu):
+    """Option share_inputs: rrtmg_b200_lw reuses the device copies rrtmg_b200_sw made of the eleven arrays both read -- when
+    it is called right after it with the same host arrays; with other arrays (or after another LW call) it uploads its own.
+    Results are bitwise those of the plain calls, also with night columns, chunked blocks and a ragged column count."""
+    cols = make_columns("T170L60", nlon=83, nlat=5, night=True)
+    other = make_columns("T170L60", nlon=83, nlat=5, night=True, seed=99)
+    plain = gpu.sw_from_columns(cols) + gpu.lw_from_columns(cols)
+    plain_other = gpu.lw_from_columns(other)
+    try:
+        gpu.set_option("share_inputs", 1)
+        for hc in (0, 64):
+            gpu.set_option("host_chunk", hc)
+            got = gpu.sw_from_columns(cols) + gpu.lw_from_columns(cols)            # LW reuses the SW uploads
+            assert all(np.array_equal(a, b) for a, b in zip(got, plain)), hc
+            again = gpu.lw_from_columns(cols)                                      # one shot: this one uploads itself
+            assert all(np.array_equal(a, b) for a, b in zip(again, plain[6:]))
+            gpu.sw_from_columns(cols)
+            got_other = gpu.lw_from_columns(other)                                 # other arrays: not the shared copies
+            assert all(np.array_equal(a, b) for a, b in zip(got_other, plain_other))
+    finally:
+        gpu.set_option("share_inputs", 0)
+        gpu.set_option("host_chunk", 0)
+
+
 def test_reference_golden_vectors(gpu):
     """The CUDA path against outputs of the reference's own code (tests/golden/ref_t42l40.npz: the reference's RRTMG
     sources machine-translated F90 -> C and run on config C4 columns, tests/golden/make_ref_vectors.py) -- no oracle in
@@ -195,18 +219,18 @@ def _dev_variants(gpu):
 
 
 def test_sw_solver_variants_agree(gpu, oracle):
-    """The default SW solver (variant 4, one-warp blocks) runs the reference's top-down recurrence first and then propagates
-    the upward flux with coefficients kept by that sweep (algebraically vrtqdr_sw :103-150); variant 5 keeps those
-    coefficients in an L2-resident scratch / shared memory instead of local memory.  Development builds
-    (RRTMG_B200_DEV_VARIANTS=1) also carry variant 3 (the same scheme in 7-warp blocks, bitwise equal sums), 2 (bottom-up
-    first), 1 (both of the reference's recurrences literally) and 0 (the first version).  All must match the oracle, and
-    each other to rounding."""
+    """Development builds only (RRTMG_B200_DEV_VARIANTS=1): the default SW solver (variant 4, one-warp blocks: the reference's
+    top-down recurrence first, then the upward flux from coefficients kept by that sweep, algebraically vrtqdr_sw :103-150)
+    against variant 3 (the same scheme in 7-warp blocks, bitwise equal sums), 2 (bottom-up first), 1 (both of the
+    reference's recurrences literally), 0 (the first version), 5 and 6 (the kept coefficients in an L2-resident scratch /
+    shared memory instead of local memory).  All must match the oracle, and each other to rounding."""
+    if not _dev_variants(gpu):
+        pytest.skip("the library was built without RRTMG_B200_DEV_VARIANTS: it carries the default solver only")
     cols = make_columns("T170L60", nlon=64, nlat=8, night=True)
     ref = oracle.rrtmg_sw(cols)
     res = {}
-    dev = _dev_variants(gpu)
     try:
-        for v in (5, 4) + ((3, 2, 1, 0) if dev else ()):
+        for v in (6, 5, 4, 3, 2, 1, 0):
             gpu.set_option("sw_solver_variant", v)
             res[v] = gpu.sw_from_columns(cols)
             _check_outputs(res[v], ref, SW_OUT)
@@ -215,20 +239,25 @@ def test_sw_solver_variants_agree(gpu, oracle):
             for k, v in (("x0", wpb), ("x1", flags), ("x2", ns)):
                 gpu.set_option(k, v)
             _check_outputs(gpu.sw_from_columns(cols), ref, SW_OUT)
+        gpu.set_option("sw_solver_variant", 6)                                     # exp table in shared memory, one block per SM
+        for wps, flags in ((16, 3), (20, 0), (24, 1), (28, 2)):
+            gpu.set_option("x0", wps)
+            gpu.set_option("x1", flags)
+            _check_outputs(gpu.sw_from_columns(cols), ref, SW_OUT)
     finally:
         gpu.set_option("sw_solver_variant", DEFAULT_SW_VARIANT)
         for k, v in (("x0", 0), ("x1", 3), ("x2", 0)):
             gpu.set_option(k, v)
-    for a, b, n in zip(res[5], res[4], SW_OUT):                           # stack in L2 / shared memory: same formulas
-        assert np.max(np.abs(a - b)) < (1e-7 if "hr" in n else 1e-8), n
-    if dev:
-        assert all(np.array_equal(a, b) for a, b in zip(res[4], res[3]))      # same sums in the same order
-        for v in (2, 3):
-            for a, b, n in zip(res[v], res[1], SW_OUT):
-                if "hr" in n:
-                    assert np.max(np.abs(a - b)) < 1e-7, (v, n)          # K/day
-                else:
-                    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.abs(b).max())) < 1e-10, (v, n)
+    for v in (5, 6):
+        for a, b, n in zip(res[v], res[4], SW_OUT):                       # stack in L2 / shared memory: same formulas
+            assert np.max(np.abs(a - b)) < (1e-7 if "hr" in n else 1e-8), (v, n)
+    assert all(np.array_equal(a, b) for a, b in zip(res[4], res[3]))      # same sums in the same order
+    for v in (2, 3):
+        for a, b, n in zip(res[v], res[1], SW_OUT):
+            if "hr" in n:
+                assert np.max(np.abs(a - b)) < 1e-7, (v, n)          # K/day
+            else:
+                assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.abs(b).max())) < 1e-10, (v, n)
 
 
 def test_emissivity_and_aerosol_inputs(gpu, oracle):
