@@ -338,7 +338,7 @@ def main():
 
     D = Dev(cols)
     nl, nv = ncol * nlay, ncol * (nlay + 1)
-    houts = {k: torch.empty(v.numel(), dtype=torch.float64).pin_memory() for k, v in D.out.items()}
+    houts_main = {k: torch.empty(v.numel(), dtype=torch.float64).pin_memory() for k, v in D.out.items()}
     torch.cuda.synchronize()
 
     def P(t):
@@ -384,8 +384,11 @@ def main():
         if two_streams:
             stream.wait_stream(side)
 
-    def step_host(clear_sky):
-        h = D.host
+    def step_host(clear_sky, X=None, houts_x=None):
+        X = D if X is None else X
+        h = X.host
+        ncol = X.n
+        houts = houts_main if houts_x is None else houts_x
         g = (lambda k: P(h[k])) if secondary else (lambda k: NULL)
         cs = (lambda t: P(t)) if clear_sky else (lambda t: NULL)
         rc = L_.rrtmg_b200_sw(C.c_int(ncol), C.c_int(nlay), C.byref(icld), C.byref(iaer),
@@ -471,7 +474,17 @@ def main():
             ms_o = timed(lambda: step_device(W), nshort)
             other = {"scaling": "weak", "columns_per_gpu": W.n, "ms_per_step": ms_o, "value": W.n * world / (ms_o * 1e-3),
                      "unit": "columns/s", "what": "every rank one full batch of the named resolution, device-resident"}
-            del W
+            # ... and end to end, as the shim calls it (share_inputs, no clear-sky outputs): all ranks pull on the host memory at once
+            hw = {k: torch.empty(v.numel(), dtype=torch.float64).pin_memory() for k, v in W.out.items() if not k.endswith("c")}
+            hw.update({k: None for k in W.out if k.endswith("c")})
+            L_.rrtmg_b200_set_option(b"share_inputs", C.c_long(1))
+            ms_we = timed_host(lambda: step_host(False, W, hw), 3)
+            L_.rrtmg_b200_set_option(b"share_inputs", C.c_long(0))
+            wl, wv = W.n * nlay, W.n * (nlay + 1)
+            other["e2e"] = {"value": W.n * world / (ms_we * 1e-3), "unit": "columns/s", "ms_per_step": ms_we, "steps": 3,
+                            "h2d_bytes_per_step": 8 * (5 * wl + 2 * wv + 3 * W.n) if not secondary else None,
+                            "d2h_bytes_per_step": 8 * (4 * wv + 2 * wl)}
+            del W, hw
         elif nlat_full % world == 0:
             rows = nlat_full // world
             S = Dev(batch((rank * rows, (rank + 1) * rows)))
