@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(32, WPB) sw_solver_l2_kernel(SwTables T, SwIn 
 // sum of pass 1 is parked in w.part instead of shared memory.
 // Knobs: x0 = warps per SM (16, 20, 24, 28), x1 bit 0 = evict_last policy, bit 1 = discard.
 // =====================================================================================================
-template <int LMAX, int W, int U = SV_U>
+template <int LMAX, int W, bool LOC = false, int U = SV_U>
 __global__ void __launch_bounds__(32 * W, 1) sw_solver_sm_kernel(SwTables T, SwIn in, SwWork w, long long nitems, int flags)
 {
     constexpr bool R1 = true;
@@ -954,12 +954,17 @@ __global__ void __launch_bounds__(32 * W, 1) sw_solver_sm_kernel(SwTables T, SwI
     const long long nhw = (long long)w.nc * SV_HPC;
     const long long stride = (long long)gridDim.x * W;
 
+    // LOC (variant 7): the stack in per-thread local memory as in sw_solver_warp_kernel; only the table moves to shared memory
+    constexpr int LL = LOC ? LMAX + 1 : 1;
+    double lr[LL], lp[LL], lq[LL];
     auto put = [&](int s, double r, double p, double q) {
+        if (LOC) { lr[LOC ? s : 0] = r; lp[LOC ? s : 0] = p; lq[LOC ? s : 0] = q; return; }
         double *d = gstk + (size_t)s * 96;
         if (pol_on) { st_hint(d, r, pol); st_hint(d + 32, p, pol); st_hint(d + 64, q, pol); }
         else { d[0] = r; d[32] = p; d[64] = q; }
     };
     auto get = [&](int s, double &r, double &p, double &q) {
+        if (LOC) { r = lr[LOC ? s : 0]; p = lp[LOC ? s : 0]; q = lq[LOC ? s : 0]; return; }
         const double *d = gstk + (size_t)s * 96;
         if (pol_on) { r = ld_hint(d, pol); p = ld_hint(d + 32, pol); q = ld_hint(d + 64, pol); }
         else { r = ld_na(d); p = ld_na(d + 32); q = ld_na(d + 64); }
@@ -1091,7 +1096,7 @@ __global__ void __launch_bounds__(32 * W, 1) sw_solver_sm_kernel(SwTables T, SwI
                     *dst = (row & 1) ? *dst + acc : acc;
                 }
             });
-            if (disc_on && s0 >= 4) {
+            if (!LOC && disc_on && s0 >= 4) {
                 // levels s0-4 .. s0-1 have been consumed (warp_rows synchronised the warp after their use): drop their lines
                 const int nline = 4 * 6;
                 const char *base = reinterpret_cast<const char *>(gstk - lane + (size_t)(s0 - 4) * 96);
@@ -1424,7 +1429,7 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
     if (g_tune.sw_solver_variant == 1) { launch<LMAX, false, 5>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 2) { launch<LMAX, false, 13>(t, in, out, w, s); return; }
     if (g_tune.sw_solver_variant == 3) { launch<LMAX, false, 21>(t, in, out, w, s); return; }
-    if (g_tune.sw_solver_variant == 6) {
+    if (g_tune.sw_solver_variant == 6 || g_tune.sw_solver_variant == 7) {
         constexpr int TC = LMAX <= 64 ? 32 : 16;
         const long long nitems = ((long long)w.nc * NGPTSW + 31) / 32;
         static int nsm6 = 0;
@@ -1436,7 +1441,12 @@ static void launch_opt(const SwTables &t, const SwIn &in, const SwOut &out, SwWo
             const long long grid = std::min<long long>((nitems + W - 1) / W, (long long)nsm6);
             kern<<<(unsigned)grid, 32 * W, smem, s>>>(t, in, w, nitems, g_tune.x[1]);
         };
-        if (wps <= 16) go(sw_solver_sm_kernel<LMAX, 16>, 16);
+        if (g_tune.sw_solver_variant == 7) {        // table in shared memory, stack in local memory
+            if (wps <= 20) go(sw_solver_sm_kernel<LMAX, 20, true>, 20);
+            else if (wps <= 24) go(sw_solver_sm_kernel<LMAX, 24, true>, 24);
+            else go(sw_solver_sm_kernel<LMAX, 28, true>, 28);
+        }
+        else if (wps <= 16) go(sw_solver_sm_kernel<LMAX, 16>, 16);
         else if (wps <= 20) go(sw_solver_sm_kernel<LMAX, 20>, 20);
         else if (wps <= 24) go(sw_solver_sm_kernel<LMAX, 24>, 24);
         else go(sw_solver_sm_kernel<LMAX, 28>, 28);
