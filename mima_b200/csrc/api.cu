@@ -594,6 +594,17 @@ int pick_chunk(int ncol)
     int ch = G.chunk > 0 ? G.chunk : 65536;     // columns per pass; T170L60 step: 16384 35.4, 32768 34.0, 65536 33.65, 131072 33.6 ms
     return ch < ncol ? ch : ncol;
 }
+// The workspace of a pass is 17 GB at 65536 columns x 60 layers.  MiMA's shipped job size is 32 ranks (exp/nci_runscript.sh:7),
+// i.e. four ranks per GPU on one 8-GPU box: the pass is halved until its workspace fits into what the device has free
+// (beyond what this buffer already holds), so several ranks can share a GPU without an allocation failure.
+template <class Carve>
+int fit_chunk(int chunk, const DevBuf &have, Carve bytes_of)
+{
+    size_t freeb = 0, total = 0;
+    if (cudaMemGetInfo(&freeb, &total) != cudaSuccess) return chunk;
+    while (chunk > 1024 && bytes_of(chunk) > have.bytes + (size_t)(0.9 * (double)freeb)) chunk = (chunk + 1) / 2;
+    return chunk;
+}
 
 // ------------------------------------------------------------------------------------------------
 struct LwOpt {                // the optional cloud arguments of rrtmg_lw
@@ -740,10 +751,11 @@ int lw_device_impl(int ncol, int nlay, int *icld, int idrv, const LwIn &in0, con
     if (const int rc = lw_validate(ncol, nlay, icld, idrv, opt)) return rc;
     if (idrv == 1 && (!out0.duflx_dt || !out0.duflxc_dt)) return fail(RRTMG_B200_ERR_BAD_ARGUMENT, "rrtmg_lw: idrv = 1 needs duflx_dt and duflxc_dt");
     if (ncol == 0) return RRTMG_B200_OK;
-    const int chunk = pick_chunk(ncol);
+    int chunk = pick_chunk(ncol);
     LwWork w;
-    const bool fields = G.capture && ncol <= chunk;
     const bool cloudy = in0.icld >= 1;
+    chunk = fit_chunk(chunk, wk, [&](int c) { LwWork t; return lw_carve(t, nullptr, c, nlay, G.capture && ncol <= c, cloudy); });
+    const bool fields = G.capture && ncol <= chunk;
     if (const int rc = lw_err_begin(cloudy)) return rc;
     if (wk.ensure(lw_carve(w, nullptr, chunk, nlay, fields, cloudy))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
@@ -770,10 +782,11 @@ int sw_device_impl(int ncol, int nlay, int *icld, int *iaer, const SwIn &in0, co
     DevBuf &wk = work ? *work : G.sw_work;
     if (const int rc = sw_validate(ncol, nlay, icld, iaer, opt)) return rc;
     if (ncol == 0) return RRTMG_B200_OK;
-    const int chunk = pick_chunk(ncol);
+    int chunk = pick_chunk(ncol);
     SwWork w;
-    const bool fields = G.capture && ncol <= chunk;
     const bool general = in0.icld >= 1 || in0.iaer != 0;
+    chunk = fit_chunk(chunk, wk, [&](int c) { SwWork t; return sw_carve(t, nullptr, c, nlay, G.capture && ncol <= c, general); });
+    const bool fields = G.capture && ncol <= chunk;
     if (const int rc = sw_err_begin(general)) return rc;
     if (wk.ensure(sw_carve(w, nullptr, chunk, nlay, fields, general))) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW workspace");
     for (int c0 = 0; c0 < ncol; c0 += chunk) {
