@@ -174,6 +174,17 @@ def test_set_table_path_gives_the_same_reduced_tables(gpu):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
+def test_sw_ignores_cloud_switches_when_icld_is_zero(gpu):
+    """run_rrtmg passes the LONGWAVE cloud switches inflglw, iceflglw, liqflglw (and LW-shaped cloud/aerosol arrays) in the
+    shortwave call (rrtm_radiation.f90:692-694, 706-708).  With icld = 0 the reference never looks at them; neither does
+    the library: any switch values, no cloud arrays, same bits."""
+    cols = make_columns("T42L40", nlon=32, nlat=4, night=True)
+    ref = gpu.sw_from_columns(cols)
+    for flags in ((2, 3, 1), (1, 0, 0), (7, -1, 9)):
+        got = gpu.sw_from_columns(cols, inflgsw=flags[0], iceflgsw=flags[1], liqflgsw=flags[2])
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref)), flags
+
+
 def test_share_inputs_option(gpu):
     """Option share_inputs: rrtmg_b200_lw reuses the device copies rrtmg_b200_sw made of the eleven arrays both read -- when
     it is called right after it with the same host arrays; with other arrays (or after another LW call) it uploads its own.
