@@ -71,6 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, fmad = item
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         dev = ["-DRRTMG_B200_DEV_VARIANTS"] if os.environ.get("RRTMG_B200_DEV_VARIANTS") == "1" else []
+        dev += os.environ.get("RRTMG_B200_DEFS", "").split()          # extra -D flags of an experiment build
         cmd = cc + NVCC_FLAGS + dev + ["-fmad=true" if fmad else "-fmad=false"] + (["-Xptxas", "-v"] if verbose else []) + \
             ["-c", "-o", obj, src]
         r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

@@ -70,7 +70,7 @@ __device__ __forceinline__ void lw_layer(const double2 *__restrict__ et, double 
     } else {
         const double tblind = odepth * rcp_fast(bpade + odepth);
         const int itr = (int)(10000.0 * tblind + 0.5);
-        const double2 e = __ldg(et + itr);
+        const double2 e = ld_tbl(et + itr);
         atrans = 1. - e.x;
         if (DOWN) bbd = plfrac * (blay + e.y * dplankdn);
         else bbugas = plfrac * (blay + e.y * dplankup);

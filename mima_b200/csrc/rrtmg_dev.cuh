@@ -287,6 +287,10 @@ __device__ __forceinline__ double sqrt_fast(double a)
     return fma(g, r, g);
 }
 
+// One 16-byte gather from the {exp, tfn} / {exp, 1/exp} look-up table of a solver (read-only path).  An L1 evict_last hint
+// on these loads (LDG.E.EL.128.CONSTANT) was measured: no change in either solver (profiles/r02_summary.md).
+__device__ __forceinline__ double2 ld_tbl(const double2 *__restrict__ p) { return __ldg(p); }
+
 // Sum over g-points of R rows (R = 16 or 32) of per-thread values that the caller has stored in `tile` as
 // tile[row * S + g] (S odd, >= NACT).  Stage 1: thread t sums the strided elements of row (t % R) --
 // conflict-free because the lanes of a half-warp hold different rows and S is odd; stage 2: threads 0..R-1

@@ -82,7 +82,7 @@ __device__ __forceinline__ double sw_exp(const double2 *__restrict__ tb, double 
     }
     const double tblind = ze * rcp_fast(bpade + ze);
     const int itind = (int)(10000.0 * tblind + 0.5);
-    const double2 e = SMEM ? tb[itind] : __ldg(tb + itind);      // SMEM: tb is the block's shared-memory copy of the table
+    const double2 e = SMEM ? tb[itind] : ld_tbl(tb + itind);     // SMEM: tb is the block's shared-memory copy of the table
     recip = e.y;
     return e.x;
 }

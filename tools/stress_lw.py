@@ -1,4 +1,6 @@
-"""Stress test of the TMA-fed lw_rtrn (developer tool): many calls, compared bit for bit with the direct-load kernel."""
+"""Stress test of the TMA-fed lw_rtrn (developer tool): many calls, compared bit for bit with the direct-load kernel.
+Needs a development build of the library (RRTMG_B200_DEV_VARIANTS=1 python -m mima_b200.build --force): the default build
+carries the TMA-fed kernel only."""
 import sys
 import numpy as np
 sys.path.insert(0, '.')
