@@ -1,14 +1,15 @@
-// lw_kernels.cu -- RRTMG longwave on sm_100a: prep (inatm+setcoef), taumol (plan/execute), rtrn (clear sky).
+// lw_kernels.cu -- RRTMG longwave on sm_100a: prep (inatm + setcoef), taumol, cldprop.  The solver is in lw_solver.cu.
 //
-// What is computed follows the reference routines (cited per kernel); how it is computed is a
-// GPU-first design:
-//   lw_prep_cell_kernel  thread <-> (column, layer): unit conversion, column amounts, Planck sources;
-//   lw_prep_kernel    thread <-> column: the column sums (laytrop, precipitable water -> secant), surface Planck terms.
-//   lw_taumol_kernel  thread <-> (column, layer) cell, lanes = 32 adjacent columns; blockIdx.z selects a band
-//                     slice, so that the blocks resident on an SM at any time run the same few bands (their
-//                     code fits the instruction cache and their k-tables the L1).  Terms of the band
-//                     formula are consumed into register accumulators as they are produced.
-//   lw_rtrn_kernel    (lw_solver.cu) block <-> column, thread <-> g-point.
+// What is computed follows the reference routines (cited per kernel); how it is computed is a GPU-first design:
+//   lw_prep_cell_kernel  thread <-> (column, layer): unit conversion, column amounts, Planck sources of the layer and its
+//                        upper interface, the per-cell terms of the column sums;
+//   lw_prep_kernel       thread <-> column: the column sums in the reference's order (laytrop, precipitable water ->
+//                        diffusivity secant), surface Planck terms;
+//   lw_taumol_kernel     thread <-> (column, layer) cell, lanes = 32 adjacent columns of one layer; the cell's setcoef state
+//                        is evaluated in place (lw_cell), every term w * T[row][.] of a band formula is consumed at once
+//                        into ng register accumulators, and the warps of a block walk the 16 bands together (one block
+//                        barrier per four bands) so that the ~300 KB of straight-line band code is fetched once per block;
+//   lw_cldprop_kernel    thread <-> column (cloudy sky only).
 // Compiled with -fmad=false: fused multiply-adds appear only where written as fma().
 #include "rrtmg_dev.cuh"
 

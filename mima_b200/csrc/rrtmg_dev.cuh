@@ -1,17 +1,15 @@
 // rrtmg_dev.cuh -- device-side data layout shared by the LW and SW kernels (sm_100a).
 //
 // HBM layout (one "pass" = a chunk of nc columns, all nlay layers):
-//   * interface arrays arrive (ncol, nlay) column-major: the column index is contiguous, so a
-//     thread-per-column kernel reads fully coalesced.
-//   * per-(layer, column) interpolation state produced by the *_prep kernels is stored as
-//     structure-of-arrays fields F[field][lay][col] (column fastest) -- coalesced for the planner
-//     phase of taumol (thread <-> column at one layer).
-//   * the taumol -> solver staging fields (LW taug/fracs, SW taug/taur) are stored [col][lay][g]
-//     with the g-point index fastest: one warp of the solver (lanes = g-points) reads 256
-//     contiguous bytes per layer step, and the taumol executor (lanes = g-points of a few adjacent
-//     columns) reads each k-table row as one contiguous segment.
-//   * k-distribution tables are transposed at init from the Fortran (row, ig) to [row][ig] so the
-//     g-lanes of one stencil point are contiguous (<= 128 B).
+//   * interface arrays arrive (ncol, nlay) column-major: the column index is contiguous, so kernels whose lanes are
+//     adjacent columns of one layer (prep, taumol) read fully coalesced.
+//   * the per-cell setcoef state is NOT stored: taumol evaluates it in place (lw_cell / sw_cell).  The fields
+//     F[field][lay][col] and idx exist only for the stage-capture test hook (option capture_stages).
+//   * the taumol -> solver staging fields (LW taug/fracs, SW taug) are stored [col][lay][g] with the g-point index
+//     fastest: one warp of a solver (lanes = g-points of a column) reads 256 contiguous bytes per layer step; taumol
+//     transposes its per-cell results through a per-warp shared-memory slab and writes whole rows in 16-byte pieces.
+//   * k-distribution tables are reduced and transposed at init from the Fortran (row, ig) to [row][ig] with the row
+//     stride padded to a power of two, so that the values one interpolation term needs are one <= 128-byte line.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,14 +1,12 @@
-// sw_kernels.cu -- RRTMG shortwave on sm_100a: prep (inatm_sw+setcoef_sw), taumol_sw (plan/execute),
-// two-stream solver (spcvrt + reftra + vrtqdr, clear sky, no aerosol: the MiMA configuration).
+// sw_kernels.cu -- RRTMG shortwave on sm_100a: prep (inatm_sw + setcoef_sw), taumol_sw, cloud / aerosol optics.  The
+// two-stream solver (spcvrt + reftra + vrtqdr) is in sw_solver.cu.
 //
-//   sw_prep_kernel    thread <-> column: unit conversion, column amounts, p/T interpolation state, and the
-//                     per-band layer whose binary-species parameter selects the solar source (laysolfr).
-//   sw_taumol_kernel  tile = 128 adjacent columns of one layer; per band plan (thread <-> column) then
-//                     execute (thread <-> (column, g)): taug, taur and (at the laysolfr layer) sfluxzen
-//                     as weighted sums of table rows.
-//   sw_solver_kernel  block <-> column, thread <-> g-point: layer optical properties + PIFM two-stream
-//                     R/T (reftra) top-down, adding method bottom-up and top-down (vrtqdr), per-level
-//                     shuffle reduction over g-points weighted by the incoming solar flux.
+//   sw_prep_cell_kernel  thread <-> (column, layer): the cell's reference-pressure index and "below 100 hPa" flag;
+//   sw_prep_kernel       thread <-> column: night marker, laytrop, and per band the layer whose binary-species parameter
+//                        selects the solar source (laysolfr), replaying the sequential loops of taumol16..29;
+//   sw_taumol_kernel     thread <-> (column, layer) cell as in the LW kernel: taug per g-point, the Rayleigh descriptors
+//                        (colmol; taur of band 24) and, from the laysolfr layer, sfluxzen;
+//   sw_optics_kernel     clouds / aerosols of the general path (not MiMA's configuration).
 // Night columns (coszen < 1e-10) are skipped and written as zeros (rad.nomcica:502-510).
 // Compiled with -fmad=false: fused multiply-adds appear only where written as fma().
 #include "rrtmg_dev.cuh"
