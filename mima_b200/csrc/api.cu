@@ -929,7 +929,14 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
 int host_chunk(int ncol)
 {
     if (G.capture) return ncol;                        // stage dumps need the whole batch in one pass
-    int hc = G.host_chunk > 0 ? G.host_chunk : 16384;     // measured e2e at T170L60: 4096 53.6, 8192 48.0, 16384 47.3, 32768 50.0 ms
+    // measured e2e at T170L60 (131072 columns): 4096 53.6, 8192 48.0, 16384 47.3, 32768 50.0 ms.  A batch of fewer than four
+    // such blocks (a rank's share in strong scaling: 16384 columns at 8 GPUs) is cut into about four, so that copies and
+    // kernels still overlap: 8 GPUs x 16384 columns 9.2 ms in one block, 7.4 ms in blocks of 4096 (profiles/r02_summary.md)
+    int hc = G.host_chunk > 0 ? G.host_chunk : 16384;
+    if (G.host_chunk <= 0 && ncol < 4 * hc) {
+        hc = ((ncol + 3) / 4 + 1023) / 1024 * 1024;
+        if (hc < 4096) hc = 4096;
+    }
     if (G.chunk > 0 && G.chunk < hc) hc = G.chunk;     // option "chunk" bounds every device pass
     return hc < ncol ? hc : ncol;
 }
@@ -1647,6 +1654,13 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     // latitude row (the zonal means too), and a row block of an (si, sj, n) field is n runs of si*rows doubles.
     const size_t np_all = (size_t)si * sj, L = sk, V = sk + 1;
     int target = G.run_chunk > 0 ? G.run_chunk : 16384;           // RRTMG columns per block (e2e at T170L60: 8192 44.7, 16384 44.3, 32768 45.2 ms)
+    {
+        const long nrr = (long)(si / cfg->lonstep) * sj;           // RRTMG columns of the call: small batches in about four blocks
+        if (G.run_chunk <= 0 && nrr < 4L * target) {
+            target = (int)(((nrr + 3) / 4 + 1023) / 1024 * 1024);
+            if (target < 4096) target = 4096;
+        }
+    }
     if (G.chunk > 0 && G.chunk < target) target = G.chunk;
     int rows = (int)((long)target * cfg->lonstep / si);
     if (rows < 1) rows = 1;
