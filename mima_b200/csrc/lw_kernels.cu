@@ -317,6 +317,12 @@ struct BandAcc {
             t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
         }
     }
+    // terms whose weight is exactly zero for every column of MiMA's default configuration (the CFC cross-sections when
+    // no CFC array is passed, the O2 continuum when O2 is absent): t + 0 * T = t bit for bit, so the row is not read
+    __device__ __forceinline__ void add_nz(int off, double wgt)
+    {
+        if (wgt != 0.0) add(off, wgt);
+    }
     __device__ __forceinline__ void scale(int off)      // taug(g) *= T[off + g]
     {
         const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
@@ -549,14 +555,14 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             minor_eta(pw, B, LS_MA1, 9, em.js, em.fs, p.indm, p.minorfrac, p.colo3);
-            pw.add(B.sec[LS_X1] * B.rs, p.wx1);
+            pw.add_nz(B.sec[LS_X1] * B.rs, p.wx1);
             frac_eta(pw, B, LS_FRACA, p.colh2o, B.refrat[0], p.colco2, 8.);
         } else {
             const Eta e0 = binary(p.colo3, c_lw.rat_o3co2[p.jp - 1], p.colco2, 4.);
             const Eta e1 = binary(p.colo3, c_lw.rat_o3co2[p.jp], p.colco2, 4.);
             stencil_upper(pw, B, IND0B(5) + e0.js, e0, p.fac00, p.fac10);
             stencil_upper(pw, B, IND1B(5) + e1.js, e1, p.fac01, p.fac11);
-            pw.add(B.sec[LS_X1] * B.rs, p.wx1);
+            pw.add_nz(B.sec[LS_X1] * B.rs, p.wx1);
             frac_eta(pw, B, LS_FRACB, p.colo3, B.refrat[1], p.colco2, 4.);
         }
     } else if constexpr (BAND == 5) { // band 6: 820-980, H2O lower; CO2 minor, CFC11, CFC12 (:1297-1380)
@@ -567,8 +573,8 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
             lerp2(pw, B, LS_MA1, p.indm, p.minorfrac, adj);
         }
-        pw.add(B.sec[LS_X1] * B.rs, p.wx2);
-        pw.add(B.sec[LS_X2] * B.rs, p.wx3);
+        pw.add_nz(B.sec[LS_X1] * B.rs, p.wx2);
+        pw.add_nz(B.sec[LS_X2] * B.rs, p.wx3);
         frac_const(pw, B, LS_FRACA);
     } else if constexpr (BAND == 6) { // band 7: 980-1080, H2O/O3 lower, O3 upper; CO2 minor (:1383-1654)
         if (lower) {
@@ -605,8 +611,8 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             lerp2(pw, B, LS_MB2, p.indm, p.minorfrac, p.coln2o);
             frac_const(pw, B, LS_FRACB);
         }
-        pw.add(B.sec[LS_X1] * B.rs, p.wx3);
-        pw.add(B.sec[LS_X2] * B.rs, p.wx4);
+        pw.add_nz(B.sec[LS_X1] * B.rs, p.wx3);
+        pw.add_nz(B.sec[LS_X2] * B.rs, p.wx4);
     } else if constexpr (BAND == 8) { // band 9: 1180-1390, H2O/CH4 lower, CH4 upper; N2O minor (:1780-2040)
         const double adj = adjcol(p.coln2o, p.coldry, CHI(4, p.jp + 1), 1.5, 0.5, 0.65);
         if (lower) {
@@ -641,12 +647,12 @@ __device__ __forceinline__ void lw_band_terms(const LwPair &p, bool lower, PW &p
             key4(pw, B, LS_ABSA, IND0A(1) + 1, IND1A(1) + 1, p.colh2o, p);
             lerp2(pw, B, LS_SELF, p.inds, p.selffrac, p.selffac);
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
-            lerp2(pw, B, LS_MA1, p.indm, p.minorfrac, scaleo2);
+            if (scaleo2 != 0.0) lerp2(pw, B, LS_MA1, p.indm, p.minorfrac, scaleo2);
             frac_const(pw, B, LS_FRACA);
         } else {
             key4(pw, B, LS_ABSB, IND0B(1) + 1, IND1B(1) + 1, p.colh2o, p);
             lerp2(pw, B, LS_FOR, p.indf, p.forfrac, p.forfac);
-            lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, scaleo2);
+            if (scaleo2 != 0.0) lerp2(pw, B, LS_MB1, p.indm, p.minorfrac, scaleo2);
             frac_const(pw, B, LS_FRACB);
         }
     } else if constexpr (BAND == 11) { // band 12: 1800-2080, H2O/CO2 lower; nothing above (:2190-2392)

@@ -537,7 +537,8 @@ static void launch_tma(const LwTables &t, const LwIn &in, const LwOut &out, LwWo
 template <bool AER, int LMAX>
 static void launch_tma_pick(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s, int v)
 {
-    // measured at T170L60 (stages x layers per stage): 2x4 7.60 ms, 2x3 7.68, 3x3 7.77, 2x5 8.02, 2x6 8.31, 3x4 8.39, 4x4 10.1
+    // measured at T170L60 (stages x layers per stage): 2x4 7.60 ms, 2x3 7.68, 3x3 7.77, 2x5 8.02, 4x2 8.06, 3x2 8.07, 2x6 8.31, 3x4 8.39,
+    // 5x2 8.65, 6x1 9.74, 4x4 10.1; a suspend-time hint on the consumers' try_wait (200 ns .. 20 us): no change
     // (a 56-register build that fits six blocks per SM measured 8.4 ms)
 #ifdef RRTMG_B200_DEV_VARIANTS
     if (v == 3) { launch_tma<AER, LMAX, 3, 4>(t, in, out, w, s); return; }

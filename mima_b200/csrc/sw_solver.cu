@@ -561,6 +561,8 @@ __global__ void __launch_bounds__(SV_THREADS, 4) sw_solver_kernel(SwTables T, Sw
 // =====================================================================================================
 // WPB: resident one-warp blocks per SM the register allocation aims at (28 -> 72 registers, 32 -> 64);
 // U: layers per load group (measured at T170L60: U = 1 11.16 ms, 2 10.79 ms, 4 11.41 ms with 108 B of spills)
+// (the per-lane loop invariants kept in shared memory instead of registers -- 32 blocks per SM at 64 registers -- measured
+// 10.64 against 10.71 ms: within noise, not kept)
 template <int LMAX, int WPB, int U = SV_U>
 __global__ void __launch_bounds__(32, WPB) sw_solver_warp_kernel(SwTables T, SwIn in, SwWork w)
 {
