@@ -204,6 +204,8 @@ int rrtmg_b200_set_chunk(int ncol_per_pass);
  *                    One shot: the copies are forgotten after the LW call; an LW call with other pointers or with
  *                    LW-only array inputs (CFCs, emis, tauaer, clouds) uploads everything itself.  Default 0.
  *   "capture_stages" 1: keep a copy of lw.taug / lw.fracs, which the LW solver otherwise overwrites in place (test hook).
+ *   "lw_fused"       1 (default): clear-sky longwave calls without derivatives (icld = 0, idrv = 0) run the fused column
+ *                    kernel; 0: they run the staged kernels that every other longwave configuration uses.
  *   "kernel_timing"  see rrtmg_b200_kernel_times.
  *   "sw_solver_variant", "lw_rtrn_variant", "x0".."x7"   development builds only (RRTMG_B200_DEV_VARIANTS=1 python -m mima_b200.build
  *                    --force): the earlier and the experimental forms of the two solvers, kept for comparison (sw_solver.cu,
@@ -215,7 +217,9 @@ int rrtmg_b200_set_option(const char *key, long value);
 
 /* With option "kernel_timing" = 1 every kernel launch is bracketed by CUDA events on its stream.  Returns the
  * accumulated device time [ms] and launch count per kernel since the last reset, in the order
- * lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver (arrays of 6). */
+ * lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver, lw_column (arrays of 7).  lw_column is the fused clear-sky
+ * longwave kernel (taumol + rtrn per column, and its flux kernel); it replaces lw_taumol and lw_rtrn for icld = 0, idrv = 0
+ * unless option "lw_fused" = 0 selects the staged kernels for those calls too. */
 int rrtmg_b200_kernel_times(double *ms, long *launches, int reset);
 
 /* ---- the radiation driver around the two calls ------------------

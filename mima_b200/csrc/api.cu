@@ -543,9 +543,10 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields, bool cloud
     w.nc = nc; w.nlay = nlay;
     const size_t np = (size_t)nc * nlay;
     w.laytrop = c.take<int>(nc);
-    // per-cell setcoef state is only materialised for the stage-capture test hook
-    w.idx = fields ? c.take<uint32_t>(np) : nullptr;
-    w.f = fields ? c.take<double>(np * LF_COUNT) : nullptr;
+    // per-cell setcoef state: what the tasks of the fused clear-sky kernel read, and what the stage-capture test hook returns
+    (void)fields;
+    w.idx = c.take<uint32_t>(np);
+    w.f = c.take<double>(np * LF_COUNT);
     w.idrv = 0;
     w.dplankbnd = c.take<double>((size_t)nc * 16);
     w.cs_coldry = c.take<double>(np);
@@ -555,8 +556,14 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields, bool cloud
     w.planklay = c.take<double>(np * 16);
     w.planklev = c.take<double>((size_t)nc * (nlay + 1) * 16);
     w.plankbnd = c.take<double>((size_t)nc * 16);
-    w.taug = c.take<double>(np * NGPTLW);
-    w.fracs = c.take<double>(np * NGPTLW);
+    // staging: [col][lay][140] twice for the staged kernels; the fused kernel sees the same storage as one field of pairs
+    // over whole 32-column tiles
+    w.ncp = (nc + 31) & ~31;
+    const size_t npp = (size_t)w.ncp * nlay;
+    w.colst = c.take<double>(2 * npp * NGPTLW);
+    w.taug = w.colst;
+    w.fracs = w.colst + npp * NGPTLW;
+    w.part = c.take<double>((size_t)LW_NTASK * 2 * (nlay + 1) * w.ncp);
     w.taucloud = cloud ? c.take<double>(np * 16) : nullptr;
     w.ncbands = cloud ? c.take<int>(nc) : nullptr;
     w.err = cloud ? (int *)G.lw_err.p : nullptr;
@@ -944,7 +951,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
+Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}, 1};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1138,7 +1145,8 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
 extern "C" {
 
 /* Accumulated device time [ms] and launch count per kernel since the last reset (needs option
- * "kernel_timing" = 1).  Order: lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver. */
+ * "kernel_timing" = 1).  Order: lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver, lw_column (arrays of 7;
+ * lw_column = the fused clear-sky kernel + lw_finish, which replace lw_taumol and lw_rtrn when they apply). */
 int rrtmg_b200_kernel_times(double *ms, long *launches, int reset)
 {
     KT.collect();
@@ -1742,6 +1750,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "share_inputs") { G.share_inputs = value != 0; G.shared.valid = false; return RRTMG_B200_OK; }
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "taumol_sync") { g_tune.taumol_sync = (int)value; return RRTMG_B200_OK; }
+    if (k == "lw_fused") { g_tune.lw_fused = value != 0; return RRTMG_B200_OK; }
 #ifdef RRTMG_B200_DEV_VARIANTS
     if (k == "dev_variants") return RRTMG_B200_OK;
     if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }

@@ -1,0 +1,388 @@
+// lw_column.cu -- RRTMG longwave, clear sky: taumol and rtrn fused per (column, g-point slice) on sm_100a.
+//
+// What is computed: LW/src/rrtmg_lw_taumol.f90:260-3147 (taugb1..16, through lw_band_terms in lw_bands.cuh),
+// the Planck sources of LW/src/rrtmg_lw_setcoef.f90:154-249, and the clear branches of LW/src/rrtmg_lw_rtrnmr.f90:481-777
+// (identical in rtrnmc.f90:407-432, 481-503); taut = taug + tauaer (rad.nomcica:514-519, iaer = 10 forced).
+//
+// How: lanes = 32 adjacent columns, a warp = (32-column tile, task), a task = up to eight g-points of one band.  The thread
+// walks its column from the top layer down: it reads the cell's setcoef state (written once per cell by lw_prep_cell, read
+// back by the 23 tasks of the tile while it is still in L2), evaluates the band formula for its g-points into registers,
+// interpolates the three Planck values of the layer, and feeds the N downward recurrences at once -- the optical depths
+// never leave the registers, and the N independent chains hide the latency of the one-level-at-a-time recurrence.  What the
+// upward sweep needs again, the layer's absorptivity and upward source per g-point, goes to a scratch field as one 16-byte
+// store per lane (512 contiguous bytes per warp); the upward sweep streams it back.  So the staging traffic is one write
+// and one read of 16 bytes per (cell, g-point), every access a whole number of 128-byte lines, where the staged pipeline
+// (lw_taumol -> [col][lay][g] -> lw_rtrn) wrote the same volume in scattered 16-128 byte pieces and read it twice.  Each
+// warp leaves its g-sums per level in a partial field [task][level][column]; lw_finish adds the 23 partials of a level in
+// task order (fixed summation order: results are reproducible bit for bit) and writes fluxes and heating rates.
+//
+// Used for icld = 0, idrv = 0 without stage capture; everything else keeps the staged kernels (lw_kernels.cu, lw_solver.cu).
+// Compiled with -fmad=false like the other setcoef/taumol code; the recurrences spell their fma() out.
+#include "lw_bands.cuh"
+
+namespace rrtmg {
+
+int lw_column_upload_const(const LwConst &c)
+{
+    return cudaMemcpyToSymbol(c_lw, &c, sizeof(LwConst)) == cudaSuccess ? 0 : -1;
+}
+
+// ---- tasks: (band, first g-point inside the band, count).  Bands of more than eight g-points are cut in two so that the
+// taug / fracs / radiance registers of a task stay within the 128-register budget of four 128-thread blocks per SM.
+struct LwTask { int band, g0, n; };
+__host__ __device__ constexpr LwTask lw_task(int t)
+{
+    constexpr LwTask tk[LW_NTASK] = {
+        {0, 0, 6}, {0, 6, 4}, {1, 0, 6}, {1, 6, 6}, {2, 0, 8}, {2, 8, 8}, {3, 0, 8}, {3, 8, 6}, {4, 0, 8}, {4, 8, 8},
+        {5, 0, 8}, {6, 0, 6}, {6, 6, 6}, {7, 0, 8}, {8, 0, 6}, {8, 6, 6}, {9, 0, 6}, {10, 0, 8}, {11, 0, 8},
+        {12, 0, 4}, {13, 0, 2}, {14, 0, 2}, {15, 0, 2}};
+    return tk[t];
+}
+// launch order of the tasks of a tile group: the long ones (binary-species bands, eight g-points) first
+__constant__ unsigned char c_task_order[LW_NTASK] = {4, 5, 8, 9, 6, 7, 11, 12, 14, 15, 18, 19, 22, 21, 0, 13, 10, 17, 2, 3, 1, 16, 20};
+
+// accumulator policy of lw_band_terms for a slice [G0, G0 + N) of a band: taug and fracs stay in registers
+template <int N>
+struct SliceAcc {
+    double t[N], f[N];
+    const double *__restrict__ tab;  // band table shifted by G0: rows [row][rs]
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int g = 0; g < N; ++g) { t[g] = 0.0; f[g] = 0.0; }
+    }
+    __device__ __forceinline__ void add(int off, double wgt)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            t[2 * j] = fma(wgt, v.x, t[2 * j]);
+            t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
+        }
+    }
+    __device__ __forceinline__ void add_nz(int off, double wgt)
+    {
+        if (wgt != 0.0) add(off, wgt);
+    }
+    __device__ __forceinline__ void scale(int off)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            t[2 * j] = t[2 * j] * v.x;
+            t[2 * j + 1] = t[2 * j + 1] * v.y;
+        }
+    }
+    __device__ __forceinline__ void frac1(int off)
+    {
+        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+            const double2 v = __ldg(q + j);
+            f[2 * j] = v.x; f[2 * j + 1] = v.y;
+        }
+    }
+    __device__ __forceinline__ void frac2(int o0, double w0, int o1, double w1)
+    {
+        const double2 *__restrict__ q0 = reinterpret_cast<const double2 *>(tab + o0);
+        const double2 *__restrict__ q1 = reinterpret_cast<const double2 *>(tab + o1);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+            const double2 a = __ldg(q0 + j), b = __ldg(q1 + j);
+            f[2 * j] = fma(w1, b.x, w0 * a.x);
+            f[2 * j + 1] = fma(w1, b.y, w0 * a.y);
+        }
+    }
+    __device__ __forceinline__ void fzero()
+    {
+#pragma unroll
+        for (int g = 0; g < N; ++g) f[g] = 0.0;
+    }
+};
+
+// the cell's setcoef state as lw_prep_cell left it ([lay][col] fields); a band uses a few of these, the rest of the loads
+// are dropped by the compiler
+__device__ __forceinline__ void lw_load_pair(const LwWork &w, const LwIn &in, size_t i, LwPair &p)
+{
+    const LwIdx ix = lw_unpack(__ldg(w.idx + i));
+    p.jp = ix.jp; p.jt = ix.jt; p.jt1 = ix.jt1; p.inds = ix.inds; p.indf = ix.indf; p.indm = ix.indm;
+#define LWF(k) __ldg(w.fld(k) + i)
+    p.fac00 = LWF(LF_FAC00); p.fac01 = LWF(LF_FAC01); p.fac10 = LWF(LF_FAC10); p.fac11 = LWF(LF_FAC11);
+    p.colh2o = LWF(LF_COLH2O); p.colco2 = LWF(LF_COLCO2); p.colo3 = LWF(LF_COLO3); p.coln2o = LWF(LF_COLN2O);
+    p.colco = LWF(LF_COLCO); p.colch4 = LWF(LF_COLCH4); p.colo2 = LWF(LF_COLO2); p.colbrd = LWF(LF_COLBRD);
+    p.selffac = LWF(LF_SELFFAC); p.selffrac = LWF(LF_SELFFRAC); p.forfac = LWF(LF_FORFAC); p.forfrac = LWF(LF_FORFRAC);
+    p.minorfrac = LWF(LF_MINORFRAC); p.scaleminor = LWF(LF_SCALEMINOR); p.scaleminorn2 = LWF(LF_SCALEMINORN2);
+    p.coldry = LWF(LF_COLDRY); p.pavel = LWF(LF_PAVEL);
+    // the cross-section amounts are exactly zero when the caller passes no CFC array (MiMA's configuration)
+    p.wx1 = in.ccl4 ? LWF(LF_WX1) : 0.0; p.wx2 = in.cfc11 ? LWF(LF_WX2) : 0.0;
+    p.wx3 = in.cfc12 ? LWF(LF_WX3) : 0.0; p.wx4 = in.cfc22 ? LWF(LF_WX4) : 0.0;
+#undef LWF
+}
+
+// Which setcoef fields the formula of a band reads (bit = LwField; the index word and fac00..fac11 are read by every band
+// except where a region has no key species, and are always included).  Used to prefetch the next layer's state into L1
+// while the current layer is evaluated: the field loads are the first link of the per-layer dependency chain
+// (fields -> table rows -> exp/tfn gather), and a warp has only its own g-points to overlap it with.
+#define FB(k) (1u << (k))
+__host__ __device__ constexpr unsigned lw_band_fields(int band)
+{
+    constexpr unsigned fac = FB(LF_FAC00) | FB(LF_FAC01) | FB(LF_FAC10) | FB(LF_FAC11);
+    constexpr unsigned self = FB(LF_SELFFAC) | FB(LF_SELFFRAC) | FB(LF_FORFAC) | FB(LF_FORFRAC);
+    constexpr unsigned m[16] = {
+        fac | self | FB(LF_COLH2O) | FB(LF_COLBRD) | FB(LF_SCALEMINORN2) | FB(LF_PAVEL) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O) | FB(LF_PAVEL),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_MINORFRAC) | FB(LF_WX1),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLDRY) | FB(LF_MINORFRAC) | FB(LF_WX2) | FB(LF_WX3),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC) | FB(LF_WX3) | FB(LF_WX4),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCH4) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLO2) | FB(LF_SCALEMINOR) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLN2O) | FB(LF_COLCO2) | FB(LF_COLCO) | FB(LF_COLO3) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLCO2),
+        fac | self | FB(LF_COLN2O) | FB(LF_COLCO2) | FB(LF_COLBRD) | FB(LF_SCALEMINOR) | FB(LF_MINORFRAC),
+        fac | self | FB(LF_COLH2O) | FB(LF_COLCH4)};
+    return m[band];
+}
+#undef FB
+__device__ __forceinline__ void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int BAND>
+__device__ __forceinline__ void lw_prefetch_pair(const LwWork &w, const LwIn &in, size_t i)
+{
+    constexpr unsigned m = lw_band_fields(BAND);
+    pf_l1(w.idx + i);
+#pragma unroll
+    for (int k = 0; k < LF_COUNT; ++k) {
+        if (!((m >> k) & 1u)) continue;
+        if (k == LF_WX1 && !in.ccl4) continue;
+        if (k == LF_WX2 && !in.cfc11) continue;
+        if (k == LF_WX3 && !in.cfc12) continue;
+        if (k == LF_WX4 && !in.cfc22) continue;
+        pf_l1(w.fld(k) + i);
+    }
+}
+
+// integrated Planck function of one band at temperature t (setcoef.f90:154-249: linear in the 1 K table)
+__device__ __forceinline__ double lw_planck(const double *__restrict__ tp, double t)
+{
+    int ind = (int)(t - 159.);
+    ind = ind < 1 ? 1 : (ind > 180 ? 180 : ind);
+    const double frac = t - 159. - (double)ind;
+    const double lo = __ldg(tp + ind - 1);
+    const double d = __ldg(tp + ind) - lo;
+    return lo + frac * d;
+}
+
+template <int BAND, int G0, int N, bool AER>
+__device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in, const LwWork &w, int task, int tile, int lane)
+{
+    const int nc = w.nc, nlay = w.nlay;
+    const int col = tile * 32 + lane;
+    const bool valid = col < nc;
+    const int cc = valid ? col : nc - 1;                       // idle lanes of the last tile repeat its last column
+    const size_t ld = (size_t)in.ld;
+    const size_t ncp = (size_t)w.ncp;
+    const LwBand &B = c_lw.band[BAND];
+    const int gfirst = B.g0 + G0;                              // first g-point of the task in the 140-vector
+    const double secd = w.secdiff[(size_t)cc * 16 + BAND];
+    const double wgt = 0.5 * c_lw.delwave[BAND];
+    const double bpade = c_lw.bpade;
+    const int laytrop = w.laytrop[cc];
+    const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
+    const double *__restrict__ tp = T.totplnk + BAND * 181;
+    const double *taer = AER ? in.tauaer + cc + (size_t)BAND * nlay * ld : nullptr;
+    double2 *__restrict__ sc = reinterpret_cast<double2 *>(w.colst) + ((size_t)tile * nlay * NGPTLW + gfirst) * 32 + lane;
+    double *__restrict__ pdn = w.part + ((size_t)task * 2 * (nlay + 1)) * ncp + col;
+    double *__restrict__ pup = pdn + (size_t)(nlay + 1) * ncp;
+
+    SliceAcc<N> pw;
+    pw.tab = T.tab + B.base + G0;
+    double rad[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) rad[k] = 0.0;
+    if (valid) pdn[(size_t)nlay * ncp] = 0.0;                  // no downward flux at the top
+    double plev_up = lw_planck(tp, in.tlev[cc + (size_t)nlay * ld]);
+
+    // downward sweep (:505-618), top layer first
+    for (int lay = nlay - 1; lay >= 0; --lay) {
+        if (lay > 0) {                                         // next layer's state and temperatures towards L1
+            lw_prefetch_pair<BAND>(w, in, (size_t)(lay - 1) * nc + cc);
+            pf_l1(in.tlay + cc + (size_t)(lay - 1) * ld);
+            pf_l1(in.tlev + cc + (size_t)(lay - 1) * ld);
+            if (AER) pf_l1(taer + (size_t)(lay - 1) * ld);
+        }
+        LwPair p;
+        lw_load_pair(w, in, (size_t)lay * nc + cc, p);
+        const bool lower = (lay + 1) <= laytrop;
+        pw.clear();
+        lw_band_terms<BAND>(p, lower, pw);
+        const size_t o = cc + (size_t)lay * ld;
+        const double blay = lw_planck(tp, in.tlay[o]);
+        const double plev_dn = lw_planck(tp, in.tlev[o]);
+        const double dplankup = plev_up - blay, dplankdn = plev_dn - blay;
+        plev_up = plev_dn;
+        double ta = 0.0;
+        if (AER) ta = taer[(size_t)lay * ld];
+        double2 *__restrict__ s = sc + (size_t)lay * (NGPTLW * 32);
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double tg = pw.t[k];
+            if (AER) tg = tg + ta;
+            const double plfrac = pw.f[k];
+            double odepth = secd * tg;
+            if (odepth < 0.0) odepth = 0.0;
+            double at, tf;
+            if (odepth <= 0.06) {
+                at = odepth - 0.5 * odepth * odepth;
+                tf = 0.166667 * odepth;
+            } else {
+                const double tblind = odepth * rcp_fast(bpade + odepth);
+                const int itr = (int)(10000.0 * tblind + 0.5);
+                const double2 e = ld_tbl(et + itr);
+                at = 1. - e.x;
+                tf = e.y;
+            }
+            const double bbd = plfrac * fma(tf, dplankdn, blay);
+            const double bbu = plfrac * fma(tf, dplankup, blay);
+            rad[k] = fma(bbd - rad[k], at, rad[k]);
+            sum = fma(rad[k], wgt, sum);
+            if (valid) s[k * 32] = make_double2(at, bbu);
+        }
+        if (valid) pdn[(size_t)lay * ncp] = sum;
+    }
+    // surface (:628-636): after the last iteration pw.f holds the Planck fractions of layer 1
+    {
+        const double semiss = in.emis ? in.emis[cc + (size_t)BAND * ld] : 1.0;
+        const double pb = w.plankbnd[(size_t)cc * 16 + BAND];
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double rad0 = pw.f[k] * pb;
+            rad[k] = rad0 + (1. - semiss) * rad[k];
+            sum = fma(rad[k], wgt, sum);
+        }
+        if (valid) pup[0] = sum;
+    }
+    // upward sweep (:649-711): absorptivity and upward source come back from the scratch field, one layer ahead in registers
+    // and LC_AHEAD layers ahead on their way into L2
+    {
+        constexpr int LC_AHEAD = 4;
+        double2 v[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = valid ? sc[k * 32] : make_double2(0.0, 0.0);
+#pragma unroll 2
+        for (int lay = 0; lay < nlay; ++lay) {
+            double2 nx[N];
+            if (lay + 1 < nlay) {
+                const double2 *__restrict__ s = sc + (size_t)(lay + 1) * (NGPTLW * 32);
+#pragma unroll
+                for (int k = 0; k < N; ++k) nx[k] = valid ? s[k * 32] : make_double2(0.0, 0.0);
+            }
+            if (lay + LC_AHEAD < nlay) {
+                const double2 *__restrict__ s = sc + (size_t)(lay + LC_AHEAD) * (NGPTLW * 32);
+#pragma unroll
+                for (int k = 0; k < N; ++k) pf_l2(s + k * 32);
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                rad[k] = fma(v[k].y - rad[k], v[k].x, rad[k]);
+                sum = fma(rad[k], wgt, sum);
+            }
+            if (valid) pup[(size_t)(lay + 1) * ncp] = sum;
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[k] = nx[k];
+        }
+    }
+}
+
+// Few resident blocks per SM, all warps of a block on the same task: the loop body of a task is 10-20 KB of straight-line code
+// and the instruction cache behind the 6 KB L0 holds 32 KB -- with four 4-warp blocks of different tasks per SM the kernel
+// spent 22 of 23 issue slots waiting for instructions (profiles/r02_summary.md, experiment 5).
+#ifndef LW_COL_WARPS
+#define LW_COL_WARPS 16
+#endif
+#ifndef LW_COL_BLOCKS
+#define LW_COL_BLOCKS 1
+#endif
+constexpr int LC_WARPS = LW_COL_WARPS;
+template <bool AER>
+__global__ void __launch_bounds__(32 * LC_WARPS, LW_COL_BLOCKS) lw_column_kernel(LwTables T, LwIn in, LwWork w)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = blockIdx.x / LW_NTASK;
+    const int task = c_task_order[blockIdx.x - grp * LW_NTASK];
+    const int tile = grp * LC_WARPS + wid;
+    if (tile * 32 >= w.nc) return;
+#define LC_TASK(t) case t: lw_column_task<lw_task(t).band, lw_task(t).g0, lw_task(t).n, AER>(T, in, w, t, tile, lane); break
+    switch (task) {
+        LC_TASK(0); LC_TASK(1); LC_TASK(2); LC_TASK(3); LC_TASK(4); LC_TASK(5); LC_TASK(6); LC_TASK(7);
+        LC_TASK(8); LC_TASK(9); LC_TASK(10); LC_TASK(11); LC_TASK(12); LC_TASK(13); LC_TASK(14); LC_TASK(15);
+        LC_TASK(16); LC_TASK(17); LC_TASK(18); LC_TASK(19); LC_TASK(20); LC_TASK(21); LC_TASK(22);
+    }
+#undef LC_TASK
+}
+
+// The partial g-sums of a level, added in task order; fluxes, heating rates (:751-777) and the copy-out (rad.nomcica:546-555).
+// Block = 32 columns x 8 level lanes; the level fluxes of the tile pass through shared memory for the flux differences.
+constexpr int LF_ROWS = 8;
+__global__ void __launch_bounds__(32 * LF_ROWS) lw_finish_kernel(LwIn in, LwOut out, LwWork w)
+{
+    extern __shared__ double s_fx[];                            // [2][nlay + 1][32]
+    const int nlay = w.nlay, nlev = nlay + 1;
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const bool valid = col < w.nc;
+    const size_t ncp = (size_t)w.ncp;
+    double *s_dn = s_fx, *s_up = s_fx + (size_t)nlev * 32;
+    for (int lev = row; lev < nlev; lev += LF_ROWS) {
+        double d = 0.0, u = 0.0;
+        if (valid) {
+            const double *pd = w.part + (size_t)lev * ncp + col;
+#pragma unroll
+            for (int t = 0; t < LW_NTASK; ++t) {
+                d += pd[(size_t)t * 2 * nlev * ncp];
+                u += pd[((size_t)t * 2 + 1) * nlev * ncp];
+            }
+        }
+        s_dn[lev * 32 + lane] = d * c_lw.fluxfac;
+        s_up[lev * 32 + lane] = u * c_lw.fluxfac;
+    }
+    __syncthreads();
+    if (!valid) return;
+    for (int lev = row; lev < nlev; lev += LF_ROWS) {
+        const size_t o = col + (size_t)lev * out.ld;
+        const double u = s_up[lev * 32 + lane], d = s_dn[lev * 32 + lane];
+        out.uflx[o] = u; out.dflx[o] = d;
+        out.uflxc[o] = u; out.dflxc[o] = d;
+        if (lev < nlay) {
+            const double fnet0 = u - d, fnet1 = s_up[(lev + 1) * 32 + lane] - s_dn[(lev + 1) * 32 + lane];
+            const double pz0 = in.plev[col + (size_t)lev * in.ld], pz1 = in.plev[col + (size_t)(lev + 1) * in.ld];
+            const double h = c_lw.heatfac * (fnet0 - fnet1) / (pz0 - pz1);
+            out.hr[o] = h;
+            out.hrc[o] = h;
+        }
+    }
+}
+
+// returns the number of launches
+int lw_launch_column(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
+{
+    const int ntile = (w.nc + 31) / 32;
+    const unsigned grid = (unsigned)((ntile + LC_WARPS - 1) / LC_WARPS) * LW_NTASK;
+    if (in.tauaer) lw_column_kernel<true><<<grid, 32 * LC_WARPS, 0, s>>>(t, in, w);
+    else lw_column_kernel<false><<<grid, 32 * LC_WARPS, 0, s>>>(t, in, w);
+    const size_t smem = (size_t)2 * (w.nlay + 1) * 32 * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lw_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lw_finish_kernel<<<ntile, 32 * LF_ROWS, smem, s>>>(in, out, w);
+    return 2;
+}
+
+} // namespace rrtmg

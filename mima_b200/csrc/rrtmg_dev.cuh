@@ -105,6 +105,8 @@ struct LwOut {
     double *duflx_dt = nullptr, *duflxc_dt = nullptr;   // (ld, nlay+1), written when idrv == 1
 };
 
+constexpr int LW_NTASK = 23;   // (band, g-point slice) tasks of the fused clear-sky kernel, lw_column.cu
+
 struct LwWork {
     // cloudy sky (null otherwise): band optical depths out of cldprop [col][lay][16], ncbands (1, 5, 16) per column,
     // and the number of the Fortran `stop` some column ran into (0 = none)
@@ -124,6 +126,11 @@ struct LwWork {
     double *planklev;         // [col][lay+1][16]  (level 0 = surface)
     double *plankbnd;         // [col][16]
     double *taug, *fracs;     // [col][lay][140]
+    // fused clear-sky path (lw_column.cu): ncp = nc rounded up to whole 32-column tiles; colst = the storage of taug and
+    // fracs seen as one field of {absorptivity, upward source} pairs [tile][lay][140][32 lanes]; part = the g-sums of every
+    // task per level, [task][down, up][lay+1][ncp]
+    int fused = 0, ncp = 0;
+    double *colst = nullptr, *part = nullptr;
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
@@ -322,7 +329,7 @@ __device__ __forceinline__ double tile_reduce16(const double *tile, double *part
 #endif
 
 // optional per-kernel CUDA-event timing (api.cu); ids: 0 lw_prep, 1 lw_taumol, 2 lw_rtrn, 3 sw_prep, 4 sw_taumol, 5 sw_solver
-enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_COUNT };
+enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_LW_COLUMN, K_COUNT };
 void ktimer_begin(int id, cudaStream_t s);
 void ktimer_end(cudaStream_t s);
 
@@ -331,6 +338,7 @@ void ktimer_end(cudaStream_t s);
 struct Tuning {
     int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant, lw_rtrn_variant, taumol_sync;
     int x[8];                 // experiment knobs ("x0".."x7")
+    int lw_fused;             // 1 (default): clear-sky LW without derivatives runs the fused column kernel (lw_column.cu)
 };
 extern Tuning g_tune;
 
@@ -338,6 +346,8 @@ extern Tuning g_tune;
 int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb);
 int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb);
 int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s);   // returns the launch count
+int lw_column_upload_const(const LwConst &c);
+int lw_launch_column(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s);   // fused clear sky; returns the launch count
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s);   // returns the launch count
 
 // kernel launchers (defined in lw_kernels.cu / sw_kernels.cu); each returns the number of launches
