@@ -546,7 +546,7 @@ size_t lw_carve(LwWork &w, void *base, int nc, int nlay, bool fields, bool cloud
     // per-cell setcoef state: what the tasks of the fused clear-sky kernel read, and what the stage-capture test hook returns
     (void)fields;
     w.idx = c.take<uint32_t>(np);
-    w.f = c.take<double>(np * LF_COUNT);
+    w.f = c.take<double>((size_t)((nc + 31) & ~31) * nlay * LF_SLOTS);      // [field][lay][col], or tile-major in the fused path
     w.idrv = 0;
     w.dplankbnd = c.take<double>((size_t)nc * 16);
     w.cs_coldry = c.take<double>(np);

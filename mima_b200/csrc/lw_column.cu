@@ -20,6 +20,13 @@
 // Compiled with -fmad=false like the other setcoef/taumol code; the recurrences spell their fma() out.
 #include "lw_bands.cuh"
 
+#ifndef LW_COL_STREAM
+#define LW_COL_STREAM 1
+#endif
+#ifndef LW_COL_PIPE
+#define LW_COL_PIPE 0
+#endif
+
 namespace rrtmg {
 
 int lw_column_upload_const(const LwConst &c)
@@ -102,13 +109,13 @@ struct SliceAcc {
     }
 };
 
-// the cell's setcoef state as lw_prep_cell left it ([lay][col] fields); a band uses a few of these, the rest of the loads
-// are dropped by the compiler
-__device__ __forceinline__ void lw_load_pair(const LwWork &w, const LwIn &in, size_t i, LwPair &p)
+// the cell's setcoef state as lw_prep_cell left it (tile-major: f points at [lay][tile][0][lane], field k at f[k * 32]); a band
+// uses a few of these, the rest of the loads are dropped by the compiler
+__device__ __forceinline__ void lw_load_pair(const double *__restrict__ f, const LwIn &in, LwPair &p)
 {
-    const LwIdx ix = lw_unpack(__ldg(w.idx + i));
+#define LWF(k) __ldg(f + (k) * 32)
+    const LwIdx ix = lw_unpack((uint32_t)__double2loint(LWF(LF_COUNT)));
     p.jp = ix.jp; p.jt = ix.jt; p.jt1 = ix.jt1; p.inds = ix.inds; p.indf = ix.indf; p.indm = ix.indm;
-#define LWF(k) __ldg(w.fld(k) + i)
     p.fac00 = LWF(LF_FAC00); p.fac01 = LWF(LF_FAC01); p.fac10 = LWF(LF_FAC10); p.fac11 = LWF(LF_FAC11);
     p.colh2o = LWF(LF_COLH2O); p.colco2 = LWF(LF_COLCO2); p.colo3 = LWF(LF_COLO3); p.coln2o = LWF(LF_COLN2O);
     p.colco = LWF(LF_COLCO); p.colch4 = LWF(LF_COLCH4); p.colo2 = LWF(LF_COLO2); p.colbrd = LWF(LF_COLBRD);
@@ -121,53 +128,27 @@ __device__ __forceinline__ void lw_load_pair(const LwWork &w, const LwIn &in, si
 #undef LWF
 }
 
-// Which setcoef fields the formula of a band reads (bit = LwField; the index word and fac00..fac11 are read by every band
-// except where a region has no key species, and are always included).  Used to prefetch the next layer's state into L1
-// while the current layer is evaluated: the field loads are the first link of the per-layer dependency chain
-// (fields -> table rows -> exp/tfn gather), and a warp has only its own g-points to overlap it with.
-#define FB(k) (1u << (k))
-__host__ __device__ constexpr unsigned lw_band_fields(int band)
-{
-    constexpr unsigned fac = FB(LF_FAC00) | FB(LF_FAC01) | FB(LF_FAC10) | FB(LF_FAC11);
-    constexpr unsigned self = FB(LF_SELFFAC) | FB(LF_SELFFRAC) | FB(LF_FORFAC) | FB(LF_FORFRAC);
-    constexpr unsigned m[16] = {
-        fac | self | FB(LF_COLH2O) | FB(LF_COLBRD) | FB(LF_SCALEMINORN2) | FB(LF_PAVEL) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O) | FB(LF_PAVEL),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_MINORFRAC) | FB(LF_WX1),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLDRY) | FB(LF_MINORFRAC) | FB(LF_WX2) | FB(LF_WX3),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2) | FB(LF_COLO3) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC) | FB(LF_WX3) | FB(LF_WX4),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCH4) | FB(LF_COLN2O) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLO2) | FB(LF_SCALEMINOR) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCO2),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLN2O) | FB(LF_COLCO2) | FB(LF_COLCO) | FB(LF_COLO3) | FB(LF_COLDRY) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLCO2),
-        fac | self | FB(LF_COLN2O) | FB(LF_COLCO2) | FB(LF_COLBRD) | FB(LF_SCALEMINOR) | FB(LF_MINORFRAC),
-        fac | self | FB(LF_COLH2O) | FB(LF_COLCH4)};
-    return m[band];
-}
-#undef FB
-__device__ __forceinline__ void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int BAND>
-__device__ __forceinline__ void lw_prefetch_pair(const LwWork &w, const LwIn &in, size_t i)
+// the scratch field is written once and read once, 60 layers apart: keep it out of L1, which the k-tables, the exp/tfn
+// table and the prefetched setcoef state need
+__device__ __forceinline__ double2 ld_scratch(const double2 *p)
 {
-    constexpr unsigned m = lw_band_fields(BAND);
-    pf_l1(w.idx + i);
-#pragma unroll
-    for (int k = 0; k < LF_COUNT; ++k) {
-        if (!((m >> k) & 1u)) continue;
-        if (k == LF_WX1 && !in.ccl4) continue;
-        if (k == LF_WX2 && !in.cfc11) continue;
-        if (k == LF_WX3 && !in.cfc12) continue;
-        if (k == LF_WX4 && !in.cfc22) continue;
-        pf_l1(w.fld(k) + i);
-    }
+    double2 v;
+#if LW_COL_STREAM
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
+    v = *p;
+#endif
+    return v;
 }
-
+__device__ __forceinline__ void st_scratch(double2 *p, double a, double b)
+{
+#if LW_COL_STREAM
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+#else
+    *p = make_double2(a, b);
+#endif
+}
 // integrated Planck function of one band at temperature t (setcoef.f90:154-249: linear in the 1 K table)
 __device__ __forceinline__ double lw_planck(const double *__restrict__ tp, double t)
 {
@@ -209,24 +190,34 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
     if (valid) pdn[(size_t)nlay * ncp] = 0.0;                  // no downward flux at the top
     double plev_up = lw_planck(tp, in.tlev[cc + (size_t)nlay * ld]);
 
-    // downward sweep (:505-618), top layer first
+    // downward sweep (:505-618), top layer first.  The setcoef state and the temperatures of the NEXT layer are requested as
+    // soon as the band formula has consumed the current ones (their registers are free from there on), so that the
+    // requests are in flight during the recurrences of the current layer instead of heading the next layer's chain
+    // fields -> table rows -> exp/tfn gather.
+    LwPair p;
+    const size_t fstep = (size_t)(w.ncp >> 5) * (LF_SLOTS * 32);           // one layer of the tile-major state
+    const double *__restrict__ fp = w.f + w.tfld(nlay - 1, cc);
+    const double *__restrict__ tlp = in.tlay + cc + (size_t)(nlay - 1) * ld, *__restrict__ tvp = in.tlev + cc + (size_t)(nlay - 1) * ld;
+    lw_load_pair(fp, in, p);
+    double tl = *tlp, tv = *tvp;
     for (int lay = nlay - 1; lay >= 0; --lay) {
-        if (lay > 0) {                                         // next layer's state and temperatures towards L1
-            lw_prefetch_pair<BAND>(w, in, (size_t)(lay - 1) * nc + cc);
-            pf_l1(in.tlay + cc + (size_t)(lay - 1) * ld);
-            pf_l1(in.tlev + cc + (size_t)(lay - 1) * ld);
-            if (AER) pf_l1(taer + (size_t)(lay - 1) * ld);
-        }
-        LwPair p;
-        lw_load_pair(w, in, (size_t)lay * nc + cc, p);
+#if !LW_COL_PIPE
+        lw_load_pair(fp, in, p);
+        tl = *tlp; tv = *tvp;
+        fp -= fstep; tlp -= ld; tvp -= ld;
+#endif
         const bool lower = (lay + 1) <= laytrop;
         pw.clear();
         lw_band_terms<BAND>(p, lower, pw);
-        const size_t o = cc + (size_t)lay * ld;
-        const double blay = lw_planck(tp, in.tlay[o]);
-        const double plev_dn = lw_planck(tp, in.tlev[o]);
+        const double blay = lw_planck(tp, tl);
+        const double plev_dn = lw_planck(tp, tv);
         const double dplankup = plev_up - blay, dplankdn = plev_dn - blay;
         plev_up = plev_dn;
+#if LW_COL_PIPE
+        if (lay > 0) { fp -= fstep; tlp -= ld; tvp -= ld; }
+        lw_load_pair(fp, in, p);
+        tl = *tlp; tv = *tvp;
+#endif
         double ta = 0.0;
         if (AER) ta = taer[(size_t)lay * ld];
         double2 *__restrict__ s = sc + (size_t)lay * (NGPTLW * 32);
@@ -253,7 +244,7 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
             const double bbu = plfrac * fma(tf, dplankup, blay);
             rad[k] = fma(bbd - rad[k], at, rad[k]);
             sum = fma(rad[k], wgt, sum);
-            if (valid) s[k * 32] = make_double2(at, bbu);
+            if (valid) st_scratch(s + k * 32, at, bbu);
         }
         if (valid) pdn[(size_t)lay * ncp] = sum;
     }
@@ -276,14 +267,14 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
         constexpr int LC_AHEAD = 4;
         double2 v[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = valid ? sc[k * 32] : make_double2(0.0, 0.0);
+        for (int k = 0; k < N; ++k) v[k] = valid ? ld_scratch(sc + k * 32) : make_double2(0.0, 0.0);
 #pragma unroll 2
         for (int lay = 0; lay < nlay; ++lay) {
             double2 nx[N];
             if (lay + 1 < nlay) {
                 const double2 *__restrict__ s = sc + (size_t)(lay + 1) * (NGPTLW * 32);
 #pragma unroll
-                for (int k = 0; k < N; ++k) nx[k] = valid ? s[k * 32] : make_double2(0.0, 0.0);
+                for (int k = 0; k < N; ++k) nx[k] = valid ? ld_scratch(s + k * 32) : make_double2(0.0, 0.0);
             }
             if (lay + LC_AHEAD < nlay) {
                 const double2 *__restrict__ s = sc + (size_t)(lay + LC_AHEAD) * (NGPTLW * 32);

@@ -55,6 +55,26 @@ __global__ void __launch_bounds__(128) lw_prep_cell_kernel(LwTables T, LwIn in, 
     w.cs_coldry[i] = p.coldry;
     w.cs_wkl1[i] = wkl1;
     w.cs_lower[i] = lower ? 1 : 0;
+    if (w.fused) {             // tile-major state for the fused column kernel, which also interpolates the Planck sources itself
+        double *f = w.f + w.tfld(l, col);
+#define TF(k) f[(k) * 32]
+        TF(LF_COUNT) = __hiloint2double(0, (int)lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm));
+        TF(LF_FAC00) = p.fac00; TF(LF_FAC01) = p.fac01; TF(LF_FAC10) = p.fac10; TF(LF_FAC11) = p.fac11;
+        TF(LF_COLH2O) = p.colh2o; TF(LF_COLCO2) = p.colco2; TF(LF_COLO3) = p.colo3;
+        TF(LF_COLN2O) = p.coln2o; TF(LF_COLCO) = p.colco; TF(LF_COLCH4) = p.colch4;
+        TF(LF_COLO2) = p.colo2; TF(LF_COLBRD) = p.colbrd;
+        TF(LF_SELFFAC) = p.selffac; TF(LF_SELFFRAC) = p.selffrac;
+        TF(LF_FORFAC) = p.forfac; TF(LF_FORFRAC) = p.forfrac;
+        TF(LF_MINORFRAC) = p.minorfrac; TF(LF_SCALEMINOR) = p.scaleminor;
+        TF(LF_SCALEMINORN2) = p.scaleminorn2; TF(LF_COLDRY) = p.coldry;
+        TF(LF_PAVEL) = p.pavel;
+        if (in.ccl4) TF(LF_WX1) = p.wx1;
+        if (in.cfc11) TF(LF_WX2) = p.wx2;
+        if (in.cfc12) TF(LF_WX3) = p.wx3;
+        if (in.cfc22) TF(LF_WX4) = p.wx4;
+#undef TF
+        return;
+    }
     {
         const size_t wo = i;
         w.idx[wo] = lw_pack(p.jp, p.jt, p.jt1, p.inds, p.indf, p.indm);
@@ -70,7 +90,6 @@ __global__ void __launch_bounds__(128) lw_prep_cell_kernel(LwTables T, LwIn in, 
         w.fld(LF_PAVEL)[wo] = p.pavel;
         w.fld(LF_WX1)[wo] = p.wx1; w.fld(LF_WX2)[wo] = p.wx2; w.fld(LF_WX3)[wo] = p.wx3; w.fld(LF_WX4)[wo] = p.wx4;
     }
-    if (w.fused) return;       // the fused column kernel interpolates the Planck sources itself
     // ---- setcoef: Planck sources (setcoef.f90:154-249)
     const double tavel = in.tlay[o], tz = in.tlev[o + ld];
     int indlay = (int)(tavel - 159.);

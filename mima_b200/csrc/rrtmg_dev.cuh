@@ -105,6 +105,7 @@ struct LwOut {
     double *duflx_dt = nullptr, *duflxc_dt = nullptr;   // (ld, nlay+1), written when idrv == 1
 };
 
+constexpr int LF_SLOTS = LF_COUNT + 1;
 constexpr int LW_NTASK = 23;   // (band, g-point slice) tasks of the fused clear-sky kernel, lw_column.cu
 
 struct LwWork {
@@ -131,6 +132,12 @@ struct LwWork {
     // task per level, [task][down, up][lay+1][ncp]
     int fused = 0, ncp = 0;
     double *colst = nullptr, *part = nullptr;
+    // In the fused path the setcoef state is laid out per (layer, 32-column tile): [lay][tile][LF_SLOTS][32 lanes], slot
+    // LF_COUNT holding the packed index word -- one base pointer per layer and immediate offsets for the fields.
+    __host__ __device__ size_t tfld(int lay, int col) const
+    {
+        return (((size_t)lay * (ncp >> 5) + (col >> 5)) * LF_SLOTS) * 32 + (col & 31);
+    }
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
 };
