@@ -47,7 +47,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # lw_column: the fused clear-sky LW kernel (taumol + rtrn per column) + lw_finish; lw_taumol / lw_rtrn only run in the staged path
-KERNELS = ["lw_prep", "lw_taumol", "lw_rtrn", "sw_prep", "sw_taumol", "sw_solver", "lw_column"]
+KERNELS = ["lw_prep", "lw_taumol", "lw_rtrn", "sw_prep", "sw_taumol", "sw_solver", "lw_column", "sw_column"]
 # BASELINE.json configs: C1 T42L40, C2 T85L40, C3 T170L60 (default), C4 T42L40-4xCO2, C5 T341L80
 WORKLOADS = {"T42L40": ("T42L40", {}), "T85L40": ("T85L40", {}), "T170L60": ("T170L60", {}), "T341L80": ("T341L80", {}),
              "T42L40-4xCO2": ("T42L40", dict(co2_ppmv=1560.0, ozone="file", secondary_gases=True))}
@@ -72,6 +72,7 @@ def kernel_alg_bytes(L: int) -> dict:
         "sw_taumol": 8 * (224 * L),            # write taug, taur (112 g)
         "sw_solver": 8 * (224 * L + 6 * L + 4),
         "lw_column": 8 * (280 * L) + 8 * (280 * L + 6 * L + 4),   # the staging charge of lw_taumol + lw_rtrn, and the outputs
+        "sw_column": 8 * (224 * L) + 8 * (224 * L + 6 * L + 4),   # the same for sw_taumol + sw_solver
     }
 
 

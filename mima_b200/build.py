@@ -19,8 +19,8 @@ LIB = os.path.join(LIBDIR, "librrtmg_b200.so")
 # compiled with -fmad=false so that those decisions match an IEEE host evaluation bit for bit (fused
 # multiply-adds appear only where written as fma()); the solvers carry no such decisions and may contract.
 SOURCES = [("api.cu", False), ("lw_kernels.cu", False), ("lw_column.cu", False), ("sw_kernels.cu", False), ("driver.cu", False),
-           ("lw_solver.cu", True), ("sw_solver.cu", True)]
-HEADERS = ["rrtmg_dev.cuh", "lw_bands.cuh", os.path.join("..", "..", "include", "rrtmg_b200.h")]
+           ("lw_solver.cu", True), ("sw_solver.cu", True), ("sw_column.cu", True)]
+HEADERS = ["rrtmg_dev.cuh", "lw_bands.cuh", "sw_bands.cuh", "sw_twostream.cuh", os.path.join("..", "..", "include", "rrtmg_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

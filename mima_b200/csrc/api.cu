@@ -590,6 +590,12 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool gener
 #else
     w.stack = nullptr;
 #endif
+    w.ncp = (nc + 31) & ~31;
+    if (!general) {             // fused clear-sky kernel: tile-major setcoef state, scratch field, task sums
+        w.tf = c.take<double>((size_t)w.ncp * nlay * SF_SLOTS);
+        w.colst = c.take<double>((size_t)w.ncp * nlay * SW_NSLOT);
+        w.cpart = c.take<double>((size_t)SW_NTASK * 2 * (nlay + 1) * w.ncp);
+    }
     w.opt = general ? c.take<double>(np * 14 * 6) : nullptr;
     w.clfr = general ? c.take<double>(np) : nullptr;
     w.err = general ? (int *)G.sw_err.p : nullptr;
@@ -951,7 +957,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}, 1};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
+Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}, 1, 1};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1145,8 +1151,9 @@ int run_rrtmg_device_impl(const rrtmg_b200_rad_config &c, int si, int sj, int sk
 extern "C" {
 
 /* Accumulated device time [ms] and launch count per kernel since the last reset (needs option
- * "kernel_timing" = 1).  Order: lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver, lw_column (arrays of 7;
- * lw_column = the fused clear-sky kernel + lw_finish, which replace lw_taumol and lw_rtrn when they apply). */
+ * "kernel_timing" = 1).  Order: lw_prep, lw_taumol, lw_rtrn, sw_prep, sw_taumol, sw_solver, lw_column, sw_column (arrays
+ * of 8; lw_column / sw_column = the fused clear-sky kernels with their flux kernels, which replace taumol and the solver
+ * when they apply). */
 int rrtmg_b200_kernel_times(double *ms, long *launches, int reset)
 {
     KT.collect();
@@ -1751,6 +1758,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "lw_rtrn_pad_kb") { g_tune.lw_rtrn_pad_kb = (int)value; return RRTMG_B200_OK; }
     if (k == "taumol_sync") { g_tune.taumol_sync = (int)value; return RRTMG_B200_OK; }
     if (k == "lw_fused") { g_tune.lw_fused = value != 0; return RRTMG_B200_OK; }
+    if (k == "sw_fused") { g_tune.sw_fused = value != 0; return RRTMG_B200_OK; }
 #ifdef RRTMG_B200_DEV_VARIANTS
     if (k == "dev_variants") return RRTMG_B200_OK;
     if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }

@@ -161,6 +161,10 @@ enum SwSec {
     SS_COUNT
 };
 
+constexpr int SF_SLOTS = SF_COUNT + 1;
+constexpr int SW_NTASK = 23;                    // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
+constexpr int SW_NSLOT = 3 * NGPTSW + SW_NTASK;   // scratch slots per (tile, layer)
+
 struct SwBand {
     int ng, rs, g0, base;   // rs: padded row stride, see LwBand
     int sec[SS_COUNT];
@@ -236,6 +240,16 @@ struct SwWork {
     int *err;
     __host__ __device__ const double *fld(int k) const { return f + (size_t)k * nlay * nc; }
     __host__ __device__ double *fld(int k) { return f + (size_t)k * nlay * nc; }
+    // fused clear-sky path (sw_column.cu): ncp = nc rounded up to whole 32-column tiles; tf = the setcoef state per (layer,
+    // tile), [lay][tile][SF_SLOTS][32 lanes] with the packed index word in slot SF_COUNT; colst = per (tile, layer) the
+    // {zp, zq, rdnd} of every g-point and one downward sum per task, [tile][lay][SW_NSLOT][32 lanes]; cpart = the g-sums of
+    // every task per level, [task][up, down][lay+1][ncp]
+    int fused = 0, ncp = 0;
+    double *tf = nullptr, *colst = nullptr, *cpart = nullptr;
+    __host__ __device__ size_t tfld(int lay, int col) const
+    {
+        return (((size_t)lay * (ncp >> 5) + (col >> 5)) * SF_SLOTS) * 32 + (col & 31);
+    }
 };
 
 
@@ -336,7 +350,7 @@ __device__ __forceinline__ double tile_reduce16(const double *tile, double *part
 #endif
 
 // optional per-kernel CUDA-event timing (api.cu); ids: 0 lw_prep, 1 lw_taumol, 2 lw_rtrn, 3 sw_prep, 4 sw_taumol, 5 sw_solver
-enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_LW_COLUMN, K_COUNT };
+enum KernelId { K_LW_PREP, K_LW_TAUMOL, K_LW_RTRN, K_SW_PREP, K_SW_TAUMOL, K_SW_SOLVER, K_LW_COLUMN, K_SW_COLUMN, K_COUNT };
 void ktimer_begin(int id, cudaStream_t s);
 void ktimer_end(cudaStream_t s);
 
@@ -346,6 +360,7 @@ struct Tuning {
     int lw_rtrn_pad_kb, sw_solver_pad_kb, sw_solver_store, sw_solver_variant, lw_rtrn_variant, taumol_sync;
     int x[8];                 // experiment knobs ("x0".."x7")
     int lw_fused;             // 1 (default): clear-sky LW without derivatives runs the fused column kernel (lw_column.cu)
+    int sw_fused;             // 1 (default): SW without clouds and aerosols runs the fused column kernel (sw_column.cu)
 };
 extern Tuning g_tune;
 
@@ -354,6 +369,8 @@ int lw_solver_upload_const(const LwConst &c, const unsigned char *ngb);
 int sw_solver_upload_const(const SwConst &c, const unsigned char *ngb);
 int lw_launch_rtrn(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s);   // returns the launch count
 int lw_column_upload_const(const LwConst &c);
+int sw_column_upload_const(const SwConst &c);
+int sw_launch_column(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s);   // fused clear sky; returns the launch count
 int lw_launch_column(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s);   // fused clear sky; returns the launch count
 int sw_launch_solver(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s);   // returns the launch count
 

@@ -19,8 +19,9 @@ def test_algorithmic_bytes_split_adds_up():
     b = _bench()
     for L in (40, 60, 80):
         k = b.kernel_alg_bytes(L)
-        assert k["lw_column"] == k["lw_taumol"] + k["lw_rtrn"]        # the fused kernel carries the charge of the two it replaces
-        assert sum(v for n, v in k.items() if n != "lw_column") == b.b_alg(L) == 8 * (1060 * L + 35)
+        assert k["lw_column"] == k["lw_taumol"] + k["lw_rtrn"]        # a fused kernel carries the charge of the two it replaces
+        assert k["sw_column"] == k["sw_taumol"] + k["sw_solver"]
+        assert sum(v for n, v in k.items() if not n.endswith("_column")) == b.b_alg(L) == 8 * (1060 * L + 35)
 
 
 def test_workloads_cover_baseline_configs():
