@@ -957,7 +957,7 @@ int host_chunk(int ncol)
 } // namespace
 
 namespace rrtmg {
-Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}, 1, 1};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
+Tuning g_tune = {0, 0, 0, 4, 2, 4, {0, 3, 0, 0, 0, 0, 0, 0}, 1, 1, 0};   // taumol_sync: one block barrier per 4 bands (measured 1: 9.72, 2: 9.53, 4: 9.46, 16: 9.67 ms LW)
 void ktimer_begin(int id, cudaStream_t s)
 {
     if (!KT.on) return;
@@ -1759,6 +1759,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     if (k == "taumol_sync") { g_tune.taumol_sync = (int)value; return RRTMG_B200_OK; }
     if (k == "lw_fused") { g_tune.lw_fused = value != 0; return RRTMG_B200_OK; }
     if (k == "sw_fused") { g_tune.sw_fused = value != 0; return RRTMG_B200_OK; }
+    if (k == "col_warps" && (value == 0 || value == 8 || value == 16)) { g_tune.col_warps = (int)value; return RRTMG_B200_OK; }
 #ifdef RRTMG_B200_DEV_VARIANTS
     if (k == "dev_variants") return RRTMG_B200_OK;
     if (k == "lw_rtrn_variant") { g_tune.lw_rtrn_variant = (int)value; return RRTMG_B200_OK; }

@@ -296,21 +296,15 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
 
 // Few resident blocks per SM, all warps of a block on the same task: the loop body of a task is 10-20 KB of straight-line code
 // and the instruction cache behind the 6 KB L0 holds 32 KB -- with four 4-warp blocks of different tasks per SM the kernel
-// spent 22 of 23 issue slots waiting for instructions (profiles/r02_summary.md, experiment 5).
-#ifndef LW_COL_WARPS
-#define LW_COL_WARPS 16
-#endif
-#ifndef LW_COL_BLOCKS
-#define LW_COL_BLOCKS 1
-#endif
-constexpr int LC_WARPS = LW_COL_WARPS;
-template <bool AER>
-__global__ void __launch_bounds__(32 * LC_WARPS, LW_COL_BLOCKS) lw_column_kernel(LwTables T, LwIn in, LwWork w)
+// spent 22 of 23 issue slots waiting for instructions (profiles/r02_summary.md, experiment 5).  Two 8-warp blocks per SM
+// measured best at every batch size (T170L60: 10.4 ms against 11.1 ms with one 16-warp block; option "col_warps").
+template <bool AER, int WARPS, int BLOCKS>
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS) lw_column_kernel(LwTables T, LwIn in, LwWork w)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int grp = blockIdx.x / LW_NTASK;
     const int task = c_task_order[blockIdx.x - grp * LW_NTASK];
-    const int tile = grp * LC_WARPS + wid;
+    const int tile = grp * WARPS + wid;
     if (tile * 32 >= w.nc) return;
 #define LC_TASK(t) case t: lw_column_task<lw_task(t).band, lw_task(t).g0, lw_task(t).n, AER>(T, in, w, t, tile, lane); break
     switch (task) {
@@ -363,13 +357,21 @@ __global__ void __launch_bounds__(32 * LF_ROWS) lw_finish_kernel(LwIn in, LwOut 
     }
 }
 
+template <bool AER, int WARPS, int BLOCKS>
+static void lw_launch_column_geom(const LwTables &t, const LwIn &in, LwWork &w, cudaStream_t s)
+{
+    const int ntile = (w.nc + 31) / 32;
+    const unsigned grid = (unsigned)((ntile + WARPS - 1) / WARPS) * LW_NTASK;
+    lw_column_kernel<AER, WARPS, BLOCKS><<<grid, 32 * WARPS, 0, s>>>(t, in, w);
+}
+
 // returns the number of launches
 int lw_launch_column(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
     const int ntile = (w.nc + 31) / 32;
-    const unsigned grid = (unsigned)((ntile + LC_WARPS - 1) / LC_WARPS) * LW_NTASK;
-    if (in.tauaer) lw_column_kernel<true><<<grid, 32 * LC_WARPS, 0, s>>>(t, in, w);
-    else lw_column_kernel<false><<<grid, 32 * LC_WARPS, 0, s>>>(t, in, w);
+    const bool wide = g_tune.col_warps >= 16;
+    if (in.tauaer) { if (wide) lw_launch_column_geom<true, 16, 1>(t, in, w, s); else lw_launch_column_geom<true, 8, 2>(t, in, w, s); }
+    else { if (wide) lw_launch_column_geom<false, 16, 1>(t, in, w, s); else lw_launch_column_geom<false, 8, 2>(t, in, w, s); }
     const size_t smem = (size_t)2 * (w.nlay + 1) * 32 * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(lw_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     lw_finish_kernel<<<ntile, 32 * LF_ROWS, smem, s>>>(in, out, w);

@@ -162,7 +162,10 @@ enum SwSec {
 };
 
 constexpr int SF_SLOTS = SF_COUNT + 1;
-constexpr int SW_NTASK = 23;                    // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
+#ifndef SW_TASK_MAXN
+#define SW_TASK_MAXN 6                          // g-points per task of the fused SW kernel: at most 6 (23 tasks) or 4 (32 tasks)
+#endif
+constexpr int SW_NTASK = SW_TASK_MAXN == 6 ? 23 : 32;   // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
 constexpr int SW_NSLOT = 3 * NGPTSW + SW_NTASK;   // scratch slots per (tile, layer)
 
 struct SwBand {
@@ -361,6 +364,7 @@ struct Tuning {
     int x[8];                 // experiment knobs ("x0".."x7")
     int lw_fused;             // 1 (default): clear-sky LW without derivatives runs the fused column kernel (lw_column.cu)
     int sw_fused;             // 1 (default): SW without clouds and aerosols runs the fused column kernel (sw_column.cu)
+    int col_warps;            // block shape of the fused kernels: 0 = default (LW two 8-warp blocks per SM, SW one 16-warp block), 8 / 16 = forced
 };
 extern Tuning g_tune;
 

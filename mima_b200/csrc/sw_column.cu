@@ -25,13 +25,6 @@
 #include "sw_bands.cuh"
 #include "sw_twostream.cuh"
 
-#ifndef SW_COL_WARPS
-#define SW_COL_WARPS 16
-#endif
-#ifndef SW_COL_BLOCKS
-#define SW_COL_BLOCKS 1
-#endif
-
 namespace rrtmg {
 
 int sw_column_upload_const(const SwConst &c)
@@ -43,10 +36,17 @@ int sw_column_upload_const(const SwConst &c)
 struct SwTask { int band, g0, n; };
 __host__ __device__ constexpr SwTask sw_task(int t)
 {
+#if SW_TASK_MAXN == 6
     constexpr SwTask tk[SW_NTASK] = {
         {0, 0, 6}, {1, 0, 6}, {1, 6, 6}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 6}, {4, 6, 4}, {5, 0, 6}, {5, 6, 4},
         {6, 0, 2}, {7, 0, 6}, {7, 6, 4}, {8, 0, 4}, {8, 4, 4}, {9, 0, 6}, {10, 0, 6}, {11, 0, 4}, {11, 4, 4}, {12, 0, 6},
         {13, 0, 6}, {13, 6, 6}};
+#else
+    constexpr SwTask tk[SW_NTASK] = {
+        {0, 0, 4}, {0, 4, 2}, {1, 0, 4}, {1, 4, 4}, {1, 8, 4}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 4}, {4, 4, 4},
+        {4, 8, 2}, {5, 0, 4}, {5, 4, 4}, {5, 8, 2}, {6, 0, 2}, {7, 0, 4}, {7, 4, 4}, {7, 8, 2}, {8, 0, 4}, {8, 4, 4}, {9, 0, 4},
+        {9, 4, 2}, {10, 0, 4}, {10, 4, 2}, {11, 0, 4}, {11, 4, 4}, {12, 0, 4}, {12, 4, 2}, {13, 0, 4}, {13, 4, 4}, {13, 8, 4}};
+#endif
     return tk[t];
 }
 __host__ __device__ constexpr int sw_band_g0(int band)
@@ -57,7 +57,12 @@ __host__ __device__ constexpr int sw_band_g0(int band)
 // first scratch slot of a task inside a (tile, layer) row: three slots per g-point and one per task
 __host__ __device__ constexpr int sw_task_slot(int t) { return 3 * (sw_band_g0(sw_task(t).band) + sw_task(t).g0) + t; }
 // launch order of the tasks of a tile group: binary-species bands with six g-points first
+#if SW_TASK_MAXN == 6
 __constant__ unsigned char c_sw_task_order[SW_NTASK] = {1, 2, 9, 10, 21, 22, 0, 7, 12, 20, 3, 4, 5, 6, 14, 15, 8, 13, 16, 17, 18, 19, 11};
+#else
+__constant__ unsigned char c_sw_task_order[SW_NTASK] = {2, 3, 4, 12, 13, 29, 30, 31, 0, 5, 6, 7, 8, 9, 10, 16, 17, 19, 20, 21, 23, 25, 26, 27,
+                                                        1, 11, 14, 18, 22, 24, 28, 15};
+#endif
 
 // accumulator policy of sw_band_terms for a slice [G0, G0 + N) of a band: everything stays in registers
 template <int N>
@@ -257,20 +262,24 @@ __device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in
     }
 }
 
-// One resident block per SM, all of its warps on the same task (instruction cache: see lw_column.cu).
-constexpr int SC_WARPS = SW_COL_WARPS;
-__global__ void __launch_bounds__(32 * SC_WARPS, SW_COL_BLOCKS) sw_column_kernel(SwTables T, SwIn in, SwWork w)
+// One 16-warp block per SM, all of its warps on the same task (instruction cache: see lw_column.cu).  A task body with its six
+// inlined reftra instances is about 25 KB: two 8-warp blocks of different tasks per SM measured 21 ms against 12.9 ms.
+template <int WARPS, int BLOCKS>
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS) sw_column_kernel(SwTables T, SwIn in, SwWork w)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int grp = blockIdx.x / SW_NTASK;
     const int task = c_sw_task_order[blockIdx.x - grp * SW_NTASK];
-    const int tile = grp * SC_WARPS + wid;
+    const int tile = grp * WARPS + wid;
     if (tile * 32 >= w.nc) return;
 #define SC_TASK(t) case t: sw_column_task<t>(T, in, w, tile, lane); break
     switch (task) {
         SC_TASK(0); SC_TASK(1); SC_TASK(2); SC_TASK(3); SC_TASK(4); SC_TASK(5); SC_TASK(6); SC_TASK(7);
         SC_TASK(8); SC_TASK(9); SC_TASK(10); SC_TASK(11); SC_TASK(12); SC_TASK(13); SC_TASK(14); SC_TASK(15);
         SC_TASK(16); SC_TASK(17); SC_TASK(18); SC_TASK(19); SC_TASK(20); SC_TASK(21); SC_TASK(22);
+#if SW_TASK_MAXN != 6
+        SC_TASK(23); SC_TASK(24); SC_TASK(25); SC_TASK(26); SC_TASK(27); SC_TASK(28); SC_TASK(29); SC_TASK(30); SC_TASK(31);
+#endif
     }
 #undef SC_TASK
 }
@@ -319,12 +328,25 @@ __global__ void __launch_bounds__(32 * SF_ROWS) sw_cfinish_kernel(SwIn in, SwOut
     }
 }
 
+template <int WARPS, int BLOCKS>
+static void sw_launch_column_geom(const SwTables &t, const SwIn &in, SwWork &w, cudaStream_t s)
+{
+    const int ntile = (w.nc + 31) / 32;
+    const unsigned grid = (unsigned)((ntile + WARPS - 1) / WARPS) * SW_NTASK;
+    sw_column_kernel<WARPS, BLOCKS><<<grid, 32 * WARPS, 0, s>>>(t, in, w);
+}
+
 // returns the number of launches
 int sw_launch_column(const SwTables &t, const SwIn &in, const SwOut &out, SwWork &w, cudaStream_t s)
 {
     const int ntile = (w.nc + 31) / 32;
-    const unsigned grid = (unsigned)((ntile + SC_WARPS - 1) / SC_WARPS) * SW_NTASK;
-    sw_column_kernel<<<grid, 32 * SC_WARPS, 0, s>>>(t, in, w);
+    const bool wide = g_tune.col_warps != 8;
+#ifdef SW_COL_WARPS
+    (void)wide;
+    sw_launch_column_geom<SW_COL_WARPS, 1>(t, in, w, s);
+#else
+    if (wide) sw_launch_column_geom<16, 1>(t, in, w, s); else sw_launch_column_geom<8, 2>(t, in, w, s);
+#endif
     const size_t smem = (size_t)2 * (w.nlay + 1) * 32 * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(sw_cfinish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sw_cfinish_kernel<<<ntile, 32 * SF_ROWS, smem, s>>>(in, out, w);

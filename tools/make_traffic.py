@@ -4,10 +4,11 @@ for each kernel.  usage: make_traffic.py WORKLOAD COLUMNS_PER_LAUNCH raw1.csv [r
 import csv, json, os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 W, ncol = sys.argv[1], int(sys.argv[2])
-names = {"lw_prep": "lw_prep", "lw_taumol": "lw_taumol", "lw_rtrn": "lw_rtrn", "sw_prep": "sw_prep", "sw_taumol": "sw_taumol", "sw_solver": "sw_solver", "sw_finish": "sw_solver"}
+names = {"lw_prep": "lw_prep", "lw_taumol": "lw_taumol", "lw_rtrn": "lw_rtrn", "sw_prep": "sw_prep", "sw_taumol": "sw_taumol", "sw_solver": "sw_solver", "sw_finish": "sw_solver",
+         "lw_column": "lw_column", "lw_finish": "lw_column", "sw_column": "sw_column", "sw_cfinish": "sw_column"}
 out_path = os.path.join(ROOT, "profiles", "traffic.json")
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
-out.setdefault(W, {})
+out[W] = {}        # a capture replaces the workload's entry (kernels that no longer run must not linger)
 for f in sys.argv[3:]:
     rows = list(csv.reader(open(f)))
     hdr, units = rows[0], rows[1]
