@@ -186,8 +186,8 @@ int rrtmg_b200_sw_device(int ncol, int nlay, int *icld, int *iaer,
  * "lw.laytrop","sw.laytrop" (ncol).  Output is column-major with ncol leading, FP64. */
 long rrtmg_b200_get_stage(const char *which, double *out, long capacity);
 
-/* Columns per device pass (0 = automatic: 65536).  The workspace of one pass is ~ chunk * nlay * 2.5 KB (LW) +
- * chunk * nlay * 1.8 KB (SW): 17 GB at 65536 columns x 60 layers.  A pass whose workspace does not fit into the free device
+/* Columns per device pass (0 = automatic: 131072).  The workspace of one pass is ~ chunk * nlay * 3.2 KB (LW) +
+ * chunk * nlay * 4.3 KB (SW): 59 GB at 131072 columns x 60 layers.  A pass whose workspace does not fit into the free device
  * memory is halved until it does (several MPI ranks may share one GPU: MiMA's shipped job size is 32 ranks). */
 int rrtmg_b200_set_chunk(int ncol_per_pass);
 

@@ -604,10 +604,11 @@ size_t sw_carve(SwWork &w, void *base, int nc, int nlay, bool fields, bool gener
 
 int pick_chunk(int ncol)
 {
-    int ch = G.chunk > 0 ? G.chunk : 65536;     // columns per pass; T170L60 step: 16384 35.4, 32768 34.0, 65536 33.65, 131072 33.6 ms
+    // columns per pass; T170L60 step with the column kernels: 16384 28.6, 32768 25.5, 65536 24.3, 131072 23.8 ms
+    int ch = G.chunk > 0 ? G.chunk : 131072;
     return ch < ncol ? ch : ncol;
 }
-// The workspace of a pass is 17 GB at 65536 columns x 60 layers.  MiMA's shipped job size is 32 ranks (exp/nci_runscript.sh:7),
+// The workspace of a pass is 59 GB at 131072 columns x 60 layers (the fields of the fused and of the staged kernels).  MiMA's shipped job size is 32 ranks (exp/nci_runscript.sh:7),
 // i.e. four ranks per GPU on one 8-GPU box: the pass is halved until its workspace fits into what the device has free
 // (beyond what this buffer already holds), so several ranks can share a GPU without an allocation failure.
 // cudaMemGetInfo is a slow, synchronising driver call (measured: 2 ms per call, 4.4 ms per LW+SW step): it is asked only

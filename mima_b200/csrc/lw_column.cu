@@ -20,13 +20,6 @@
 // Compiled with -fmad=false like the other setcoef/taumol code; the recurrences spell their fma() out.
 #include "lw_bands.cuh"
 
-#ifndef LW_COL_STREAM
-#define LW_COL_STREAM 1
-#endif
-#ifndef LW_COL_PIPE
-#define LW_COL_PIPE 0
-#endif
-
 namespace rrtmg {
 
 int lw_column_upload_const(const LwConst &c)
@@ -134,20 +127,12 @@ __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.gl
 __device__ __forceinline__ double2 ld_scratch(const double2 *p)
 {
     double2 v;
-#if LW_COL_STREAM
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-#else
-    v = *p;
-#endif
     return v;
 }
 __device__ __forceinline__ void st_scratch(double2 *p, double a, double b)
 {
-#if LW_COL_STREAM
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-#else
-    *p = make_double2(a, b);
-#endif
 }
 // integrated Planck function of one band at temperature t (setcoef.f90:154-249: linear in the 1 K table)
 __device__ __forceinline__ double lw_planck(const double *__restrict__ tp, double t)
@@ -190,22 +175,15 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
     if (valid) pdn[(size_t)nlay * ncp] = 0.0;                  // no downward flux at the top
     double plev_up = lw_planck(tp, in.tlev[cc + (size_t)nlay * ld]);
 
-    // downward sweep (:505-618), top layer first.  The setcoef state and the temperatures of the NEXT layer are requested as
-    // soon as the band formula has consumed the current ones (their registers are free from there on), so that the
-    // requests are in flight during the recurrences of the current layer instead of heading the next layer's chain
-    // fields -> table rows -> exp/tfn gather.
+    // downward sweep (:505-618), top layer first
     LwPair p;
     const size_t fstep = (size_t)(w.ncp >> 5) * (LF_SLOTS * 32);           // one layer of the tile-major state
     const double *__restrict__ fp = w.f + w.tfld(nlay - 1, cc);
     const double *__restrict__ tlp = in.tlay + cc + (size_t)(nlay - 1) * ld, *__restrict__ tvp = in.tlev + cc + (size_t)(nlay - 1) * ld;
-    lw_load_pair(fp, in, p);
-    double tl = *tlp, tv = *tvp;
     for (int lay = nlay - 1; lay >= 0; --lay) {
-#if !LW_COL_PIPE
         lw_load_pair(fp, in, p);
-        tl = *tlp; tv = *tvp;
+        const double tl = *tlp, tv = *tvp;
         fp -= fstep; tlp -= ld; tvp -= ld;
-#endif
         const bool lower = (lay + 1) <= laytrop;
         pw.clear();
         lw_band_terms<BAND>(p, lower, pw);
@@ -213,11 +191,6 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
         const double plev_dn = lw_planck(tp, tv);
         const double dplankup = plev_up - blay, dplankdn = plev_dn - blay;
         plev_up = plev_dn;
-#if LW_COL_PIPE
-        if (lay > 0) { fp -= fstep; tlp -= ld; tvp -= ld; }
-        lw_load_pair(fp, in, p);
-        tl = *tlp; tv = *tvp;
-#endif
         double ta = 0.0;
         if (AER) ta = taer[(size_t)lay * ld];
         double2 *__restrict__ s = sc + (size_t)lay * (NGPTLW * 32);

@@ -162,10 +162,7 @@ enum SwSec {
 };
 
 constexpr int SF_SLOTS = SF_COUNT + 1;
-#ifndef SW_TASK_MAXN
-#define SW_TASK_MAXN 6                          // g-points per task of the fused SW kernel: at most 6 (23 tasks) or 4 (32 tasks)
-#endif
-constexpr int SW_NTASK = SW_TASK_MAXN == 6 ? 23 : 32;   // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
+constexpr int SW_NTASK = 23;                    // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
 constexpr int SW_NSLOT = 3 * NGPTSW + SW_NTASK;   // scratch slots per (tile, layer)
 
 struct SwBand {

@@ -32,21 +32,15 @@ int sw_column_upload_const(const SwConst &c)
     return cudaMemcpyToSymbol(c_sw, &c, sizeof(SwConst)) == cudaSuccess ? 0 : -1;
 }
 
-// ---- tasks: (band, first g-point inside the band, count)
+// ---- tasks: (band, first g-point inside the band, count).  Tasks of at most four g-points (32 tasks) with 16, 20 or 24 warps per
+// block measured within 3 % of this table (profiles/r02aa_sweep.txt).
 struct SwTask { int band, g0, n; };
 __host__ __device__ constexpr SwTask sw_task(int t)
 {
-#if SW_TASK_MAXN == 6
     constexpr SwTask tk[SW_NTASK] = {
         {0, 0, 6}, {1, 0, 6}, {1, 6, 6}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 6}, {4, 6, 4}, {5, 0, 6}, {5, 6, 4},
         {6, 0, 2}, {7, 0, 6}, {7, 6, 4}, {8, 0, 4}, {8, 4, 4}, {9, 0, 6}, {10, 0, 6}, {11, 0, 4}, {11, 4, 4}, {12, 0, 6},
         {13, 0, 6}, {13, 6, 6}};
-#else
-    constexpr SwTask tk[SW_NTASK] = {
-        {0, 0, 4}, {0, 4, 2}, {1, 0, 4}, {1, 4, 4}, {1, 8, 4}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 4}, {4, 4, 4},
-        {4, 8, 2}, {5, 0, 4}, {5, 4, 4}, {5, 8, 2}, {6, 0, 2}, {7, 0, 4}, {7, 4, 4}, {7, 8, 2}, {8, 0, 4}, {8, 4, 4}, {9, 0, 4},
-        {9, 4, 2}, {10, 0, 4}, {10, 4, 2}, {11, 0, 4}, {11, 4, 4}, {12, 0, 4}, {12, 4, 2}, {13, 0, 4}, {13, 4, 4}, {13, 8, 4}};
-#endif
     return tk[t];
 }
 __host__ __device__ constexpr int sw_band_g0(int band)
@@ -57,12 +51,7 @@ __host__ __device__ constexpr int sw_band_g0(int band)
 // first scratch slot of a task inside a (tile, layer) row: three slots per g-point and one per task
 __host__ __device__ constexpr int sw_task_slot(int t) { return 3 * (sw_band_g0(sw_task(t).band) + sw_task(t).g0) + t; }
 // launch order of the tasks of a tile group: binary-species bands with six g-points first
-#if SW_TASK_MAXN == 6
 __constant__ unsigned char c_sw_task_order[SW_NTASK] = {1, 2, 9, 10, 21, 22, 0, 7, 12, 20, 3, 4, 5, 6, 14, 15, 8, 13, 16, 17, 18, 19, 11};
-#else
-__constant__ unsigned char c_sw_task_order[SW_NTASK] = {2, 3, 4, 12, 13, 29, 30, 31, 0, 5, 6, 7, 8, 9, 10, 16, 17, 19, 20, 21, 23, 25, 26, 27,
-                                                        1, 11, 14, 18, 22, 24, 28, 15};
-#endif
 
 // accumulator policy of sw_band_terms for a slice [G0, G0 + N) of a band: everything stays in registers
 template <int N>
@@ -277,9 +266,6 @@ __global__ void __launch_bounds__(32 * WARPS, BLOCKS) sw_column_kernel(SwTables 
         SC_TASK(0); SC_TASK(1); SC_TASK(2); SC_TASK(3); SC_TASK(4); SC_TASK(5); SC_TASK(6); SC_TASK(7);
         SC_TASK(8); SC_TASK(9); SC_TASK(10); SC_TASK(11); SC_TASK(12); SC_TASK(13); SC_TASK(14); SC_TASK(15);
         SC_TASK(16); SC_TASK(17); SC_TASK(18); SC_TASK(19); SC_TASK(20); SC_TASK(21); SC_TASK(22);
-#if SW_TASK_MAXN != 6
-        SC_TASK(23); SC_TASK(24); SC_TASK(25); SC_TASK(26); SC_TASK(27); SC_TASK(28); SC_TASK(29); SC_TASK(30); SC_TASK(31);
-#endif
     }
 #undef SC_TASK
 }
@@ -341,12 +327,7 @@ int sw_launch_column(const SwTables &t, const SwIn &in, const SwOut &out, SwWork
 {
     const int ntile = (w.nc + 31) / 32;
     const bool wide = g_tune.col_warps != 8;
-#ifdef SW_COL_WARPS
-    (void)wide;
-    sw_launch_column_geom<SW_COL_WARPS, 1>(t, in, w, s);
-#else
     if (wide) sw_launch_column_geom<16, 1>(t, in, w, s); else sw_launch_column_geom<8, 2>(t, in, w, s);
-#endif
     const size_t smem = (size_t)2 * (w.nlay + 1) * 32 * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(sw_cfinish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sw_cfinish_kernel<<<ntile, 32 * SF_ROWS, smem, s>>>(in, out, w);

@@ -8,7 +8,7 @@ set -u
 W=${1:-T170L60}
 mkdir -p gpurun_out
 export RRTMG_SKIP_NIGHT=1
-NPASS=$(python -c "n={'T42L40':8192,'T85L40':32768,'T170L60':131072,'T341L80':524288}['$W']; print((n+65535)//65536)")
+NPASS=$(python -c "n={'T42L40':8192,'T85L40':32768,'T170L60':131072,'T341L80':524288}['$W']; print((n+131071)//131072)")
 STEP=$((NPASS * 8)); SKIP=$((2 * STEP))
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lw_|sw_" -s $SKIP -c 4 -f -o gpurun_out/prof_${W}_sw \
     python bench.py --steps 1 --warmup 2 --workload $W --no-cpu > gpurun_out/ncu_full_${W}.log 2>&1

@@ -1,16 +1,19 @@
 #!/bin/bash
-# final-tree session: the whole GPU suite + smoke + ncu captures (traffic.json stamp) + bench lines
+# final-tree session: the whole GPU suite + smoke + compute-sanitizer + ncu captures (traffic.json stamp) + bench lines
 set -u
-TAG=${1:-r2k}
+TAG=${1:-r2fin}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+for TOOL in memcheck initcheck; do
+  timeout 900 compute-sanitizer --tool $TOOL --print-limit 5 python tools/sanitize_workload.py > gpurun_out/${TAG}_sanitizer_$TOOL.log 2>&1
+  echo "compute-sanitizer $TOOL: $(grep -E 'ERROR SUMMARY' gpurun_out/${TAG}_sanitizer_$TOOL.log | tail -1)"
+done
 bash tools/gpu_profile.sh T170L60 2>&1 | tail -3
 for W in T170L60 T85L40 T42L40 T42L40-4xCO2; do
   timeout 600 python bench.py --steps 20 --warmup 3 --workload $W > gpurun_out/${TAG}_bench_$W.json 2> gpurun_out/${TAG}_bench_$W.err || tail -5 gpurun_out/${TAG}_bench_$W.err
 done
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null
-python tools/gpu_sweep.py T170L60 "" "chunk=131072" "chunk=32768" "lw_fused=0,sw_fused=0" 2>&1 | tee gpurun_out/${TAG}_sweep.txt
 rm -f gpurun_out/*.ncu-rep
 python - <<PY
 import json

@@ -8,6 +8,18 @@ c = make_columns("T42L40", nlon=32, nlat=4, night=True)
 rng = np.random.default_rng(1)
 cl = cloud_field(c, rng)
 rrtmg.lw_from_columns(c); rrtmg.sw_from_columns(c)
+# column kernels: a ragged last tile, less than one tile, the aerosol instantiation of lw_column, both block shapes
+for n in (77, 5):
+    c2 = c.take(np.arange(n))
+    rrtmg.lw_from_columns(c2); rrtmg.sw_from_columns(c2)
+rrtmg.lw_from_columns(c, tauaer=np.asfortranarray(rng.uniform(0.0, 0.05, (c.ncol, c.nlay, 16))))
+for cw in (8, 16, 0):
+    rrtmg.set_option("col_warps", cw)
+    rrtmg.lw_from_columns(c2); rrtmg.sw_from_columns(c2)
+# the staged clear-sky kernels
+rrtmg.set_option("lw_fused", 0); rrtmg.set_option("sw_fused", 0)
+rrtmg.lw_from_columns(c); rrtmg.sw_from_columns(c)
+rrtmg.set_option("lw_fused", 1); rrtmg.set_option("sw_fused", 1)
 import os
 if not os.environ.get("SAN_NO_TMA"):
     rrtmg.lw_from_columns(c, idrv=1)
