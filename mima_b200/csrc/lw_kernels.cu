@@ -1,14 +1,17 @@
-// lw_kernels.cu -- RRTMG longwave on sm_100a: prep (inatm + setcoef), taumol, cldprop.  The solver is in lw_solver.cu.
+// lw_kernels.cu -- RRTMG longwave on sm_100a: prep (inatm + setcoef), the staged taumol kernel, cldprop.  The fused clear-sky
+// kernel is in lw_column.cu, the staged solvers in lw_solver.cu; the per-cell arithmetic they share in lw_bands.cuh.
 //
 // What is computed follows the reference routines (cited per kernel); how it is computed is a GPU-first design:
-//   lw_prep_cell_kernel  thread <-> (column, layer): unit conversion, column amounts, Planck sources of the layer and its
-//                        upper interface, the per-cell terms of the column sums;
+//   lw_prep_cell_kernel  thread <-> (column, layer): unit conversion, column amounts, interpolation indices and factors
+//                        (lw_cell), the per-cell terms of the column sums; for the column kernel the state goes to the
+//                        tile-major field, for the staged kernels the Planck sources of the layer and its upper interface;
 //   lw_prep_kernel       thread <-> column: the column sums in the reference's order (laytrop, precipitable water ->
 //                        diffusivity secant), surface Planck terms;
-//   lw_taumol_kernel     thread <-> (column, layer) cell, lanes = 32 adjacent columns of one layer; the cell's setcoef state
-//                        is evaluated in place (lw_cell), every term w * T[row][.] of a band formula is consumed at once
-//                        into ng register accumulators, and the warps of a block walk the 16 bands together (one block
-//                        barrier per four bands) so that the ~300 KB of straight-line band code is fetched once per block;
+//   lw_taumol_kernel     (staged path: clouds, idrv = 1, stage capture) thread <-> (column, layer) cell, lanes = 32 adjacent
+//                        columns of one layer; the cell's setcoef state is evaluated in place (lw_cell), every term
+//                        w * T[row][.] of a band formula is consumed at once into ng register accumulators, and the warps
+//                        of a block walk the 16 bands together (one block barrier per four bands) so that the ~300 KB of
+//                        straight-line band code is fetched once per block;
 //   lw_cldprop_kernel    thread <-> column (cloudy sky only).
 // Compiled with -fmad=false: fused multiply-adds appear only where written as fma().
 #include "lw_bands.cuh"

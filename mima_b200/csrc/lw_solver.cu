@@ -1,4 +1,6 @@
-// lw_solver.cu -- RRTMG longwave clear-sky radiative transfer on sm_100a.
+// lw_solver.cu -- RRTMG longwave radiative transfer on sm_100a: the STAGED solvers (they read the [col][lay][g] staging that
+// lw_taumol_kernel writes).  They serve idrv = 1, cloudy skies and stage capture; clear-sky calls without derivatives run
+// the fused column kernel of lw_column.cu instead (option lw_fused = 0 sends those here as well).
 //
 // rtrn: LW/src/rrtmg_lw_rtrnmr.f90:481-777 ("Clear layer" branches; identical in rtrnmc.f90:407-432,481-503).
 //       taut = taug + tauaer (rad.nomcica:514-519, iaer = 10 forced).

@@ -2,12 +2,16 @@
 //
 // HBM layout (one "pass" = a chunk of nc columns, all nlay layers):
 //   * interface arrays arrive (ncol, nlay) column-major: the column index is contiguous, so kernels whose lanes are
-//     adjacent columns of one layer (prep, taumol) read fully coalesced.
-//   * the per-cell setcoef state is NOT stored: taumol evaluates it in place (lw_cell / sw_cell).  The fields
-//     F[field][lay][col] and idx exist only for the stage-capture test hook (option capture_stages).
-//   * the taumol -> solver staging fields (LW taug/fracs, SW taug) are stored [col][lay][g] with the g-point index
-//     fastest: one warp of a solver (lanes = g-points of a column) reads 256 contiguous bytes per layer step; taumol
-//     transposes its per-cell results through a per-warp shared-memory slab and writes whole rows in 16-byte pieces.
+//     adjacent columns of one layer (prep, taumol, the column kernels) read fully coalesced.
+//   * clear sky (lw_column.cu, sw_column.cu): everything between the kernels is tile-major -- per 32-column tile
+//     [layer][slot][32 lanes], a slot being one 256-byte row at an immediate offset: the setcoef state written by
+//     *_prep_cell (LwWork::f / SwWork::tf), the scratch field between the two sweeps of a column kernel (colst) and the
+//     per-task g-sums per level (part / cpart).
+//   * staged kernels (clouds, aerosols, idrv = 1, stage capture): the per-cell setcoef state is evaluated in place by
+//     taumol (lw_cell / sw_cell; the fields F[field][lay][col] and idx are what the stage-capture hook returns); the
+//     taumol -> solver staging fields (LW taug/fracs, SW taug) are stored [col][lay][g] with the g-point index fastest:
+//     one warp of a solver (lanes = g-points of a column) reads 256 contiguous bytes per layer step; taumol transposes
+//     its per-cell results through a per-warp shared-memory slab and writes whole rows in 16-byte pieces.
 //   * k-distribution tables are reduced and transposed at init from the Fortran (row, ig) to [row][ig] with the row
 //     stride padded to a power of two, so that the values one interpolation term needs are one <= 128-byte line.
 #pragma once

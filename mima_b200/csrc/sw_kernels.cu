@@ -1,11 +1,14 @@
-// sw_kernels.cu -- RRTMG shortwave on sm_100a: prep (inatm_sw + setcoef_sw), taumol_sw, cloud / aerosol optics.  The
-// two-stream solver (spcvrt + reftra + vrtqdr) is in sw_solver.cu.
+// sw_kernels.cu -- RRTMG shortwave on sm_100a: prep (inatm_sw + setcoef_sw), the staged taumol_sw kernel, cloud / aerosol
+// optics.  The fused clear-sky kernel is in sw_column.cu, the staged two-stream solvers (spcvrt + reftra + vrtqdr) in
+// sw_solver.cu; the per-cell arithmetic they share in sw_bands.cuh and sw_twostream.cuh.
 //
-//   sw_prep_cell_kernel  thread <-> (column, layer): the cell's reference-pressure index and "below 100 hPa" flag;
+//   sw_prep_cell_kernel  thread <-> (column, layer): the cell's reference-pressure index and "below 100 hPa" flag; for the
+//                        column kernel the whole setcoef state into the tile-major field;
 //   sw_prep_kernel       thread <-> column: night marker, laytrop, and per band the layer whose binary-species parameter
 //                        selects the solar source (laysolfr), replaying the sequential loops of taumol16..29;
-//   sw_taumol_kernel     thread <-> (column, layer) cell as in the LW kernel: taug per g-point, the Rayleigh descriptors
-//                        (colmol; taur of band 24) and, from the laysolfr layer, sfluxzen;
+//   sw_taumol_kernel     (staged path: clouds, aerosols, stage capture) thread <-> (column, layer) cell as in the LW kernel:
+//                        taug per g-point, the Rayleigh descriptors (colmol; taur of band 24) and, from the laysolfr layer,
+//                        sfluxzen;
 //   sw_optics_kernel     clouds / aerosols of the general path (not MiMA's configuration).
 // Night columns (coszen < 1e-10) are skipped and written as zeros (rad.nomcica:502-510).
 // Compiled with -fmad=false: fused multiply-adds appear only where written as fma().

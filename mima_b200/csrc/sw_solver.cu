@@ -1,4 +1,6 @@
-// sw_solver.cu -- RRTMG shortwave two-stream solver on sm_100a (clear sky, no aerosol: the MiMA configuration).
+// sw_solver.cu -- RRTMG shortwave two-stream solvers on sm_100a: the STAGED kernels (they read the [col][lay][g] staging that
+// sw_taumol_kernel writes).  The general kernel serves clouds and aerosols; the clear-sky one serves stage capture and option
+// sw_fused = 0 -- clear-sky calls run the fused column kernel of sw_column.cu by default.
 //
 // spcvrt_sw (SW/src/rrtmg_sw_spcvrt.f90:296-619) + reftra_sw (rrtmg_sw_reftra.f90:129-300, kmodts=2)
 //         + vrtqdr_sw (rrtmg_sw_vrtqdr.f90:103-150) + heating (rrtmg_sw_rad.nomcica.f90:686-727).
@@ -7,7 +9,7 @@
 // clear-sky stream bit for bit, so one stream is computed and stored to both outputs.
 //
 // Kernels in this file:
-//   sw_solver_warp_kernel + sw_finish_kernel  the default (option sw_solver_variant = 4): one warp per block, the
+//   sw_solver_warp_kernel + sw_finish_kernel  the staged clear-sky solver (option sw_solver_variant = 4): one warp per block, the
 //        reference's top-down recurrence first, then a two-term upward flux recurrence on three stored values per
 //        cell -- reftra is evaluated once per cell.  Derivation at "Top-down first" in sw_solver_kernel, layout and
 //        the reason for one-warp blocks at sw_solver_warp_kernel.

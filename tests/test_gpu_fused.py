@@ -35,7 +35,10 @@ def test_fused_and_staged_kernels_agree(gpu, oracle, kw):
         _check_outputs(fused, ref, names)
         _check_outputs(staged, ref, names)
         for a, b, n in zip(fused, staged, names):
-            assert np.max(np.abs(a - b)) <= 1e-11 * max(np.abs(b).max(), 1e-300), n
+            if "hr" in n:        # flux differences over layers of down to 0.1 hPa: K/day, against the 1e-4 of north_star
+                assert np.max(np.abs(a - b)) <= 1e-7, n
+            else:
+                assert np.max(np.abs(a - b)) <= 1e-11 * max(np.abs(b).max(), 1e-300), n
             if c.ncol >= 256:
                 assert not np.array_equal(a, b), n                   # two different kernels did run
 
