@@ -275,8 +275,19 @@ template <bool AER, int WARPS, int BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS) lw_column_kernel(LwTables T, LwIn in, LwWork w)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int grp = blockIdx.x / LW_NTASK;
-    const int task = c_task_order[blockIdx.x - grp * LW_NTASK];
+    // Block order: super-groups of COL_SUPER_COLS columns; inside one, all tile groups of the longest task first, then all
+    // of the next, ... (c_task_order).  The 23 tasks of a tile then still run close enough in time to share the tile's
+    // setcoef state through L2 (a super-group's state is ~50 MB), and what is left for the end of the grid are the short
+    // tasks of the last super-group: with ~5 blocks per SM (a rank's 16384 columns at 8 GPUs) the kernel's tail is a short
+    // block instead of a long one.
+    constexpr int SG = COL_SUPER_COLS / (32 * WARPS);
+    const int ngrp = ((w.nc + 31) / 32 + WARPS - 1) / WARPS;
+    const int sg = blockIdx.x / (SG * LW_NTASK);
+    const int gcount = min(SG, ngrp - sg * SG);
+    const int r = blockIdx.x - sg * (SG * LW_NTASK);
+    const int rank = r / gcount;
+    const int grp = sg * SG + (r - rank * gcount);
+    const int task = c_task_order[rank];
     const int tile = grp * WARPS + wid;
     if (tile * 32 >= w.nc) return;
 #define LC_TASK(t) case t: lw_column_task<lw_task(t).band, lw_task(t).g0, lw_task(t).n, AER>(T, in, w, t, tile, lane); break

@@ -367,6 +367,7 @@ struct Tuning {
     int sw_fused;             // 1 (default): SW without clouds and aerosols runs the fused column kernel (sw_column.cu)
     int col_warps;            // block shape of the fused kernels: 0 = default (LW two 8-warp blocks per SM, SW one 16-warp block), 8 / 16 = forced
 };
+constexpr int COL_SUPER_COLS = 4096;   // columns per super-group of the column kernels' block order
 extern Tuning g_tune;
 
 // solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)

@@ -257,8 +257,15 @@ template <int WARPS, int BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS) sw_column_kernel(SwTables T, SwIn in, SwWork w)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int grp = blockIdx.x / SW_NTASK;
-    const int task = c_sw_task_order[blockIdx.x - grp * SW_NTASK];
+    // block order: super-groups of columns, inside one the tile groups of the longest task first (see lw_column_kernel)
+    constexpr int SG = COL_SUPER_COLS / (32 * WARPS);
+    const int ngrp = ((w.nc + 31) / 32 + WARPS - 1) / WARPS;
+    const int sg = blockIdx.x / (SG * SW_NTASK);
+    const int gcount = min(SG, ngrp - sg * SG);
+    const int r = blockIdx.x - sg * (SG * SW_NTASK);
+    const int rank = r / gcount;
+    const int grp = sg * SG + (r - rank * gcount);
+    const int task = c_sw_task_order[rank];
     const int tile = grp * WARPS + wid;
     if (tile * 32 >= w.nc) return;
 #define SC_TASK(t) case t: sw_column_task<t>(T, in, w, tile, lane); break
