@@ -367,7 +367,9 @@ struct Tuning {
     int sw_fused;             // 1 (default): SW without clouds and aerosols runs the fused column kernel (sw_column.cu)
     int col_warps;            // block shape of the fused kernels: 0 = default (LW two 8-warp blocks per SM, SW one 16-warp block), 8 / 16 = forced
 };
-constexpr int COL_SUPER_COLS = 4096;   // columns per super-group of the column kernels' block order
+// columns per super-group of the column kernels' block order (T170L60 step in one pass / in 16384-column passes / T42L40:
+// 2048: 23.6 / 26.6 / 1.33 ms, 4096: 23.7 / 25.9 / 1.31, 8192: 24.2 / 26.2 / 1.26; task-fastest order as before: 23.7 / 28.6 / 1.45)
+constexpr int COL_SUPER_COLS = 4096;
 extern Tuning g_tune;
 
 // solver translation units (lw_solver.cu / sw_solver.cu, compiled with FMA contraction on; see build.py)

@@ -50,8 +50,9 @@ __host__ __device__ constexpr int sw_band_g0(int band)
 }
 // first scratch slot of a task inside a (tile, layer) row: three slots per g-point and one per task
 __host__ __device__ constexpr int sw_task_slot(int t) { return 3 * (sw_band_g0(sw_task(t).band) + sw_task(t).g0) + t; }
-// launch order of the tasks of a tile group: binary-species bands with six g-points first
-__constant__ unsigned char c_sw_task_order[SW_NTASK] = {1, 2, 9, 10, 21, 22, 0, 7, 12, 20, 3, 4, 5, 6, 14, 15, 8, 13, 16, 17, 18, 19, 11};
+// launch order of the tasks inside a super-group, longest first: reftra dominates, so tasks of six g-points come before those of
+// four, binary-species bands before single-species ones
+__constant__ unsigned char c_sw_task_order[SW_NTASK] = {1, 2, 9, 20, 0, 21, 22, 7, 12, 16, 17, 10, 3, 4, 5, 6, 14, 15, 8, 13, 18, 19, 11};
 
 // accumulator policy of sw_band_terms for a slice [G0, G0 + N) of a band: everything stays in registers
 template <int N>
