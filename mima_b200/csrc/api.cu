@@ -55,7 +55,7 @@ struct State {
     bool lw_ready = false;
     LwConst lwc;
     LwTables lwt{};
-    DevBuf lw_tab, lw_totplnk, lw_exptfn, lw_work, lw_cap, lw_err;
+    DevBuf lw_tab, lw_slices, lw_totplnk, lw_exptfn, lw_work, lw_cap, lw_err;
     bool lw_have_cld = false;
     LwWork lw_last{};
     int lw_last_ncol = 0;
@@ -63,7 +63,7 @@ struct State {
     bool sw_ready = false;
     SwConst swc;
     SwTables swt{};
-    DevBuf sw_tab, sw_exptbl, sw_work, sw_err;
+    DevBuf sw_tab, sw_slices, sw_exptbl, sw_work, sw_err;
     bool sw_have_cld = false;
     SwWork sw_last{};
     int sw_last_ncol = 0;
@@ -249,6 +249,33 @@ int append_const_row(std::vector<double> &tab, int base, int ng, const double *v
     return row0;
 }
 
+// The per-task slices of the band tables for the column kernels (ColSlices, rrtmg_dev.cuh): task t of band b gets the rows of
+// the band's table restricted to its g-points [g0, g0 + n), row stride slice_rs(b), as one contiguous 128-byte aligned piece.
+template <class Band>
+int build_slices(const std::vector<double> &tab, const Band *bands, int nband, ColTask (*task)(int), int (*slice_rs)(int),
+                 DevBuf &buf, ColSlices &out)
+{
+    std::vector<double> sl;
+    out.max_bytes = 0;
+    for (int t = 0; t < COL_NTASK; ++t) {
+        const ColTask k = task(t);
+        const Band &B = bands[k.band];
+        const size_t end = k.band + 1 < nband ? (size_t)bands[k.band + 1].base : tab.size();
+        const int rows = (int)((end - (size_t)B.base) / B.rs), srs = slice_rs(k.band);
+        while (sl.size() % 16) sl.push_back(0.0);
+        out.off[t] = (int)sl.size();
+        out.bytes[t] = rows * srs * 8;
+        if (out.bytes[t] > out.max_bytes) out.max_bytes = out.bytes[t];
+        for (int r = 0; r < rows; ++r)
+            for (int j = 0; j < srs; ++j)
+                sl.push_back(j < k.n && k.g0 + j < B.rs ? tab[(size_t)B.base + (size_t)r * B.rs + k.g0 + j] : 0.0);
+    }
+    if (buf.ensure(sl.size() * 8)) return -1;
+    if (cudaMemcpy(buf.p, sl.data(), sl.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    out.data = (const double *)buf.p;
+    return 0;
+}
+
 int copy_exact(const char *name, double *dst, long n)
 {
     const HostArr *a = find(name);
@@ -390,6 +417,8 @@ int lw_init_impl(double cpdair)
     G.lwt.totplnk = (const double *)G.lw_totplnk.p;
     G.lwt.totplnkderiv = (const double *)G.lw_totplnk.p + 181 * 16;
     G.lwt.exptfn = (const double *)G.lw_exptfn.p;
+    if (build_slices(tab, c.band, NBNDLW, lw_task, lw_slice_rs, G.lw_slices, G.lwt.sl))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc / copy failed for the LW table slices");
     if (lw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_lw) failed");
     {   // cloud absorption coefficients of cldprop (lwcldpr); optional: needed for inflglw > 0 only
         static LwCldConst k;
@@ -501,6 +530,8 @@ int sw_init_impl(double cpdair)
     CUDA_OK(cudaMemcpy(G.sw_exptbl.p, et.data(), et.size() * 8, cudaMemcpyHostToDevice));
     G.swt.tab = (const double *)G.sw_tab.p;
     G.swt.exptbl = (const double *)G.sw_exptbl.p;
+    if (build_slices(tab, c.band, NBNDSW, sw_task, sw_slice_rs, G.sw_slices, G.swt.sl))
+        return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc / copy failed for the SW table slices");
     if (sw_upload_const(c)) return fail(RRTMG_B200_ERR_CUDA, "cudaMemcpyToSymbol(c_sw) failed");
     {   // cloud optical properties of cldprop_sw (swcldpr); optional: needed for inflgsw = 2 only
         static SwCldConst k;
@@ -1247,7 +1278,7 @@ int rrtmg_b200_sw_init(double cpdair)
 int rrtmg_b200_finalize(void)
 {
     std::lock_guard<std::mutex> lk(G.mu);
-    for (DevBuf *b : {&G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.lw_err, &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_err})
+    for (DevBuf *b : {&G.lw_slices, &G.sw_slices, &G.lw_tab, &G.lw_totplnk, &G.lw_exptfn, &G.lw_work, &G.lw_cap, &G.lw_err, &G.sw_tab, &G.sw_exptbl, &G.sw_work, &G.sw_err})
         b->release();
     P_lw.release();
     P_sw.release();

@@ -22,30 +22,43 @@
 
 namespace rrtmg {
 
+// This unit's copy of the constant block carries the row stride of the task slices (col_slice_rs) instead of the stride of the
+// band tables in global memory: the band formulas of lw_bands.cuh form every row offset as row * B.rs.
 int lw_column_upload_const(const LwConst &c)
 {
-    return cudaMemcpyToSymbol(c_lw, &c, sizeof(LwConst)) == cudaSuccess ? 0 : -1;
+    static LwConst k;
+    k = c;
+    for (int b = 0; b < NBNDLW; ++b) k.band[b].rs = lw_slice_rs(b);
+    return cudaMemcpyToSymbol(c_lw, &k, sizeof(LwConst)) == cudaSuccess ? 0 : -1;
 }
 
-// ---- tasks: (band, first g-point inside the band, count).  Bands of more than eight g-points are cut in two so that the
-// taug / fracs / radiance registers of a task stay within the 128-register budget of four 128-thread blocks per SM.
-struct LwTask { int band, g0, n; };
-__host__ __device__ constexpr LwTask lw_task(int t)
-{
-    constexpr LwTask tk[LW_NTASK] = {
-        {0, 0, 6}, {0, 6, 4}, {1, 0, 6}, {1, 6, 6}, {2, 0, 8}, {2, 8, 8}, {3, 0, 8}, {3, 8, 6}, {4, 0, 8}, {4, 8, 8},
-        {5, 0, 8}, {6, 0, 6}, {6, 6, 6}, {7, 0, 8}, {8, 0, 6}, {8, 6, 6}, {9, 0, 6}, {10, 0, 8}, {11, 0, 8},
-        {12, 0, 4}, {13, 0, 2}, {14, 0, 2}, {15, 0, 2}};
-    return tk[t];
-}
 // launch order of the tasks of a tile group: the long ones (binary-species bands, eight g-points) first
 __constant__ unsigned char c_task_order[LW_NTASK] = {4, 5, 8, 9, 6, 7, 11, 12, 14, 15, 18, 19, 22, 21, 0, 13, 10, 17, 2, 3, 1, 16, 20};
 
-// accumulator policy of lw_band_terms for a slice [G0, G0 + N) of a band: taug and fracs stay in registers
+// 16 bytes of a table row from the block's shared-memory copy of the task slice (LDS.128 with an immediate offset)
+template <int IMM>
+__device__ __forceinline__ double2 lds2(uint32_t a)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int N, int J = 0, class F>
+__device__ __forceinline__ void row_pairs(uint32_t a, F f)
+{
+    if constexpr (J < N / 2) {
+        const double2 v = lds2<J * 16>(a);
+        f(2 * J, v.x);
+        f(2 * J + 1, v.y);
+        row_pairs<N, J + 1>(a, f);
+    }
+}
+// accumulator policy of lw_band_terms for the g-point slice of a task: taug and fracs stay in registers, the table rows come
+// from the task's slice in shared memory (row offsets `off` in doubles, stride col_slice_rs)
 template <int N>
 struct SliceAcc {
     double t[N], f[N];
-    const double *__restrict__ tab;  // band table shifted by G0: rows [row][rs]
+    uint32_t tab;                    // shared-memory address of the slice
     __device__ __forceinline__ void clear()
     {
 #pragma unroll
@@ -53,13 +66,7 @@ struct SliceAcc {
     }
     __device__ __forceinline__ void add(int off, double wgt)
     {
-        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
-#pragma unroll
-        for (int j = 0; j < N / 2; ++j) {
-            const double2 v = __ldg(q + j);
-            t[2 * j] = fma(wgt, v.x, t[2 * j]);
-            t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
-        }
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { t[g] = fma(wgt, v, t[g]); });
     }
     __device__ __forceinline__ void add_nz(int off, double wgt)
     {
@@ -67,33 +74,16 @@ struct SliceAcc {
     }
     __device__ __forceinline__ void scale(int off)
     {
-        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
-#pragma unroll
-        for (int j = 0; j < N / 2; ++j) {
-            const double2 v = __ldg(q + j);
-            t[2 * j] = t[2 * j] * v.x;
-            t[2 * j + 1] = t[2 * j + 1] * v.y;
-        }
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { t[g] = t[g] * v; });
     }
     __device__ __forceinline__ void frac1(int off)
     {
-        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
-#pragma unroll
-        for (int j = 0; j < N / 2; ++j) {
-            const double2 v = __ldg(q + j);
-            f[2 * j] = v.x; f[2 * j + 1] = v.y;
-        }
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { f[g] = v; });
     }
     __device__ __forceinline__ void frac2(int o0, double w0, int o1, double w1)
     {
-        const double2 *__restrict__ q0 = reinterpret_cast<const double2 *>(tab + o0);
-        const double2 *__restrict__ q1 = reinterpret_cast<const double2 *>(tab + o1);
-#pragma unroll
-        for (int j = 0; j < N / 2; ++j) {
-            const double2 a = __ldg(q0 + j), b = __ldg(q1 + j);
-            f[2 * j] = fma(w1, b.x, w0 * a.x);
-            f[2 * j + 1] = fma(w1, b.y, w0 * a.y);
-        }
+        row_pairs<N>(tab + o0 * 8, [&](int g, double v) { f[g] = w0 * v; });
+        row_pairs<N>(tab + o1 * 8, [&](int g, double v) { f[g] = fma(w1, v, f[g]); });
     }
     __device__ __forceinline__ void fzero()
     {
@@ -146,7 +136,8 @@ __device__ __forceinline__ double lw_planck(const double *__restrict__ tp, doubl
 }
 
 template <int BAND, int G0, int N, bool AER>
-__device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in, const LwWork &w, int task, int tile, int lane)
+__device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in, const LwWork &w, int task, int tile, int lane,
+                                               uint32_t slice)
 {
     const int nc = w.nc, nlay = w.nlay;
     const int col = tile * 32 + lane;
@@ -168,7 +159,7 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
     double *__restrict__ pup = pdn + (size_t)(nlay + 1) * ncp;
 
     SliceAcc<N> pw;
-    pw.tab = T.tab + B.base + G0;
+    pw.tab = slice;
     double rad[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) rad[k] = 0.0;
@@ -289,8 +280,12 @@ __global__ void __launch_bounds__(32 * WARPS, BLOCKS) lw_column_kernel(LwTables 
     const int grp = sg * SG + (r - rank * gcount);
     const int task = c_task_order[rank];
     const int tile = grp * WARPS + wid;
+    // the task's slice of the band table: one bulk copy (TMA) into shared memory per block
+    extern __shared__ __align__(128) unsigned char s_slice[];
+    __shared__ uint64_t s_bar;
+    const uint32_t slice = stage_to_shared(s_slice, &s_bar, T.sl.data + T.sl.off[task], (uint32_t)T.sl.bytes[task]);
     if (tile * 32 >= w.nc) return;
-#define LC_TASK(t) case t: lw_column_task<lw_task(t).band, lw_task(t).g0, lw_task(t).n, AER>(T, in, w, t, tile, lane); break
+#define LC_TASK(t) case t: lw_column_task<lw_task(t).band, lw_task(t).g0, lw_task(t).n, AER>(T, in, w, t, tile, lane, slice); break
     switch (task) {
         LC_TASK(0); LC_TASK(1); LC_TASK(2); LC_TASK(3); LC_TASK(4); LC_TASK(5); LC_TASK(6); LC_TASK(7);
         LC_TASK(8); LC_TASK(9); LC_TASK(10); LC_TASK(11); LC_TASK(12); LC_TASK(13); LC_TASK(14); LC_TASK(15);
@@ -346,14 +341,16 @@ static void lw_launch_column_geom(const LwTables &t, const LwIn &in, LwWork &w, 
 {
     const int ntile = (w.nc + 31) / 32;
     const unsigned grid = (unsigned)((ntile + WARPS - 1) / WARPS) * LW_NTASK;
-    lw_column_kernel<AER, WARPS, BLOCKS><<<grid, 32 * WARPS, 0, s>>>(t, in, w);
+    const size_t smem = (size_t)t.sl.max_bytes;
+    cudaFuncSetAttribute(lw_column_kernel<AER, WARPS, BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lw_column_kernel<AER, WARPS, BLOCKS><<<grid, 32 * WARPS, smem, s>>>(t, in, w);
 }
 
 // returns the number of launches
 int lw_launch_column(const LwTables &t, const LwIn &in, const LwOut &out, LwWork &w, cudaStream_t s)
 {
     const int ntile = (w.nc + 31) / 32;
-    const bool wide = g_tune.col_warps >= 16;
+    const bool wide = g_tune.col_warps != 8;
     if (in.tauaer) { if (wide) lw_launch_column_geom<true, 16, 1>(t, in, w, s); else lw_launch_column_geom<true, 8, 2>(t, in, w, s); }
     else { if (wide) lw_launch_column_geom<false, 16, 1>(t, in, w, s); else lw_launch_column_geom<false, 8, 2>(t, in, w, s); }
     const size_t smem = (size_t)2 * (w.nlay + 1) * 32 * sizeof(double);

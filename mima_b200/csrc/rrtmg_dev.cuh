@@ -55,6 +55,54 @@ enum LwSec {
     LS_COUNT
 };
 
+// ---- (band, g-point slice) tasks of the fused clear-sky column kernels (lw_column.cu, sw_column.cu) and the per-task copies of
+// the k-distribution tables they stage into shared memory.  A task = up to eight (LW) / six (SW) g-points of ONE band; bands of
+// more g-points are cut in two so that a task's registers fit the 128-register budget of 16 warps per SM.
+constexpr int COL_NTASK = 23;                    // both codes happen to have 23 tasks
+struct ColTask { int band, g0, n; };
+__host__ __device__ constexpr ColTask lw_task(int t)
+{
+    constexpr ColTask tk[COL_NTASK] = {
+        {0, 0, 6}, {0, 6, 4}, {1, 0, 6}, {1, 6, 6}, {2, 0, 8}, {2, 8, 8}, {3, 0, 8}, {3, 8, 6}, {4, 0, 8}, {4, 8, 8},
+        {5, 0, 8}, {6, 0, 6}, {6, 6, 6}, {7, 0, 8}, {8, 0, 6}, {8, 6, 6}, {9, 0, 6}, {10, 0, 8}, {11, 0, 8},
+        {12, 0, 4}, {13, 0, 2}, {14, 0, 2}, {15, 0, 2}};
+    return tk[t];
+}
+// SW tasks of at most four g-points (32 tasks) with 16, 20 or 24 warps per block measured within 3 % of this table
+// (profiles/r02aa_sweep.txt).
+__host__ __device__ constexpr ColTask sw_task(int t)
+{
+    constexpr ColTask tk[COL_NTASK] = {
+        {0, 0, 6}, {1, 0, 6}, {1, 6, 6}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 6}, {4, 6, 4}, {5, 0, 6}, {5, 6, 4},
+        {6, 0, 2}, {7, 0, 6}, {7, 6, 4}, {8, 0, 4}, {8, 4, 4}, {9, 0, 6}, {10, 0, 6}, {11, 0, 4}, {11, 4, 4}, {12, 0, 6},
+        {13, 0, 6}, {13, 6, 6}};
+    return tk[t];
+}
+// Row stride (in doubles) of a band's task slices: wide enough for the band's largest task and an ODD number of 16-byte units, so
+// that the distinct rows the lanes of a quarter-warp read with one LDS.128 fall into different bank groups unless they are a
+// multiple of eight rows apart (microbenchmark tools/micro/l1_rows.cu: two rows 144 B apart cost 2.2 clk, 128 B apart 4.1 clk).
+__host__ __device__ constexpr int col_slice_rs(int nmax) { return nmax > 6 ? 10 : (nmax > 2 ? 6 : 2); }
+__host__ __device__ constexpr int lw_slice_rs(int band)
+{
+    int n = 0;
+    for (int t = 0; t < COL_NTASK; ++t) if (lw_task(t).band == band && lw_task(t).n > n) n = lw_task(t).n;
+    return col_slice_rs(n);
+}
+__host__ __device__ constexpr int sw_slice_rs(int band)
+{
+    int n = 0;
+    for (int t = 0; t < COL_NTASK; ++t) if (sw_task(t).band == band && sw_task(t).n > n) n = sw_task(t).n;
+    return col_slice_rs(n);
+}
+// The slices: for task t the rows of its band's table restricted to the task's g-points, [row][slice_rs] (zero padded), one
+// contiguous piece of `data` per task -- what one bulk copy (TMA) brings into the shared memory of a block working on task t.
+struct ColSlices {
+    const double *data;
+    int off[COL_NTASK];       // first element of the task's slice (multiple of 16 doubles)
+    int bytes[COL_NTASK];     // size of the slice (multiple of 16 bytes)
+    int max_bytes;
+};
+
 struct LwBand {
     int ng;            // reduced g-points in the band
     int rs;            // row stride of the band table in doubles (ng rounded up to a power of two: a row never
@@ -80,6 +128,7 @@ struct LwTables {             // device pointers
     const double *totplnk;    // (181,16) column-major as in the Fortran
     const double *totplnkderiv;   // (181,16): d(totplnk)/dT for idrv = 1
     const double *exptfn;     // interleaved {exp_tbl[i], tfn_tbl[i]}, i = 0..NTBL
+    ColSlices sl;             // per-task table slices of the column kernel
 };
 
 struct LwIn {                 // interface arrays of the current pass (device pointers, may be offset)
@@ -110,7 +159,7 @@ struct LwOut {
 };
 
 constexpr int LF_SLOTS = LF_COUNT + 1;
-constexpr int LW_NTASK = 23;   // (band, g-point slice) tasks of the fused clear-sky kernel, lw_column.cu
+constexpr int LW_NTASK = COL_NTASK;
 
 struct LwWork {
     // cloudy sky (null otherwise): band optical depths out of cldprop [col][lay][16], ncbands (1, 5, 16) per column,
@@ -166,7 +215,7 @@ enum SwSec {
 };
 
 constexpr int SF_SLOTS = SF_COUNT + 1;
-constexpr int SW_NTASK = 23;                    // (band, g-point slice) tasks of the fused clear-sky kernel, sw_column.cu
+constexpr int SW_NTASK = COL_NTASK;
 constexpr int SW_NSLOT = 3 * NGPTSW + SW_NTASK;   // scratch slots per (tile, layer)
 
 struct SwBand {
@@ -187,6 +236,7 @@ struct SwConst {
 struct SwTables {
     const double *tab;
     const double *exptbl;     // interleaved {exp_tbl[i], 1/exp_tbl[i]}, i = 0..NTBL
+    ColSlices sl;             // per-task table slices of the column kernel
 };
 
 struct SwIn {
@@ -320,6 +370,56 @@ __device__ __forceinline__ double sqrt_fast(double a)
 // One 16-byte gather from the {exp, tfn} / {exp, 1/exp} look-up table of a solver (read-only path).  An L1 evict_last hint
 // on these loads (LDG.E.EL.128.CONSTANT) was measured: no change in either solver (profiles/r02_summary.md).
 __device__ __forceinline__ double2 ld_tbl(const double2 *__restrict__ p) { return __ldg(p); }
+
+// ---- mbarrier and 1-D bulk-copy (TMA) helpers: the staging ring of lw_rtrn_tma_kernel and the shared-memory look-up tables of
+// the column kernels
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Stage `bytes` (a multiple of 16) of global memory into the block's shared memory: thread 0 issues 1-D bulk copies (TMA) that
+// complete on one mbarrier, every thread waits for it.  Returns the shared-memory address of the copy, passed through an opaque
+// asm behind the wait so that no load from the copy (non-volatile ld.shared asm) can be scheduled in front of it.
+__device__ __forceinline__ uint32_t stage_to_shared(void *dst, uint64_t *bar, const void *src, uint32_t bytes)
+{
+    constexpr uint32_t CH = 32768;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, bytes);
+        for (uint32_t o = 0; o < bytes; o += CH)
+            tma_load_1d(static_cast<unsigned char *>(dst) + o, static_cast<const unsigned char *>(src) + o, min(CH, bytes - o), bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    uint32_t a = smem_u32(dst);
+    asm volatile("" : "+r"(a) :: "memory");
+    return a;
+}
 
 // Sum over g-points of R rows (R = 16 or 32) of per-thread values that the caller has stored in `tile` as
 // tile[row * S + g] (S odd, >= NACT).  Stage 1: thread t sums the strided elements of row (t % R) --

@@ -27,22 +27,16 @@
 
 namespace rrtmg {
 
+// This unit's copy of the constant block carries the row stride of the task slices (col_slice_rs) instead of the stride of the
+// band tables in global memory: the band formulas of sw_bands.cuh form every row offset as row * B.rs.
 int sw_column_upload_const(const SwConst &c)
 {
-    return cudaMemcpyToSymbol(c_sw, &c, sizeof(SwConst)) == cudaSuccess ? 0 : -1;
+    static SwConst k;
+    k = c;
+    for (int b = 0; b < NBNDSW; ++b) k.band[b].rs = sw_slice_rs(b);
+    return cudaMemcpyToSymbol(c_sw, &k, sizeof(SwConst)) == cudaSuccess ? 0 : -1;
 }
 
-// ---- tasks: (band, first g-point inside the band, count).  Tasks of at most four g-points (32 tasks) with 16, 20 or 24 warps per
-// block measured within 3 % of this table (profiles/r02aa_sweep.txt).
-struct SwTask { int band, g0, n; };
-__host__ __device__ constexpr SwTask sw_task(int t)
-{
-    constexpr SwTask tk[SW_NTASK] = {
-        {0, 0, 6}, {1, 0, 6}, {1, 6, 6}, {2, 0, 4}, {2, 4, 4}, {3, 0, 4}, {3, 4, 4}, {4, 0, 6}, {4, 6, 4}, {5, 0, 6}, {5, 6, 4},
-        {6, 0, 2}, {7, 0, 6}, {7, 6, 4}, {8, 0, 4}, {8, 4, 4}, {9, 0, 6}, {10, 0, 6}, {11, 0, 4}, {11, 4, 4}, {12, 0, 6},
-        {13, 0, 6}, {13, 6, 6}};
-    return tk[t];
-}
 __host__ __device__ constexpr int sw_band_g0(int band)
 {
     constexpr int g0[14] = {0, 6, 18, 26, 34, 44, 54, 56, 66, 74, 80, 86, 94, 100};
@@ -54,11 +48,30 @@ __host__ __device__ constexpr int sw_task_slot(int t) { return 3 * (sw_band_g0(s
 // four, binary-species bands before single-species ones
 __constant__ unsigned char c_sw_task_order[SW_NTASK] = {1, 2, 9, 20, 0, 21, 22, 7, 12, 16, 17, 10, 3, 4, 5, 6, 14, 15, 8, 13, 18, 19, 11};
 
-// accumulator policy of sw_band_terms for a slice [G0, G0 + N) of a band: everything stays in registers
+// 16 bytes of a table row from the block's shared-memory copy of the task slice (LDS.128 with an immediate offset)
+template <int IMM>
+__device__ __forceinline__ double2 lds2(uint32_t a)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int N, int J = 0, class F>
+__device__ __forceinline__ void row_pairs(uint32_t a, F f)
+{
+    if constexpr (J < N / 2) {
+        const double2 v = lds2<J * 16>(a);
+        f(2 * J, v.x);
+        f(2 * J + 1, v.y);
+        row_pairs<N, J + 1>(a, f);
+    }
+}
+// accumulator policy of sw_band_terms for the g-point slice of a task: everything stays in registers, the table rows come from
+// the task's slice in shared memory (row offsets `off` in doubles, stride col_slice_rs)
 template <int N>
 struct SwSliceAcc {
     double t[N], r[N], sf[N];        // taug; taur of band 24; solar source
-    const double *__restrict__ tab;  // band table shifted by G0
+    uint32_t tab;                    // shared-memory address of the slice
     __device__ __forceinline__ void clear()
     {
 #pragma unroll
@@ -66,13 +79,7 @@ struct SwSliceAcc {
     }
     __device__ __forceinline__ void add(int off, double wgt)
     {
-        const double2 *__restrict__ q = reinterpret_cast<const double2 *>(tab + off);
-#pragma unroll
-        for (int j = 0; j < N / 2; ++j) {
-            const double2 v = __ldg(q + j);
-            t[2 * j] = fma(wgt, v.x, t[2 * j]);
-            t[2 * j + 1] = fma(wgt, v.y, t[2 * j + 1]);
-        }
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { t[g] = fma(wgt, v, t[g]); });
     }
     __device__ __forceinline__ void addc(double c)
     {
@@ -81,23 +88,21 @@ struct SwSliceAcc {
     }
     __device__ __forceinline__ void rayl1(int off, double wgt)
     {
-#pragma unroll
-        for (int g = 0; g < N; ++g) r[g] = wgt * __ldg(tab + off + g);
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { r[g] = wgt * v; });
     }
     __device__ __forceinline__ void rayl2(int o0, double w0, int o1, double w1)
     {
-#pragma unroll
-        for (int g = 0; g < N; ++g) r[g] = fma(w1, __ldg(tab + o1 + g), w0 * __ldg(tab + o0 + g));
+        row_pairs<N>(tab + o0 * 8, [&](int g, double v) { r[g] = w0 * v; });
+        row_pairs<N>(tab + o1 * 8, [&](int g, double v) { r[g] = fma(w1, v, r[g]); });
     }
     __device__ __forceinline__ void sflux1(int off, double wgt)
     {
-#pragma unroll
-        for (int g = 0; g < N; ++g) sf[g] = wgt * __ldg(tab + off + g);
+        row_pairs<N>(tab + off * 8, [&](int g, double v) { sf[g] = wgt * v; });
     }
     __device__ __forceinline__ void sflux2(int o0, double w0, int o1, double w1)
     {
-#pragma unroll
-        for (int g = 0; g < N; ++g) sf[g] = fma(w1, __ldg(tab + o1 + g), w0 * __ldg(tab + o0 + g));
+        row_pairs<N>(tab + o0 * 8, [&](int g, double v) { sf[g] = w0 * v; });
+        row_pairs<N>(tab + o1 * 8, [&](int g, double v) { sf[g] = fma(w1, v, sf[g]); });
     }
 };
 
@@ -127,7 +132,7 @@ __device__ __forceinline__ void st_stream(double *p, double v)
 __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int TASK>
-__device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in, const SwWork &w, int tile, int lane)
+__device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in, const SwWork &w, int tile, int lane, uint32_t slice)
 {
     constexpr int BAND = sw_task(TASK).band, G0 = sw_task(TASK).g0, N = sw_task(TASK).n;
     constexpr int SLOT = sw_task_slot(TASK);
@@ -153,7 +158,7 @@ __device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in
     double *__restrict__ pdn = pup + (size_t)(klev + 1) * ncp;
 
     SwSliceAcc<N> pw;
-    pw.tab = T.tab + B.base + G0;
+    pw.tab = slice;
     SwPair p;
     // ---- the solar source: the band formula at the layer the reference leaves sfluxzen from (0 = never written)
     double zinc[N];
@@ -171,8 +176,12 @@ __device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in
     }
     // Rayleigh: taur(g) = colmol * rayl(g) with one table row per band, except band 24 (pw.r)
     double raylg[N];
+    if (BAND == 8) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) raylg[k] = BAND == 8 ? 1.0 : __ldg(T.tab + B.base + B.sec[SS_RAYL] * B.rs + G0 + k);
+        for (int k = 0; k < N; ++k) raylg[k] = 1.0;
+    } else {
+        row_pairs<N>(slice + B.sec[SS_RAYL] * B.rs * 8, [&](int g, double v) { raylg[g] = v; });
+    }
 
     // ---- pass 1, top -> surface: reftra + vrtqdr's top-down recurrence
     double tdn[N], rdnd[N], tdbt[N];
@@ -268,8 +277,12 @@ __global__ void __launch_bounds__(32 * WARPS, BLOCKS) sw_column_kernel(SwTables 
     const int grp = sg * SG + (r - rank * gcount);
     const int task = c_sw_task_order[rank];
     const int tile = grp * WARPS + wid;
+    // the task's slice of the band table: one bulk copy (TMA) into shared memory per block
+    extern __shared__ __align__(128) unsigned char s_slice[];
+    __shared__ uint64_t s_bar;
+    const uint32_t slice = stage_to_shared(s_slice, &s_bar, T.sl.data + T.sl.off[task], (uint32_t)T.sl.bytes[task]);
     if (tile * 32 >= w.nc) return;
-#define SC_TASK(t) case t: sw_column_task<t>(T, in, w, tile, lane); break
+#define SC_TASK(t) case t: sw_column_task<t>(T, in, w, tile, lane, slice); break
     switch (task) {
         SC_TASK(0); SC_TASK(1); SC_TASK(2); SC_TASK(3); SC_TASK(4); SC_TASK(5); SC_TASK(6); SC_TASK(7);
         SC_TASK(8); SC_TASK(9); SC_TASK(10); SC_TASK(11); SC_TASK(12); SC_TASK(13); SC_TASK(14); SC_TASK(15);
@@ -327,7 +340,9 @@ static void sw_launch_column_geom(const SwTables &t, const SwIn &in, SwWork &w, 
 {
     const int ntile = (w.nc + 31) / 32;
     const unsigned grid = (unsigned)((ntile + WARPS - 1) / WARPS) * SW_NTASK;
-    sw_column_kernel<WARPS, BLOCKS><<<grid, 32 * WARPS, 0, s>>>(t, in, w);
+    const size_t smem = (size_t)t.sl.max_bytes;
+    cudaFuncSetAttribute(sw_column_kernel<WARPS, BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sw_column_kernel<WARPS, BLOCKS><<<grid, 32 * WARPS, smem, s>>>(t, in, w);
 }
 
 // returns the number of launches
