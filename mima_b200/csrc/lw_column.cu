@@ -4,10 +4,17 @@
 // the Planck sources of LW/src/rrtmg_lw_setcoef.f90:154-249, and the clear branches of LW/src/rrtmg_lw_rtrnmr.f90:481-777
 // (identical in rtrnmc.f90:407-432, 481-503); taut = taug + tauaer (rad.nomcica:514-519, iaer = 10 forced).
 //
-// How: lanes = 32 adjacent columns, a warp = (32-column tile, task), a task = up to eight g-points of one band.  The thread
-// walks its column from the top layer down: it reads the cell's setcoef state (written once per cell by lw_prep_cell, read
-// back by the 23 tasks of the tile while it is still in L2), evaluates the band formula for its g-points into registers,
-// interpolates the three Planck values of the layer, and feeds the N downward recurrences at once -- the optical depths
+// How: lanes = 32 adjacent columns, a warp = (32-column tile, task), a task = up to eight g-points of one band, a block = 16
+// tiles on ONE task.  The block first stages the task's slice of its band's k-distribution table -- every row of the band table
+// restricted to the task's g-points, at most 164 KB -- into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier,
+// stage_to_shared); the slices are laid out at init (ColSlices, api.cu) with a row stride of an odd number of 16-byte units, so
+// the two to four distinct rows that the 32 columns of a warp read with one LDS.128 fall into different banks.  Per-lane reads
+// of warp-uniform or nearly uniform table rows cost the L1 data pipe one pass per quarter-warp AND distinct row
+// (tools/micro/l1_rows.cu: 4.1 clk per row from L1, 2.2 clk from shared memory); with the rows read through L1 that pipe was
+// the kernel's bound (75 % busy; rows made loop-invariant: -1.9 ms, profiles/r02_summary.md experiment 6).
+// The thread then walks its column from the top layer down: it reads the cell's setcoef state (written once per cell by
+// lw_prep_cell, read back by the 23 tasks of the tile while it is still in L2), evaluates the band formula for its g-points into
+// registers, interpolates the three Planck values of the layer, and feeds the N downward recurrences at once -- the optical depths
 // never leave the registers, and the N independent chains hide the latency of the one-level-at-a-time recurrence.  What the
 // upward sweep needs again, the layer's absorptivity and upward source per g-point, goes to a scratch field as one 16-byte
 // store per lane (512 contiguous bytes per warp); the upward sweep streams it back.  So the staging traffic is one write
@@ -258,10 +265,11 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
     }
 }
 
-// Few resident blocks per SM, all warps of a block on the same task: the loop body of a task is 10-20 KB of straight-line code
-// and the instruction cache behind the 6 KB L0 holds 32 KB -- with four 4-warp blocks of different tasks per SM the kernel
-// spent 22 of 23 issue slots waiting for instructions (profiles/r02_summary.md, experiment 5).  Two 8-warp blocks per SM
-// measured best at every batch size (T170L60: 10.4 ms against 11.1 ms with one 16-warp block; option "col_warps").
+// One 16-warp block per SM, all of its warps on the same task: the loop body of a task is 10-20 KB of straight-line code and the
+// instruction cache behind the 6 KB L0 holds 32 KB -- with four 4-warp blocks of different tasks per SM the kernel spent 22 of 23
+// issue slots waiting for instructions (profiles/r02_summary.md, experiment 5) -- and the task's table slice is staged once per
+// block.  The dynamic shared memory of a launch is the largest slice (a launch has one size), which leaves room for one block per
+// SM; option "col_warps" = 8 runs 8-warp blocks (a test knob: half the warps per SM).
 template <bool AER, int WARPS, int BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS) lw_column_kernel(LwTables T, LwIn in, LwWork w)
 {

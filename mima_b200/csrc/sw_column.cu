@@ -8,7 +8,8 @@
 // u_above = zp * u_below + zq and the diffuse downward flux as rdnd * u.
 //
 // How: as lw_column.cu.  Lanes = 32 adjacent columns, a warp = (32-column tile, task), a task = up to six g-points of one
-// band.  The thread first evaluates the band formula at the layer that selects the solar source (laysolfr, sw_prep), then
+// band, a block = 16 tiles on one task; the block stages the task's slice of the band table into shared memory with one TMA
+// bulk copy and reads its rows with LDS.128 (see lw_column.cu).  The thread first evaluates the band formula at the layer that selects the solar source (laysolfr, sw_prep), then
 // walks its column from the top layer down: setcoef state of the cell (tile-major fields written by sw_prep_cell), band
 // formula into registers, reftra and the downward recurrences for its g-points -- the optical depths never leave the
 // registers, neighbouring columns take the same branch of reftra far more often than neighbouring g-points do, and the
@@ -261,8 +262,8 @@ __device__ __forceinline__ void sw_column_task(const SwTables &T, const SwIn &in
     }
 }
 
-// One 16-warp block per SM, all of its warps on the same task (instruction cache: see lw_column.cu).  A task body with its six
-// inlined reftra instances is about 25 KB: two 8-warp blocks of different tasks per SM measured 21 ms against 12.9 ms.
+// One 16-warp block per SM, all of its warps on the same task (instruction cache and table slice: see lw_column.cu).  A task
+// body with its six inlined reftra instances is about 25 KB.
 template <int WARPS, int BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS) sw_column_kernel(SwTables T, SwIn in, SwWork w)
 {

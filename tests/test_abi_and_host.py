@@ -28,6 +28,31 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/rrtmg_b200.h but not exported"
 
 
+def test_column_kernels_stage_their_tables_by_tma():
+    """The clear-sky column kernels read the k-distribution rows from a shared-memory copy brought in by TMA bulk copies:
+    their SASS must hold the bulk copy (UBLKCP), its mbarrier wait and 128-bit shared loads, and no 128-bit global
+    table load except the exp-table gather."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as ge
+    ge.build()
+    from mima_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    for unit in ("lw_column", "sw_column"):
+        obj = os.path.join(build.LIBDIR, "obj", unit + ".o")
+        if not os.path.exists(obj):
+            pytest.skip("object files not kept next to the library")
+        sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
+        kern = sass.split("Function : ")
+        col = [k for k in kern if "column_kernel" in k.split("\n", 1)[0]]
+        assert col, unit
+        for k in col:
+            assert "UBLKCP" in k and "SYNCS.PHASECHK" in k, "no TMA bulk copy / mbarrier wait in " + k.split("\n", 1)[0]
+            assert k.count("LDS.128") > 100, "table rows are not read from shared memory in " + k.split("\n", 1)[0]
+
+
 def _has_gpu():
     try:
         import torch

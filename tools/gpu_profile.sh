@@ -15,7 +15,14 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lw_
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lw_|sw_" -s $((SKIP + NPASS * 4)) -c 4 -f -o gpurun_out/prof_${W}_lw \
     python bench.py --steps 1 --warmup 2 --workload $W --no-cpu >> gpurun_out/ncu_full_${W}.log 2>&1
 tail -2 gpurun_out/ncu_full_${W}.log
-for x in sw lw; do ncu -i gpurun_out/prof_${W}_$x.ncu-rep --page raw --csv > gpurun_out/prof_${W}_${x}_raw.csv 2>/dev/null; done
+# the reports themselves (2 x ~40 MB with the source pages of the column kernels) exceed the 64 MiB copy-back limit: export the raw
+# pages and the per-instruction source page of the column kernel here, keep only those
+for x in sw lw; do
+  ncu -i gpurun_out/prof_${W}_$x.ncu-rep --page raw --csv > gpurun_out/prof_${W}_${x}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_${W}_$x.ncu-rep --page source --csv -k regex:"${x}_column" > gpurun_out/prof_${W}_${x}col_source.csv 2>/dev/null
+  gzip -f gpurun_out/prof_${W}_${x}col_source.csv
+  rm -f gpurun_out/prof_${W}_$x.ncu-rep
+done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"lw_|sw_" -s $SKIP -c $((2 * STEP)) --csv --log-file gpurun_out/launches_${W}.csv \
     python bench.py --steps 2 --warmup 2 --workload $W --no-cpu > gpurun_out/ncu_list_${W}.log 2>&1
 ls -la gpurun_out/ | tail -8

@@ -3,6 +3,11 @@
 usage: ncu_src_top.py source.csv [N]"""
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
+# an export can hold several views (or kernels) one after the other: keep the first
+for i in range(2, len(rows)):
+    if rows[i] and rows[i][0] == "Kernel Name":
+        rows = rows[:i]
+        break
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
