@@ -16,10 +16,13 @@
 // lw_prep_cell, read back by the 23 tasks of the tile while it is still in L2), evaluates the band formula for its g-points into
 // registers, interpolates the three Planck values of the layer, and feeds the N downward recurrences at once -- the optical depths
 // never leave the registers, and the N independent chains hide the latency of the one-level-at-a-time recurrence.  What the
-// upward sweep needs again, the layer's absorptivity and upward source per g-point, goes to a scratch field as one 16-byte
-// store per lane (512 contiguous bytes per warp); the upward sweep streams it back.  So the staging traffic is one write
-// and one read of 16 bytes per (cell, g-point), every access a whole number of 128-byte lines, where the staged pipeline
-// (lw_taumol -> [col][lay][g] -> lw_rtrn) wrote the same volume in scattered 16-128 byte pieces and read it twice.  Each
+// upward sweep needs again goes to a scratch field in whole 512-byte rows per warp: the layer's optical depths (8 bytes per
+// g-point, two per 16-byte store) and, per task, how the layer's Planck fractions were formed (a weight and two row offsets);
+// the upward sweep streams that back and forms absorptivity, fractions and upward source again with the operations of the
+// downward sweep -- bitwise the same values -- instead of reading {absorptivity, source} pairs of 16 bytes per g-point.  So the
+// staging traffic is one write and one read of 8 bytes per (cell, g-point) plus 16 per (cell, task), every access a whole
+// number of 128-byte lines, where the staged pipeline (lw_taumol -> [col][lay][g] -> lw_rtrn) wrote 16 bytes per (cell,
+// g-point) in scattered 16-128 byte pieces and read them twice.  Each
 // warp leaves its g-sums per level in a partial field [task][level][column]; lw_finish adds the 23 partials of a level in
 // task order (fixed summation order: results are reproducible bit for bit) and writes fluxes and heating rates.
 //
@@ -66,6 +69,10 @@ template <int N>
 struct SliceAcc {
     double t[N], f[N];
     uint32_t tab;                    // shared-memory address of the slice
+    // how the Planck fractions of the layer were formed, for the upward sweep to form them again: none (0), one row (1),
+    // (1 - fw1) * row(fo0) + fw1 * row(fo1) (2)
+    int fkind, fo0, fo1;
+    double fw1;
     __device__ __forceinline__ void clear()
     {
 #pragma unroll
@@ -85,17 +92,35 @@ struct SliceAcc {
     }
     __device__ __forceinline__ void frac1(int off)
     {
+        fkind = 1; fo0 = off; fo1 = 0; fw1 = 0.0;
         row_pairs<N>(tab + off * 8, [&](int g, double v) { f[g] = v; });
     }
+    // every caller passes w0 = 1 - w1 (frac_eta in lw_bands.cuh): the upward sweep forms it the same way
     __device__ __forceinline__ void frac2(int o0, double w0, int o1, double w1)
     {
+        fkind = 2; fo0 = o0; fo1 = o1; fw1 = w1;
         row_pairs<N>(tab + o0 * 8, [&](int g, double v) { f[g] = w0 * v; });
         row_pairs<N>(tab + o1 * 8, [&](int g, double v) { f[g] = fma(w1, v, f[g]); });
     }
     __device__ __forceinline__ void fzero()
     {
+        fkind = 0; fo0 = 0; fo1 = 0; fw1 = 0.0;
 #pragma unroll
         for (int g = 0; g < N; ++g) f[g] = 0.0;
+    }
+    // the fractions again from what frac1 / frac2 / fzero recorded (bitwise the same values)
+    __device__ __forceinline__ void refrac(int kind, int o0, int o1, double w1)
+    {
+        if (kind == 2) {
+            const double w0 = 1. - w1;
+            row_pairs<N>(tab + o0 * 8, [&](int g, double v) { f[g] = w0 * v; });
+            row_pairs<N>(tab + o1 * 8, [&](int g, double v) { f[g] = fma(w1, v, f[g]); });
+        } else if (kind == 1) {
+            row_pairs<N>(tab + o0 * 8, [&](int g, double v) { f[g] = v; });
+        } else {
+#pragma unroll
+            for (int g = 0; g < N; ++g) f[g] = 0.0;
+        }
     }
 };
 
@@ -131,6 +156,27 @@ __device__ __forceinline__ void st_scratch(double2 *p, double a, double b)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+__device__ __forceinline__ double ld_part(const double *p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// absorptivity and the Pade "tau function" of one (cell, g-point) from its optical depth (rtrnmr.f90:536-560): series below 0.06,
+// the reference's look-up table above; called by both sweeps, so that the upward one reproduces the downward one's values
+__device__ __forceinline__ void lw_trans(const double2 *__restrict__ et, double bpade, double odepth, double &at, double &tf)
+{
+    if (odepth <= 0.06) {
+        at = odepth - 0.5 * odepth * odepth;
+        tf = 0.166667 * odepth;
+    } else {
+        const double tblind = odepth * rcp_fast(bpade + odepth);
+        const int itr = (int)(10000.0 * tblind + 0.5);
+        const double2 e = ld_tbl(et + itr);
+        at = 1. - e.x;
+        tf = e.y;
+    }
+}
 // integrated Planck function of one band at temperature t (setcoef.f90:154-249: linear in the 1 K table)
 __device__ __forceinline__ double lw_planck(const double *__restrict__ tp, double t)
 {
@@ -161,7 +207,10 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
     const double2 *__restrict__ et = reinterpret_cast<const double2 *>(T.exptfn);
     const double *__restrict__ tp = T.totplnk + BAND * 181;
     const double *taer = AER ? in.tauaer + cc + (size_t)BAND * nlay * ld : nullptr;
-    double2 *__restrict__ sc = reinterpret_cast<double2 *>(w.colst) + ((size_t)tile * nlay * NGPTLW + gfirst) * 32 + lane;
+    // scratch: per (tile, layer) LW_CSLOT 16-byte slots of 32 lanes; a task owns N / 2 slots of optical-depth pairs and one slot
+    // {weight, packed row offsets} that says how the layer's Planck fractions were formed
+    constexpr int NP = N / 2;
+    double2 *__restrict__ sc = reinterpret_cast<double2 *>(w.colst) + ((size_t)tile * nlay * LW_CSLOT + (gfirst >> 1) + task) * 32 + lane;
     double *__restrict__ pdn = w.part + ((size_t)task * 2 * (nlay + 1)) * ncp + col;
     double *__restrict__ pup = pdn + (size_t)(nlay + 1) * ncp;
 
@@ -191,8 +240,8 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
         plev_up = plev_dn;
         double ta = 0.0;
         if (AER) ta = taer[(size_t)lay * ld];
-        double2 *__restrict__ s = sc + (size_t)lay * (NGPTLW * 32);
-        double sum = 0.0;
+        double2 *__restrict__ s = sc + (size_t)lay * (LW_CSLOT * 32);
+        double sum = 0.0, od0 = 0.0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double tg = pw.t[k];
@@ -201,23 +250,17 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
             double odepth = secd * tg;
             if (odepth < 0.0) odepth = 0.0;
             double at, tf;
-            if (odepth <= 0.06) {
-                at = odepth - 0.5 * odepth * odepth;
-                tf = 0.166667 * odepth;
-            } else {
-                const double tblind = odepth * rcp_fast(bpade + odepth);
-                const int itr = (int)(10000.0 * tblind + 0.5);
-                const double2 e = ld_tbl(et + itr);
-                at = 1. - e.x;
-                tf = e.y;
-            }
+            lw_trans(et, bpade, odepth, at, tf);
             const double bbd = plfrac * fma(tf, dplankdn, blay);
-            const double bbu = plfrac * fma(tf, dplankup, blay);
             rad[k] = fma(bbd - rad[k], at, rad[k]);
             sum = fma(rad[k], wgt, sum);
-            if (valid) st_scratch(s + k * 32, at, bbu);
+            if (k & 1) { if (valid) st_scratch(s + (k >> 1) * 32, od0, odepth); }
+            else od0 = odepth;
         }
-        if (valid) pdn[(size_t)lay * ncp] = sum;
+        if (valid) {
+            st_scratch(s + NP * 32, pw.fw1, __hiloint2double(pw.fo1 | (pw.fkind << 28), pw.fo0));
+            pdn[(size_t)lay * ncp] = sum;
+        }
     }
     // surface (:628-636): after the last iteration pw.f holds the Planck fractions of layer 1
     {
@@ -232,35 +275,52 @@ __device__ __forceinline__ void lw_column_task(const LwTables &T, const LwIn &in
         }
         if (valid) pup[0] = sum;
     }
-    // upward sweep (:649-711): absorptivity and upward source come back from the scratch field, one layer ahead in registers
-    // and LC_AHEAD layers ahead on their way into L2
+    // upward sweep (:649-711): the optical depths and the fraction recipe come back from the scratch field, one layer ahead in
+    // registers and LC_AHEAD layers ahead on their way into L2; absorptivity, Planck fractions and the upward source are formed
+    // again by the operations of the downward sweep (bitwise the same values).  Half the scratch bytes of storing {absorptivity,
+    // source} per g-point, for arithmetic the kernel has room for
     {
-        constexpr int LC_AHEAD = 4;
-        double2 v[N];
+        constexpr int LC_AHEAD = 4, NS = NP + 1;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        const double *__restrict__ tlp = in.tlay + cc, *__restrict__ tvp = in.tlev + cc + ld;   // layer 1, its upper interface
+        double2 v[NS];
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = valid ? ld_scratch(sc + k * 32) : make_double2(0.0, 0.0);
+        for (int j = 0; j < NS; ++j) v[j] = valid ? ld_scratch(sc + j * 32) : zero2;
+        double tl = *tlp, tv = *tvp;
 #pragma unroll 2
         for (int lay = 0; lay < nlay; ++lay) {
-            double2 nx[N];
+            double2 nx[NS];
+            double tln = 0.0, tvn = 0.0;
             if (lay + 1 < nlay) {
-                const double2 *__restrict__ s = sc + (size_t)(lay + 1) * (NGPTLW * 32);
+                const double2 *__restrict__ s = sc + (size_t)(lay + 1) * (LW_CSLOT * 32);
 #pragma unroll
-                for (int k = 0; k < N; ++k) nx[k] = valid ? ld_scratch(s + k * 32) : make_double2(0.0, 0.0);
+                for (int j = 0; j < NS; ++j) nx[j] = valid ? ld_scratch(s + j * 32) : zero2;
+                tlp += ld; tvp += ld;
+                tln = *tlp; tvn = *tvp;
             }
             if (lay + LC_AHEAD < nlay) {
-                const double2 *__restrict__ s = sc + (size_t)(lay + LC_AHEAD) * (NGPTLW * 32);
+                const double2 *__restrict__ s = sc + (size_t)(lay + LC_AHEAD) * (LW_CSLOT * 32);
 #pragma unroll
-                for (int k = 0; k < N; ++k) pf_l2(s + k * 32);
+                for (int j = 0; j < NS; ++j) pf_l2(s + j * 32);
             }
+            const double blay = lw_planck(tp, tl);
+            const double dplankup = lw_planck(tp, tv) - blay;
+            const int hi = __double2hiint(v[NP].y), lo = __double2loint(v[NP].y);
+            pw.refrac(valid ? (hi >> 28) : 0, lo, hi & 0x0fffffff, v[NP].x);
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                rad[k] = fma(v[k].y - rad[k], v[k].x, rad[k]);
+                const double odepth = (k & 1) ? v[k >> 1].y : v[k >> 1].x;
+                double at, tf;
+                lw_trans(et, bpade, odepth, at, tf);
+                const double bbu = pw.f[k] * fma(tf, dplankup, blay);
+                rad[k] = fma(bbu - rad[k], at, rad[k]);
                 sum = fma(rad[k], wgt, sum);
             }
             if (valid) pup[(size_t)(lay + 1) * ncp] = sum;
 #pragma unroll
-            for (int k = 0; k < N; ++k) v[k] = nx[k];
+            for (int j = 0; j < NS; ++j) v[j] = nx[j];
+            tl = tln; tv = tvn;
         }
     }
 }
@@ -317,12 +377,15 @@ __global__ void __launch_bounds__(32 * LF_ROWS) lw_finish_kernel(LwIn in, LwOut 
     for (int lev = row; lev < nlev; lev += LF_ROWS) {
         double d = 0.0, u = 0.0;
         if (valid) {
+            // the 46 loads into registers first, then the sums in task order: with the load and the addition of a task in one statement
+            // the loads went out one DRAM round trip after the other
             const double *pd = w.part + (size_t)lev * ncp + col;
+            const size_t plane = (size_t)nlev * ncp;
+            double vd[LW_NTASK], vu[LW_NTASK];
 #pragma unroll
-            for (int t = 0; t < LW_NTASK; ++t) {
-                d += pd[(size_t)t * 2 * nlev * ncp];
-                u += pd[((size_t)t * 2 + 1) * nlev * ncp];
-            }
+            for (int t = 0; t < LW_NTASK; ++t) { vd[t] = ld_part(pd + (size_t)(2 * t) * plane); vu[t] = ld_part(pd + (size_t)(2 * t + 1) * plane); }
+#pragma unroll
+            for (int t = 0; t < LW_NTASK; ++t) { d += vd[t]; u += vu[t]; }
         }
         s_dn[lev * 32 + lane] = d * c_lw.fluxfac;
         s_up[lev * 32 + lane] = u * c_lw.fluxfac;

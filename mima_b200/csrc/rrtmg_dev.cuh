@@ -160,6 +160,7 @@ struct LwOut {
 
 constexpr int LF_SLOTS = LF_COUNT + 1;
 constexpr int LW_NTASK = COL_NTASK;
+constexpr int LW_CSLOT = NGPTLW / 2 + LW_NTASK;   // 16-byte scratch slots per (tile, layer) of lw_column: g-point pairs + one per task
 
 struct LwWork {
     // cloudy sky (null otherwise): band optical depths out of cldprop [col][lay][16], ncbands (1, 5, 16) per column,
@@ -181,7 +182,8 @@ struct LwWork {
     double *plankbnd;         // [col][16]
     double *taug, *fracs;     // [col][lay][140]
     // fused clear-sky path (lw_column.cu): ncp = nc rounded up to whole 32-column tiles; colst = the storage of taug and
-    // fracs seen as one field of {absorptivity, upward source} pairs [tile][lay][140][32 lanes]; part = the g-sums of every
+    // fracs seen as the scratch field between the two sweeps, [tile][lay][LW_CSLOT][32 lanes] of 16 bytes (per task its optical
+    // depths in pairs and one {weight, row offsets} slot for the Planck fractions); part = the g-sums of every
     // task per level, [task][down, up][lay+1][ncp]
     int fused = 0, ncp = 0;
     double *colst = nullptr, *part = nullptr;
