@@ -156,12 +156,6 @@ __device__ __forceinline__ void st_scratch(double2 *p, double a, double b)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
-__device__ __forceinline__ double ld_part(const double *p)
-{
-    double v;
-    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
 // absorptivity and the Pade "tau function" of one (cell, g-point) from its optical depth (rtrnmr.f90:536-560): series below 0.06,
 // the reference's look-up table above; called by both sweeps, so that the upward one reproduces the downward one's values
 __device__ __forceinline__ void lw_trans(const double2 *__restrict__ et, double bpade, double odepth, double &at, double &tf)
@@ -377,15 +371,12 @@ __global__ void __launch_bounds__(32 * LF_ROWS) lw_finish_kernel(LwIn in, LwOut 
     for (int lev = row; lev < nlev; lev += LF_ROWS) {
         double d = 0.0, u = 0.0;
         if (valid) {
-            // the 46 loads into registers first, then the sums in task order: with the load and the addition of a task in one statement
-            // the loads went out one DRAM round trip after the other
             const double *pd = w.part + (size_t)lev * ncp + col;
-            const size_t plane = (size_t)nlev * ncp;
-            double vd[LW_NTASK], vu[LW_NTASK];
 #pragma unroll
-            for (int t = 0; t < LW_NTASK; ++t) { vd[t] = ld_part(pd + (size_t)(2 * t) * plane); vu[t] = ld_part(pd + (size_t)(2 * t + 1) * plane); }
-#pragma unroll
-            for (int t = 0; t < LW_NTASK; ++t) { d += vd[t]; u += vu[t]; }
+            for (int t = 0; t < LW_NTASK; ++t) {
+                d += pd[(size_t)t * 2 * nlev * ncp];
+                u += pd[((size_t)t * 2 + 1) * nlev * ncp];
+            }
         }
         s_dn[lev * 32 + lane] = d * c_lw.fluxfac;
         s_up[lev * 32 + lane] = u * c_lw.fluxfac;

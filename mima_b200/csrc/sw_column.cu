@@ -308,15 +308,12 @@ __global__ void __launch_bounds__(32 * SF_ROWS) sw_cfinish_kernel(SwIn in, SwOut
     for (int lev = row; lev < nlev; lev += SF_ROWS) {
         double d = 0.0, u = 0.0;
         if (active) {
-            // the 46 loads into registers first, then the sums in task order: with the load and the addition of a task in one statement
-            // the loads went out one DRAM round trip after the other
             const double *pu = w.cpart + (size_t)lev * ncp + col;
-            const size_t plane = (size_t)nlev * ncp;
-            double vu[SW_NTASK], vd[SW_NTASK];
 #pragma unroll
-            for (int t = 0; t < SW_NTASK; ++t) { vu[t] = ld_stream(pu + (size_t)(2 * t) * plane); vd[t] = ld_stream(pu + (size_t)(2 * t + 1) * plane); }
-#pragma unroll
-            for (int t = 0; t < SW_NTASK; ++t) { u += vu[t]; d += vd[t]; }
+            for (int t = 0; t < SW_NTASK; ++t) {
+                u += pu[(size_t)t * 2 * nlev * ncp];
+                d += pu[((size_t)t * 2 + 1) * nlev * ncp];
+            }
         }
         s_up[lev * 32 + lane] = u;
         s_dn[lev * 32 + lane] = d;
