@@ -49,6 +49,7 @@ struct State {
     long launches = 0;
     int chunk = 0;
     int host_chunk = 0;
+    int host_slots = 4;       // slots of the host-pointer pipelines (2..MAXSLOT)
     int run_chunk = 0;
     bool capture = false;
     // LW
@@ -891,21 +892,27 @@ double sw_adjflux(double adjes, int dyofyr, double scon)
     return adjflx * solvar;
 }
 
-// Host-pointer ABI: the batch is cut into column chunks that flow through a two-slot pipeline (two streams,
-// two sets of device buffers), so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of
-// chunk i.  A column chunk of a column-major (ncol, rows) array is a 2-D copy with source pitch ncol*8.
+// Host-pointer ABI: the batch is cut into column chunks that flow through a pipeline of `host_slots` slots (one stream and
+// one set of device buffers each), so the H2D copies of the next chunks and the D2H copies of the previous ones overlap the
+// kernels of chunk i.  A slot's copy-in, kernels and copy-out are in stream order, so with two slots the copy-in of chunk
+// i+2 waits for the copy-out of chunk i: a chunk's period is max(kernels, (copy-in + kernels + copy-out) / 2), and the
+// copy-in of a chunk (PCIe) takes about as long as its SW kernels.  With n slots the period is max(copy-in, kernels, copy-out,
+// sum / n); T170L60 end to end (shim-style / all outputs / run_rrtmg, ms per step): 2 slots 29.8 / 39.7 / 28.5, 3 slots 25.0 /
+// 29.5 / 26.4, 4 slots (default) 24.2 / 26.6 / 24.0, against 21.8 ms of kernels (profiles/r02ar_sweep_host_slots.txt).  A column chunk of a column-major (ncol, rows) array is a 2-D copy with source
+// pitch ncol*8.
+constexpr int MAXSLOT = 6;
 struct Pipe {
-    cudaStream_t st[2] = {nullptr, nullptr};
-    DevBuf in[2], out[2], work[2];
+    cudaStream_t st[MAXSLOT] = {};
+    DevBuf in[MAXSLOT], out[MAXSLOT], work[MAXSLOT];
     int ready()
     {
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < MAXSLOT; ++i)
             if (!st[i] && cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess) return -1;
         return 0;
     }
     void release()
     {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < MAXSLOT; ++i) {
             in[i].release(); out[i].release(); work[i].release();
             if (st[i]) { cudaStreamDestroy(st[i]); st[i] = nullptr; }
         }
@@ -915,7 +922,7 @@ Pipe P_lw, P_sw;
 // error exit of a pipelined host call: copies of the other block may still be in flight to or from the caller's buffers
 int drain(Pipe &P, int rc)
 {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MAXSLOT; ++i)
         if (P.st[i]) cudaStreamSynchronize(P.st[i]);
     return rc;
 }
@@ -971,6 +978,12 @@ struct Slot {                 // bump allocator over one slot's device buffer + 
     }
 };
 
+int host_slots(int nblocks)
+{
+    const int n = G.host_slots < 2 ? 2 : (G.host_slots > MAXSLOT ? MAXSLOT : G.host_slots);
+    return nblocks < n ? (nblocks < 1 ? 1 : nblocks) : n;
+}
+
 int host_chunk(int ncol)
 {
     if (G.capture) return ncol;                        // stage dumps need the whole batch in one pass
@@ -1021,7 +1034,7 @@ struct DrvSlot {                     // one stage of the host-pointer pipeline (
     }
 };
 struct DrvState {
-    DrvSlot slot[2];
+    DrvSlot slot[MAXSLOT];
     DevBuf gas, misc;
     size_t gas_n = 0;
     double gas_val[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1370,7 +1383,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
     const size_t out_bytes = (size_t)hc * (6 * V + 2 * L) * 8 + 10 * 256;
     LwWork wsz;
     const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields, cloud);
-    const int nslot = hc < ncol ? 2 : 1;
+    const int nslot = host_slots((ncol + hc - 1) / hc);
     for (int i = 0; i < nslot; ++i)
         if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes))
             return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW pipeline buffers");
@@ -1385,7 +1398,7 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
     int idx = 0;
     for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
         const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
-        const int slot = idx & 1;
+        const int slot = idx % nslot;
         cudaStream_t st = P_lw.st[slot];
         Slot a{(char *)P_lw.in[slot].p, 0, c0, nc, ncol, st, true};
         auto in11 = [&](int k, const double *h, size_t rows) { return shared ? (h ? G.shared.dev[k] + c0 : nullptr) : a.up(h, rows); };
@@ -1466,7 +1479,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
     const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
     SwWork wsz;
     const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields, general);
-    const int nslot = hc < ncol ? 2 : 1;
+    const int nslot = host_slots((ncol + hc - 1) / hc);
     for (int i = 0; i < nslot; ++i)
         if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes))
             return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW pipeline buffers");
@@ -1491,7 +1504,7 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
     int idx = 0;
     for (int c0 = 0; c0 < ncol; c0 += hc, ++idx) {
         const int nc = (ncol - c0 < hc) ? ncol - c0 : hc;
-        const int slot = idx & 1;
+        const int slot = idx % nslot;
         cudaStream_t st = P_sw.st[slot];
         Slot a{(char *)P_sw.in[slot].p, 0, c0, nc, ncol, st, true};
         auto in11 = [&](int k, const double *h, size_t rows) { return share ? a.up_full(h, G.shared.dev[k], rows) : a.up(h, rows); };
@@ -1712,7 +1725,7 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     int rows = (int)((long)target * cfg->lonstep / si);
     if (rows < 1) rows = 1;
     if (rows > sj) rows = sj;
-    const int nslot = rows < sj ? 2 : 1;
+    const int nslot = host_slots((sj + rows - 1) / rows);
     auto pad = [](size_t n) { return (n * 8 + 255) & ~(size_t)255; };
     const size_t npb = (size_t)si * rows;
     const size_t hin = 5 * pad(npb) + 6 * pad(npb * L) + 3 * pad(npb * V);
@@ -1731,7 +1744,7 @@ int rrtmg_b200_run_rrtmg(const rrtmg_b200_rad_config *cfg, int si, int sj, int s
     int idx = 0;
     for (int j0 = 0; j0 < sj; j0 += rows, ++idx) {
         const int nr = (sj - j0 < rows) ? sj - j0 : rows;
-        DrvSlot &S = D.slot[idx & 1];
+        DrvSlot &S = D.slot[idx % nslot];
         cudaStream_t st = S.st;
         // a block is "columns" [j0*si, (j0+nr)*si) of a column-major (si*sj, n) array
         Slot a{(char *)S.host_in.p, 0, j0 * si, nr * si, (int)np_all, st, true};
@@ -1784,6 +1797,7 @@ int rrtmg_b200_set_option(const char *key, long value)
     const std::string k(key ? key : "");
     if (k == "chunk") return rrtmg_b200_set_chunk((int)value);
     if (k == "host_chunk") { G.host_chunk = (int)value; return RRTMG_B200_OK; }
+    if (k == "host_slots" && value >= 2 && value <= MAXSLOT) { G.host_slots = (int)value; return RRTMG_B200_OK; }
     if (k == "run_chunk") { G.run_chunk = (int)value; return RRTMG_B200_OK; }
     if (k == "capture_stages") { G.capture = value != 0; return RRTMG_B200_OK; }
     if (k == "share_inputs") { G.share_inputs = value != 0; G.shared.valid = false; return RRTMG_B200_OK; }
