@@ -195,10 +195,11 @@ def test_share_inputs_option(gpu):
     plain_other = gpu.lw_from_columns(other)
     try:
         gpu.set_option("share_inputs", 1)
-        for hc in (0, 64):
+        for hc, slots in ((0, 4), (64, 4), (64, 2), (64, 3), (32, 6)):
             gpu.set_option("host_chunk", hc)
+            gpu.set_option("host_slots", slots)                                    # pipeline depth of the host-pointer calls
             got = gpu.sw_from_columns(cols) + gpu.lw_from_columns(cols)            # LW reuses the SW uploads
-            assert all(np.array_equal(a, b) for a, b in zip(got, plain)), hc
+            assert all(np.array_equal(a, b) for a, b in zip(got, plain)), (hc, slots)
             again = gpu.lw_from_columns(cols)                                      # one shot: this one uploads itself
             assert all(np.array_equal(a, b) for a, b in zip(again, plain[6:]))
             gpu.sw_from_columns(cols)
@@ -207,6 +208,7 @@ def test_share_inputs_option(gpu):
     finally:
         gpu.set_option("share_inputs", 0)
         gpu.set_option("host_chunk", 0)
+        gpu.set_option("host_slots", 4)
 
 
 def test_reference_golden_vectors(gpu):
