@@ -910,6 +910,13 @@ struct Pipe {
             if (!st[i] && cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess) return -1;
         return 0;
     }
+    // slot i could not be allocated: give its partial buffers back, clear the allocation error, keep slots 0..i-1
+    int shrink(int i)
+    {
+        in[i].release(); out[i].release(); work[i].release();
+        (void)cudaGetLastError();
+        return i;
+    }
     void release()
     {
         for (int i = 0; i < MAXSLOT; ++i) {
@@ -1383,10 +1390,12 @@ int rrtmg_b200_lw(int ncol, int nlay, int *icld, int idrv,
     const size_t out_bytes = (size_t)hc * (6 * V + 2 * L) * 8 + 10 * 256;
     LwWork wsz;
     const size_t work_bytes = lw_carve(wsz, nullptr, hc, nlay, fields, cloud);
-    const int nslot = host_slots((ncol + hc - 1) / hc);
+    int nslot = host_slots((ncol + hc - 1) / hc);
     for (int i = 0; i < nslot; ++i)
-        if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes))
-            return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW pipeline buffers");
+        if (P_lw.in[i].ensure(in_bytes) || P_lw.out[i].ensure(out_bytes) || P_lw.work[i].ensure(work_bytes)) {
+            if (i < 2) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the LW pipeline buffers");
+            nslot = P_lw.shrink(i);                     // no room for a deeper pipeline: run with the slots that fit
+        }
     // inputs left on the device by the rrtmg_b200_sw call just before (option share_inputs)?
     const double *hp[11] = {play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr};
     bool shared = G.share_inputs && G.shared.valid && G.shared.ncol == ncol && G.shared.nlay == nlay;
@@ -1479,10 +1488,12 @@ int rrtmg_b200_sw(int ncol, int nlay, int *icld, int *iaer,
     const size_t out_bytes = (size_t)hc * (4 * V + 2 * L) * 8 + 8 * 256;
     SwWork wsz;
     const size_t work_bytes = sw_carve(wsz, nullptr, hc, nlay, fields, general);
-    const int nslot = host_slots((ncol + hc - 1) / hc);
+    int nslot = host_slots((ncol + hc - 1) / hc);
     for (int i = 0; i < nslot; ++i)
-        if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes))
-            return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW pipeline buffers");
+        if (P_sw.in[i].ensure(in_bytes) || P_sw.out[i].ensure(out_bytes) || P_sw.work[i].ensure(work_bytes)) {
+            if (i < 2) return fail(RRTMG_B200_ERR_CUDA, "cudaMalloc failed for the SW pipeline buffers");
+            nslot = P_sw.shrink(i);                     // no room for a deeper pipeline: run with the slots that fit
+        }
     const double adjflux = sw_adjflux(adjes, dyofyr, scon);
     // option share_inputs: the eleven arrays rrtmg_lw reads too are uploaded into full-batch device arrays and kept
     const bool share = G.share_inputs && !general && !fields;
