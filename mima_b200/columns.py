@@ -218,6 +218,37 @@ def make_columns(resolution: str = "T42L40", *, seed: int = 20240917, co2_ppmv: 
     )
 
 
+def wild_columns(seed: int, nlay: int = 40, nlon: int = 64, nlat: int = 8) -> Columns:
+    """Columns far outside the bench generator's climate, for branch coverage in the parity tests: surface pressures from
+    300 to 1080 hPa, temperature profiles shifted by up to +-35 K, humidity over four orders of magnitude, ozone x 0..5,
+    CO2 x 0.2..30, every secondary gas and CFC x 0..5, emissivities 0.6..1, albedo 0..1, a fifth of the columns at night,
+    earth-sun distance, day of year and solar constant varied."""
+    rng = np.random.default_rng(seed)
+    c = make_columns("T42L40", nlon=nlon, nlat=nlat, nlay=nlay, secondary_gases=True, seed=seed)
+    n, L = c.ncol, c.nlay
+    f = rng.uniform(0.3, 1.08, n)
+    c.play = np.asfortranarray(c.play * f[:, None])
+    c.plev = np.asfortranarray(c.plev * f[:, None])
+    dT = rng.uniform(-35, 35, n)[:, None] + rng.normal(0, 4, (n, L))
+    c.tlay = np.asfortranarray(np.clip(c.tlay + dT, 100, 370))
+    c.tlev = np.asfortranarray(np.clip(c.tlev + np.concatenate([dT, dT[:, -1:]], 1), 100, 370))
+    c.tsfc = np.clip(c.tsfc + dT[:, 0], 100, 370)
+    c.h2o = np.asfortranarray(np.clip(c.h2o * np.exp(rng.normal(0, 2.0, (n, L))), 2e-7, 0.06))
+    c.o3 = np.asfortranarray(c.o3 * rng.uniform(0, 5, (n, L)))
+    c.co2 = np.asfortranarray(c.co2 * np.exp(rng.uniform(np.log(0.2), np.log(30), (n, 1))) * np.ones((1, L)))
+    for k, nom in (("ch4", 1.8e-6), ("n2o", 3.2e-7), ("o2", 0.209), ("cfc11", 2.5e-10), ("cfc12", 5.3e-10),
+                   ("cfc22", 2e-10), ("ccl4", 9e-11)):
+        setattr(c, k, np.asfortranarray(nom * rng.uniform(0, 5, (n, L))))
+    c.o2 = np.asfortranarray(np.clip(c.o2, 0, 0.5))
+    c.emis = np.asfortranarray(rng.uniform(0.6, 1.0, (n, 16)))
+    c.albedo = rng.uniform(0, 1, n)
+    c.coszen = np.where(rng.random(n) < 0.2, 0.0, rng.uniform(0, 1, n))
+    c.adjes = float(rng.uniform(0.9, 1.1))
+    c.dyofyr = int(rng.integers(0, 366))
+    c.scon = float(rng.uniform(1300, 1400))
+    return c
+
+
 def make_gcm_state(resolution: str = "T42L40", **kw) -> dict:
     """The same synthetic atmosphere as make_columns(), in the layout MiMA's run_rrtmg receives
     (see gcm_state_from_columns)."""

@@ -21,6 +21,16 @@ def test_layer_counts(gpu, oracle, nlay):
     _check_outputs(gpu.lw_from_columns(c, idrv=1), ref, LW_OUT + ("duflx_dt", "duflxc_dt"), hr_tight=1e-6)
 
 
+@pytest.mark.parametrize("seed,nlay", [(1, 40), (2, 60)])
+def test_wild_columns(gpu, oracle, seed, nlay):
+    """Columns far outside the bench climate (mima_b200.columns.wild_columns: every gas and CFC present and varied over orders
+    of magnitude, mountains and deep lows, +-35 K, grey surfaces, earth-sun adjustment) at the north-star tolerances."""
+    from mima_b200.columns import wild_columns
+    c = wild_columns(seed, nlay, nlon=64, nlat=4)
+    _check_outputs(gpu.lw_from_columns(c), oracle.rrtmg_lw(c), LW_OUT, tight=False)
+    _check_outputs(gpu.sw_from_columns(c), oracle.rrtmg_sw(c), SW_OUT, tight=False)
+
+
 @pytest.mark.parametrize("ncol", [1, 2, 31, 32, 33, 63, 65, 255, 257])
 def test_column_counts(gpu, oracle, ncol):
     base = make_columns("T170L60", nlon=257, nlat=1, night=True, seed=7)

@@ -155,6 +155,16 @@ def test_clear_sky(ref, oracle, kw):
     _same(oracle.rrtmg_lw(cols), ref.rrtmg_lw(cols), LW, "lw")
 
 
+@pytest.mark.parametrize("seed,nlay", [(1, 40), (2, 60), (3, 25), (4, 80)])
+def test_wild_columns(ref, oracle, seed, nlay):
+    """Columns far outside the bench climate (mima_b200.columns.wild_columns): every gas and CFC present and varied over
+    orders of magnitude, mountains and deep lows, +-35 K, grey surfaces, earth-sun adjustment."""
+    from mima_b200.columns import wild_columns
+    cols = wild_columns(seed, nlay)
+    _same(oracle.rrtmg_sw(cols), ref.rrtmg_sw(cols), SW, "sw")
+    _same(oracle.rrtmg_lw(cols, idrv=1), ref.rrtmg_lw(cols, idrv=1), LW + ("duflx_dt", "duflxc_dt"), "lw")
+
+
 def test_idrv_emissivity_aerosol(ref, oracle):
     cols = make_columns("T42L40", nlon=32, nlat=4)
     rng = np.random.default_rng(7)
