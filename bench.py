@@ -82,7 +82,8 @@ def b_alg(L: int) -> int:
 
 def profiled(workload: str):
     """The committed ncu capture of this workload (profiles/traffic.json) if it was taken on the CUDA sources in the tree
-    (stamp = sha256 of mima_b200/csrc, written by tools/make_traffic.py), else None and why."""
+    (stamp = sha256 of the kernel translation units and device headers under mima_b200/csrc, mima_b200.build.source_hash,
+    written by tools/make_traffic.py), else None and why."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))[workload]

@@ -37,12 +37,12 @@ def nvcc() -> str:
 
 
 def source_hash() -> str:
-    """sha256 over the translation units that hold kernels and over the headers (api.cu is host code only: C ABI, host pipelines,
-    table set-up): profiles/traffic.json is stamped with it (tools/make_traffic.py), and bench.py reports the ncu-measured DRAM
-    traffic only while the stamp matches the tree it runs."""
+    """sha256 over the translation units that hold kernels and the device headers they include (api.cu and the public header it
+    alone includes are host code: C ABI, host pipelines, table set-up): profiles/traffic.json is stamped with it
+    (tools/make_traffic.py), and bench.py reports the ncu-measured DRAM traffic only while the stamp matches the tree it runs."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted([x for x, _ in SOURCES if x != "api.cu"] + HEADERS):
+    for f in sorted([x for x, _ in SOURCES if x != "api.cu"] + [x for x in HEADERS if x.endswith(".cuh")]):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
     return h.hexdigest()
